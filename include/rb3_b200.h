@@ -1,0 +1,116 @@
+/*
+ * rb3_b200.h -- C ABI of the B200-native BWT-merge engine (librb3b200.so).
+ *
+ * Drop-in boundary for the merge path of `ropebwt3 build` (lh3/ropebwt3
+ * v3.10-r281).  Plain pointers and sizes only; every entry point names the
+ * reference interface it replaces (file:line relative to the reference tree).
+ * The dynamic B+-tree rope (mrope_t) is replaced by an opaque, device-resident
+ * static index that is rebuilt by a streaming merge at every batch.
+ *
+ * Conventions: symbols are nt6 codes 0..5 = $ACGTN (io.c:12-21).  All functions
+ * returning int return 0 on success and a negative code on failure; the message
+ * is available from rb3b_last_error().  There is NO CPU fallback: without a
+ * usable CUDA device every call fails with RB3B_ENODEV.
+ *
+ * Threading: like the reference, an index must not be used from two
+ * threads at once; different indices may be.
+ */
+#ifndef RB3_B200_H
+#define RB3_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB3B_ASIZE 6
+
+#define RB3B_OK        0
+#define RB3B_ENODEV   -1   /* no CUDA device / CUDA runtime error */
+#define RB3B_ENOMEM   -2
+#define RB3B_EINVAL   -3   /* bad argument (symbol >= 6, missing sentinel, ...) */
+#define RB3B_EIO      -4
+#define RB3B_EFORMAT  -5
+
+typedef struct rb3b_index_s rb3b_index_t;
+
+/* ---- runtime -------------------------------------------------------------- */
+int         rb3b_init(int device);                 /* select device, create stream + memory pool */
+const char *rb3b_last_error(void);
+const char *rb3b_version(void);
+int         rb3b_set_stream(void *cuda_stream);    /* run on a caller-owned cudaStream_t (NULL = own stream) */
+int         rb3b_sync(void);
+int         rb3b_set_param(const char *key, int64_t value);   /* tuning knobs: "seg_len", "splitter", "rank_lanes" */
+int64_t     rb3b_get_stat(const char *key);        /* counters of the last call: "kernel_launches", "n_segments", "fix_rounds", "unresolved_rows", "n_blocks" ... */
+
+/* ---- index life cycle (replaces mr_init / mr_destroy, mrope.c:15-34) ------- */
+rb3b_index_t *rb3b_index_create(void);
+void          rb3b_index_destroy(rb3b_index_t *idx);
+
+/* ---- building blocks of `build` -------------------------------------------- */
+/* rb3_enc_plain2fmr (fm-index.c:114-137): first batch, BWT in host memory. */
+int rb3b_index_from_plain(rb3b_index_t *idx, int64_t len, const uint8_t *bwt);
+/* same with the BWT already resident in device memory */
+int rb3b_index_from_plain_dev(rb3b_index_t *idx, int64_t len, const uint8_t *d_bwt);
+/* rb3_enc_fmd2fmr (fm-index.c:56-85) / mr_restore (mrope.c:161): load a run list (need not be coalesced). */
+int rb3b_index_from_runs(rb3b_index_t *idx, int64_t n_runs, const uint8_t *sym, const int64_t *len);
+
+/* rb3_fmi_merge_plain (fm-index.c:279-303): merge the partial BWT `bwt` of a new
+ * batch (host memory, caller-owned) into the index in place. */
+int rb3b_merge_plain(rb3b_index_t *idx, int64_t len, const uint8_t *bwt);
+/* same, partial BWT already in device memory (no host<->device copies) */
+int rb3b_merge_plain_dev(rb3b_index_t *idx, int64_t len, const uint8_t *d_bwt);
+
+/* rb3_mg_rank_plain (fm-index.c:202-225): the interleave array only.  rb[i] =
+ * (ka+i)<<6 | B[i]<<3 | bucket(i) exactly as fm-index.c:168; acc[7] = C[] of the batch. */
+int rb3b_mg_rank_plain(const rb3b_index_t *idx, int64_t len, const uint8_t *bwt, int64_t *rb, int64_t acc[RB3B_ASIZE + 1]);
+int rb3b_mg_rank_plain_dev(const rb3b_index_t *idx, int64_t len, const uint8_t *d_bwt, int64_t *d_rb, int64_t acc[RB3B_ASIZE + 1]);
+
+/* rb3_fmi_merge (fm-index.c:251-277) for `ropebwt3 merge`: B is another index. */
+int rb3b_merge_index(rb3b_index_t *idx, const rb3b_index_t *other);
+
+/* ---- queries --------------------------------------------------------------- */
+/* mr_rank1a (mrope.h:70, mrope.c:71-121) / rld_rank1a (rld0.c:416-437), batched:
+ * ok[q*6+c] = |{i<k[q] : B[i]=c}|, sym[q] = B[k[q]] or -1 when k[q] >= n. */
+int rb3b_rank1a(const rb3b_index_t *idx, int64_t nq, const int64_t *k, int64_t *ok, int8_t *sym);
+int rb3b_rank1a_dev(const rb3b_index_t *idx, int64_t nq, const int64_t *d_k, int64_t *d_ok, int8_t *d_sym);
+/* LF-walk flavour used by the merge: out[q] = C[c[q]] + rank(c[q], k[q]) */
+int rb3b_lf_dev(const rb3b_index_t *idx, int64_t nq, const int64_t *d_k, const uint8_t *d_c, int64_t *d_out, int variant);
+
+/* rb3_fmi_get_acc (fm-index.c:544-550): acc[c] = #symbols < c; returns total length */
+int64_t rb3b_get_acc(const rb3b_index_t *idx, int64_t acc[RB3B_ASIZE + 1]);
+int64_t rb3b_index_bytes(const rb3b_index_t *idx);   /* device bytes held by the index */
+
+/* ---- export ---------------------------------------------------------------- */
+/* canonical (coalesced) run list; call with sym==NULL to get the count. mr_itr_next_block loop (fm-index.c:41-51). */
+int64_t rb3b_export_runs(const rb3b_index_t *idx, uint8_t *sym, int64_t *len, int64_t cap);
+/* rb3_enc_fmr2fmd + rld_dump (fm-index.c:31-54, rld0.c:222-243): byte-identical .fmd; fn "-" = stdout */
+int rb3b_dump_fmd(const rb3b_index_t *idx, const char *fn);
+/* mr_dump (mrope.c:152-159): a legal .fmr (loadable by mr_restore and extendable by the CPU code) */
+int rb3b_dump_fmr(const rb3b_index_t *idx, const char *fn, int max_nodes, int block_len);
+/* mr_print_bwt (mrope.c:195-210): plain text + '\n' */
+int rb3b_dump_plain(const rb3b_index_t *idx, const char *fn);
+/* rb3_fmi_restore (fm-index.h:123-133): sniff FMD magic first, then FMR */
+int rb3b_restore(rb3b_index_t *idx, const char *fn);
+/* host-only encoders behind the two dumps (no device needed): run list -> malloc'd file image, returns its size.
+ * rld_enc/rld_enc_finish/rld_rank_index/rld_dump (rld0.c:137-243) and mr_dump/rope_dump_node (mrope.c:152, rope.c:265-287). */
+int64_t rb3b_fmd_image(int64_t n_runs, const uint8_t *sym, const int64_t *len, uint8_t **out);
+int64_t rb3b_fmr_image(int64_t n_runs, const uint8_t *sym, const int64_t *len, int max_nodes, int block_len, uint8_t **out);
+void    rb3b_host_free(void *p);
+
+/* ---- partial BWT of a batch (rb3_build_sais, sais-ss.c:50-56) on the GPU ----- */
+/* text: concatenated 0-terminated nt6 strings (host); bwt_out: host, len bytes (may alias text). */
+int rb3b_build_bwt(int64_t len, const uint8_t *text, uint8_t *bwt_out);
+int rb3b_build_bwt_dev(int64_t len, const uint8_t *d_text, uint8_t *d_bwt_out);
+
+/* ---- device memory helpers for callers without a CUDA runtime of their own -- */
+void *rb3b_dev_alloc(int64_t bytes);
+void  rb3b_dev_free(void *p);
+int   rb3b_h2d(void *dst, const void *src, int64_t bytes);
+int   rb3b_d2h(void *dst, const void *src, int64_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,194 @@
+/*
+ * rb3b_bwt.cu -- partial BWT of one batch on the device, the producer of the
+ * merge path's input.  Same contract as rb3_build_sais (sais-ss.c:10-56): the
+ * text is a concatenation of 0-terminated nt6 strings; suffixes are compared up
+ * to and including their first sentinel, an earlier sentinel being smaller
+ * (libsais GSA order); BWT[i] = T[SA[i]-1], or T[len-1] when SA[i] == 0.
+ *
+ * The algorithm is not the reference's (libsais is induced sorting on the
+ * host): this is prefix doubling on top of a device radix sort.  Round 0 sorts
+ * all suffixes by their first 21 symbols packed 3 bits each (cut after a
+ * sentinel; the stable sort orders equal sentinel-terminated prefixes by
+ * position, which is exactly the sentinel order); every later round doubles
+ * the compared length by sorting the still ambiguous suffixes' (rank[i],
+ * rank[i+h]) pairs.
+ *
+ * Also here: rb3b_merge_index, the BWT-vs-BWT flavour (rb3_fmi_merge,
+ * fm-index.c:251-277), which expands the other index and reuses merge_plain.
+ */
+#include <cub/cub.cuh>
+#include "rb3b_internal.cuh"
+
+#define TPB 256
+#define KMER 21
+
+static inline unsigned nblk(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+__global__ void k_kmer_keys(uint32_t n, const uint8_t *__restrict__ T, uint64_t *__restrict__ key, uint32_t *__restrict__ idx, int *__restrict__ bad)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint64_t k = 0;
+	int ended = 0;
+	for (int j = 0; j < KMER; ++j) {
+		uint32_t p = i + j;
+		int c = (!ended && p < n) ? T[p] : 0;
+		if (c >= RB3B_ASIZE) { *bad = 1; c = 5; }
+		k = k << 3 | (uint64_t)c;
+		if (c == 0) ended = 1;
+	}
+	key[i] = k << 1 | (uint64_t)ended; /* bit 0: the prefix holds a sentinel, i.e. the suffix is fully compared */
+	idx[i] = i;
+}
+
+/* head[j] = 1 when sorted element j starts a new group; a finished suffix is always its own group */
+__global__ void k_group_heads(uint32_t n, const uint64_t *__restrict__ key, int first_round, uint32_t *__restrict__ head)
+{
+	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	bool h = j == 0 || key[j] != key[j - 1] || (first_round && (key[j] & 1));
+	head[j] = h ? j : 0;
+}
+
+/* after the max-scan head[j] is the index of the first element of j's group = the new rank */
+__global__ void k_assign_rank(uint32_t n, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ head, uint32_t *__restrict__ rank, unsigned long long *n_amb)
+{
+	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	rank[idx[j]] = head[j];
+	bool amb = head[j] != j || (j + 1 < n && head[j + 1] == head[j]);
+	unsigned m = __ballot_sync(__activemask(), amb);
+	if (amb && (threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) atomicAdd(n_amb, (unsigned long long)__popc(m));
+}
+
+__global__ void k_pair_keys(uint32_t n, uint32_t h, const uint32_t *__restrict__ rank, uint64_t *__restrict__ key, uint32_t *__restrict__ idx)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint64_t r2 = (uint64_t)i + h < n ? rank[i + h] : 0;
+	key[i] = (uint64_t)rank[i] << 32 | r2;
+	idx[i] = i;
+}
+
+__global__ void k_sa_to_bwt(uint32_t n, const uint8_t *__restrict__ T, const uint32_t *__restrict__ sa, uint8_t *__restrict__ bwt)
+{
+	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	uint32_t p = sa[j];
+	bwt[j] = T[p == 0 ? n - 1 : p - 1];
+}
+
+static int sort_pairs(uint64_t *k_in, uint64_t *k_out, uint32_t *v_in, uint32_t *v_out, uint32_t n, int end_bit)
+{
+	size_t tmp = 0;
+	CK(cub::DeviceRadixSort::SortPairs((void*)0, tmp, k_in, k_out, v_in, v_out, (int64_t)n, 0, end_bit, rb3b_stream));
+	DBuf<uint8_t> t;
+	TRY(t.alloc(tmp));
+	CK(cub::DeviceRadixSort::SortPairs((void*)t.p, tmp, k_in, k_out, v_in, v_out, (int64_t)n, 0, end_bit, rb3b_stream));
+	return RB3B_OK;
+}
+
+static int scan_max_u32(uint32_t *d, uint32_t n)
+{
+	size_t tmp = 0;
+	CK(cub::DeviceScan::InclusiveScan((void*)0, tmp, d, d, cub::Max(), (int64_t)n, rb3b_stream));
+	DBuf<uint8_t> t;
+	TRY(t.alloc(tmp));
+	CK(cub::DeviceScan::InclusiveScan((void*)t.p, tmp, d, d, cub::Max(), (int64_t)n, rb3b_stream));
+	return RB3B_OK;
+}
+
+/* suffix array of the batch (generalised, sentinel order by position) into sa[len] (device, uint32) */
+static int suffix_sort(int64_t len, const uint8_t *d_text, DBuf<uint32_t> &sa)
+{
+	if (len >= (1LL << 32) - 2) return rb3b_fail(RB3B_EINVAL, "batches of 2^32 symbols or more are not supported by the device suffix sorter yet");
+	uint32_t n = (uint32_t)len;
+	uint8_t last = 1;
+	CK(cudaMemcpyAsync(&last, d_text + len - 1, 1, cudaMemcpyDeviceToHost, rb3b_stream));
+	CK(cudaStreamSynchronize(rb3b_stream));
+	if (last != 0) return rb3b_fail(RB3B_EINVAL, "the batch text must end with a sentinel (mrope.c:310 asserts the same)");
+	DBuf<uint64_t> key0, key1;
+	DBuf<uint32_t> idx0, rank, head;
+	DBuf<int> bad;
+	DBuf<unsigned long long> amb;
+	TRY(key0.alloc(n)); TRY(key1.alloc(n)); TRY(idx0.alloc(n)); TRY(sa.alloc(n)); TRY(rank.alloc(n)); TRY(head.alloc(n)); TRY(bad.alloc(1)); TRY(amb.alloc(1));
+	CK(cudaMemsetAsync(bad.p, 0, sizeof(int), rb3b_stream));
+	k_kmer_keys<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, d_text, key0.p, idx0.p, bad.p); CKK();
+	int rounds = 0, launches = 1;
+	for (uint64_t h = KMER;; h <<= 1) {
+		TRY(sort_pairs(key0.p, key1.p, idx0.p, sa.p, n, 64));
+		k_group_heads<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, key1.p, rounds == 0, head.p); CKK();
+		TRY(scan_max_u32(head.p, n));
+		CK(cudaMemsetAsync(amb.p, 0, 8, rb3b_stream));
+		k_assign_rank<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, sa.p, head.p, rank.p, amb.p); CKK();
+		unsigned long long n_amb = 0;
+		int hbad = 0;
+		CK(cudaMemcpyAsync(&n_amb, amb.p, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+		if (rounds == 0) CK(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, rb3b_stream));
+		CK(cudaStreamSynchronize(rb3b_stream));
+		if (hbad) return rb3b_fail(RB3B_EINVAL, "batch text holds a symbol >= %d", RB3B_ASIZE);
+		++rounds; launches += 12;
+		if (n_amb == 0 || h >= n) break;
+		k_pair_keys<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, (uint32_t)h, rank.p, key0.p, idx0.p); CKK();
+	}
+	rb3b_stat_set("sa_rounds", rounds);
+	rb3b_stat_add("kernel_launches", launches);
+	return RB3B_OK;
+}
+
+extern "C" int rb3b_build_bwt_dev(int64_t len, const uint8_t *d_text, uint8_t *d_bwt_out)
+{
+	TRY(rb3b_ensure_init());
+	if (len <= 0) return rb3b_fail(RB3B_EINVAL, "empty batch");
+	DBuf<uint32_t> sa;
+	DBuf<uint8_t> tmp;
+	TRY(suffix_sort(len, d_text, sa));
+	uint8_t *dst = d_bwt_out;
+	if (d_bwt_out == d_text) { TRY(tmp.alloc(len)); dst = tmp.p; } /* in place, like the reference */
+	k_sa_to_bwt<<<nblk(len, TPB), TPB, 0, rb3b_stream>>>((uint32_t)len, d_text, sa.p, dst); CKK();
+	if (dst != d_bwt_out) CK(cudaMemcpyAsync(d_bwt_out, dst, len, cudaMemcpyDeviceToDevice, rb3b_stream));
+	return RB3B_OK;
+}
+
+extern "C" int rb3b_build_bwt(int64_t len, const uint8_t *text, uint8_t *bwt_out)
+{
+	TRY(rb3b_ensure_init());
+	if (len <= 0) return rb3b_fail(RB3B_EINVAL, "empty batch");
+	DBuf<uint8_t> t, b;
+	TRY(t.alloc(len)); TRY(b.alloc(len));
+	CK(cudaMemcpyAsync(t.p, text, len, cudaMemcpyHostToDevice, rb3b_stream));
+	TRY(rb3b_build_bwt_dev(len, t.p, b.p));
+	CK(cudaMemcpyAsync(bwt_out, b.p, len, cudaMemcpyDeviceToHost, rb3b_stream));
+	CK(cudaStreamSynchronize(rb3b_stream));
+	return RB3B_OK;
+}
+
+/* ---- BWT-vs-BWT merge ---- */
+
+__global__ void k_runs_to_plain(int64_t n_runs, int64_t n, const uint8_t *__restrict__ sym, const int64_t *__restrict__ start, uint8_t *__restrict__ out)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	int64_t lo = 0, hi = n_runs; /* last run with start <= i */
+	while (hi - lo > 1) {
+		int64_t mid = (lo + hi) >> 1;
+		if (start[mid] <= i) lo = mid; else hi = mid;
+	}
+	out[i] = sym[lo];
+}
+
+extern "C" int rb3b_merge_index(rb3b_index_t *x, const rb3b_index_t *other)
+{
+	TRY(rb3b_ensure_init());
+	if (other->n == 0) return RB3B_OK;
+	DBuf<uint8_t> sym, plain;
+	DBuf<int64_t> len, start;
+	int64_t n_runs;
+	TRY(rb3b_export_runs_dev(other, sym, len, &n_runs));
+	TRY(start.alloc(n_runs)); TRY(plain.alloc(other->n));
+	TRY(rb3b_scan_excl_i64(len.p, start.p, n_runs));
+	k_runs_to_plain<<<nblk(other->n, TPB), TPB, 0, rb3b_stream>>>(n_runs, other->n, sym.p, start.p, plain.p); CKK();
+	TRY(rb3b_merge_plain_dev(x, other->n, plain.p));
+	CK(cudaStreamSynchronize(rb3b_stream));
+	return RB3B_OK;
+}

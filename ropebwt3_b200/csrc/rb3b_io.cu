@@ -1,0 +1,433 @@
+/*
+ * rb3b_io.cu -- host-side readers/writers of the on-disk formats that the merge
+ * path's callers exchange: .fmd (rld0.c:107-243), .fmr
+ * (mrope.c:152-177, rope.c:265-330, rle.h:39-75) and the plain-text dump
+ * (mrope.c:195-210).  The .fmd written here is byte-identical to the
+ * reference's for the same run sequence; the .fmr is a legal tree the reference
+ * can load and keep inserting into (its bytes depend on batching even in the
+ * reference, README.md:170-171).
+ *
+ * Everything works on the canonical run list exported from the device index.
+ */
+#include <string.h>
+#include <stdlib.h>
+#include <string>
+#include <vector>
+#include "rb3b_internal.cuh"
+
+typedef std::vector<uint8_t> bytes_t;
+
+static inline int ilog2_u64(uint64_t v) { return v ? 63 - __builtin_clzll(v) : -1; }
+
+/* ------------------------------------------------------------------ */
+/* FMD writer                                                           */
+/* ------------------------------------------------------------------ */
+
+namespace {
+
+const int FMD_SSIZE = 8;                    /* words per small block (sbits = 3, fm-index.c:18) */
+const int64_t FMD_LSIZE = 1LL << 23;        /* words per chunk (rld0.h:11-13) */
+const int FMD_HDR_WORDS[3] = { 2, 4, 7 };   /* rld0.c:71-73 */
+
+class FmdWriter {
+public:
+	FmdWriter() : head_(0), cur_(2), free_(64), pend_sym_(-1), pend_len_(0)
+	{
+		words_.assign(2 * FMD_SSIZE, 0);
+		tail_ = tail_of(0);
+		memset(run_, 0, sizeof(run_)); memset(mark_, 0, sizeof(mark_));
+	}
+	/* rld_enc (rld0.c:153-161): neighbours with the same symbol are fused before coding */
+	void put(int sym, int64_t len)
+	{
+		if (len <= 0) return;
+		if (sym == pend_sym_) { pend_len_ += len; return; }
+		if (pend_len_) code(pend_len_, pend_sym_);
+		pend_sym_ = sym; pend_len_ = len;
+	}
+	/* rld_enc_finish + rld_rank_index + rld_dump (rld0.c:163-243) */
+	void finish(bytes_t &out)
+	{
+		if (pend_len_) code(pend_len_, pend_sym_);
+		pend_len_ = 0;
+		open_block(); /* trailing header-only block carries the last data block's counts */
+		const uint64_t n_words = (uint64_t)cur_, n_bytes = n_words * 8, total = mark_[0];
+		std::vector<uint64_t> frames;
+		uint64_t n_frames = build_frames(n_words, total, frames);
+		out.clear();
+		out.reserve(80 + n_bytes + frames.size() * 8);
+		const char magic[4] = { 'R', 'L', 'D', 3 };
+		append(out, magic, 4);
+		uint32_t geom = RB3B_ASIZE << 16 | 3;
+		append(out, &geom, 4);
+		uint64_t zero = 0;
+		append(out, &zero, 8); append(out, &n_bytes, 8); append(out, &n_frames, 8);
+		append(out, mark_ + 1, RB3B_ASIZE * 8);
+		append(out, words_.data(), n_bytes);
+		append(out, frames.data(), frames.size() * 8);
+	}
+private:
+	std::vector<uint64_t> words_;
+	int64_t head_, cur_, tail_;  /* first word of the open block, word being filled, last usable word */
+	int free_;                   /* unused low bits of words_[cur_] */
+	uint64_t run_[RB3B_ASIZE + 1], mark_[RB3B_ASIZE + 1]; /* totals now / at the start of the open block; [0] = all */
+	int pend_sym_; int64_t pend_len_;
+
+	static void append(bytes_t &o, const void *p, size_t n) { const uint8_t *q = (const uint8_t*)p; o.insert(o.end(), q, q + n); }
+	static int64_t tail_of(int64_t head)
+	{ /* the last block of a 2^23-word chunk gives up one more word (rld0.h:81) */
+		return head + FMD_SSIZE - (((head + FMD_SSIZE) & (FMD_LSIZE - 1)) == 0 ? 2 : 1);
+	}
+	void open_block()
+	{ /* enc_next_block, rld0.c:107-135 */
+		uint64_t delta[RB3B_ASIZE + 1];
+		head_ += FMD_SSIZE;
+		if ((size_t)(head_ + 2 * FMD_SSIZE) > words_.size()) words_.resize(words_.size() * 2 > (size_t)(head_ + 2 * FMD_SSIZE) ? words_.size() * 2 : head_ + 2 * FMD_SSIZE, 0);
+		for (int i = 0; i <= RB3B_ASIZE; ++i) delta[i] = run_[i] - mark_[i];
+		int type = delta[0] < 0x4000 ? 0 : delta[0] < 0x40000000 ? 1 : 2;
+		uint8_t *dst = (uint8_t*)&words_[head_];
+		for (int i = 0; i <= RB3B_ASIZE; ++i) {
+			if (type == 0) { uint16_t v = (uint16_t)delta[i]; memcpy(dst + 2 * i, &v, 2); }
+			else if (type == 1) { uint32_t v = (uint32_t)delta[i]; memcpy(dst + 4 * i, &v, 4); }
+			else memcpy(dst + 8 * i, &delta[i], 8);
+		}
+		words_[head_] |= (uint64_t)type << 62;
+		cur_ = head_ + FMD_HDR_WORDS[type]; free_ = 64; tail_ = tail_of(head_);
+		memcpy(mark_, run_, sizeof(run_));
+	}
+	void code(int64_t len, int sym)
+	{ /* rld_delta_enc1 + rld_enc1, rld0.c:45-51,137-151 */
+		int y = ilog2_u64((uint64_t)len), z = ilog2_u64((uint64_t)y + 1);
+		int width = 2 * z + 1 + y + 3;
+		uint64_t bits = ((((uint64_t)len ^ (1ULL << y)) | (uint64_t)(y + 1) << y) << 3) | (uint64_t)sym;
+		if (width >= free_ && cur_ == tail_) open_block();
+		if (width > free_) {
+			int spill = width - free_;
+			words_[cur_++] |= bits >> spill;
+			free_ = 64 - spill;
+			words_[cur_] = bits << free_;
+		} else {
+			free_ -= width;
+			words_[cur_] |= bits << free_;
+		}
+		run_[0] += len; run_[sym + 1] += len;
+	}
+	uint64_t build_frames(uint64_t n_words, uint64_t total, std::vector<uint64_t> &fr)
+	{ /* rld_rank_index, rld0.c:163-204 */
+		const int W = RB3B_ASIZE + 1;
+		uint64_t n_blks = n_words / FMD_SSIZE + 1, last = n_words / FMD_SSIZE * FMD_SSIZE;
+		int ibits = ilog2_u64(total / n_blks) + 4;
+		uint64_t n_frames = ((total + (1ULL << ibits) - 1) >> ibits) + 1, k = 1, sofar[RB3B_ASIZE];
+		fr.assign(n_frames * W, 0);
+		memset(sofar, 0, sizeof(sofar));
+		for (uint64_t i = FMD_SSIZE; i <= last; i += FMD_SSIZE) {
+			const uint8_t *src = (const uint8_t*)&words_[i];
+			int type = (int)(words_[i] >> 62);
+			uint64_t sum = 0;
+			for (int j = 1; j <= RB3B_ASIZE; ++j) {
+				if (type == 0) { uint16_t v; memcpy(&v, src + 2 * j, 2); sofar[j - 1] += v; }
+				else if (type == 1) { uint32_t v; memcpy(&v, src + 4 * j, 4); sofar[j - 1] += v & 0x3fffffffu; }
+				else { uint64_t v; memcpy(&v, src + 8 * j, 8); sofar[j - 1] += v; }
+				sum += sofar[j - 1];
+			}
+			while (sum >= k << ibits) ++k;
+			if (k < n_frames) {
+				fr[k * W] = i;
+				memcpy(&fr[k * W + 1], sofar, sizeof(sofar));
+			}
+		}
+		for (k = 1; k < n_frames; ++k)
+			if (fr[k * W] == 0) memcpy(&fr[k * W], &fr[(k - 1) * W], W * 8);
+		return n_frames;
+	}
+};
+
+/* ------------------------------------------------------------------ */
+/* FMD reader (rld0.h:85-125 restated on a flat image)                  */
+/* ------------------------------------------------------------------ */
+
+struct RunList {
+	std::vector<uint8_t> sym; std::vector<int64_t> len;
+	void add(int c, int64_t l)
+	{
+		if (l <= 0) return;
+		if (!sym.empty() && sym.back() == c) len.back() += l;
+		else { sym.push_back((uint8_t)c); len.push_back(l); }
+	}
+};
+
+/* 64 bits of the block's payload starting at bit offset `bit`; zero past the last usable word */
+static uint64_t payload_bits(const uint64_t *w, int64_t first, int64_t tail, int64_t bit)
+{
+	int64_t wi = first + (bit >> 6);
+	int sh = (int)(bit & 63);
+	if (wi > tail) return 0;
+	uint64_t x = w[wi] << sh;
+	if (sh && wi < tail) x |= w[wi + 1] >> (64 - sh);
+	return x;
+}
+
+static int fmd_parse(const bytes_t &img, RunList &runs)
+{
+	if (img.size() < 80 || memcmp(img.data(), "RLD\3", 4) != 0) return RB3B_EFORMAT;
+	uint32_t geom; uint64_t n_bytes, n_frames;
+	memcpy(&geom, &img[4], 4); memcpy(&n_bytes, &img[16], 8); memcpy(&n_frames, &img[24], 8);
+	if (geom != (RB3B_ASIZE << 16 | 3)) return rb3b_fail(RB3B_EFORMAT, "FMD with asize/sbits 0x%x is not supported (only 6/3)", geom);
+	if (img.size() < 80 + n_bytes) return rb3b_fail(RB3B_EFORMAT, "truncated FMD");
+	std::vector<uint64_t> w(n_bytes / 8 + 1, 0);
+	memcpy(w.data(), &img[80], n_bytes);
+	int64_t n_words = n_bytes / 8, last = n_words / FMD_SSIZE * FMD_SSIZE;
+	for (int64_t h = 0; h < last; h += FMD_SSIZE) {
+		int64_t first = h + FMD_HDR_WORDS[w[h] >> 62], tail = h + FMD_SSIZE - (((h + FMD_SSIZE) & (FMD_LSIZE - 1)) == 0 ? 2 : 1), bit = 0;
+		for (;;) {
+			uint64_t x = payload_bits(w.data(), first, tail, bit);
+			if (x >> 58 == 0) break; /* six zero bits cannot start a code */
+			int z = __builtin_clzll(x);
+			int y = (int)(x << z >> (63 - z)) - 1;
+			uint64_t l = (y ? payload_bits(w.data(), first, tail, bit + 2 * z + 1) >> (64 - y) : 0) | 1ULL << y;
+			int c = (int)(payload_bits(w.data(), first, tail, bit + 2 * z + 1 + y) >> 61);
+			if (c >= RB3B_ASIZE) break;
+			runs.add(c, (int64_t)l);
+			bit += 2 * z + 1 + y + 3;
+		}
+	}
+	return RB3B_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/* FMR codec                                                            */
+/* ------------------------------------------------------------------ */
+
+static int rle_put(uint8_t *p, int c, int64_t l)
+{ /* rle.h:53-75 */
+	if (l < 16) { p[0] = (uint8_t)(l << 3 | c); return 1; }
+	if (l < 256) { p[0] = (uint8_t)(0xC0 | (l >> 6) << 3 | c); p[1] = (uint8_t)(0x80 | (l & 0x3f)); return 2; }
+	int n = l < (1LL << 19) ? 4 : 8;
+	p[0] = (uint8_t)((n == 4 ? 0xE0 : 0xF0) | (l >> (6 * (n - 1))) << 3 | c);
+	for (int i = 1; i < n; ++i) p[i] = (uint8_t)(0x80 | ((l >> (6 * (n - 1 - i))) & 0x3f));
+	return n;
+}
+
+static const int64_t RLE_MAX_RUN = (1LL << 43) - 1; /* rle.h:68-73 */
+
+struct Leaf { int64_t cnt[RB3B_ASIZE]; std::vector<uint8_t> code; };
+
+static void fmr_node(bytes_t &o, const std::vector<Leaf> &lv, size_t lo, size_t hi, int height, int fan)
+{ /* pre-order node record, rope.c:265-280 */
+	size_t per = 1;
+	for (int i = 0; i < height; ++i) per *= fan;
+	size_t n_child = (hi - lo + per - 1) / per;
+	uint8_t is_bottom = height == 0;
+	int16_t n = (int16_t)n_child;
+	o.push_back(is_bottom);
+	o.insert(o.end(), (uint8_t*)&n, (uint8_t*)&n + 2);
+	for (size_t i = 0; i < n_child; ++i) {
+		/* spread the leaves evenly over the children */
+		size_t a = lo + (hi - lo) * i / n_child, b = lo + (hi - lo) * (i + 1) / n_child;
+		if (is_bottom) {
+			const Leaf &L = lv[a];
+			uint16_t nb = (uint16_t)L.code.size();
+			o.insert(o.end(), (const uint8_t*)L.cnt, (const uint8_t*)L.cnt + 48);
+			o.insert(o.end(), (uint8_t*)&nb, (uint8_t*)&nb + 2);
+			o.insert(o.end(), L.code.begin(), L.code.end());
+		} else fmr_node(o, lv, a, b, height - 1, fan);
+	}
+}
+
+static void fmr_encode(const uint8_t *sym, const int64_t *len, int64_t n_runs, int max_nodes, int block_len, bytes_t &o)
+{
+	int64_t acc[RB3B_ASIZE + 1] = {0, 0, 0, 0, 0, 0, 0};
+	for (int64_t i = 0; i < n_runs; ++i) acc[sym[i] + 1] += len[i];
+	for (int a = 0; a < RB3B_ASIZE; ++a) acc[a + 1] += acc[a];
+	const uint8_t hdr[4] = { 'R', 'B', 2, 0 }; /* sorting order 0: input order */
+	o.assign(hdr, hdr + 4);
+	const int leaf_cap = block_len - 18 - 16; /* keep clear of the split trigger nbytes + 18 > block_len (rope.c:143) */
+	const int fan = max_nodes > 4 ? max_nodes / 2 : 2; /* half-full nodes: the CPU code splits full ones on the way down */
+	int64_t ri = 0, used = 0, pos = 0;
+	for (int a = 0; a < RB3B_ASIZE; ++a) {
+		std::vector<Leaf> lv;
+		RunList rope; /* rope a = rows [acc[a], acc[a+1]) (mrope.c:157, fm-index.c:72-81) */
+		while (pos < acc[a + 1]) {
+			int64_t t = len[ri] - used;
+			if (t > acc[a + 1] - pos) t = acc[a + 1] - pos;
+			rope.add(sym[ri], t);
+			used += t; pos += t;
+			if (used == len[ri]) ++ri, used = 0;
+		}
+		for (size_t i = 0; i < rope.sym.size(); ++i) {
+			int64_t left = rope.len[i];
+			while (left > 0) {
+				int64_t l = left < RLE_MAX_RUN ? left : RLE_MAX_RUN;
+				uint8_t tmp[8];
+				int nb = rle_put(tmp, rope.sym[i], l);
+				if (lv.empty() || (int)lv.back().code.size() + nb > leaf_cap) { lv.push_back(Leaf()); memset(lv.back().cnt, 0, 48); }
+				lv.back().code.insert(lv.back().code.end(), tmp, tmp + nb);
+				lv.back().cnt[rope.sym[i]] += l;
+				left -= l;
+			}
+		}
+		if (lv.empty()) { lv.push_back(Leaf()); memset(lv.back().cnt, 0, 48); } /* empty rope: one empty leaf (rope.c:64-67) */
+		int32_t mn = max_nodes, bl = block_len;
+		o.insert(o.end(), (uint8_t*)&mn, (uint8_t*)&mn + 4);
+		o.insert(o.end(), (uint8_t*)&bl, (uint8_t*)&bl + 4);
+		int height = 0;
+		for (size_t cap = fan; cap < lv.size(); cap *= fan) ++height;
+		fmr_node(o, lv, 0, lv.size(), height, fan);
+	}
+}
+
+struct FmrCursor { const uint8_t *p, *end; };
+
+static int fmr_read_node(FmrCursor &c, RunList &runs, int depth)
+{ /* rope.c:289-317 */
+	if (c.p + 3 > c.end || depth > 64) return RB3B_EFORMAT;
+	uint8_t is_bottom = c.p[0];
+	int16_t n; memcpy(&n, c.p + 1, 2);
+	c.p += 3;
+	for (int i = 0; i < n; ++i) {
+		if (!is_bottom) { int rc = fmr_read_node(c, runs, depth + 1); if (rc) return rc; continue; }
+		if (c.p + 50 > c.end) return RB3B_EFORMAT;
+		uint16_t nb; memcpy(&nb, c.p + 48, 2);
+		c.p += 50;
+		if (c.p + nb > c.end) return RB3B_EFORMAT;
+		for (const uint8_t *q = c.p, *e = c.p + nb; q < e;) { /* rle_dec1, rle.h:39-51 */
+			int sym = q[0] & 7, n_byte;
+			int64_t l;
+			if ((q[0] & 0x80) == 0) { l = q[0] >> 3; n_byte = 1; }
+			else if (q[0] >> 5 == 6) { l = (int64_t)(q[0] & 0x18) << 3 | (q[1] & 0x3f); n_byte = 2; }
+			else {
+				n_byte = (q[0] & 0x10) ? 8 : 4;
+				l = q[0] >> 3 & 1;
+				for (int j = 1; j < n_byte; ++j) l = l << 6 | (q[j] & 0x3f);
+			}
+			if (sym >= RB3B_ASIZE) return RB3B_EFORMAT;
+			runs.add(sym, l);
+			q += n_byte;
+		}
+		c.p += nb;
+	}
+	return RB3B_OK;
+}
+
+static int fmr_parse(const bytes_t &img, RunList &runs)
+{
+	if (img.size() < 4 || memcmp(img.data(), "RB\2", 3) != 0) return RB3B_EFORMAT;
+	FmrCursor c = { img.data() + 4, img.data() + img.size() };
+	for (int a = 0; a < RB3B_ASIZE; ++a) {
+		if (c.p + 8 > c.end) return rb3b_fail(RB3B_EFORMAT, "truncated FMR");
+		c.p += 8; /* max_nodes, block_len */
+		if (fmr_read_node(c, runs, 0) != RB3B_OK) return rb3b_fail(RB3B_EFORMAT, "corrupt FMR node record");
+	}
+	return RB3B_OK;
+}
+
+/* ------------------------------------------------------------------ */
+
+static int read_file(const char *fn, bytes_t &out)
+{
+	FILE *fp = strcmp(fn, "-") ? fopen(fn, "rb") : stdin;
+	if (!fp) return rb3b_fail(RB3B_EIO, "failed to open '%s' for reading", fn);
+	uint8_t buf[1 << 16];
+	size_t n;
+	out.clear();
+	while ((n = fread(buf, 1, sizeof(buf), fp)) > 0) out.insert(out.end(), buf, buf + n);
+	if (fp != stdin) fclose(fp);
+	return RB3B_OK;
+}
+
+static int write_file(const char *fn, const void *p, size_t n)
+{
+	FILE *fp = strcmp(fn, "-") ? fopen(fn, "wb") : stdout;
+	if (!fp) return rb3b_fail(RB3B_EIO, "failed to open '%s' for writing", fn);
+	size_t w = fwrite(p, 1, n, fp);
+	if (fp != stdout) fclose(fp); else fflush(fp);
+	return w == n ? RB3B_OK : rb3b_fail(RB3B_EIO, "short write to '%s'", fn);
+}
+
+static int fetch_runs(const rb3b_index_t *x, std::vector<uint8_t> &sym, std::vector<int64_t> &len)
+{
+	int64_t n = rb3b_export_runs(x, 0, 0, 0);
+	if (n < 0) return (int)n;
+	sym.resize(n); len.resize(n);
+	if (n == 0) return RB3B_OK;
+	int64_t m = rb3b_export_runs(x, sym.data(), len.data(), n);
+	return m < 0 ? (int)m : RB3B_OK;
+}
+
+} /* namespace */
+
+/* in-memory variants used by the tests and the CLI */
+extern "C" int64_t rb3b_fmd_image(int64_t n_runs, const uint8_t *sym, const int64_t *len, uint8_t **out)
+{
+	FmdWriter w;
+	bytes_t img;
+	for (int64_t i = 0; i < n_runs; ++i) w.put(sym[i], len[i]);
+	w.finish(img);
+	*out = (uint8_t*)malloc(img.size() ? img.size() : 1);
+	memcpy(*out, img.data(), img.size());
+	return (int64_t)img.size();
+}
+
+extern "C" int64_t rb3b_fmr_image(int64_t n_runs, const uint8_t *sym, const int64_t *len, int max_nodes, int block_len, uint8_t **out)
+{
+	bytes_t img;
+	fmr_encode(sym, len, n_runs, max_nodes > 0 ? max_nodes : 64, block_len > 0 ? block_len : 512, img);
+	*out = (uint8_t*)malloc(img.size());
+	memcpy(*out, img.data(), img.size());
+	return (int64_t)img.size();
+}
+
+extern "C" void rb3b_host_free(void *p) { free(p); }
+
+extern "C" int rb3b_dump_fmd(const rb3b_index_t *x, const char *fn)
+{
+	std::vector<uint8_t> sym; std::vector<int64_t> len;
+	TRY(fetch_runs(x, sym, len));
+	FmdWriter w;
+	bytes_t img;
+	for (size_t i = 0; i < sym.size(); ++i) w.put(sym[i], len[i]);
+	w.finish(img);
+	return write_file(fn, img.data(), img.size());
+}
+
+extern "C" int rb3b_dump_fmr(const rb3b_index_t *x, const char *fn, int max_nodes, int block_len)
+{
+	std::vector<uint8_t> sym; std::vector<int64_t> len;
+	TRY(fetch_runs(x, sym, len));
+	if (max_nodes <= 0) max_nodes = 64;
+	if (block_len <= 0) block_len = 512;
+	if (block_len < 64 || (block_len & 7)) return rb3b_fail(RB3B_EINVAL, "block_len must be a multiple of 8 and >= 64 (rope.c:59-61)");
+	bytes_t img;
+	fmr_encode(sym.data(), len.data(), (int64_t)sym.size(), max_nodes, block_len, img);
+	return write_file(fn, img.data(), img.size());
+}
+
+extern "C" int rb3b_dump_plain(const rb3b_index_t *x, const char *fn)
+{ /* mr_print_bwt, mrope.c:195-210 */
+	std::vector<uint8_t> sym; std::vector<int64_t> len;
+	TRY(fetch_runs(x, sym, len));
+	FILE *fp = strcmp(fn, "-") ? fopen(fn, "wb") : stdout;
+	if (!fp) return rb3b_fail(RB3B_EIO, "failed to open '%s' for writing", fn);
+	std::string buf;
+	for (size_t i = 0; i < sym.size(); ++i) {
+		buf.assign((size_t)(len[i] < (1 << 20) ? len[i] : (1 << 20)), "$ACGTN"[sym[i]]);
+		for (int64_t left = len[i]; left > 0; left -= (int64_t)buf.size())
+			fwrite(buf.data(), 1, (size_t)(left < (int64_t)buf.size() ? left : (int64_t)buf.size()), fp);
+	}
+	fputc('\n', fp);
+	if (fp != stdout) fclose(fp); else fflush(fp);
+	return RB3B_OK;
+}
+
+extern "C" int rb3b_restore(rb3b_index_t *x, const char *fn)
+{ /* rb3_fmi_restore (fm-index.h:123-133): FMD magic first, then FMR */
+	bytes_t img;
+	RunList runs;
+	TRY(read_file(fn, img));
+	int rc;
+	if (img.size() >= 4 && memcmp(img.data(), "RLD\3", 4) == 0) rc = fmd_parse(img, runs);
+	else if (img.size() >= 4 && memcmp(img.data(), "RB\2", 3) == 0) rc = fmr_parse(img, runs);
+	else return rb3b_fail(RB3B_EFORMAT, "'%s' is neither FMD nor FMR", fn);
+	if (rc != RB3B_OK) return rc;
+	return rb3b_index_from_runs(x, (int64_t)runs.sym.size(), runs.sym.data(), runs.len.data());
+}

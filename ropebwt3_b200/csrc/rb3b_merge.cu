@@ -1,0 +1,460 @@
+/*
+ * rb3b_merge.cu -- the merge hot path on the device.
+ *
+ * Replaces rb3_fmi_merge_plain (fm-index.c:279-303):
+ *   phase A  rb3_mg_rank_plain + rb3_mg_rank1_plain (fm-index.c:160-225): for
+ *            every row i of the batch BWT B, ka[i] = #suffixes of the indexed
+ *            collection A that are smaller than suffix i of B.
+ *   phase B  worker_mgins (fm-index.c:237-249) / rope_insert_run (rope.c:114) /
+ *            rle_insert_cached (rle.c:10): interleave B into A.
+ *
+ * The reference walks one dependent LF chain per new sequence.  Here every chain
+ * is cut into segments at "marked" rows of B.  A segment that does not start at a
+ * sentinel does not know its ka yet, so it starts with the bracket [lo,hi] = SA
+ * interval (in A) of the empty string restricted to its first symbol and narrows
+ * it by backward search with the symbols it walks over; once lo == hi the value
+ * is exact (the walked string no longer occurs in A) and independent of anything
+ * to its right.  Rows walked before the collapse stay unresolved and are filled
+ * in a later round by re-walking them from the exact value with which the
+ * segment to the right arrived at the mark.  Rounds repeat until nothing is
+ * unresolved (a batch sequence that is an exact substring of A degenerates to
+ * the sequential chain, still correct).
+ *
+ * Phase B is a streaming merge: because ka[] is non-decreasing, block b of A
+ * and the rows with bstart[b] <= ka < bstart[b+1] form an independent tile whose
+ * merged runs are counted, prefix-summed and written into a fresh block array.
+ */
+#include <string.h>
+#include <cub/cub.cuh>
+#include "rb3b_internal.cuh"
+
+#define TPB 256
+#define PREP_PER_THREAD 16
+#define PREP_TILE (TPB * PREP_PER_THREAD)
+
+static inline unsigned nblk(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+static int n_sm(void)
+{
+	static int n = 0;
+	if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+	return n;
+}
+
+/* ------------------------------------------------------------------ */
+/* LF mapping of the batch (fm-index.c:207-216)                         */
+/* lfb[i] = LF_B(i) << 4 | mark << 3 | B[i]                             */
+/* ------------------------------------------------------------------ */
+
+__global__ void __launch_bounds__(TPB) k_prep_count(int64_t len, const uint8_t *__restrict__ bwt, int64_t nt, int64_t *__restrict__ tcnt, int *__restrict__ bad)
+{
+	__shared__ unsigned int sh[RB3B_ASIZE];
+	if (threadIdx.x < RB3B_ASIZE) sh[threadIdx.x] = 0;
+	__syncthreads();
+	int64_t i0 = (int64_t)blockIdx.x * PREP_TILE + (int64_t)threadIdx.x * PREP_PER_THREAD;
+	unsigned int c[RB3B_ASIZE] = {0, 0, 0, 0, 0, 0};
+	for (int j = 0; j < PREP_PER_THREAD; ++j) {
+		int64_t i = i0 + j;
+		if (i < len) {
+			int a = bwt[i];
+			if (a >= RB3B_ASIZE) { *bad = 1; a = 5; }
+#pragma unroll
+			for (int b = 0; b < RB3B_ASIZE; ++b) c[b] += a == b;
+		}
+	}
+#pragma unroll
+	for (int b = 0; b < RB3B_ASIZE; ++b) {
+		unsigned int v = c[b];
+		for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+		if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sh[b], v);
+	}
+	__syncthreads();
+	if (threadIdx.x < RB3B_ASIZE) tcnt[(int64_t)threadIdx.x * (nt + 1) + blockIdx.x] = sh[threadIdx.x];
+	if (blockIdx.x == 0 && threadIdx.x < RB3B_ASIZE) tcnt[(int64_t)threadIdx.x * (nt + 1) + nt] = 0;
+}
+
+struct Acc7 { int64_t v[RB3B_ASIZE + 1]; };
+
+__global__ void __launch_bounds__(TPB) k_prep_lf(int64_t len, const uint8_t *__restrict__ bwt, int64_t nt, const int64_t *__restrict__ tex,
+                                                  Acc7 accB, int64_t seg_len, uint64_t *__restrict__ lfb)
+{
+	typedef cub::BlockScan<uint32_t, TPB> Scan;
+	__shared__ typename Scan::TempStorage tmp[3];
+	int64_t i0 = (int64_t)blockIdx.x * PREP_TILE + (int64_t)threadIdx.x * PREP_PER_THREAD;
+	uint8_t s[PREP_PER_THREAD];
+	uint32_t p[3] = {0, 0, 0}, ex[3]; /* p[w] holds counts of symbols 2w (low half) and 2w+1 (high half) */
+	for (int j = 0; j < PREP_PER_THREAD; ++j) {
+		int64_t i = i0 + j;
+		s[j] = i < len ? bwt[i] : 7;
+		if (s[j] < RB3B_ASIZE) p[s[j] >> 1] += 1u << (16 * (s[j] & 1));
+	}
+	Scan(tmp[0]).ExclusiveSum(p[0], ex[0]);
+	Scan(tmp[1]).ExclusiveSum(p[1], ex[1]);
+	Scan(tmp[2]).ExclusiveSum(p[2], ex[2]);
+	int64_t base[RB3B_ASIZE];
+#pragma unroll
+	for (int a = 0; a < RB3B_ASIZE; ++a)
+		base[a] = accB.v[a] + (tex[(int64_t)a * (nt + 1) + blockIdx.x] - tex[(int64_t)a * (nt + 1)]) + ((ex[a >> 1] >> (16 * (a & 1))) & 0xffffu);
+	for (int j = 0; j < PREP_PER_THREAD; ++j) {
+		int64_t i = i0 + j;
+		if (i >= len) break;
+		int a = s[j];
+		int64_t lf = 0;
+#pragma unroll
+		for (int b = 0; b < RB3B_ASIZE; ++b) if (a == b) lf = base[b]++;
+		uint64_t mark = (i < accB.v[1] || i % seg_len == 0) ? 8u : 0u;
+		lfb[i] = (uint64_t)lf << 4 | mark | (uint64_t)a;
+	}
+}
+
+/* ------------------------------------------------------------------ */
+/* segmented LF walk                                                    */
+/* ------------------------------------------------------------------ */
+
+struct Segs {
+	int64_t n_seg, n_seq, seg_len, m0;  /* sampled segment j (>= n_seq) starts at row (m0 + j - n_seq) * seg_len */
+	int64_t *d;       /* #rows at the start of the segment that are still unresolved */
+	int64_t *len;     /* #rows of the segment */
+	int64_t *succ;    /* segment entered after the last row, or -1 at the start of a sequence */
+	int64_t *arr_lo, *arr_hi; /* bracket with which the walk arrived at succ's first row */
+};
+
+__device__ __forceinline__ int64_t seg_row(const Segs &S, int64_t s) { return s < S.n_seq ? s : (S.m0 + (s - S.n_seq)) * S.seg_len; }
+__device__ __forceinline__ int64_t seg_of_row(const Segs &S, int64_t r) { return r < S.n_seq ? r : S.n_seq + (r / S.seg_len - S.m0); }
+
+/* round 1: every segment walks from its mark to the next mark */
+__global__ void __launch_bounds__(TPB) k_walk_first(DevIndex A, Acc7 accB, Segs S, const uint64_t *__restrict__ lfb, int64_t *__restrict__ ka, int64_t *next_seg)
+{
+	const int gl = threadIdx.x & 7, gbase = threadIdx.x & 24;
+	const unsigned gmask = rb3b_gmask();
+	for (;;) {
+		int64_t s = 0;
+		if (gl == 0) s = (int64_t)atomicAdd((unsigned long long*)next_seg, 1ULL);
+		s = __shfl_sync(gmask, s, gbase);
+		if (s >= S.n_seg) break;
+		int64_t kb = seg_row(S, s), lo, hi, d = 0, len = 0, succ = -1;
+		if (s < S.n_seq) lo = hi = A.acc[1]; /* new sentinels sort after all old ones, fm-index.c:164 */
+		else {
+			int c0 = 1;
+			while (c0 < RB3B_ASIZE - 1 && kb >= accB.v[c0 + 1]) ++c0;
+			lo = A.acc[c0]; hi = A.acc[c0 + 1];
+		}
+		uint64_t x = __ldg(lfb + kb);
+		for (;;) {
+			int c = (int)(x & 7);
+			if (lo == hi) { if (gl == 0) ka[kb] = lo; }
+			else ++d;
+			++len;
+			if (c == 0) break; /* reached the first symbol of the sequence, fm-index.c:170 */
+			kb = (int64_t)(x >> 4);
+			x = __ldg(lfb + kb); /* the B chain does not depend on A: fetch one step ahead */
+			if (lo == hi) lo = hi = A.acc[c] + rb3b_rank_c(A, lo, c);
+			else {
+				lo = A.acc[c] + rb3b_rank_c(A, lo, c);
+				hi = A.acc[c] + rb3b_rank_c(A, hi, c);
+			}
+			if (x & 8) { succ = seg_of_row(S, kb); break; }
+		}
+		if (gl == 0) { S.d[s] = d; S.len[s] = len; S.succ[s] = succ; S.arr_lo[s] = lo; S.arr_hi[s] = hi; }
+	}
+}
+
+/* after round 1: segments whose predecessor arrived with an exact value and that have unresolved rows */
+__global__ void k_collect_first(Segs S, int64_t *__restrict__ wl_seg, int64_t *__restrict__ wl_val, unsigned long long *wl_n)
+{
+	int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= S.n_seg) return;
+	int64_t t = S.succ[s];
+	if (t >= 0 && S.arr_lo[s] == S.arr_hi[s] && S.d[t] > 0) {
+		unsigned long long o = atomicAdd(wl_n, 1ULL);
+		wl_seg[o] = t; wl_val[o] = S.arr_lo[s];
+	}
+}
+
+/* round >= 2: re-walk the unresolved prefix of each listed segment from its now exact start */
+__global__ void __launch_bounds__(TPB) k_walk_fix(DevIndex A, Segs S, const uint64_t *__restrict__ lfb, int64_t *__restrict__ ka, int64_t n_items,
+                                                   const int64_t *__restrict__ wl_seg, const int64_t *__restrict__ wl_val, int64_t *next_item,
+                                                   int64_t *__restrict__ nx_seg, int64_t *__restrict__ nx_val, unsigned long long *nx_n)
+{
+	const int gl = threadIdx.x & 7, gbase = threadIdx.x & 24;
+	const unsigned gmask = rb3b_gmask();
+	for (;;) {
+		int64_t it = 0;
+		if (gl == 0) it = (int64_t)atomicAdd((unsigned long long*)next_item, 1ULL);
+		it = __shfl_sync(gmask, it, gbase);
+		if (it >= n_items) break;
+		int64_t t = wl_seg[it], v = wl_val[it], kb = seg_row(S, t), d = S.d[t], len = S.len[t];
+		uint64_t x = __ldg(lfb + kb);
+		for (int64_t i = 0; i < d; ++i) {
+			int c = (int)(x & 7);
+			if (gl == 0) ka[kb] = v;
+			if (c == 0) break;
+			kb = (int64_t)(x >> 4);
+			x = __ldg(lfb + kb);
+			v = A.acc[c] + rb3b_rank_c(A, v, c);
+		}
+		if (gl == 0) {
+			S.d[t] = 0;
+			int64_t u = S.succ[t];
+			if (d == len && u >= 0) { /* never collapsed: only now is the arrival value known */
+				S.arr_lo[t] = S.arr_hi[t] = v;
+				if (S.d[u] > 0) { /* u is processed by nobody else in this round: its only predecessor is t */
+					unsigned long long o = atomicAdd(nx_n, 1ULL);
+					nx_seg[o] = u; nx_val[o] = v;
+				}
+			}
+		}
+	}
+}
+
+__global__ void k_seg_check(Segs S, unsigned long long *sums)
+{
+	int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= S.n_seg) return;
+	if (S.d[s]) atomicAdd(&sums[0], (unsigned long long)S.d[s]);
+	atomicAdd(&sums[1], (unsigned long long)S.len[s]);
+}
+
+/* rb[i] = (ka+i)<<6 | B[i]<<3 | first symbol of suffix i (fm-index.c:168) */
+__global__ void k_pack_rb(int64_t len, const uint8_t *__restrict__ bwt, const int64_t *__restrict__ ka, Acc7 accB, int64_t *__restrict__ rb)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= len) return;
+	int c0 = 0;
+	while (c0 < RB3B_ASIZE - 1 && i >= accB.v[c0 + 1]) ++c0;
+	rb[i] = (ka[i] + i) << 6 | (int64_t)bwt[i] << 3 | c0;
+}
+
+__global__ void k_check_monotone(int64_t len, const int64_t *__restrict__ ka, int64_t nA, int *bad)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= len) return;
+	int64_t v = ka[i];
+	if (v < 0 || v > nA || (i > 0 && ka[i - 1] > v)) *bad = 1;
+}
+
+/* interleave positions of the batch in device memory: ka[len], accB */
+static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, DBuf<int64_t> &ka, int64_t accB[RB3B_ASIZE + 1])
+{
+	int64_t nt = (len + PREP_TILE - 1) / PREP_TILE;
+	DBuf<int64_t> tcnt, tex;
+	DBuf<int> bad;
+	DBuf<uint64_t> lfb;
+	int hbad = 0;
+	if (len <= 0) return rb3b_fail(RB3B_EINVAL, "empty batch");
+	if (A->n_blocks == 0) return rb3b_fail(RB3B_EINVAL, "rank phase on an empty index");
+	/* batch LF mapping */
+	TRY(tcnt.alloc((nt + 1) * RB3B_ASIZE)); TRY(tex.alloc((nt + 1) * RB3B_ASIZE)); TRY(bad.alloc(1)); TRY(lfb.alloc(len));
+	CK(cudaMemsetAsync(bad.p, 0, sizeof(int), rb3b_stream));
+	k_prep_count<<<(unsigned)nt, TPB, 0, rb3b_stream>>>(len, d_bwt, nt, tcnt.p, bad.p); CKK();
+	TRY(rb3b_scan_excl_i64(tcnt.p, tex.p, (nt + 1) * RB3B_ASIZE));
+	int64_t tot[RB3B_ASIZE], base[RB3B_ASIZE];
+	for (int a = 0; a < RB3B_ASIZE; ++a) {
+		CK(cudaMemcpyAsync(&tot[a], tex.p + a * (nt + 1) + nt, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+		CK(cudaMemcpyAsync(&base[a], tex.p + a * (nt + 1), 8, cudaMemcpyDeviceToHost, rb3b_stream));
+	}
+	CK(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, rb3b_stream));
+	CK(cudaStreamSynchronize(rb3b_stream));
+	if (hbad) return rb3b_fail(RB3B_EINVAL, "batch BWT holds a symbol >= %d", RB3B_ASIZE);
+	Acc7 acc;
+	acc.v[0] = 0;
+	for (int a = 0; a < RB3B_ASIZE; ++a) acc.v[a + 1] = acc.v[a] + (tot[a] - base[a]);
+	memcpy(accB, acc.v, sizeof(acc.v));
+	if (acc.v[1] <= 0) return rb3b_fail(RB3B_EINVAL, "batch BWT holds no sentinel");
+	int64_t seg_len = rb3b_seg_len;
+	k_prep_lf<<<(unsigned)nt, TPB, 0, rb3b_stream>>>(len, d_bwt, nt, tex.p, acc, seg_len, lfb.p); CKK();
+	/* segments */
+	Segs S;
+	S.n_seq = acc.v[1]; S.seg_len = seg_len;
+	S.m0 = (S.n_seq + seg_len - 1) / seg_len;
+	int64_t n_samp = (len - 1) / seg_len - S.m0 + 1;
+	if (n_samp < 0) n_samp = 0;
+	S.n_seg = S.n_seq + n_samp;
+	DBuf<int64_t> seg, wl, ctr;
+	TRY(seg.alloc(S.n_seg * 5)); TRY(wl.alloc(S.n_seg * 4)); TRY(ctr.alloc(8)); TRY(ka.alloc(len));
+	S.d = seg.p; S.len = seg.p + S.n_seg; S.succ = seg.p + 2 * S.n_seg; S.arr_lo = seg.p + 3 * S.n_seg; S.arr_hi = seg.p + 4 * S.n_seg;
+	CK(cudaMemsetAsync(ctr.p, 0, 8 * 8, rb3b_stream));
+	CK(cudaMemsetAsync(ka.p, 0xff, len * 8, rb3b_stream));
+	DevIndex dA = rb3b_dev_view(A);
+	int64_t groups = S.n_seg, want = (groups * RB3B_GROUP + TPB - 1) / TPB, cap = (int64_t)n_sm() * 8;
+	k_walk_first<<<(unsigned)(want < cap ? want : cap), TPB, 0, rb3b_stream>>>(dA, acc, S, lfb.p, ka.p, ctr.p); CKK();
+	int64_t *wl_seg[2] = { wl.p, wl.p + 2 * S.n_seg }, *wl_val[2] = { wl.p + S.n_seg, wl.p + 3 * S.n_seg };
+	k_collect_first<<<nblk(S.n_seg, TPB), TPB, 0, rb3b_stream>>>(S, wl_seg[0], wl_val[0], (unsigned long long*)(ctr.p + 1)); CKK();
+	int64_t n_items = 0, rounds = 1, launches = 4, fix_rows = 0;
+	CK(cudaMemcpyAsync(&n_items, ctr.p + 1, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+	CK(cudaStreamSynchronize(rb3b_stream));
+	int cur = 0;
+	while (n_items > 0) {
+		/* ctr[2] = item cursor, ctr[3] = size of the next list */
+		CK(cudaMemsetAsync(ctr.p + 2, 0, 16, rb3b_stream));
+		want = (n_items * RB3B_GROUP + TPB - 1) / TPB;
+		k_walk_fix<<<(unsigned)(want < cap ? want : cap), TPB, 0, rb3b_stream>>>(dA, S, lfb.p, ka.p, n_items, wl_seg[cur], wl_val[cur], ctr.p + 2,
+			wl_seg[cur ^ 1], wl_val[cur ^ 1], (unsigned long long*)(ctr.p + 3)); CKK();
+		fix_rows += n_items;
+		CK(cudaMemcpyAsync(&n_items, ctr.p + 3, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+		CK(cudaStreamSynchronize(rb3b_stream));
+		cur ^= 1; ++rounds; ++launches;
+	}
+	unsigned long long sums[2];
+	CK(cudaMemsetAsync(ctr.p + 4, 0, 16, rb3b_stream));
+	k_seg_check<<<nblk(S.n_seg, TPB), TPB, 0, rb3b_stream>>>(S, (unsigned long long*)(ctr.p + 4)); CKK();
+	CK(cudaMemcpyAsync(sums, ctr.p + 4, 16, cudaMemcpyDeviceToHost, rb3b_stream));
+	CK(cudaStreamSynchronize(rb3b_stream));
+	rb3b_stat_set("n_segments", S.n_seg);
+	rb3b_stat_set("fix_rounds", rounds - 1);
+	rb3b_stat_set("fix_segments", fix_rows);
+	rb3b_stat_set("unresolved_rows", (int64_t)sums[0]);
+	rb3b_stat_add("kernel_launches", launches + 1);
+	if (sums[0] != 0 || (int64_t)sums[1] != len)
+		return rb3b_fail(RB3B_EINVAL, "batch is not the BWT of a sentinel-terminated string set (%lld of %lld rows reachable, %lld unresolved)",
+		                 (long long)sums[1], (long long)len, (long long)sums[0]);
+	return RB3B_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/* streaming merge                                                      */
+/* ------------------------------------------------------------------ */
+
+__global__ void k_tile_bounds(int64_t nb, const uint64_t *__restrict__ bstart, int64_t len, const int64_t *__restrict__ ka, int64_t *__restrict__ blo)
+{
+	int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (b > nb) return;
+	if (b == nb) { blo[b] = len; return; }
+	int64_t key = (int64_t)bstart[b], lo = 0, hi = len; /* first i with ka[i] >= key */
+	while (lo < hi) {
+		int64_t mid = (lo + hi) >> 1;
+		if (ka[mid] < key) lo = mid + 1; else hi = mid;
+	}
+	blo[b] = lo;
+}
+
+template<bool WRITE> struct Emit {
+	int sym; int64_t len, e; uint4 *out;
+	__device__ __forceinline__ void flush() {
+		if (len > 0) {
+			if (WRITE) e = rb3b_emit_run(out, e, sym, len);
+			else e += rb3b_nent(len);
+		}
+	}
+	__device__ __forceinline__ void put(int c, int64_t l) {
+		if (c == sym) len += l;
+		else { flush(); sym = c; len = l; }
+	}
+};
+
+/* one thread per tile = block b of A plus the batch rows that fall inside it */
+template<bool WRITE>
+__global__ void __launch_bounds__(128) k_merge(int64_t nb, const uint4 *__restrict__ blocks, const uint64_t *__restrict__ bstart, const int64_t *__restrict__ blo,
+                                               const int64_t *__restrict__ ka, const uint8_t *__restrict__ bwt,
+                                               int64_t *__restrict__ cnt, const int64_t *__restrict__ eoff, uint4 *out)
+{
+	int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= nb) return;
+	Emit<WRITE> E;
+	E.sym = -1; E.len = 0; E.e = WRITE ? eoff[b] : 0; E.out = out;
+	int64_t pos = (int64_t)bstart[b], i = blo[b], iend = blo[b + 1];
+	int64_t nxt = i < iend ? ka[i] : INT64_MAX;
+	for (int q = 2; q < 8; ++q) {
+		uint4 v = blocks[b * 8 + q];
+		const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			uint32_t e = (w[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+			int64_t l = rb3b_ent_len(e);
+			int s = e >> 13;
+			if (l == 0) continue;
+			while (nxt < pos + l) { /* a batch row lands inside (or right before) this run */
+				int64_t t = nxt - pos;
+				if (t > 0) { E.put(s, t); l -= t; pos += t; }
+				E.put(bwt[i], 1);
+				++i;
+				nxt = i < iend ? ka[i] : INT64_MAX;
+			}
+			E.put(s, l); pos += l;
+		}
+	}
+	for (; i < iend; ++i) E.put(bwt[i], 1); /* rows that go after the very last symbol of A */
+	E.flush();
+	if (!WRITE) cnt[b] = E.e;
+}
+
+static int merge_phase(rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, const int64_t *d_ka)
+{
+	int64_t nb = A->n_blocks, last[2];
+	DBuf<int64_t> blo, cnt, eoff;
+	DBuf<int> bad;
+	DBuf<uint4> out;
+	int hbad = 0;
+	TRY(blo.alloc(nb + 1)); TRY(cnt.alloc(nb)); TRY(eoff.alloc(nb)); TRY(bad.alloc(1));
+	CK(cudaMemsetAsync(bad.p, 0, sizeof(int), rb3b_stream));
+	k_check_monotone<<<nblk(len, TPB), TPB, 0, rb3b_stream>>>(len, d_ka, A->n, bad.p); CKK();
+	k_tile_bounds<<<nblk(nb + 1, TPB), TPB, 0, rb3b_stream>>>(nb, A->bstart, len, d_ka, blo.p); CKK();
+	k_merge<false><<<nblk(nb, 128), 128, 0, rb3b_stream>>>(nb, A->blocks, A->bstart, blo.p, d_ka, d_bwt, cnt.p, 0, 0); CKK();
+	TRY(rb3b_scan_excl_i64(cnt.p, eoff.p, nb));
+	CK(cudaMemcpyAsync(&last[0], eoff.p + nb - 1, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+	CK(cudaMemcpyAsync(&last[1], cnt.p + nb - 1, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+	CK(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, rb3b_stream));
+	CK(cudaStreamSynchronize(rb3b_stream));
+	if (hbad) return rb3b_fail(RB3B_EINVAL, "interleave positions are not monotone: the batch is not a valid BWT");
+	int64_t n_ent = last[0] + last[1], nb2 = (n_ent + RB3B_ENT_PER_BLK - 1) / RB3B_ENT_PER_BLK;
+	if (nb2 >= (1LL << 32) - 16) return rb3b_fail(RB3B_EINVAL, "index too large for 32-bit block ids");
+	TRY(out.alloc(nb2 * 8));
+	CK(cudaMemsetAsync(out.p, 0, nb2 * 128, rb3b_stream));
+	k_merge<true><<<nblk(nb, 128), 128, 0, rb3b_stream>>>(nb, A->blocks, A->bstart, blo.p, d_ka, d_bwt, 0, eoff.p, out.p); CKK();
+	cudaFreeAsync(A->blocks, rb3b_stream);
+	A->blocks = out.take();
+	A->n_blocks = nb2; A->n_entries = n_ent;
+	rb3b_stat_add("kernel_launches", 4 + 6);
+	return rb3b_index_finalize(A);
+}
+
+/* ------------------------------------------------------------------ */
+/* C ABI                                                                */
+/* ------------------------------------------------------------------ */
+
+extern "C" int rb3b_mg_rank_plain_dev(const rb3b_index_t *x, int64_t len, const uint8_t *d_bwt, int64_t *d_rb, int64_t acc[RB3B_ASIZE + 1])
+{
+	TRY(rb3b_ensure_init());
+	DBuf<int64_t> ka;
+	Acc7 a;
+	TRY(rank_phase(x, len, d_bwt, ka, a.v));
+	k_pack_rb<<<nblk(len, TPB), TPB, 0, rb3b_stream>>>(len, d_bwt, ka.p, a, d_rb); CKK();
+	if (acc) memcpy(acc, a.v, sizeof(a.v));
+	return RB3B_OK;
+}
+
+extern "C" int rb3b_mg_rank_plain(const rb3b_index_t *x, int64_t len, const uint8_t *bwt, int64_t *rb, int64_t acc[RB3B_ASIZE + 1])
+{
+	TRY(rb3b_ensure_init());
+	DBuf<uint8_t> d; DBuf<int64_t> drb;
+	if (len <= 0) return rb3b_fail(RB3B_EINVAL, "empty batch");
+	TRY(d.alloc(len)); TRY(drb.alloc(len));
+	CK(cudaMemcpyAsync(d.p, bwt, len, cudaMemcpyHostToDevice, rb3b_stream));
+	TRY(rb3b_mg_rank_plain_dev(x, len, d.p, drb.p, acc));
+	CK(cudaMemcpyAsync(rb, drb.p, len * 8, cudaMemcpyDeviceToHost, rb3b_stream));
+	CK(cudaStreamSynchronize(rb3b_stream));
+	return RB3B_OK;
+}
+
+extern "C" int rb3b_merge_plain_dev(rb3b_index_t *x, int64_t len, const uint8_t *d_bwt)
+{
+	TRY(rb3b_ensure_init());
+	if (len <= 0) return RB3B_OK;
+	if (x->n_blocks == 0) return rb3b_index_from_plain_dev(x, len, d_bwt);
+	DBuf<int64_t> ka;
+	int64_t accB[RB3B_ASIZE + 1];
+	TRY(rank_phase(x, len, d_bwt, ka, accB));
+	return merge_phase(x, len, d_bwt, ka.p);
+}
+
+extern "C" int rb3b_merge_plain(rb3b_index_t *x, int64_t len, const uint8_t *bwt)
+{
+	TRY(rb3b_ensure_init());
+	DBuf<uint8_t> d;
+	if (len <= 0) return RB3B_OK;
+	TRY(d.alloc(len));
+	CK(cudaMemcpyAsync(d.p, bwt, len, cudaMemcpyHostToDevice, rb3b_stream));
+	TRY(rb3b_merge_plain_dev(x, len, d.p));
+	CK(cudaStreamSynchronize(rb3b_stream));
+	return RB3B_OK;
+}

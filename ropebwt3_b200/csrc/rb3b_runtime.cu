@@ -1,0 +1,121 @@
+/*
+ * rb3b_runtime.cu -- device selection, stream, memory pool, error text, counters.
+ * There is no CPU fallback anywhere in this library: if no CUDA device can be
+ * initialised every entry point fails with RB3B_ENODEV.
+ */
+#include <stdarg.h>
+#include <string.h>
+#include <map>
+#include <string>
+#include "rb3b_internal.cuh"
+
+cudaStream_t rb3b_stream = 0;
+int64_t rb3b_seg_len = 2048;      /* target LF-walk segment length ("seg_len") */
+int64_t rb3b_rank_variant = 0;    /* 0: LDG.128 per lane, 1: cp.async.bulk (TMA) staged */
+
+static int g_inited = 0, g_device = 0, g_own_stream = 0;
+static cudaStream_t g_my_stream = 0;
+static thread_local char g_err[1024] = "";
+static std::map<std::string, int64_t> g_stats;
+static std::map<std::string, int64_t> g_params;
+
+int rb3b_fail(int code, const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+void rb3b_stat_set(const char *key, int64_t v) { g_stats[key] = v; }
+void rb3b_stat_add(const char *key, int64_t v) { g_stats[key] += v; }
+
+extern "C" const char *rb3b_last_error(void) { return g_err; }
+extern "C" const char *rb3b_version(void) { return "rb3b200-0.1 (ropebwt3 3.10-r281 merge path, sm_100a)"; }
+
+extern "C" int rb3b_init(int device)
+{
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n <= 0)
+		return rb3b_fail(RB3B_ENODEV, "no CUDA device (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count=0");
+	if (device < 0 || device >= n) return rb3b_fail(RB3B_EINVAL, "device %d out of range [0,%d)", device, n);
+	CK(cudaSetDevice(device));
+	g_device = device;
+	if (!g_my_stream) CK(cudaStreamCreateWithFlags(&g_my_stream, cudaStreamNonBlocking));
+	if (!g_own_stream) rb3b_stream = g_my_stream;
+	cudaMemPool_t pool;
+	CK(cudaDeviceGetDefaultMemPool(&pool, device));
+	uint64_t thr = UINT64_MAX; /* keep freed scratch in the pool: merges reuse it */
+	CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+	g_inited = 1;
+	return RB3B_OK;
+}
+
+int rb3b_ensure_init(void)
+{
+	if (g_inited) { cudaSetDevice(g_device); return RB3B_OK; }
+	return rb3b_init(0);
+}
+
+extern "C" int rb3b_set_stream(void *s)
+{
+	TRY(rb3b_ensure_init());
+	if (s) { rb3b_stream = (cudaStream_t)s; g_own_stream = 1; }
+	else { rb3b_stream = g_my_stream; g_own_stream = 0; }
+	return RB3B_OK;
+}
+
+extern "C" int rb3b_sync(void)
+{
+	TRY(rb3b_ensure_init());
+	CK(cudaStreamSynchronize(rb3b_stream));
+	return RB3B_OK;
+}
+
+extern "C" int rb3b_set_param(const char *key, int64_t value)
+{
+	if (!strcmp(key, "seg_len")) { if (value < 16) return rb3b_fail(RB3B_EINVAL, "seg_len must be >= 16"); rb3b_seg_len = value; }
+	else if (!strcmp(key, "rank_variant")) rb3b_rank_variant = value;
+	else g_params[key] = value;
+	return RB3B_OK;
+}
+
+int64_t rb3b_get_param(const char *key, int64_t dflt)
+{
+	std::map<std::string, int64_t>::iterator it = g_params.find(key);
+	return it == g_params.end() ? dflt : it->second;
+}
+
+extern "C" int64_t rb3b_get_stat(const char *key)
+{
+	std::map<std::string, int64_t>::iterator it = g_stats.find(key);
+	return it == g_stats.end() ? -1 : it->second;
+}
+
+extern "C" void *rb3b_dev_alloc(int64_t bytes)
+{
+	void *p = 0;
+	if (rb3b_ensure_init() != RB3B_OK) return 0;
+	if (cudaMalloc(&p, bytes > 0 ? bytes : 1) != cudaSuccess) { rb3b_fail(RB3B_ENOMEM, "cudaMalloc(%lld) failed", (long long)bytes); return 0; }
+	return p;
+}
+
+extern "C" void rb3b_dev_free(void *p) { if (p) cudaFree(p); }
+
+extern "C" int rb3b_h2d(void *dst, const void *src, int64_t bytes)
+{
+	TRY(rb3b_ensure_init());
+	CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, rb3b_stream));
+	CK(cudaStreamSynchronize(rb3b_stream));
+	return RB3B_OK;
+}
+
+extern "C" int rb3b_d2h(void *dst, const void *src, int64_t bytes)
+{
+	TRY(rb3b_ensure_init());
+	CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, rb3b_stream));
+	CK(cudaStreamSynchronize(rb3b_stream));
+	return RB3B_OK;
+}

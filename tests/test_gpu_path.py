@@ -1,0 +1,276 @@
+"""Parity of the CUDA hot path (through the C ABI) against the CPU oracle, the golden
+fixtures made with the unmodified reference, and -- when oracle/_ref travelled to the box --
+the reference itself.  Everything here is integer work: the bar is bit-exact."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+MERGE_SETS = ["merge_small", "merge_div", "merge_dup"]
+
+
+def runs_of(idx, oracle):
+    s, l = idx.export_runs()
+    s2, l2 = oracle.coalesce(s, l)
+    assert np.array_equal(s, s2) and np.array_equal(l, l2), "export_runs must already be canonical"
+    return s, l
+
+
+# ---------------------------------------------------------------- index + rank
+
+@pytest.mark.parametrize("n_runs,max_len,big", [(1, 1, 0), (1, 100000, 0), (47, 9, 0), (48, 9, 0), (49, 9, 0),
+                                                (5000, 40, 0), (200000, 6, 0), (3000, 5000, 0), (4000, 30, 17)])
+def test_rank1a_random_runs(rb3, oracle, n_runs, max_len, big):
+    from ropebwt3_b200 import synth
+    rng = np.random.default_rng(n_runs + max_len)
+    sym, ln = synth.random_runs(rng, n_runs, max_len, big_every=big)
+    idx = rb3.Index.from_runs(sym, ln)
+    n = int(ln.sum())
+    assert len(idx) == n
+    starts = np.concatenate([[0], np.cumsum(ln)])
+    k = np.concatenate([rng.integers(0, n, 4000), starts[:2000], np.maximum(starts[1:2001] - 1, 0), [n, n + 1, n + 10**9]]).astype(np.int64)
+    ok, ret = idx.rank1a(k)
+    ok0, ret0 = oracle.rank1a(sym, ln, k)
+    bad = np.flatnonzero((ok != ok0).any(1) | (ret != ret0))
+    assert len(bad) == 0, "first mismatch at k=%d: got %s/%d want %s/%d" % (k[bad[0]], ok[bad[0]], ret[bad[0]], ok0[bad[0]], ret0[bad[0]])
+    s2, l2 = runs_of(idx, oracle)
+    assert np.array_equal(s2, sym) and np.array_equal(l2, ln)
+    acc = idx.acc()
+    tot = np.zeros(6, np.int64)
+    np.add.at(tot, sym, ln)
+    assert np.array_equal(np.diff(acc), tot)
+
+
+def test_rank1a_golden(rb3, oracle, golden):
+    for name in MERGE_SETS + ["long_runs"]:
+        g = golden(name)
+        sym, ln, _ = oracle.fmd_decode(bytes(g["fmd"]))
+        idx = rb3.Index.from_runs(sym, ln)
+        ok, ret = idx.rank1a(g["q_k"])
+        assert np.array_equal(ok, g["q_ok"]) and np.array_equal(ret, g["q_ret"]), name
+
+
+def test_from_plain_matches_runs(rb3, oracle, golden):
+    g = golden("merge_small")
+    bwt = g["bwt0"]
+    idx = rb3.Index.from_plain(bwt)
+    s, l = runs_of(idx, oracle)
+    s0, l0 = oracle.plain2runs(bwt)
+    assert np.array_equal(s, s0) and np.array_equal(l, l0)
+    # empty and one-symbol BWTs (edge cases of rb3_enc_plain2fmr)
+    e = rb3.Index.from_plain(np.zeros(0, np.uint8))
+    assert len(e) == 0 and len(e.export_runs()[0]) == 0
+    ok, ret = e.rank1a([0, 5])
+    assert ret.tolist() == [-1, -1] and ok.sum() == 0
+    one = rb3.Index.from_plain(np.array([0], np.uint8))
+    ok, ret = one.rank1a([0, 1])
+    assert ret.tolist() == [0, -1] and ok[1, 0] == 1
+    with pytest.raises(rb3.Rb3bError):
+        rb3.Index.from_plain(np.array([1, 2, 6, 0], np.uint8))  # fm-index.c:125 asserts symbols < 6
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_lf_dev(rb3, oracle, variant):
+    import torch
+    from ropebwt3_b200 import synth
+    rng = np.random.default_rng(77)
+    sym, ln = synth.random_runs(rng, 30000, 25, big_every=1001)
+    idx = rb3.Index.from_runs(sym, ln)
+    n = int(ln.sum())
+    k = np.concatenate([rng.integers(0, n + 1, 50000), [0, n]]).astype(np.int64)
+    c = rng.integers(0, 6, len(k)).astype(np.uint8)
+    dk, dc = torch.from_numpy(k).cuda(), torch.from_numpy(c).cuda()
+    out = torch.empty(len(k), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    idx.lf_dev(len(k), dk.data_ptr(), dc.data_ptr(), out.data_ptr(), variant)
+    rb3.sync()
+    ok0, _ = oracle.rank1a(sym, ln, k)
+    want = idx.acc()[c] + ok0[np.arange(len(k)), c]
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
+# ---------------------------------------------------------------- the merge path
+
+@pytest.mark.parametrize("seg_len", [16, 100, 2048])
+@pytest.mark.parametrize("name", MERGE_SETS)
+def test_merge_chain_golden(rb3, oracle, golden, name, seg_len):
+    """rb3_mg_rank_plain and rb3_fmi_merge_plain, batch by batch, against reference outputs."""
+    g = golden(name)
+    rb3.set_param("seg_len", seg_len)
+    try:
+        idx = rb3.rb3_enc_plain2fmr(g["bwt0"])
+        for b in range(1, int(g["n_batches"])):
+            bwt = g["bwt%d" % b]
+            rb, acc = rb3.rb3_mg_rank_plain(idx, bwt)
+            assert np.array_equal(acc, g["acc%d" % b])
+            bad = np.flatnonzero(rb != g["rb%d" % b])
+            assert len(bad) == 0, "%s batch %d: %d rows differ, first row %d got %d want %d (unresolved=%d rounds=%d)" % (
+                name, b, len(bad), bad[0], rb[bad[0]] >> 6, g["rb%d" % b][bad[0]] >> 6, rb3.get_stat("unresolved_rows"), rb3.get_stat("fix_rounds"))
+            rb3.rb3_fmi_merge_plain(idx, bwt)
+            assert np.array_equal(idx.acc(), g["accA%d" % b])
+        sym, ln = runs_of(idx, oracle)
+        s0, l0, _ = oracle.fmd_decode(bytes(g["fmd"]))
+        assert np.array_equal(sym, s0) and np.array_equal(ln, l0)
+        with tempfile.TemporaryDirectory() as d:
+            idx.dump_fmd(os.path.join(d, "x.fmd"))
+            assert open(os.path.join(d, "x.fmd"), "rb").read() == bytes(g["fmd"])
+        ok, ret = idx.rank1a(g["q_k"])
+        assert np.array_equal(ok, g["q_ok"]) and np.array_equal(ret, g["q_ret"])
+    finally:
+        rb3.set_param("seg_len", 2048)
+
+
+def test_merge_vs_oracle_seeded(rb3, oracle):
+    """Fresh seeded inputs (not in the fixtures), device BWT construction included."""
+    from ropebwt3_b200 import synth
+    gs = synth.genomes(8, 20000, seed=101, sub=0.01, indel=0.001)
+    gs.append(gs[3].copy())                       # an exact duplicate
+    gs.append(np.full(3000, 1, np.uint8))         # a homopolymer
+    gs.append(np.array([1, 2, 5, 5, 3, 4] * 50, np.uint8))  # Ns
+    idx = sym = ln = None
+    rb3.set_param("seg_len", 256)
+    try:
+        for i in range(0, len(gs), 2):
+            text = synth.batch_text(gs[i:i + 2])
+            bwt = rb3.rb3_build_sais(text)
+            assert np.array_equal(bwt, oracle.build_bwt(text)), "device BWT differs from the oracle for batch %d" % i
+            if idx is None:
+                idx = rb3.Index.from_plain(bwt)
+                sym, ln = oracle.plain2runs(bwt)
+            else:
+                rb, acc = idx.mg_rank_plain(bwt)
+                rb0, acc0 = oracle.mg_rank_plain(sym, ln, bwt)
+                assert np.array_equal(acc, acc0)
+                assert np.array_equal(rb, rb0), "interleave array differs at batch %d" % i
+                idx.merge_plain(bwt)
+                sym, ln = oracle.merge_runs(sym, ln, rb0)
+            s, l = runs_of(idx, oracle)
+            assert np.array_equal(s, sym) and np.array_equal(l, ln), "merged runs differ at batch %d" % i
+    finally:
+        rb3.set_param("seg_len", 2048)
+
+
+def test_build_bwt_golden(rb3, golden):
+    for name in MERGE_SETS:
+        g = golden(name)
+        for b in range(int(g["n_batches"])):
+            assert np.array_equal(rb3.rb3_build_sais(g["text%d" % b]), g["bwt%d" % b]), (name, b)
+    g = golden("reads")
+    assert np.array_equal(rb3.rb3_build_sais(g["text"]), g["bwt"])
+    with pytest.raises(rb3.Rb3bError):
+        rb3.rb3_build_sais(np.array([1, 2, 3], np.uint8))  # no trailing sentinel (mrope.c:310)
+
+
+def test_merge_errors(rb3, golden):
+    g = golden("merge_small")
+    idx = rb3.Index.from_plain(g["bwt0"])
+    with pytest.raises(rb3.Rb3bError):
+        idx.merge_plain(np.array([1, 2, 3, 4], np.uint8))      # no sentinel
+    with pytest.raises(rb3.Rb3bError):
+        idx.merge_plain(np.array([1, 0, 7], np.uint8))         # symbol out of range
+    with pytest.raises(rb3.Rb3bError):
+        idx.merge_plain(np.array([0, 1, 1], np.uint8))         # not a BWT: the A-cycle never reaches the sentinel
+    # the index is untouched by failed merges
+    assert np.array_equal(idx.acc(), g["accA0"])
+
+
+def test_dump_restore_roundtrip(rb3, oracle, golden):
+    g = golden("merge_div")
+    with tempfile.TemporaryDirectory() as d:
+        for ext, key in [("fmd", "fmd"), ("fmr", "fmr")]:
+            fn = os.path.join(d, "ref." + ext)
+            open(fn, "wb").write(bytes(g[key]))
+            idx = rb3.Index.restore(fn)              # rb3_fmi_restore: both formats
+            out = os.path.join(d, "mine.fmd")
+            idx.dump_fmd(out)
+            assert open(out, "rb").read() == bytes(g["fmd"])
+            out = os.path.join(d, "mine.fmr")
+            idx.dump_fmr(out)
+            idx2 = rb3.Index.restore(out)
+            assert np.array_equal(np.concatenate(idx2.export_runs()), np.concatenate(idx.export_runs()))
+            out = os.path.join(d, "mine.txt")
+            idx.dump_plain(out)
+            s, l, _ = oracle.fmd_decode(bytes(g["fmd"]))
+            assert open(out).read() == oracle.to_ascii(oracle.runs2plain(s, l)) + "\n"
+        with pytest.raises(rb3.Rb3bError):
+            rb3.Index.restore(os.path.join(d, "missing.fmd"))
+        open(os.path.join(d, "junk"), "wb").write(b"hello world")
+        with pytest.raises(rb3.Rb3bError):
+            rb3.Index.restore(os.path.join(d, "junk"))
+
+
+def test_incremental_append_equals_scratch(rb3, oracle, golden):
+    """`-i` semantics: restore an existing index and append == building from scratch."""
+    g = golden("merge_small")
+    nb = int(g["n_batches"])
+    with tempfile.TemporaryDirectory() as d:
+        a = rb3.Index.from_plain(g["bwt0"])
+        for b in range(1, 3):
+            a.merge_plain(g["bwt%d" % b])
+        fn = os.path.join(d, "half.fmr")
+        a.dump_fmr(fn)
+        r = rb3.Index.restore(fn)
+        for b in range(3, nb):
+            r.merge_plain(g["bwt%d" % b])
+        out = os.path.join(d, "full.fmd")
+        r.dump_fmd(out)
+        assert open(out, "rb").read() == bytes(g["fmd"])
+
+
+def test_merge_index(rb3, oracle, golden):
+    """rb3_fmi_merge (BWT-vs-BWT): merging index B into A == merging B's plain BWT."""
+    g = golden("merge_small")
+    a = rb3.Index.from_plain(g["bwt0"])
+    a.merge_plain(g["bwt1"])
+    b = rb3.Index.from_plain(g["bwt2"])
+    from ropebwt3_b200 import capi
+    capi.check(capi.lib().rb3b_merge_index(a.h, b.h))
+    c = rb3.Index.from_plain(g["bwt0"])
+    c.merge_plain(g["bwt1"])
+    c.merge_plain(g["bwt2"])
+    assert np.array_equal(np.concatenate(a.export_runs()), np.concatenate(c.export_runs()))
+
+
+def test_device_pointer_entry_points(rb3, golden):
+    import torch
+    g = golden("merge_small")
+    d0 = torch.from_numpy(g["bwt0"]).cuda()
+    d1 = torch.from_numpy(g["bwt1"]).cuda()
+    torch.cuda.synchronize()
+    idx = rb3.Index.from_plain_dev(d0.data_ptr(), len(g["bwt0"]))
+    rb = torch.empty(len(g["bwt1"]), dtype=torch.int64, device="cuda")
+    acc = idx.mg_rank_plain_dev(d1.data_ptr(), len(g["bwt1"]), rb.data_ptr())
+    rb3.sync()
+    assert np.array_equal(rb.cpu().numpy(), g["rb1"]) and np.array_equal(acc, g["acc1"])
+    idx.merge_plain_dev(d1.data_ptr(), len(g["bwt1"]))
+    rb3.sync()
+    assert np.array_equal(idx.acc(), g["accA1"])
+
+
+def test_against_reference_binary_midsize(rb3, oracle):
+    """20 x 50 kb genomes merged one per batch; the .fmd must equal the reference CLI's byte for byte."""
+    from oracle import ref
+    if not os.path.exists(ref.BIN):
+        pytest.skip("oracle/_ref/ropebwt3 did not travel")
+    from ropebwt3_b200 import synth
+    gs = synth.genomes(20, 50000, seed=44)
+    with tempfile.TemporaryDirectory() as d:
+        fa = os.path.join(d, "g.txt")
+        with open(fa, "w") as f:
+            for g_ in gs:
+                f.write(oracle.to_ascii(g_) + "\n")
+        want = ref.run(["build", "-L", "-d", "-t4", fa])
+        idx = None
+        for g_ in gs:
+            bwt = rb3.rb3_build_sais(synth.batch_text([g_]))
+            if idx is None:
+                idx = rb3.Index.from_plain(bwt)
+            else:
+                idx.merge_plain(bwt)
+        out = os.path.join(d, "mine.fmd")
+        idx.dump_fmd(out)
+        got = open(out, "rb").read()
+        assert got == want, "fmd differs from the reference: %d vs %d bytes" % (len(got), len(want))
