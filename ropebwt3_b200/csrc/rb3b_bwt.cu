@@ -114,7 +114,7 @@ static int suffix_sort(int64_t len, const uint8_t *d_text, DBuf<uint32_t> &sa)
 	TRY(key0.alloc(n)); TRY(key1.alloc(n)); TRY(idx0.alloc(n)); TRY(sa.alloc(n)); TRY(rank.alloc(n)); TRY(head.alloc(n)); TRY(bad.alloc(1)); TRY(amb.alloc(1));
 	CK(cudaMemsetAsync(bad.p, 0, sizeof(int), rb3b_stream));
 	k_kmer_keys<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, d_text, key0.p, idx0.p, bad.p); CKK();
-	int rounds = 0, launches = 1;
+	int rounds = 0;
 	for (uint64_t h = KMER;; h <<= 1) {
 		TRY(sort_pairs(key0.p, key1.p, idx0.p, sa.p, n, 64));
 		k_group_heads<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, key1.p, rounds == 0, head.p); CKK();
@@ -127,12 +127,11 @@ static int suffix_sort(int64_t len, const uint8_t *d_text, DBuf<uint32_t> &sa)
 		if (rounds == 0) CK(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, rb3b_stream));
 		CK(cudaStreamSynchronize(rb3b_stream));
 		if (hbad) return rb3b_fail(RB3B_EINVAL, "batch text holds a symbol >= %d", RB3B_ASIZE);
-		++rounds; launches += 12;
+		++rounds;
 		if (n_amb == 0 || h >= n) break;
 		k_pair_keys<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, (uint32_t)h, rank.p, key0.p, idx0.p); CKK();
 	}
 	rb3b_stat_set("sa_rounds", rounds);
-	rb3b_stat_add("kernel_launches", launches);
 	return RB3B_OK;
 }
 
@@ -142,11 +141,15 @@ extern "C" int rb3b_build_bwt_dev(int64_t len, const uint8_t *d_text, uint8_t *d
 	if (len <= 0) return rb3b_fail(RB3B_EINVAL, "empty batch");
 	DBuf<uint32_t> sa;
 	DBuf<uint8_t> tmp;
+	rb3b_tic(T_BWT);
 	TRY(suffix_sort(len, d_text, sa));
 	uint8_t *dst = d_bwt_out;
 	if (d_bwt_out == d_text) { TRY(tmp.alloc(len)); dst = tmp.p; } /* in place, like the reference */
 	k_sa_to_bwt<<<nblk(len, TPB), TPB, 0, rb3b_stream>>>((uint32_t)len, d_text, sa.p, dst); CKK();
 	if (dst != d_bwt_out) CK(cudaMemcpyAsync(d_bwt_out, dst, len, cudaMemcpyDeviceToDevice, rb3b_stream));
+	rb3b_toc(T_BWT);
+	CK(cudaStreamSynchronize(rb3b_stream));
+	rb3b_tflush();
 	return RB3B_OK;
 }
 

@@ -204,12 +204,14 @@ __global__ void k_blk_header(int64_t nb, uint4 *blocks, const int64_t *__restric
 	}
 }
 
-__global__ void k_dir_scatter(int64_t nb, const uint64_t *__restrict__ bstart, int shift, uint32_t *__restrict__ dir)
+__global__ void k_dir_scatter(int64_t nb, const uint64_t *__restrict__ bstart, int shift, uint32_t *__restrict__ dir, int64_t n_dir)
 {
 	int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (b >= nb) return;
 	uint64_t s = bstart[b], j = (s + ((1ULL << shift) - 1)) >> shift;
 	if ((j << shift) < bstart[b + 1]) dir[j] = (uint32_t)b;
+	if (b == nb - 1) /* cells at or past the end must name the last block: they bound the search from above */
+		for (j = (bstart[nb] + ((1ULL << shift) - 1)) >> shift; j < (uint64_t)n_dir; ++j) dir[j] = (uint32_t)b;
 }
 
 int rb3b_index_finalize(rb3b_index_s *x)
@@ -245,7 +247,7 @@ int rb3b_index_finalize(rb3b_index_s *x)
 	x->n_dir = (x->n >> shift) + 2;
 	TRY(dir.alloc(x->n_dir));
 	CK(cudaMemsetAsync(dir.p, 0, x->n_dir * 4, rb3b_stream));
-	k_dir_scatter<<<nblk(nb, TPB), TPB, 0, rb3b_stream>>>(nb, bstart.p, shift, dir.p); CKK();
+	k_dir_scatter<<<nblk(nb, TPB), TPB, 0, rb3b_stream>>>(nb, bstart.p, shift, dir.p, x->n_dir); CKK();
 	TRY(scan_max_u32(dir.p, x->n_dir));
 	if (x->bstart) cudaFreeAsync(x->bstart, rb3b_stream);
 	if (x->dir) cudaFreeAsync(x->dir, rb3b_stream);
@@ -436,7 +438,6 @@ extern "C" int rb3b_rank1a_dev(const rb3b_index_t *x, int64_t nq, const int64_t 
 	if (nq <= 0) return RB3B_OK;
 	int64_t want = (nq * RB3B_GROUP + TPB - 1) / TPB, cap = (int64_t)n_sm() * 8 * 4;
 	k_rank1a<<<(unsigned)(want < cap ? want : cap), TPB, 0, rb3b_stream>>>(rb3b_dev_view(x), nq, d_k, d_ok, d_sym); CKK();
-	rb3b_stat_add("kernel_launches", 1);
 	return RB3B_OK;
 }
 
@@ -464,7 +465,6 @@ extern "C" int rb3b_lf_dev(const rb3b_index_t *x, int64_t nq, const int64_t *d_k
 	if (variant == 1) return rb3b_lf_tma_launch(x, nq, d_k, d_c, d_out);
 	int64_t want = (nq * RB3B_GROUP + TPB - 1) / TPB, cap = (int64_t)n_sm() * 8 * 8;
 	k_lf<<<(unsigned)(want < cap ? want : cap), TPB, 0, rb3b_stream>>>(rb3b_dev_view(x), nq, d_k, d_c, d_out); CKK();
-	rb3b_stat_add("kernel_launches", 1);
 	return RB3B_OK;
 }
 

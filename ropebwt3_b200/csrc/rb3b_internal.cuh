@@ -72,10 +72,16 @@ int  rb3b_fail(int code, const char *fmt, ...);
 int  rb3b_ensure_init(void);
 void rb3b_stat_set(const char *key, int64_t v);
 void rb3b_stat_add(const char *key, int64_t v);
+extern int64_t rb3b_n_launch;   /* kernels of this library launched so far (CUB internals not counted) */
+/* device-side timing of the main kernels: tic/toc record events on the stream, tflush (after a sync) adds "us_<name>" stats */
+enum { T_PREP, T_WALK1, T_WALKFIX, T_MERGE, T_FINAL, T_BWT, T_COUNT };
+void rb3b_tic(int id);
+void rb3b_toc(int id);
+void rb3b_tflush(void);
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
 	return rb3b_fail(RB3B_ENODEV, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
-#define CKK() CK(cudaGetLastError())
+#define CKK() do { ++rb3b_n_launch; CK(cudaGetLastError()); } while (0)   /* after every launch of one of OUR kernels */
 #define TRY(call) do { int r_ = (call); if (r_ != RB3B_OK) return r_; } while (0)
 
 /* stream-ordered scratch buffer */

@@ -246,6 +246,7 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	/* batch LF mapping */
 	TRY(tcnt.alloc((nt + 1) * RB3B_ASIZE)); TRY(tex.alloc((nt + 1) * RB3B_ASIZE)); TRY(bad.alloc(1)); TRY(lfb.alloc(len));
 	CK(cudaMemsetAsync(bad.p, 0, sizeof(int), rb3b_stream));
+	rb3b_tic(T_PREP);
 	k_prep_count<<<(unsigned)nt, TPB, 0, rb3b_stream>>>(len, d_bwt, nt, tcnt.p, bad.p); CKK();
 	TRY(rb3b_scan_excl_i64(tcnt.p, tex.p, (nt + 1) * RB3B_ASIZE));
 	int64_t tot[RB3B_ASIZE], base[RB3B_ASIZE];
@@ -263,6 +264,7 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	if (acc.v[1] <= 0) return rb3b_fail(RB3B_EINVAL, "batch BWT holds no sentinel");
 	int64_t seg_len = rb3b_seg_len;
 	k_prep_lf<<<(unsigned)nt, TPB, 0, rb3b_stream>>>(len, d_bwt, nt, tex.p, acc, seg_len, lfb.p); CKK();
+	rb3b_toc(T_PREP);
 	/* segments */
 	Segs S;
 	S.n_seq = acc.v[1]; S.seg_len = seg_len;
@@ -277,10 +279,12 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	CK(cudaMemsetAsync(ka.p, 0xff, len * 8, rb3b_stream));
 	DevIndex dA = rb3b_dev_view(A);
 	int64_t groups = S.n_seg, want = (groups * RB3B_GROUP + TPB - 1) / TPB, cap = (int64_t)n_sm() * 8;
+	rb3b_tic(T_WALK1);
 	k_walk_first<<<(unsigned)(want < cap ? want : cap), TPB, 0, rb3b_stream>>>(dA, acc, S, lfb.p, ka.p, ctr.p); CKK();
+	rb3b_toc(T_WALK1);
 	int64_t *wl_seg[2] = { wl.p, wl.p + 2 * S.n_seg }, *wl_val[2] = { wl.p + S.n_seg, wl.p + 3 * S.n_seg };
 	k_collect_first<<<nblk(S.n_seg, TPB), TPB, 0, rb3b_stream>>>(S, wl_seg[0], wl_val[0], (unsigned long long*)(ctr.p + 1)); CKK();
-	int64_t n_items = 0, rounds = 1, launches = 4, fix_rows = 0;
+	int64_t n_items = 0, rounds = 1, fix_rows = 0;
 	CK(cudaMemcpyAsync(&n_items, ctr.p + 1, 8, cudaMemcpyDeviceToHost, rb3b_stream));
 	CK(cudaStreamSynchronize(rb3b_stream));
 	int cur = 0;
@@ -288,23 +292,26 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 		/* ctr[2] = item cursor, ctr[3] = size of the next list */
 		CK(cudaMemsetAsync(ctr.p + 2, 0, 16, rb3b_stream));
 		want = (n_items * RB3B_GROUP + TPB - 1) / TPB;
+		rb3b_tic(T_WALKFIX);
 		k_walk_fix<<<(unsigned)(want < cap ? want : cap), TPB, 0, rb3b_stream>>>(dA, S, lfb.p, ka.p, n_items, wl_seg[cur], wl_val[cur], ctr.p + 2,
 			wl_seg[cur ^ 1], wl_val[cur ^ 1], (unsigned long long*)(ctr.p + 3)); CKK();
+		rb3b_toc(T_WALKFIX);
 		fix_rows += n_items;
 		CK(cudaMemcpyAsync(&n_items, ctr.p + 3, 8, cudaMemcpyDeviceToHost, rb3b_stream));
 		CK(cudaStreamSynchronize(rb3b_stream));
-		cur ^= 1; ++rounds; ++launches;
+		rb3b_tflush();
+		cur ^= 1; ++rounds;
 	}
 	unsigned long long sums[2];
 	CK(cudaMemsetAsync(ctr.p + 4, 0, 16, rb3b_stream));
 	k_seg_check<<<nblk(S.n_seg, TPB), TPB, 0, rb3b_stream>>>(S, (unsigned long long*)(ctr.p + 4)); CKK();
 	CK(cudaMemcpyAsync(sums, ctr.p + 4, 16, cudaMemcpyDeviceToHost, rb3b_stream));
 	CK(cudaStreamSynchronize(rb3b_stream));
+	rb3b_tflush();
 	rb3b_stat_set("n_segments", S.n_seg);
 	rb3b_stat_set("fix_rounds", rounds - 1);
 	rb3b_stat_set("fix_segments", fix_rows);
 	rb3b_stat_set("unresolved_rows", (int64_t)sums[0]);
-	rb3b_stat_add("kernel_launches", launches + 1);
 	if (sums[0] != 0 || (int64_t)sums[1] != len)
 		return rb3b_fail(RB3B_EINVAL, "batch is not the BWT of a sentinel-terminated string set (%lld of %lld rows reachable, %lld unresolved)",
 		                 (long long)sums[1], (long long)len, (long long)sums[0]);
@@ -387,6 +394,7 @@ static int merge_phase(rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, const
 	int hbad = 0;
 	TRY(blo.alloc(nb + 1)); TRY(cnt.alloc(nb)); TRY(eoff.alloc(nb)); TRY(bad.alloc(1));
 	CK(cudaMemsetAsync(bad.p, 0, sizeof(int), rb3b_stream));
+	rb3b_tic(T_MERGE);
 	k_check_monotone<<<nblk(len, TPB), TPB, 0, rb3b_stream>>>(len, d_ka, A->n, bad.p); CKK();
 	k_tile_bounds<<<nblk(nb + 1, TPB), TPB, 0, rb3b_stream>>>(nb, A->bstart, len, d_ka, blo.p); CKK();
 	k_merge<false><<<nblk(nb, 128), 128, 0, rb3b_stream>>>(nb, A->blocks, A->bstart, blo.p, d_ka, d_bwt, cnt.p, 0, 0); CKK();
@@ -401,11 +409,16 @@ static int merge_phase(rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, const
 	TRY(out.alloc(nb2 * 8));
 	CK(cudaMemsetAsync(out.p, 0, nb2 * 128, rb3b_stream));
 	k_merge<true><<<nblk(nb, 128), 128, 0, rb3b_stream>>>(nb, A->blocks, A->bstart, blo.p, d_ka, d_bwt, 0, eoff.p, out.p); CKK();
+	rb3b_toc(T_MERGE);
 	cudaFreeAsync(A->blocks, rb3b_stream);
 	A->blocks = out.take();
 	A->n_blocks = nb2; A->n_entries = n_ent;
-	rb3b_stat_add("kernel_launches", 4 + 6);
-	return rb3b_index_finalize(A);
+	rb3b_tic(T_FINAL);
+	int rc = rb3b_index_finalize(A);
+	rb3b_toc(T_FINAL);
+	cudaStreamSynchronize(rb3b_stream);
+	rb3b_tflush();
+	return rc;
 }
 
 /* ------------------------------------------------------------------ */

@@ -113,6 +113,5 @@ int rb3b_lf_tma_launch(const rb3b_index_s *x, int64_t nq, const int64_t *d_k, co
 	int64_t want = (nq * RB3B_GROUP + TPB - 1) / TPB, cap = (int64_t)sm * 8;
 	k_lf_tma<<<(unsigned)(want < cap ? want : cap), TPB, 0, rb3b_stream>>>(rb3b_dev_view(x), nq, d_k, d_c, d_out);
 	CKK();
-	rb3b_stat_add("kernel_launches", 1);
 	return RB3B_OK;
 }

@@ -28,6 +28,34 @@ int rb3b_fail(int code, const char *fmt, ...)
 	return code;
 }
 
+int64_t rb3b_n_launch = 0;
+static cudaEvent_t g_ev[T_COUNT][2];
+static int g_ev_ok = 0, g_ev_pending[T_COUNT];
+static const char *g_ev_name[T_COUNT] = { "us_prep", "us_walk_first", "us_walk_fix", "us_merge", "us_finalize", "us_bwt" };
+
+void rb3b_tic(int id)
+{
+	if (!g_ev_ok) {
+		for (int i = 0; i < T_COUNT; ++i) { cudaEventCreate(&g_ev[i][0]); cudaEventCreate(&g_ev[i][1]); g_ev_pending[i] = 0; }
+		g_ev_ok = 1;
+	}
+	if (g_ev_pending[id]) rb3b_tflush();
+	cudaEventRecord(g_ev[id][0], rb3b_stream);
+}
+
+void rb3b_toc(int id) { cudaEventRecord(g_ev[id][1], rb3b_stream); g_ev_pending[id] = 1; }
+
+void rb3b_tflush(void)
+{
+	for (int i = 0; i < T_COUNT; ++i)
+		if (g_ev_ok && g_ev_pending[i]) {
+			float ms = 0;
+			cudaEventSynchronize(g_ev[i][1]);
+			if (cudaEventElapsedTime(&ms, g_ev[i][0], g_ev[i][1]) == cudaSuccess) rb3b_stat_add(g_ev_name[i], (int64_t)(ms * 1000.0f + 0.5f));
+			g_ev_pending[i] = 0;
+		}
+}
+
 void rb3b_stat_set(const char *key, int64_t v) { g_stats[key] = v; }
 void rb3b_stat_add(const char *key, int64_t v) { g_stats[key] += v; }
 
@@ -90,6 +118,8 @@ int64_t rb3b_get_param(const char *key, int64_t dflt)
 
 extern "C" int64_t rb3b_get_stat(const char *key)
 {
+	if (!strcmp(key, "kernel_launches")) return rb3b_n_launch;
+	if (!strcmp(key, "reset")) { g_stats.clear(); rb3b_n_launch = 0; return 0; }
 	std::map<std::string, int64_t>::iterator it = g_stats.find(key);
 	return it == g_stats.end() ? -1 : it->second;
 }
