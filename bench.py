@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- bases/sec indexed through the BWT-merge hot path (BASELINE.json configs[1]).
+
+Workload: merge-build of synthetic 5 Mb bacterial genomes, one genome (both strands,
+10^7 symbols) per merge, exactly the README multi-file form of `ropebwt3 build`.
+A *step* is one rb3_fmi_merge_plain of one genome's partial BWT into the growing index.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path
+  python bench.py --impl reference [...]                        the reference's CPU path (oracle/_ref)
+
+`value`  = bases/s with the partial BWTs already resident in HBM (device pointers in).
+`e2e`    = the same merges through the host-buffer C-ABI call (H2D copy of every batch and
+           the D2H reads of the result inside the timed region).
+`roofline` is for the dominant kernel (k_walk_first), timed with CUDA events on its stream.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "bases/sec indexed (build)"
+UNIT = "bases/s"
+GENOME_LEN = 5_000_000
+SEED = 43  # 42 + config index
+LF_STEP_BYTES = 160  # 128-B index block + 8 B query + 8 B result + 8 B LF_B read + 8 B ka write
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=96)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--genome-len", type=int, default=GENOME_LEN)
+    ap.add_argument("--seg-len", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def config_of(a, extra=None):
+    c = {"workload": "configs[1]: merge-build of synthetic %.1f Mb bacterial genomes (0.5%% subst + 0.05%% indel from a random earlier genome), one genome = one merge of %d symbols (both strands); %d genomes in total" % (
+        a.genome_len / 1e6, 2 * a.genome_len + 2, 1 + a.warmup + a.steps),
+        "genome_len": a.genome_len, "genomes": 1 + a.warmup + a.steps, "seed": SEED,
+        "l2": "no explicit flush: every step reads a new 10 MB batch and streams ~170 MB of per-batch LF/interleave arrays (> 126 MB L2); the index itself (tens of MB) is L2-resident by nature at this config"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile(suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.f.name):
+            t = [x.strip() for x in line.split(",")]
+            if len(t) < 8 or not t[0].isdigit() or int(t[0]) != self.idx:
+                continue
+            try:
+                sm.append(float(t[1])); mx.append(float(t[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], t[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def make_genomes(a):
+    from ropebwt3_b200 import synth
+    return synth.genomes(1 + a.warmup + a.steps, a.genome_len, seed=SEED, sub=0.005, indel=0.0005)
+
+
+# --------------------------------------------------------------------------- our arm
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    import ropebwt3_b200 as R
+    from ropebwt3_b200 import synth, capi
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    R.init(local)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    capi.check(capi.lib().rb3b_set_stream(stream.cuda_stream))
+    if a.seg_len:
+        R.set_param("seg_len", a.seg_len)
+
+    # ---- synthetic input, partial BWTs built on the device (untimed producer of the path's input)
+    t0 = time.time()
+    gs = make_genomes(a)
+    n_g = len(gs)
+    d_bwt, h_bwt, lens = [], [], []
+    t_bwt = 0.0
+    for g in gs:
+        text = synth.batch_text([g])
+        d_text = torch.from_numpy(text).cuda()
+        out = torch.empty_like(d_text)
+        torch.cuda.synchronize()
+        t1 = time.time()
+        capi.check(capi.lib().rb3b_build_bwt_dev(len(text), d_text.data_ptr(), out.data_ptr()))
+        R.sync()
+        t_bwt += time.time() - t1
+        d_bwt.append(out)
+        hb = torch.empty(len(text), dtype=torch.uint8).pin_memory()
+        hb.copy_(out)
+        h_bwt.append(hb)
+        lens.append(len(text))
+    bases = [len(g) for g in gs]
+    t_setup = time.time() - t0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident run
+    idx = R.Index.from_plain_dev(d_bwt[0].data_ptr(), lens[0])
+    for i in range(1, 1 + a.warmup):
+        idx.merge_plain_dev(d_bwt[i].data_ptr(), lens[i])
+    barrier()
+    R.get_stat("reset")
+    sampler = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
+    e0.record(stream)
+    for i in range(1 + a.warmup, n_g):
+        idx.merge_plain_dev(d_bwt[i].data_ptr(), lens[i])
+    e1.record(stream)
+    barrier()
+    wall_dev = time.time() - w0
+    ms_dev = e0.elapsed_time(e1)
+    st = {k: R.get_stat(k) for k in ["us_prep", "us_walk_first", "us_walk_fix", "us_merge", "us_finalize", "kernel_launches", "n_segments", "fix_rounds", "n_blocks"]}
+    acc_dev = idx.acc()
+    index_bytes = idx.nbytes()
+    timed_bases = sum(bases[1 + a.warmup:])
+    timed_syms = sum(lens[1 + a.warmup:])
+
+    # ---- end to end through the host-buffer C-ABI call
+    ms_e2e, e2e_val, d2h = 0.0, 0.0, 0
+    if not a.no_e2e:
+        idx2 = R.Index.from_plain(h_bwt[0].numpy())
+        for i in range(1, 1 + a.warmup):
+            idx2.merge_plain(h_bwt[i].numpy())
+        barrier()
+        hp = [h.data_ptr() for h in h_bwt]
+        L = capi.lib()
+        acc_host = np.zeros(7, np.int64)
+        e0.record(stream)
+        w0 = time.time()
+        for i in range(1 + a.warmup, n_g):
+            capi.check(L.rb3b_merge_plain(idx2.h, lens[i], hp[i]))       # H2D of the batch + merge + sync
+            L.rb3b_get_acc(idx2.h, acc_host.ctypes.data)                   # the step's result: new C[] of the index
+        e1.record(stream)
+        barrier()
+        wall_e2e = time.time() - w0
+        ms_e2e = max(e0.elapsed_time(e1), wall_e2e * 1e3)
+        assert np.array_equal(acc_host, acc_dev), "host-buffer and device-pointer builds disagree"
+        # D2H per merge: 2x6 totals of the batch, 3 scalars (tiles), 2x6 totals + 2 counters of the new index, worklist counters
+        d2h = 8 * (12 + 3 + 12 + 2 + 2 + 2 * max(1, st["fix_rounds"] // max(1, a.steps)))
+        e2e_val = timed_bases / (ms_e2e / 1e3)
+    clocks = sampler.stop()
+
+    # ---- sanity of the result (full parity lives in tests/): totals must add up
+    expect = np.zeros(6, np.int64)
+    for g in gs:
+        cnt = np.bincount(g, minlength=6)[:6]
+        expect += cnt + cnt[[0, 4, 3, 2, 1, 5]]
+        expect[0] += 2
+    assert np.array_equal(np.diff(acc_dev), expect), "symbol totals of the built index are wrong"
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([ms_dev, ms_e2e], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev = float(t[0])
+        if not a.no_e2e:
+            ms_e2e = float(t[1])
+            e2e_val = timed_bases / (ms_e2e / 1e3)
+
+    value = timed_bases / (ms_dev / 1e3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    walk_s = st["us_walk_first"] / 1e6
+    achieved = LF_STEP_BYTES * timed_syms / walk_s / 1e9 if walk_s > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "walk_first_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    line = {
+        "metric": METRIC, "value": value * world, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/int64", "data": "synthetic",
+        "config": config_of(a, {"seg_len": a.seg_len or 2048, "parallelism": "replicas only" if world > 1 else "1 GPU"}),
+        "e2e": None if a.no_e2e else {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(np.mean(lens[1 + a.warmup:])), "d2h_bytes_per_step": int(d2h),
+                                      "ms_per_step": ms_e2e / a.steps},
+        "gpu_launches": int(st["kernel_launches"]),
+        "clocks": clocks,
+        "roofline": {"kernel": "k_walk_first (segmented LF walk: batched rank over the RLE index + LF_B gather + interleave scatter)",
+                     "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                     "traffic": traffic, "bytes_per_unit": LF_STEP_BYTES, "units_per_launch": timed_syms / a.steps,
+                     "avg_launch_ms": walk_s * 1e3 / a.steps,
+                     "note": "latency-bound dependent chains on an L2-resident index at this config; see profiles/"},
+        "phase_ms_per_step": {k[3:]: st[k] / 1e3 / a.steps for k in st if k.startswith("us_")},
+        "wall_ms_per_step": wall_dev * 1e3 / a.steps,
+        "setup": {"genomes_and_bwt_s": t_setup, "device_bwt_build_s": t_bwt, "bwt_build_bases_per_s": sum(bases) / t_bwt},
+        "index": {"symbols": int(acc_dev[6]), "device_bytes": int(index_bytes), "blocks": int(st["n_blocks"])},
+        "walk": {"segments_per_step": st["n_segments"], "fix_rounds_total": st["fix_rounds"]},
+    }
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(a, gs, idx_state_genomes=1 + a.warmup, budget_s=20.0)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------- CPU reference
+
+def ref_index_of(gs, n_threads):
+    """Index of the given genomes built by the reference itself (libsais + rb3_enc_plain2fmr)."""
+    from oracle import ref
+    from ropebwt3_b200 import synth
+    text = synth.batch_text(gs)
+    bwt = ref.build_sais(text, 2 * len(gs), n_threads)
+    return ref.Rope.from_plain(bwt, n_threads)
+
+
+def cpu_baseline(a, gs, idx_state_genomes, budget_s):
+    """The reference's rb3_fmi_merge_plain (oracle/_ref/librb3ref.so) on the host cores, on a bounded sample."""
+    from oracle import ref
+    from ropebwt3_b200 import synth
+    cores = os.cpu_count() or 1
+    if not ref.available():
+        return port_baseline(a, gs, budget_s)
+    n0 = min(idx_state_genomes, 4)
+    rope = ref_index_of(gs[:n0], cores)
+    frag = min(a.genome_len, 1_000_000)
+    done_bases, t_used, n_merge = 0, 0.0, 0
+    for g in gs[n0:]:
+        piece = g[:frag]
+        bwt = ref.build_sais(synth.batch_text([piece]), 2, cores)
+        t0 = time.time()
+        rope.merge_plain(bwt, cores)
+        t_used += time.time() - t0
+        done_bases += len(piece)
+        n_merge += 1
+        if t_used > budget_s:
+            break
+    rope.close()
+    return {"value": done_bases / t_used, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": "%d merges (rb3_fmi_merge_plain, n_threads=%d) of a %.1f Mb genome prefix (both strands) into the reference's index of the first %d genomes; %.1f s of CPU wall time; only 2 chains per merge exist, so the reference's rank phase cannot use more than 2 threads here" % (
+                n_merge, cores, frag / 1e6, n0, t_used)}
+
+
+def port_baseline(a, gs, budget_s):
+    from oracle import oracle as O
+    from ropebwt3_b200 import synth
+    frag = 200_000
+    sym, ln = O.plain2runs(O.build_bwt(synth.batch_text([gs[0][:frag]])))
+    bwt = O.build_bwt(synth.batch_text([gs[1][:frag]]))
+    t0 = time.time()
+    O.merge_plain(sym, ln, bwt)
+    dt = time.time() - t0
+    return {"value": frag / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "one merge of a %d bp genome prefix into a %d bp one with the scalar oracle port (oracle/_ref absent)" % (frag, frag)}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from oracle import ref
+    from ropebwt3_b200 import synth
+    cores = os.cpu_count() or 1
+    gs = make_genomes(a)
+    if not ref.available():
+        b = port_baseline(a, gs, 20.0)
+        line = {"impl": "reference", "metric": METRIC, "value": b["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64", "data": "synthetic",
+                "config": config_of(a), "cpu_baseline": b, "e2e": {"value": b["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+    n0 = min(1 + a.warmup, 4)
+    rope = ref_index_of(gs[:n0], cores)
+    rest = gs[n0:] if len(gs) > n0 else gs[-1:]
+    # size the per-step sample so that the whole run stays within ~150 s of merge time
+    probe = rest[0][:100_000]
+    bwt = ref.build_sais(synth.batch_text([probe]), 2, cores)
+    t0 = time.time()
+    rope.merge_plain(bwt, cores)
+    rate = len(probe) / (time.time() - t0)
+    frag = int(max(20_000, min(a.genome_len, rate * 150.0 / (a.steps + a.warmup))))
+    times, nb = [], 0
+    for i in range(a.warmup + a.steps):
+        g = rest[(i + 1) % len(rest)]
+        piece = g[:frag]
+        bwt = ref.build_sais(synth.batch_text([piece]), 2, cores)
+        t0 = time.time()
+        rope.merge_plain(bwt, cores)
+        dt = time.time() - t0
+        if i >= a.warmup:
+            times.append(dt)
+            nb += len(piece)
+    rope.close()
+    tot = sum(times)
+    val = nb / tot
+    sample = "each step = rb3_fmi_merge_plain(n_threads=%d) of a %.2f Mb prefix of the next genome (both strands, %d symbols) into the reference's own index (first %d genomes + earlier steps); sized from a 100 kb probe so that %d steps take ~150 s" % (
+        cores, frag / 1e6, 2 * frag + 2, n0, a.steps + a.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": tot * 1e3 / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/int64", "data": "synthetic", "config": config_of(a, {"sample_bases_per_step": frag}),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

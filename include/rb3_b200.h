@@ -55,6 +55,7 @@ int rb3b_index_from_plain(rb3b_index_t *idx, int64_t len, const uint8_t *bwt);
 int rb3b_index_from_plain_dev(rb3b_index_t *idx, int64_t len, const uint8_t *d_bwt);
 /* rb3_enc_fmd2fmr (fm-index.c:56-85) / mr_restore (mrope.c:161): load a run list (need not be coalesced). */
 int rb3b_index_from_runs(rb3b_index_t *idx, int64_t n_runs, const uint8_t *sym, const int64_t *len);
+int rb3b_index_from_runs_device(rb3b_index_t *idx, int64_t n_runs, const uint8_t *d_sym, const int64_t *d_len);   /* run list in device memory */
 
 /* rb3_fmi_merge_plain (fm-index.c:279-303): merge the partial BWT `bwt` of a new
  * batch (host memory, caller-owned) into the index in place. */

@@ -412,6 +412,12 @@ extern "C" int rb3b_index_from_runs(rb3b_index_t *x, int64_t n_runs, const uint8
 	return rb3b_index_from_runs_dev(x, n_runs, ds.p, dl.p);
 }
 
+extern "C" int rb3b_index_from_runs_device(rb3b_index_t *x, int64_t n_runs, const uint8_t *d_sym, const int64_t *d_len)
+{
+	TRY(rb3b_ensure_init());
+	return rb3b_index_from_runs_dev(x, n_runs, d_sym, d_len);
+}
+
 extern "C" int rb3b_index_from_plain_dev(rb3b_index_t *x, int64_t len, const uint8_t *d_bwt)
 {
 	TRY(rb3b_ensure_init());
