@@ -214,6 +214,25 @@ __global__ void k_dir_scatter(int64_t nb, const uint64_t *__restrict__ bstart, i
 		for (j = (bstart[nb] + ((1ULL << shift) - 1)) >> shift; j < (uint64_t)n_dir; ++j) dir[j] = (uint32_t)b;
 }
 
+/* tmp[j] = block containing position j << shift; build the 8-B cells described in rb3b_internal.cuh */
+__global__ void k_dir_pack(int64_t n_dir, const uint32_t *__restrict__ tmp, const uint64_t *__restrict__ bstart, int shift, uint64_t *__restrict__ dir)
+{
+	int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n_dir) return;
+	uint32_t b0 = tmp[j], b1 = j + 1 < n_dir ? tmp[j + 1] : b0;
+	uint64_t lo = (uint64_t)j << shift, hi = (uint64_t)(j + 1) << shift;
+	uint32_t inside = b1 - b0; /* block starts in (lo, hi) */
+	if (inside && bstart[b1] == hi) --inside;
+	uint64_t cell = b0;
+	if (inside == 0) cell |= (uint64_t)RB3B_DIR_NONE << 32;
+	else {
+		uint64_t off = bstart[b0 + 1] - lo;
+		if (inside == 1 && off < RB3B_DIR_NONE) cell |= off << 32;
+		else cell |= 1ULL << 63;
+	}
+	dir[j] = cell;
+}
+
 int rb3b_index_finalize(rb3b_index_s *x)
 {
 	int64_t nb = x->n_blocks;
@@ -222,8 +241,8 @@ int rb3b_index_finalize(rb3b_index_s *x)
 	x->bytes = 0;
 	if (nb == 0) { x->n_dir = 0; x->dir_shift = 0; return RB3B_OK; }
 	DBuf<int64_t> cnt, ex;
-	DBuf<uint64_t> bstart;
-	DBuf<uint32_t> dir;
+	DBuf<uint64_t> bstart, dir;
+	DBuf<uint32_t> tmp;
 	int64_t m = (nb + 1) * RB3B_ASIZE, tot[RB3B_ASIZE], base[RB3B_ASIZE];
 	TRY(cnt.alloc(m)); TRY(ex.alloc(m)); TRY(bstart.alloc(nb + 1));
 	k_blk_count<<<nblk(nb + 1, 128), 128, 0, rb3b_stream>>>(nb, x->blocks, cnt.p); CKK();
@@ -240,20 +259,21 @@ int rb3b_index_finalize(rb3b_index_s *x)
 	}
 	x->n = x->acc[RB3B_ASIZE];
 	if (x->n >= (1LL << 42)) return rb3b_fail(RB3B_EINVAL, "index longer than 2^42 symbols is not supported by the 42-bit block headers");
-	/* directory: about four cells per block */
+	/* directory: two to four cells per block */
 	int shift = 0;
-	while (shift < 40 && (x->n >> (shift + 1)) >= nb * 4) ++shift;
+	while (shift < 40 && (x->n >> (shift + 1)) >= nb * 2) ++shift;
 	x->dir_shift = shift;
 	x->n_dir = (x->n >> shift) + 2;
-	TRY(dir.alloc(x->n_dir));
-	CK(cudaMemsetAsync(dir.p, 0, x->n_dir * 4, rb3b_stream));
-	k_dir_scatter<<<nblk(nb, TPB), TPB, 0, rb3b_stream>>>(nb, bstart.p, shift, dir.p, x->n_dir); CKK();
-	TRY(scan_max_u32(dir.p, x->n_dir));
+	TRY(tmp.alloc(x->n_dir)); TRY(dir.alloc(x->n_dir));
+	CK(cudaMemsetAsync(tmp.p, 0, x->n_dir * 4, rb3b_stream));
+	k_dir_scatter<<<nblk(nb, TPB), TPB, 0, rb3b_stream>>>(nb, bstart.p, shift, tmp.p, x->n_dir); CKK();
+	TRY(scan_max_u32(tmp.p, x->n_dir));
+	k_dir_pack<<<nblk(x->n_dir, TPB), TPB, 0, rb3b_stream>>>(x->n_dir, tmp.p, bstart.p, shift, dir.p); CKK();
 	if (x->bstart) cudaFreeAsync(x->bstart, rb3b_stream);
 	if (x->dir) cudaFreeAsync(x->dir, rb3b_stream);
 	x->bstart = bstart.take();
 	x->dir = dir.take();
-	x->bytes = (size_t)nb * 128 + (size_t)(nb + 1) * 8 + (size_t)x->n_dir * 4;
+	x->bytes = (size_t)nb * 128 + (size_t)(nb + 1) * 8 + (size_t)x->n_dir * 8;
 	rb3b_stat_set("n_blocks", nb);
 	rb3b_stat_set("dir_shift", shift);
 	return RB3B_OK;
@@ -313,11 +333,11 @@ int rb3b_export_runs_dev(const rb3b_index_s *x, DBuf<uint8_t> &sym, DBuf<int64_t
 /* batched rank kernels                                                 */
 /* ------------------------------------------------------------------ */
 
-/* rank1a: all six counts and the symbol at k; one 8-lane group per query */
+/* rank1a (mr_rank1a / rld_rank1a contract): all six counts and the symbol at k; one 8-lane group per query */
 __global__ void __launch_bounds__(TPB) k_rank1a(DevIndex x, int64_t nq, const int64_t *__restrict__ k_, int64_t *__restrict__ ok, int8_t *__restrict__ sym)
 {
-	const unsigned gmask = rb3b_gmask();
-	const int gl = threadIdx.x & 7, gbase = threadIdx.x & 24;
+	typedef Grp<8> G8;
+	const int gl = G8::lane();
 	int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3, ng = ((int64_t)gridDim.x * blockDim.x) >> 3;
 	for (int64_t q = g; q < nq; q += ng) {
 		int64_t k = k_[q];
@@ -326,52 +346,42 @@ __global__ void __launch_bounds__(TPB) k_rank1a(DevIndex x, int64_t nq, const in
 			if (gl == 0) sym[q] = -1;
 			continue;
 		}
-		int64_t b = rb3b_locate(x, k, gl, gmask);
-		uint4 v = __ldg(x.blocks + b * 8 + gl);
-		BlkLane B;
-		rb3b_decode(v, gl, gmask, B);
-		uint32_t off = (uint32_t)((uint64_t)k - B.start);
-		bool mine = off >= B.pre && off < B.pre + B.tot;  /* the lane whose entries cover position k */
-		uint32_t rem = off > B.pre ? min(off - B.pre, B.tot) : 0;
-		uint32_t c[RB3B_ASIZE] = {0, 0, 0, 0, 0, 0};
-		int sk = -1;
+		uint4 v[1];
+		G8::load(x, G8::locate(x, k), v);
+		/* B[k] = the symbol whose count grows between k and k+1 */
+		int64_t mine = 0, next = 0;
 #pragma unroll
-		for (int j = 0; j < 8; ++j) {
-			uint32_t take = min(B.len[j], rem);
-			if (mine && sk < 0 && rem < B.len[j]) sk = (int)B.sym[j];
-#pragma unroll
-			for (int a = 0; a < RB3B_ASIZE; ++a) c[a] += B.sym[j] == (uint32_t)a ? take : 0;
-			rem -= take;
+		for (int a = 0; a < RB3B_ASIZE; ++a) {
+			int64_t r0 = G8::count(v, k, a), r1 = G8::count(v, k + 1, a);
+			if (gl == a) { mine = r0; next = r1; }
 		}
-#pragma unroll
-		for (int a = 0; a < RB3B_ASIZE; ++a)
-#pragma unroll
-			for (int d = RB3B_GROUP / 2; d > 0; d >>= 1) c[a] += __shfl_xor_sync(gmask, c[a], d, RB3B_GROUP);
-		unsigned who = __ballot_sync(gmask, mine) & gmask;
-		sk = __shfl_sync(gmask, sk, who ? __ffs(who) - 1 : gbase);
-		/* header counts live in lanes 0 and 1 */
-		uint64_t h0 = __shfl_sync(gmask, B.c0, gbase + (gl >= 3)), h1 = __shfl_sync(gmask, B.c1, gbase + (gl >= 3)), h2 = __shfl_sync(gmask, B.c2, gbase + (gl >= 3));
-		if (gl < RB3B_ASIZE) {
-			int a3 = gl % 3;
-			uint64_t h = a3 == 0 ? h0 : a3 == 1 ? h1 : h2;
-			uint32_t cc = gl == 0 ? c[0] : gl == 1 ? c[1] : gl == 2 ? c[2] : gl == 3 ? c[3] : gl == 4 ? c[4] : c[5];
-			ok[q * RB3B_ASIZE + gl] = (int64_t)(h + cc);
-		}
-		if (gl == 0) sym[q] = (int8_t)sk;
+		unsigned grew = __ballot_sync(G8::mask(), gl < RB3B_ASIZE && next != mine) >> G8::base();
+		if (gl < RB3B_ASIZE) ok[q * RB3B_ASIZE + gl] = mine;
+		if (gl == 0) sym[q] = (int8_t)(__ffs(grew) - 1);
 	}
 }
 
 /* LF flavour used by the merge: out = C[c] + rank(c,k); 144 algorithmic bytes per query */
+template<int G>
 __global__ void __launch_bounds__(TPB) k_lf(DevIndex x, int64_t nq, const int64_t *__restrict__ k_, const uint8_t *__restrict__ c_, int64_t *__restrict__ out)
 {
-	const int gl = threadIdx.x & 7;
-	int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3, ng = ((int64_t)gridDim.x * blockDim.x) >> 3;
+	const int gl = Grp<G>::lane();
+	int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G, ng = ((int64_t)gridDim.x * blockDim.x) / G;
 	for (int64_t q = g; q < nq; q += ng) {
 		int64_t k = k_[q];
 		int c = c_[q];
-		int64_t r = x.acc[c] + rb3b_rank_c(x, k, c);
+		int64_t r = x.acc[c] + Grp<G>::rank(x, k, c);
 		if (gl == 0) out[q] = r;
 	}
+}
+
+template<int G> static int launch_lf(const rb3b_index_s *x, int64_t nq, const int64_t *d_k, const uint8_t *d_c, int64_t *d_out, int n_sm)
+{
+	int occ = 4;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lf<G>, TPB, 0);
+	int64_t want = (nq * G + TPB - 1) / TPB, cap = (int64_t)n_sm * (occ > 0 ? occ : 4);
+	k_lf<G><<<(unsigned)(want < cap ? want : cap), TPB, 0, rb3b_stream>>>(rb3b_dev_view(x), nq, d_k, d_c, d_out); CKK();
+	return RB3B_OK;
 }
 
 /* ------------------------------------------------------------------ */
@@ -443,6 +453,11 @@ extern "C" int rb3b_rank1a_dev(const rb3b_index_t *x, int64_t nq, const int64_t 
 	TRY(rb3b_ensure_init());
 	if (nq <= 0) return RB3B_OK;
 	int64_t want = (nq * RB3B_GROUP + TPB - 1) / TPB, cap = (int64_t)n_sm() * 8 * 4;
+	if (x->n_blocks == 0) { /* empty index: every count is zero (mrope.c:89-93 with zero totals) */
+		CK(cudaMemsetAsync(d_ok, 0, nq * RB3B_ASIZE * 8, rb3b_stream));
+		CK(cudaMemsetAsync(d_sym, 0xff, nq, rb3b_stream));
+		return RB3B_OK;
+	}
 	k_rank1a<<<(unsigned)(want < cap ? want : cap), TPB, 0, rb3b_stream>>>(rb3b_dev_view(x), nq, d_k, d_ok, d_sym); CKK();
 	return RB3B_OK;
 }
@@ -464,14 +479,16 @@ extern "C" int rb3b_rank1a(const rb3b_index_t *x, int64_t nq, const int64_t *k, 
 int rb3b_lf_tma_launch(const rb3b_index_s *x, int64_t nq, const int64_t *d_k, const uint8_t *d_c, int64_t *d_out); /* rb3b_rank_tma.cu */
 
 extern "C" int rb3b_lf_dev(const rb3b_index_t *x, int64_t nq, const int64_t *d_k, const uint8_t *d_c, int64_t *d_out, int variant)
-{
+{ /* variant: 0 default, 1 cp.async.bulk staged, 2/4/8 lanes per query */
 	TRY(rb3b_ensure_init());
 	if (nq <= 0) return RB3B_OK;
 	if (x->n_blocks == 0) return rb3b_fail(RB3B_EINVAL, "empty index");
 	if (variant == 1) return rb3b_lf_tma_launch(x, nq, d_k, d_c, d_out);
-	int64_t want = (nq * RB3B_GROUP + TPB - 1) / TPB, cap = (int64_t)n_sm() * 8 * 8;
-	k_lf<<<(unsigned)(want < cap ? want : cap), TPB, 0, rb3b_stream>>>(rb3b_dev_view(x), nq, d_k, d_c, d_out); CKK();
-	return RB3B_OK;
+	if (variant == 0) variant = (int)rb3b_rank_variant ? (int)rb3b_rank_variant : 4;
+	if (variant == 2) return launch_lf<2>(x, nq, d_k, d_c, d_out, n_sm());
+	if (variant == 4) return launch_lf<4>(x, nq, d_k, d_c, d_out, n_sm());
+	if (variant == 8) return launch_lf<8>(x, nq, d_k, d_c, d_out, n_sm());
+	return rb3b_fail(RB3B_EINVAL, "unknown rank variant %d", variant);
 }
 
 extern "C" int64_t rb3b_get_acc(const rb3b_index_t *x, int64_t acc[RB3B_ASIZE + 1])

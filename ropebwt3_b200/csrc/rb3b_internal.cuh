@@ -10,11 +10,15 @@
  *       quad 2-7 48 run entries of 16 bit:  sym:3 | big:1 | val:12
  *                length = val (big=0) or val<<12 (big=1); val==0 -> padding
  *   bstart[b]  absolute position of the first symbol of block b (bstart[nb] = n)
- *   dir[j]     index of the block containing position j << dir_shift
+ *   dir[j]     8-B cell for positions [j << dir_shift, (j+1) << dir_shift):
+ *                bits 0-31  b0 = block containing the first position of the cell
+ *                bits 32-62 off = offset in the cell at which block b0+1 starts
+ *                           (0x7fffffff: no block starts inside the cell)
+ *                bit 63     more than one block starts inside: search bstart[]
  *
- * One rank query therefore touches one dir sector, (sometimes) one bstart
- * sector and exactly one 128-B block, which an 8-lane group reads with a single
- * coalesced 16-B-per-lane load and reduces with shuffles.
+ * One rank query therefore touches one dir cell and exactly one 128-B block
+ * (plus, rarely, a few bstart entries), which a group of G = 2, 4 or 8 lanes
+ * reads with 16-B-per-lane loads and reduces with shuffles.
  */
 #ifndef RB3B_INTERNAL_CUH
 #define RB3B_INTERNAL_CUH
@@ -38,7 +42,7 @@ struct rb3b_index_s {
 	int64_t n_blocks, n_entries;
 	uint4 *blocks;                /* n_blocks * 8 quads */
 	uint64_t *bstart;             /* n_blocks + 1 */
-	uint32_t *dir;                /* n_dir */
+	uint64_t *dir;                /* n_dir cells: b0 | off << 32 | multi << 63 */
 	int64_t n_dir;
 	int dir_shift;
 	size_t bytes;
@@ -48,7 +52,7 @@ struct rb3b_index_s {
 struct DevIndex {
 	const uint4 *blocks;
 	const uint64_t *bstart;
-	const uint32_t *dir;
+	const uint64_t *dir;
 	int64_t n, n_blocks;
 	int dir_shift;
 	int64_t tot[RB3B_ASIZE];
@@ -84,6 +88,13 @@ void rb3b_tflush(void);
 #define CKK() do { ++rb3b_n_launch; CK(cudaGetLastError()); } while (0)   /* after every launch of one of OUR kernels */
 #define TRY(call) do { int r_ = (call); if (r_ != RB3B_OK) return r_; } while (0)
 
+static inline size_t rb3b_round_cap(size_t bytes)
+{
+	size_t c = 1 << 16;
+	while (c < bytes) c += (c >> 2) & ~(size_t)255;
+	return c;
+}
+
 /* stream-ordered scratch buffer */
 template<typename T> struct DBuf {
 	T *p; size_t n;
@@ -92,7 +103,8 @@ template<typename T> struct DBuf {
 	int alloc(size_t n_) {
 		release();
 		n = n_;
-		cudaError_t e = cudaMallocAsync((void**)&p, (n ? n : 1) * sizeof(T), rb3b_stream);
+		/* sizes are quantised (x1.25 steps) so that the slightly larger buffers of the next merge reuse pool blocks */
+		cudaError_t e = cudaMallocAsync((void**)&p, rb3b_round_cap((n ? n : 1) * sizeof(T)), rb3b_stream);
 		if (e != cudaSuccess) { p = 0; return rb3b_fail(RB3B_ENOMEM, "cudaMallocAsync(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e)); }
 		return RB3B_OK;
 	}
@@ -112,10 +124,7 @@ int rb3b_export_runs_dev(const rb3b_index_s *x, DBuf<uint8_t> &sym, DBuf<int64_t
 /* ---- device helpers ---- */
 #ifdef __CUDACC__
 
-__device__ __forceinline__ unsigned rb3b_gmask()
-{ /* mask of the 8-lane group this thread belongs to */
-	return 0xffu << (threadIdx.x & 24);
-}
+#define RB3B_DIR_NONE 0x7fffffffu
 
 __device__ __forceinline__ void rb3b_hdr_unpack(const uint4 v, uint64_t &c0, uint64_t &c1, uint64_t &c2)
 {
@@ -165,90 +174,123 @@ __device__ __forceinline__ int64_t rb3b_emit_run(uint4 *blocks, int64_t e, int c
 	return e;
 }
 
-/* block containing position k (0 <= k < n); executed by all lanes of a group with the same k */
-__device__ __forceinline__ int64_t rb3b_locate(const DevIndex &x, int64_t k, int gl, unsigned gmask)
-{
-	int64_t j = k >> x.dir_shift;
-	uint32_t b0 = __ldg(x.dir + j), b1 = __ldg(x.dir + j + 1);
-	while (b1 - b0 > RB3B_GROUP) {
-		uint32_t mid = b0 + (b1 - b0 + 1) / 2;
-		if (__ldg(x.bstart + mid) <= (uint64_t)k) b0 = mid; else b1 = mid - 1;
-	}
-	if (b1 > b0) {
-		uint32_t cand = b0 + 1 + gl;
-		bool le = cand <= b1 && __ldg(x.bstart + cand) <= (uint64_t)k;
-		b0 += __popc(__ballot_sync(gmask, le) & gmask);
-	}
-	return b0;
-}
+/*
+ * Rank machinery for a group of G lanes (G = 2, 4 or 8) working on one query.
+ * Lane gl holds quads [gl*NQ, (gl+1)*NQ) of the 128-B block, NQ = 8/G.
+ */
+template<int G> struct Grp {
+	static const int NQ = 8 / G;
+	__device__ __forceinline__ static int lane() { return threadIdx.x & (G - 1); }
+	__device__ __forceinline__ static int base() { return threadIdx.x & 31 & ~(G - 1); }
+	__device__ __forceinline__ static unsigned mask() { return ((1u << G) - 1u) << base(); }
 
-/* Decoded view of one block in the registers of an 8-lane group */
-struct BlkLane {
-	uint32_t len[8];
-	uint32_t sym[8];
-	uint32_t tot;      /* symbols held by this lane */
-	uint32_t pre;      /* symbols held by lower lanes of the group */
-	uint64_t start;    /* absolute position of the block */
-	uint64_t c0, c1, c2; /* header counts of this lane (lanes 0,1 only) */
-};
-
-__device__ __forceinline__ void rb3b_decode(const uint4 v, int gl, unsigned gmask, BlkLane &B)
-{
-	uint64_t hs = 0;
-	B.c0 = B.c1 = B.c2 = 0; B.tot = 0;
-	if (gl < 2) {
-		rb3b_hdr_unpack(v, B.c0, B.c1, B.c2);
-		hs = B.c0 + B.c1 + B.c2;
-#pragma unroll
-		for (int j = 0; j < 8; ++j) B.len[j] = 0, B.sym[j] = 7;
-	} else {
-		const uint32_t w[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-		for (int j = 0; j < 8; ++j) {
-			uint32_t e = (w[j >> 1] >> (16 * (j & 1))) & 0xffffu;
-			B.len[j] = rb3b_ent_len(e);
-			B.sym[j] = e >> 13;
-			B.tot += B.len[j];
+	/* block containing position k (0 <= k < n); all lanes of the group pass the same k */
+	__device__ __forceinline__ static int64_t locate(const DevIndex &x, int64_t k)
+	{
+		int64_t j = k >> x.dir_shift;
+		uint64_t cell = __ldg(x.dir + j);
+		uint32_t b0 = (uint32_t)cell, off = (uint32_t)(cell >> 32) & RB3B_DIR_NONE;
+		uint64_t in_cell = (uint64_t)k - ((uint64_t)j << x.dir_shift);
+		if ((int64_t)cell < 0) { /* rare: several block starts inside the cell */
+			uint32_t b1 = (uint32_t)__ldg(x.dir + j + 1);
+			while (b0 < b1) { /* last block in [b0,b1] whose start is <= k; same trip count for the whole group */
+				uint32_t mid = b0 + (b1 - b0 + 1) / 2;
+				if (__ldg(x.bstart + mid) <= (uint64_t)k) b0 = mid; else b1 = mid - 1;
+			}
+			return b0;
 		}
+		return (int64_t)b0 + (in_cell >= off ? 1 : 0);
 	}
-	int gbase = threadIdx.x & 24;
-	B.start = __shfl_sync(gmask, hs, gbase) + __shfl_sync(gmask, hs, gbase + 1);
-	uint32_t inc = B.tot;
-#pragma unroll
-	for (int d = 1; d < RB3B_GROUP; d <<= 1) {
-		uint32_t t = __shfl_up_sync(gmask, inc, d, RB3B_GROUP);
-		if (gl >= d) inc += t;
-	}
-	B.pre = inc - B.tot;
-}
 
-/* #c in [0,k) of the indexed BWT; all 8 lanes of the group call with identical (k,c) */
-__device__ __forceinline__ int64_t rb3b_rank_c(const DevIndex &x, int64_t k, int c)
-{
-	if (k >= x.n) return x.tot[c];
-	if (k <= 0) return 0;
-	const unsigned gmask = rb3b_gmask();
-	const int gl = threadIdx.x & 7, gbase = threadIdx.x & 24;
-	int64_t b = rb3b_locate(x, k, gl, gmask);
-	uint4 v = __ldg(x.blocks + b * 8 + gl);
-	BlkLane B;
-	rb3b_decode(v, gl, gmask, B);
-	int cc = c - 3 * gl;
-	uint64_t hc = (gl < 2 && cc >= 0 && cc < 3) ? (cc == 0 ? B.c0 : cc == 1 ? B.c1 : B.c2) : 0;
-	uint64_t base = __shfl_sync(gmask, hc, gbase + (c >= 3));
-	uint32_t off = (uint32_t)((uint64_t)k - B.start);
-	uint32_t rem = off > B.pre ? min(off - B.pre, B.tot) : 0;
-	uint32_t contrib = 0;
+	__device__ __forceinline__ static void load(const DevIndex &x, int64_t b, uint4 (&v)[NQ])
+	{
+		const uint4 *p = x.blocks + b * 8 + lane() * NQ;
 #pragma unroll
-	for (int j = 0; j < 8; ++j) {
-		uint32_t take = min(B.len[j], rem);
-		contrib += B.sym[j] == (uint32_t)c ? take : 0;
-		rem -= take;
+		for (int j = 0; j < NQ; ++j) v[j] = __ldg(p + j);
 	}
+
+	/* #c among the first (k - start of block) symbols of the block held in v, plus the header count of c */
+	__device__ __forceinline__ static int64_t count(const uint4 (&v)[NQ], int64_t k, int c)
+	{
+		const int gl = lane(), gb = base();
+		const unsigned gm = mask();
+		uint64_t hs = 0, hc = 0; /* sum of the header counts held by this lane; header count of symbol c */
+		if (G == 8) {
+			if (gl < 2) {
+				uint64_t a0, a1, a2;
+				rb3b_hdr_unpack(v[0], a0, a1, a2);
+				hs = a0 + a1 + a2;
+				int cc = c - 3 * gl;
+				hc = cc == 0 ? a0 : cc == 1 ? a1 : cc == 2 ? a2 : 0;
+			}
+		} else if (gl == 0) {
+			uint64_t a[6];
+			rb3b_hdr_unpack(v[0], a[0], a[1], a[2]);
+			rb3b_hdr_unpack(v[NQ > 1 ? 1 : 0], a[3], a[4], a[5]);
+			hs = a[0] + a[1] + a[2] + a[3] + a[4] + a[5];
+			hc = c == 0 ? a[0] : c == 1 ? a[1] : c == 2 ? a[2] : c == 3 ? a[3] : c == 4 ? a[4] : a[5];
+		}
+		uint64_t start = __shfl_sync(gm, hs, gb);
+		if (G == 8) start += __shfl_sync(gm, hs, gb + 1);
+		uint64_t basec = __shfl_sync(gm, hc, gb + ((G == 8 && c >= 3) ? 1 : 0));
+		/* entries */
+		uint32_t len[NQ * 8], tot = 0;
+		uint32_t isc = 0; /* bit i: entry i has symbol c */
 #pragma unroll
-	for (int d = RB3B_GROUP / 2; d > 0; d >>= 1) contrib += __shfl_xor_sync(gmask, contrib, d, RB3B_GROUP);
-	return (int64_t)(base + contrib);
-}
+		for (int j = 0; j < NQ; ++j) {
+			const bool ent = gl * NQ + j >= 2; /* quads 0,1 are the header */
+			const uint32_t w[4] = { v[j].x, v[j].y, v[j].z, v[j].w };
+#pragma unroll
+			for (int i = 0; i < 8; ++i) {
+				uint32_t e = (w[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+				uint32_t l = ent ? rb3b_ent_len(e) : 0;
+				len[j * 8 + i] = l;
+				isc |= ((e >> 13) == (uint32_t)c ? 1u : 0u) << (j * 8 + i);
+				tot += l;
+			}
+		}
+		uint32_t inc = tot;
+#pragma unroll
+		for (int d = 1; d < G; d <<= 1) {
+			uint32_t t = __shfl_up_sync(gm, inc, d, G);
+			if (gl >= d) inc += t;
+		}
+		uint32_t pre = inc - tot, off = (uint32_t)((uint64_t)k - start);
+		uint32_t rem = off > pre ? min(off - pre, tot) : 0, contrib = 0;
+#pragma unroll
+		for (int i = 0; i < NQ * 8; ++i) {
+			uint32_t take = min(len[i], rem);
+			contrib += (isc >> i & 1) ? take : 0;
+			rem -= take;
+		}
+#pragma unroll
+		for (int d = G / 2; d > 0; d >>= 1) contrib += __shfl_xor_sync(gm, contrib, d, G);
+		return (int64_t)(basec + contrib);
+	}
+
+	/* #c in [0,k) */
+	__device__ __forceinline__ static int64_t rank(const DevIndex &x, int64_t k, int c)
+	{
+		int64_t kk = k < x.n ? (k < 0 ? 0 : k) : x.n - 1;
+		uint4 v[NQ];
+		load(x, locate(x, kk), v);
+		int64_t r = count(v, kk, c);
+		return k < x.n ? r : x.tot[c];
+	}
+
+	/* two positions at once, same symbol: the two block fetches overlap and the instruction stream is the same
+	 * whether or not k1 == k2, which keeps the groups of a warp in lockstep during the LF walk */
+	__device__ __forceinline__ static void rank2(const DevIndex &x, int64_t k1, int64_t k2, int c, int64_t &r1, int64_t &r2)
+	{
+		int64_t q1 = k1 < x.n ? k1 : x.n - 1, q2 = k2 < x.n ? k2 : x.n - 1;
+		int64_t b1 = locate(x, q1), b2 = locate(x, q2);
+		uint4 v1[NQ], v2[NQ];
+		load(x, b1, v1); load(x, b2, v2);
+		int64_t t = x.tot[c];
+		r1 = count(v1, q1, c); r2 = count(v2, q2, c);
+		r1 = k1 < x.n ? r1 : t; r2 = k2 < x.n ? r2 : t;
+	}
+};
 
 #endif /* __CUDACC__ */
 #endif

@@ -43,8 +43,12 @@ static int n_sm(void)
 
 /* ------------------------------------------------------------------ */
 /* LF mapping of the batch (fm-index.c:207-216)                         */
-/* lfb[i] = LF_B(i) << 4 | mark << 3 | B[i]                             */
+/* lfb[i] = LF_B(i) << 5 | coarse mark << 4 | fine mark << 3 | B[i]     */
 /* ------------------------------------------------------------------ */
+
+#define LFB_SHIFT 5
+#define LFB_FINE 8u
+#define LFB_COARSE 16u
 
 __global__ void __launch_bounds__(TPB) k_prep_count(int64_t len, const uint8_t *__restrict__ bwt, int64_t nt, int64_t *__restrict__ tcnt, int *__restrict__ bad)
 {
@@ -76,7 +80,7 @@ __global__ void __launch_bounds__(TPB) k_prep_count(int64_t len, const uint8_t *
 struct Acc7 { int64_t v[RB3B_ASIZE + 1]; };
 
 __global__ void __launch_bounds__(TPB) k_prep_lf(int64_t len, const uint8_t *__restrict__ bwt, int64_t nt, const int64_t *__restrict__ tex,
-                                                  Acc7 accB, int64_t seg_len, uint64_t *__restrict__ lfb)
+                                                  Acc7 accB, int64_t fine_len, uint64_t *__restrict__ lfb)
 {
 	typedef cub::BlockScan<uint32_t, TPB> Scan;
 	__shared__ typename Scan::TempStorage tmp[3];
@@ -102,9 +106,73 @@ __global__ void __launch_bounds__(TPB) k_prep_lf(int64_t len, const uint8_t *__r
 		int64_t lf = 0;
 #pragma unroll
 		for (int b = 0; b < RB3B_ASIZE; ++b) if (a == b) lf = base[b]++;
-		uint64_t mark = (i < accB.v[1] || i % seg_len == 0) ? 8u : 0u;
-		lfb[i] = (uint64_t)lf << 4 | mark | (uint64_t)a;
+		uint64_t mark = (i < accB.v[1] || i % fine_len == 0) ? LFB_FINE : 0u;
+		lfb[i] = (uint64_t)lf << LFB_SHIFT | mark | (uint64_t)a;
 	}
+}
+
+/* ------------------------------------------------------------------ */
+/* balanced segmentation of the chains                                  */
+/* ------------------------------------------------------------------ */
+
+/* Fine marks: the sentinel rows (fine node = row) and every fine_len-th row.  They cut the chains into short
+ * pieces of random length; walking them (LF_B only, no rank) and list-ranking the pieces gives every fine
+ * mark its distance to the start of its sequence, from which evenly spaced coarse marks are chosen. */
+struct Fine {
+	int64_t n_fine, n_seq, fine_len, m0;
+	__host__ __device__ int64_t row(int64_t f) const { return f < n_seq ? f : (m0 + (f - n_seq)) * fine_len; }
+	__host__ __device__ int64_t of_row(int64_t r) const { return r < n_seq ? r : n_seq + (r / fine_len - m0); }
+};
+
+__global__ void k_fine_walk(Fine F, const uint64_t *__restrict__ lfb, int64_t *__restrict__ succ, int64_t *__restrict__ dist)
+{
+	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (f >= F.n_fine) return;
+	int64_t kb = F.row(f), n = 0, nx = -1;
+	uint64_t x = __ldg(lfb + kb);
+	for (;;) {
+		++n;
+		if ((x & 7) == 0) break;
+		kb = (int64_t)(x >> LFB_SHIFT);
+		x = __ldg(lfb + kb);
+		if (x & LFB_FINE) { nx = F.of_row(kb); break; }
+	}
+	succ[f] = nx; dist[f] = n;
+}
+
+/* Wyllie pointer jumping: after ceil(log2 n) rounds dist[f] = #rows from fine mark f to the start of its sequence */
+__global__ void k_list_rank(int64_t n, const int64_t *__restrict__ succ_in, const int64_t *__restrict__ dist_in, int64_t *__restrict__ succ_out, int64_t *__restrict__ dist_out)
+{
+	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (f >= n) return;
+	int64_t s = succ_in[f], d = dist_in[f];
+	if (s >= 0) { d += dist_in[s]; s = succ_in[s]; }
+	succ_out[f] = s; dist_out[f] = d;
+}
+
+/* a fine mark becomes a coarse mark when the walk crosses a multiple of seg_len on the way to it */
+__global__ void k_coarse_flag(Fine F, int64_t seg_len, const int64_t *__restrict__ succ, const int64_t *__restrict__ piece, const int64_t *__restrict__ to_end, int64_t *__restrict__ flag)
+{
+	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (f >= F.n_fine) return;
+	if (f < F.n_seq) flag[f] = 1;
+	int64_t s = succ[f];
+	if (s >= 0) {
+		int64_t r = to_end[f], rs = r - piece[f];
+		if (r / seg_len != rs / seg_len) flag[s] = 1;
+	}
+}
+
+__global__ void k_coarse_fill(Fine F, const int64_t *__restrict__ flag, const int64_t *__restrict__ sid, int64_t *__restrict__ seg_row, int32_t *__restrict__ cmap, uint64_t *__restrict__ lfb)
+{
+	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (f >= F.n_fine) return;
+	if (flag[f]) {
+		int64_t r = F.row(f);
+		seg_row[sid[f]] = r;
+		cmap[f] = (int32_t)sid[f];
+		lfb[r] |= LFB_COARSE;
+	} else cmap[f] = -1;
 }
 
 /* ------------------------------------------------------------------ */
@@ -112,28 +180,30 @@ __global__ void __launch_bounds__(TPB) k_prep_lf(int64_t len, const uint8_t *__r
 /* ------------------------------------------------------------------ */
 
 struct Segs {
-	int64_t n_seg, n_seq, seg_len, m0;  /* sampled segment j (>= n_seq) starts at row (m0 + j - n_seq) * seg_len */
+	int64_t n_seg, n_seq;
+	const int64_t *row;   /* first row of the segment (a coarse mark) */
+	const int32_t *cmap;  /* fine node -> segment, -1 if the fine mark is not a coarse mark */
 	int64_t *d;       /* #rows at the start of the segment that are still unresolved */
 	int64_t *len;     /* #rows of the segment */
 	int64_t *succ;    /* segment entered after the last row, or -1 at the start of a sequence */
 	int64_t *arr_lo, *arr_hi; /* bracket with which the walk arrived at succ's first row */
 };
 
-__device__ __forceinline__ int64_t seg_row(const Segs &S, int64_t s) { return s < S.n_seq ? s : (S.m0 + (s - S.n_seq)) * S.seg_len; }
-__device__ __forceinline__ int64_t seg_of_row(const Segs &S, int64_t r) { return r < S.n_seq ? r : S.n_seq + (r / S.seg_len - S.m0); }
+#define WALK_G 8
+typedef Grp<WALK_G> WG;
 
 /* round 1: every segment walks from its mark to the next mark */
-__global__ void __launch_bounds__(TPB) k_walk_first(DevIndex A, Acc7 accB, Segs S, const uint64_t *__restrict__ lfb, int64_t *__restrict__ ka, int64_t *next_seg)
+__global__ void __launch_bounds__(TPB) k_walk_first(DevIndex A, Acc7 accB, Segs S, Fine F, const uint64_t *__restrict__ lfb, int64_t *__restrict__ ka, int64_t *next_seg)
 {
-	const int gl = threadIdx.x & 7, gbase = threadIdx.x & 24;
-	const unsigned gmask = rb3b_gmask();
+	const int gl = WG::lane(), gbase = WG::base();
+	const unsigned gmask = WG::mask();
 	for (;;) {
 		int64_t s = 0;
 		if (gl == 0) s = (int64_t)atomicAdd((unsigned long long*)next_seg, 1ULL);
 		s = __shfl_sync(gmask, s, gbase);
 		if (s >= S.n_seg) break;
-		int64_t kb = seg_row(S, s), lo, hi, d = 0, len = 0, succ = -1;
-		if (s < S.n_seq) lo = hi = A.acc[1]; /* new sentinels sort after all old ones, fm-index.c:164 */
+		int64_t kb = S.row[s], lo, hi, d = 0, len = 0, succ = -1;
+		if (kb < S.n_seq) lo = hi = A.acc[1]; /* new sentinels sort after all old ones, fm-index.c:164 */
 		else {
 			int c0 = 1;
 			while (c0 < RB3B_ASIZE - 1 && kb >= accB.v[c0 + 1]) ++c0;
@@ -146,14 +216,12 @@ __global__ void __launch_bounds__(TPB) k_walk_first(DevIndex A, Acc7 accB, Segs 
 			else ++d;
 			++len;
 			if (c == 0) break; /* reached the first symbol of the sequence, fm-index.c:170 */
-			kb = (int64_t)(x >> 4);
+			kb = (int64_t)(x >> LFB_SHIFT);
 			x = __ldg(lfb + kb); /* the B chain does not depend on A: fetch one step ahead */
-			if (lo == hi) lo = hi = A.acc[c] + rb3b_rank_c(A, lo, c);
-			else {
-				lo = A.acc[c] + rb3b_rank_c(A, lo, c);
-				hi = A.acc[c] + rb3b_rank_c(A, hi, c);
-			}
-			if (x & 8) { succ = seg_of_row(S, kb); break; }
+			int64_t r1, r2;
+			WG::rank2(A, lo, hi, c, r1, r2);
+			lo = A.acc[c] + r1; hi = A.acc[c] + r2;
+			if (x & LFB_COARSE) { succ = S.cmap[F.of_row(kb)]; break; }
 		}
 		if (gl == 0) { S.d[s] = d; S.len[s] = len; S.succ[s] = succ; S.arr_lo[s] = lo; S.arr_hi[s] = hi; }
 	}
@@ -176,22 +244,22 @@ __global__ void __launch_bounds__(TPB) k_walk_fix(DevIndex A, Segs S, const uint
                                                    const int64_t *__restrict__ wl_seg, const int64_t *__restrict__ wl_val, int64_t *next_item,
                                                    int64_t *__restrict__ nx_seg, int64_t *__restrict__ nx_val, unsigned long long *nx_n)
 {
-	const int gl = threadIdx.x & 7, gbase = threadIdx.x & 24;
-	const unsigned gmask = rb3b_gmask();
+	const int gl = WG::lane(), gbase = WG::base();
+	const unsigned gmask = WG::mask();
 	for (;;) {
 		int64_t it = 0;
 		if (gl == 0) it = (int64_t)atomicAdd((unsigned long long*)next_item, 1ULL);
 		it = __shfl_sync(gmask, it, gbase);
 		if (it >= n_items) break;
-		int64_t t = wl_seg[it], v = wl_val[it], kb = seg_row(S, t), d = S.d[t], len = S.len[t];
+		int64_t t = wl_seg[it], v = wl_val[it], kb = S.row[t], d = S.d[t], len = S.len[t];
 		uint64_t x = __ldg(lfb + kb);
 		for (int64_t i = 0; i < d; ++i) {
 			int c = (int)(x & 7);
 			if (gl == 0) ka[kb] = v;
 			if (c == 0) break;
-			kb = (int64_t)(x >> 4);
+			kb = (int64_t)(x >> LFB_SHIFT);
 			x = __ldg(lfb + kb);
-			v = A.acc[c] + rb3b_rank_c(A, v, c);
+			v = A.acc[c] + WG::rank(A, v, c);
 		}
 		if (gl == 0) {
 			S.d[t] = 0;
@@ -233,6 +301,8 @@ __global__ void k_check_monotone(int64_t len, const int64_t *__restrict__ ka, in
 	if (v < 0 || v > nA || (i > 0 && ka[i - 1] > v)) *bad = 1;
 }
 
+int64_t rb3b_get_param(const char *key, int64_t dflt); /* rb3b_runtime.cu */
+
 /* interleave positions of the batch in device memory: ka[len], accB */
 static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, DBuf<int64_t> &ka, int64_t accB[RB3B_ASIZE + 1])
 {
@@ -262,36 +332,63 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	for (int a = 0; a < RB3B_ASIZE; ++a) acc.v[a + 1] = acc.v[a] + (tot[a] - base[a]);
 	memcpy(accB, acc.v, sizeof(acc.v));
 	if (acc.v[1] <= 0) return rb3b_fail(RB3B_EINVAL, "batch BWT holds no sentinel");
+	/* fine marks, their list ranks, coarse marks */
 	int64_t seg_len = rb3b_seg_len;
-	k_prep_lf<<<(unsigned)nt, TPB, 0, rb3b_stream>>>(len, d_bwt, nt, tex.p, acc, seg_len, lfb.p); CKK();
-	rb3b_toc(T_PREP);
+	Fine F;
+	F.n_seq = acc.v[1];
+	F.fine_len = rb3b_get_param("fine_len", 64);
+	if (F.fine_len > seg_len) F.fine_len = seg_len;
+	if (F.fine_len < 1) F.fine_len = 1;
+	F.m0 = (F.n_seq + F.fine_len - 1) / F.fine_len;
+	int64_t n_samp = (len - 1) / F.fine_len - F.m0 + 1;
+	F.n_fine = F.n_seq + (n_samp > 0 ? n_samp : 0);
+	k_prep_lf<<<(unsigned)nt, TPB, 0, rb3b_stream>>>(len, d_bwt, nt, tex.p, acc, F.fine_len, lfb.p); CKK();
+	DBuf<int64_t> fn; /* succ, piece, 2 x (succ, dist) ping-pong, flag, sid */
+	DBuf<int32_t> cmap;
+	TRY(fn.alloc(F.n_fine * 8)); TRY(cmap.alloc(F.n_fine));
+	int64_t *f_succ = fn.p, *f_piece = fn.p + F.n_fine, *pp[2][2] = { { fn.p + 2 * F.n_fine, fn.p + 3 * F.n_fine }, { fn.p + 4 * F.n_fine, fn.p + 5 * F.n_fine } };
+	int64_t *f_flag = fn.p + 6 * F.n_fine, *f_sid = fn.p + 7 * F.n_fine;
+	k_fine_walk<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, lfb.p, f_succ, f_piece); CKK();
+	const int64_t *cs = f_succ, *cd = f_piece;
+	int cur = 0;
+	for (int64_t span = 1; span < F.n_fine; span <<= 1) {
+		k_list_rank<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F.n_fine, cs, cd, pp[cur][0], pp[cur][1]); CKK();
+		cs = pp[cur][0]; cd = pp[cur][1]; cur ^= 1;
+	}
+	CK(cudaMemsetAsync(f_flag, 0, F.n_fine * 8, rb3b_stream));
+	k_coarse_flag<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, seg_len, f_succ, f_piece, cd, f_flag); CKK();
+	TRY(rb3b_scan_excl_i64(f_flag, f_sid, F.n_fine));
+	int64_t last[2];
+	CK(cudaMemcpyAsync(&last[0], f_sid + F.n_fine - 1, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+	CK(cudaMemcpyAsync(&last[1], f_flag + F.n_fine - 1, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+	CK(cudaStreamSynchronize(rb3b_stream));
 	/* segments */
 	Segs S;
-	S.n_seq = acc.v[1]; S.seg_len = seg_len;
-	S.m0 = (S.n_seq + seg_len - 1) / seg_len;
-	int64_t n_samp = (len - 1) / seg_len - S.m0 + 1;
-	if (n_samp < 0) n_samp = 0;
-	S.n_seg = S.n_seq + n_samp;
+	S.n_seq = F.n_seq;
+	S.n_seg = last[0] + last[1];
 	DBuf<int64_t> seg, wl, ctr;
-	TRY(seg.alloc(S.n_seg * 5)); TRY(wl.alloc(S.n_seg * 4)); TRY(ctr.alloc(8)); TRY(ka.alloc(len));
+	TRY(seg.alloc(S.n_seg * 6)); TRY(wl.alloc(S.n_seg * 4)); TRY(ctr.alloc(8)); TRY(ka.alloc(len));
 	S.d = seg.p; S.len = seg.p + S.n_seg; S.succ = seg.p + 2 * S.n_seg; S.arr_lo = seg.p + 3 * S.n_seg; S.arr_hi = seg.p + 4 * S.n_seg;
+	S.row = seg.p + 5 * S.n_seg; S.cmap = cmap.p;
+	k_coarse_fill<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, f_flag, f_sid, seg.p + 5 * S.n_seg, cmap.p, lfb.p); CKK();
+	rb3b_toc(T_PREP);
 	CK(cudaMemsetAsync(ctr.p, 0, 8 * 8, rb3b_stream));
 	CK(cudaMemsetAsync(ka.p, 0xff, len * 8, rb3b_stream));
 	DevIndex dA = rb3b_dev_view(A);
-	int64_t groups = S.n_seg, want = (groups * RB3B_GROUP + TPB - 1) / TPB, cap = (int64_t)n_sm() * 8;
+	int64_t groups = S.n_seg, want = (groups * WALK_G + TPB - 1) / TPB, cap = (int64_t)n_sm() * 8;
 	rb3b_tic(T_WALK1);
-	k_walk_first<<<(unsigned)(want < cap ? want : cap), TPB, 0, rb3b_stream>>>(dA, acc, S, lfb.p, ka.p, ctr.p); CKK();
+	k_walk_first<<<(unsigned)(want < cap ? want : cap), TPB, 0, rb3b_stream>>>(dA, acc, S, F, lfb.p, ka.p, ctr.p); CKK();
 	rb3b_toc(T_WALK1);
 	int64_t *wl_seg[2] = { wl.p, wl.p + 2 * S.n_seg }, *wl_val[2] = { wl.p + S.n_seg, wl.p + 3 * S.n_seg };
 	k_collect_first<<<nblk(S.n_seg, TPB), TPB, 0, rb3b_stream>>>(S, wl_seg[0], wl_val[0], (unsigned long long*)(ctr.p + 1)); CKK();
 	int64_t n_items = 0, rounds = 1, fix_rows = 0;
 	CK(cudaMemcpyAsync(&n_items, ctr.p + 1, 8, cudaMemcpyDeviceToHost, rb3b_stream));
 	CK(cudaStreamSynchronize(rb3b_stream));
-	int cur = 0;
+	cur = 0;
 	while (n_items > 0) {
 		/* ctr[2] = item cursor, ctr[3] = size of the next list */
 		CK(cudaMemsetAsync(ctr.p + 2, 0, 16, rb3b_stream));
-		want = (n_items * RB3B_GROUP + TPB - 1) / TPB;
+		want = (n_items * WALK_G + TPB - 1) / TPB;
 		rb3b_tic(T_WALKFIX);
 		k_walk_fix<<<(unsigned)(want < cap ? want : cap), TPB, 0, rb3b_stream>>>(dA, S, lfb.p, ka.p, n_items, wl_seg[cur], wl_val[cur], ctr.p + 2,
 			wl_seg[cur ^ 1], wl_val[cur ^ 1], (unsigned long long*)(ctr.p + 3)); CKK();
@@ -309,7 +406,9 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	CK(cudaStreamSynchronize(rb3b_stream));
 	rb3b_tflush();
 	rb3b_stat_set("n_segments", S.n_seg);
+	rb3b_stat_set("n_fine", F.n_fine);
 	rb3b_stat_set("fix_rounds", rounds - 1);
+	rb3b_stat_add("fix_rounds_total", rounds - 1);
 	rb3b_stat_set("fix_segments", fix_rows);
 	rb3b_stat_set("unresolved_rows", (int64_t)sums[0]);
 	if (sums[0] != 0 || (int64_t)sums[1] != len)
@@ -407,7 +506,7 @@ static int merge_phase(rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, const
 	int64_t n_ent = last[0] + last[1], nb2 = (n_ent + RB3B_ENT_PER_BLK - 1) / RB3B_ENT_PER_BLK;
 	if (nb2 >= (1LL << 32) - 16) return rb3b_fail(RB3B_EINVAL, "index too large for 32-bit block ids");
 	TRY(out.alloc(nb2 * 8));
-	CK(cudaMemsetAsync(out.p, 0, nb2 * 128, rb3b_stream));
+	CK(cudaMemsetAsync(out.p + (nb2 - 1) * 8, 0, 128, rb3b_stream)); /* padding of the last block; everything else is written */
 	k_merge<true><<<nblk(nb, 128), 128, 0, rb3b_stream>>>(nb, A->blocks, A->bstart, blo.p, d_ka, d_bwt, 0, eoff.p, out.p); CKK();
 	rb3b_toc(T_MERGE);
 	cudaFreeAsync(A->blocks, rb3b_stream);

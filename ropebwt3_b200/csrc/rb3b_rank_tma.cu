@@ -40,8 +40,9 @@ __global__ void __launch_bounds__(TPB) k_lf_tma(DevIndex x, int64_t nq, const in
 {
 	__shared__ __align__(128) uint4 stage[NGRP][NST][8];
 	__shared__ __align__(8) uint64_t bars[NGRP][NST];
-	const int gl = threadIdx.x & 7, gbase = threadIdx.x & 24, gi = threadIdx.x >> 3;
-	const unsigned gmask = rb3b_gmask();
+	typedef Grp<8> G8;
+	const int gl = G8::lane(), gi = threadIdx.x >> 3;
+	const unsigned gmask = G8::mask();
 	const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3, ng = ((int64_t)gridDim.x * blockDim.x) >> 3;
 	if (gl == 0) {
 #pragma unroll
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(TPB) k_lf_tma(DevIndex x, int64_t nq, const in
 			kq[s] = k_[q]; cq[s] = c_[q]; if (kq[s] < 0) kq[s] = 0; \
 			if (kq[s] >= x.n) kind[s] = 2; \
 			else { \
-				int64_t b_ = rb3b_locate(x, kq[s], gl, gmask); \
+				int64_t b_ = G8::locate(x, kq[s]); \
 				if (gl == 0) { \
 					uint32_t bar_ = smem_u32(&bars[gi][s]); \
 					mbar_expect_tx(bar_, 128); \
@@ -79,24 +80,11 @@ __global__ void __launch_bounds__(TPB) k_lf_tma(DevIndex x, int64_t nq, const in
 			else if (kind[s] == 1) {
 				mbar_wait(smem_u32(&bars[gi][s]), (parity >> s) & 1);
 				parity ^= 1u << s;
-				uint4 v = stage[gi][s][gl];
-				BlkLane B;
-				rb3b_decode(v, gl, gmask, B);
+				uint4 v[1];
+				v[0] = stage[gi][s][gl];
 				const int c = cq[s];
-				int cc = c - 3 * gl;
-				uint64_t hc = (gl < 2 && cc >= 0 && cc < 3) ? (cc == 0 ? B.c0 : cc == 1 ? B.c1 : B.c2) : 0;
-				uint64_t base = __shfl_sync(gmask, hc, gbase + (c >= 3));
-				uint32_t off = (uint32_t)((uint64_t)kq[s] - B.start);
-				uint32_t rem = off > B.pre ? min(off - B.pre, B.tot) : 0, contrib = 0;
-#pragma unroll
-				for (int j = 0; j < 8; ++j) {
-					uint32_t take = min(B.len[j], rem);
-					contrib += B.sym[j] == (uint32_t)c ? take : 0;
-					rem -= take;
-				}
-#pragma unroll
-				for (int d = RB3B_GROUP / 2; d > 0; d >>= 1) contrib += __shfl_xor_sync(gmask, contrib, d, RB3B_GROUP);
-				if (gl == 0) out[q] = x.acc[c] + (int64_t)(base + contrib);
+				int64_t r = G8::count(v, kq[s], c);
+				if (gl == 0) out[q] = x.acc[c] + r;
 			}
 			__syncwarp(gmask); /* every lane has read the stage before it is refilled */
 			ISSUE(s, q + (int64_t)NST * ng);

@@ -72,7 +72,7 @@ def test_from_plain_matches_runs(rb3, oracle, golden):
         rb3.Index.from_plain(np.array([1, 2, 6, 0], np.uint8))  # fm-index.c:125 asserts symbols < 6
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4, 8])
 def test_lf_dev(rb3, oracle, variant):
     import torch
     from ropebwt3_b200 import synth

@@ -21,7 +21,7 @@ def main():
     ap.add_argument("--queries", type=float, default=64e6)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--max-len", type=int, default=30)
-    ap.add_argument("--variants", default="0,1")
+    ap.add_argument("--variants", default="8,4,2,1")
     a = ap.parse_args()
     R.init(0)
     st = torch.cuda.Stream()
@@ -68,7 +68,7 @@ def main():
             assert torch.equal(ref, out), "variants disagree"
         ms = float(np.median(ts))
         gbs = nq * 144 / (ms / 1e3) / 1e9
-        print(json.dumps({"kernel": "k_lf" if v == 0 else "k_lf_tma", "variant": v, "index_bytes": idx.nbytes(), "index_symbols": n, "queries": nq,
+        print(json.dumps({"kernel": "k_lf_tma" if v == 1 else "k_lf<%d>" % v, "variant": v, "index_bytes": idx.nbytes(), "index_symbols": n, "queries": nq,
                           "ms": ms, "gqueries_per_s": nq / ms / 1e6, "achieved_GBps": gbs, "peak_GBps": peak, "frac": gbs / peak,
                           "bytes_per_query": 144}))
 
