@@ -127,9 +127,22 @@ __global__ void k_run_emit(int64_t n_runs, const uint8_t *__restrict__ sym, cons
 	if (len[r] > 0) rb3b_emit_run(blocks, eoff[r], sym[r], len[r]);
 }
 
+int rb3b_reserve(void **p, int64_t *cap, int64_t need, size_t elt)
+{
+	if (*p && *cap >= need) return RB3B_OK;
+	if (*p) cudaFreeAsync(*p, rb3b_stream);
+	*p = 0; *cap = 0;
+	int64_t want = need + need / 2 + 1024;
+	cudaError_t e = cudaMallocAsync(p, (size_t)want * elt, rb3b_stream);
+	if (e != cudaSuccess) { *p = 0; return rb3b_fail(RB3B_ENOMEM, "cudaMallocAsync(%lld bytes): %s", (long long)(want * (int64_t)elt), cudaGetErrorString(e)); }
+	*cap = want;
+	return RB3B_OK;
+}
+
 int rb3b_index_free_dev(rb3b_index_s *x)
 {
 	if (x->blocks) cudaFreeAsync(x->blocks, rb3b_stream);
+	if (x->spare) cudaFreeAsync(x->spare, rb3b_stream);
 	if (x->bstart) cudaFreeAsync(x->bstart, rb3b_stream);
 	if (x->dir) cudaFreeAsync(x->dir, rb3b_stream);
 	memset(x, 0, sizeof(*x));
@@ -140,7 +153,6 @@ int rb3b_index_from_runs_dev(rb3b_index_s *x, int64_t n_runs, const uint8_t *d_s
 {
 	DBuf<int64_t> nent, eoff;
 	DBuf<int> bad;
-	DBuf<uint4> blocks;
 	int64_t last[2] = {0, 0};
 	int hbad = 0;
 	rb3b_index_free_dev(x);
@@ -159,10 +171,9 @@ int rb3b_index_from_runs_dev(rb3b_index_s *x, int64_t n_runs, const uint8_t *d_s
 	x->n_blocks = (x->n_entries + RB3B_ENT_PER_BLK - 1) / RB3B_ENT_PER_BLK;
 	if (x->n_blocks >= (1LL << 32) - 16) return rb3b_fail(RB3B_EINVAL, "index too large for 32-bit block ids");
 	if (x->n_blocks == 0) return rb3b_index_finalize(x);
-	TRY(blocks.alloc(x->n_blocks * 8));
-	CK(cudaMemsetAsync(blocks.p, 0, x->n_blocks * 128, rb3b_stream));
-	k_run_emit<<<nblk(n_runs, TPB), TPB, 0, rb3b_stream>>>(n_runs, d_sym, d_len, eoff.p, blocks.p); CKK();
-	x->blocks = blocks.take();
+	TRY(rb3b_reserve((void**)&x->blocks, &x->cap_blocks, x->n_blocks * 8, sizeof(uint4)));
+	CK(cudaMemsetAsync(x->blocks + (x->n_blocks - 1) * 8, 0, 128, rb3b_stream)); /* padding of the last block */
+	k_run_emit<<<nblk(n_runs, TPB), TPB, 0, rb3b_stream>>>(n_runs, d_sym, d_len, eoff.p, x->blocks); CKK();
 	return rb3b_index_finalize(x);
 }
 
@@ -170,37 +181,69 @@ int rb3b_index_from_runs_dev(rb3b_index_s *x, int64_t n_runs, const uint8_t *d_s
 /* finalize: headers, bstart, dir                                       */
 /* ------------------------------------------------------------------ */
 
-/* cnt is laid out [7][nb+1]: rows 0..5 per-symbol counts of a block, row 6 unused */
-__global__ void k_blk_count(int64_t nb, const uint4 *__restrict__ blocks, int64_t *__restrict__ cnt)
+struct Cnt6 {
+	int64_t v[RB3B_ASIZE];
+	__host__ __device__ Cnt6 operator+(const Cnt6 &o) const { Cnt6 r; for (int a = 0; a < RB3B_ASIZE; ++a) r.v[a] = v[a] + o.v[a]; return r; }
+};
+
+__device__ __forceinline__ Cnt6 blk_counts(const uint4 *__restrict__ blocks, int64_t b)
 {
-	int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (b > nb) return;
-	int64_t c[RB3B_ASIZE] = {0, 0, 0, 0, 0, 0};
-	if (b < nb) {
-		for (int q = 2; q < 8; ++q) {
-			uint4 v = blocks[b * 8 + q];
-			const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+	Cnt6 c;
 #pragma unroll
-			for (int j = 0; j < 8; ++j) {
-				uint32_t e = (w[j >> 1] >> (16 * (j & 1))) & 0xffffu, l = rb3b_ent_len(e), s = e >> 13;
+	for (int a = 0; a < RB3B_ASIZE; ++a) c.v[a] = 0;
+	for (int q = 2; q < 8; ++q) {
+		uint4 v = blocks[b * 8 + q];
+		const uint32_t w[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
-				for (int a = 0; a < RB3B_ASIZE; ++a) c[a] += s == (uint32_t)a ? l : 0;
-			}
+		for (int j = 0; j < 8; ++j) {
+			uint32_t e = (w[j >> 1] >> (16 * (j & 1))) & 0xffffu, l = rb3b_ent_len(e), s = e >> 13;
+#pragma unroll
+			for (int a = 0; a < RB3B_ASIZE; ++a) c.v[a] += s == (uint32_t)a ? l : 0;
 		}
 	}
-	for (int a = 0; a < RB3B_ASIZE; ++a) cnt[a * (nb + 1) + b] = c[a];
+	return c;
 }
 
-__global__ void k_blk_header(int64_t nb, uint4 *blocks, const int64_t *__restrict__ ex, uint64_t *__restrict__ bstart)
+#define FIN_TPB 128
+
+/* pass 1: per-symbol totals of every chunk of FIN_TPB blocks, laid out [6][n_chunks+1] for one flat scan */
+__global__ void __launch_bounds__(FIN_TPB) k_fin_count(int64_t nb, const uint4 *__restrict__ blocks, int64_t n_chunks, int64_t *__restrict__ ctot)
 {
-	int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (b > nb) return;
-	uint64_t c[RB3B_ASIZE], s = 0;
-	for (int a = 0; a < RB3B_ASIZE; ++a) { c[a] = (uint64_t)(ex[a * (nb + 1) + b] - ex[a * (nb + 1)]); s += c[a]; }
-	bstart[b] = s;
+	typedef cub::BlockReduce<int64_t, FIN_TPB> Red;
+	__shared__ typename Red::TempStorage tmp[RB3B_ASIZE];
+	int64_t b = (int64_t)blockIdx.x * FIN_TPB + threadIdx.x;
+	Cnt6 c;
+	if (b < nb) c = blk_counts(blocks, b);
+	else for (int a = 0; a < RB3B_ASIZE; ++a) c.v[a] = 0;
+#pragma unroll
+	for (int a = 0; a < RB3B_ASIZE; ++a) {
+		int64_t t = Red(tmp[a]).Sum(c.v[a]);
+		if (threadIdx.x == 0) ctot[(int64_t)a * (n_chunks + 1) + blockIdx.x] = t;
+	}
+	if (blockIdx.x == 0 && threadIdx.x < RB3B_ASIZE) ctot[(int64_t)threadIdx.x * (n_chunks + 1) + n_chunks] = 0;
+}
+
+/* pass 2: recount, scan inside the chunk, add the chunk base: block headers and bstart */
+__global__ void __launch_bounds__(FIN_TPB) k_fin_write(int64_t nb, uint4 *blocks, int64_t n_chunks, const int64_t *__restrict__ cex, uint64_t *__restrict__ bstart)
+{
+	typedef cub::BlockScan<int64_t, FIN_TPB> Scan;
+	__shared__ typename Scan::TempStorage tmp[RB3B_ASIZE];
+	int64_t b = (int64_t)blockIdx.x * FIN_TPB + threadIdx.x;
+	Cnt6 c;
+	if (b < nb) c = blk_counts(blocks, b);
+	else for (int a = 0; a < RB3B_ASIZE; ++a) c.v[a] = 0;
+	uint64_t h[RB3B_ASIZE], s = 0;
+#pragma unroll
+	for (int a = 0; a < RB3B_ASIZE; ++a) {
+		int64_t ex;
+		Scan(tmp[a]).ExclusiveSum(c.v[a], ex);
+		h[a] = (uint64_t)(ex + cex[(int64_t)a * (n_chunks + 1) + blockIdx.x] - cex[(int64_t)a * (n_chunks + 1)]);
+		s += h[a];
+	}
+	if (b <= nb) bstart[b] = s; /* thread b == nb sees zero counts of its own: s is the grand total */
 	if (b < nb) {
-		blocks[b * 8 + 0] = rb3b_hdr_pack(c[0], c[1], c[2]);
-		blocks[b * 8 + 1] = rb3b_hdr_pack(c[3], c[4], c[5]);
+		blocks[b * 8 + 0] = rb3b_hdr_pack(h[0], h[1], h[2]);
+		blocks[b * 8 + 1] = rb3b_hdr_pack(h[3], h[4], h[5]);
 	}
 }
 
@@ -240,17 +283,18 @@ int rb3b_index_finalize(rb3b_index_s *x)
 	memset(x->tot, 0, sizeof(x->tot)); memset(x->acc, 0, sizeof(x->acc));
 	x->bytes = 0;
 	if (nb == 0) { x->n_dir = 0; x->dir_shift = 0; return RB3B_OK; }
-	DBuf<int64_t> cnt, ex;
-	DBuf<uint64_t> bstart, dir;
+	DBuf<int64_t> ctot, cex;
 	DBuf<uint32_t> tmp;
-	int64_t m = (nb + 1) * RB3B_ASIZE, tot[RB3B_ASIZE], base[RB3B_ASIZE];
-	TRY(cnt.alloc(m)); TRY(ex.alloc(m)); TRY(bstart.alloc(nb + 1));
-	k_blk_count<<<nblk(nb + 1, 128), 128, 0, rb3b_stream>>>(nb, x->blocks, cnt.p); CKK();
-	TRY(rb3b_scan_excl_i64(cnt.p, ex.p, m));
-	k_blk_header<<<nblk(nb + 1, 128), 128, 0, rb3b_stream>>>(nb, x->blocks, ex.p, bstart.p); CKK();
+	int64_t n_chunks = (nb + 1 + FIN_TPB - 1) / FIN_TPB; /* covers index nb too: that thread writes bstart[nb] */
+	int64_t m = (n_chunks + 1) * RB3B_ASIZE, tot[RB3B_ASIZE], base[RB3B_ASIZE];
+	TRY(ctot.alloc(m)); TRY(cex.alloc(m));
+	TRY(rb3b_reserve((void**)&x->bstart, &x->cap_bstart, nb + 1, 8));
+	k_fin_count<<<(unsigned)n_chunks, FIN_TPB, 0, rb3b_stream>>>(nb, x->blocks, n_chunks, ctot.p); CKK();
+	TRY(rb3b_scan_excl_i64(ctot.p, cex.p, m));
+	k_fin_write<<<(unsigned)n_chunks, FIN_TPB, 0, rb3b_stream>>>(nb, x->blocks, n_chunks, cex.p, x->bstart); CKK();
 	for (int a = 0; a < RB3B_ASIZE; ++a) {
-		CK(cudaMemcpyAsync(&tot[a], ex.p + a * (nb + 1) + nb, 8, cudaMemcpyDeviceToHost, rb3b_stream));
-		CK(cudaMemcpyAsync(&base[a], ex.p + a * (nb + 1), 8, cudaMemcpyDeviceToHost, rb3b_stream));
+		CK(cudaMemcpyAsync(&tot[a], cex.p + a * (n_chunks + 1) + n_chunks, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+		CK(cudaMemcpyAsync(&base[a], cex.p + a * (n_chunks + 1), 8, cudaMemcpyDeviceToHost, rb3b_stream));
 	}
 	CK(cudaStreamSynchronize(rb3b_stream));
 	for (int a = 0; a < RB3B_ASIZE; ++a) {
@@ -264,15 +308,12 @@ int rb3b_index_finalize(rb3b_index_s *x)
 	while (shift < 40 && (x->n >> (shift + 1)) >= nb * 2) ++shift;
 	x->dir_shift = shift;
 	x->n_dir = (x->n >> shift) + 2;
-	TRY(tmp.alloc(x->n_dir)); TRY(dir.alloc(x->n_dir));
+	TRY(tmp.alloc(x->n_dir));
+	TRY(rb3b_reserve((void**)&x->dir, &x->cap_dir, x->n_dir, 8));
 	CK(cudaMemsetAsync(tmp.p, 0, x->n_dir * 4, rb3b_stream));
-	k_dir_scatter<<<nblk(nb, TPB), TPB, 0, rb3b_stream>>>(nb, bstart.p, shift, tmp.p, x->n_dir); CKK();
+	k_dir_scatter<<<nblk(nb, TPB), TPB, 0, rb3b_stream>>>(nb, x->bstart, shift, tmp.p, x->n_dir); CKK();
 	TRY(scan_max_u32(tmp.p, x->n_dir));
-	k_dir_pack<<<nblk(x->n_dir, TPB), TPB, 0, rb3b_stream>>>(x->n_dir, tmp.p, bstart.p, shift, dir.p); CKK();
-	if (x->bstart) cudaFreeAsync(x->bstart, rb3b_stream);
-	if (x->dir) cudaFreeAsync(x->dir, rb3b_stream);
-	x->bstart = bstart.take();
-	x->dir = dir.take();
+	k_dir_pack<<<nblk(x->n_dir, TPB), TPB, 0, rb3b_stream>>>(x->n_dir, tmp.p, x->bstart, shift, x->dir); CKK();
 	x->bytes = (size_t)nb * 128 + (size_t)(nb + 1) * 8 + (size_t)x->n_dir * 8;
 	rb3b_stat_set("n_blocks", nb);
 	rb3b_stat_set("dir_shift", shift);

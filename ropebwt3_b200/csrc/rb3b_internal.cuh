@@ -41,6 +41,8 @@ struct rb3b_index_s {
 	int64_t acc[RB3B_ASIZE + 1];  /* C[] */
 	int64_t n_blocks, n_entries;
 	uint4 *blocks;                /* n_blocks * 8 quads */
+	uint4 *spare;                 /* the other half of the ping-pong pair: the next merge writes here */
+	int64_t cap_blocks, cap_spare, cap_bstart, cap_dir; /* capacities (elements) of the persistent buffers */
 	uint64_t *bstart;             /* n_blocks + 1 */
 	uint64_t *dir;                /* n_dir cells: b0 | off << 32 | multi << 63 */
 	int64_t n_dir;
@@ -115,6 +117,8 @@ private:
 };
 
 /* ---- primitives (rb3b_index.cu) ---- */
+/* grow-only persistent buffer: reallocates (x1.5) only when `need` exceeds the capacity; contents are not kept */
+int rb3b_reserve(void **p, int64_t *cap, int64_t need, size_t elt);
 int rb3b_scan_excl_i64(const int64_t *d_in, int64_t *d_out, int64_t n);              /* exclusive prefix sum */
 int rb3b_index_free_dev(rb3b_index_s *x);
 int rb3b_index_from_runs_dev(rb3b_index_s *x, int64_t n_runs, const uint8_t *d_sym, const int64_t *d_len);

@@ -219,7 +219,10 @@ __global__ void __launch_bounds__(TPB) k_walk_first(DevIndex A, Acc7 accB, Segs 
 			kb = (int64_t)(x >> LFB_SHIFT);
 			x = __ldg(lfb + kb); /* the B chain does not depend on A: fetch one step ahead */
 			int64_t r1, r2;
-			WG::rank2(A, lo, hi, c, r1, r2);
+			/* the groups that currently run together take the two-position path only while one of them still
+			 * carries a bracket; either path is correct for an exact group, so this is purely a cost choice */
+			if (__any_sync(__activemask(), lo != hi)) WG::rank2(A, lo, hi, c, r1, r2);
+			else r1 = r2 = WG::rank(A, lo, c);
 			lo = A.acc[c] + r1; hi = A.acc[c] + r2;
 			if (x & LFB_COARSE) { succ = S.cmap[F.of_row(kb)]; break; }
 		}
@@ -489,7 +492,6 @@ static int merge_phase(rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, const
 	int64_t nb = A->n_blocks, last[2];
 	DBuf<int64_t> blo, cnt, eoff;
 	DBuf<int> bad;
-	DBuf<uint4> out;
 	int hbad = 0;
 	TRY(blo.alloc(nb + 1)); TRY(cnt.alloc(nb)); TRY(eoff.alloc(nb)); TRY(bad.alloc(1));
 	CK(cudaMemsetAsync(bad.p, 0, sizeof(int), rb3b_stream));
@@ -505,12 +507,11 @@ static int merge_phase(rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, const
 	if (hbad) return rb3b_fail(RB3B_EINVAL, "interleave positions are not monotone: the batch is not a valid BWT");
 	int64_t n_ent = last[0] + last[1], nb2 = (n_ent + RB3B_ENT_PER_BLK - 1) / RB3B_ENT_PER_BLK;
 	if (nb2 >= (1LL << 32) - 16) return rb3b_fail(RB3B_EINVAL, "index too large for 32-bit block ids");
-	TRY(out.alloc(nb2 * 8));
-	CK(cudaMemsetAsync(out.p + (nb2 - 1) * 8, 0, 128, rb3b_stream)); /* padding of the last block; everything else is written */
-	k_merge<true><<<nblk(nb, 128), 128, 0, rb3b_stream>>>(nb, A->blocks, A->bstart, blo.p, d_ka, d_bwt, 0, eoff.p, out.p); CKK();
+	TRY(rb3b_reserve((void**)&A->spare, &A->cap_spare, nb2 * 8, sizeof(uint4)));
+	CK(cudaMemsetAsync(A->spare + (nb2 - 1) * 8, 0, 128, rb3b_stream)); /* padding of the last block; everything else is written */
+	k_merge<true><<<nblk(nb, 128), 128, 0, rb3b_stream>>>(nb, A->blocks, A->bstart, blo.p, d_ka, d_bwt, 0, eoff.p, A->spare); CKK();
 	rb3b_toc(T_MERGE);
-	cudaFreeAsync(A->blocks, rb3b_stream);
-	A->blocks = out.take();
+	{ uint4 *t = A->blocks; A->blocks = A->spare; A->spare = t; int64_t c = A->cap_blocks; A->cap_blocks = A->cap_spare; A->cap_spare = c; }
 	A->n_blocks = nb2; A->n_entries = n_ent;
 	rb3b_tic(T_FINAL);
 	int rc = rb3b_index_finalize(A);
