@@ -30,7 +30,7 @@ METRIC = "bases/sec indexed (build)"
 UNIT = "bases/s"
 GENOME_LEN = 5_000_000
 SEED = 43  # 42 + config index
-LF_STEP_BYTES = 160  # 128-B index block + 8 B query + 8 B result + 8 B LF_B read + 8 B ka write
+LF_STEP_BYTES = 160  # 128-B index cell + 8 B query + 8 B result + 8 B LF_B read + 8 B ka write
 
 
 def parse():
@@ -167,7 +167,7 @@ def run_b200(a):
     barrier()
     wall_dev = time.time() - w0
     ms_dev = e0.elapsed_time(e1)
-    st = {k: R.get_stat(k) for k in ["us_prep", "us_walk_first", "us_walk_fix", "us_merge", "us_finalize", "kernel_launches", "n_segments", "fix_rounds", "n_blocks"]}
+    st = {k: R.get_stat(k) for k in ["us_prep", "us_walk_first", "us_walk_fix", "us_merge", "us_finalize", "kernel_launches", "n_segments", "fix_rounds", "fix_rounds_total", "n_cells", "n_ovf_cells", "cell_shift"]}
     acc_dev = idx.acc()
     index_bytes = idx.nbytes()
     timed_bases = sum(bases[1 + a.warmup:])
@@ -247,8 +247,8 @@ def run_b200(a):
         "phase_ms_per_step": {k[3:]: st[k] / 1e3 / a.steps for k in st if k.startswith("us_")},
         "wall_ms_per_step": wall_dev * 1e3 / a.steps,
         "setup": {"genomes_and_bwt_s": t_setup, "device_bwt_build_s": t_bwt, "bwt_build_bases_per_s": sum(bases) / t_bwt},
-        "index": {"symbols": int(acc_dev[6]), "device_bytes": int(index_bytes), "blocks": int(st["n_blocks"])},
-        "walk": {"segments_per_step": st["n_segments"], "fix_rounds_total": st["fix_rounds"]},
+        "index": {"symbols": int(acc_dev[6]), "device_bytes": int(index_bytes), "cells": int(st["n_cells"]), "overflow_cells": int(st["n_ovf_cells"]), "cell_span": 1 << int(st["cell_shift"])},
+        "walk": {"segments_per_step": st["n_segments"], "fix_rounds_total": st["fix_rounds_total"]},
     }
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(a, gs, idx_state_genomes=1 + a.warmup, budget_s=20.0)

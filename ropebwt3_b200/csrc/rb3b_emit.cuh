@@ -1,0 +1,258 @@
+/*
+ * rb3b_emit.cuh -- the cell writer shared by index construction (runs -> cells)
+ * and by the streaming merge (cells + batch rows -> cells).
+ *
+ * One thread produces one OUTPUT cell = 2^shift consecutive positions of the
+ * result.  Output position P holds batch row i when ka[i] + i == P (the rows'
+ * merged positions are strictly increasing), otherwise the next symbol of the
+ * source stream.  Because every tile has the same span the work is balanced
+ * and every cell lands at an arithmetic address: no global entry offsets.
+ *
+ *   pass 1 (WRITE = false)  count the entries of every cell -> nent[], per-chunk
+ *                           symbol totals and overflow-block totals
+ *   (host)                  one small exclusive scan over the chunk totals
+ *   pass 2 (WRITE = true)   redo the merge, write entries (inline or into the
+ *                           cell's overflow blocks), then the headers from a
+ *                           CTA-level scan + the chunk bases
+ *
+ * Replaces worker_mgins / rope_insert_run / rle_insert_cached (fm-index.c:237-249,
+ * rope.c:114-148, rle.c:10-89) and worker_p2fmr (fm-index.c:97-112).
+ */
+#ifndef RB3B_EMIT_CUH
+#define RB3B_EMIT_CUH
+
+#include <cub/cub.cuh>
+#include "rb3b_internal.cuh"
+
+#define EMIT_TPB 128
+
+struct EmitOut {
+	uint4 *cells, *ovf;
+	int shift;
+	int64_t n_out, n_cells, n_chunks;
+};
+
+/* source stream given as a run list with start positions (start[] = exclusive scan of the lengths) */
+struct RunSrc {
+	const uint8_t *sym; const int64_t *start;
+	int64_t n_runs, n, r, rem64;
+	int cur;
+	__device__ __forceinline__ int64_t run_end(int64_t i) const { return i + 1 < n_runs ? start[i + 1] : n; }
+	__device__ __forceinline__ void seek(int64_t pos)
+	{
+		int64_t lo = 0, hi = n_runs; /* last run whose start is <= pos; with equal starts that is the non-empty one */
+		while (hi - lo > 1) {
+			int64_t mid = (lo + hi) >> 1;
+			if (start[mid] <= pos) lo = mid; else hi = mid;
+		}
+		r = lo; cur = sym[r]; rem64 = run_end(r) - pos;
+	}
+	__device__ __forceinline__ uint32_t avail(int64_t lim) const { return (uint32_t)(rem64 < lim ? rem64 : lim); }
+	__device__ __forceinline__ void advance(uint32_t l)
+	{
+		rem64 -= l;
+		while (rem64 == 0 && r + 1 < n_runs) { ++r; cur = sym[r]; rem64 = run_end(r) - start[r]; }
+	}
+};
+
+/* source stream given as an index */
+struct CellSrc {
+	CellReader R;
+	int64_t n;
+	int cur;
+	__device__ __forceinline__ void seek(int64_t pos) { R.seek(pos); cur = R.cur; }
+	__device__ __forceinline__ uint32_t avail(int64_t lim) const { return (uint32_t)((int64_t)R.rem < lim ? (int64_t)R.rem : lim); }
+	__device__ __forceinline__ void advance(uint32_t l) { R.advance(l); cur = R.cur; }
+};
+
+template<bool WRITE> struct CellEmitter {
+	int sym; uint32_t len, ne, pos;
+	uint32_t cc[RB3B_ASIZE];
+	bool is_ovf;
+	uint4 *cell, *blk; /* this cell; its first overflow block */
+	__device__ __forceinline__ void init(uint4 *cell_, uint4 *blk_, bool is_ovf_)
+	{
+		sym = -1; len = ne = pos = 0; cell = cell_; blk = blk_; is_ovf = is_ovf_;
+#pragma unroll
+		for (int a = 0; a < RB3B_ASIZE; ++a) cc[a] = 0;
+	}
+	__device__ __forceinline__ void flush()
+	{
+		if (len == 0) return;
+		if (WRITE) {
+			uint16_t e = (uint16_t)((uint32_t)sym << 13 | len);
+			if (!is_ovf) ((uint16_t*)(cell + 2))[ne] = e;
+			else {
+				uint32_t t = ne / RB3B_ENT_PER_OVF, s = ne % RB3B_ENT_PER_OVF;
+				if (s == 0) { /* a new overflow block: its header and its slot in the cell's directory */
+					uint16_t *h = (uint16_t*)(blk + (int64_t)t * 8);
+#pragma unroll
+					for (int a = 0; a < RB3B_ASIZE; ++a) h[a] = (uint16_t)cc[a];
+					h[6] = h[7] = 0;
+					if (t > 0) ((uint16_t*)(cell + 3))[t - 1] = (uint16_t)pos;
+				}
+				((uint16_t*)(blk + (int64_t)t * 8 + 1))[s] = e;
+			}
+		}
+		++ne; pos += len;
+#pragma unroll
+		for (int a = 0; a < RB3B_ASIZE; ++a) cc[a] += sym == a ? len : 0;
+		len = 0;
+	}
+	__device__ __forceinline__ void put(int c, uint32_t l)
+	{
+		if (c == sym) len += l;
+		else { flush(); sym = c; len = l; }
+	}
+};
+
+__host__ __device__ __forceinline__ uint32_t rb3b_ovf_blocks(uint32_t nent)
+{ return nent > RB3B_ENT_PER_CELL ? (nent + RB3B_ENT_PER_OVF - 1) / RB3B_ENT_PER_OVF : 0; }
+
+/* ctot / cex layout: [7][n_chunks + 1]; rows 0-5 symbol totals of a chunk of EMIT_TPB cells, row 6 overflow blocks */
+template<class Src, bool WRITE>
+__global__ void __launch_bounds__(EMIT_TPB) k_emit(Src src, EmitOut O, int64_t lenB, const int64_t *__restrict__ ka, const uint8_t *__restrict__ bwt,
+                                                    const int64_t *__restrict__ ilo, uint16_t *__restrict__ nent, int64_t *__restrict__ ctot,
+                                                    const int64_t *__restrict__ cex, unsigned long long *__restrict__ stats)
+{
+	typedef cub::BlockReduce<int64_t, EMIT_TPB> Red;
+	typedef cub::BlockScan<int64_t, EMIT_TPB> Scan;
+	__shared__ union { typename Red::TempStorage r; typename Scan::TempStorage s; } tmp[RB3B_ASIZE + 1];
+	const int64_t j = (int64_t)blockIdx.x * EMIT_TPB + threadIdx.x;
+	const bool live = j < O.n_cells;
+	CellEmitter<WRITE> E;
+	int64_t novf = 0, ovf_base = 0;
+	if (WRITE) {
+		novf = live ? rb3b_ovf_blocks(nent[j]) : 0;
+		Scan(tmp[RB3B_ASIZE].s).ExclusiveSum(novf, ovf_base);
+		ovf_base += cex[(int64_t)RB3B_ASIZE * (O.n_chunks + 1) + blockIdx.x] - cex[(int64_t)RB3B_ASIZE * (O.n_chunks + 1)];
+	}
+	E.init(O.cells + j * 8, O.ovf + ovf_base * 8, novf > 0);
+	if (live) {
+		const int64_t P0 = j << O.shift, P1 = min((long long)O.n_out, (long long)(P0 + (1LL << O.shift)));
+		int64_t i = ilo ? ilo[j] : 0, iend = ilo ? ilo[j + 1] : 0, P = P0;
+		int64_t nextB = i < iend ? ka[i] + i : INT64_MAX;
+		if (P0 - i < src.n) src.seek(P0 - i);
+		while (P < P1) {
+			if (nextB == P) {
+				E.put(bwt[i], 1);
+				++i; ++P;
+				nextB = i < iend ? ka[i] + i : INT64_MAX;
+				continue;
+			}
+			uint32_t t = src.avail((nextB < P1 ? nextB : P1) - P);
+			E.put(src.cur, t);
+			src.advance(t);
+			P += t;
+		}
+		E.flush();
+	}
+	if (!WRITE) {
+		if (live) nent[j] = (uint16_t)E.ne;
+		int64_t ov = live ? rb3b_ovf_blocks(E.ne) : 0;
+#pragma unroll
+		for (int a = 0; a <= RB3B_ASIZE; ++a) {
+			int64_t t = Red(tmp[a].r).Sum(a < RB3B_ASIZE ? (int64_t)E.cc[a < RB3B_ASIZE ? a : 0] : ov);
+			if (threadIdx.x == 0) ctot[(int64_t)a * (O.n_chunks + 1) + blockIdx.x] = t;
+		}
+		if (blockIdx.x == 0 && threadIdx.x <= RB3B_ASIZE) ctot[(int64_t)threadIdx.x * (O.n_chunks + 1) + O.n_chunks] = 0;
+		if (live) {
+			atomicAdd(&stats[0], (unsigned long long)E.ne);
+			if (ov) atomicAdd(&stats[1], 1ULL);
+		}
+	} else {
+		uint64_t h[RB3B_ASIZE];
+#pragma unroll
+		for (int a = 0; a < RB3B_ASIZE; ++a) {
+			int64_t ex;
+			Scan(tmp[a].s).ExclusiveSum((int64_t)E.cc[a], ex);
+			h[a] = (uint64_t)(ex + cex[(int64_t)a * (O.n_chunks + 1) + blockIdx.x] - cex[(int64_t)a * (O.n_chunks + 1)]);
+		}
+		if (live) {
+			uint4 *cell = O.cells + j * 8;
+			cell[0] = rb3b_hdr_pack(h[0], h[1], h[2], novf > 0);
+			cell[1] = rb3b_hdr_pack(h[3], h[4], h[5], false);
+			if (novf > 0) {
+				cell[2] = make_uint4((uint32_t)ovf_base, (uint32_t)novf, 0u, 0u);
+				for (uint32_t t = (uint32_t)novf; t < RB3B_MAX_OVF; ++t) ((uint16_t*)(cell + 3))[t - 1] = 0xffffu;
+			} else
+				for (uint32_t e = E.ne; e < RB3B_ENT_PER_CELL; ++e) ((uint16_t*)(cell + 2))[e] = 0;
+		}
+	}
+}
+
+/* ilo[j] = first batch row whose merged position ka[i] + i is >= j << shift (j = 0..n_cells) */
+static __global__ void k_tile_bounds(int64_t n_cells, int shift, int64_t len, const int64_t *__restrict__ ka, int64_t *__restrict__ ilo)
+{
+	int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j > n_cells) return;
+	int64_t key = j << shift, lo = 0, hi = len;
+	while (lo < hi) {
+		int64_t mid = (lo + hi) >> 1;
+		if (ka[mid] + mid < key) lo = mid + 1; else hi = mid;
+	}
+	ilo[j] = lo;
+}
+
+/*
+ * Host driver: write the stream `src` (n_src symbols) interleaved with the batch rows (lenB, ka, bwt; lenB may be 0)
+ * into the spare buffers of x, then make them current.  est_entries steers the cell span.
+ */
+template<class Src>
+static int rb3b_emit_build(rb3b_index_s *x, Src src, int64_t n_src, int64_t lenB, const int64_t *d_ka, const uint8_t *d_bwt, int64_t est_entries)
+{
+	const int64_t n_out = n_src + lenB;
+	int shift = rb3b_pick_shift(n_out, est_entries);
+	DBuf<int64_t> ilo, ctot, cex;
+	DBuf<uint16_t> nent;
+	DBuf<unsigned long long> stats;
+	unsigned long long hstats[2] = {0, 0};
+	EmitOut O;
+	TRY(stats.alloc(2));
+	for (;;) {
+		O.shift = shift; O.n_out = n_out;
+		O.n_cells = (n_out + (1LL << shift) - 1) >> shift;
+		O.n_chunks = (O.n_cells + EMIT_TPB - 1) / EMIT_TPB;
+		O.cells = 0; O.ovf = 0;
+		if (O.n_cells >= (1LL << 40)) return rb3b_fail(RB3B_EINVAL, "index too large");
+		TRY(nent.alloc(O.n_cells)); TRY(ctot.alloc((O.n_chunks + 1) * (RB3B_ASIZE + 1))); TRY(cex.alloc((O.n_chunks + 1) * (RB3B_ASIZE + 1)));
+		if (lenB > 0) {
+			TRY(ilo.alloc(O.n_cells + 1));
+			k_tile_bounds<<<(unsigned)((O.n_cells + 1 + 255) / 256), 256, 0, rb3b_stream>>>(O.n_cells, shift, lenB, d_ka, ilo.p); CKK();
+		}
+		CK(cudaMemsetAsync(stats.p, 0, 16, rb3b_stream));
+		k_emit<Src, false><<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(src, O, lenB, d_ka, d_bwt, lenB > 0 ? ilo.p : 0, nent.p, ctot.p, 0, stats.p); CKK();
+		CK(cudaMemcpyAsync(hstats, stats.p, 16, cudaMemcpyDeviceToHost, rb3b_stream));
+		CK(cudaStreamSynchronize(rb3b_stream));
+		/* too many overflow cells: halve the span and count again (cheap, rare) */
+		if (shift > RB3B_MIN_SHIFT && (double)hstats[1] > 0.03 * (double)O.n_cells) { --shift; continue; }
+		break;
+	}
+	TRY(rb3b_scan_excl_i64(ctot.p, cex.p, (O.n_chunks + 1) * (RB3B_ASIZE + 1)));
+	int64_t tot[RB3B_ASIZE + 1], base[RB3B_ASIZE + 1];
+	for (int a = 0; a <= RB3B_ASIZE; ++a) {
+		CK(cudaMemcpyAsync(&tot[a], cex.p + a * (O.n_chunks + 1) + O.n_chunks, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+		CK(cudaMemcpyAsync(&base[a], cex.p + a * (O.n_chunks + 1), 8, cudaMemcpyDeviceToHost, rb3b_stream));
+	}
+	CK(cudaStreamSynchronize(rb3b_stream));
+	int64_t n_ovf = tot[RB3B_ASIZE] - base[RB3B_ASIZE];
+	if (n_ovf >= (1LL << 32)) return rb3b_fail(RB3B_EINVAL, "too many overflow blocks");
+	TRY(rb3b_reserve((void**)&x->cells2, &x->cap_cells2, O.n_cells * 8, sizeof(uint4)));
+	TRY(rb3b_reserve((void**)&x->ovf2, &x->cap_ovf2, n_ovf * 8 + 8, sizeof(uint4)));
+	O.cells = x->cells2; O.ovf = x->ovf2;
+	k_emit<Src, true><<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(src, O, lenB, d_ka, d_bwt, lenB > 0 ? ilo.p : 0, nent.p, 0, cex.p, stats.p); CKK();
+	/* swap the ping-pong halves (the kernels that read the old half are already enqueued on the same stream) */
+	{ uint4 *t = x->cells; x->cells = x->cells2; x->cells2 = t; int64_t c = x->cap_cells; x->cap_cells = x->cap_cells2; x->cap_cells2 = c; }
+	{ uint4 *t = x->ovf; x->ovf = x->ovf2; x->ovf2 = t; int64_t c = x->cap_ovf; x->cap_ovf = x->cap_ovf2; x->cap_ovf2 = c; }
+	x->shift = shift; x->n_cells = O.n_cells; x->n_ovf = n_ovf; x->n_entries = (int64_t)hstats[0];
+	x->acc[0] = 0;
+	for (int a = 0; a < RB3B_ASIZE; ++a) { x->tot[a] = tot[a] - base[a]; x->acc[a + 1] = x->acc[a] + x->tot[a]; }
+	x->n = x->acc[RB3B_ASIZE];
+	x->bytes = (size_t)(O.n_cells + n_ovf) * 128;
+	rb3b_stat_set("n_cells", O.n_cells); rb3b_stat_set("n_ovf_blocks", n_ovf); rb3b_stat_set("n_ovf_cells", (int64_t)hstats[1]);
+	rb3b_stat_set("cell_shift", shift); rb3b_stat_set("n_entries", (int64_t)hstats[0]);
+	if (x->n != n_out) return rb3b_fail(RB3B_EINVAL, "internal error: wrote %lld symbols, expected %lld", (long long)x->n, (long long)n_out);
+	return RB3B_OK;
+}
+
+#endif

@@ -4,21 +4,23 @@
  * Device index layout (replaces the B+-tree rope of rope.c/rle.c and the
  * frame+header walk of rld0.c:371-408; see DESIGN.md "Data layout in HBM"):
  *
- *   blocks[b]  128 B, 128-B aligned = 8 x uint4 (one per lane of an 8-lane group)
- *       quad 0   counts of $,A,C  before the block, 3 x 42 bit packed in 128 bit
- *       quad 1   counts of G,T,N  before the block, same packing
- *       quad 2-7 48 run entries of 16 bit:  sym:3 | big:1 | val:12
- *                length = val (big=0) or val<<12 (big=1); val==0 -> padding
- *   bstart[b]  absolute position of the first symbol of block b (bstart[nb] = n)
- *   dir[j]     8-B cell for positions [j << dir_shift, (j+1) << dir_shift):
- *                bits 0-31  b0 = block containing the first position of the cell
- *                bits 32-62 off = offset in the cell at which block b0+1 starts
- *                           (0x7fffffff: no block starts inside the cell)
- *                bit 63     more than one block starts inside: search bstart[]
+ *   The BWT is cut into CELLS of a fixed span of 2^shift positions
+ *   (5 <= shift <= 10).  cells[j] is one 128-B line = 8 x uint4 describing
+ *   positions [j << shift, (j+1) << shift):
+ *       quad 0   counts of $,A,C before the cell, 3 x 42 bit; bit 127 = OVERFLOW
+ *       quad 1   counts of G,T,N before the cell, same packing
+ *       quad 2-7 inline cell: up to 48 run entries of 16 bit, sym:3 | len:13,
+ *                len == 0 = padding.  A run never crosses a cell boundary.
+ *   A cell whose span holds more than 48 runs is an overflow cell:
+ *       quad 2   u32 first overflow block, u32 number of blocks
+ *       quad 3-7 40 x u16: offset in the cell at which blocks 1..40 start
+ *   ovf[b]     128-B overflow block: quad 0 = 6 x u16 counts of the symbols of
+ *              this cell that precede the block (+2 spare), quads 1-7 = 56 entries.
  *
- * One rank query therefore touches one dir cell and exactly one 128-B block
- * (plus, rarely, a few bstart entries), which a group of G = 2, 4 or 8 lanes
- * reads with 16-B-per-lane loads and reduces with shuffles.
+ * The cell of position k is cells[k >> shift]: a rank query is ONE 128-B access
+ * at an arithmetic address (plus one overflow block for the few dense cells),
+ * read by a group of G = 2, 4 or 8 lanes with 16-B-per-lane loads and reduced
+ * with shuffles.  shift is chosen per index so that an average cell is ~40% full.
  */
 #ifndef RB3B_INTERNAL_CUH
 #define RB3B_INTERNAL_CUH
@@ -28,35 +30,32 @@
 #include <cuda_runtime.h>
 #include "../../include/rb3_b200.h"
 
-#define RB3B_ENT_PER_BLK 48
-#define RB3B_BIG_SHIFT   12
-#define RB3B_VAL_MASK    0xfffu
-#define RB3B_BIG_BIT     0x1000u
-#define RB3B_GROUP       8          /* lanes cooperating on one query */
-#define RB3B_M42         ((1ULL << 42) - 1)
+#define RB3B_ENT_PER_CELL 48
+#define RB3B_ENT_PER_OVF  56
+#define RB3B_MAX_OVF      41
+#define RB3B_MIN_SHIFT    5
+#define RB3B_MAX_SHIFT    10
+#define RB3B_LEN_MASK     0x1fffu
+#define RB3B_M42          ((1ULL << 42) - 1)
+#define RB3B_GROUP        8          /* lanes per query of the API rank kernels and of the LF walk */
 
 struct rb3b_index_s {
 	int64_t n;                    /* #symbols */
 	int64_t tot[RB3B_ASIZE];      /* marginal counts */
 	int64_t acc[RB3B_ASIZE + 1];  /* C[] */
-	int64_t n_blocks, n_entries;
-	uint4 *blocks;                /* n_blocks * 8 quads */
-	uint4 *spare;                 /* the other half of the ping-pong pair: the next merge writes here */
-	int64_t cap_blocks, cap_spare, cap_bstart, cap_dir; /* capacities (elements) of the persistent buffers */
-	uint64_t *bstart;             /* n_blocks + 1 */
-	uint64_t *dir;                /* n_dir cells: b0 | off << 32 | multi << 63 */
-	int64_t n_dir;
-	int dir_shift;
+	int shift;                    /* log2 of the cell span */
+	int64_t n_cells, n_ovf, n_entries;
+	uint4 *cells, *ovf;           /* n_cells * 8 and n_ovf * 8 quads */
+	uint4 *cells2, *ovf2;         /* the other half of the ping-pong pair: the next merge writes here */
+	int64_t cap_cells, cap_ovf, cap_cells2, cap_ovf2; /* capacities in quads */
 	size_t bytes;
 };
 
 /* by-value kernel argument */
 struct DevIndex {
-	const uint4 *blocks;
-	const uint64_t *bstart;
-	const uint64_t *dir;
-	int64_t n, n_blocks;
-	int dir_shift;
+	const uint4 *cells, *ovf;
+	int64_t n, n_cells;
+	int shift;
 	int64_t tot[RB3B_ASIZE];
 	int64_t acc[RB3B_ASIZE + 1];
 };
@@ -64,8 +63,8 @@ struct DevIndex {
 static inline DevIndex rb3b_dev_view(const rb3b_index_s *x)
 {
 	DevIndex d;
-	d.blocks = x->blocks; d.bstart = x->bstart; d.dir = x->dir;
-	d.n = x->n; d.n_blocks = x->n_blocks; d.dir_shift = x->dir_shift;
+	d.cells = x->cells; d.ovf = x->ovf;
+	d.n = x->n; d.n_cells = x->n_cells; d.shift = x->shift;
 	for (int c = 0; c < RB3B_ASIZE; ++c) d.tot[c] = x->tot[c];
 	for (int c = 0; c <= RB3B_ASIZE; ++c) d.acc[c] = x->acc[c];
 	return d;
@@ -122,13 +121,11 @@ int rb3b_reserve(void **p, int64_t *cap, int64_t need, size_t elt);
 int rb3b_scan_excl_i64(const int64_t *d_in, int64_t *d_out, int64_t n);              /* exclusive prefix sum */
 int rb3b_index_free_dev(rb3b_index_s *x);
 int rb3b_index_from_runs_dev(rb3b_index_s *x, int64_t n_runs, const uint8_t *d_sym, const int64_t *d_len);
-int rb3b_index_finalize(rb3b_index_s *x);     /* blocks hold entries; fills headers, bstart, dir, totals */
 int rb3b_export_runs_dev(const rb3b_index_s *x, DBuf<uint8_t> &sym, DBuf<int64_t> &len, int64_t *n_runs);
+int rb3b_pick_shift(int64_t n, int64_t n_entries_est);
 
 /* ---- device helpers ---- */
 #ifdef __CUDACC__
-
-#define RB3B_DIR_NONE 0x7fffffffu
 
 __device__ __forceinline__ void rb3b_hdr_unpack(const uint4 v, uint64_t &c0, uint64_t &c1, uint64_t &c2)
 {
@@ -138,49 +135,39 @@ __device__ __forceinline__ void rb3b_hdr_unpack(const uint4 v, uint64_t &c0, uin
 	c2 = (hi >> 20) & RB3B_M42;
 }
 
-__device__ __forceinline__ uint4 rb3b_hdr_pack(uint64_t c0, uint64_t c1, uint64_t c2)
+__device__ __forceinline__ uint4 rb3b_hdr_pack(uint64_t c0, uint64_t c1, uint64_t c2, bool flag)
 {
-	uint64_t lo = c0 | c1 << 42, hi = c1 >> 22 | c2 << 20;
+	uint64_t lo = c0 | c1 << 42, hi = c1 >> 22 | c2 << 20 | (flag ? 1ULL << 63 : 0);
 	return make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
 }
 
-__device__ __forceinline__ uint32_t rb3b_ent_len(uint32_t e)
-{
-	uint32_t l = e & RB3B_VAL_MASK;
-	return (e & RB3B_BIG_BIT) ? l << RB3B_BIG_SHIFT : l;
-}
+__device__ __forceinline__ bool rb3b_is_ovf(const uint4 q0) { return (q0.w >> 31) != 0; }
 
-/* number of 16-bit entries needed by a run of length l */
-__host__ __device__ __forceinline__ int64_t rb3b_nent(int64_t l)
+/* #c among the first `off` symbols of an overflow cell (excluding the cell header count).  Slow path, executed
+ * identically by every lane that calls it. */
+static __device__ __noinline__ uint32_t rb3b_ovf_count(const uint4 *__restrict__ cell, const uint4 *__restrict__ ovf, uint32_t off, int c)
 {
-	int64_t q = l >> RB3B_BIG_SHIFT;
-	return (q + 4094) / 4095 + ((l & RB3B_VAL_MASK) ? 1 : 0);
-}
-
-/* pointer to entry e of the entry space embedded in the blocks */
-__device__ __forceinline__ uint16_t *rb3b_ent_ptr(uint4 *blocks, int64_t e)
-{
-	int64_t b = e / RB3B_ENT_PER_BLK;
-	int s = (int)(e - b * RB3B_ENT_PER_BLK);
-	return (uint16_t*)(blocks + b * 8 + 2) + s;
-}
-
-/* write the entries of run (c,l) starting at entry index e; returns next e */
-__device__ __forceinline__ int64_t rb3b_emit_run(uint4 *blocks, int64_t e, int c, int64_t l)
-{
-	int64_t q = l >> RB3B_BIG_SHIFT;
-	while (q > 0) {
-		int64_t t = q < 4095 ? q : 4095;
-		*rb3b_ent_ptr(blocks, e++) = (uint16_t)(c << 13 | RB3B_BIG_BIT | (uint32_t)t);
-		q -= t;
+	uint4 q2 = __ldg(cell + 2);
+	uint32_t first = q2.x, nblk = q2.y, t = 0, start = 0;
+	const uint16_t *st = (const uint16_t*)(cell + 3);
+	for (uint32_t i = 0; i + 1 < nblk; ++i) {
+		uint32_t s = st[i];
+		if (s <= off) { t = i + 1; start = s; } else break;
 	}
-	if (l & RB3B_VAL_MASK) *rb3b_ent_ptr(blocks, e++) = (uint16_t)(c << 13 | (uint32_t)(l & RB3B_VAL_MASK));
-	return e;
+	const uint4 *blk = ovf + (int64_t)(first + t) * 8;
+	uint32_t cnt = ((const uint16_t*)blk)[c], rem = off - start;
+	const uint16_t *e = (const uint16_t*)(blk + 1);
+	for (int i = 0; i < RB3B_ENT_PER_OVF && rem > 0; ++i) {
+		uint32_t x = e[i], l = x & RB3B_LEN_MASK, take = l < rem ? l : rem;
+		if ((x >> 13) == (uint32_t)c) cnt += take;
+		rem -= take;
+	}
+	return cnt;
 }
 
 /*
  * Rank machinery for a group of G lanes (G = 2, 4 or 8) working on one query.
- * Lane gl holds quads [gl*NQ, (gl+1)*NQ) of the 128-B block, NQ = 8/G.
+ * Lane gl holds quads [gl*NQ, (gl+1)*NQ) of the 128-B cell, NQ = 8/G.
  */
 template<int G> struct Grp {
 	static const int NQ = 8 / G;
@@ -188,58 +175,40 @@ template<int G> struct Grp {
 	__device__ __forceinline__ static int base() { return threadIdx.x & 31 & ~(G - 1); }
 	__device__ __forceinline__ static unsigned mask() { return ((1u << G) - 1u) << base(); }
 
-	/* block containing position k (0 <= k < n); all lanes of the group pass the same k */
-	__device__ __forceinline__ static int64_t locate(const DevIndex &x, int64_t k)
+	__device__ __forceinline__ static void load(const DevIndex &x, int64_t j, uint4 (&v)[NQ])
 	{
-		int64_t j = k >> x.dir_shift;
-		uint64_t cell = __ldg(x.dir + j);
-		uint32_t b0 = (uint32_t)cell, off = (uint32_t)(cell >> 32) & RB3B_DIR_NONE;
-		uint64_t in_cell = (uint64_t)k - ((uint64_t)j << x.dir_shift);
-		if ((int64_t)cell < 0) { /* rare: several block starts inside the cell */
-			uint32_t b1 = (uint32_t)__ldg(x.dir + j + 1);
-			while (b0 < b1) { /* last block in [b0,b1] whose start is <= k; same trip count for the whole group */
-				uint32_t mid = b0 + (b1 - b0 + 1) / 2;
-				if (__ldg(x.bstart + mid) <= (uint64_t)k) b0 = mid; else b1 = mid - 1;
-			}
-			return b0;
-		}
-		return (int64_t)b0 + (in_cell >= off ? 1 : 0);
-	}
-
-	__device__ __forceinline__ static void load(const DevIndex &x, int64_t b, uint4 (&v)[NQ])
-	{
-		const uint4 *p = x.blocks + b * 8 + lane() * NQ;
+		const uint4 *p = x.cells + j * 8 + lane() * NQ;
 #pragma unroll
-		for (int j = 0; j < NQ; ++j) v[j] = __ldg(p + j);
+		for (int i = 0; i < NQ; ++i) v[i] = __ldg(p + i);
 	}
 
-	/* #c among the first (k - start of block) symbols of the block held in v, plus the header count of c */
-	__device__ __forceinline__ static int64_t count(const uint4 (&v)[NQ], int64_t k, int c)
+	/* #c in [0, k) given the cell of k in v; 0 <= k < n.  All lanes of the group pass the same (k, c). */
+	__device__ __forceinline__ static int64_t count(const DevIndex &x, const uint4 (&v)[NQ], int64_t k, int c)
 	{
 		const int gl = lane(), gb = base();
 		const unsigned gm = mask();
-		uint64_t hs = 0, hc = 0; /* sum of the header counts held by this lane; header count of symbol c */
+		uint64_t hc = 0; /* header count of symbol c, held by one lane */
+		uint32_t flag = 0;
 		if (G == 8) {
 			if (gl < 2) {
 				uint64_t a0, a1, a2;
 				rb3b_hdr_unpack(v[0], a0, a1, a2);
-				hs = a0 + a1 + a2;
 				int cc = c - 3 * gl;
 				hc = cc == 0 ? a0 : cc == 1 ? a1 : cc == 2 ? a2 : 0;
+				flag = gl == 0 ? v[0].w >> 31 : 0;
 			}
 		} else if (gl == 0) {
 			uint64_t a[6];
 			rb3b_hdr_unpack(v[0], a[0], a[1], a[2]);
 			rb3b_hdr_unpack(v[NQ > 1 ? 1 : 0], a[3], a[4], a[5]);
-			hs = a[0] + a[1] + a[2] + a[3] + a[4] + a[5];
 			hc = c == 0 ? a[0] : c == 1 ? a[1] : c == 2 ? a[2] : c == 3 ? a[3] : c == 4 ? a[4] : a[5];
+			flag = v[0].w >> 31;
 		}
-		uint64_t start = __shfl_sync(gm, hs, gb);
-		if (G == 8) start += __shfl_sync(gm, hs, gb + 1);
 		uint64_t basec = __shfl_sync(gm, hc, gb + ((G == 8 && c >= 3) ? 1 : 0));
-		/* entries */
-		uint32_t len[NQ * 8], tot = 0;
-		uint32_t isc = 0; /* bit i: entry i has symbol c */
+		flag = __shfl_sync(gm, flag, gb);
+		const uint32_t off = (uint32_t)k & ((1u << x.shift) - 1u);
+		if (flag) return (int64_t)(basec + rb3b_ovf_count(x.cells + (k >> x.shift) * 8, x.ovf, off, c)); /* rare, group-uniform */
+		uint32_t len[NQ * 8], tot = 0, isc = 0; /* isc bit i: entry i has symbol c */
 #pragma unroll
 		for (int j = 0; j < NQ; ++j) {
 			const bool ent = gl * NQ + j >= 2; /* quads 0,1 are the header */
@@ -247,7 +216,7 @@ template<int G> struct Grp {
 #pragma unroll
 			for (int i = 0; i < 8; ++i) {
 				uint32_t e = (w[i >> 1] >> (16 * (i & 1))) & 0xffffu;
-				uint32_t l = ent ? rb3b_ent_len(e) : 0;
+				uint32_t l = ent ? (e & RB3B_LEN_MASK) : 0;
 				len[j * 8 + i] = l;
 				isc |= ((e >> 13) == (uint32_t)c ? 1u : 0u) << (j * 8 + i);
 				tot += l;
@@ -259,7 +228,7 @@ template<int G> struct Grp {
 			uint32_t t = __shfl_up_sync(gm, inc, d, G);
 			if (gl >= d) inc += t;
 		}
-		uint32_t pre = inc - tot, off = (uint32_t)((uint64_t)k - start);
+		uint32_t pre = inc - tot;
 		uint32_t rem = off > pre ? min(off - pre, tot) : 0, contrib = 0;
 #pragma unroll
 		for (int i = 0; i < NQ * 8; ++i) {
@@ -277,23 +246,69 @@ template<int G> struct Grp {
 	{
 		int64_t kk = k < x.n ? (k < 0 ? 0 : k) : x.n - 1;
 		uint4 v[NQ];
-		load(x, locate(x, kk), v);
-		int64_t r = count(v, kk, c);
+		load(x, kk >> x.shift, v);
+		int64_t r = count(x, v, kk, c);
 		return k < x.n ? r : x.tot[c];
 	}
 
-	/* two positions at once, same symbol: the two block fetches overlap and the instruction stream is the same
+	/* two positions at once, same symbol: the two cell fetches overlap and the instruction stream is the same
 	 * whether or not k1 == k2, which keeps the groups of a warp in lockstep during the LF walk */
 	__device__ __forceinline__ static void rank2(const DevIndex &x, int64_t k1, int64_t k2, int c, int64_t &r1, int64_t &r2)
 	{
 		int64_t q1 = k1 < x.n ? k1 : x.n - 1, q2 = k2 < x.n ? k2 : x.n - 1;
-		int64_t b1 = locate(x, q1), b2 = locate(x, q2);
 		uint4 v1[NQ], v2[NQ];
-		load(x, b1, v1); load(x, b2, v2);
+		load(x, q1 >> x.shift, v1); load(x, q2 >> x.shift, v2);
 		int64_t t = x.tot[c];
-		r1 = count(v1, q1, c); r2 = count(v2, q2, c);
+		r1 = count(x, v1, q1, c); r2 = count(x, v2, q2, c);
 		r1 = k1 < x.n ? r1 : t; r2 = k2 < x.n ? r2 : t;
 	}
+};
+
+/* Sequential reader of the symbols of an index from a given position on (used by the merge and the export) */
+struct CellReader {
+	const uint4 *cells, *ovf;
+	int64_t n, j;        /* current cell */
+	int shift;
+	uint32_t left;       /* positions of the current cell not yet consumed */
+	uint32_t eidx;       /* next entry of the current cell */
+	uint32_t first;      /* first overflow block, or 0xffffffff for an inline cell */
+	int cur; uint32_t rem; /* current run piece */
+
+	__device__ __forceinline__ uint32_t entry(uint32_t i) const
+	{
+		if (first == 0xffffffffu) return ((const uint16_t*)(cells + j * 8 + 2))[i];
+		return ((const uint16_t*)(ovf + (int64_t)(first + i / RB3B_ENT_PER_OVF) * 8 + 1))[i % RB3B_ENT_PER_OVF];
+	}
+	__device__ __forceinline__ void open_cell()
+	{
+		uint4 q0 = cells[j * 8];
+		first = rb3b_is_ovf(q0) ? cells[j * 8 + 2].x : 0xffffffffu;
+		int64_t p0 = j << shift, span = n - p0 < (1LL << shift) ? n - p0 : (1LL << shift);
+		left = (uint32_t)span; eidx = 0;
+	}
+	__device__ __forceinline__ void next_piece()
+	{ /* precondition: rem == 0 */
+		if (left == 0) {
+			if (((j + 1) << shift) >= n) { cur = -1; return; }
+			++j; open_cell();
+		}
+		uint32_t e = entry(eidx++);
+		cur = (int)(e >> 13); rem = e & RB3B_LEN_MASK;
+		left -= rem;
+	}
+	__device__ __forceinline__ void seek(int64_t pos)
+	{ /* 0 <= pos < n */
+		j = pos >> shift;
+		open_cell();
+		uint32_t skip = (uint32_t)(pos - (j << shift));
+		rem = 0;
+		for (;;) {
+			next_piece();
+			if (skip < rem) { rem -= skip; return; }
+			skip -= rem; rem = 0;
+		}
+	}
+	__device__ __forceinline__ void advance(uint32_t l) { rem -= l; if (rem == 0) next_piece(); }
 };
 
 #endif /* __CUDACC__ */

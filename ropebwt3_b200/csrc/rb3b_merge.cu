@@ -27,6 +27,7 @@
 #include <string.h>
 #include <cub/cub.cuh>
 #include "rb3b_internal.cuh"
+#include "rb3b_emit.cuh"
 
 #define TPB 256
 #define PREP_PER_THREAD 16
@@ -315,7 +316,7 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	DBuf<uint64_t> lfb;
 	int hbad = 0;
 	if (len <= 0) return rb3b_fail(RB3B_EINVAL, "empty batch");
-	if (A->n_blocks == 0) return rb3b_fail(RB3B_EINVAL, "rank phase on an empty index");
+	if (A->n_cells == 0) return rb3b_fail(RB3B_EINVAL, "rank phase on an empty index");
 	/* batch LF mapping */
 	TRY(tcnt.alloc((nt + 1) * RB3B_ASIZE)); TRY(tex.alloc((nt + 1) * RB3B_ASIZE)); TRY(bad.alloc(1)); TRY(lfb.alloc(len));
 	CK(cudaMemsetAsync(bad.p, 0, sizeof(int), rb3b_stream));
@@ -421,101 +422,27 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 }
 
 /* ------------------------------------------------------------------ */
-/* streaming merge                                                      */
+/* streaming merge (rb3b_emit.cuh)                                      */
 /* ------------------------------------------------------------------ */
-
-__global__ void k_tile_bounds(int64_t nb, const uint64_t *__restrict__ bstart, int64_t len, const int64_t *__restrict__ ka, int64_t *__restrict__ blo)
-{
-	int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (b > nb) return;
-	if (b == nb) { blo[b] = len; return; }
-	int64_t key = (int64_t)bstart[b], lo = 0, hi = len; /* first i with ka[i] >= key */
-	while (lo < hi) {
-		int64_t mid = (lo + hi) >> 1;
-		if (ka[mid] < key) lo = mid + 1; else hi = mid;
-	}
-	blo[b] = lo;
-}
-
-template<bool WRITE> struct Emit {
-	int sym; int64_t len, e; uint4 *out;
-	__device__ __forceinline__ void flush() {
-		if (len > 0) {
-			if (WRITE) e = rb3b_emit_run(out, e, sym, len);
-			else e += rb3b_nent(len);
-		}
-	}
-	__device__ __forceinline__ void put(int c, int64_t l) {
-		if (c == sym) len += l;
-		else { flush(); sym = c; len = l; }
-	}
-};
-
-/* one thread per tile = block b of A plus the batch rows that fall inside it */
-template<bool WRITE>
-__global__ void __launch_bounds__(128) k_merge(int64_t nb, const uint4 *__restrict__ blocks, const uint64_t *__restrict__ bstart, const int64_t *__restrict__ blo,
-                                               const int64_t *__restrict__ ka, const uint8_t *__restrict__ bwt,
-                                               int64_t *__restrict__ cnt, const int64_t *__restrict__ eoff, uint4 *out)
-{
-	int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (b >= nb) return;
-	Emit<WRITE> E;
-	E.sym = -1; E.len = 0; E.e = WRITE ? eoff[b] : 0; E.out = out;
-	int64_t pos = (int64_t)bstart[b], i = blo[b], iend = blo[b + 1];
-	int64_t nxt = i < iend ? ka[i] : INT64_MAX;
-	for (int q = 2; q < 8; ++q) {
-		uint4 v = blocks[b * 8 + q];
-		const uint32_t w[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-		for (int j = 0; j < 8; ++j) {
-			uint32_t e = (w[j >> 1] >> (16 * (j & 1))) & 0xffffu;
-			int64_t l = rb3b_ent_len(e);
-			int s = e >> 13;
-			if (l == 0) continue;
-			while (nxt < pos + l) { /* a batch row lands inside (or right before) this run */
-				int64_t t = nxt - pos;
-				if (t > 0) { E.put(s, t); l -= t; pos += t; }
-				E.put(bwt[i], 1);
-				++i;
-				nxt = i < iend ? ka[i] : INT64_MAX;
-			}
-			E.put(s, l); pos += l;
-		}
-	}
-	for (; i < iend; ++i) E.put(bwt[i], 1); /* rows that go after the very last symbol of A */
-	E.flush();
-	if (!WRITE) cnt[b] = E.e;
-}
 
 static int merge_phase(rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, const int64_t *d_ka)
 {
-	int64_t nb = A->n_blocks, last[2];
-	DBuf<int64_t> blo, cnt, eoff;
 	DBuf<int> bad;
 	int hbad = 0;
-	TRY(blo.alloc(nb + 1)); TRY(cnt.alloc(nb)); TRY(eoff.alloc(nb)); TRY(bad.alloc(1));
+	TRY(bad.alloc(1));
 	CK(cudaMemsetAsync(bad.p, 0, sizeof(int), rb3b_stream));
 	rb3b_tic(T_MERGE);
 	k_check_monotone<<<nblk(len, TPB), TPB, 0, rb3b_stream>>>(len, d_ka, A->n, bad.p); CKK();
-	k_tile_bounds<<<nblk(nb + 1, TPB), TPB, 0, rb3b_stream>>>(nb, A->bstart, len, d_ka, blo.p); CKK();
-	k_merge<false><<<nblk(nb, 128), 128, 0, rb3b_stream>>>(nb, A->blocks, A->bstart, blo.p, d_ka, d_bwt, cnt.p, 0, 0); CKK();
-	TRY(rb3b_scan_excl_i64(cnt.p, eoff.p, nb));
-	CK(cudaMemcpyAsync(&last[0], eoff.p + nb - 1, 8, cudaMemcpyDeviceToHost, rb3b_stream));
-	CK(cudaMemcpyAsync(&last[1], cnt.p + nb - 1, 8, cudaMemcpyDeviceToHost, rb3b_stream));
 	CK(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, rb3b_stream));
 	CK(cudaStreamSynchronize(rb3b_stream));
 	if (hbad) return rb3b_fail(RB3B_EINVAL, "interleave positions are not monotone: the batch is not a valid BWT");
-	int64_t n_ent = last[0] + last[1], nb2 = (n_ent + RB3B_ENT_PER_BLK - 1) / RB3B_ENT_PER_BLK;
-	if (nb2 >= (1LL << 32) - 16) return rb3b_fail(RB3B_EINVAL, "index too large for 32-bit block ids");
-	TRY(rb3b_reserve((void**)&A->spare, &A->cap_spare, nb2 * 8, sizeof(uint4)));
-	CK(cudaMemsetAsync(A->spare + (nb2 - 1) * 8, 0, 128, rb3b_stream)); /* padding of the last block; everything else is written */
-	k_merge<true><<<nblk(nb, 128), 128, 0, rb3b_stream>>>(nb, A->blocks, A->bstart, blo.p, d_ka, d_bwt, 0, eoff.p, A->spare); CKK();
+	CellSrc src;
+	src.R.cells = A->cells; src.R.ovf = A->ovf; src.R.n = A->n; src.R.shift = A->shift;
+	src.R.j = 0; src.R.left = 0; src.R.eidx = 0; src.R.first = 0xffffffffu; src.R.cur = -1; src.R.rem = 0;
+	src.n = A->n; src.cur = -1;
+	/* every inserted row adds at most two entries; most extend or split a run of a shared column */
+	int rc = rb3b_emit_build(A, src, A->n, len, d_ka, d_bwt, A->n_entries + len / 2);
 	rb3b_toc(T_MERGE);
-	{ uint4 *t = A->blocks; A->blocks = A->spare; A->spare = t; int64_t c = A->cap_blocks; A->cap_blocks = A->cap_spare; A->cap_spare = c; }
-	A->n_blocks = nb2; A->n_entries = n_ent;
-	rb3b_tic(T_FINAL);
-	int rc = rb3b_index_finalize(A);
-	rb3b_toc(T_FINAL);
 	cudaStreamSynchronize(rb3b_stream);
 	rb3b_tflush();
 	return rc;
@@ -553,7 +480,7 @@ extern "C" int rb3b_merge_plain_dev(rb3b_index_t *x, int64_t len, const uint8_t 
 {
 	TRY(rb3b_ensure_init());
 	if (len <= 0) return RB3B_OK;
-	if (x->n_blocks == 0) return rb3b_index_from_plain_dev(x, len, d_bwt);
+	if (x->n_cells == 0) return rb3b_index_from_plain_dev(x, len, d_bwt);
 	DBuf<int64_t> ka;
 	int64_t accB[RB3B_ASIZE + 1];
 	TRY(rank_phase(x, len, d_bwt, ka, accB));

@@ -1,7 +1,7 @@
 /*
  * rb3b_rank_tma.cu -- LF/rank kernel, bulk-copy (TMA engine) variant.
  *
- * Same arithmetic as k_lf (rb3b_index.cu) but the 128-B index block of every
+ * Same arithmetic as k_lf (rb3b_index.cu) but the 128-B index cell of every
  * query is fetched with cp.async.bulk (SASS UBLKCP) into a per-group ring of
  * shared-memory stages and its arrival is tracked with an mbarrier, so each
  * 8-lane group keeps NST block fetches in flight instead of one and no
@@ -60,11 +60,10 @@ __global__ void __launch_bounds__(TPB) k_lf_tma(DevIndex x, int64_t nq, const in
 			kq[s] = k_[q]; cq[s] = c_[q]; if (kq[s] < 0) kq[s] = 0; \
 			if (kq[s] >= x.n) kind[s] = 2; \
 			else { \
-				int64_t b_ = G8::locate(x, kq[s]); \
 				if (gl == 0) { \
 					uint32_t bar_ = smem_u32(&bars[gi][s]); \
 					mbar_expect_tx(bar_, 128); \
-					bulk_g2s(smem_u32(&stage[gi][s][0]), x.blocks + b_ * 8, 128, bar_); \
+					bulk_g2s(smem_u32(&stage[gi][s][0]), x.cells + (kq[s] >> x.shift) * 8, 128, bar_); \
 				} \
 				kind[s] = 1; \
 			} \
@@ -83,7 +82,7 @@ __global__ void __launch_bounds__(TPB) k_lf_tma(DevIndex x, int64_t nq, const in
 				uint4 v[1];
 				v[0] = stage[gi][s][gl];
 				const int c = cq[s];
-				int64_t r = G8::count(v, kq[s], c);
+				int64_t r = G8::count(x, v, kq[s], c);
 				if (gl == 0) out[q] = x.acc[c] + r;
 			}
 			__syncwarp(gmask); /* every lane has read the stage before it is refilled */

@@ -44,6 +44,45 @@ def test_rank1a_random_runs(rb3, oracle, n_runs, max_len, big):
     assert np.array_equal(np.diff(acc), tot)
 
 
+def test_overflow_cells(rb3, oracle):
+    """Mostly long runs (wide cells) with dense stretches of length-1 runs: cells with > 48 runs use overflow blocks."""
+    rng = np.random.default_rng(5)
+    sym, ln = [], []
+    for rep in range(40):
+        k = int(rng.integers(100, 3000))
+        s = rng.integers(0, 6, k).astype(np.uint8)
+        for i in range(1, k):
+            if s[i] == s[i - 1]:
+                s[i] = (s[i] + 1) % 6
+        sym.append(s); ln.append(np.ones(k, np.int64))
+        s2, l2 = np.array([(s[-1] + 1) % 6, (s[-1] + 2) % 6], np.uint8), rng.integers(50000, 2000000, 2)
+        sym.append(s2); ln.append(l2.astype(np.int64))
+    sym, ln = oracle.coalesce(np.concatenate(sym), np.concatenate(ln))
+    idx = rb3.Index.from_runs(sym, ln)
+    assert rb3.get_stat("cell_shift") == 10 and rb3.get_stat("n_ovf_cells") > 0
+    n = int(ln.sum())
+    starts = np.concatenate([[0], np.cumsum(ln)])
+    k = np.concatenate([rng.integers(0, n, 5000), starts[:-1], starts[1:] - 1, starts[rng.integers(0, len(starts) - 1, 3000)] + 1, [n]]).astype(np.int64)
+    k = np.minimum(k, n)
+    ok, ret = idx.rank1a(k)
+    ok0, ret0 = oracle.rank1a(sym, ln, k)
+    bad = np.flatnonzero((ok != ok0).any(1) | (ret != ret0))
+    assert len(bad) == 0, "first mismatch at k=%d: got %s/%d want %s/%d" % (k[bad[0]], ok[bad[0]], ret[bad[0]], ok0[bad[0]], ret0[bad[0]])
+    s2, l2 = runs_of(idx, oracle)
+    assert np.array_equal(s2, sym) and np.array_equal(l2, ln)
+    # merging into an index with overflow cells: insert a batch whose rows land everywhere
+    text = np.concatenate([rng.integers(1, 5, 3000).astype(np.uint8), [0]])
+    bwt = oracle.build_bwt(text)
+    # positions do not matter for the writer test: use the oracle for both the interleave and the merge
+    rb0, _ = oracle.mg_rank_plain(sym, ln, bwt)
+    rb, _ = idx.mg_rank_plain(bwt)
+    assert np.array_equal(rb, rb0)
+    idx.merge_plain(bwt)
+    s3, l3 = runs_of(idx, oracle)
+    s4, l4 = oracle.merge_runs(sym, ln, rb0)
+    assert np.array_equal(s3, s4) and np.array_equal(l3, l4)
+
+
 def test_rank1a_golden(rb3, oracle, golden):
     for name in MERGE_SETS + ["long_runs"]:
         g = golden(name)
