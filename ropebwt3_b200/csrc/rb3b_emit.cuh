@@ -65,6 +65,16 @@ struct CellSrc {
 	__device__ __forceinline__ void advance(uint32_t l) { R.advance(l); cur = R.cur; }
 };
 
+/* source stream given as a bitmap index */
+struct BmSrc {
+	BmReader R;
+	int64_t n;
+	int cur;
+	__device__ __forceinline__ void seek(int64_t pos) { R.seek(pos); cur = R.cur; }
+	__device__ __forceinline__ uint32_t avail(int64_t lim) const { return (uint32_t)((int64_t)R.rem < lim ? (int64_t)R.rem : lim); }
+	__device__ __forceinline__ void advance(uint32_t l) { R.advance(l); cur = R.cur; }
+};
+
 template<bool WRITE> struct CellEmitter {
 	int sym; uint32_t len, ne, pos;
 	uint32_t cc[RB3B_ASIZE];
@@ -244,13 +254,152 @@ static int rb3b_emit_build(rb3b_index_s *x, Src src, int64_t n_src, int64_t lenB
 	/* swap the ping-pong halves (the kernels that read the old half are already enqueued on the same stream) */
 	{ uint4 *t = x->cells; x->cells = x->cells2; x->cells2 = t; int64_t c = x->cap_cells; x->cap_cells = x->cap_cells2; x->cap_cells2 = c; }
 	{ uint4 *t = x->ovf; x->ovf = x->ovf2; x->ovf2 = t; int64_t c = x->cap_ovf; x->cap_ovf = x->cap_ovf2; x->cap_ovf2 = c; }
-	x->shift = shift; x->n_cells = O.n_cells; x->n_ovf = n_ovf; x->n_entries = (int64_t)hstats[0];
+	x->kind = RB3B_KIND_RLE; x->shift = shift; x->n_cells = O.n_cells; x->n_ovf = n_ovf; x->n_entries = (int64_t)hstats[0];
+	rb3b_stat_set("index_kind", RB3B_KIND_RLE);
 	x->acc[0] = 0;
 	for (int a = 0; a < RB3B_ASIZE; ++a) { x->tot[a] = tot[a] - base[a]; x->acc[a + 1] = x->acc[a] + x->tot[a]; }
 	x->n = x->acc[RB3B_ASIZE];
 	x->bytes = (size_t)(O.n_cells + n_ovf) * 128;
 	rb3b_stat_set("n_cells", O.n_cells); rb3b_stat_set("n_ovf_blocks", n_ovf); rb3b_stat_set("n_ovf_cells", (int64_t)hstats[1]);
 	rb3b_stat_set("cell_shift", shift); rb3b_stat_set("n_entries", (int64_t)hstats[0]);
+	if (x->n != n_out) return rb3b_fail(RB3B_EINVAL, "internal error: wrote %lld symbols, expected %lld", (long long)x->n, (long long)n_out);
+	return RB3B_OK;
+}
+
+
+/* ------------------------------------------------------------------ */
+/* bitmap output                                                        */
+/* ------------------------------------------------------------------ */
+
+/* One thread per output cell of 128 positions.  The planes are assembled in registers-backed local memory and
+ * written once; quad 0 temporarily receives the cell's own six symbol counts (6 x u16), which k_bm_fin_* turn into
+ * the absolute header counts with a two-level scan. */
+template<class Src>
+__global__ void __launch_bounds__(EMIT_TPB) k_emit_bm(Src src, EmitOut O, int64_t lenB, const int64_t *__restrict__ ka, const uint8_t *__restrict__ bwt,
+                                                       const int64_t *__restrict__ ilo)
+{
+	const int64_t j = (int64_t)blockIdx.x * EMIT_TPB + threadIdx.x;
+	if (j >= O.n_cells) return;
+	uint32_t pl[RB3B_ASIZE][4];
+#pragma unroll
+	for (int a = 0; a < RB3B_ASIZE; ++a)
+#pragma unroll
+		for (int w = 0; w < 4; ++w) pl[a][w] = 0;
+	const int64_t P0 = j << RB3B_BM_SHIFT, P1 = P0 + 128 < O.n_out ? P0 + 128 : O.n_out;
+	int64_t i = ilo ? ilo[j] : 0, iend = ilo ? ilo[j + 1] : 0, P = P0;
+	int64_t nextB = i < iend ? ka[i] + i : INT64_MAX;
+	if (P0 - i < src.n) src.seek(P0 - i);
+	while (P < P1) {
+		int sym; uint32_t t;
+		if (nextB == P) {
+			sym = bwt[i]; t = 1;
+			++i;
+			nextB = i < iend ? ka[i] + i : INT64_MAX;
+		} else {
+			t = src.avail((nextB < P1 ? nextB : P1) - P);
+			sym = src.cur;
+			src.advance(t);
+		}
+		/* set bits [p, p+t) of plane sym */
+		uint32_t p = (uint32_t)(P - P0), e = p + t;
+#pragma unroll
+		for (int w = 0; w < 4; ++w) {
+			int lo = (int)p - 32 * w, hi = (int)e - 32 * w;
+			lo = lo < 0 ? 0 : lo; hi = hi > 32 ? 32 : hi;
+			if (lo < hi) {
+				uint32_t m = (hi == 32 ? 0xffffffffu : (1u << hi) - 1u) & ~((1u << lo) - 1u);
+#pragma unroll
+				for (int a = 0; a < RB3B_ASIZE; ++a) pl[a][w] |= a == sym ? m : 0u;
+			}
+		}
+		P += t;
+	}
+	uint4 *cell = O.cells + j * 8;
+	uint32_t c[RB3B_ASIZE];
+#pragma unroll
+	for (int a = 0; a < RB3B_ASIZE; ++a) {
+		c[a] = __popc(pl[a][0]) + __popc(pl[a][1]) + __popc(pl[a][2]) + __popc(pl[a][3]);
+		cell[rb3b_bm_plane_quad(a)] = make_uint4(pl[a][0], pl[a][1], pl[a][2], pl[a][3]);
+	}
+	cell[0] = make_uint4(c[0] | c[1] << 16, c[2] | c[3] << 16, c[4] | c[5] << 16, 0u);
+}
+
+__device__ __forceinline__ void rb3b_bm_local_counts(const uint4 *cells, int64_t j, int64_t c[RB3B_ASIZE])
+{
+	uint4 q = cells[j * 8];
+	c[0] = q.x & 0xffffu; c[1] = q.x >> 16; c[2] = q.y & 0xffffu; c[3] = q.y >> 16; c[4] = q.z & 0xffffu; c[5] = q.z >> 16;
+}
+
+/* chunk totals of the per-cell counts left in quad 0 by k_emit_bm; layout [6][n_chunks+1] */
+static __global__ void __launch_bounds__(EMIT_TPB) k_bm_fin_count(EmitOut O, int64_t *__restrict__ ctot)
+{
+	typedef cub::BlockReduce<int64_t, EMIT_TPB> Red;
+	__shared__ typename Red::TempStorage tmp[RB3B_ASIZE];
+	const int64_t j = (int64_t)blockIdx.x * EMIT_TPB + threadIdx.x;
+	int64_t c[RB3B_ASIZE] = {0, 0, 0, 0, 0, 0};
+	if (j < O.n_cells) rb3b_bm_local_counts(O.cells, j, c);
+#pragma unroll
+	for (int a = 0; a < RB3B_ASIZE; ++a) {
+		int64_t t = Red(tmp[a]).Sum(c[a]);
+		if (threadIdx.x == 0) ctot[(int64_t)a * (O.n_chunks + 1) + blockIdx.x] = t;
+	}
+	if (blockIdx.x == 0 && threadIdx.x < RB3B_ASIZE) ctot[(int64_t)threadIdx.x * (O.n_chunks + 1) + O.n_chunks] = 0;
+}
+
+static __global__ void __launch_bounds__(EMIT_TPB) k_bm_fin_write(EmitOut O, const int64_t *__restrict__ cex)
+{
+	typedef cub::BlockScan<int64_t, EMIT_TPB> Scan;
+	__shared__ typename Scan::TempStorage tmp[RB3B_ASIZE];
+	const int64_t j = (int64_t)blockIdx.x * EMIT_TPB + threadIdx.x;
+	int64_t c[RB3B_ASIZE] = {0, 0, 0, 0, 0, 0};
+	if (j < O.n_cells) rb3b_bm_local_counts(O.cells, j, c);
+	uint64_t h[RB3B_ASIZE];
+#pragma unroll
+	for (int a = 0; a < RB3B_ASIZE; ++a) {
+		int64_t ex;
+		Scan(tmp[a]).ExclusiveSum(c[a], ex);
+		h[a] = (uint64_t)(ex + cex[(int64_t)a * (O.n_chunks + 1) + blockIdx.x] - cex[(int64_t)a * (O.n_chunks + 1)]);
+	}
+	if (j < O.n_cells) {
+		O.cells[j * 8] = rb3b_hdr_pack(h[0], h[1], h[2], false);
+		O.cells[j * 8 + 4] = rb3b_hdr_pack(h[3], h[4], h[5], false);
+	}
+}
+
+template<class Src>
+static int rb3b_emit_build_bm(rb3b_index_s *x, Src src, int64_t n_src, int64_t lenB, const int64_t *d_ka, const uint8_t *d_bwt)
+{
+	const int64_t n_out = n_src + lenB;
+	DBuf<int64_t> ilo, ctot, cex;
+	EmitOut O;
+	O.shift = RB3B_BM_SHIFT; O.n_out = n_out;
+	O.n_cells = (n_out + 127) >> RB3B_BM_SHIFT;
+	O.n_chunks = (O.n_cells + EMIT_TPB - 1) / EMIT_TPB;
+	TRY(ctot.alloc((O.n_chunks + 1) * RB3B_ASIZE)); TRY(cex.alloc((O.n_chunks + 1) * RB3B_ASIZE));
+	if (lenB > 0) {
+		TRY(ilo.alloc(O.n_cells + 1));
+		k_tile_bounds<<<(unsigned)((O.n_cells + 1 + 255) / 256), 256, 0, rb3b_stream>>>(O.n_cells, O.shift, lenB, d_ka, ilo.p); CKK();
+	}
+	TRY(rb3b_reserve((void**)&x->cells2, &x->cap_cells2, O.n_cells * 8, sizeof(uint4)));
+	O.cells = x->cells2; O.ovf = 0;
+	k_emit_bm<Src><<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(src, O, lenB, d_ka, d_bwt, lenB > 0 ? ilo.p : 0); CKK();
+	k_bm_fin_count<<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(O, ctot.p); CKK();
+	TRY(rb3b_scan_excl_i64(ctot.p, cex.p, (O.n_chunks + 1) * RB3B_ASIZE));
+	k_bm_fin_write<<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(O, cex.p); CKK();
+	int64_t tot[RB3B_ASIZE], base[RB3B_ASIZE];
+	for (int a = 0; a < RB3B_ASIZE; ++a) {
+		CK(cudaMemcpyAsync(&tot[a], cex.p + a * (O.n_chunks + 1) + O.n_chunks, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+		CK(cudaMemcpyAsync(&base[a], cex.p + a * (O.n_chunks + 1), 8, cudaMemcpyDeviceToHost, rb3b_stream));
+	}
+	CK(cudaStreamSynchronize(rb3b_stream));
+	{ uint4 *t = x->cells; x->cells = x->cells2; x->cells2 = t; int64_t c = x->cap_cells; x->cap_cells = x->cap_cells2; x->cap_cells2 = c; }
+	x->kind = RB3B_KIND_BM; x->shift = RB3B_BM_SHIFT; x->n_cells = O.n_cells; x->n_ovf = 0; x->n_entries = 0;
+	x->acc[0] = 0;
+	for (int a = 0; a < RB3B_ASIZE; ++a) { x->tot[a] = tot[a] - base[a]; x->acc[a + 1] = x->acc[a] + x->tot[a]; }
+	x->n = x->acc[RB3B_ASIZE];
+	x->bytes = (size_t)O.n_cells * 128;
+	rb3b_stat_set("n_cells", O.n_cells); rb3b_stat_set("n_ovf_blocks", 0); rb3b_stat_set("n_ovf_cells", 0);
+	rb3b_stat_set("cell_shift", RB3B_BM_SHIFT); rb3b_stat_set("index_kind", RB3B_KIND_BM);
 	if (x->n != n_out) return rb3b_fail(RB3B_EINVAL, "internal error: wrote %lld symbols, expected %lld", (long long)x->n, (long long)n_out);
 	return RB3B_OK;
 }

@@ -140,6 +140,17 @@ int rb3b_pick_shift(int64_t n, int64_t n_entries_est)
 	return shift;
 }
 
+int64_t rb3b_get_param(const char *key, int64_t dflt); /* rb3b_runtime.cu */
+
+/* bitmap cells cost 1 byte per symbol (twice that with the ping-pong half): use them while that is affordable */
+int rb3b_want_bitmap(int64_t n_symbols)
+{
+	int64_t kind = rb3b_get_param("index_kind", 0); /* 0 auto, 1 RLE cells, 2 bitmap cells */
+	if (kind == 1) return 0;
+	if (kind == 2) return 1;
+	return n_symbols <= rb3b_get_param("bitmap_max_symbols", 24000000000LL);
+}
+
 int rb3b_index_free_dev(rb3b_index_s *x)
 {
 	if (x->cells) cudaFreeAsync(x->cells, rb3b_stream);
@@ -172,6 +183,7 @@ int rb3b_index_from_runs_dev(rb3b_index_s *x, int64_t n_runs, const uint8_t *d_s
 	if (n >= (1LL << 42)) return rb3b_fail(RB3B_EINVAL, "index longer than 2^42 symbols is not supported by the 42-bit cell headers");
 	RunSrc src;
 	src.sym = d_sym; src.start = start.p; src.n_runs = n_runs; src.n = n; src.r = 0; src.rem64 = 0; src.cur = -1;
+	if (rb3b_want_bitmap(n)) return rb3b_emit_build_bm(x, src, n, 0, 0, 0);
 	return rb3b_emit_build(x, src, n, 0, 0, 0, n_runs);
 }
 
@@ -179,48 +191,60 @@ int rb3b_index_from_runs_dev(rb3b_index_s *x, int64_t n_runs, const uint8_t *d_s
 /* export: cells -> canonical (coalesced) run list                      */
 /* ------------------------------------------------------------------ */
 
-/* one thread per cell: a run starts at every entry whose symbol differs from the symbol just before it */
-template<bool WRITE>
-__global__ void k_export(DevIndex x, int64_t *__restrict__ cnt, const int64_t *__restrict__ off, uint8_t *__restrict__ rsym, int64_t *__restrict__ rpos)
+/* one thread per cell: a run starts wherever the symbol differs from the symbol just before it */
+template<class Reader, bool WRITE>
+__global__ void k_export(Reader R, int shift, int64_t n, int64_t n_cells, int64_t *__restrict__ cnt, const int64_t *__restrict__ off, uint8_t *__restrict__ rsym, int64_t *__restrict__ rpos)
 {
 	int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= x.n_cells) return;
-	CellReader R;
-	R.cells = x.cells; R.ovf = x.ovf; R.n = x.n; R.shift = x.shift;
-	int prev = -1, n = 0;
-	if (j > 0) { R.seek((j << x.shift) - 1); prev = R.cur; }
-	int64_t pos = j << x.shift, end = pos + (1LL << x.shift) < x.n ? pos + (1LL << x.shift) : x.n, o = WRITE ? off[j] : 0;
+	if (j >= n_cells) return;
+	int prev = -1, m = 0;
+	if (j > 0) { R.seek((j << shift) - 1); prev = R.cur; }
+	int64_t pos = j << shift, end = pos + (1LL << shift) < n ? pos + (1LL << shift) : n, o = WRITE ? off[j] : 0;
 	R.seek(pos);
 	while (pos < end) {
 		if (R.cur != prev) {
-			if (WRITE) { rsym[o + n] = (uint8_t)R.cur; rpos[o + n] = pos; }
-			++n; prev = R.cur;
+			if (WRITE) { rsym[o + m] = (uint8_t)R.cur; rpos[o + m] = pos; }
+			++m; prev = R.cur;
 		}
 		uint32_t l = R.rem;
+		if ((int64_t)l > end - pos) l = (uint32_t)(end - pos);
 		pos += l;
 		if (pos < end) R.advance(l);
 	}
-	if (!WRITE) cnt[j] = n;
+	if (!WRITE) cnt[j] = m;
 }
 
-int rb3b_export_runs_dev(const rb3b_index_s *x, DBuf<uint8_t> &sym, DBuf<int64_t> &len, int64_t *n_runs)
+template<class Reader>
+static int export_with(Reader R, const rb3b_index_s *x, DBuf<uint8_t> &sym, DBuf<int64_t> &len, int64_t *n_runs)
 {
 	int64_t nc = x->n_cells, last[2];
-	*n_runs = 0;
-	if (nc == 0) return RB3B_OK;
 	DBuf<int64_t> cnt, off, pos;
-	DevIndex d = rb3b_dev_view(x);
 	TRY(cnt.alloc(nc)); TRY(off.alloc(nc));
-	k_export<false><<<nblk(nc, 128), 128, 0, rb3b_stream>>>(d, cnt.p, 0, 0, 0); CKK();
+	k_export<Reader, false><<<nblk(nc, 128), 128, 0, rb3b_stream>>>(R, x->shift, x->n, nc, cnt.p, 0, 0, 0); CKK();
 	TRY(rb3b_scan_excl_i64(cnt.p, off.p, nc));
 	CK(cudaMemcpyAsync(&last[0], off.p + nc - 1, 8, cudaMemcpyDeviceToHost, rb3b_stream));
 	CK(cudaMemcpyAsync(&last[1], cnt.p + nc - 1, 8, cudaMemcpyDeviceToHost, rb3b_stream));
 	CK(cudaStreamSynchronize(rb3b_stream));
 	*n_runs = last[0] + last[1];
 	TRY(sym.alloc(*n_runs)); TRY(pos.alloc(*n_runs)); TRY(len.alloc(*n_runs));
-	k_export<true><<<nblk(nc, 128), 128, 0, rb3b_stream>>>(d, 0, off.p, sym.p, pos.p); CKK();
+	k_export<Reader, true><<<nblk(nc, 128), 128, 0, rb3b_stream>>>(R, x->shift, x->n, nc, 0, off.p, sym.p, pos.p); CKK();
 	k_starts_to_len<<<nblk(*n_runs, TPB), TPB, 0, rb3b_stream>>>(*n_runs, x->n, pos.p, len.p); CKK();
 	return RB3B_OK;
+}
+
+int rb3b_export_runs_dev(const rb3b_index_s *x, DBuf<uint8_t> &sym, DBuf<int64_t> &len, int64_t *n_runs)
+{
+	*n_runs = 0;
+	if (x->n_cells == 0) return RB3B_OK;
+	if (x->kind == RB3B_KIND_BM) {
+		BmReader R;
+		R.cells = x->cells; R.n = x->n; R.pos = 0; R.cur = -1; R.rem = 0;
+		return export_with(R, x, sym, len, n_runs);
+	}
+	CellReader R;
+	R.cells = x->cells; R.ovf = x->ovf; R.n = x->n; R.shift = x->shift;
+	R.j = 0; R.left = 0; R.eidx = 0; R.first = 0xffffffffu; R.cur = -1; R.rem = 0;
+	return export_with(R, x, sym, len, n_runs);
 }
 
 /* ------------------------------------------------------------------ */
@@ -253,26 +277,70 @@ __global__ void __launch_bounds__(TPB) k_rank1a(DevIndex x, int64_t nq, const in
 	}
 }
 
-/* LF flavour used by the merge: out = C[c] + rank(c,k); 144 algorithmic bytes per query */
-template<int G>
-__global__ void __launch_bounds__(TPB) k_lf(DevIndex x, int64_t nq, const int64_t *__restrict__ k_, const uint8_t *__restrict__ c_, int64_t *__restrict__ out)
+/* bitmap cells: one thread per query */
+__global__ void __launch_bounds__(TPB) k_rank1a_bm(DevIndex x, int64_t nq, const int64_t *__restrict__ k_, int64_t *__restrict__ ok, int8_t *__restrict__ sym)
 {
-	const int gl = Grp<G>::lane();
-	int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G, ng = ((int64_t)gridDim.x * blockDim.x) / G;
-	for (int64_t q = g; q < nq; q += ng) {
+	int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t q = t; q < nq; q += nt) {
 		int64_t k = k_[q];
-		int c = c_[q];
-		int64_t r = x.acc[c] + Grp<G>::rank(x, k, c);
-		if (gl == 0) out[q] = r;
+		int s = -1;
+		if (k >= x.n || k < 0) {
+			for (int a = 0; a < RB3B_ASIZE; ++a) ok[q * RB3B_ASIZE + a] = k < 0 ? 0 : x.tot[a];
+		} else {
+			for (int a = 0; a < RB3B_ASIZE; ++a) {
+				ok[q * RB3B_ASIZE + a] = BmRank::count(x, k, a);
+				uint32_t w = __ldg((const uint32_t*)(x.cells + (k >> RB3B_BM_SHIFT) * 8 + rb3b_bm_plane_quad(a)) + ((k & 127) >> 5));
+				if (w >> (k & 31) & 1u) s = a;
+			}
+		}
+		sym[q] = (int8_t)s;
 	}
 }
 
-template<int G> static int launch_lf(const rb3b_index_s *x, int64_t nq, const int64_t *d_k, const uint8_t *d_c, int64_t *d_out, int n_sm)
+__global__ void __launch_bounds__(TPB) k_lf_bm(DevIndex x, int64_t nq, const int64_t *__restrict__ k_, const uint8_t *__restrict__ c_, int64_t *__restrict__ out)
+{
+	int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t q = t; q < nq; q += nt) {
+		int c = c_[q];
+		out[q] = x.acc[c] + BmRank::rank(x, k_[q], c);
+	}
+}
+
+/* LF flavour used by the merge: out = C[c] + rank(c,k); 144 algorithmic bytes per query.
+ * Every group of G lanes works on U queries at a time so that U cell fetches are in flight per group. */
+template<int G, int U>
+__global__ void __launch_bounds__(TPB) k_lf(DevIndex x, int64_t nq, const int64_t *__restrict__ k_, const uint8_t *__restrict__ c_, int64_t *__restrict__ out)
+{
+	typedef Grp<G> GG;
+	const int gl = GG::lane();
+	int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G, ng = ((int64_t)gridDim.x * blockDim.x) / G;
+	for (int64_t q0 = g; q0 < nq; q0 += ng * U) {
+		int64_t k[U], kk[U];
+		int c[U];
+		uint4 v[U][GG::NQ];
+#pragma unroll
+		for (int u = 0; u < U; ++u) {
+			int64_t q = q0 + (int64_t)u * ng;
+			k[u] = q < nq ? k_[q] : 0; c[u] = q < nq ? c_[q] : 0;
+			kk[u] = k[u] < x.n ? (k[u] < 0 ? 0 : k[u]) : x.n - 1;
+			GG::load(x, kk[u] >> x.shift, v[u]);
+		}
+#pragma unroll
+		for (int u = 0; u < U; ++u) {
+			int64_t q = q0 + (int64_t)u * ng;
+			int64_t r = GG::count(x, v[u], kk[u], c[u]);
+			r = k[u] < x.n ? r : x.tot[c[u]];
+			if (gl == 0 && q < nq) out[q] = x.acc[c[u]] + r;
+		}
+	}
+}
+
+template<int G, int U> static int launch_lf(const rb3b_index_s *x, int64_t nq, const int64_t *d_k, const uint8_t *d_c, int64_t *d_out, int n_sm)
 {
 	int occ = 4;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lf<G>, TPB, 0);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lf<G, U>, TPB, 0);
 	int64_t want = (nq * G + TPB - 1) / TPB, cap = (int64_t)n_sm * (occ > 0 ? occ : 4);
-	k_lf<G><<<(unsigned)(want < cap ? want : cap), TPB, 0, rb3b_stream>>>(rb3b_dev_view(x), nq, d_k, d_c, d_out); CKK();
+	k_lf<G, U><<<(unsigned)(want < cap ? want : cap), TPB, 0, rb3b_stream>>>(rb3b_dev_view(x), nq, d_k, d_c, d_out); CKK();
 	return RB3B_OK;
 }
 
@@ -350,6 +418,11 @@ extern "C" int rb3b_rank1a_dev(const rb3b_index_t *x, int64_t nq, const int64_t 
 		CK(cudaMemsetAsync(d_sym, 0xff, nq, rb3b_stream));
 		return RB3B_OK;
 	}
+	if (x->kind == RB3B_KIND_BM) {
+		want = (nq + TPB - 1) / TPB;
+		k_rank1a_bm<<<(unsigned)(want < cap ? want : cap), TPB, 0, rb3b_stream>>>(rb3b_dev_view(x), nq, d_k, d_ok, d_sym); CKK();
+		return RB3B_OK;
+	}
 	k_rank1a<<<(unsigned)(want < cap ? want : cap), TPB, 0, rb3b_stream>>>(rb3b_dev_view(x), nq, d_k, d_ok, d_sym); CKK();
 	return RB3B_OK;
 }
@@ -371,15 +444,25 @@ extern "C" int rb3b_rank1a(const rb3b_index_t *x, int64_t nq, const int64_t *k, 
 int rb3b_lf_tma_launch(const rb3b_index_s *x, int64_t nq, const int64_t *d_k, const uint8_t *d_c, int64_t *d_out); /* rb3b_rank_tma.cu */
 
 extern "C" int rb3b_lf_dev(const rb3b_index_t *x, int64_t nq, const int64_t *d_k, const uint8_t *d_c, int64_t *d_out, int variant)
-{ /* variant: 0 default, 1 cp.async.bulk staged, 2/4/8 lanes per query */
+{ /* variant: 0 default, 1 cp.async.bulk staged, G (2/4/8) lanes per query, GU = G lanes with U queries in flight */
 	TRY(rb3b_ensure_init());
 	if (nq <= 0) return RB3B_OK;
 	if (x->n_cells == 0) return rb3b_fail(RB3B_EINVAL, "empty index");
+	if (x->kind == RB3B_KIND_BM) { /* bitmap cells have a single kernel: two 16-B loads and a popcount per query */
+		int64_t want = (nq + TPB - 1) / TPB, cap = (int64_t)n_sm() * 8 * 4;
+		k_lf_bm<<<(unsigned)(want < cap ? want : cap), TPB, 0, rb3b_stream>>>(rb3b_dev_view(x), nq, d_k, d_c, d_out); CKK();
+		return RB3B_OK;
+	}
 	if (variant == 1) return rb3b_lf_tma_launch(x, nq, d_k, d_c, d_out);
-	if (variant == 0) variant = (int)rb3b_rank_variant ? (int)rb3b_rank_variant : 4;
-	if (variant == 2) return launch_lf<2>(x, nq, d_k, d_c, d_out, n_sm());
-	if (variant == 4) return launch_lf<4>(x, nq, d_k, d_c, d_out, n_sm());
-	if (variant == 8) return launch_lf<8>(x, nq, d_k, d_c, d_out, n_sm());
+	if (variant == 0) variant = (int)rb3b_rank_variant ? (int)rb3b_rank_variant : 42;
+	if (variant == 2) return launch_lf<2, 1>(x, nq, d_k, d_c, d_out, n_sm());
+	if (variant == 4) return launch_lf<4, 1>(x, nq, d_k, d_c, d_out, n_sm());
+	if (variant == 8) return launch_lf<8, 1>(x, nq, d_k, d_c, d_out, n_sm());
+	if (variant == 22) return launch_lf<2, 2>(x, nq, d_k, d_c, d_out, n_sm()); /* G lanes, 2 queries in flight per group */
+	if (variant == 42) return launch_lf<4, 2>(x, nq, d_k, d_c, d_out, n_sm());
+	if (variant == 82) return launch_lf<8, 2>(x, nq, d_k, d_c, d_out, n_sm());
+	if (variant == 44) return launch_lf<4, 4>(x, nq, d_k, d_c, d_out, n_sm());
+	if (variant == 84) return launch_lf<8, 4>(x, nq, d_k, d_c, d_out, n_sm());
 	return rb3b_fail(RB3B_EINVAL, "unknown rank variant %d", variant);
 }
 

@@ -21,6 +21,14 @@
  * at an arithmetic address (plus one overflow block for the few dense cells),
  * read by a group of G = 2, 4 or 8 lanes with 16-B-per-lane loads and reduced
  * with shuffles.  shift is chosen per index so that an average cell is ~40% full.
+ *
+ * Second cell kind, BITMAP (kind = 1), used while the index fits 1 byte per
+ * symbol in HBM: span 128, two self-contained 64-B halves
+ *       quad 0   counts of $,A,C before the cell (3 x 42 bit)
+ *       quad 1-3 one-hot bit planes of $, A, C: bit p set <=> position p holds it
+ *       quad 4   counts of G,T,N            quad 5-7  planes of G, T, N
+ * rank(c, k) = count + popcount(plane below k): two 16-B loads inside one 64-B
+ * DRAM atom, ~20 instructions, one thread per query, no decoding at all.
  */
 #ifndef RB3B_INTERNAL_CUH
 #define RB3B_INTERNAL_CUH
@@ -37,6 +45,9 @@
 #define RB3B_MAX_SHIFT    10
 #define RB3B_LEN_MASK     0x1fffu
 #define RB3B_M42          ((1ULL << 42) - 1)
+#define RB3B_KIND_RLE     0
+#define RB3B_KIND_BM      1
+#define RB3B_BM_SHIFT     7
 #define RB3B_GROUP        8          /* lanes per query of the API rank kernels and of the LF walk */
 
 struct rb3b_index_s {
@@ -44,6 +55,7 @@ struct rb3b_index_s {
 	int64_t tot[RB3B_ASIZE];      /* marginal counts */
 	int64_t acc[RB3B_ASIZE + 1];  /* C[] */
 	int shift;                    /* log2 of the cell span */
+	int kind;                     /* RB3B_KIND_RLE or RB3B_KIND_BM */
 	int64_t n_cells, n_ovf, n_entries;
 	uint4 *cells, *ovf;           /* n_cells * 8 and n_ovf * 8 quads */
 	uint4 *cells2, *ovf2;         /* the other half of the ping-pong pair: the next merge writes here */
@@ -55,7 +67,7 @@ struct rb3b_index_s {
 struct DevIndex {
 	const uint4 *cells, *ovf;
 	int64_t n, n_cells;
-	int shift;
+	int shift, kind;
 	int64_t tot[RB3B_ASIZE];
 	int64_t acc[RB3B_ASIZE + 1];
 };
@@ -64,7 +76,7 @@ static inline DevIndex rb3b_dev_view(const rb3b_index_s *x)
 {
 	DevIndex d;
 	d.cells = x->cells; d.ovf = x->ovf;
-	d.n = x->n; d.n_cells = x->n_cells; d.shift = x->shift;
+	d.n = x->n; d.n_cells = x->n_cells; d.shift = x->shift; d.kind = x->kind;
 	for (int c = 0; c < RB3B_ASIZE; ++c) d.tot[c] = x->tot[c];
 	for (int c = 0; c <= RB3B_ASIZE; ++c) d.acc[c] = x->acc[c];
 	return d;
@@ -123,6 +135,7 @@ int rb3b_index_free_dev(rb3b_index_s *x);
 int rb3b_index_from_runs_dev(rb3b_index_s *x, int64_t n_runs, const uint8_t *d_sym, const int64_t *d_len);
 int rb3b_export_runs_dev(const rb3b_index_s *x, DBuf<uint8_t> &sym, DBuf<int64_t> &len, int64_t *n_runs);
 int rb3b_pick_shift(int64_t n, int64_t n_entries_est);
+int rb3b_want_bitmap(int64_t n_symbols);
 
 /* ---- device helpers ---- */
 #ifdef __CUDACC__
@@ -169,7 +182,8 @@ static __device__ __noinline__ uint32_t rb3b_ovf_count(const uint4 *__restrict__
  * Rank machinery for a group of G lanes (G = 2, 4 or 8) working on one query.
  * Lane gl holds quads [gl*NQ, (gl+1)*NQ) of the 128-B cell, NQ = 8/G.
  */
-template<int G> struct Grp {
+template<int G_> struct Grp {
+	static const int G = G_;
 	static const int NQ = 8 / G;
 	__device__ __forceinline__ static int lane() { return threadIdx.x & (G - 1); }
 	__device__ __forceinline__ static int base() { return threadIdx.x & 31 & ~(G - 1); }
@@ -309,6 +323,85 @@ struct CellReader {
 		}
 	}
 	__device__ __forceinline__ void advance(uint32_t l) { rem -= l; if (rem == 0) next_piece(); }
+};
+
+
+/* ---- bitmap cells ---- */
+
+__device__ __forceinline__ int rb3b_bm_plane_quad(int s) { return s < 3 ? 1 + s : 2 + s; }
+
+/* set bits of the 128-bit plane p among positions [0, off), 0 <= off <= 128 */
+__device__ __forceinline__ uint32_t rb3b_bm_popc_below(const uint4 p, uint32_t off)
+{
+	const uint32_t w[4] = { p.x, p.y, p.z, p.w };
+	uint32_t r = 0;
+#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		int t = (int)off - 32 * i;
+		uint32_t m = t >= 32 ? 0xffffffffu : t <= 0 ? 0u : (1u << t) - 1u;
+		r += __popc(w[i] & m);
+	}
+	return r;
+}
+
+/* one thread per query */
+struct BmRank {
+	static const int G = 1;
+	__device__ __forceinline__ static int lane() { return 0; }
+	__device__ __forceinline__ static int base() { return threadIdx.x & 31; }
+	__device__ __forceinline__ static unsigned mask() { return 1u << (threadIdx.x & 31); }
+	__device__ __forceinline__ static int64_t count(const DevIndex &x, int64_t k, int c)
+	{ /* 0 <= k < n */
+		const int h = c >= 3, cc = c - 3 * h;
+		const uint4 *half = x.cells + (k >> RB3B_BM_SHIFT) * 8 + 4 * h;
+		uint4 cq = __ldg(half), pq = __ldg(half + 1 + cc);
+		uint64_t a0, a1, a2;
+		rb3b_hdr_unpack(cq, a0, a1, a2);
+		return (int64_t)((cc == 0 ? a0 : cc == 1 ? a1 : a2) + rb3b_bm_popc_below(pq, (uint32_t)k & 127u));
+	}
+	__device__ __forceinline__ static int64_t rank(const DevIndex &x, int64_t k, int c)
+	{
+		int64_t kk = k < x.n ? (k < 0 ? 0 : k) : x.n - 1;
+		int64_t r = count(x, kk, c);
+		return k < x.n ? r : x.tot[c];
+	}
+	__device__ __forceinline__ static void rank2(const DevIndex &x, int64_t k1, int64_t k2, int c, int64_t &r1, int64_t &r2)
+	{
+		int64_t q1 = k1 < x.n ? k1 : x.n - 1, q2 = k2 < x.n ? k2 : x.n - 1, t = x.tot[c];
+		r1 = count(x, q1, c); r2 = count(x, q2, c);
+		r1 = k1 < x.n ? r1 : t; r2 = k2 < x.n ? r2 : t;
+	}
+};
+
+/* Sequential reader of a bitmap index as run pieces (same interface as CellReader) */
+struct BmReader {
+	const uint4 *cells;
+	int64_t n, pos; /* pos = position of the current piece */
+	int cur; uint32_t rem;
+	__device__ __forceinline__ uint32_t word(int64_t j, int s, int w) const { return __ldg((const uint32_t*)(cells + j * 8 + rb3b_bm_plane_quad(s)) + w); }
+	__device__ __forceinline__ void load_piece()
+	{ /* the maximal run starting at pos that stays inside pos's cell */
+		if (pos >= n) { cur = -1; rem = 0; return; }
+		const int64_t j = pos >> RB3B_BM_SHIFT;
+		uint32_t p = (uint32_t)pos & 127u, w = p >> 5, b = p & 31u;
+		int s = 0;
+#pragma unroll
+		for (int a = 1; a < RB3B_ASIZE; ++a) if (word(j, a, w) >> b & 1u) s = a;
+		cur = s;
+		uint32_t len = 0;
+		for (;;) {
+			uint32_t inv = ~(word(j, s, w) >> b); /* zero bits above the shifted-in zeros count as run ends */
+			uint32_t ones = inv ? (uint32_t)__ffs(inv) - 1u : 32u;
+			if (ones > 32u - b) ones = 32u - b;
+			len += ones;
+			if (ones < 32u - b || w == 3) break;
+			++w; b = 0;
+		}
+		int64_t cap = n - pos;
+		rem = (int64_t)len < cap ? len : (uint32_t)cap;
+	}
+	__device__ __forceinline__ void seek(int64_t p) { pos = p; load_piece(); }
+	__device__ __forceinline__ void advance(uint32_t l) { rem -= l; pos += l; if (rem == 0) load_piece(); }
 };
 
 #endif /* __CUDACC__ */

@@ -190,10 +190,11 @@ struct Segs {
 	int64_t *arr_lo, *arr_hi; /* bracket with which the walk arrived at succ's first row */
 };
 
-#define WALK_G 8
-typedef Grp<WALK_G> WG;
+/* The walk kernels are written for a "ranker" WG: Grp<8> (RLE cells, 8 lanes per walk) or BmRank (bitmap cells,
+ * one thread per walk). */
 
 /* round 1: every segment walks from its mark to the next mark */
+template<class WG>
 __global__ void __launch_bounds__(TPB) k_walk_first(DevIndex A, Acc7 accB, Segs S, Fine F, const uint64_t *__restrict__ lfb, int64_t *__restrict__ ka, int64_t *next_seg)
 {
 	const int gl = WG::lane(), gbase = WG::base();
@@ -244,6 +245,7 @@ __global__ void k_collect_first(Segs S, int64_t *__restrict__ wl_seg, int64_t *_
 }
 
 /* round >= 2: re-walk the unresolved prefix of each listed segment from its now exact start */
+template<class WG>
 __global__ void __launch_bounds__(TPB) k_walk_fix(DevIndex A, Segs S, const uint64_t *__restrict__ lfb, int64_t *__restrict__ ka, int64_t n_items,
                                                    const int64_t *__restrict__ wl_seg, const int64_t *__restrict__ wl_val, int64_t *next_item,
                                                    int64_t *__restrict__ nx_seg, int64_t *__restrict__ nx_val, unsigned long long *nx_n)
@@ -379,9 +381,14 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	CK(cudaMemsetAsync(ctr.p, 0, 8 * 8, rb3b_stream));
 	CK(cudaMemsetAsync(ka.p, 0xff, len * 8, rb3b_stream));
 	DevIndex dA = rb3b_dev_view(A);
-	int64_t groups = S.n_seg, want = (groups * WALK_G + TPB - 1) / TPB, cap = (int64_t)n_sm() * 8;
+	const bool bm = A->kind == RB3B_KIND_BM;
+	/* bitmap walks are single threads: small CTAs spread the few thousand walks over all SMs */
+	const int wg = bm ? 1 : 8, wtpb = bm ? 32 : TPB;
+	int64_t want = (S.n_seg * wg + wtpb - 1) / wtpb, cap = (int64_t)n_sm() * (bm ? 32 : 8);
 	rb3b_tic(T_WALK1);
-	k_walk_first<<<(unsigned)(want < cap ? want : cap), TPB, 0, rb3b_stream>>>(dA, acc, S, F, lfb.p, ka.p, ctr.p); CKK();
+	if (bm) k_walk_first<BmRank><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, acc, S, F, lfb.p, ka.p, ctr.p);
+	else k_walk_first<Grp<8> ><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, acc, S, F, lfb.p, ka.p, ctr.p);
+	CKK();
 	rb3b_toc(T_WALK1);
 	int64_t *wl_seg[2] = { wl.p, wl.p + 2 * S.n_seg }, *wl_val[2] = { wl.p + S.n_seg, wl.p + 3 * S.n_seg };
 	k_collect_first<<<nblk(S.n_seg, TPB), TPB, 0, rb3b_stream>>>(S, wl_seg[0], wl_val[0], (unsigned long long*)(ctr.p + 1)); CKK();
@@ -392,10 +399,13 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	while (n_items > 0) {
 		/* ctr[2] = item cursor, ctr[3] = size of the next list */
 		CK(cudaMemsetAsync(ctr.p + 2, 0, 16, rb3b_stream));
-		want = (n_items * WALK_G + TPB - 1) / TPB;
+		want = (n_items * wg + wtpb - 1) / wtpb;
 		rb3b_tic(T_WALKFIX);
-		k_walk_fix<<<(unsigned)(want < cap ? want : cap), TPB, 0, rb3b_stream>>>(dA, S, lfb.p, ka.p, n_items, wl_seg[cur], wl_val[cur], ctr.p + 2,
-			wl_seg[cur ^ 1], wl_val[cur ^ 1], (unsigned long long*)(ctr.p + 3)); CKK();
+		if (bm) k_walk_fix<BmRank><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, S, lfb.p, ka.p, n_items, wl_seg[cur], wl_val[cur], ctr.p + 2,
+			wl_seg[cur ^ 1], wl_val[cur ^ 1], (unsigned long long*)(ctr.p + 3));
+		else k_walk_fix<Grp<8> ><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, S, lfb.p, ka.p, n_items, wl_seg[cur], wl_val[cur], ctr.p + 2,
+			wl_seg[cur ^ 1], wl_val[cur ^ 1], (unsigned long long*)(ctr.p + 3));
+		CKK();
 		rb3b_toc(T_WALKFIX);
 		fix_rows += n_items;
 		CK(cudaMemcpyAsync(&n_items, ctr.p + 3, 8, cudaMemcpyDeviceToHost, rb3b_stream));
@@ -436,12 +446,21 @@ static int merge_phase(rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, const
 	CK(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, rb3b_stream));
 	CK(cudaStreamSynchronize(rb3b_stream));
 	if (hbad) return rb3b_fail(RB3B_EINVAL, "interleave positions are not monotone: the batch is not a valid BWT");
-	CellSrc src;
-	src.R.cells = A->cells; src.R.ovf = A->ovf; src.R.n = A->n; src.R.shift = A->shift;
-	src.R.j = 0; src.R.left = 0; src.R.eidx = 0; src.R.first = 0xffffffffu; src.R.cur = -1; src.R.rem = 0;
-	src.n = A->n; src.cur = -1;
-	/* every inserted row adds at most two entries; most extend or split a run of a shared column */
-	int rc = rb3b_emit_build(A, src, A->n, len, d_ka, d_bwt, A->n_entries + len / 2);
+	int rc;
+	if (A->kind == RB3B_KIND_BM) {
+		BmSrc src;
+		src.R.cells = A->cells; src.R.n = A->n; src.R.pos = 0; src.R.cur = -1; src.R.rem = 0;
+		src.n = A->n; src.cur = -1;
+		if (rb3b_want_bitmap(A->n + len)) rc = rb3b_emit_build_bm(A, src, A->n, len, d_ka, d_bwt);
+		else rc = rb3b_emit_build(A, src, A->n, len, d_ka, d_bwt, (A->n + len) / 16); /* outgrew 1 B/symbol: switch to RLE cells */
+	} else {
+		CellSrc src;
+		src.R.cells = A->cells; src.R.ovf = A->ovf; src.R.n = A->n; src.R.shift = A->shift;
+		src.R.j = 0; src.R.left = 0; src.R.eidx = 0; src.R.first = 0xffffffffu; src.R.cur = -1; src.R.rem = 0;
+		src.n = A->n; src.cur = -1;
+		/* every inserted row adds at most two entries; most extend or split a run of a shared column */
+		rc = rb3b_emit_build(A, src, A->n, len, d_ka, d_bwt, A->n_entries + len / 2);
+	}
 	rb3b_toc(T_MERGE);
 	cudaStreamSynchronize(rb3b_stream);
 	rb3b_tflush();

@@ -12,6 +12,14 @@ pytestmark = pytest.mark.gpu
 MERGE_SETS = ["merge_small", "merge_div", "merge_dup"]
 
 
+@pytest.fixture(params=["rle", "bitmap"], autouse=True)
+def index_kind(request, rb3):
+    """Every test runs on both device layouts: run-length cells and one-hot bitmap cells."""
+    rb3.set_param("index_kind", 1 if request.param == "rle" else 2)
+    yield request.param
+    rb3.set_param("index_kind", 0)
+
+
 def runs_of(idx, oracle):
     s, l = idx.export_runs()
     s2, l2 = oracle.coalesce(s, l)
@@ -58,6 +66,7 @@ def test_overflow_cells(rb3, oracle):
         s2, l2 = np.array([(s[-1] + 1) % 6, (s[-1] + 2) % 6], np.uint8), rng.integers(50000, 2000000, 2)
         sym.append(s2); ln.append(l2.astype(np.int64))
     sym, ln = oracle.coalesce(np.concatenate(sym), np.concatenate(ln))
+    rb3.set_param("index_kind", 1)
     idx = rb3.Index.from_runs(sym, ln)
     assert rb3.get_stat("cell_shift") == 10 and rb3.get_stat("n_ovf_cells") > 0
     n = int(ln.sum())
@@ -111,7 +120,7 @@ def test_from_plain_matches_runs(rb3, oracle, golden):
         rb3.Index.from_plain(np.array([1, 2, 6, 0], np.uint8))  # fm-index.c:125 asserts symbols < 6
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 4, 8])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4, 8, 22, 42, 44, 82, 84])
 def test_lf_dev(rb3, oracle, variant):
     import torch
     from ropebwt3_b200 import synth
@@ -190,6 +199,27 @@ def test_merge_vs_oracle_seeded(rb3, oracle):
             assert np.array_equal(s, sym) and np.array_equal(l, ln), "merged runs differ at batch %d" % i
     finally:
         rb3.set_param("seg_len", 2048)
+
+
+def test_bitmap_to_rle_transition(rb3, oracle, golden):
+    """An index that outgrows the 1 byte/symbol budget switches from bitmap cells to run-length cells in the merge."""
+    g = golden("merge_small")
+    rb3.set_param("index_kind", 0)
+    rb3.set_param("bitmap_max_symbols", 3 * len(g["bwt0"]) + 10)
+    try:
+        idx = rb3.Index.from_plain(g["bwt0"])
+        kinds = [rb3.get_stat("index_kind")]
+        for b in range(1, int(g["n_batches"])):
+            rb, _ = idx.mg_rank_plain(g["bwt%d" % b])
+            assert np.array_equal(rb, g["rb%d" % b])
+            idx.merge_plain(g["bwt%d" % b])
+            kinds.append(rb3.get_stat("index_kind"))
+        assert kinds[0] == 1 and kinds[-1] == 0, kinds
+        s0, l0, _ = oracle.fmd_decode(bytes(g["fmd"]))
+        s, l = runs_of(idx, oracle)
+        assert np.array_equal(s, s0) and np.array_equal(l, l0)
+    finally:
+        rb3.set_param("bitmap_max_symbols", 24000000000)
 
 
 def test_build_bwt_golden(rb3, golden):

@@ -21,9 +21,11 @@ def main():
     ap.add_argument("--queries", type=float, default=64e6)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--max-len", type=int, default=30)
-    ap.add_argument("--variants", default="8,4,2,1")
+    ap.add_argument("--variants", default="8,4,2,42,22,1")
+    ap.add_argument("--kind", default="rle", choices=["rle", "bitmap"])
     a = ap.parse_args()
     R.init(0)
+    R.set_param("index_kind", 1 if a.kind == "rle" else 2)
     st = torch.cuda.Stream()
     torch.cuda.set_stream(st)
     capi.check(capi.lib().rb3b_set_stream(st.cuda_stream))
@@ -50,7 +52,7 @@ def main():
     except Exception:
         pass
     ref = None
-    for v in [int(x) for x in a.variants.split(",")]:
+    for v in ([int(x) for x in a.variants.split(",")] if a.kind == "rle" else [0]):
         for _ in range(3):
             idx.lf_dev(nq, k.data_ptr(), c.data_ptr(), out.data_ptr(), v)
         torch.cuda.synchronize()
@@ -68,9 +70,9 @@ def main():
             assert torch.equal(ref, out), "variants disagree"
         ms = float(np.median(ts))
         gbs = nq * 144 / (ms / 1e3) / 1e9
-        print(json.dumps({"kernel": "k_lf_tma" if v == 1 else "k_lf<%d>" % v, "variant": v, "index_bytes": idx.nbytes(), "index_symbols": n, "queries": nq,
+        print(json.dumps({"kernel": "k_lf_bm" if a.kind == "bitmap" else "k_lf_tma" if v == 1 else ("k_lf<%d,1>" % v if v < 10 else "k_lf<%d,%d>" % (v // 10, v % 10)), "variant": v, "index_bytes": idx.nbytes(), "index_symbols": n, "queries": nq,
                           "ms": ms, "gqueries_per_s": nq / ms / 1e6, "achieved_GBps": gbs, "peak_GBps": peak, "frac": gbs / peak,
-                          "bytes_per_query": 144}))
+                          "bytes_per_query": 144, "index_kind": a.kind}))
 
 
 if __name__ == "__main__":
