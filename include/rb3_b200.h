@@ -47,6 +47,9 @@ int64_t     rb3b_get_stat(const char *key);        /* counters of the last call:
 /* ---- index life cycle (replaces mr_init / mr_destroy, mrope.c:15-34) ------- */
 rb3b_index_t *rb3b_index_create(void);
 void          rb3b_index_destroy(rb3b_index_t *idx);
+/* optional size hint (like mr_init's pool pre-sizing has no equivalent in the reference): the index is expected to grow
+ * to n_symbols; device buffers are sized once instead of being regrown by the merges */
+int           rb3b_index_reserve(rb3b_index_t *idx, int64_t n_symbols);
 
 /* ---- building blocks of `build` -------------------------------------------- */
 /* rb3_enc_plain2fmr (fm-index.c:114-137): first batch, BWT in host memory. */

@@ -77,6 +77,10 @@ class Index:
         capi.check(x._L.rb3b_restore(x.h, fn.encode()))
         return x
 
+    def reserve(self, n_symbols):
+        """Size hint: the index will grow to about n_symbols (avoids regrowing device buffers merge after merge)."""
+        capi.check(self._L.rb3b_index_reserve(self.h, int(n_symbols)))
+
     # ---- the merge path -----------------------------------------------------
     def merge_plain(self, bwt):
         b = _u8(bwt)

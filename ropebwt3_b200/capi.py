@@ -26,6 +26,7 @@ SIGNATURES = {
     "rb3b_get_stat": (_i64, [C.c_char_p]),
     "rb3b_index_create": (_vp, []),
     "rb3b_index_destroy": (None, [_vp]),
+    "rb3b_index_reserve": (_int, [_vp, _i64]),
     "rb3b_index_from_plain": (_int, [_vp, _i64, _vp]),
     "rb3b_index_from_plain_dev": (_int, [_vp, _i64, _vp]),
     "rb3b_index_from_runs": (_int, [_vp, _i64, _vp, _vp]),

@@ -363,6 +363,29 @@ extern "C" rb3b_index_t *rb3b_index_create(void)
 	return x;
 }
 
+extern "C" int rb3b_index_reserve(rb3b_index_t *x, int64_t n_symbols)
+{ /* like vector::reserve: size both ping-pong halves for an index of n_symbols so that merges never reallocate */
+	TRY(rb3b_ensure_init());
+	if (!rb3b_want_bitmap(n_symbols)) return RB3B_OK; /* RLE cells: size depends on the data; grown on demand */
+	int64_t quads = ((n_symbols + 127) >> RB3B_BM_SHIFT) * 8;
+	if (x->cap_cells2 < quads) {
+		if (x->cells2) cudaFreeAsync(x->cells2, rb3b_stream);
+		x->cells2 = 0; x->cap_cells2 = 0;
+		CK(cudaMallocAsync((void**)&x->cells2, (size_t)quads * sizeof(uint4), rb3b_stream));
+		x->cap_cells2 = quads;
+	}
+	if (x->cap_cells < quads) { /* the current half holds live data: move it */
+		uint4 *p = 0;
+		CK(cudaMallocAsync((void**)&p, (size_t)quads * sizeof(uint4), rb3b_stream));
+		if (x->cells) {
+			CK(cudaMemcpyAsync(p, x->cells, (size_t)x->n_cells * 128, cudaMemcpyDeviceToDevice, rb3b_stream));
+			cudaFreeAsync(x->cells, rb3b_stream);
+		}
+		x->cells = p; x->cap_cells = quads;
+	}
+	return RB3B_OK;
+}
+
 extern "C" void rb3b_index_destroy(rb3b_index_t *x)
 {
 	if (!x) return;

@@ -10,7 +10,7 @@
 #include "rb3b_internal.cuh"
 
 cudaStream_t rb3b_stream = 0;
-int64_t rb3b_seg_len = 2048;      /* target LF-walk segment length ("seg_len") */
+int64_t rb3b_seg_len = 512;       /* target LF-walk segment length ("seg_len") */
 int64_t rb3b_rank_variant = 0;    /* 0: LDG.128 per lane, 1: cp.async.bulk (TMA) staged */
 
 static int g_inited = 0, g_device = 0, g_own_stream = 0;
@@ -119,6 +119,7 @@ int64_t rb3b_get_param(const char *key, int64_t dflt)
 extern "C" int64_t rb3b_get_stat(const char *key)
 {
 	if (!strcmp(key, "kernel_launches")) return rb3b_n_launch;
+	if (!strcmp(key, "seg_len")) return rb3b_seg_len;
 	if (!strcmp(key, "reset")) { g_stats.clear(); rb3b_n_launch = 0; return 0; }
 	std::map<std::string, int64_t>::iterator it = g_stats.find(key);
 	return it == g_stats.end() ? -1 : it->second;
