@@ -1,0 +1,269 @@
+/*
+ * rb3b_build.c -- `ropebwt3 build` on the B200 engine (C host side).
+ *
+ * Keeps the reference CLI for its default construction path (libsais + merge):
+ * option string "l:n:m:t:2sri:LFRo:dbTS:p:e" with argument permutation
+ * (build.c:146), defaults of rb3_bopt_init (build.c:31-41), -i incremental
+ * append (build.c:172-184), per-file batching by -m (io.c:104-125: a batch
+ * closes after the record that makes it longer than -m), forward strand then
+ * reverse complement per record (io.c:84-102), -S checkpoint after every input
+ * file (build.c:232-238), output formats -d/-b/plain (build.c:245-251), exit
+ * codes (build.c:175-178,243).  Everything on the hot path -- partial BWT of
+ * a batch, interleave array, merge -- runs on the device through librb3b200.so;
+ * this file only parses options and sequence files.
+ *
+ * Not covered (documented in DESIGN.md): -2/-s/-r (ropebwt2 insertion, config 0),
+ * -T (tree dump: there is no tree), -e (BRE).  -t and -p are accepted and
+ * ignored (parallelism comes from the device); -l/-n only shape the .fmr dump.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+#include <unistd.h>
+#include <time.h>
+#include <sys/resource.h>
+#include <zlib.h>
+#include "../include/rb3_b200.h"
+
+static const unsigned char nt6_table[128] = { /* io.c:12-21: $ACGTN = 0..5 */
+	0, 1, 2, 3,  4, 5, 5, 5,  5, 5, 5, 5,  5, 5, 5, 5,  5, 5, 5, 5,  5, 5, 5, 5,  5, 5, 5, 5,  5, 5, 5, 5,
+	5, 5, 5, 5,  5, 5, 5, 5,  5, 5, 5, 5,  5, 5, 5, 5,  5, 5, 5, 5,  5, 5, 5, 5,  5, 5, 5, 5,  5, 5, 5, 5,
+	5, 1, 5, 2,  5, 5, 5, 3,  5, 5, 5, 5,  5, 5, 5, 5,  5, 5, 5, 5,  4, 5, 5, 5,  5, 5, 5, 5,  5, 5, 5, 5,
+	5, 1, 5, 2,  5, 5, 5, 3,  5, 5, 5, 5,  5, 5, 5, 5,  5, 5, 5, 5,  4, 5, 5, 5,  5, 5, 5, 5,  5, 5, 5, 5
+};
+
+typedef struct { char *s; size_t l, m; } str_t;
+
+static void str_reserve(str_t *b, size_t need)
+{
+	if (need > b->m) {
+		b->m = need + (need >> 1) + 64;
+		b->s = (char*)realloc(b->s, b->m);
+		if (b->s == 0) { fprintf(stderr, "ERROR: out of host memory\n"); exit(1); }
+	}
+}
+
+static double t_real0;
+static double realtime(void) { struct timespec ts; clock_gettime(CLOCK_REALTIME, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; }
+static double cputime(void) { struct rusage r; getrusage(RUSAGE_SELF, &r); return r.ru_utime.tv_sec + r.ru_stime.tv_sec + 1e-6 * (r.ru_utime.tv_usec + r.ru_stime.tv_usec); }
+#define LOG(...) do { fprintf(stderr, "[M::main_build::%.3f*%.2f] ", realtime() - t_real0, cputime() / (realtime() - t_real0 + 1e-9)); fprintf(stderr, __VA_ARGS__); fputc('\n', stderr); } while (0)
+
+static int64_t parse_num(const char *str)
+{ /* misc.c:7-16 */
+	char *p;
+	double x = strtod(str, &p);
+	if (*p == 'G' || *p == 'g') x *= 1e9;
+	else if (*p == 'M' || *p == 'm') x *= 1e6;
+	else if (*p == 'K' || *p == 'k') x *= 1e3;
+	return (int64_t)(x + .499);
+}
+
+/* ---- sequence reader: FASTA/FASTQ (multi-line) or one sequence per line; gzip transparent ---- */
+
+typedef struct {
+	gzFile fp;
+	int is_line, last; /* last: a character read ahead (-2 none) */
+	unsigned char buf[1 << 16];
+	int n, p;
+} reader_t;
+
+static int rd_getc(reader_t *r)
+{
+	if (r->p >= r->n) {
+		r->n = gzread(r->fp, r->buf, sizeof(r->buf));
+		r->p = 0;
+		if (r->n <= 0) return -1;
+	}
+	return r->buf[r->p++];
+}
+
+static int rd_line(reader_t *r, str_t *out, int append)
+{ /* one line without its terminator; -1 at EOF with nothing read */
+	int c, got = 0;
+	if (!append) out->l = 0;
+	while ((c = rd_getc(r)) >= 0) {
+		got = 1;
+		if (c == '\n') break;
+		str_reserve(out, out->l + 2);
+		out->s[out->l++] = (char)c;
+	}
+	if (!got) return -1;
+	if (out->l && out->s[out->l - 1] == '\r') --out->l;
+	str_reserve(out, out->l + 1);
+	out->s[out->l] = 0;
+	return 0;
+}
+
+/* next record's residues into rec; returns -1 at EOF */
+static int rd_record(reader_t *r, str_t *rec, str_t *tmp)
+{
+	int c;
+	if (r->is_line) return rd_line(r, rec, 0);
+	if (r->last == -2) { /* skip to the first header */
+		while ((c = rd_getc(r)) >= 0 && c != '>' && c != '@') {}
+		if (c < 0) return -1;
+		r->last = c;
+	}
+	if (r->last < 0) return -1;
+	if (rd_line(r, tmp, 0) < 0) { r->last = -1; return -1; } /* rest of the header line */
+	rec->l = 0;
+	for (;;) {
+		c = rd_getc(r);
+		if (c < 0) { r->last = -1; break; }
+		if (c == '>' || c == '@') { r->last = c; break; }
+		if (c == '+') { /* FASTQ: skip the '+' line and as many quality characters as residues */
+			size_t q = 0;
+			rd_line(r, tmp, 0);
+			while (q < rec->l && rd_line(r, tmp, 0) == 0) q += tmp->l;
+			while ((c = rd_getc(r)) >= 0 && c != '>' && c != '@') {}
+			r->last = c < 0 ? -1 : c;
+			break;
+		}
+		if (c == '\n' || c == '\r') continue;
+		str_reserve(rec, rec->l + 2);
+		rec->s[rec->l++] = (char)c;
+		rd_line(r, rec, 1); /* the rest of this sequence line */
+	}
+	str_reserve(rec, rec->l + 1);
+	rec->s[rec->l] = 0;
+	return 0;
+}
+
+static void seq_add(str_t *seq, const str_t *rec, int is_for, int is_rev, int64_t *n_seq)
+{ /* rb3_seq_add, io.c:84-102 */
+	size_t i, l = rec->l;
+	if (is_for) {
+		str_reserve(seq, seq->l + l + 1);
+		for (i = 0; i < l; ++i) { unsigned char c = (unsigned char)rec->s[i]; seq->s[seq->l + i] = c < 128 ? nt6_table[c] : 5; }
+		seq->s[seq->l + l] = 0;
+		seq->l += l + 1; ++*n_seq;
+	}
+	if (is_rev) {
+		str_reserve(seq, seq->l + l + 1);
+		for (i = 0; i < l; ++i) {
+			unsigned char c = (unsigned char)rec->s[l - 1 - i];
+			int x = c < 128 ? nt6_table[c] : 5;
+			seq->s[seq->l + i] = (x >= 1 && x <= 4) ? 5 - x : x;
+		}
+		seq->s[seq->l + l] = 0;
+		seq->l += l + 1; ++*n_seq;
+	}
+}
+
+static int usage(FILE *fp)
+{
+	fprintf(fp, "Usage: ropebwt3-b200 build [options] <in.fa> [...]\n");
+	fprintf(fp, "Options (those of `ropebwt3 build`):\n");
+	fprintf(fp, "  -m NUM   batch size [7G]             -i FILE  append to an existing .fmr/.fmd index\n");
+	fprintf(fp, "  -L       one sequence per line       -F/-R    skip forward / reverse strand\n");
+	fprintf(fp, "  -o FILE  output file [stdout]        -d/-b    write .fmd / .fmr (default: plain text BWT)\n");
+	fprintf(fp, "  -S FILE  save the index (.fmr) after every input file\n");
+	fprintf(fp, "  -l INT   leaf block length of the .fmr dump [512]   -n INT  max children per node [64]\n");
+	fprintf(fp, "  -t INT / -p INT  accepted for compatibility; the device provides the parallelism\n");
+	fprintf(fp, "  -2 -s -r -T -e   not supported by this engine (ropebwt2 insertion order, tree dump, BRE)\n");
+	fprintf(fp, "Environment: RB3B_DEVICE=<cuda device>\n");
+	return fp == stdout ? 0 : 1;
+}
+
+#define DIE_IF(rc, what) do { if ((rc) < 0) { fprintf(stderr, "ERROR: %s: %s\n", what, rb3b_last_error()); exit(1); } } while (0)
+
+int main(int argc, char *argv[])
+{
+	int c, i, is_line = 0, no_for = 0, no_rev = 0, fmt = 0 /* 0 plain, 1 fmd, 2 fmr */, block_len = 512, max_nodes = 64;
+	int64_t batch = 7000000000LL;
+	const char *fn_in = 0, *fn_tmp = 0;
+	str_t seq = {0, 0, 0}, rec = {0, 0, 0}, tmp = {0, 0, 0};
+	rb3b_index_t *idx = 0;
+	void *d_text = 0;
+	int64_t d_cap = 0;
+
+	t_real0 = realtime();
+	if (argc >= 2 && strcmp(argv[1], "version") == 0) { puts(rb3b_version()); return 0; }
+	if (argc < 2 || strcmp(argv[1], "build") != 0) return usage(stderr);
+	--argc; ++argv;
+	while ((c = getopt(argc, argv, "l:n:m:t:2sri:LFRo:dbTS:p:e")) >= 0) {
+		if (c == 'm') batch = parse_num(optarg);
+		else if (c == 't' || c == 'p') {}
+		else if (c == 'l') block_len = atoi(optarg);
+		else if (c == 'n') max_nodes = atoi(optarg);
+		else if (c == 'i') fn_in = optarg;
+		else if (c == 'L') is_line = 1;
+		else if (c == 'F') no_for = 1;
+		else if (c == 'R') no_rev = 1;
+		else if (c == 'o') { if (freopen(optarg, "wb", stdout) == 0) { fprintf(stderr, "ERROR: failed to open '%s' for writing\n", optarg); return 1; } }
+		else if (c == 'd') fmt = 1;
+		else if (c == 'b') fmt = 2;
+		else if (c == 'S') fn_tmp = optarg;
+		else if (c == '2' || c == 's' || c == 'r' || c == 'T' || c == 'e') {
+			fprintf(stderr, "ERROR: option -%c (ropebwt2 insertion / tree dump / BRE) is outside this engine's scope; use the CPU ropebwt3 for it\n", c);
+			return 1;
+		} else return usage(stderr);
+	}
+	if (argc == optind && fn_in == 0) return usage(stderr);
+	if (no_for && no_rev) { fprintf(stderr, "ERROR: -F and -R together leave nothing to index\n"); return 1; }
+
+	DIE_IF(rb3b_init(getenv("RB3B_DEVICE") ? atoi(getenv("RB3B_DEVICE")) : 0), "no usable CUDA device");
+	if (fn_in) {
+		idx = rb3b_index_create();
+		if (rb3b_restore(idx, fn_in) < 0) { /* build.c:175-178 */
+			fprintf(stderr, "ERROR: failed to open index file '%s' (%s)\n", fn_in, rb3b_last_error());
+			return 1;
+		}
+		LOG("loaded the index from file '%s'", fn_in);
+	}
+	for (i = optind; i < argc; ++i) {
+		reader_t *r = (reader_t*)calloc(1, sizeof(reader_t));
+		int eof = 0;
+		r->fp = strcmp(argv[i], "-") ? gzopen(argv[i], "r") : gzdopen(0, "r");
+		if (r->fp == 0) { /* build.c:207-210: report and go on */
+			fprintf(stderr, "ERROR: failed to open file '%s'\n", argv[i]);
+			free(r);
+			continue;
+		}
+		r->is_line = is_line; r->last = -2;
+		while (!eof) {
+			int64_t n_seq = 0;
+			seq.l = 0;
+			while (rd_record(r, &rec, &tmp) == 0) {
+				seq_add(&seq, &rec, !no_for, !no_rev, &n_seq);
+				if (batch > 0 && (int64_t)seq.l > batch) break; /* io.c:114,119 */
+			}
+			if (n_seq == 0) break;
+			if (batch <= 0 || (int64_t)seq.l <= batch) eof = 1;
+			LOG("read %ld symbols from file '%s'", (long)seq.l, argv[i]);
+			if ((int64_t)seq.l > d_cap) {
+				rb3b_dev_free(d_text);
+				d_cap = (int64_t)seq.l + (int64_t)(seq.l >> 2);
+				d_text = rb3b_dev_alloc(d_cap);
+				if (d_text == 0) { fprintf(stderr, "ERROR: %s\n", rb3b_last_error()); return 1; }
+			}
+			DIE_IF(rb3b_h2d(d_text, seq.s, (int64_t)seq.l), "host to device copy");
+			DIE_IF(rb3b_build_bwt_dev((int64_t)seq.l, (const uint8_t*)d_text, (uint8_t*)d_text), "partial BWT"); /* rb3_build_sais, in place */
+			LOG("constructed partial BWT for %ld symbols", (long)seq.l);
+			if (idx == 0) {
+				idx = rb3b_index_create();
+				DIE_IF(rb3b_index_from_plain_dev(idx, (int64_t)seq.l, (const uint8_t*)d_text), "encoding the partial BWT");
+				LOG("encoded the partial BWT for %ld symbols", (long)seq.l);
+			} else {
+				DIE_IF(rb3b_merge_plain_dev(idx, (int64_t)seq.l, (const uint8_t*)d_text), "merging the partial BWT");
+				LOG("merged the partial BWT for %ld symbols", (long)seq.l);
+			}
+		}
+		gzclose(r->fp);
+		free(r);
+		if (fn_tmp && idx) {
+			DIE_IF(rb3b_dump_fmr(idx, fn_tmp, max_nodes, block_len), "saving the index");
+			LOG("saved the current index to '%s'", fn_tmp);
+		}
+	}
+	if (idx == 0) return 1; /* build.c:243 */
+	if (fmt == 2) DIE_IF(rb3b_dump_fmr(idx, "-", max_nodes, block_len), "writing .fmr");
+	else if (fmt == 1) DIE_IF(rb3b_dump_fmd(idx, "-"), "writing .fmd");
+	else DIE_IF(rb3b_dump_plain(idx, "-"), "writing the BWT");
+	rb3b_index_destroy(idx);
+	rb3b_dev_free(d_text);
+	free(seq.s); free(rec.s); free(tmp.s);
+	fprintf(stderr, "[M::main] Real time: %.3f sec; CPU: %.3f sec\n", realtime() - t_real0, cputime());
+	return 0;
+}

@@ -137,6 +137,7 @@ static int suffix_sort(int64_t len, const uint8_t *d_text, DBuf<uint32_t> &sa)
 
 extern "C" int rb3b_build_bwt_dev(int64_t len, const uint8_t *d_text, uint8_t *d_bwt_out)
 {
+	ApiScope scope_;
 	TRY(rb3b_ensure_init());
 	if (len <= 0) return rb3b_fail(RB3B_EINVAL, "empty batch");
 	DBuf<uint32_t> sa;
@@ -155,6 +156,7 @@ extern "C" int rb3b_build_bwt_dev(int64_t len, const uint8_t *d_text, uint8_t *d
 
 extern "C" int rb3b_build_bwt(int64_t len, const uint8_t *text, uint8_t *bwt_out)
 {
+	ApiScope scope_;
 	TRY(rb3b_ensure_init());
 	if (len <= 0) return rb3b_fail(RB3B_EINVAL, "empty batch");
 	DBuf<uint8_t> t, b;
@@ -182,6 +184,7 @@ __global__ void k_runs_to_plain(int64_t n_runs, int64_t n, const uint8_t *__rest
 
 extern "C" int rb3b_merge_index(rb3b_index_t *x, const rb3b_index_t *other)
 {
+	ApiScope scope_;
 	TRY(rb3b_ensure_init());
 	if (other->n == 0) return RB3B_OK;
 	DBuf<uint8_t> sym, plain;

@@ -395,6 +395,7 @@ extern "C" void rb3b_index_destroy(rb3b_index_t *x)
 
 extern "C" int rb3b_index_from_runs(rb3b_index_t *x, int64_t n_runs, const uint8_t *sym, const int64_t *len)
 {
+	ApiScope scope_;
 	TRY(rb3b_ensure_init());
 	DBuf<uint8_t> ds; DBuf<int64_t> dl;
 	TRY(ds.alloc(n_runs)); TRY(dl.alloc(n_runs));
@@ -407,12 +408,14 @@ extern "C" int rb3b_index_from_runs(rb3b_index_t *x, int64_t n_runs, const uint8
 
 extern "C" int rb3b_index_from_runs_device(rb3b_index_t *x, int64_t n_runs, const uint8_t *d_sym, const int64_t *d_len)
 {
+	ApiScope scope_;
 	TRY(rb3b_ensure_init());
 	return rb3b_index_from_runs_dev(x, n_runs, d_sym, d_len);
 }
 
 extern "C" int rb3b_index_from_plain_dev(rb3b_index_t *x, int64_t len, const uint8_t *d_bwt)
 {
+	ApiScope scope_;
 	TRY(rb3b_ensure_init());
 	DBuf<uint8_t> sym; DBuf<int64_t> rlen;
 	int64_t n_runs;
@@ -423,6 +426,7 @@ extern "C" int rb3b_index_from_plain_dev(rb3b_index_t *x, int64_t len, const uin
 
 extern "C" int rb3b_index_from_plain(rb3b_index_t *x, int64_t len, const uint8_t *bwt)
 {
+	ApiScope scope_;
 	TRY(rb3b_ensure_init());
 	DBuf<uint8_t> d;
 	if (len < 0) return rb3b_fail(RB3B_EINVAL, "negative length");
@@ -433,6 +437,7 @@ extern "C" int rb3b_index_from_plain(rb3b_index_t *x, int64_t len, const uint8_t
 
 extern "C" int rb3b_rank1a_dev(const rb3b_index_t *x, int64_t nq, const int64_t *d_k, int64_t *d_ok, int8_t *d_sym)
 {
+	ApiScope scope_;
 	TRY(rb3b_ensure_init());
 	if (nq <= 0) return RB3B_OK;
 	int64_t want = (nq * RB3B_GROUP + TPB - 1) / TPB, cap = (int64_t)n_sm() * 8 * 4;
@@ -452,6 +457,7 @@ extern "C" int rb3b_rank1a_dev(const rb3b_index_t *x, int64_t nq, const int64_t 
 
 extern "C" int rb3b_rank1a(const rb3b_index_t *x, int64_t nq, const int64_t *k, int64_t *ok, int8_t *sym)
 {
+	ApiScope scope_;
 	TRY(rb3b_ensure_init());
 	if (nq <= 0) return RB3B_OK;
 	DBuf<int64_t> dk, dok; DBuf<int8_t> ds;
@@ -468,6 +474,7 @@ int rb3b_lf_tma_launch(const rb3b_index_s *x, int64_t nq, const int64_t *d_k, co
 
 extern "C" int rb3b_lf_dev(const rb3b_index_t *x, int64_t nq, const int64_t *d_k, const uint8_t *d_c, int64_t *d_out, int variant)
 { /* variant: 0 default, 1 cp.async.bulk staged, G (2/4/8) lanes per query, GU = G lanes with U queries in flight */
+	ApiScope scope_;
 	TRY(rb3b_ensure_init());
 	if (nq <= 0) return RB3B_OK;
 	if (x->n_cells == 0) return rb3b_fail(RB3B_EINVAL, "empty index");
@@ -499,6 +506,7 @@ extern "C" int64_t rb3b_index_bytes(const rb3b_index_t *x) { return (int64_t)x->
 
 extern "C" int64_t rb3b_export_runs(const rb3b_index_t *x, uint8_t *sym, int64_t *len, int64_t cap)
 {
+	ApiScope scope_;
 	if (rb3b_ensure_init() != RB3B_OK) return RB3B_ENODEV;
 	DBuf<uint8_t> ds; DBuf<int64_t> dl;
 	int64_t n_runs;

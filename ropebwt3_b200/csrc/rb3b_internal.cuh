@@ -101,28 +101,25 @@ void rb3b_tflush(void);
 #define CKK() do { ++rb3b_n_launch; CK(cudaGetLastError()); } while (0)   /* after every launch of one of OUR kernels */
 #define TRY(call) do { int r_ = (call); if (r_ != RB3B_OK) return r_; } while (0)
 
-static inline size_t rb3b_round_cap(size_t bytes)
-{
-	size_t c = 1 << 16;
-	while (c < bytes) c += (c >> 2) & ~(size_t)255;
-	return c;
-}
+/*
+ * Scratch memory.  Every API call bump-allocates its temporaries from a device arena that is reset when the
+ * outermost call returns, so steady-state merges perform no cudaMalloc/cudaFree at all (allocation growth used
+ * to cost more than the kernels).  The arena grows by adding chunks; the next reset folds them into one.
+ */
+void *rb3b_arena_alloc(size_t bytes);
+void rb3b_arena_enter(void);
+void rb3b_arena_leave(void);
+struct ApiScope { ApiScope() { rb3b_arena_enter(); } ~ApiScope() { rb3b_arena_leave(); } };
 
-/* stream-ordered scratch buffer */
 template<typename T> struct DBuf {
 	T *p; size_t n;
 	DBuf() : p(0), n(0) {}
-	~DBuf() { release(); }
 	int alloc(size_t n_) {
-		release();
 		n = n_;
-		/* sizes are quantised (x1.25 steps) so that the slightly larger buffers of the next merge reuse pool blocks */
-		cudaError_t e = cudaMallocAsync((void**)&p, rb3b_round_cap((n ? n : 1) * sizeof(T)), rb3b_stream);
-		if (e != cudaSuccess) { p = 0; return rb3b_fail(RB3B_ENOMEM, "cudaMallocAsync(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e)); }
+		p = (T*)rb3b_arena_alloc((n ? n : 1) * sizeof(T));
+		if (p == 0) return rb3b_fail(RB3B_ENOMEM, "device arena: cannot allocate %zu bytes", n * sizeof(T));
 		return RB3B_OK;
 	}
-	void release() { if (p) { cudaFreeAsync(p, rb3b_stream); p = 0; } }
-	T *take() { T *q = p; p = 0; return q; }
 private:
 	DBuf(const DBuf&); DBuf &operator=(const DBuf&);
 };

@@ -473,6 +473,7 @@ static int merge_phase(rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, const
 
 extern "C" int rb3b_mg_rank_plain_dev(const rb3b_index_t *x, int64_t len, const uint8_t *d_bwt, int64_t *d_rb, int64_t acc[RB3B_ASIZE + 1])
 {
+	ApiScope scope_;
 	TRY(rb3b_ensure_init());
 	DBuf<int64_t> ka;
 	Acc7 a;
@@ -484,6 +485,7 @@ extern "C" int rb3b_mg_rank_plain_dev(const rb3b_index_t *x, int64_t len, const 
 
 extern "C" int rb3b_mg_rank_plain(const rb3b_index_t *x, int64_t len, const uint8_t *bwt, int64_t *rb, int64_t acc[RB3B_ASIZE + 1])
 {
+	ApiScope scope_;
 	TRY(rb3b_ensure_init());
 	DBuf<uint8_t> d; DBuf<int64_t> drb;
 	if (len <= 0) return rb3b_fail(RB3B_EINVAL, "empty batch");
@@ -497,6 +499,7 @@ extern "C" int rb3b_mg_rank_plain(const rb3b_index_t *x, int64_t len, const uint
 
 extern "C" int rb3b_merge_plain_dev(rb3b_index_t *x, int64_t len, const uint8_t *d_bwt)
 {
+	ApiScope scope_;
 	TRY(rb3b_ensure_init());
 	if (len <= 0) return RB3B_OK;
 	if (x->n_cells == 0) return rb3b_index_from_plain_dev(x, len, d_bwt);
@@ -508,6 +511,7 @@ extern "C" int rb3b_merge_plain_dev(rb3b_index_t *x, int64_t len, const uint8_t 
 
 extern "C" int rb3b_merge_plain(rb3b_index_t *x, int64_t len, const uint8_t *bwt)
 {
+	ApiScope scope_;
 	TRY(rb3b_ensure_init());
 	DBuf<uint8_t> d;
 	if (len <= 0) return RB3B_OK;

@@ -19,6 +19,48 @@ static thread_local char g_err[1024] = "";
 static std::map<std::string, int64_t> g_stats;
 static std::map<std::string, int64_t> g_params;
 
+/* ---- scratch arena ---- */
+#include <vector>
+struct Chunk { char *p; size_t cap; };
+static std::vector<Chunk> g_chunks;
+static size_t g_chunk_i = 0, g_chunk_off = 0, g_used = 0, g_high = 0;
+static int g_depth = 0;
+
+void *rb3b_arena_alloc(size_t bytes)
+{
+	bytes = (bytes + 511) & ~(size_t)511;
+	for (;;) {
+		if (g_chunk_i < g_chunks.size() && g_chunk_off + bytes <= g_chunks[g_chunk_i].cap) {
+			void *p = g_chunks[g_chunk_i].p + g_chunk_off;
+			g_chunk_off += bytes; g_used += bytes;
+			if (g_used > g_high) g_high = g_used;
+			return p;
+		}
+		if (g_chunk_i + 1 < g_chunks.size()) { ++g_chunk_i; g_chunk_off = 0; continue; }
+		Chunk c;
+		c.cap = bytes > ((size_t)64 << 20) ? bytes + (bytes >> 2) : (size_t)64 << 20;
+		if (cudaMalloc((void**)&c.p, c.cap) != cudaSuccess) { cudaGetLastError(); return 0; }
+		g_chunks.push_back(c);
+		g_chunk_i = g_chunks.size() - 1; g_chunk_off = 0;
+	}
+}
+
+void rb3b_arena_enter(void) { ++g_depth; }
+
+void rb3b_arena_leave(void)
+{
+	if (--g_depth > 0) return;
+	if (g_chunks.size() > 1) { /* fold the chunks into one that fits everything the last call needed */
+		cudaStreamSynchronize(rb3b_stream);
+		for (size_t i = 0; i < g_chunks.size(); ++i) cudaFree(g_chunks[i].p);
+		g_chunks.clear();
+		Chunk c;
+		c.cap = g_high + (g_high >> 2) + ((size_t)16 << 20);
+		if (cudaMalloc((void**)&c.p, c.cap) == cudaSuccess) g_chunks.push_back(c); else cudaGetLastError();
+	}
+	g_chunk_i = 0; g_chunk_off = 0; g_used = 0;
+}
+
 int rb3b_fail(int code, const char *fmt, ...)
 {
 	va_list ap;

@@ -1,0 +1,113 @@
+"""The C host CLI (cli/ropebwt3-b200 build) against the reference CLI (oracle/_ref/ropebwt3 build) on the same files:
+.fmd byte-identical, plain output identical, .fmr loadable/extendable by the reference."""
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "cli", "ropebwt3-b200")
+
+
+def run(binary, args, stdin=None, check=True):
+    p = subprocess.run([binary] + [str(a) for a in args], input=stdin, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    if check and p.returncode != 0:
+        raise RuntimeError("%s %s failed (%d): %s" % (binary, args, p.returncode, p.stderr.decode()[-800:]))
+    return p
+
+
+@pytest.fixture(scope="module")
+def files(tmp_path_factory, oracle):
+    from oracle import ref
+    if not os.path.exists(CLI):
+        pytest.fail("cli/ropebwt3-b200 is not built (run __graft_entry__.build())")
+    if not os.path.exists(ref.BIN):
+        pytest.skip("oracle/_ref/ropebwt3 did not travel")
+    from ropebwt3_b200 import synth
+    d = tmp_path_factory.mktemp("cli")
+    gs = synth.genomes(6, 30000, seed=77)
+    gs[2][100:140] = 5  # a stretch of Ns
+    fa = []
+    for i, g in enumerate(gs):
+        s = oracle.to_ascii(g)
+        body = ">g%d some description\n" % i + "\n".join(s[k:k + 80] for k in range(0, len(s), 80)) + "\n"
+        fn = str(d / ("g%d.fa" % i))
+        if i == 1:
+            fn += ".gz"
+            with gzip.open(fn, "wb") as f:
+                f.write(body.encode())
+        else:
+            open(fn, "w").write(body)
+        fa.append(fn)
+    multi = str(d / "all.fa")
+    with open(multi, "w") as f:
+        for i, g in enumerate(gs):
+            f.write(">s%d\n%s\n" % (i, oracle.to_ascii(g).lower() if i == 3 else oracle.to_ascii(g)))
+    lines = str(d / "lines.txt")
+    with open(lines, "w") as f:
+        for g in gs:
+            f.write(oracle.to_ascii(g[:5000]) + "\n")
+    fq = str(d / "reads.fq")
+    rng = np.random.default_rng(3)
+    with open(fq, "w") as f:
+        for i in range(200):
+            s0 = int(rng.integers(0, 29000))
+            r = oracle.to_ascii(gs[0][s0:s0 + 150])
+            f.write("@r%d\n%s\n+\n%s\n" % (i, r, "I" * len(r)))
+    return {"dir": d, "fa": fa, "multi": multi, "lines": lines, "fq": fq, "ref": ref.BIN}
+
+
+def test_multi_file_build_fmd(files):
+    want = run(files["ref"], ["build", "-t4", "-d"] + files["fa"]).stdout
+    got = run(CLI, ["build", "-t4", "-d"] + files["fa"]).stdout
+    assert got == want and len(got) > 1000
+
+
+@pytest.mark.parametrize("opts", [["-m", "50k"], ["-m", "7g"], ["-R"], ["-F"], ["-m", "100k", "-R"]])
+def test_single_file_batches(files, opts):
+    want = run(files["ref"], ["build", "-d"] + opts + [files["multi"]]).stdout
+    got = run(CLI, ["build", "-d"] + opts + [files["multi"]]).stdout
+    assert got == want
+
+
+def test_line_input_stdin_fastq_and_plain_output(files):
+    data = open(files["lines"], "rb").read()
+    assert run(CLI, ["build", "-L", "-"], stdin=data).stdout == run(files["ref"], ["build", "-L", "-"], stdin=data).stdout
+    assert run(CLI, ["build", "-Ld", files["lines"]]).stdout == run(files["ref"], ["build", "-Ld", files["lines"]]).stdout
+    assert run(CLI, ["build", "-d", files["fq"]]).stdout == run(files["ref"], ["build", "-d", files["fq"]]).stdout
+    toy = b"AGG\nAGC\n"
+    assert run(CLI, ["build", "-L", "-"], stdin=toy).stdout == b"GTCT$$G$CGGA$ACC\n"
+    assert run(CLI, ["build", "-LR", "-"], stdin=toy).stdout == b"GC$$GGAA\n"
+
+
+def test_incremental_append_and_checkpoint(files):
+    d = files["dir"]
+    half, ckpt, out = str(d / "half.fmr"), str(d / "ckpt.fmr"), str(d / "full.fmd")
+    run(CLI, ["build", "-b", "-o", half] + files["fa"][:3])
+    run(CLI, ["build", "-d", "-i", half, "-S", ckpt, "-o", out] + files["fa"][3:])
+    want = run(files["ref"], ["build", "-d"] + files["fa"]).stdout
+    assert open(out, "rb").read() == want
+    # the checkpoint is a valid FMR of the whole collection; the reference converts it to the same FMD
+    assert run(files["ref"], ["build", "-d", "-i", ckpt]).stdout == want
+    # and the reference can keep inserting into our half-way FMR
+    assert run(files["ref"], ["build", "-d", "-i", half] + files["fa"][3:]).stdout == want
+    # appending to a reference-made .fmd works as well (rb3_fmi_restore sniffs both formats)
+    ref_half = str(d / "ref_half.fmd")
+    open(ref_half, "wb").write(run(files["ref"], ["build", "-d"] + files["fa"][:3]).stdout)
+    assert run(CLI, ["build", "-d", "-i", ref_half] + files["fa"][3:]).stdout == want
+    # pure format conversion: no input files, only -i (build.c:169)
+    assert run(CLI, ["build", "-d", "-i", half]).stdout == run(files["ref"], ["build", "-d"] + files["fa"][:3]).stdout
+
+
+def test_error_behaviour(files):
+    assert run(CLI, ["build", "-d", "-i", "/nonexistent.fmr", files["multi"]], check=False).returncode == 1   # build.c:175-178
+    p = run(CLI, ["build", "-d", "/nonexistent.fa", files["lines"] + ".nope"], check=False)                  # build.c:207-210,243
+    assert p.returncode == 1 and b"failed to open file" in p.stderr
+    p = run(CLI, ["build", "-d", "/nonexistent.fa"] + files["fa"][:1], check=False)                           # bad file skipped, rest built
+    assert p.returncode == 0 and p.stdout == run(files["ref"], ["build", "-d"] + files["fa"][:1]).stdout
+    assert run(CLI, ["build", "-r", files["multi"]], check=False).returncode == 1                             # documented scope limit
+    assert run(CLI, ["build"], check=False).returncode == 1
