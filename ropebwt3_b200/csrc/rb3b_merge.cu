@@ -176,6 +176,16 @@ __global__ void k_coarse_fill(Fine F, const int64_t *__restrict__ flag, const in
 	} else cmap[f] = -1;
 }
 
+/* length of every segment = rows between its coarse mark and the next one (or the start of the sequence) */
+__global__ void k_seg_len(Fine F, const int64_t *__restrict__ flag, const int64_t *__restrict__ sid, const int64_t *__restrict__ succ, const int64_t *__restrict__ piece, int64_t *__restrict__ seglen)
+{
+	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (f >= F.n_fine || !flag[f]) return;
+	int64_t n = 0, g = f;
+	do { n += piece[g]; g = succ[g]; } while (g >= 0 && !flag[g]);
+	seglen[sid[f]] = n;
+}
+
 /* ------------------------------------------------------------------ */
 /* segmented LF walk                                                    */
 /* ------------------------------------------------------------------ */
@@ -188,7 +198,16 @@ struct Segs {
 	int64_t *len;     /* #rows of the segment */
 	int64_t *succ;    /* segment entered after the last row, or -1 at the start of a sequence */
 	int64_t *arr_lo, *arr_hi; /* bracket with which the walk arrived at succ's first row */
+	/* fix-up log (bitmap cells): while a walk carries a bracket it records, in walk order, the row, the bracket's low
+	 * end, the row's symbol and whether the bracket is at most 128 wide.  The later rounds then stream this log
+	 * instead of chasing LF_B, and for narrow brackets the two cells that can hold the exact position are known in
+	 * advance, so their loads no longer sit on the dependent chain. */
+	const int64_t *logbase; /* per segment: first log slot; NULL = no log */
+	int64_t *log_kb, *log_lo;
 };
+
+#define LOG_C_SHIFT 42
+#define LOG_NARROW (1LL << 45)
 
 /* The walk kernels are written for a "ranker" WG: Grp<8> (RLE cells, 8 lanes per walk) or BmRank (bitmap cells,
  * one thread per walk). */
@@ -215,7 +234,14 @@ __global__ void __launch_bounds__(TPB) k_walk_first(DevIndex A, Acc7 accB, Segs 
 		for (;;) {
 			int c = (int)(x & 7);
 			if (lo == hi) { if (gl == 0) ka[kb] = lo; }
-			else ++d;
+			else {
+				if (S.logbase && gl == 0) {
+					int64_t o = S.logbase[s] + d;
+					S.log_kb[o] = kb;
+					S.log_lo[o] = lo | (int64_t)c << LOG_C_SHIFT | (hi - lo <= 128 ? LOG_NARROW : 0);
+				}
+				++d;
+			}
 			++len;
 			if (c == 0) break; /* reached the first symbol of the sequence, fm-index.c:170 */
 			kb = (int64_t)(x >> LFB_SHIFT);
@@ -241,6 +267,69 @@ __global__ void k_collect_first(Segs S, int64_t *__restrict__ wl_seg, int64_t *_
 	if (t >= 0 && S.arr_lo[s] == S.arr_hi[s] && S.d[t] > 0) {
 		unsigned long long o = atomicAdd(wl_n, 1ULL);
 		wl_seg[o] = t; wl_val[o] = S.arr_lo[s];
+	}
+}
+
+/* exact rank when the position v is known to lie in cell j or j+1 (j = cell of the bracket's low end): q holds the
+ * count quad and the plane quad of symbol c for both cells, loaded before v was known */
+__device__ __forceinline__ int64_t bm_rank_near(const DevIndex &A, const uint4 (&q)[4], int64_t j, int64_t v, int c)
+{
+	if (v >= A.n) return A.tot[c];
+	const int cc = c >= 3 ? c - 3 : c, second = (v >> RB3B_BM_SHIFT) != j;
+	const uint4 cq = second ? q[2] : q[0], pq = second ? q[3] : q[1];
+	uint64_t a0, a1, a2;
+	rb3b_hdr_unpack(cq, a0, a1, a2);
+	return (int64_t)((cc == 0 ? a0 : cc == 1 ? a1 : a2) + rb3b_bm_popc_below(pq, (uint32_t)v & 127u));
+}
+
+/* round >= 2 with the fix-up log (bitmap cells, one thread per segment): stream the log four rows at a time */
+__global__ void __launch_bounds__(64) k_walk_fix_log(DevIndex A, Segs S, int64_t *__restrict__ ka, int64_t n_items,
+                                                      const int64_t *__restrict__ wl_seg, const int64_t *__restrict__ wl_val,
+                                                      int64_t *__restrict__ nx_seg, int64_t *__restrict__ nx_val, unsigned long long *nx_n)
+{
+	const int U = 4;
+	int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (it >= n_items) return;
+	const int64_t t = wl_seg[it], d = S.d[t], len = S.len[t], base = S.logbase[t];
+	int64_t v = wl_val[it];
+	bool ended = false;
+	for (int64_t i0 = 0; i0 < d && !ended; i0 += U) {
+		int64_t kb[U], w[U], j[U];
+		uint4 q[U][4];
+#pragma unroll
+		for (int u = 0; u < U; ++u) {
+			int64_t i = i0 + u < d ? i0 + u : d - 1;
+			kb[u] = S.log_kb[base + i]; w[u] = S.log_lo[base + i];
+		}
+#pragma unroll
+		for (int u = 0; u < U; ++u) { /* cell loads do not depend on v: all of them are in flight before the chain starts */
+			int64_t lo = w[u] & (int64_t)RB3B_M42;
+			int c = (int)(w[u] >> LOG_C_SHIFT) & 7, h = c >= 3, cc = c - 3 * h;
+			j[u] = (lo < A.n ? lo : A.n - 1) >> RB3B_BM_SHIFT;
+			int64_t j2 = j[u] + 1 < A.n_cells ? j[u] + 1 : j[u];
+			if (w[u] & LOG_NARROW) {
+				q[u][0] = __ldg(A.cells + j[u] * 8 + 4 * h); q[u][1] = __ldg(A.cells + j[u] * 8 + 4 * h + 1 + cc);
+				q[u][2] = __ldg(A.cells + j2 * 8 + 4 * h);   q[u][3] = __ldg(A.cells + j2 * 8 + 4 * h + 1 + cc);
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < U; ++u) {
+			if (i0 + u >= d || ended) break;
+			int c = (int)(w[u] >> LOG_C_SHIFT) & 7;
+			ka[kb[u]] = v;
+			if (c == 0) { ended = true; break; }
+			int64_t r = (w[u] & LOG_NARROW) ? bm_rank_near(A, q[u], j[u], v, c) : BmRank::rank(A, v, c);
+			v = A.acc[c] + r;
+		}
+	}
+	S.d[t] = 0;
+	int64_t u2 = S.succ[t];
+	if (d == len && u2 >= 0) {
+		S.arr_lo[t] = S.arr_hi[t] = v;
+		if (S.d[u2] > 0) {
+			unsigned long long o = atomicAdd(nx_n, 1ULL);
+			nx_seg[o] = u2; nx_val[o] = v;
+		}
 	}
 }
 
@@ -377,11 +466,19 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	S.d = seg.p; S.len = seg.p + S.n_seg; S.succ = seg.p + 2 * S.n_seg; S.arr_lo = seg.p + 3 * S.n_seg; S.arr_hi = seg.p + 4 * S.n_seg;
 	S.row = seg.p + 5 * S.n_seg; S.cmap = cmap.p;
 	k_coarse_fill<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, f_flag, f_sid, seg.p + 5 * S.n_seg, cmap.p, lfb.p); CKK();
+	const bool bm = A->kind == RB3B_KIND_BM;
+	DBuf<int64_t> seglen, logbase, logbuf;
+	S.logbase = 0; S.log_kb = S.log_lo = 0;
+	if (bm && rb3b_get_param("fix_log", 1) && len * 16 <= rb3b_get_param("fix_log_max_bytes", 16LL << 30)) {
+		TRY(seglen.alloc(S.n_seg)); TRY(logbase.alloc(S.n_seg)); TRY(logbuf.alloc(2 * len));
+		k_seg_len<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, f_flag, f_sid, f_succ, f_piece, seglen.p); CKK();
+		TRY(rb3b_scan_excl_i64(seglen.p, logbase.p, S.n_seg));
+		S.logbase = logbase.p; S.log_kb = logbuf.p; S.log_lo = logbuf.p + len;
+	}
 	rb3b_toc(T_PREP);
 	CK(cudaMemsetAsync(ctr.p, 0, 8 * 8, rb3b_stream));
 	CK(cudaMemsetAsync(ka.p, 0xff, len * 8, rb3b_stream));
 	DevIndex dA = rb3b_dev_view(A);
-	const bool bm = A->kind == RB3B_KIND_BM;
 	/* bitmap walks are single threads: small CTAs spread the few thousand walks over all SMs */
 	const int wg = bm ? 1 : 8, wtpb = bm ? 32 : TPB;
 	int64_t want = (S.n_seg * wg + wtpb - 1) / wtpb, cap = (int64_t)n_sm() * (bm ? 32 : 8);
@@ -401,7 +498,9 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 		CK(cudaMemsetAsync(ctr.p + 2, 0, 16, rb3b_stream));
 		want = (n_items * wg + wtpb - 1) / wtpb;
 		rb3b_tic(T_WALKFIX);
-		if (bm) k_walk_fix<BmRank><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, S, lfb.p, ka.p, n_items, wl_seg[cur], wl_val[cur], ctr.p + 2,
+		if (bm && S.logbase) k_walk_fix_log<<<nblk(n_items, 64), 64, 0, rb3b_stream>>>(dA, S, ka.p, n_items, wl_seg[cur], wl_val[cur],
+			wl_seg[cur ^ 1], wl_val[cur ^ 1], (unsigned long long*)(ctr.p + 3));
+		else if (bm) k_walk_fix<BmRank><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, S, lfb.p, ka.p, n_items, wl_seg[cur], wl_val[cur], ctr.p + 2,
 			wl_seg[cur ^ 1], wl_val[cur ^ 1], (unsigned long long*)(ctr.p + 3));
 		else k_walk_fix<Grp<8> ><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, S, lfb.p, ka.p, n_items, wl_seg[cur], wl_val[cur], ctr.p + 2,
 			wl_seg[cur ^ 1], wl_val[cur ^ 1], (unsigned long long*)(ctr.p + 3));
