@@ -282,53 +282,70 @@ __device__ __forceinline__ int64_t bm_rank_near(const DevIndex &A, const uint4 (
 	return (int64_t)((cc == 0 ? a0 : cc == 1 ? a1 : a2) + rb3b_bm_popc_below(pq, (uint32_t)v & 127u));
 }
 
-/* round >= 2 with the fix-up log (bitmap cells, one thread per segment): stream the log four rows at a time */
-__global__ void __launch_bounds__(64) k_walk_fix_log(DevIndex A, Segs S, int64_t *__restrict__ ka, int64_t n_items,
-                                                      const int64_t *__restrict__ wl_seg, const int64_t *__restrict__ wl_val,
-                                                      int64_t *__restrict__ nx_seg, int64_t *__restrict__ nx_val, unsigned long long *nx_n)
-{
-	const int U = 4;
-	int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (it >= n_items) return;
-	const int64_t t = wl_seg[it], d = S.d[t], len = S.len[t], base = S.logbase[t];
-	int64_t v = wl_val[it];
-	bool ended = false;
-	for (int64_t i0 = 0; i0 < d && !ended; i0 += U) {
-		int64_t kb[U], w[U], j[U];
-		uint4 q[U][4];
-#pragma unroll
-		for (int u = 0; u < U; ++u) {
-			int64_t i = i0 + u < d ? i0 + u : d - 1;
-			kb[u] = S.log_kb[base + i]; w[u] = S.log_lo[base + i];
-		}
-#pragma unroll
-		for (int u = 0; u < U; ++u) { /* cell loads do not depend on v: all of them are in flight before the chain starts */
-			int64_t lo = w[u] & (int64_t)RB3B_M42;
-			int c = (int)(w[u] >> LOG_C_SHIFT) & 7, h = c >= 3, cc = c - 3 * h;
-			j[u] = (lo < A.n ? lo : A.n - 1) >> RB3B_BM_SHIFT;
-			int64_t j2 = j[u] + 1 < A.n_cells ? j[u] + 1 : j[u];
-			if (w[u] & LOG_NARROW) {
-				q[u][0] = __ldg(A.cells + j[u] * 8 + 4 * h); q[u][1] = __ldg(A.cells + j[u] * 8 + 4 * h + 1 + cc);
-				q[u][2] = __ldg(A.cells + j2 * 8 + 4 * h);   q[u][3] = __ldg(A.cells + j2 * 8 + 4 * h + 1 + cc);
-			}
-		}
-#pragma unroll
-		for (int u = 0; u < U; ++u) {
-			if (i0 + u >= d || ended) break;
-			int c = (int)(w[u] >> LOG_C_SHIFT) & 7;
-			ka[kb[u]] = v;
-			if (c == 0) { ended = true; break; }
-			int64_t r = (w[u] & LOG_NARROW) ? bm_rank_near(A, q[u], j[u], v, c) : BmRank::rank(A, v, c);
-			v = A.acc[c] + r;
+/* one logged row held by one lane */
+struct LogRow {
+	int64_t kb, j;
+	int c, narrow;
+	uint4 q[4];
+	__device__ __forceinline__ void load(const DevIndex &A, const Segs &S, int64_t slot, bool valid)
+	{
+		kb = 0; j = 0; c = 0; narrow = 0;
+		if (!valid) return;
+		kb = S.log_kb[slot];
+		int64_t w = S.log_lo[slot], lo = w & (int64_t)RB3B_M42;
+		c = (int)(w >> LOG_C_SHIFT) & 7; narrow = (w & LOG_NARROW) != 0;
+		j = (lo < A.n ? lo : A.n - 1) >> RB3B_BM_SHIFT;
+		if (narrow) { /* the two cells that can hold the exact position: loads independent of the chain */
+			const int h = c >= 3, cc = c - 3 * h;
+			const int64_t j2 = j + 1 < A.n_cells ? j + 1 : j;
+			q[0] = __ldg(A.cells + j * 8 + 4 * h);  q[1] = __ldg(A.cells + j * 8 + 4 * h + 1 + cc);
+			q[2] = __ldg(A.cells + j2 * 8 + 4 * h); q[3] = __ldg(A.cells + j2 * 8 + 4 * h + 1 + cc);
 		}
 	}
-	S.d[t] = 0;
-	int64_t u2 = S.succ[t];
-	if (d == len && u2 >= 0) {
-		S.arr_lo[t] = S.arr_hi[t] = v;
-		if (S.d[u2] > 0) {
-			unsigned long long o = atomicAdd(nx_n, 1ULL);
-			nx_seg[o] = u2; nx_val[o] = v;
+};
+
+/* round >= 2 with the fix-up log (bitmap cells): one WARP per listed segment.  Each lane fetches one logged row
+ * (coalesced) and the cells it may need, for the current 32 rows and, ahead of time, for the next 32; then the exact
+ * value is passed from lane to lane: the dependent chain is ~30 instructions per row with no memory access on it
+ * except for the few rows whose bracket was still wider than a cell pair. */
+__global__ void __launch_bounds__(128) k_walk_fix_log(DevIndex A, Segs S, int64_t *__restrict__ ka, int64_t n_items,
+                                                       const int64_t *__restrict__ wl_seg, const int64_t *__restrict__ wl_val,
+                                                       int64_t *__restrict__ nx_seg, int64_t *__restrict__ nx_val, unsigned long long *nx_n)
+{
+	const int lane = threadIdx.x & 31;
+	int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (it >= n_items) return; /* warp-uniform */
+	const int64_t t = wl_seg[it], d = S.d[t], len = S.len[t], base = S.logbase[t];
+	int64_t v = wl_val[it];
+	int ended = 0;
+	LogRow cur, nxt;
+	cur.load(A, S, base + lane, lane < d);
+	for (int64_t i0 = 0; i0 < d && !ended; i0 += 32) {
+		nxt.load(A, S, base + i0 + 32 + lane, i0 + 32 + lane < d);
+		const int cnt = d - i0 < 32 ? (int)(d - i0) : 32;
+		for (int u = 0; u < cnt; ++u) {
+			int64_t nv = v;
+			int e = 0;
+			if (lane == u) {
+				ka[cur.kb] = v;
+				if (cur.c == 0) e = 1;
+				else nv = A.acc[cur.c] + (cur.narrow ? bm_rank_near(A, cur.q, cur.j, v, cur.c) : BmRank::rank(A, v, cur.c));
+			}
+			v = __shfl_sync(0xffffffffu, nv, u);
+			ended = __shfl_sync(0xffffffffu, e, u);
+			if (ended) break;
+		}
+		cur = nxt;
+	}
+	if (lane == 0) {
+		S.d[t] = 0;
+		int64_t u2 = S.succ[t];
+		if (d == len && u2 >= 0) {
+			S.arr_lo[t] = S.arr_hi[t] = v;
+			if (S.d[u2] > 0) {
+				unsigned long long o = atomicAdd(nx_n, 1ULL);
+				nx_seg[o] = u2; nx_val[o] = v;
+			}
 		}
 	}
 }
@@ -498,7 +515,7 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 		CK(cudaMemsetAsync(ctr.p + 2, 0, 16, rb3b_stream));
 		want = (n_items * wg + wtpb - 1) / wtpb;
 		rb3b_tic(T_WALKFIX);
-		if (bm && S.logbase) k_walk_fix_log<<<nblk(n_items, 64), 64, 0, rb3b_stream>>>(dA, S, ka.p, n_items, wl_seg[cur], wl_val[cur],
+		if (bm && S.logbase) k_walk_fix_log<<<nblk(n_items * 32, 128), 128, 0, rb3b_stream>>>(dA, S, ka.p, n_items, wl_seg[cur], wl_val[cur],
 			wl_seg[cur ^ 1], wl_val[cur ^ 1], (unsigned long long*)(ctr.p + 3));
 		else if (bm) k_walk_fix<BmRank><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, S, lfb.p, ka.p, n_items, wl_seg[cur], wl_val[cur], ctr.p + 2,
 			wl_seg[cur ^ 1], wl_val[cur ^ 1], (unsigned long long*)(ctr.p + 3));
