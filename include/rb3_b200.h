@@ -71,6 +71,15 @@ int rb3b_merge_plain_dev(rb3b_index_t *idx, int64_t len, const uint8_t *d_bwt);
 int rb3b_mg_rank_plain(const rb3b_index_t *idx, int64_t len, const uint8_t *bwt, int64_t *rb, int64_t acc[RB3B_ASIZE + 1]);
 int rb3b_mg_rank_plain_dev(const rb3b_index_t *idx, int64_t len, const uint8_t *d_bwt, int64_t *d_rb, int64_t acc[RB3B_ASIZE + 1]);
 
+/* Multi-device building blocks.  The reference parallelises rb3_mg_rank_plain over the new sequences with kt_for
+ * (fm-index.c:220); here the index is replicated and device `part` of `n_parts` computes the interleave positions of
+ * its share of every sequence.  d_ka[len] (device): position of every row this part resolved, -1 elsewhere; the
+ * element-wise MAX over all parts (ncclAllReduce) is the array of rb3b_mg_rank_plain without the packing.
+ * Returns 0; 1 when the part could not resolve all of its rows locally (fall back to part 0 of 1); < 0 on error. */
+int rb3b_mg_rank_part(const rb3b_index_t *idx, int64_t len, const uint8_t *d_bwt, int part, int n_parts, int64_t *d_ka);
+/* second half of rb3_fmi_merge_plain (worker_mgins, fm-index.c:237-249 / :295) given the complete d_ka[len] */
+int rb3b_merge_with_ka(rb3b_index_t *idx, int64_t len, const uint8_t *d_bwt, const int64_t *d_ka);
+
 /* rb3_fmi_merge (fm-index.c:251-277) for `ropebwt3 merge`: B is another index. */
 int rb3b_merge_index(rb3b_index_t *idx, const rb3b_index_t *other);
 

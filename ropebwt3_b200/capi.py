@@ -35,6 +35,8 @@ SIGNATURES = {
     "rb3b_merge_plain_dev": (_int, [_vp, _i64, _vp]),
     "rb3b_mg_rank_plain": (_int, [_vp, _i64, _vp, _vp, _vp]),
     "rb3b_mg_rank_plain_dev": (_int, [_vp, _i64, _vp, _vp, _vp]),
+    "rb3b_mg_rank_part": (_int, [_vp, _i64, _vp, _int, _int, _vp]),
+    "rb3b_merge_with_ka": (_int, [_vp, _i64, _vp, _vp]),
     "rb3b_merge_index": (_int, [_vp, _vp]),
     "rb3b_rank1a": (_int, [_vp, _i64, _vp, _vp, _vp]),
     "rb3b_rank1a_dev": (_int, [_vp, _i64, _vp, _vp, _vp]),

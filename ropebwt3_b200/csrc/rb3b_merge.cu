@@ -142,13 +142,49 @@ __global__ void k_fine_walk(Fine F, const uint64_t *__restrict__ lfb, int64_t *_
 }
 
 /* Wyllie pointer jumping: after ceil(log2 n) rounds dist[f] = #rows from fine mark f to the start of its sequence */
-__global__ void k_list_rank(int64_t n, const int64_t *__restrict__ succ_in, const int64_t *__restrict__ dist_in, int64_t *__restrict__ succ_out, int64_t *__restrict__ dist_out)
+__global__ void k_list_rank(int64_t n, const int64_t *__restrict__ succ_in, const int64_t *__restrict__ dist_in, const int64_t *__restrict__ term_in,
+                            int64_t *__restrict__ succ_out, int64_t *__restrict__ dist_out, int64_t *__restrict__ term_out)
 {
 	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (f >= n) return;
-	int64_t s = succ_in[f], d = dist_in[f];
-	if (s >= 0) { d += dist_in[s]; s = succ_in[s]; }
-	succ_out[f] = s; dist_out[f] = d;
+	int64_t s = succ_in[f], d = dist_in[f], t = term_in ? term_in[f] : f; /* t: last fine mark of f's chain seen so far */
+	if (s >= 0) { d += dist_in[s]; t = term_in ? term_in[s] : s; s = succ_in[s]; }
+	succ_out[f] = s; dist_out[f] = d; term_out[f] = t;
+}
+
+/* the sentinel fine mark p starts a chain: record the chain's length at its terminal mark */
+__global__ void k_chain_len(int64_t n_seq, const int64_t *__restrict__ to_end, const int64_t *__restrict__ term, int64_t *__restrict__ chain_len)
+{
+	int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p < n_seq) chain_len[term[p]] = to_end[p];
+}
+
+/* Which segments does device `part` of `n_parts` walk?  Long chains are cut into n_parts contiguous stretches (by the
+ * distance walked from the sentinel); a part also walks the `halo` rows before its stretch speculatively so that its
+ * first segment receives an exact value without any exchange.  Short chains go to one part as a whole.
+ * role: 0 not mine, 1 mine (counts for completeness), 2 halo (walked, result not required). */
+__global__ void k_seg_role(Fine F, const int64_t *__restrict__ flag, const int64_t *__restrict__ sid, const int64_t *__restrict__ to_end,
+                           const int64_t *__restrict__ term, const int64_t *__restrict__ chain_len, int part, int n_parts, int64_t halo, int64_t min_stretch,
+                           uint8_t *__restrict__ role)
+{
+	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (f >= F.n_fine || !flag[f]) return;
+	int r = 1;
+	if (n_parts > 1) {
+		int64_t L = chain_len[term[f]], ds = L - to_end[f]; /* rows walked from the sentinel before this segment */
+		if (L <= 0 || ds < 0) r = 1; /* not a valid BWT: let the completeness check report it */
+		else if (L < min_stretch * n_parts) r = (int)(term[f] % n_parts) == part;
+		else {
+			int64_t q = ds * n_parts / L;
+			if (q >= n_parts) q = n_parts - 1;
+			if (q == part) r = 1;
+			else {
+				int64_t b = ((int64_t)part * L + n_parts - 1) / n_parts; /* first ds of my stretch */
+				r = (part > 0 && ds < b && ds + halo >= b) ? 2 : 0;
+			}
+		}
+	}
+	role[sid[f]] = (uint8_t)r;
 }
 
 /* a fine mark becomes a coarse mark when the walk crosses a multiple of seg_len on the way to it */
@@ -202,12 +238,15 @@ struct Segs {
 	 * end, the row's symbol and whether the bracket is at most 128 wide.  The later rounds then stream this log
 	 * instead of chasing LF_B, and for narrow brackets the two cells that can hold the exact position are known in
 	 * advance, so their loads no longer sit on the dependent chain. */
+	const uint8_t *role;    /* 0: another device walks this segment, 1: mine, 2: halo */
 	const int64_t *logbase; /* per segment: first log slot; NULL = no log */
 	int64_t *log_kb, *log_lo;
 };
 
 #define LOG_C_SHIFT 42
 #define LOG_NARROW (1LL << 45)
+#define LOG_NCELL 3              /* a "narrow" bracket spans at most LOG_NCELL consecutive cells */
+#define LOG_WIDTH ((LOG_NCELL - 1) * 128)
 
 /* The walk kernels are written for a "ranker" WG: Grp<8> (RLE cells, 8 lanes per walk) or BmRank (bitmap cells,
  * one thread per walk). */
@@ -223,6 +262,7 @@ __global__ void __launch_bounds__(TPB) k_walk_first(DevIndex A, Acc7 accB, Segs 
 		if (gl == 0) s = (int64_t)atomicAdd((unsigned long long*)next_seg, 1ULL);
 		s = __shfl_sync(gmask, s, gbase);
 		if (s >= S.n_seg) break;
+		if (S.role[s] == 0) continue; /* group-uniform */
 		int64_t kb = S.row[s], lo, hi, d = 0, len = 0, succ = -1;
 		if (kb < S.n_seq) lo = hi = A.acc[1]; /* new sentinels sort after all old ones, fm-index.c:164 */
 		else {
@@ -238,7 +278,7 @@ __global__ void __launch_bounds__(TPB) k_walk_first(DevIndex A, Acc7 accB, Segs 
 				if (S.logbase && gl == 0) {
 					int64_t o = S.logbase[s] + d;
 					S.log_kb[o] = kb;
-					S.log_lo[o] = lo | (int64_t)c << LOG_C_SHIFT | (hi - lo <= 128 ? LOG_NARROW : 0);
+					S.log_lo[o] = lo | (int64_t)c << LOG_C_SHIFT | (hi - lo <= LOG_WIDTH ? LOG_NARROW : 0);
 				}
 				++d;
 			}
@@ -262,7 +302,7 @@ __global__ void __launch_bounds__(TPB) k_walk_first(DevIndex A, Acc7 accB, Segs 
 __global__ void k_collect_first(Segs S, int64_t *__restrict__ wl_seg, int64_t *__restrict__ wl_val, unsigned long long *wl_n)
 {
 	int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= S.n_seg) return;
+	if (s >= S.n_seg || S.role[s] == 0) return;
 	int64_t t = S.succ[s];
 	if (t >= 0 && S.arr_lo[s] == S.arr_hi[s] && S.d[t] > 0) {
 		unsigned long long o = atomicAdd(wl_n, 1ULL);
@@ -270,13 +310,15 @@ __global__ void k_collect_first(Segs S, int64_t *__restrict__ wl_seg, int64_t *_
 	}
 }
 
-/* exact rank when the position v is known to lie in cell j or j+1 (j = cell of the bracket's low end): q holds the
- * count quad and the plane quad of symbol c for both cells, loaded before v was known */
-__device__ __forceinline__ int64_t bm_rank_near(const DevIndex &A, const uint4 (&q)[4], int64_t j, int64_t v, int c)
+/* exact rank when the position v is known to lie in one of the cells j .. j+LOG_NCELL-1 (j = cell of the bracket's
+ * low end): q holds the count quad and the plane quad of symbol c of those cells, loaded before v was known */
+__device__ __forceinline__ int64_t bm_rank_near(const DevIndex &A, const uint4 (&q)[2 * LOG_NCELL], int64_t j, int64_t v, int c)
 {
 	if (v >= A.n) return A.tot[c];
-	const int cc = c >= 3 ? c - 3 : c, second = (v >> RB3B_BM_SHIFT) != j;
-	const uint4 cq = second ? q[2] : q[0], pq = second ? q[3] : q[1];
+	const int cc = c >= 3 ? c - 3 : c, which = (int)((v >> RB3B_BM_SHIFT) - j);
+	uint4 cq = q[0], pq = q[1];
+#pragma unroll
+	for (int i = 1; i < LOG_NCELL; ++i) if (which == i) { cq = q[2 * i]; pq = q[2 * i + 1]; }
 	uint64_t a0, a1, a2;
 	rb3b_hdr_unpack(cq, a0, a1, a2);
 	return (int64_t)((cc == 0 ? a0 : cc == 1 ? a1 : a2) + rb3b_bm_popc_below(pq, (uint32_t)v & 127u));
@@ -286,7 +328,7 @@ __device__ __forceinline__ int64_t bm_rank_near(const DevIndex &A, const uint4 (
 struct LogRow {
 	int64_t kb, j;
 	int c, narrow;
-	uint4 q[4];
+	uint4 q[2 * LOG_NCELL];
 	__device__ __forceinline__ void load(const DevIndex &A, const Segs &S, int64_t slot, bool valid)
 	{
 		kb = 0; j = 0; c = 0; narrow = 0;
@@ -297,9 +339,11 @@ struct LogRow {
 		j = (lo < A.n ? lo : A.n - 1) >> RB3B_BM_SHIFT;
 		if (narrow) { /* the two cells that can hold the exact position: loads independent of the chain */
 			const int h = c >= 3, cc = c - 3 * h;
-			const int64_t j2 = j + 1 < A.n_cells ? j + 1 : j;
-			q[0] = __ldg(A.cells + j * 8 + 4 * h);  q[1] = __ldg(A.cells + j * 8 + 4 * h + 1 + cc);
-			q[2] = __ldg(A.cells + j2 * 8 + 4 * h); q[3] = __ldg(A.cells + j2 * 8 + 4 * h + 1 + cc);
+#pragma unroll
+			for (int i = 0; i < LOG_NCELL; ++i) {
+				const int64_t ji = j + i < A.n_cells ? j + i : A.n_cells - 1;
+				q[2 * i] = __ldg(A.cells + ji * 8 + 4 * h); q[2 * i + 1] = __ldg(A.cells + ji * 8 + 4 * h + 1 + cc);
+			}
 		}
 	}
 };
@@ -391,8 +435,10 @@ __global__ void k_seg_check(Segs S, unsigned long long *sums)
 {
 	int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= S.n_seg) return;
+	if (S.role[s] != 1) return;
 	if (S.d[s]) atomicAdd(&sums[0], (unsigned long long)S.d[s]);
 	atomicAdd(&sums[1], (unsigned long long)S.len[s]);
+	atomicAdd(&sums[2], 1ULL);
 }
 
 /* rb[i] = (ka+i)<<6 | B[i]<<3 | first symbol of suffix i (fm-index.c:168) */
@@ -416,7 +462,10 @@ __global__ void k_check_monotone(int64_t len, const int64_t *__restrict__ ka, in
 int64_t rb3b_get_param(const char *key, int64_t dflt); /* rb3b_runtime.cu */
 
 /* interleave positions of the batch in device memory: ka[len], accB */
-static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, DBuf<int64_t> &ka, int64_t accB[RB3B_ASIZE + 1])
+/* part/n_parts: see k_seg_role.  ka_out != NULL: write there instead of allocating.  *incomplete is set when a part could
+ * not resolve all of its own rows locally (only possible with n_parts > 1). */
+static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, DBuf<int64_t> &ka, int64_t accB[RB3B_ASIZE + 1],
+                      int part = 0, int n_parts = 1, int64_t *ka_out = 0, int *incomplete = 0)
 {
 	int64_t nt = (len + PREP_TILE - 1) / PREP_TILE;
 	DBuf<int64_t> tcnt, tex;
@@ -455,17 +504,18 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	int64_t n_samp = (len - 1) / F.fine_len - F.m0 + 1;
 	F.n_fine = F.n_seq + (n_samp > 0 ? n_samp : 0);
 	k_prep_lf<<<(unsigned)nt, TPB, 0, rb3b_stream>>>(len, d_bwt, nt, tex.p, acc, F.fine_len, lfb.p); CKK();
-	DBuf<int64_t> fn; /* succ, piece, 2 x (succ, dist) ping-pong, flag, sid */
+	DBuf<int64_t> fn; /* succ, piece, 2 x (succ, dist, term) ping-pong, flag, sid, chain_len */
 	DBuf<int32_t> cmap;
-	TRY(fn.alloc(F.n_fine * 8)); TRY(cmap.alloc(F.n_fine));
-	int64_t *f_succ = fn.p, *f_piece = fn.p + F.n_fine, *pp[2][2] = { { fn.p + 2 * F.n_fine, fn.p + 3 * F.n_fine }, { fn.p + 4 * F.n_fine, fn.p + 5 * F.n_fine } };
-	int64_t *f_flag = fn.p + 6 * F.n_fine, *f_sid = fn.p + 7 * F.n_fine;
+	TRY(fn.alloc(F.n_fine * 11)); TRY(cmap.alloc(F.n_fine));
+	int64_t *f_succ = fn.p, *f_piece = fn.p + F.n_fine;
+	int64_t *pp[2][3] = { { fn.p + 2 * F.n_fine, fn.p + 3 * F.n_fine, fn.p + 4 * F.n_fine }, { fn.p + 5 * F.n_fine, fn.p + 6 * F.n_fine, fn.p + 7 * F.n_fine } };
+	int64_t *f_flag = fn.p + 8 * F.n_fine, *f_sid = fn.p + 9 * F.n_fine, *f_clen = fn.p + 10 * F.n_fine;
 	k_fine_walk<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, lfb.p, f_succ, f_piece); CKK();
-	const int64_t *cs = f_succ, *cd = f_piece;
+	const int64_t *cs = f_succ, *cd = f_piece, *ct = 0;
 	int cur = 0;
-	for (int64_t span = 1; span < F.n_fine; span <<= 1) {
-		k_list_rank<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F.n_fine, cs, cd, pp[cur][0], pp[cur][1]); CKK();
-		cs = pp[cur][0]; cd = pp[cur][1]; cur ^= 1;
+	for (int64_t span = 1; span < F.n_fine || ct == 0; span <<= 1) { /* at least once: it also initialises the terminal marks */
+		k_list_rank<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F.n_fine, cs, cd, ct, pp[cur][0], pp[cur][1], pp[cur][2]); CKK();
+		cs = pp[cur][0]; cd = pp[cur][1]; ct = pp[cur][2]; cur ^= 1;
 	}
 	CK(cudaMemsetAsync(f_flag, 0, F.n_fine * 8, rb3b_stream));
 	k_coarse_flag<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, seg_len, f_succ, f_piece, cd, f_flag); CKK();
@@ -479,7 +529,14 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	S.n_seq = F.n_seq;
 	S.n_seg = last[0] + last[1];
 	DBuf<int64_t> seg, wl, ctr;
-	TRY(seg.alloc(S.n_seg * 6)); TRY(wl.alloc(S.n_seg * 4)); TRY(ctr.alloc(8)); TRY(ka.alloc(len));
+	DBuf<uint8_t> role;
+	TRY(seg.alloc(S.n_seg * 6)); TRY(wl.alloc(S.n_seg * 4)); TRY(ctr.alloc(8)); TRY(role.alloc(S.n_seg));
+	if (ka_out) ka.p = ka_out; else TRY(ka.alloc(len));
+	CK(cudaMemsetAsync(seg.p, 0, S.n_seg * 5 * 8, rb3b_stream)); /* d = 0 for the segments other devices walk */
+	k_chain_len<<<nblk(F.n_seq, TPB), TPB, 0, rb3b_stream>>>(F.n_seq, cd, ct, f_clen); CKK();
+	k_seg_role<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, f_flag, f_sid, cd, ct, f_clen, part, n_parts,
+		rb3b_get_param("halo_segments", 8) * seg_len, 4 * seg_len, role.p); CKK();
+	S.role = role.p;
 	S.d = seg.p; S.len = seg.p + S.n_seg; S.succ = seg.p + 2 * S.n_seg; S.arr_lo = seg.p + 3 * S.n_seg; S.arr_hi = seg.p + 4 * S.n_seg;
 	S.row = seg.p + 5 * S.n_seg; S.cmap = cmap.p;
 	k_coarse_fill<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, f_flag, f_sid, seg.p + 5 * S.n_seg, cmap.p, lfb.p); CKK();
@@ -529,10 +586,10 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 		rb3b_tflush();
 		cur ^= 1; ++rounds;
 	}
-	unsigned long long sums[2];
-	CK(cudaMemsetAsync(ctr.p + 4, 0, 16, rb3b_stream));
+	unsigned long long sums[3];
+	CK(cudaMemsetAsync(ctr.p + 4, 0, 24, rb3b_stream));
 	k_seg_check<<<nblk(S.n_seg, TPB), TPB, 0, rb3b_stream>>>(S, (unsigned long long*)(ctr.p + 4)); CKK();
-	CK(cudaMemcpyAsync(sums, ctr.p + 4, 16, cudaMemcpyDeviceToHost, rb3b_stream));
+	CK(cudaMemcpyAsync(sums, ctr.p + 4, 24, cudaMemcpyDeviceToHost, rb3b_stream));
 	CK(cudaStreamSynchronize(rb3b_stream));
 	rb3b_tflush();
 	rb3b_stat_set("n_segments", S.n_seg);
@@ -541,6 +598,12 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	rb3b_stat_add("fix_rounds_total", rounds - 1);
 	rb3b_stat_set("fix_segments", fix_rows);
 	rb3b_stat_set("unresolved_rows", (int64_t)sums[0]);
+	rb3b_stat_set("own_segments", (int64_t)sums[2]);
+	rb3b_stat_set("own_rows", (int64_t)sums[1]);
+	if (n_parts > 1) { /* completeness of the whole batch is checked after the exchange */
+		if (incomplete) *incomplete = sums[0] != 0;
+		return RB3B_OK;
+	}
 	if (sums[0] != 0 || (int64_t)sums[1] != len)
 		return rb3b_fail(RB3B_EINVAL, "batch is not the BWT of a sentinel-terminated string set (%lld of %lld rows reachable, %lld unresolved)",
 		                 (long long)sums[1], (long long)len, (long long)sums[0]);
@@ -611,6 +674,29 @@ extern "C" int rb3b_mg_rank_plain(const rb3b_index_t *x, int64_t len, const uint
 	CK(cudaMemcpyAsync(rb, drb.p, len * 8, cudaMemcpyDeviceToHost, rb3b_stream));
 	CK(cudaStreamSynchronize(rb3b_stream));
 	return RB3B_OK;
+}
+
+/* ---- multi-device building blocks: index replicated, rows of the batch split among the devices ---- */
+
+extern "C" int rb3b_mg_rank_part(const rb3b_index_t *x, int64_t len, const uint8_t *d_bwt, int part, int n_parts, int64_t *d_ka)
+{
+	ApiScope scope_;
+	TRY(rb3b_ensure_init());
+	if (n_parts < 1 || part < 0 || part >= n_parts) return rb3b_fail(RB3B_EINVAL, "part %d of %d", part, n_parts);
+	DBuf<int64_t> ka;
+	int64_t accB[RB3B_ASIZE + 1];
+	int incomplete = 0;
+	TRY(rank_phase(x, len, d_bwt, ka, accB, part, n_parts, d_ka, &incomplete));
+	return incomplete ? 1 : RB3B_OK;
+}
+
+extern "C" int rb3b_merge_with_ka(rb3b_index_t *x, int64_t len, const uint8_t *d_bwt, const int64_t *d_ka)
+{
+	ApiScope scope_;
+	TRY(rb3b_ensure_init());
+	if (len <= 0) return RB3B_OK;
+	if (x->n_cells == 0) return rb3b_fail(RB3B_EINVAL, "merge_with_ka on an empty index");
+	return merge_phase(x, len, d_bwt, d_ka); /* rejects arrays with holes (-1) or out of order */
 }
 
 extern "C" int rb3b_merge_plain_dev(rb3b_index_t *x, int64_t len, const uint8_t *d_bwt)

@@ -305,6 +305,59 @@ def test_merge_index(rb3, oracle, golden):
     assert np.array_equal(np.concatenate(a.export_runs()), np.concatenate(c.export_runs()))
 
 
+@pytest.mark.parametrize("n_parts", [2, 3, 8])
+def test_sharded_rank_phase(rb3, oracle, n_parts):
+    """rb3b_mg_rank_part for every part (run one after the other on this GPU): MAX-combining the parts gives exactly the
+    single-device interleave array; rb3b_merge_with_ka then equals rb3b_merge_plain."""
+    import torch
+    from ropebwt3_b200 import synth, capi
+    L = capi.lib()
+    gs = synth.genomes(5, 60000, seed=5, sub=0.01, indel=0.001)
+    gs.append(gs[2].copy())                                   # an exact duplicate: its chains never collapse
+    rb3.set_param("seg_len", 256)
+    try:
+        idx = rb3.Index.from_plain(rb3.rb3_build_sais(synth.batch_text(gs[:2])))
+        for k, g in enumerate(gs[2:]):
+            bwt = rb3.rb3_build_sais(synth.batch_text([g] if k % 2 else [g, g[:7000]]))
+            n = len(bwt)
+            rb, _ = idx.mg_rank_plain(bwt)
+            full = (rb >> 6) - np.arange(n)
+            d_bwt = torch.from_numpy(bwt).cuda()
+            parts, rcs = [], []
+            for p in range(n_parts):
+                ka = torch.empty(n, dtype=torch.int64, device="cuda")
+                torch.cuda.synchronize()
+                rcs.append(capi.check(L.rb3b_mg_rank_part(idx.h, n, d_bwt.data_ptr(), p, n_parts, ka.data_ptr())))
+                rb3.sync()
+                parts.append(ka.cpu().numpy())
+            if max(rcs) == 0:
+                comb = np.max(np.stack(parts), 0)
+                assert np.array_equal(comb, full), "parts=%d batch %d: %d rows differ" % (n_parts, k, int((comb != full).sum()))
+                for p_ in parts:   # whatever a part did resolve is right
+                    m = p_ >= 0
+                    assert np.array_equal(p_[m], full[m])
+            else:
+                assert k == 3, "only the duplicate genome may need the fallback"
+                comb = full
+            d_ka = torch.from_numpy(comb).cuda()
+            torch.cuda.synchronize()
+            capi.check(L.rb3b_merge_with_ka(idx.h, n, d_bwt.data_ptr(), d_ka.data_ptr()))
+            rb3.sync()
+        s, l = runs_of(idx, oracle)
+        sym, ln = None, None
+        want = rb3.Index.from_plain(rb3.rb3_build_sais(synth.batch_text(gs[:2])))
+        for k, g in enumerate(gs[2:]):
+            want.merge_plain(rb3.rb3_build_sais(synth.batch_text([g] if k % 2 else [g, g[:7000]])))
+        s0, l0 = want.export_runs()
+        assert np.array_equal(s, s0) and np.array_equal(l, l0)
+        # holes are refused
+        bad = torch.full((n,), -1, dtype=torch.int64, device="cuda")
+        with pytest.raises(rb3.Rb3bError):
+            capi.check(L.rb3b_merge_with_ka(idx.h, n, d_bwt.data_ptr(), bad.data_ptr()))
+    finally:
+        rb3.set_param("seg_len", 512)
+
+
 def test_device_pointer_entry_points(rb3, golden):
     import torch
     g = golden("merge_small")
