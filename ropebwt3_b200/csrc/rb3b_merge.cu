@@ -289,7 +289,10 @@ __global__ void __launch_bounds__(TPB) k_walk_first(DevIndex A, Acc7 accB, Segs 
 			int64_t r1, r2;
 			/* the groups that currently run together take the two-position path only while one of them still
 			 * carries a bracket; either path is correct for an exact group, so this is purely a cost choice */
-			if (__any_sync(__activemask(), lo != hi)) WG::rank2(A, lo, hi, c, r1, r2);
+			if (WG::G == 1) { /* one thread per walk: a private branch costs nothing and saves the second cell fetch */
+				if (lo != hi) WG::rank2(A, lo, hi, c, r1, r2);
+				else r1 = r2 = WG::rank(A, lo, c);
+			} else if (__any_sync(__activemask(), lo != hi)) WG::rank2(A, lo, hi, c, r1, r2);
 			else r1 = r2 = WG::rank(A, lo, c);
 			lo = A.acc[c] + r1; hi = A.acc[c] + r2;
 			if (x & LFB_COARSE) { succ = S.cmap[F.of_row(kb)]; break; }
@@ -310,41 +313,50 @@ __global__ void k_collect_first(Segs S, int64_t *__restrict__ wl_seg, int64_t *_
 	}
 }
 
-/* exact rank when the position v is known to lie in one of the cells j .. j+LOG_NCELL-1 (j = cell of the bracket's
- * low end): q holds the count quad and the plane quad of symbol c of those cells, loaded before v was known */
-__device__ __forceinline__ int64_t bm_rank_near(const DevIndex &A, const uint4 (&q)[2 * LOG_NCELL], int64_t j, int64_t v, int c)
-{
-	if (v >= A.n) return A.tot[c];
-	const int cc = c >= 3 ? c - 3 : c, which = (int)((v >> RB3B_BM_SHIFT) - j);
-	uint4 cq = q[0], pq = q[1];
-#pragma unroll
-	for (int i = 1; i < LOG_NCELL; ++i) if (which == i) { cq = q[2 * i]; pq = q[2 * i + 1]; }
-	uint64_t a0, a1, a2;
-	rb3b_hdr_unpack(cq, a0, a1, a2);
-	return (int64_t)((cc == 0 ? a0 : cc == 1 ? a1 : a2) + rb3b_bm_popc_below(pq, (uint32_t)v & 127u));
-}
-
-/* one logged row held by one lane */
+/* one logged row held by one lane; for a narrow bracket everything that does not depend on the exact value is
+ * precomputed: T[w] = #c between the window start and 32-bit word w of the window, W[w] = that word of plane c */
 struct LogRow {
-	int64_t kb, j;
+	int64_t kb, pos0, base; /* row; first position of the window; C[c] + #c before the window */
 	int c, narrow;
-	uint4 q[2 * LOG_NCELL];
+	uint32_t T[4 * LOG_NCELL], W[4 * LOG_NCELL];
 	__device__ __forceinline__ void load(const DevIndex &A, const Segs &S, int64_t slot, bool valid)
 	{
-		kb = 0; j = 0; c = 0; narrow = 0;
+		kb = 0; pos0 = 0; base = 0; c = 0; narrow = 0;
 		if (!valid) return;
 		kb = S.log_kb[slot];
 		int64_t w = S.log_lo[slot], lo = w & (int64_t)RB3B_M42;
 		c = (int)(w >> LOG_C_SHIFT) & 7; narrow = (w & LOG_NARROW) != 0;
-		j = (lo < A.n ? lo : A.n - 1) >> RB3B_BM_SHIFT;
-		if (narrow) { /* the two cells that can hold the exact position: loads independent of the chain */
-			const int h = c >= 3, cc = c - 3 * h;
+		if (!narrow) return;
+		const int h = c >= 3, cc = c - 3 * h;
+		const int64_t j = (lo < A.n ? lo : A.n - 1) >> RB3B_BM_SHIFT;
+		uint4 cq[LOG_NCELL], pq[LOG_NCELL];
 #pragma unroll
-			for (int i = 0; i < LOG_NCELL; ++i) {
-				const int64_t ji = j + i < A.n_cells ? j + i : A.n_cells - 1;
-				q[2 * i] = __ldg(A.cells + ji * 8 + 4 * h); q[2 * i + 1] = __ldg(A.cells + ji * 8 + 4 * h + 1 + cc);
-			}
+		for (int i = 0; i < LOG_NCELL; ++i) { /* loads independent of the chain */
+			const int64_t ji = j + i < A.n_cells ? j + i : A.n_cells - 1;
+			cq[i] = __ldg(A.cells + ji * 8 + 4 * h); pq[i] = __ldg(A.cells + ji * 8 + 4 * h + 1 + cc);
 		}
+		uint64_t h0 = 0;
+#pragma unroll
+		for (int i = 0; i < LOG_NCELL; ++i) {
+			uint64_t a0, a1, a2;
+			rb3b_hdr_unpack(cq[i], a0, a1, a2);
+			uint64_t hi = cc == 0 ? a0 : cc == 1 ? a1 : a2;
+			if (i == 0) h0 = hi;
+			uint32_t run = (uint32_t)(hi - h0);
+			const uint32_t ww[4] = { pq[i].x, pq[i].y, pq[i].z, pq[i].w };
+#pragma unroll
+			for (int k = 0; k < 4; ++k) { T[4 * i + k] = run; W[4 * i + k] = ww[k]; run += __popc(ww[k]); }
+		}
+		pos0 = j << RB3B_BM_SHIFT;
+		base = A.acc[c] + (int64_t)h0;
+	}
+	/* C[c] + rank(c, v) for the exact value v, which lies inside the window */
+	__device__ __forceinline__ int64_t step(const DevIndex &A, int64_t v) const
+	{
+		if (v >= A.n) return A.acc[c] + A.tot[c];
+		if (!narrow) return A.acc[c] + BmRank::rank(A, v, c);
+		uint32_t off = (uint32_t)(v - pos0), w = off >> 5;
+		return base + T[w] + __popc(W[w] & ((1u << (off & 31u)) - 1u));
 	}
 };
 
@@ -373,7 +385,7 @@ __global__ void __launch_bounds__(128) k_walk_fix_log(DevIndex A, Segs S, int64_
 			if (lane == u) {
 				ka[cur.kb] = v;
 				if (cur.c == 0) e = 1;
-				else nv = A.acc[cur.c] + (cur.narrow ? bm_rank_near(A, cur.q, cur.j, v, cur.c) : BmRank::rank(A, v, cur.c));
+				else nv = cur.step(A, v);
 			}
 			v = __shfl_sync(0xffffffffu, nv, u);
 			ended = __shfl_sync(0xffffffffu, e, u);
