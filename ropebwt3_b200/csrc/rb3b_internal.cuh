@@ -95,6 +95,7 @@ enum { T_PREP, T_WALK1, T_WALKFIX, T_MERGE, T_FINAL, T_BWT, T_COUNT };
 void rb3b_tic(int id);
 void rb3b_toc(int id);
 void rb3b_tflush(void);
+void rb3b_l2_pin(const void *p, size_t bytes);   /* persisting-L2 access window for the library stream; (0,0) clears it */
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
 	return rb3b_fail(RB3B_ENODEV, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
@@ -348,13 +349,16 @@ struct BmRank {
 	__device__ __forceinline__ static int base() { return threadIdx.x & 31; }
 	__device__ __forceinline__ static unsigned mask() { return 1u << (threadIdx.x & 31); }
 	__device__ __forceinline__ static int64_t count(const DevIndex &x, int64_t k, int c)
-	{ /* 0 <= k < n */
+	{ /* 0 <= k < n.  Kept short on purpose: in the LF walk this sits on a dependent chain, one call per row. */
 		const int h = c >= 3, cc = c - 3 * h;
-		const uint4 *half = x.cells + (k >> RB3B_BM_SHIFT) * 8 + 4 * h;
-		uint4 cq = __ldg(half), pq = __ldg(half + 1 + cc);
-		uint64_t a0, a1, a2;
-		rb3b_hdr_unpack(cq, a0, a1, a2);
-		return (int64_t)((cc == 0 ? a0 : cc == 1 ? a1 : a2) + rb3b_bm_popc_below(pq, (uint32_t)k & 127u));
+		const uint4 *half = x.cells + ((k >> RB3B_BM_SHIFT) * 8 + 4 * h);
+		const uint4 cq = __ldg(half), pq = __ldg(half + 1 + cc);
+		const uint64_t lo = (uint64_t)cq.x | (uint64_t)cq.y << 32, hi = (uint64_t)cq.z | (uint64_t)cq.w << 32;
+		const uint64_t cnt = (cc == 0 ? lo : cc == 1 ? (lo >> 42 | hi << 22) : hi >> 20) & RB3B_M42;
+		const uint64_t p0 = (uint64_t)pq.x | (uint64_t)pq.y << 32, p1 = (uint64_t)pq.z | (uint64_t)pq.w << 32;
+		const uint32_t o = (uint32_t)k & 127u;
+		const uint64_t m0 = o >= 64u ? ~0ULL : (1ULL << o) - 1ULL, m1 = o <= 64u ? 0ULL : (1ULL << (o - 64u)) - 1ULL;
+		return (int64_t)(cnt + (uint32_t)(__popcll(p0 & m0) + __popcll(p1 & m1)));
 	}
 	__device__ __forceinline__ static int64_t rank(const DevIndex &x, int64_t k, int c)
 	{

@@ -240,7 +240,7 @@ struct Segs {
 	 * advance, so their loads no longer sit on the dependent chain. */
 	const uint8_t *role;    /* 0: another device walks this segment, 1: mine, 2: halo */
 	const int64_t *logbase; /* per segment: first log slot; NULL = no log */
-	int64_t *log_kb, *log_lo;
+	longlong2 *log;         /* x = row, y = low end | symbol << 42 | narrow flag */
 };
 
 #define LOG_C_SHIFT 42
@@ -277,8 +277,7 @@ __global__ void __launch_bounds__(TPB) k_walk_first(DevIndex A, Acc7 accB, Segs 
 			else {
 				if (S.logbase && gl == 0) {
 					int64_t o = S.logbase[s] + d;
-					S.log_kb[o] = kb;
-					S.log_lo[o] = lo | (int64_t)c << LOG_C_SHIFT | (hi - lo <= LOG_WIDTH ? LOG_NARROW : 0);
+					S.log[o] = make_longlong2(kb, lo | (int64_t)c << LOG_C_SHIFT | (hi - lo <= LOG_WIDTH ? LOG_NARROW : 0));
 				}
 				++d;
 			}
@@ -289,10 +288,8 @@ __global__ void __launch_bounds__(TPB) k_walk_first(DevIndex A, Acc7 accB, Segs 
 			int64_t r1, r2;
 			/* the groups that currently run together take the two-position path only while one of them still
 			 * carries a bracket; either path is correct for an exact group, so this is purely a cost choice */
-			if (WG::G == 1) { /* one thread per walk: a private branch costs nothing and saves the second cell fetch */
-				if (lo != hi) WG::rank2(A, lo, hi, c, r1, r2);
-				else r1 = r2 = WG::rank(A, lo, c);
-			} else if (__any_sync(__activemask(), lo != hi)) WG::rank2(A, lo, hi, c, r1, r2);
+			/* (a private per-thread branch was measured slower for one-thread walks too: the two paths serialise) */
+			if (__any_sync(__activemask(), lo != hi)) WG::rank2(A, lo, hi, c, r1, r2);
 			else r1 = r2 = WG::rank(A, lo, c);
 			lo = A.acc[c] + r1; hi = A.acc[c] + r2;
 			if (x & LFB_COARSE) { succ = S.cmap[F.of_row(kb)]; break; }
@@ -323,8 +320,9 @@ struct LogRow {
 	{
 		kb = 0; pos0 = 0; base = 0; c = 0; narrow = 0;
 		if (!valid) return;
-		kb = S.log_kb[slot];
-		int64_t w = S.log_lo[slot], lo = w & (int64_t)RB3B_M42;
+		const longlong2 rec = S.log[slot];
+		kb = rec.x;
+		int64_t w = rec.y, lo = w & (int64_t)RB3B_M42;
 		c = (int)(w >> LOG_C_SHIFT) & 7; narrow = (w & LOG_NARROW) != 0;
 		if (!narrow) return;
 		const int h = c >= 3, cc = c - 3 * h;
@@ -509,7 +507,7 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	int64_t seg_len = rb3b_seg_len;
 	Fine F;
 	F.n_seq = acc.v[1];
-	F.fine_len = rb3b_get_param("fine_len", 64);
+	F.fine_len = rb3b_get_param("fine_len", 32);
 	if (F.fine_len > seg_len) F.fine_len = seg_len;
 	if (F.fine_len < 1) F.fine_len = 1;
 	F.m0 = (F.n_seq + F.fine_len - 1) / F.fine_len;
@@ -554,17 +552,20 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	k_coarse_fill<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, f_flag, f_sid, seg.p + 5 * S.n_seg, cmap.p, lfb.p); CKK();
 	const bool bm = A->kind == RB3B_KIND_BM;
 	DBuf<int64_t> seglen, logbase, logbuf;
-	S.logbase = 0; S.log_kb = S.log_lo = 0;
+	S.logbase = 0; S.log = 0;
 	if (bm && rb3b_get_param("fix_log", 1) && len * 16 <= rb3b_get_param("fix_log_max_bytes", 16LL << 30)) {
 		TRY(seglen.alloc(S.n_seg)); TRY(logbase.alloc(S.n_seg)); TRY(logbuf.alloc(2 * len));
 		k_seg_len<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, f_flag, f_sid, f_succ, f_piece, seglen.p); CKK();
 		TRY(rb3b_scan_excl_i64(seglen.p, logbase.p, S.n_seg));
-		S.logbase = logbase.p; S.log_kb = logbuf.p; S.log_lo = logbuf.p + len;
+		S.logbase = logbase.p; S.log = (longlong2*)logbuf.p;
 	}
 	rb3b_toc(T_PREP);
 	CK(cudaMemsetAsync(ctr.p, 0, 8 * 8, rb3b_stream));
 	CK(cudaMemsetAsync(ka.p, 0xff, len * 8, rb3b_stream));
 	DevIndex dA = rb3b_dev_view(A);
+	/* the batch LF table is hit once per row at random: keep it resident in L2 while the index cells stream through */
+	const bool pin = rb3b_get_param("pin_lfb", 0) != 0; /* measured slower on B200 (set-aside shrinks the L2 left for cells, ka and the log): off by default */
+	if (pin) rb3b_l2_pin(lfb.p, (size_t)len * 8);
 	/* bitmap walks are single threads: small CTAs spread the few thousand walks over all SMs */
 	const int wg = bm ? 1 : 8, wtpb = bm ? 32 : TPB;
 	int64_t want = (S.n_seg * wg + wtpb - 1) / wtpb, cap = (int64_t)n_sm() * (bm ? 32 : 8);
@@ -598,6 +599,7 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 		rb3b_tflush();
 		cur ^= 1; ++rounds;
 	}
+	if (pin) rb3b_l2_pin(0, 0);
 	unsigned long long sums[3];
 	CK(cudaMemsetAsync(ctr.p + 4, 0, 24, rb3b_stream));
 	k_seg_check<<<nblk(S.n_seg, TPB), TPB, 0, rb3b_stream>>>(S, (unsigned long long*)(ctr.p + 4)); CKK();
