@@ -324,6 +324,81 @@ __global__ void __launch_bounds__(EMIT_TPB) k_emit_bm(Src src, EmitOut O, int64_
 	cell[0] = make_uint4(c[0] | c[1] << 16, c[2] | c[3] << 16, c[4] | c[5] << 16, 0u);
 }
 
+
+/* Bitmap -> bitmap merge without decoding runs.  The A symbols of an output cell are 128 consecutive bits (per plane)
+ * of at most two A cells: X = (A planes >> offset).  With k batch rows landing at output offsets b_0 < ... < b_{k-1}
+ * the output is, per plane, the OR over t = 0..k of (X << t) restricted to the gap between b_{t-1} and b_t, plus the
+ * one-hot bits of the inserted rows: per gap a 128-bit mask-and-or and a shift by one for six planes. */
+static __global__ void __launch_bounds__(EMIT_TPB) k_emit_bm_fast(const uint4 *__restrict__ A, int64_t nA, int64_t nA_cells, EmitOut O,
+                                                                   const int64_t *__restrict__ ka, const uint8_t *__restrict__ bwt, const int64_t *__restrict__ ilo)
+{
+	const int64_t j = (int64_t)blockIdx.x * EMIT_TPB + threadIdx.x;
+	if (j >= O.n_cells) return;
+	const int64_t P0 = j << RB3B_BM_SHIFT;
+	const int n_out = (int)(O.n_out - P0 < 128 ? O.n_out - P0 : 128);
+	const int64_t i0 = ilo[j], i1 = ilo[j + 1], a0 = P0 - i0;
+	const int64_t jA = a0 >> RB3B_BM_SHIFT;
+	const uint32_t q = ((uint32_t)a0 & 127u) >> 5, r = (uint32_t)a0 & 31u;
+	uint32_t X[RB3B_ASIZE][4], OUT[RB3B_ASIZE][4];
+#pragma unroll
+	for (int s = 0; s < RB3B_ASIZE; ++s) {
+		uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
+		if (jA < nA_cells) c0 = __ldg(A + jA * 8 + rb3b_bm_plane_quad(s));
+		if (jA + 1 < nA_cells) c1 = __ldg(A + (jA + 1) * 8 + rb3b_bm_plane_quad(s));
+		uint32_t w[9] = { c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, 0u };
+		if (q & 1u) {
+#pragma unroll
+			for (int i = 0; i < 8; ++i) w[i] = w[i + 1];
+		}
+		if (q & 2u) {
+#pragma unroll
+			for (int i = 0; i < 7; ++i) w[i] = i + 2 < 9 ? w[i + 2] : 0u;
+		}
+#pragma unroll
+		for (int i = 0; i < 4; ++i) { X[s][i] = __funnelshift_r(w[i], w[i + 1], r); OUT[s][i] = 0; }
+	}
+	int prev = -1;
+	const int k = (int)(i1 - i0);
+	for (int t = 0; t <= k; ++t) {
+		int b = n_out, sym = -1;
+		if (t < k) { b = (int)(ka[i0 + t] + i0 + t - P0); sym = bwt[i0 + t]; }
+		const int lo = prev + 1, hi = b; /* gap [lo, hi) receives A symbols */
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			int l = lo - 32 * i, h = hi - 32 * i;
+			l = l < 0 ? 0 : l; h = h > 32 ? 32 : h;
+			uint32_t m = l < h ? ((h == 32 ? 0xffffffffu : (1u << h) - 1u) & ~((1u << l) - 1u)) : 0u;
+			uint32_t one = (sym >= 0 && (b >> 5) == i) ? 1u << (b & 31) : 0u;
+#pragma unroll
+			for (int s = 0; s < RB3B_ASIZE; ++s) OUT[s][i] |= (X[s][i] & m) | (s == sym ? one : 0u);
+		}
+#pragma unroll
+		for (int s = 0; s < RB3B_ASIZE; ++s) { /* X <<= 1 */
+			X[s][3] = __funnelshift_l(X[s][2], X[s][3], 1);
+			X[s][2] = __funnelshift_l(X[s][1], X[s][2], 1);
+			X[s][1] = __funnelshift_l(X[s][0], X[s][1], 1);
+			X[s][0] <<= 1;
+		}
+		prev = b;
+	}
+	uint4 *cell = O.cells + j * 8;
+	uint32_t c[RB3B_ASIZE];
+#pragma unroll
+	for (int s = 0; s < RB3B_ASIZE; ++s) {
+		c[s] = __popc(OUT[s][0]) + __popc(OUT[s][1]) + __popc(OUT[s][2]) + __popc(OUT[s][3]);
+		cell[rb3b_bm_plane_quad(s)] = make_uint4(OUT[s][0], OUT[s][1], OUT[s][2], OUT[s][3]);
+	}
+	cell[0] = make_uint4(c[0] | c[1] << 16, c[2] | c[3] << 16, c[4] | c[5] << 16, 0u);
+}
+
+template<class Src> static inline bool rb3b_launch_emit_bm_fast(const Src &, const EmitOut &, int64_t, const int64_t *, const uint8_t *, const int64_t *) { return false; }
+static inline bool rb3b_launch_emit_bm_fast(const BmSrc &src, const EmitOut &O, int64_t lenB, const int64_t *d_ka, const uint8_t *d_bwt, const int64_t *d_ilo)
+{
+	if (lenB <= 0 || d_ilo == 0) return false;
+	k_emit_bm_fast<<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(src.R.cells, src.n, (src.n + 127) >> RB3B_BM_SHIFT, O, d_ka, d_bwt, d_ilo);
+	return true;
+}
+
 __device__ __forceinline__ void rb3b_bm_local_counts(const uint4 *cells, int64_t j, int64_t c[RB3B_ASIZE])
 {
 	uint4 q = cells[j * 8];
@@ -382,7 +457,9 @@ static int rb3b_emit_build_bm(rb3b_index_s *x, Src src, int64_t n_src, int64_t l
 	}
 	TRY(rb3b_reserve((void**)&x->cells2, &x->cap_cells2, O.n_cells * 8, sizeof(uint4)));
 	O.cells = x->cells2; O.ovf = 0;
-	k_emit_bm<Src><<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(src, O, lenB, d_ka, d_bwt, lenB > 0 ? ilo.p : 0); CKK();
+	if (!rb3b_launch_emit_bm_fast(src, O, lenB, d_ka, d_bwt, lenB > 0 ? ilo.p : 0))
+		k_emit_bm<Src><<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(src, O, lenB, d_ka, d_bwt, lenB > 0 ? ilo.p : 0);
+	CKK();
 	k_bm_fin_count<<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(O, ctot.p); CKK();
 	TRY(rb3b_scan_excl_i64(ctot.p, cex.p, (O.n_chunks + 1) * RB3B_ASIZE));
 	k_bm_fin_write<<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(O, cex.p); CKK();
