@@ -369,39 +369,39 @@ __global__ void __launch_bounds__(128) k_walk_fix_log(DevIndex A, Segs S, int64_
 	const int lane = threadIdx.x & 31;
 	int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (it >= n_items) return; /* warp-uniform */
-	const int64_t t = wl_seg[it], d = S.d[t], len = S.len[t], base = S.logbase[t];
-	int64_t v = wl_val[it];
-	int ended = 0;
-	LogRow cur, nxt;
-	cur.load(A, S, base + lane, lane < d);
-	for (int64_t i0 = 0; i0 < d && !ended; i0 += 32) {
-		nxt.load(A, S, base + i0 + 32 + lane, i0 + 32 + lane < d);
-		const int cnt = d - i0 < 32 ? (int)(d - i0) : 32;
-		for (int u = 0; u < cnt; ++u) {
-			int64_t nv = v;
-			int e = 0;
-			if (lane == u) {
-				ka[cur.kb] = v;
-				if (cur.c == 0) e = 1;
-				else nv = cur.step(A, v);
+	int64_t t = wl_seg[it], v = wl_val[it];
+	for (;;) { /* a segment that never collapsed hands its exact arrival straight to its successor: same warp, no new launch */
+		const int64_t d = S.d[t], len = S.len[t], base = S.logbase[t];
+		int ended = 0;
+		LogRow cur, nxt;
+		cur.load(A, S, base + lane, lane < d);
+		for (int64_t i0 = 0; i0 < d && !ended; i0 += 32) {
+			nxt.load(A, S, base + i0 + 32 + lane, i0 + 32 + lane < d);
+			const int cnt = d - i0 < 32 ? (int)(d - i0) : 32;
+			for (int u = 0; u < cnt; ++u) {
+				int64_t nv = v;
+				int e = 0;
+				if (lane == u) {
+					ka[cur.kb] = v;
+					if (cur.c == 0) e = 1;
+					else nv = cur.step(A, v);
+				}
+				v = __shfl_sync(0xffffffffu, nv, u);
+				ended = __shfl_sync(0xffffffffu, e, u);
+				if (ended) break;
 			}
-			v = __shfl_sync(0xffffffffu, nv, u);
-			ended = __shfl_sync(0xffffffffu, e, u);
-			if (ended) break;
+			cur = nxt;
 		}
-		cur = nxt;
-	}
-	if (lane == 0) {
-		S.d[t] = 0;
-		int64_t u2 = S.succ[t];
-		if (d == len && u2 >= 0) {
-			S.arr_lo[t] = S.arr_hi[t] = v;
-			if (S.d[u2] > 0) {
-				unsigned long long o = atomicAdd(nx_n, 1ULL);
-				nx_seg[o] = u2; nx_val[o] = v;
-			}
+		const int64_t u2 = S.succ[t];
+		__syncwarp();
+		if (lane == 0) {
+			S.d[t] = 0;
+			if (d == len && u2 >= 0) S.arr_lo[t] = S.arr_hi[t] = v;
 		}
+		if (!(d == len && u2 >= 0 && S.d[u2] > 0)) break; /* u2's only predecessor is t: nobody else touches it */
+		t = u2;
 	}
+	(void)nx_seg; (void)nx_val; (void)nx_n;
 }
 
 /* round >= 2: re-walk the unresolved prefix of each listed segment from its now exact start */
