@@ -191,12 +191,23 @@ __global__ void __launch_bounds__(EMIT_TPB) k_emit(Src src, EmitOut O, int64_t l
 	}
 }
 
-/* ilo[j] = first batch row whose merged position ka[i] + i is >= j << shift (j = 0..n_cells) */
-static __global__ void k_tile_bounds(int64_t n_cells, int shift, int64_t len, const int64_t *__restrict__ ka, int64_t *__restrict__ ilo)
+/* ilo[j] = first batch row whose merged position ka[i] + i is >= j << shift (j = 0..n_cells).  The rows of a batch are
+ * spread almost evenly over the merged sequence, so the search gallops out from an interpolated guess. */
+static __global__ void k_tile_bounds(int64_t n_cells, int shift, int64_t len, int64_t n_out, const int64_t *__restrict__ ka, int64_t *__restrict__ ilo)
 {
 	int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (j > n_cells) return;
-	int64_t key = j << shift, lo = 0, hi = len;
+	const int64_t key = j << shift;
+	int64_t g = (int64_t)((double)key * (double)len / (double)(n_out > 0 ? n_out : 1));
+	g = g < 0 ? 0 : g > len ? len : g;
+	int64_t lo, hi, step = 16; /* invariant: every row < lo is below the key, every row >= hi is not */
+	if (g < len && ka[g] + g < key) {
+		lo = g + 1; hi = len;
+		while (lo + step < len) { if (ka[lo + step - 1] + lo + step - 1 < key) { lo += step; step <<= 1; } else { hi = lo + step - 1; break; } }
+	} else {
+		hi = g; lo = 0;
+		while (hi - step > 0) { if (ka[hi - step] + hi - step < key) { lo = hi - step + 1; break; } else { hi -= step; step <<= 1; } }
+	}
 	while (lo < hi) {
 		int64_t mid = (lo + hi) >> 1;
 		if (ka[mid] + mid < key) lo = mid + 1; else hi = mid;
@@ -228,7 +239,7 @@ static int rb3b_emit_build(rb3b_index_s *x, Src src, int64_t n_src, int64_t lenB
 		TRY(nent.alloc(O.n_cells)); TRY(ctot.alloc((O.n_chunks + 1) * (RB3B_ASIZE + 1))); TRY(cex.alloc((O.n_chunks + 1) * (RB3B_ASIZE + 1)));
 		if (lenB > 0) {
 			TRY(ilo.alloc(O.n_cells + 1));
-			k_tile_bounds<<<(unsigned)((O.n_cells + 1 + 255) / 256), 256, 0, rb3b_stream>>>(O.n_cells, shift, lenB, d_ka, ilo.p); CKK();
+			k_tile_bounds<<<(unsigned)((O.n_cells + 1 + 255) / 256), 256, 0, rb3b_stream>>>(O.n_cells, shift, lenB, n_out, d_ka, ilo.p); CKK();
 		}
 		CK(cudaMemsetAsync(stats.p, 0, 16, rb3b_stream));
 		k_emit<Src, false><<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(src, O, lenB, d_ka, d_bwt, lenB > 0 ? ilo.p : 0, nent.p, ctot.p, 0, stats.p); CKK();
@@ -274,21 +285,41 @@ static int rb3b_emit_build(rb3b_index_s *x, Src src, int64_t n_src, int64_t lenB
 /* One thread per output cell of 128 positions.  The planes are assembled in registers-backed local memory and
  * written once; quad 0 temporarily receives the cell's own six symbol counts (6 x u16), which k_bm_fin_* turn into
  * the absolute header counts with a two-level scan. */
+/* common tail of the bitmap emit kernels: write the planes, the compact per-cell counts and the chunk totals */
+__device__ __forceinline__ void rb3b_bm_finish_cell(const EmitOut &O, int64_t j, bool live, uint32_t (&pl)[RB3B_ASIZE][4], uint4 *__restrict__ lcnt, int64_t *__restrict__ ctot)
+{
+	typedef cub::BlockReduce<uint32_t, EMIT_TPB> Red;
+	__shared__ typename Red::TempStorage tmp[RB3B_ASIZE];
+	uint32_t c[RB3B_ASIZE];
+#pragma unroll
+	for (int a = 0; a < RB3B_ASIZE; ++a) {
+		c[a] = live ? __popc(pl[a][0]) + __popc(pl[a][1]) + __popc(pl[a][2]) + __popc(pl[a][3]) : 0u;
+		if (live) O.cells[j * 8 + rb3b_bm_plane_quad(a)] = make_uint4(pl[a][0], pl[a][1], pl[a][2], pl[a][3]);
+	}
+	if (live) lcnt[j] = make_uint4(c[0] | c[1] << 16, c[2] | c[3] << 16, c[4] | c[5] << 16, 0u);
+#pragma unroll
+	for (int a = 0; a < RB3B_ASIZE; ++a) {
+		uint32_t t = Red(tmp[a]).Sum(c[a]);
+		if (threadIdx.x == 0) ctot[(int64_t)a * (O.n_chunks + 1) + blockIdx.x] = t;
+	}
+	if (blockIdx.x == 0 && threadIdx.x < RB3B_ASIZE) ctot[(int64_t)threadIdx.x * (O.n_chunks + 1) + O.n_chunks] = 0;
+}
+
 template<class Src>
 __global__ void __launch_bounds__(EMIT_TPB) k_emit_bm(Src src, EmitOut O, int64_t lenB, const int64_t *__restrict__ ka, const uint8_t *__restrict__ bwt,
-                                                       const int64_t *__restrict__ ilo)
+                                                       const int64_t *__restrict__ ilo, uint4 *__restrict__ lcnt, int64_t *__restrict__ ctot)
 {
 	const int64_t j = (int64_t)blockIdx.x * EMIT_TPB + threadIdx.x;
-	if (j >= O.n_cells) return;
+	const bool live = j < O.n_cells;
 	uint32_t pl[RB3B_ASIZE][4];
 #pragma unroll
 	for (int a = 0; a < RB3B_ASIZE; ++a)
 #pragma unroll
 		for (int w = 0; w < 4; ++w) pl[a][w] = 0;
-	const int64_t P0 = j << RB3B_BM_SHIFT, P1 = P0 + 128 < O.n_out ? P0 + 128 : O.n_out;
-	int64_t i = ilo ? ilo[j] : 0, iend = ilo ? ilo[j + 1] : 0, P = P0;
+	const int64_t P0 = j << RB3B_BM_SHIFT, P1 = !live ? P0 : P0 + 128 < O.n_out ? P0 + 128 : O.n_out;
+	int64_t i = (ilo && live) ? ilo[j] : 0, iend = (ilo && live) ? ilo[j + 1] : 0, P = P0;
 	int64_t nextB = i < iend ? ka[i] + i : INT64_MAX;
-	if (P0 - i < src.n) src.seek(P0 - i);
+	if (live && P0 - i < src.n) src.seek(P0 - i);
 	while (P < P1) {
 		int sym; uint32_t t;
 		if (nextB == P) {
@@ -314,14 +345,7 @@ __global__ void __launch_bounds__(EMIT_TPB) k_emit_bm(Src src, EmitOut O, int64_
 		}
 		P += t;
 	}
-	uint4 *cell = O.cells + j * 8;
-	uint32_t c[RB3B_ASIZE];
-#pragma unroll
-	for (int a = 0; a < RB3B_ASIZE; ++a) {
-		c[a] = __popc(pl[a][0]) + __popc(pl[a][1]) + __popc(pl[a][2]) + __popc(pl[a][3]);
-		cell[rb3b_bm_plane_quad(a)] = make_uint4(pl[a][0], pl[a][1], pl[a][2], pl[a][3]);
-	}
-	cell[0] = make_uint4(c[0] | c[1] << 16, c[2] | c[3] << 16, c[4] | c[5] << 16, 0u);
+	rb3b_bm_finish_cell(O, j, live, pl, lcnt, ctot);
 }
 
 
@@ -330,21 +354,22 @@ __global__ void __launch_bounds__(EMIT_TPB) k_emit_bm(Src src, EmitOut O, int64_
  * the output is, per plane, the OR over t = 0..k of (X << t) restricted to the gap between b_{t-1} and b_t, plus the
  * one-hot bits of the inserted rows: per gap a 128-bit mask-and-or and a shift by one for six planes. */
 static __global__ void __launch_bounds__(EMIT_TPB) k_emit_bm_fast(const uint4 *__restrict__ A, int64_t nA, int64_t nA_cells, EmitOut O,
-                                                                   const int64_t *__restrict__ ka, const uint8_t *__restrict__ bwt, const int64_t *__restrict__ ilo)
+                                                                   const int64_t *__restrict__ ka, const uint8_t *__restrict__ bwt, const int64_t *__restrict__ ilo,
+                                                                   uint4 *__restrict__ lcnt, int64_t *__restrict__ ctot)
 {
 	const int64_t j = (int64_t)blockIdx.x * EMIT_TPB + threadIdx.x;
-	if (j >= O.n_cells) return;
+	const bool live = j < O.n_cells;
 	const int64_t P0 = j << RB3B_BM_SHIFT;
-	const int n_out = (int)(O.n_out - P0 < 128 ? O.n_out - P0 : 128);
-	const int64_t i0 = ilo[j], i1 = ilo[j + 1], a0 = P0 - i0;
+	const int n_out = !live ? 0 : (int)(O.n_out - P0 < 128 ? O.n_out - P0 : 128);
+	const int64_t i0 = live ? ilo[j] : 0, i1 = live ? ilo[j + 1] : 0, a0 = P0 - i0;
 	const int64_t jA = a0 >> RB3B_BM_SHIFT;
 	const uint32_t q = ((uint32_t)a0 & 127u) >> 5, r = (uint32_t)a0 & 31u;
 	uint32_t X[RB3B_ASIZE][4], OUT[RB3B_ASIZE][4];
 #pragma unroll
 	for (int s = 0; s < RB3B_ASIZE; ++s) {
 		uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
-		if (jA < nA_cells) c0 = __ldg(A + jA * 8 + rb3b_bm_plane_quad(s));
-		if (jA + 1 < nA_cells) c1 = __ldg(A + (jA + 1) * 8 + rb3b_bm_plane_quad(s));
+		if (live && jA < nA_cells) c0 = __ldg(A + jA * 8 + rb3b_bm_plane_quad(s));
+		if (live && jA + 1 < nA_cells) c1 = __ldg(A + (jA + 1) * 8 + rb3b_bm_plane_quad(s));
 		uint32_t w[9] = { c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, 0u };
 		if (q & 1u) {
 #pragma unroll
@@ -359,7 +384,7 @@ static __global__ void __launch_bounds__(EMIT_TPB) k_emit_bm_fast(const uint4 *_
 	}
 	int prev = -1;
 	const int k = (int)(i1 - i0);
-	for (int t = 0; t <= k; ++t) {
+	for (int t = 0; t <= k && live; ++t) {
 		int b = n_out, sym = -1;
 		if (t < k) { b = (int)(ka[i0 + t] + i0 + t - P0); sym = bwt[i0 + t]; }
 		const int lo = prev + 1, hi = b; /* gap [lo, hi) receives A symbols */
@@ -381,53 +406,28 @@ static __global__ void __launch_bounds__(EMIT_TPB) k_emit_bm_fast(const uint4 *_
 		}
 		prev = b;
 	}
-	uint4 *cell = O.cells + j * 8;
-	uint32_t c[RB3B_ASIZE];
-#pragma unroll
-	for (int s = 0; s < RB3B_ASIZE; ++s) {
-		c[s] = __popc(OUT[s][0]) + __popc(OUT[s][1]) + __popc(OUT[s][2]) + __popc(OUT[s][3]);
-		cell[rb3b_bm_plane_quad(s)] = make_uint4(OUT[s][0], OUT[s][1], OUT[s][2], OUT[s][3]);
-	}
-	cell[0] = make_uint4(c[0] | c[1] << 16, c[2] | c[3] << 16, c[4] | c[5] << 16, 0u);
+	rb3b_bm_finish_cell(O, j, live, OUT, lcnt, ctot);
 }
 
-template<class Src> static inline bool rb3b_launch_emit_bm_fast(const Src &, const EmitOut &, int64_t, const int64_t *, const uint8_t *, const int64_t *) { return false; }
-static inline bool rb3b_launch_emit_bm_fast(const BmSrc &src, const EmitOut &O, int64_t lenB, const int64_t *d_ka, const uint8_t *d_bwt, const int64_t *d_ilo)
+template<class Src> static inline bool rb3b_launch_emit_bm_fast(const Src &, const EmitOut &, int64_t, const int64_t *, const uint8_t *, const int64_t *, uint4 *, int64_t *) { return false; }
+static inline bool rb3b_launch_emit_bm_fast(const BmSrc &src, const EmitOut &O, int64_t lenB, const int64_t *d_ka, const uint8_t *d_bwt, const int64_t *d_ilo, uint4 *lcnt, int64_t *ctot)
 {
 	if (lenB <= 0 || d_ilo == 0) return false;
-	k_emit_bm_fast<<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(src.R.cells, src.n, (src.n + 127) >> RB3B_BM_SHIFT, O, d_ka, d_bwt, d_ilo);
+	k_emit_bm_fast<<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(src.R.cells, src.n, (src.n + 127) >> RB3B_BM_SHIFT, O, d_ka, d_bwt, d_ilo, lcnt, ctot);
 	return true;
 }
 
-__device__ __forceinline__ void rb3b_bm_local_counts(const uint4 *cells, int64_t j, int64_t c[RB3B_ASIZE])
-{
-	uint4 q = cells[j * 8];
-	c[0] = q.x & 0xffffu; c[1] = q.x >> 16; c[2] = q.y & 0xffffu; c[3] = q.y >> 16; c[4] = q.z & 0xffffu; c[5] = q.z >> 16;
-}
-
-/* chunk totals of the per-cell counts left in quad 0 by k_emit_bm; layout [6][n_chunks+1] */
-static __global__ void __launch_bounds__(EMIT_TPB) k_bm_fin_count(EmitOut O, int64_t *__restrict__ ctot)
-{
-	typedef cub::BlockReduce<int64_t, EMIT_TPB> Red;
-	__shared__ typename Red::TempStorage tmp[RB3B_ASIZE];
-	const int64_t j = (int64_t)blockIdx.x * EMIT_TPB + threadIdx.x;
-	int64_t c[RB3B_ASIZE] = {0, 0, 0, 0, 0, 0};
-	if (j < O.n_cells) rb3b_bm_local_counts(O.cells, j, c);
-#pragma unroll
-	for (int a = 0; a < RB3B_ASIZE; ++a) {
-		int64_t t = Red(tmp[a]).Sum(c[a]);
-		if (threadIdx.x == 0) ctot[(int64_t)a * (O.n_chunks + 1) + blockIdx.x] = t;
-	}
-	if (blockIdx.x == 0 && threadIdx.x < RB3B_ASIZE) ctot[(int64_t)threadIdx.x * (O.n_chunks + 1) + O.n_chunks] = 0;
-}
-
-static __global__ void __launch_bounds__(EMIT_TPB) k_bm_fin_write(EmitOut O, const int64_t *__restrict__ cex)
+/* absolute header counts = scan of the per-cell counts inside the chunk + the chunk bases */
+static __global__ void __launch_bounds__(EMIT_TPB) k_bm_fin_write(EmitOut O, const uint4 *__restrict__ lcnt, const int64_t *__restrict__ cex)
 {
 	typedef cub::BlockScan<int64_t, EMIT_TPB> Scan;
 	__shared__ typename Scan::TempStorage tmp[RB3B_ASIZE];
 	const int64_t j = (int64_t)blockIdx.x * EMIT_TPB + threadIdx.x;
 	int64_t c[RB3B_ASIZE] = {0, 0, 0, 0, 0, 0};
-	if (j < O.n_cells) rb3b_bm_local_counts(O.cells, j, c);
+	if (j < O.n_cells) {
+		uint4 q = lcnt[j];
+		c[0] = q.x & 0xffffu; c[1] = q.x >> 16; c[2] = q.y & 0xffffu; c[3] = q.y >> 16; c[4] = q.z & 0xffffu; c[5] = q.z >> 16;
+	}
 	uint64_t h[RB3B_ASIZE];
 #pragma unroll
 	for (int a = 0; a < RB3B_ASIZE; ++a) {
@@ -446,23 +446,23 @@ static int rb3b_emit_build_bm(rb3b_index_s *x, Src src, int64_t n_src, int64_t l
 {
 	const int64_t n_out = n_src + lenB;
 	DBuf<int64_t> ilo, ctot, cex;
+	DBuf<uint4> lcnt;
 	EmitOut O;
 	O.shift = RB3B_BM_SHIFT; O.n_out = n_out;
 	O.n_cells = (n_out + 127) >> RB3B_BM_SHIFT;
 	O.n_chunks = (O.n_cells + EMIT_TPB - 1) / EMIT_TPB;
-	TRY(ctot.alloc((O.n_chunks + 1) * RB3B_ASIZE)); TRY(cex.alloc((O.n_chunks + 1) * RB3B_ASIZE));
+	TRY(ctot.alloc((O.n_chunks + 1) * RB3B_ASIZE)); TRY(cex.alloc((O.n_chunks + 1) * RB3B_ASIZE)); TRY(lcnt.alloc(O.n_cells));
 	if (lenB > 0) {
 		TRY(ilo.alloc(O.n_cells + 1));
-		k_tile_bounds<<<(unsigned)((O.n_cells + 1 + 255) / 256), 256, 0, rb3b_stream>>>(O.n_cells, O.shift, lenB, d_ka, ilo.p); CKK();
+		k_tile_bounds<<<(unsigned)((O.n_cells + 1 + 255) / 256), 256, 0, rb3b_stream>>>(O.n_cells, O.shift, lenB, n_out, d_ka, ilo.p); CKK();
 	}
 	TRY(rb3b_reserve((void**)&x->cells2, &x->cap_cells2, O.n_cells * 8, sizeof(uint4)));
 	O.cells = x->cells2; O.ovf = 0;
-	if (!rb3b_launch_emit_bm_fast(src, O, lenB, d_ka, d_bwt, lenB > 0 ? ilo.p : 0))
-		k_emit_bm<Src><<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(src, O, lenB, d_ka, d_bwt, lenB > 0 ? ilo.p : 0);
+	if (!rb3b_launch_emit_bm_fast(src, O, lenB, d_ka, d_bwt, lenB > 0 ? ilo.p : 0, lcnt.p, ctot.p))
+		k_emit_bm<Src><<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(src, O, lenB, d_ka, d_bwt, lenB > 0 ? ilo.p : 0, lcnt.p, ctot.p);
 	CKK();
-	k_bm_fin_count<<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(O, ctot.p); CKK();
 	TRY(rb3b_scan_excl_i64(ctot.p, cex.p, (O.n_chunks + 1) * RB3B_ASIZE));
-	k_bm_fin_write<<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(O, cex.p); CKK();
+	k_bm_fin_write<<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(O, lcnt.p, cex.p); CKK();
 	int64_t tot[RB3B_ASIZE], base[RB3B_ASIZE];
 	for (int a = 0; a < RB3B_ASIZE; ++a) {
 		CK(cudaMemcpyAsync(&tot[a], cex.p + a * (O.n_chunks + 1) + O.n_chunks, 8, cudaMemcpyDeviceToHost, rb3b_stream));
