@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--seg-len", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-rank-bench", action="store_true")
     return ap.parse_args()
 
 
@@ -288,6 +289,10 @@ def run_b200(a):
         "index": {"symbols": int(acc_dev[6]), "device_bytes": int(index_bytes), "cells": int(st["n_cells"]), "overflow_cells": int(st["n_ovf_cells"]), "cell_span": 1 << int(st["cell_shift"])},
         "walk": {"segments_per_step": st["n_segments"], "fix_rounds_total": st["fix_rounds_total"]},
     }
+    if rank == 0 and world == 1 and not a.no_rank_bench:
+        del idx, d_bwt
+        torch.cuda.empty_cache()
+        line["rank_kernel"] = rank_kernel_bench(R, capi, torch, stream, peak)
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(a, gs, idx_state_genomes=1 + a.warmup, budget_s=20.0)
     if rank == 0:
@@ -295,6 +300,42 @@ def run_b200(a):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def rank_kernel_bench(R, capi, torch, stream, peak, n_symbols=4_000_000_000, nq=32_000_000):
+    """BASELINE.json's second metric: achieved HBM GB/s of the batched rank kernel on independent random queries over an
+    index far larger than L2 (4 G symbols = 4 GB of bitmap cells), 144 algorithmic bytes per query."""
+    g = torch.Generator(device="cuda").manual_seed(1)
+    n_runs = n_symbols // 16
+    sym = torch.randint(0, 6, (n_runs,), device="cuda", dtype=torch.uint8, generator=g)
+    ln = torch.randint(1, 32, (n_runs,), device="cuda", dtype=torch.int64, generator=g)
+    idx = R.Index()
+    torch.cuda.synchronize()
+    capi.check(capi.lib().rb3b_index_from_runs_device(idx.h, n_runs, sym.data_ptr(), ln.data_ptr()))
+    R.sync()
+    n = len(idx)
+    del sym, ln
+    k = torch.randint(0, n, (nq,), device="cuda", dtype=torch.int64, generator=g)
+    c = torch.randint(0, 6, (nq,), device="cuda", dtype=torch.uint8, generator=g)
+    out = torch.empty(nq, dtype=torch.int64, device="cuda")
+    for _ in range(3):
+        idx.lf_dev(nq, k.data_ptr(), c.data_ptr(), out.data_ptr(), 0)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        idx.lf_dev(nq, k.data_ptr(), c.data_ptr(), out.data_ptr(), 0)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = float(np.median(ts))
+    gbs = nq * 144 / (ms / 1e3) / 1e9
+    res = {"kernel": "k_lf_bm (one thread per query: two 16-B loads + popcount)", "index_symbols": int(n), "index_bytes": idx.nbytes(),
+           "queries": nq, "ms": ms, "gqueries_per_s": nq / ms / 1e6, "bytes_per_query": 144, "achieved": gbs, "unit": "GB/s",
+           "peak": peak, "frac": gbs / peak, "frac_of_nominal_8TBps": gbs / 8000.0}
+    idx.close()
+    return res
 
 
 # --------------------------------------------------------------------------- CPU reference

@@ -1,4 +1,4 @@
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_" -s 2400 -c 400 --csv --log-file gpurun_out/launches_late.csv python bench.py --steps 66 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_" -s 2400 -c 400 --csv --log-file gpurun_out/launches_late.csv python bench.py --steps 66 --warmup 3 --no-cpu-baseline --no-e2e --no-rank-bench > /dev/null 2>&1
 python - <<'PY'
 import csv
 rows=[x for x in csv.reader(open('gpurun_out/launches_late.csv')) if len(x)>5]
