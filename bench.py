@@ -51,7 +51,7 @@ def config_of(a, extra=None):
     c = {"workload": "configs[1]: merge-build of synthetic %.1f Mb bacterial genomes (0.5%% subst + 0.05%% indel from a random earlier genome), one genome = one merge of %d symbols (both strands); %d genomes in total" % (
         a.genome_len / 1e6, 2 * a.genome_len + 2, 1 + a.warmup + a.steps),
         "genome_len": a.genome_len, "genomes": 1 + a.warmup + a.steps, "seed": SEED,
-        "l2": "no explicit flush: every step reads a new 10 MB batch and streams ~170 MB of per-batch LF/interleave arrays (> 126 MB L2); the index itself (tens of MB) is L2-resident by nature at this config"}
+        "l2": "no explicit flush needed: every step touches a new 10 MB batch, ~330 MB of per-batch LF/interleave/log arrays and an index of 40 MB to 1 GB (1 B/symbol), all far above the 126 MB L2"}
     if extra:
         c.update(extra)
     return c
@@ -277,12 +277,12 @@ def run_b200(a):
                                       "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": int(st["kernel_launches"]),
         "clocks": clocks,
-        "roofline": {"kernel": "k_walk_first (segmented LF walk: batched rank over the RLE index + LF_B gather + interleave scatter)",
+        "roofline": {"kernel": "k_walk_first<BmRank> (round 1 of the segmented LF walk: per row one LF_B gather, one or two rank lookups in the bitmap cells, one interleave-position scatter)",
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                      "traffic": traffic, "bytes_per_unit": LF_STEP_BYTES, "units_per_launch": timed_syms / a.steps,
                      "avg_launch_ms": walk_s * 1e3 / a.steps,
-                     "note": "latency-bound dependent chains on an L2-resident index at this config; see profiles/"},
+                     "note": "dependent chains: one DRAM access per row per walk and only n/seg_len walks in flight, so the kernel is bound by DRAM latency x random-sector throughput, not by streaming bandwidth; the rank primitive itself is measured under rank_kernel; see DESIGN.md 5 and profiles/"},
         "phase_ms_per_step": {k[3:]: st[k] / 1e3 / a.steps for k in st if k.startswith("us_")},
         "wall_ms_per_step": wall_dev * 1e3 / a.steps,
         "setup": {"genomes_and_bwt_s": t_setup, "device_bwt_build_s": t_bwt, "bwt_build_bases_per_s": sum(bases) / t_bwt},
