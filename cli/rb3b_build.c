@@ -79,14 +79,23 @@ static int rd_getc(reader_t *r)
 }
 
 static int rd_line(reader_t *r, str_t *out, int append)
-{ /* one line without its terminator; -1 at EOF with nothing read */
-	int c, got = 0;
+{ /* one line without its terminator; -1 at EOF with nothing read.  Works on whole buffer spans (memchr + memcpy). */
+	int got = 0;
 	if (!append) out->l = 0;
-	while ((c = rd_getc(r)) >= 0) {
+	for (;;) {
+		if (r->p >= r->n) {
+			r->n = gzread(r->fp, r->buf, sizeof(r->buf));
+			r->p = 0;
+			if (r->n <= 0) break;
+		}
 		got = 1;
-		if (c == '\n') break;
-		str_reserve(out, out->l + 2);
-		out->s[out->l++] = (char)c;
+		unsigned char *s = r->buf + r->p, *e = (unsigned char*)memchr(s, '\n', r->n - r->p);
+		size_t l = e ? (size_t)(e - s) : (size_t)(r->n - r->p);
+		str_reserve(out, out->l + l + 2);
+		memcpy(out->s + out->l, s, l);
+		out->l += l;
+		r->p += (int)l + (e ? 1 : 0);
+		if (e) break;
 	}
 	if (!got) return -1;
 	if (out->l && out->s[out->l - 1] == '\r') --out->l;
