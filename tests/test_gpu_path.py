@@ -224,6 +224,28 @@ def test_bitmap_to_rle_transition(rb3, oracle, golden):
         rb3.set_param("bitmap_max_symbols", 24000000000)
 
 
+@pytest.mark.parametrize("knob,value", [("fix_log", 0), ("pin_lfb", 1), ("fine_len", 7), ("fix_log_max_bytes", 1000)])
+def test_optional_code_paths(rb3, oracle, golden, knob, value):
+    """The tuning knobs select other kernels (multi-round fix-up without the log, persisting-L2 window, other mark
+    spacing); every one of them must give the reference's interleave array and merged index."""
+    g = golden("merge_dup")
+    defaults = {"fix_log": 1, "pin_lfb": 0, "fine_len": 32, "fix_log_max_bytes": 16 << 30}
+    rb3.set_param(knob, value)
+    rb3.set_param("seg_len", 64)
+    try:
+        idx = rb3.Index.from_plain(g["bwt0"])
+        for b in range(1, int(g["n_batches"])):
+            rb, _ = idx.mg_rank_plain(g["bwt%d" % b])
+            assert np.array_equal(rb, g["rb%d" % b]), (knob, b)
+            idx.merge_plain(g["bwt%d" % b])
+        s0, l0, _ = oracle.fmd_decode(bytes(g["fmd"]))
+        s, l = runs_of(idx, oracle)
+        assert np.array_equal(s, s0) and np.array_equal(l, l0)
+    finally:
+        rb3.set_param(knob, defaults[knob])
+        rb3.set_param("seg_len", 512)
+
+
 def test_build_bwt_golden(rb3, golden):
     for name in MERGE_SETS:
         g = golden(name)
