@@ -358,80 +358,50 @@ struct LogRow {
 	}
 };
 
-/* shared-memory image of one prepared row */
-struct FixRow {
-	int64_t kb, pos0, base;
-	int32_t c, narrow;
-	uint32_t W[4 * LOG_NCELL];
-	uint16_t T[4 * LOG_NCELL];
-};
-
-#define FIX_G 8      /* lanes per segment */
-#define FIX_R 2      /* rows prepared per lane and iteration */
-#define FIX_TPB 64
-
-/* round >= 2 with the fix-up log (bitmap cells): a group of 8 lanes per listed segment.  Every lane fetches two logged
- * rows per iteration (coalesced) together with the cells they may need, one iteration ahead, and publishes the
- * precomputed tables in shared memory; lane 0 of the group then runs the dependent chain over the 16 rows:
- * ~20 instructions and two shared-memory reads per row, no global memory access except for the few rows whose bracket
- * was still wider than the cell window.  Four chains advance per warp instruction.  A segment that never collapsed
- * hands its exact arrival straight to its successor (same group, no new launch). */
-__global__ void __launch_bounds__(FIX_TPB) k_walk_fix_log(DevIndex A, Segs S, int64_t *__restrict__ ka, int64_t n_items,
-                                                           const int64_t *__restrict__ wl_seg, const int64_t *__restrict__ wl_val)
+/* round >= 2 with the fix-up log (bitmap cells): one WARP per listed segment.  Each lane fetches one logged row
+ * (coalesced) and the cells it may need, for the current 32 rows and, ahead of time, for the next 32; then the exact
+ * value is passed from lane to lane: the dependent chain is ~30 instructions per row with no memory access on it
+ * except for the few rows whose bracket was still wider than a cell pair. */
+__global__ void __launch_bounds__(128) k_walk_fix_log(DevIndex A, Segs S, int64_t *__restrict__ ka, int64_t n_items,
+                                                       const int64_t *__restrict__ wl_seg, const int64_t *__restrict__ wl_val,
+                                                       int64_t *__restrict__ nx_seg, int64_t *__restrict__ nx_val, unsigned long long *nx_n)
 {
-	__shared__ FixRow rows[FIX_TPB / FIX_G][FIX_G * FIX_R];
-	const int gl = threadIdx.x & (FIX_G - 1), gi = threadIdx.x / FIX_G, gb = threadIdx.x & 31 & ~(FIX_G - 1);
-	const unsigned gm = ((1u << FIX_G) - 1u) << gb;
-	const int64_t it = ((int64_t)blockIdx.x * FIX_TPB + threadIdx.x) / FIX_G;
-	if (it >= n_items) return; /* group-uniform */
+	const int lane = threadIdx.x & 31;
+	int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (it >= n_items) return; /* warp-uniform */
 	int64_t t = wl_seg[it], v = wl_val[it];
-	FixRow *mine = rows[gi];
-	for (;;) {
+	for (;;) { /* a segment that never collapsed hands its exact arrival straight to its successor: same warp, no new launch */
 		const int64_t d = S.d[t], len = S.len[t], base = S.logbase[t];
-		LogRow nx[FIX_R];
-#pragma unroll
-		for (int r = 0; r < FIX_R; ++r) nx[r].load(A, S, base + r * FIX_G + gl, r * FIX_G + gl < d);
 		int ended = 0;
-		for (int64_t i0 = 0; i0 < d && !ended; i0 += FIX_G * FIX_R) {
-#pragma unroll
-			for (int r = 0; r < FIX_R; ++r) {
-				FixRow &o = mine[r * FIX_G + gl];
-				o.kb = nx[r].kb; o.pos0 = nx[r].pos0; o.base = nx[r].base; o.c = nx[r].c; o.narrow = nx[r].narrow;
-#pragma unroll
-				for (int k = 0; k < 4 * LOG_NCELL; ++k) { o.W[k] = nx[r].W[k]; o.T[k] = (uint16_t)nx[r].T[k]; }
-			}
-#pragma unroll
-			for (int r = 0; r < FIX_R; ++r) {
-				const int64_t i = i0 + FIX_G * FIX_R + r * FIX_G + gl;
-				nx[r].load(A, S, base + i, i < d);
-			}
-			__syncwarp(gm);
-			if (gl == 0) {
-				const int cnt = d - i0 < FIX_G * FIX_R ? (int)(d - i0) : FIX_G * FIX_R;
-				for (int u = 0; u < cnt; ++u) {
-					const FixRow &R = mine[u];
-					ka[R.kb] = v;
-					const int c = R.c;
-					if (c == 0) { ended = 1; break; }
-					if (v >= A.n) v = A.acc[c] + A.tot[c];
-					else if (R.narrow) {
-						const uint32_t off = (uint32_t)(v - R.pos0), w = off >> 5;
-						v = R.base + R.T[w] + __popc(R.W[w] & ((1u << (off & 31u)) - 1u));
-					} else v = A.acc[c] + BmRank::rank(A, v, c);
+		LogRow cur, nxt;
+		cur.load(A, S, base + lane, lane < d);
+		for (int64_t i0 = 0; i0 < d && !ended; i0 += 32) {
+			nxt.load(A, S, base + i0 + 32 + lane, i0 + 32 + lane < d);
+			const int cnt = d - i0 < 32 ? (int)(d - i0) : 32;
+			for (int u = 0; u < cnt; ++u) {
+				int64_t nv = v;
+				int e = 0;
+				if (lane == u) {
+					ka[cur.kb] = v;
+					if (cur.c == 0) e = 1;
+					else nv = cur.step(A, v);
 				}
+				v = __shfl_sync(0xffffffffu, nv, u);
+				ended = __shfl_sync(0xffffffffu, e, u);
+				if (ended) break;
 			}
-			v = __shfl_sync(gm, v, gb);
-			ended = __shfl_sync(gm, ended, gb);
-			__syncwarp(gm); /* the rows are consumed before they are overwritten */
+			cur = nxt;
 		}
 		const int64_t u2 = S.succ[t];
-		if (gl == 0) {
+		__syncwarp();
+		if (lane == 0) {
 			S.d[t] = 0;
 			if (d == len && u2 >= 0) S.arr_lo[t] = S.arr_hi[t] = v;
 		}
 		if (!(d == len && u2 >= 0 && S.d[u2] > 0)) break; /* u2's only predecessor is t: nobody else touches it */
 		t = u2;
 	}
+	(void)nx_seg; (void)nx_val; (void)nx_n;
 }
 
 /* round >= 2: re-walk the unresolved prefix of each listed segment from its now exact start */
@@ -615,7 +585,8 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 		CK(cudaMemsetAsync(ctr.p + 2, 0, 16, rb3b_stream));
 		want = (n_items * wg + wtpb - 1) / wtpb;
 		rb3b_tic(T_WALKFIX);
-		if (bm && S.logbase) k_walk_fix_log<<<nblk(n_items * FIX_G, FIX_TPB), FIX_TPB, 0, rb3b_stream>>>(dA, S, ka.p, n_items, wl_seg[cur], wl_val[cur]);
+		if (bm && S.logbase) k_walk_fix_log<<<nblk(n_items * 32, 128), 128, 0, rb3b_stream>>>(dA, S, ka.p, n_items, wl_seg[cur], wl_val[cur],
+			wl_seg[cur ^ 1], wl_val[cur ^ 1], (unsigned long long*)(ctr.p + 3));
 		else if (bm) k_walk_fix<BmRank><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, S, lfb.p, ka.p, n_items, wl_seg[cur], wl_val[cur], ctr.p + 2,
 			wl_seg[cur ^ 1], wl_val[cur ^ 1], (unsigned long long*)(ctr.p + 3));
 		else k_walk_fix<Grp<8> ><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, S, lfb.p, ka.p, n_items, wl_seg[cur], wl_val[cur], ctr.p + 2,
