@@ -181,7 +181,7 @@ def run_b200(a):
     barrier()
     wall_dev = time.time() - w0
     ms_dev = e0.elapsed_time(e1)
-    st = {k: R.get_stat(k) for k in ["us_prep", "us_walk_first", "us_walk_fix", "us_merge", "us_finalize", "kernel_launches", "n_segments", "fix_rounds", "fix_rounds_total", "n_cells", "n_ovf_cells", "cell_shift"]}
+    st = {k: R.get_stat(k) for k in ["us_prep", "us_walk_first", "us_walk_fix", "us_merge", "us_finalize", "kernel_launches", "n_segments", "fix_rounds", "fix_rounds_total", "n_cells", "n_ovf_cells", "cell_shift", "fix_rows", "fix_wide_rows", "fix_longest_chain"]}
     acc_dev = idx.acc()
     index_bytes = idx.nbytes()
     timed_bases = sum(bases[1 + a.warmup:])
@@ -287,7 +287,7 @@ def run_b200(a):
         "wall_ms_per_step": wall_dev * 1e3 / a.steps,
         "setup": {"genomes_and_bwt_s": t_setup, "device_bwt_build_s": t_bwt, "bwt_build_bases_per_s": sum(bases) / t_bwt},
         "index": {"symbols": int(acc_dev[6]), "device_bytes": int(index_bytes), "cells": int(st["n_cells"]), "overflow_cells": int(st["n_ovf_cells"]), "cell_span": 1 << int(st["cell_shift"])},
-        "walk": {"segments_per_step": st["n_segments"], "fix_rounds_total": st["fix_rounds_total"]},
+        "walk": {"segments_per_step": st["n_segments"], "fix_rounds_total": st["fix_rounds_total"], "last_step_fix_rows": st["fix_rows"], "last_step_fix_wide_rows": st["fix_wide_rows"], "last_step_fix_longest_chain": st["fix_longest_chain"]},
     }
     if rank == 0 and world == 1 and not a.no_rank_bench:
         del idx, d_bwt

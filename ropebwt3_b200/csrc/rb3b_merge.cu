@@ -370,12 +370,15 @@ __global__ void __launch_bounds__(128) k_walk_fix_log(DevIndex A, Segs S, int64_
 	int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (it >= n_items) return; /* warp-uniform */
 	int64_t t = wl_seg[it], v = wl_val[it];
+	unsigned long long n_rows = 0, n_wide = 0; /* statistics only */
 	for (;;) { /* a segment that never collapsed hands its exact arrival straight to its successor: same warp, no new launch */
 		const int64_t d = S.d[t], len = S.len[t], base = S.logbase[t];
 		int ended = 0;
 		LogRow cur, nxt;
 		cur.load(A, S, base + lane, lane < d);
+		n_rows += (unsigned long long)d;
 		for (int64_t i0 = 0; i0 < d && !ended; i0 += 32) {
+			n_wide += __popc(__ballot_sync(0xffffffffu, i0 + lane < d && !cur.narrow));
 			nxt.load(A, S, base + i0 + 32 + lane, i0 + 32 + lane < d);
 			const int cnt = d - i0 < 32 ? (int)(d - i0) : 32;
 			for (int u = 0; u < cnt; ++u) {
@@ -401,7 +404,10 @@ __global__ void __launch_bounds__(128) k_walk_fix_log(DevIndex A, Segs S, int64_
 		if (!(d == len && u2 >= 0 && S.d[u2] > 0)) break; /* u2's only predecessor is t: nobody else touches it */
 		t = u2;
 	}
-	(void)nx_seg; (void)nx_val; (void)nx_n;
+	if (lane == 0) { /* nx_n doubles as a statistics block: [1] rows, [2] rows with a wide bracket, [3] longest chain */
+		atomicAdd(nx_n + 1, n_rows); atomicAdd(nx_n + 2, n_wide); atomicMax(nx_n + 3, n_rows);
+	}
+	(void)nx_seg; (void)nx_val;
 }
 
 /* round >= 2: re-walk the unresolved prefix of each listed segment from its now exact start */
@@ -582,7 +588,7 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	cur = 0;
 	while (n_items > 0) {
 		/* ctr[2] = item cursor, ctr[3] = size of the next list */
-		CK(cudaMemsetAsync(ctr.p + 2, 0, 16, rb3b_stream));
+		CK(cudaMemsetAsync(ctr.p + 2, 0, 40, rb3b_stream));
 		want = (n_items * wg + wtpb - 1) / wtpb;
 		rb3b_tic(T_WALKFIX);
 		if (bm && S.logbase) k_walk_fix_log<<<nblk(n_items * 32, 128), 128, 0, rb3b_stream>>>(dA, S, ka.p, n_items, wl_seg[cur], wl_val[cur],
@@ -594,8 +600,11 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 		CKK();
 		rb3b_toc(T_WALKFIX);
 		fix_rows += n_items;
-		CK(cudaMemcpyAsync(&n_items, ctr.p + 3, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+		int64_t fst[4] = {0, 0, 0, 0};
+		CK(cudaMemcpyAsync(fst, ctr.p + 3, 32, cudaMemcpyDeviceToHost, rb3b_stream));
 		CK(cudaStreamSynchronize(rb3b_stream));
+		n_items = fst[0];
+		if (bm && S.logbase) { rb3b_stat_set("fix_rows", fst[1]); rb3b_stat_set("fix_wide_rows", fst[2]); rb3b_stat_set("fix_longest_chain", fst[3]); }
 		rb3b_tflush();
 		cur ^= 1; ++rounds;
 	}
