@@ -358,15 +358,26 @@ struct LogRow {
 	}
 };
 
+/* shared-memory image of one prepared row */
+struct FixRow {
+	int64_t kb, pos0, base;
+	int32_t cn, pad;               /* symbol | narrow << 3 */
+	uint2 TW[4 * LOG_NCELL];       /* x = word of plane c, y = #c between the window start and that word */
+};
+
 /* round >= 2 with the fix-up log (bitmap cells): one WARP per listed segment.  Each lane fetches one logged row
- * (coalesced) and the cells it may need, for the current 32 rows and, ahead of time, for the next 32; then the exact
- * value is passed from lane to lane: the dependent chain is ~30 instructions per row with no memory access on it
- * except for the few rows whose bracket was still wider than a cell pair. */
+ * (coalesced) and the cells it may need, one iteration (32 rows) ahead, precomputes the row's count/word tables and
+ * publishes them in shared memory; lane 0 then runs the dependent chain over the 32 rows: ~20 instructions and two
+ * shared-memory reads per row, no global memory access except for the few rows whose bracket was still wider than
+ * the cell window.  (Handing the value from lane to lane with shuffles cost 56 warp instructions per row and made
+ * the kernel issue-bound; 8-lane groups had too few rows in flight per memory round trip.) */
 __global__ void __launch_bounds__(128) k_walk_fix_log(DevIndex A, Segs S, int64_t *__restrict__ ka, int64_t n_items,
                                                        const int64_t *__restrict__ wl_seg, const int64_t *__restrict__ wl_val,
                                                        int64_t *__restrict__ nx_seg, int64_t *__restrict__ nx_val, unsigned long long *nx_n)
 {
+	__shared__ FixRow rows[4][32]; /* one prepared row per lane, four warps per block */
 	const int lane = threadIdx.x & 31;
+	FixRow *mine = rows[threadIdx.x >> 5];
 	int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (it >= n_items) return; /* warp-uniform */
 	int64_t t = wl_seg[it], v = wl_val[it];
@@ -374,29 +385,44 @@ __global__ void __launch_bounds__(128) k_walk_fix_log(DevIndex A, Segs S, int64_
 	for (;;) { /* a segment that never collapsed hands its exact arrival straight to its successor: same warp, no new launch */
 		const int64_t d = S.d[t], len = S.len[t], base = S.logbase[t];
 		int ended = 0;
-		LogRow cur, nxt;
-		cur.load(A, S, base + lane, lane < d);
+		LogRow nxt;
+		nxt.load(A, S, base + lane, lane < d);
 		n_rows += (unsigned long long)d;
 		for (int64_t i0 = 0; i0 < d && !ended; i0 += 32) {
-			n_wide += __popc(__ballot_sync(0xffffffffu, i0 + lane < d && !cur.narrow));
-			nxt.load(A, S, base + i0 + 32 + lane, i0 + 32 + lane < d);
-			const int cnt = d - i0 < 32 ? (int)(d - i0) : 32;
-			for (int u = 0; u < cnt; ++u) {
-				int64_t nv = v;
-				int e = 0;
-				if (lane == u) {
-					ka[cur.kb] = v;
-					if (cur.c == 0) e = 1;
-					else nv = cur.step(A, v);
-				}
-				v = __shfl_sync(0xffffffffu, nv, u);
-				ended = __shfl_sync(0xffffffffu, e, u);
-				if (ended) break;
+			n_wide += __popc(__ballot_sync(0xffffffffu, i0 + lane < d && !nxt.narrow));
+			{ /* publish this lane's row, then start fetching the row it will hold in the next iteration */
+				FixRow &o = mine[lane];
+				o.kb = nxt.kb; o.pos0 = nxt.pos0; o.base = nxt.base; o.cn = nxt.c | (nxt.narrow ? 8 : 0);
+#pragma unroll
+				for (int k = 0; k < 4 * LOG_NCELL; ++k) o.TW[k] = make_uint2(nxt.W[k], nxt.T[k]);
 			}
-			cur = nxt;
+			nxt.load(A, S, base + i0 + 32 + lane, i0 + 32 + lane < d);
+			__syncwarp();
+			if (lane == 0) { /* the dependent chain; the fields of the next row are fetched while this row is computed */
+				const int cnt = d - i0 < 32 ? (int)(d - i0) : 32;
+				int64_t kb = mine[0].kb, p0 = mine[0].pos0, bs = mine[0].base;
+				int cn = mine[0].cn;
+				for (int u = 0; u < cnt; ++u) {
+					const int un = u + 1 < 32 ? u + 1 : 31;
+					const int64_t kb2 = mine[un].kb, p02 = mine[un].pos0, bs2 = mine[un].base;
+					const int cn2 = mine[un].cn;
+					ka[kb] = v;
+					const int c = cn & 7;
+					if (c == 0) { ended = 1; break; }
+					if (v >= A.n) v = A.acc[c] + A.tot[c];
+					else if (cn & 8) {
+						const uint32_t off = (uint32_t)(v - p0);
+						const uint2 tw = mine[u].TW[off >> 5];
+						v = bs + tw.y + __popc(tw.x & ((1u << (off & 31u)) - 1u));
+					} else v = A.acc[c] + BmRank::rank(A, v, c);
+					kb = kb2; p0 = p02; bs = bs2; cn = cn2;
+				}
+			}
+			v = __shfl_sync(0xffffffffu, v, 0);
+			ended = __shfl_sync(0xffffffffu, ended, 0);
+			__syncwarp(); /* the rows are consumed before they are overwritten */
 		}
 		const int64_t u2 = S.succ[t];
-		__syncwarp();
 		if (lane == 0) {
 			S.d[t] = 0;
 			if (d == len && u2 >= 0) S.arr_lo[t] = S.arr_hi[t] = v;
