@@ -334,16 +334,18 @@ struct LogRow {
 			cq[i] = __ldg(A.cells + ji * 8 + 4 * h); pq[i] = __ldg(A.cells + ji * 8 + 4 * h + 1 + cc);
 		}
 		uint64_t h0 = 0;
+		uint32_t run = 0;
 #pragma unroll
 		for (int i = 0; i < LOG_NCELL; ++i) {
 			uint64_t a0, a1, a2;
 			rb3b_hdr_unpack(cq[i], a0, a1, a2);
 			uint64_t hi = cc == 0 ? a0 : cc == 1 ? a1 : a2;
 			if (i == 0) h0 = hi;
-			uint32_t run = (uint32_t)(hi - h0);
+			const bool real = j + i < A.n_cells; /* past the end of the index: no symbols, the count stays */
+			if (real) run = (uint32_t)(hi - h0);
 			const uint32_t ww[4] = { pq[i].x, pq[i].y, pq[i].z, pq[i].w };
 #pragma unroll
-			for (int k = 0; k < 4; ++k) { T[4 * i + k] = run; W[4 * i + k] = ww[k]; run += __popc(ww[k]); }
+			for (int k = 0; k < 4; ++k) { T[4 * i + k] = run; W[4 * i + k] = real ? ww[k] : 0u; run += real ? __popc(ww[k]) : 0; }
 		}
 		pos0 = j << RB3B_BM_SHIFT;
 		base = A.acc[c] + (int64_t)h0;
@@ -358,26 +360,30 @@ struct LogRow {
 	}
 };
 
-/* shared-memory image of one prepared row */
-struct FixRow {
-	int64_t kb, pos0, base;
-	int32_t cn, pad;               /* symbol | narrow << 3 */
-	uint2 TW[4 * LOG_NCELL];       /* x = word of plane c, y = #c between the window start and that word */
+/* shared-memory image of the 32 rows a warp works on */
+struct FixRows {
+	uint2 TW[32][4 * LOG_NCELL];   /* per row: x = word of plane c, y = #c between the window start and that word */
+	int64_t kb[32], pos0[32], base[32];
+	int32_t K[32];                 /* base - first position of the NEXT row's window: keeps the chain in 32 bits */
+	uint32_t off[32];              /* result: exact value of the row relative to its window */
+	int32_t c[32];
 };
 
 /* round >= 2 with the fix-up log (bitmap cells): one WARP per listed segment.  Each lane fetches one logged row
- * (coalesced) and the cells it may need, one iteration (32 rows) ahead, precomputes the row's count/word tables and
- * publishes them in shared memory; lane 0 then runs the dependent chain over the 32 rows: ~20 instructions and two
- * shared-memory reads per row, no global memory access except for the few rows whose bracket was still wider than
- * the cell window.  (Handing the value from lane to lane with shuffles cost 56 warp instructions per row and made
- * the kernel issue-bound; 8-lane groups had too few rows in flight per memory round trip.) */
+ * (coalesced) and the cells it may need, one iteration (32 rows) ahead, and publishes the row's count/word tables in
+ * shared memory.  Lane 0 then runs the dependent chain.  For a row with a narrow bracket the exact value is carried as a
+ * 32-bit offset into the row's cell window: off' = K + T[off >> 5] + popc(W[off >> 5] below off), one 8-byte
+ * shared-memory read and ~10 instructions per row (the kernel is bound by the instruction count of this serial
+ * chain: handing the value from lane to lane with shuffles cost 56 warp instructions per row).  Afterwards all
+ * lanes write the interleave positions of their rows.  Rows whose bracket was wider than the window (the first ~10 of
+ * a segment) take the general path with a random cell access. */
 __global__ void __launch_bounds__(128) k_walk_fix_log(DevIndex A, Segs S, int64_t *__restrict__ ka, int64_t n_items,
                                                        const int64_t *__restrict__ wl_seg, const int64_t *__restrict__ wl_val,
                                                        int64_t *__restrict__ nx_seg, int64_t *__restrict__ nx_val, unsigned long long *nx_n)
 {
-	__shared__ FixRow rows[4][32]; /* one prepared row per lane, four warps per block */
+	__shared__ FixRows rows[4]; /* four warps per block */
 	const int lane = threadIdx.x & 31;
-	FixRow *mine = rows[threadIdx.x >> 5];
+	FixRows &R = rows[threadIdx.x >> 5];
 	int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (it >= n_items) return; /* warp-uniform */
 	int64_t t = wl_seg[it], v = wl_val[it];
@@ -389,35 +395,48 @@ __global__ void __launch_bounds__(128) k_walk_fix_log(DevIndex A, Segs S, int64_
 		nxt.load(A, S, base + lane, lane < d);
 		n_rows += (unsigned long long)d;
 		for (int64_t i0 = 0; i0 < d && !ended; i0 += 32) {
-			n_wide += __popc(__ballot_sync(0xffffffffu, i0 + lane < d && !nxt.narrow));
-			{ /* publish this lane's row, then start fetching the row it will hold in the next iteration */
-				FixRow &o = mine[lane];
-				o.kb = nxt.kb; o.pos0 = nxt.pos0; o.base = nxt.base; o.cn = nxt.c | (nxt.narrow ? 8 : 0);
+			const int cnt = d - i0 < 32 ? (int)(d - i0) : 32;
+			const bool live = lane < cnt;
+			/* this lane's row: fast = its step can be taken from the tables */
+			const bool fast = live && nxt.narrow && nxt.c != 0;
+			const int64_t my_kb = nxt.kb, my_pos0 = nxt.pos0, my_base = nxt.base;
+			const int64_t next_pos0 = __shfl_down_sync(0xffffffffu, nxt.pos0, 1);
+			const unsigned fastmask = __ballot_sync(0xffffffffu, fast);
+			/* link: the next row of this iteration is fast too, so the value can stay relative */
+			const bool link = fast && lane + 1 < cnt && (fastmask >> (lane + 1) & 1u);
+			const unsigned linkmask = __ballot_sync(0xffffffffu, link);
+			n_wide += __popc(__ballot_sync(0xffffffffu, live && !nxt.narrow));
 #pragma unroll
-				for (int k = 0; k < 4 * LOG_NCELL; ++k) o.TW[k] = make_uint2(nxt.W[k], nxt.T[k]);
-			}
-			nxt.load(A, S, base + i0 + 32 + lane, i0 + 32 + lane < d);
+			for (int k = 0; k < 4 * LOG_NCELL; ++k) R.TW[lane][k] = make_uint2(nxt.W[k], nxt.T[k]);
+			R.kb[lane] = my_kb; R.pos0[lane] = my_pos0; R.base[lane] = my_base; R.c[lane] = nxt.c;
+			R.K[lane] = link ? (int32_t)(my_base - next_pos0) : 0;
+			R.off[lane] = 0xffffffffu;
+			nxt.load(A, S, base + i0 + 32 + lane, i0 + 32 + lane < d); /* fetch the next iteration's row meanwhile */
 			__syncwarp();
-			if (lane == 0) { /* the dependent chain; the fields of the next row are fetched while this row is computed */
-				const int cnt = d - i0 < 32 ? (int)(d - i0) : 32;
-				int64_t kb = mine[0].kb, p0 = mine[0].pos0, bs = mine[0].base;
-				int cn = mine[0].cn;
-				for (int u = 0; u < cnt; ++u) {
-					const int un = u + 1 < 32 ? u + 1 : 31;
-					const int64_t kb2 = mine[un].kb, p02 = mine[un].pos0, bs2 = mine[un].base;
-					const int cn2 = mine[un].cn;
-					ka[kb] = v;
-					const int c = cn & 7;
-					if (c == 0) { ended = 1; break; }
-					if (v >= A.n) v = A.acc[c] + A.tot[c];
-					else if (cn & 8) {
-						const uint32_t off = (uint32_t)(v - p0);
-						const uint2 tw = mine[u].TW[off >> 5];
-						v = bs + tw.y + __popc(tw.x & ((1u << (off & 31u)) - 1u));
-					} else v = A.acc[c] + BmRank::rank(A, v, c);
-					kb = kb2; p0 = p02; bs = bs2; cn = cn2;
+			if (lane == 0) {
+				int u = 0;
+				while (u < cnt) {
+					if (fastmask >> u & 1u) { /* a run of table rows: 32-bit relative chain */
+						uint32_t off = (uint32_t)(v - R.pos0[u]);
+						for (;;) {
+							R.off[u] = off;
+							const uint2 tw = R.TW[u][off >> 5];
+							const uint32_t r = tw.y + __popc(tw.x & ((1u << (off & 31u)) - 1u));
+							if (!(linkmask >> u & 1u)) { v = R.base[u] + r; ++u; break; }
+							off = (uint32_t)(R.K[u] + (int32_t)r);
+							++u;
+						}
+					} else { /* general row */
+						ka[R.kb[u]] = v;
+						const int c = R.c[u];
+						if (c == 0) { ended = 1; break; }
+						v = A.acc[c] + BmRank::rank(A, v, c);
+						++u;
+					}
 				}
 			}
+			__syncwarp();
+			if (R.off[lane] != 0xffffffffu) ka[my_kb] = my_pos0 + R.off[lane]; /* rows resolved through the tables */
 			v = __shfl_sync(0xffffffffu, v, 0);
 			ended = __shfl_sync(0xffffffffu, ended, 0);
 			__syncwarp(); /* the rows are consumed before they are overwritten */
