@@ -41,16 +41,25 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--genome-len", type=int, default=GENOME_LEN)
     ap.add_argument("--seg-len", type=int, default=0)
+    ap.add_argument("--genomes-per-merge", type=int, default=0,
+                    help="genomes per batch (one batch = one partial BWT = one merge); default: the number of GPUs, i.e. weak scaling")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-rank-bench", action="store_true")
     return ap.parse_args()
 
 
+def gpm_of(a):
+    """genomes per merge: 1 on one GPU (the README's one-file-per-genome form); N on N GPUs (weak scaling: the rows each
+    GPU walks per step stay the same)"""
+    return a.genomes_per_merge if a.genomes_per_merge > 0 else max(1, a.gpus)
+
+
 def config_of(a, extra=None):
-    c = {"workload": "configs[1]: merge-build of synthetic %.1f Mb bacterial genomes (0.5%% subst + 0.05%% indel from a random earlier genome), one genome = one merge of %d symbols (both strands); %d genomes in total" % (
-        a.genome_len / 1e6, 2 * a.genome_len + 2, 1 + a.warmup + a.steps),
-        "genome_len": a.genome_len, "genomes": 1 + a.warmup + a.steps, "seed": SEED,
+    g = gpm_of(a)
+    c = {"workload": "configs[1]: merge-build of synthetic %.1f Mb bacterial genomes (0.5%% subst + 0.05%% indel from a random earlier genome), %d genome(s) = one batch = one merge of %d symbols (both strands); %d genomes in total" % (
+        a.genome_len / 1e6, g, g * (2 * a.genome_len + 2), g * (1 + a.warmup + a.steps)),
+        "genome_len": a.genome_len, "genomes": g * (1 + a.warmup + a.steps), "genomes_per_merge": g, "seed": SEED,
         "l2": "no explicit flush needed: every step touches a new 10 MB batch, ~330 MB of per-batch LF/interleave/log arrays and an index of 40 MB to 1 GB (1 B/symbol), all far above the 126 MB L2"}
     if extra:
         c.update(extra)
@@ -99,7 +108,7 @@ class ClockSampler:
 
 def make_genomes(a):
     from ropebwt3_b200 import synth
-    return synth.genomes(1 + a.warmup + a.steps, a.genome_len, seed=SEED, sub=0.005, indel=0.0005)
+    return synth.genomes(gpm_of(a) * (1 + a.warmup + a.steps), a.genome_len, seed=SEED, sub=0.005, indel=0.0005)
 
 
 # --------------------------------------------------------------------------- our arm
@@ -128,11 +137,12 @@ def run_b200(a):
     # ---- synthetic input, partial BWTs built on the device (untimed producer of the path's input)
     t0 = time.time()
     gs = make_genomes(a)
-    n_g = len(gs)
+    G = gpm_of(a)
+    n_g = len(gs) // G          # batches
     d_bwt, h_bwt, lens = [], [], []
     t_bwt = 0.0
-    for g in gs:
-        text = synth.batch_text([g])
+    for b in range(n_g):
+        text = synth.batch_text(gs[b * G:(b + 1) * G])
         d_text = torch.from_numpy(text).cuda()
         out = torch.empty_like(d_text)
         torch.cuda.synchronize()
@@ -145,7 +155,7 @@ def run_b200(a):
         hb.copy_(out)
         h_bwt.append(hb)
         lens.append(len(text))
-    bases = [len(g) for g in gs]
+    bases = [sum(len(g) for g in gs[b * G:(b + 1) * G]) for b in range(n_g)]
     t_setup = time.time() - t0
 
     def barrier():
@@ -270,9 +280,9 @@ def run_b200(a):
         pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
+        "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/int64", "data": "synthetic",
-        "config": config_of(a, {"seg_len": a.seg_len or R.get_stat("seg_len"), "parallelism": "1 GPU" if world == 1 else "index replicated; rank phase of every merge split over %d ranks (chain stretches + halo), NCCL all-reduce(MAX) of the 8 B/row interleave array, merge replicated; %d of %d merges sharded" % (world, n_sharded, a.steps)}),
+        "config": config_of(a, {"seg_len": a.seg_len or R.get_stat("seg_len"), "parallelism": "1 GPU" if world == 1 else "weak scaling: %d genomes per merge on %d GPUs; index replicated; rank phase of every merge split over the ranks (chain stretches + halo), NCCL all-reduce(MAX) of the 8 B/row interleave array, merge replicated; %d of %d merges sharded" % (G, world, n_sharded, a.steps)}),
         "e2e": None if a.no_e2e else {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(np.mean(lens[1 + a.warmup:])), "d2h_bytes_per_step": int(d2h),
                                       "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": int(st["kernel_launches"]),
@@ -356,24 +366,25 @@ def cpu_baseline(a, gs, idx_state_genomes, budget_s):
     cores = os.cpu_count() or 1
     if not ref.available():
         return port_baseline(a, gs, budget_s)
-    n0 = min(idx_state_genomes, 4)
+    G = gpm_of(a)
+    n0 = min(idx_state_genomes * G, 4)
     rope = ref_index_of(gs[:n0], cores)
     frag = min(a.genome_len, 1_000_000)
     done_bases, t_used, n_merge = 0, 0.0, 0
-    for g in gs[n0:]:
-        piece = g[:frag]
-        bwt = ref.build_sais(synth.batch_text([piece]), 2, cores)
+    for b in range(n0, len(gs) - G + 1, G):
+        pieces = [g[:frag] for g in gs[b:b + G]]
+        bwt = ref.build_sais(synth.batch_text(pieces), 2 * G, cores)
         t0 = time.time()
         rope.merge_plain(bwt, cores)
         t_used += time.time() - t0
-        done_bases += len(piece)
+        done_bases += sum(len(x) for x in pieces)
         n_merge += 1
         if t_used > budget_s:
             break
     rope.close()
     return {"value": done_bases / t_used, "unit": UNIT, "cores": cores, "kind": "reference",
-            "sample": "%d merges (rb3_fmi_merge_plain, n_threads=%d) of a %.1f Mb genome prefix (both strands) into the reference's index of the first %d genomes; %.1f s of CPU wall time; only 2 chains per merge exist, so the reference's rank phase cannot use more than 2 threads here" % (
-                n_merge, cores, frag / 1e6, n0, t_used)}
+            "sample": "%d merges (rb3_fmi_merge_plain, n_threads=%d) of %d genome prefix(es) of %.1f Mb each (both strands) into the reference's index of the first %d genomes; %.1f s of CPU wall time; only %d chains per merge exist, so the reference's rank phase cannot use more than %d threads here" % (
+                n_merge, cores, G, frag / 1e6, n0, t_used, 2 * G, 2 * G)}
 
 
 def port_baseline(a, gs, budget_s):
@@ -396,7 +407,10 @@ def run_reference(a):
     from oracle import ref
     from ropebwt3_b200 import synth
     cores = os.cpu_count() or 1
-    gs = make_genomes(a)
+    G = gpm_of(a)
+    # the bounded sample never needs more than a few dozen genomes; the generator is seeded, so these are the first
+    # genomes of the b200 arm's set
+    gs = synth.genomes(min(G * (1 + a.warmup + a.steps), 4 + 8 * G), a.genome_len, seed=SEED, sub=0.005, indel=0.0005)
     if not ref.available():
         b = port_baseline(a, gs, 20.0)
         line = {"impl": "reference", "metric": METRIC, "value": b["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
@@ -413,12 +427,12 @@ def run_reference(a):
     t0 = time.time()
     rope.merge_plain(bwt, cores)
     rate = len(probe) / (time.time() - t0)
-    frag = int(max(20_000, min(a.genome_len, rate * 150.0 / (a.steps + a.warmup))))
+    frag = int(max(20_000, min(a.genome_len, rate * 150.0 / (a.steps + a.warmup) / G)))
     times, nb = [], 0
     for i in range(a.warmup + a.steps):
-        g = rest[(i + 1) % len(rest)]
-        piece = g[:frag]
-        bwt = ref.build_sais(synth.batch_text([piece]), 2, cores)
+        pieces = [rest[(i * G + j + 1) % len(rest)][:frag] for j in range(G)]
+        piece = np.concatenate(pieces)
+        bwt = ref.build_sais(synth.batch_text(pieces), 2 * G, cores)
         t0 = time.time()
         rope.merge_plain(bwt, cores)
         dt = time.time() - t0
@@ -428,11 +442,11 @@ def run_reference(a):
     rope.close()
     tot = sum(times)
     val = nb / tot
-    sample = "each step = rb3_fmi_merge_plain(n_threads=%d) of a %.2f Mb prefix of the next genome (both strands, %d symbols) into the reference's own index (first %d genomes + earlier steps); sized from a 100 kb probe so that %d steps take ~150 s" % (
-        cores, frag / 1e6, 2 * frag + 2, n0, a.steps + a.warmup)
+    sample = "each step = rb3_fmi_merge_plain(n_threads=%d) of %.2f Mb prefixes of the next %d genome(s) (both strands, %d symbols) into the reference's own index (first %d genomes + earlier steps); sized from a 100 kb probe so that %d steps take ~150 s" % (
+        cores, frag / 1e6, G, G * (2 * frag + 2), n0, a.steps + a.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": tot * 1e3 / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8/int64", "data": "synthetic", "config": config_of(a, {"sample_bases_per_step": frag}),
+            "dtype": "u8/int64", "data": "synthetic", "config": config_of(a, {"sample_bases_per_step": frag * G}),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
