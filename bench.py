@@ -191,7 +191,7 @@ def run_b200(a):
     barrier()
     wall_dev = time.time() - w0
     ms_dev = e0.elapsed_time(e1)
-    st = {k: R.get_stat(k) for k in ["us_prep", "us_walk_first", "us_walk_fix", "us_merge", "us_finalize", "kernel_launches", "n_segments", "fix_rounds", "fix_rounds_total", "n_cells", "n_ovf_cells", "cell_shift", "fix_rows", "fix_wide_rows", "fix_longest_chain"]}
+    st = {k: R.get_stat(k) for k in ["us_prep", "us_walk_first", "us_walk_fix", "us_merge", "us_scatter", "kernel_launches", "n_segments", "fix_rounds", "fix_rounds_total", "n_cells", "n_ovf_cells", "cell_shift", "fix_rows", "fix_wide_rows", "fix_longest_chain"]}
     acc_dev = idx.acc()
     index_bytes = idx.nbytes()
     timed_bases = sum(bases[1 + a.warmup:])

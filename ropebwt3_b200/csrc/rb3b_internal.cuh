@@ -91,7 +91,7 @@ void rb3b_stat_set(const char *key, int64_t v);
 void rb3b_stat_add(const char *key, int64_t v);
 extern int64_t rb3b_n_launch;   /* kernels of this library launched so far (CUB internals not counted) */
 /* device-side timing of the main kernels: tic/toc record events on the stream, tflush (after a sync) adds "us_<name>" stats */
-enum { T_PREP, T_WALK1, T_WALKFIX, T_MERGE, T_FINAL, T_BWT, T_COUNT };
+enum { T_PREP, T_WALK1, T_WALKFIX, T_MERGE, T_SCATTER, T_BWT, T_COUNT };
 void rb3b_tic(int id);
 void rb3b_toc(int id);
 void rb3b_tflush(void);

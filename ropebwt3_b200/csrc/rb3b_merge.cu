@@ -8,21 +8,34 @@
  *   phase B  worker_mgins (fm-index.c:237-249) / rope_insert_run (rope.c:114) /
  *            rle_insert_cached (rle.c:10): interleave B into A.
  *
- * The reference walks one dependent LF chain per new sequence.  Here every chain
- * is cut into segments at "marked" rows of B.  A segment that does not start at a
- * sentinel does not know its ka yet, so it starts with the bracket [lo,hi] = SA
- * interval (in A) of the empty string restricted to its first symbol and narrows
- * it by backward search with the symbols it walks over; once lo == hi the value
- * is exact (the walked string no longer occurs in A) and independent of anything
- * to its right.  Rows walked before the collapse stay unresolved and are filled
- * in a later round by re-walking them from the exact value with which the
- * segment to the right arrived at the mark.  Rounds repeat until nothing is
- * unresolved (a batch sequence that is an exact substring of A degenerates to
- * the sequential chain, still correct).
+ * The reference walks one dependent LF chain per new sequence, and every step of
+ * it chases two things at once: LF_B (where is the next row of B) and rank_A
+ * (where does it go in A).  Here the two are separated:
  *
- * Phase B is a streaming merge: because ka[] is non-decreasing, block b of A
- * and the rows with bstart[b] <= ka < bstart[b+1] form an independent tile whose
- * merged runs are counted, prefix-summed and written into a fresh block array.
+ *   1. B only: the chains of LF_B are cut at "fine marks" (the sentinel rows and
+ *      every fine_len-th row), the pieces are walked and LIST-RANKED (Wyllie
+ *      pointer jumping), which gives every piece its offset in WALK ORDER.  A
+ *      second walk of the pieces writes the batch in walk order: wsym[p] = the
+ *      p-th symbol met by the reference's loop (all sequences one after the
+ *      other), wrow[p] = the row it was met at.  This is the text of the batch
+ *      read backwards and its inverse suffix array, recovered from the BWT
+ *      alone; it touches only the batch's own LF table.
+ *   2. A only: walk order is cut into equal SLICES of seg_len positions; one
+ *      walk per slice streams its symbols (sequential, no dependent load) and
+ *      performs the rank chain on A: one random 64-B access per row.  A slice
+ *      that does not start at a sentinel does not know its ka yet, so it starts
+ *      with the bracket [lo,hi] = SA interval (in A) of its first symbol and
+ *      narrows it by backward search with the symbols it walks over; once
+ *      lo == hi the value is exact (the walked string no longer occurs in A)
+ *      and independent of anything before it.  Rows walked before the collapse
+ *      stay unresolved (flagged in kseq[]) and are filled in by the fix-up pass
+ *      from the exact value with which the previous slice arrived.  A batch
+ *      sequence that is an exact substring of A degenerates to the sequential
+ *      chain, still correct.
+ *   3. ka[wrow[p]] = kseq[p]: one scatter back to row order.
+ *
+ * Phase B is a streaming merge: ka[] is non-decreasing, so every output cell is
+ * produced independently from a slice of A and a slice of the batch.
  */
 #include <string.h>
 #include <cub/cub.cuh>
@@ -32,6 +45,8 @@
 #define TPB 256
 #define PREP_PER_THREAD 16
 #define PREP_TILE (TPB * PREP_PER_THREAD)
+
+int64_t rb3b_get_param(const char *key, int64_t dflt); /* rb3b_runtime.cu */
 
 static inline unsigned nblk(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
@@ -44,12 +59,11 @@ static int n_sm(void)
 
 /* ------------------------------------------------------------------ */
 /* LF mapping of the batch (fm-index.c:207-216)                         */
-/* lfb[i] = LF_B(i) << 5 | coarse mark << 4 | fine mark << 3 | B[i]     */
+/* lf[i] = LF_B(i) << 3 | B[i]; 32-bit entries while len < 2^29         */
 /* ------------------------------------------------------------------ */
 
-#define LFB_SHIFT 5
-#define LFB_FINE 8u
-#define LFB_COARSE 16u
+#define LF_SHIFT 3
+#define LF32_MAX_LEN (1LL << 29)
 
 __global__ void __launch_bounds__(TPB) k_prep_count(int64_t len, const uint8_t *__restrict__ bwt, int64_t nt, int64_t *__restrict__ tcnt, int *__restrict__ bad)
 {
@@ -80,8 +94,9 @@ __global__ void __launch_bounds__(TPB) k_prep_count(int64_t len, const uint8_t *
 
 struct Acc7 { int64_t v[RB3B_ASIZE + 1]; };
 
+template<typename LfT>
 __global__ void __launch_bounds__(TPB) k_prep_lf(int64_t len, const uint8_t *__restrict__ bwt, int64_t nt, const int64_t *__restrict__ tex,
-                                                  Acc7 accB, int64_t fine_len, uint64_t *__restrict__ lfb)
+                                                  Acc7 accB, LfT *__restrict__ lf)
 {
 	typedef cub::BlockScan<uint32_t, TPB> Scan;
 	__shared__ typename Scan::TempStorage tmp[3];
@@ -104,226 +119,232 @@ __global__ void __launch_bounds__(TPB) k_prep_lf(int64_t len, const uint8_t *__r
 		int64_t i = i0 + j;
 		if (i >= len) break;
 		int a = s[j];
-		int64_t lf = 0;
+		int64_t v = 0;
 #pragma unroll
-		for (int b = 0; b < RB3B_ASIZE; ++b) if (a == b) lf = base[b]++;
-		uint64_t mark = (i < accB.v[1] || i % fine_len == 0) ? LFB_FINE : 0u;
-		lfb[i] = (uint64_t)lf << LFB_SHIFT | mark | (uint64_t)a;
+		for (int b = 0; b < RB3B_ASIZE; ++b) if (a == b) v = base[b]++;
+		lf[i] = (LfT)((uint64_t)v << LF_SHIFT | (uint64_t)a);
 	}
 }
 
 /* ------------------------------------------------------------------ */
-/* balanced segmentation of the chains                                  */
+/* the batch in walk order                                              */
 /* ------------------------------------------------------------------ */
 
-/* Fine marks: the sentinel rows (fine node = row) and every fine_len-th row.  They cut the chains into short
- * pieces of random length; walking them (LF_B only, no rank) and list-ranking the pieces gives every fine
- * mark its distance to the start of its sequence, from which evenly spaced coarse marks are chosen. */
+/* Fine marks: the sentinel rows (fine node = row) and every fine_len-th row (fine_len a power of two).  They cut the
+ * chains into short pieces of random length. */
 struct Fine {
-	int64_t n_fine, n_seq, fine_len, m0;
-	__host__ __device__ int64_t row(int64_t f) const { return f < n_seq ? f : (m0 + (f - n_seq)) * fine_len; }
-	__host__ __device__ int64_t of_row(int64_t r) const { return r < n_seq ? r : n_seq + (r / fine_len - m0); }
+	int64_t n_fine, n_seq, m0;
+	int fshift;
+	__host__ __device__ int64_t row(int64_t f) const { return f < n_seq ? f : (m0 + (f - n_seq)) << fshift; }
+	__host__ __device__ int64_t of_row(int64_t r) const { return r < n_seq ? r : n_seq + ((r >> fshift) - m0); }
+	__host__ __device__ bool is_mark(int64_t r) const { return r < n_seq || (r & ((1LL << fshift) - 1)) == 0; }
 };
 
-__global__ void k_fine_walk(Fine F, const uint64_t *__restrict__ lfb, int64_t *__restrict__ succ, int64_t *__restrict__ dist)
+/* list-ranking node of a fine mark: x = #rows from the mark to the end of what has been linked so far,
+ * y = next mark (low 32 bits, -1 = none) | last mark of the chain seen so far (high 32 bits) */
+typedef longlong2 FNode;
+__device__ __forceinline__ FNode fnode(int64_t dist, int32_t succ, int32_t term) { return make_longlong2(dist, (int64_t)((uint64_t)(uint32_t)succ | (uint64_t)(uint32_t)term << 32)); }
+__device__ __forceinline__ int32_t fnode_succ(const FNode &n) { return (int32_t)(uint32_t)n.y; }
+__device__ __forceinline__ int32_t fnode_term(const FNode &n) { return (int32_t)(uint32_t)((uint64_t)n.y >> 32); }
+
+/* walk every piece once (LF_B only, no rank): its length and the piece that follows it */
+template<typename LfT>
+__global__ void k_fine_walk(Fine F, const LfT *__restrict__ lf, FNode *__restrict__ node)
 {
 	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (f >= F.n_fine) return;
 	int64_t kb = F.row(f), n = 0, nx = -1;
-	uint64_t x = __ldg(lfb + kb);
 	for (;;) {
+		const uint64_t x = __ldg(lf + kb);
 		++n;
-		if ((x & 7) == 0) break;
-		kb = (int64_t)(x >> LFB_SHIFT);
-		x = __ldg(lfb + kb);
-		if (x & LFB_FINE) { nx = F.of_row(kb); break; }
+		if ((x & 7) == 0) break; /* first symbol of the sequence: the chain ends here, fm-index.c:170 */
+		kb = (int64_t)(x >> LF_SHIFT);
+		if (F.is_mark(kb)) { nx = F.of_row(kb); break; }
 	}
-	succ[f] = nx; dist[f] = n;
+	node[f] = fnode(n, (int32_t)nx, (int32_t)f);
 }
 
-/* Wyllie pointer jumping: after ceil(log2 n) rounds dist[f] = #rows from fine mark f to the start of its sequence */
-__global__ void k_list_rank(int64_t n, const int64_t *__restrict__ succ_in, const int64_t *__restrict__ dist_in, const int64_t *__restrict__ term_in,
-                            int64_t *__restrict__ succ_out, int64_t *__restrict__ dist_out, int64_t *__restrict__ term_out)
+/* Wyllie pointer jumping: after ceil(log2 n) rounds x = #rows from fine mark f to the start of its sequence.  One 16-byte
+ * gather per mark and round. */
+__global__ void k_list_rank(int64_t n, const FNode *__restrict__ in, FNode *__restrict__ out)
 {
 	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (f >= n) return;
-	int64_t s = succ_in[f], d = dist_in[f], t = term_in ? term_in[f] : f; /* t: last fine mark of f's chain seen so far */
-	if (s >= 0) { d += dist_in[s]; t = term_in ? term_in[s] : s; s = succ_in[s]; }
-	succ_out[f] = s; dist_out[f] = d; term_out[f] = t;
+	FNode a = in[f];
+	const int32_t s = fnode_succ(a);
+	if (s >= 0) {
+		const FNode b = in[s];
+		a = fnode(a.x + b.x, fnode_succ(b), fnode_term(b));
+	}
+	out[f] = a;
 }
 
-/* the sentinel fine mark p starts a chain: record the chain's length at its terminal mark */
-__global__ void k_chain_len(int64_t n_seq, const int64_t *__restrict__ to_end, const int64_t *__restrict__ term, int64_t *__restrict__ chain_len)
+/* the sentinel fine mark p starts chain p: its length, and which chain the terminal mark belongs to */
+__global__ void k_chain_len(int64_t n_seq, const FNode *__restrict__ node, int64_t *__restrict__ chain_len, int64_t *__restrict__ chain_of)
 {
 	int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (p < n_seq) chain_len[term[p]] = to_end[p];
+	if (p < n_seq) { const FNode a = node[p]; chain_len[p] = a.x; chain_of[fnode_term(a)] = p; }
 }
 
-/* Which segments does device `part` of `n_parts` walk?  Long chains are cut into n_parts contiguous stretches (by the
- * distance walked from the sentinel); a part also walks the `halo` rows before its stretch speculatively so that its
- * first segment receives an exact value without any exchange.  Short chains go to one part as a whole.
- * role: 0 not mine, 1 mine (counts for completeness), 2 halo (walked, result not required). */
-__global__ void k_seg_role(Fine F, const int64_t *__restrict__ flag, const int64_t *__restrict__ sid, const int64_t *__restrict__ to_end,
-                           const int64_t *__restrict__ term, const int64_t *__restrict__ chain_len, int part, int n_parts, int64_t halo, int64_t min_stretch,
-                           uint8_t *__restrict__ role)
-{
-	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (f >= F.n_fine || !flag[f]) return;
-	int r = 1;
-	if (n_parts > 1) {
-		int64_t L = chain_len[term[f]], ds = L - to_end[f]; /* rows walked from the sentinel before this segment */
-		if (L <= 0 || ds < 0) r = 1; /* not a valid BWT: let the completeness check report it */
-		else if (L < min_stretch * n_parts) r = (int)(term[f] % n_parts) == part;
-		else {
-			int64_t q = ds * n_parts / L;
-			if (q >= n_parts) q = n_parts - 1;
-			if (q == part) r = 1;
-			else {
-				int64_t b = ((int64_t)part * L + n_parts - 1) / n_parts; /* first ds of my stretch */
-				r = (part > 0 && ds < b && ds + halo >= b) ? 2 : 0;
-			}
-		}
-	}
-	role[sid[f]] = (uint8_t)r;
-}
-
-/* a fine mark becomes a coarse mark when the walk crosses a multiple of seg_len on the way to it */
-__global__ void k_coarse_flag(Fine F, int64_t seg_len, const int64_t *__restrict__ succ, const int64_t *__restrict__ piece, const int64_t *__restrict__ to_end, int64_t *__restrict__ flag)
-{
-	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (f >= F.n_fine) return;
-	if (f < F.n_seq) flag[f] = 1;
-	int64_t s = succ[f];
-	if (s >= 0) {
-		int64_t r = to_end[f], rs = r - piece[f];
-		if (r / seg_len != rs / seg_len) flag[s] = 1;
-	}
-}
-
-__global__ void k_coarse_fill(Fine F, const int64_t *__restrict__ flag, const int64_t *__restrict__ sid, int64_t *__restrict__ seg_row, int32_t *__restrict__ cmap, uint64_t *__restrict__ lfb)
-{
-	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (f >= F.n_fine) return;
-	if (flag[f]) {
-		int64_t r = F.row(f);
-		seg_row[sid[f]] = r;
-		cmap[f] = (int32_t)sid[f];
-		lfb[r] |= LFB_COARSE;
-	} else cmap[f] = -1;
-}
-
-/* length of every segment = rows between its coarse mark and the next one (or the start of the sequence) */
-__global__ void k_seg_len(Fine F, const int64_t *__restrict__ flag, const int64_t *__restrict__ sid, const int64_t *__restrict__ succ, const int64_t *__restrict__ piece, int64_t *__restrict__ seglen)
-{
-	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (f >= F.n_fine || !flag[f]) return;
-	int64_t n = 0, g = f;
-	do { n += piece[g]; g = succ[g]; } while (g >= 0 && !flag[g]);
-	seglen[sid[f]] = n;
-}
-
-/* ------------------------------------------------------------------ */
-/* segmented LF walk                                                    */
-/* ------------------------------------------------------------------ */
-
-struct Segs {
-	int64_t n_seg, n_seq;
-	const int64_t *row;   /* first row of the segment (a coarse mark) */
-	const int32_t *cmap;  /* fine node -> segment, -1 if the fine mark is not a coarse mark */
-	int64_t *d;       /* #rows at the start of the segment that are still unresolved */
-	int64_t *len;     /* #rows of the segment */
-	int64_t *succ;    /* segment entered after the last row, or -1 at the start of a sequence */
-	int64_t *arr_lo, *arr_hi; /* bracket with which the walk arrived at succ's first row */
-	/* fix-up log (bitmap cells): while a walk carries a bracket it records, in walk order, the row, the bracket's low
-	 * end, the row's symbol and whether the bracket is at most 128 wide.  The later rounds then stream this log
-	 * instead of chasing LF_B, and for narrow brackets the two cells that can hold the exact position are known in
-	 * advance, so their loads no longer sit on the dependent chain. */
-	const uint8_t *role;    /* 0: another device walks this segment, 1: mine, 2: halo */
-	const int64_t *logbase; /* per segment: first log slot; NULL = no log */
-	longlong2 *log;         /* x = row, y = low end | symbol << 42 | narrow flag */
+/* second walk of the pieces: write the batch in walk order.  Chain p occupies positions [chain_base[p], +chain_len[p]);
+ * the piece of fine mark f starts node[f].x positions before the end of its chain.  Every thread writes one contiguous
+ * stretch; it collects 8 symbols / 16 bytes of rows in registers and stores them as one aligned word (the unaligned
+ * head and tail go out element by element: neighbouring pieces own the rest of those words). */
+template<typename RowT> struct RowVec;
+template<> struct RowVec<uint32_t> {
+	static const int N = 4;
+	uint32_t r[4];
+	__device__ __forceinline__ void push(uint32_t v) { r[0] = r[1]; r[1] = r[2]; r[2] = r[3]; r[3] = v; }
+	__device__ __forceinline__ void store(uint32_t *dst) const { *(uint4*)dst = make_uint4(r[0], r[1], r[2], r[3]); }
+	__device__ __forceinline__ uint32_t last(int k) const { return k == 0 ? r[3] : k == 1 ? r[2] : k == 2 ? r[1] : r[0]; } /* k-th newest */
+};
+template<> struct RowVec<int64_t> {
+	static const int N = 2;
+	int64_t r[2];
+	__device__ __forceinline__ void push(int64_t v) { r[0] = r[1]; r[1] = v; }
+	__device__ __forceinline__ void store(int64_t *dst) const { *(longlong2*)dst = make_longlong2(r[0], r[1]); }
+	__device__ __forceinline__ int64_t last(int k) const { return k == 0 ? r[1] : r[0]; }
 };
 
-#define LOG_C_SHIFT 42
-#define LOG_NARROW (1LL << 45)
+template<typename LfT, typename RowT>
+__global__ void k_write_walk(Fine F, int64_t len, const LfT *__restrict__ lf, const FNode *__restrict__ node,
+                             const int64_t *__restrict__ chain_of, const int64_t *__restrict__ chain_base, const int64_t *__restrict__ chain_len,
+                             RowT *__restrict__ wrow, uint8_t *__restrict__ wsym)
+{
+	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (f >= F.n_fine) return;
+	const FNode me = node[f];
+	const int64_t p = chain_of[fnode_term(me)];
+	if (p < 0) return; /* not on a chain that starts at a sentinel: not a valid BWT, reported by the caller */
+	int64_t pos = chain_base[p] + chain_len[p] - me.x, kb = F.row(f);
+	if (pos < 0 || pos + me.x > len) return; /* cannot happen for a valid BWT */
+	uint64_t sw = 0;
+	int ns = 0, nr = 0; /* symbols / rows collected */
+	RowVec<RowT> rv;
+	rv.r[0] = rv.r[1] = 0; if (RowVec<RowT>::N == 4) { rv.r[RowVec<RowT>::N - 2] = 0; rv.r[RowVec<RowT>::N - 1] = 0; }
+	for (;;) {
+		const uint64_t x = __ldg(lf + kb);
+		const uint64_t c = x & 7;
+		if (ns == 0 && (pos & 7) != 0) wsym[pos] = (uint8_t)c; /* unaligned head */
+		else {
+			sw = sw >> 8 | c << 56;
+			if (++ns == 8) { *(uint64_t*)(wsym + pos - 7) = sw; ns = 0; }
+		}
+		if (nr == 0 && (pos & (RowVec<RowT>::N - 1)) != 0) wrow[pos] = (RowT)kb;
+		else {
+			rv.push((RowT)kb);
+			if (++nr == RowVec<RowT>::N) { rv.store(wrow + pos - (RowVec<RowT>::N - 1)); nr = 0; }
+		}
+		++pos;
+		if (c == 0) break;
+		kb = (int64_t)(x >> LF_SHIFT);
+		if (F.is_mark(kb)) break;
+	}
+	/* tails: the ns newest symbols are the top bytes of sw, the nr newest rows the last entries of rv */
+	for (int k = 0; k < ns; ++k) wsym[pos - 1 - k] = (uint8_t)(sw >> (56 - 8 * k));
+	for (int k = 0; k < nr; ++k) wrow[pos - 1 - k] = rv.last(k);
+}
+
+/* ------------------------------------------------------------------ */
+/* sliced LF walk over A                                                */
+/* ------------------------------------------------------------------ */
+
+struct Slices {
+	int64_t n_seg, len, seg_len;  /* slice s = walk-order positions [s * seg_len, min(len, (s + 1) * seg_len)); seg_len % 8 == 0 */
+	int64_t own_lo, own_hi;       /* slices this device is responsible for */
+	int64_t walk_lo;              /* first slice this device walks (own_lo minus the halo) */
+	int64_t *d;                   /* #rows at the start of the slice that are still unresolved */
+	int64_t *arr_lo, *arr_hi;     /* bracket with which the walk arrived at the first row of the next slice */
+	__host__ __device__ int64_t slice_len(int64_t s) const { int64_t r = len - s * seg_len; return r < seg_len ? r : seg_len; }
+};
+
+/* kseq[p]: interleave position of walk-order position p, or, while unresolved, the low end of its bracket plus flags */
+#define KS_UNRES  (1LL << 62)
+#define KS_NARROW (1LL << 61)
 #define LOG_NCELL 3              /* a "narrow" bracket spans at most LOG_NCELL consecutive cells */
 #define LOG_WIDTH ((LOG_NCELL - 1) * 128)
 
 /* The walk kernels are written for a "ranker" WG: Grp<8> (RLE cells, 8 lanes per walk) or BmRank (bitmap cells,
  * one thread per walk). */
 
-/* round 1: every segment walks from its mark to the next mark */
+/* round 1: every slice is walked from its first position to its last */
 template<class WG>
-__global__ void __launch_bounds__(TPB) k_walk_first(DevIndex A, Acc7 accB, Segs S, Fine F, const uint64_t *__restrict__ lfb, int64_t *__restrict__ ka, int64_t *next_seg)
+__global__ void __launch_bounds__(TPB) k_walk_first(DevIndex A, Slices S, const uint8_t *__restrict__ wsym, int64_t *__restrict__ kseq, int64_t *next_seg)
 {
 	const int gl = WG::lane(), gbase = WG::base();
 	const unsigned gmask = WG::mask();
 	for (;;) {
 		int64_t s = 0;
-		if (gl == 0) s = (int64_t)atomicAdd((unsigned long long*)next_seg, 1ULL);
+		if (gl == 0) s = S.walk_lo + (int64_t)atomicAdd((unsigned long long*)next_seg, 1ULL);
 		s = __shfl_sync(gmask, s, gbase);
-		if (s >= S.n_seg) break;
-		if (S.role[s] == 0) continue; /* group-uniform */
-		int64_t kb = S.row[s], lo, hi, d = 0, len = 0, succ = -1;
-		if (kb < S.n_seq) lo = hi = A.acc[1]; /* new sentinels sort after all old ones, fm-index.c:164 */
-		else {
-			int c0 = 1;
-			while (c0 < RB3B_ASIZE - 1 && kb >= accB.v[c0 + 1]) ++c0;
-			lo = A.acc[c0]; hi = A.acc[c0 + 1];
-		}
-		uint64_t x = __ldg(lfb + kb);
-		for (;;) {
-			int c = (int)(x & 7);
-			if (lo == hi) { if (gl == 0) ka[kb] = lo; }
-			else {
-				if (S.logbase && gl == 0) {
-					int64_t o = S.logbase[s] + d;
-					S.log[o] = make_longlong2(kb, lo | (int64_t)c << LOG_C_SHIFT | (hi - lo <= LOG_WIDTH ? LOG_NARROW : 0));
+		if (s >= S.own_hi) break;
+		const int64_t p0 = s * S.seg_len, n = S.slice_len(s);
+		const int c0 = s == 0 ? 0 : (int)wsym[p0 - 1]; /* the symbol that led here = first symbol of this row's suffix */
+		int64_t lo, hi, d = 0;
+		if (c0 == 0) lo = hi = A.acc[1]; /* a sentinel row: new sentinels sort after all old ones, fm-index.c:164 */
+		else { lo = A.acc[c0]; hi = A.acc[c0 + 1]; }
+		uint64_t w = __ldg((const uint64_t*)(wsym + p0)); /* wsym is padded: whole words can always be read */
+		for (int64_t j = 0; j < n; j += 8) {
+			const uint64_t wn = j + 8 < n ? __ldg((const uint64_t*)(wsym + p0 + j + 8)) : 0; /* the symbols do not depend on A: fetch ahead */
+			int64_t vb[8];
+#pragma unroll
+			for (int jj = 0; jj < 8; ++jj) {
+				const int c = (int)(w >> (8 * jj)) & 7;
+				const bool live = j + jj < n;
+				if (lo == hi) vb[jj] = lo;
+				else { vb[jj] = lo | KS_UNRES | (hi - lo <= LOG_WIDTH ? KS_NARROW : 0); d += live; }
+				if (live) {
+					if (c == 0) lo = hi = A.acc[1]; /* first symbol of the sequence (fm-index.c:170): the next position is a sentinel row */
+					else {
+						int64_t r1, r2;
+						/* the walks that currently run together take the two-position path only while one of them still
+						 * carries a bracket; either path is correct for an exact walk, so this is purely a cost choice
+						 * (a private per-thread branch was measured slower: the two paths serialise) */
+						if (__any_sync(__activemask(), lo != hi)) WG::rank2(A, lo, hi, c, r1, r2);
+						else r1 = r2 = WG::rank(A, lo, c);
+						lo = A.acc[c] + r1; hi = A.acc[c] + r2;
+					}
 				}
-				++d;
 			}
-			++len;
-			if (c == 0) break; /* reached the first symbol of the sequence, fm-index.c:170 */
-			kb = (int64_t)(x >> LFB_SHIFT);
-			x = __ldg(lfb + kb); /* the B chain does not depend on A: fetch one step ahead */
-			int64_t r1, r2;
-			/* the groups that currently run together take the two-position path only while one of them still
-			 * carries a bracket; either path is correct for an exact group, so this is purely a cost choice */
-			/* (a private per-thread branch was measured slower for one-thread walks too: the two paths serialise) */
-			if (__any_sync(__activemask(), lo != hi)) WG::rank2(A, lo, hi, c, r1, r2);
-			else r1 = r2 = WG::rank(A, lo, c);
-			lo = A.acc[c] + r1; hi = A.acc[c] + r2;
-			if (x & LFB_COARSE) { succ = S.cmap[F.of_row(kb)]; break; }
+			if (gl == 0) {
+				if (j + 8 <= n) { /* full 64-B line of results */
+					longlong2 *o = (longlong2*)(kseq + p0 + j);
+					o[0] = make_longlong2(vb[0], vb[1]); o[1] = make_longlong2(vb[2], vb[3]);
+					o[2] = make_longlong2(vb[4], vb[5]); o[3] = make_longlong2(vb[6], vb[7]);
+				} else {
+#pragma unroll
+					for (int jj = 0; jj < 8; ++jj) if (j + jj < n) kseq[p0 + j + jj] = vb[jj];
+				}
+			}
+			w = wn;
 		}
-		if (gl == 0) { S.d[s] = d; S.len[s] = len; S.succ[s] = succ; S.arr_lo[s] = lo; S.arr_hi[s] = hi; }
+		if (gl == 0) { S.d[s] = d; S.arr_lo[s] = lo; S.arr_hi[s] = hi; }
 	}
 }
 
-/* after round 1: segments whose predecessor arrived with an exact value and that have unresolved rows */
-__global__ void k_collect_first(Segs S, int64_t *__restrict__ wl_seg, int64_t *__restrict__ wl_val, unsigned long long *wl_n)
+/* after round 1: slices whose predecessor arrived with an exact value and that have unresolved rows */
+__global__ void k_collect_first(Slices S, int64_t *__restrict__ wl_seg, int64_t *__restrict__ wl_val, unsigned long long *wl_n)
 {
-	int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= S.n_seg || S.role[s] == 0) return;
-	int64_t t = S.succ[s];
-	if (t >= 0 && S.arr_lo[s] == S.arr_hi[s] && S.d[t] > 0) {
+	int64_t s = S.walk_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (s + 1 >= S.own_hi) return;
+	if (S.arr_lo[s] == S.arr_hi[s] && S.d[s + 1] > 0) {
 		unsigned long long o = atomicAdd(wl_n, 1ULL);
-		wl_seg[o] = t; wl_val[o] = S.arr_lo[s];
+		wl_seg[o] = s + 1; wl_val[o] = S.arr_lo[s];
 	}
 }
 
-/* one logged row held by one lane; for a narrow bracket everything that does not depend on the exact value is
+/* one unresolved row held by one lane; for a narrow bracket everything that does not depend on the exact value is
  * precomputed: T[w] = #c between the window start and 32-bit word w of the window, W[w] = that word of plane c */
 struct LogRow {
-	int64_t kb, pos0, base; /* row; first position of the window; C[c] + #c before the window */
+	int64_t pos0, base; /* first position of the window; C[c] + #c before the window */
 	int c, narrow;
 	uint32_t T[4 * LOG_NCELL], W[4 * LOG_NCELL];
-	__device__ __forceinline__ void load(const DevIndex &A, const Segs &S, int64_t slot, bool valid)
+	__device__ __forceinline__ void load(const DevIndex &A, const int64_t *__restrict__ kseq, const uint8_t *__restrict__ wsym, int64_t slot, bool valid)
 	{
-		kb = 0; pos0 = 0; base = 0; c = 0; narrow = 0;
+		pos0 = 0; base = 0; c = 0; narrow = 0;
 		if (!valid) return;
-		const longlong2 rec = S.log[slot];
-		kb = rec.x;
-		int64_t w = rec.y, lo = w & (int64_t)RB3B_M42;
-		c = (int)(w >> LOG_C_SHIFT) & 7; narrow = (w & LOG_NARROW) != 0;
+		const int64_t w = kseq[slot], lo = w & (int64_t)RB3B_M42;
+		c = (int)wsym[slot]; narrow = (w & KS_NARROW) != 0;
 		if (!narrow) return;
 		const int h = c >= 3, cc = c - 3 * h;
 		const int64_t j = (lo < A.n ? lo : A.n - 1) >> RB3B_BM_SHIFT;
@@ -350,36 +371,27 @@ struct LogRow {
 		pos0 = j << RB3B_BM_SHIFT;
 		base = A.acc[c] + (int64_t)h0;
 	}
-	/* C[c] + rank(c, v) for the exact value v, which lies inside the window */
-	__device__ __forceinline__ int64_t step(const DevIndex &A, int64_t v) const
-	{
-		if (v >= A.n) return A.acc[c] + A.tot[c];
-		if (!narrow) return A.acc[c] + BmRank::rank(A, v, c);
-		uint32_t off = (uint32_t)(v - pos0), w = off >> 5;
-		return base + T[w] + __popc(W[w] & ((1u << (off & 31u)) - 1u));
-	}
 };
 
 /* shared-memory image of the 32 rows a warp works on */
 struct FixRows {
 	uint2 TW[32][4 * LOG_NCELL];   /* per row: x = word of plane c, y = #c between the window start and that word */
-	int64_t kb[32], pos0[32], base[32];
+	int64_t pos0[32], base[32];
 	int32_t K[32];                 /* base - first position of the NEXT row's window: keeps the chain in 32 bits */
 	uint32_t off[32];              /* result: exact value of the row relative to its window */
 	int32_t c[32];
 };
 
-/* round >= 2 with the fix-up log (bitmap cells): one WARP per listed segment.  Each lane fetches one logged row
- * (coalesced) and the cells it may need, one iteration (32 rows) ahead, and publishes the row's count/word tables in
- * shared memory.  Lane 0 then runs the dependent chain.  For a row with a narrow bracket the exact value is carried as a
- * 32-bit offset into the row's cell window: off' = K + T[off >> 5] + popc(W[off >> 5] below off), one 8-byte
- * shared-memory read and ~10 instructions per row (the kernel is bound by the instruction count of this serial
- * chain: handing the value from lane to lane with shuffles cost 56 warp instructions per row).  Afterwards all
- * lanes write the interleave positions of their rows.  Rows whose bracket was wider than the window (the first ~10 of
- * a segment) take the general path with a random cell access. */
-__global__ void __launch_bounds__(128) k_walk_fix_log(DevIndex A, Segs S, int64_t *__restrict__ ka, int64_t n_items,
-                                                       const int64_t *__restrict__ wl_seg, const int64_t *__restrict__ wl_val,
-                                                       int64_t *__restrict__ nx_seg, int64_t *__restrict__ nx_val, unsigned long long *nx_n)
+/* fix-up for bitmap cells: one WARP per listed slice.  Each lane fetches one unresolved row (coalesced: kseq and wsym
+ * are in walk order) and the cells it may need, one iteration (32 rows) ahead, and publishes the row's count/word tables
+ * in shared memory.  Lane 0 then runs the dependent chain.  For a row with a narrow bracket the exact value is carried as
+ * a 32-bit offset into the row's cell window: off' = K + T[off >> 5] + popc(W[off >> 5] below off), one 8-byte
+ * shared-memory read and ~10 instructions per row.  Afterwards all lanes write the interleave positions of their rows.
+ * Rows whose bracket was wider than the window (the first ~10 of a slice) take the general path with a random cell
+ * access.  A slice that never collapsed hands its exact arrival straight to the next slice in the same warp, so one
+ * launch resolves every cascade. */
+__global__ void __launch_bounds__(128) k_walk_fix_log(DevIndex A, Slices S, const uint8_t *__restrict__ wsym, int64_t *__restrict__ kseq, int64_t n_items,
+                                                       const int64_t *__restrict__ wl_seg, const int64_t *__restrict__ wl_val, unsigned long long *stats)
 {
 	__shared__ FixRows rows[4]; /* four warps per block */
 	const int lane = threadIdx.x & 31;
@@ -388,18 +400,18 @@ __global__ void __launch_bounds__(128) k_walk_fix_log(DevIndex A, Segs S, int64_
 	if (it >= n_items) return; /* warp-uniform */
 	int64_t t = wl_seg[it], v = wl_val[it];
 	unsigned long long n_rows = 0, n_wide = 0; /* statistics only */
-	for (;;) { /* a segment that never collapsed hands its exact arrival straight to its successor: same warp, no new launch */
-		const int64_t d = S.d[t], len = S.len[t], base = S.logbase[t];
+	for (;;) {
+		const int64_t d = S.d[t], len = S.slice_len(t), base = t * S.seg_len;
 		int ended = 0;
 		LogRow nxt;
-		nxt.load(A, S, base + lane, lane < d);
+		nxt.load(A, kseq, wsym, base + lane, lane < d);
 		n_rows += (unsigned long long)d;
 		for (int64_t i0 = 0; i0 < d && !ended; i0 += 32) {
 			const int cnt = d - i0 < 32 ? (int)(d - i0) : 32;
 			const bool live = lane < cnt;
 			/* this lane's row: fast = its step can be taken from the tables */
 			const bool fast = live && nxt.narrow && nxt.c != 0;
-			const int64_t my_kb = nxt.kb, my_pos0 = nxt.pos0, my_base = nxt.base;
+			const int64_t my_pos0 = nxt.pos0, my_base = nxt.base;
 			const int64_t next_pos0 = __shfl_down_sync(0xffffffffu, nxt.pos0, 1);
 			const unsigned fastmask = __ballot_sync(0xffffffffu, fast);
 			/* link: the next row of this iteration is fast too, so the value can stay relative */
@@ -408,10 +420,10 @@ __global__ void __launch_bounds__(128) k_walk_fix_log(DevIndex A, Segs S, int64_
 			n_wide += __popc(__ballot_sync(0xffffffffu, live && !nxt.narrow));
 #pragma unroll
 			for (int k = 0; k < 4 * LOG_NCELL; ++k) R.TW[lane][k] = make_uint2(nxt.W[k], nxt.T[k]);
-			R.kb[lane] = my_kb; R.pos0[lane] = my_pos0; R.base[lane] = my_base; R.c[lane] = nxt.c;
+			R.pos0[lane] = my_pos0; R.base[lane] = my_base; R.c[lane] = nxt.c;
 			R.K[lane] = link ? (int32_t)(my_base - next_pos0) : 0;
 			R.off[lane] = 0xffffffffu;
-			nxt.load(A, S, base + i0 + 32 + lane, i0 + 32 + lane < d); /* fetch the next iteration's row meanwhile */
+			nxt.load(A, kseq, wsym, base + i0 + 32 + lane, i0 + 32 + lane < d); /* fetch the next iteration's row meanwhile */
 			__syncwarp();
 			if (lane == 0) {
 				int u = 0;
@@ -427,37 +439,37 @@ __global__ void __launch_bounds__(128) k_walk_fix_log(DevIndex A, Segs S, int64_
 							++u;
 						}
 					} else { /* general row */
-						ka[R.kb[u]] = v;
+						kseq[base + i0 + u] = v;
 						const int c = R.c[u];
-						if (c == 0) { ended = 1; break; }
+						if (c == 0) { ended = 1; break; } /* the next position is a sentinel row, exact by itself */
 						v = A.acc[c] + BmRank::rank(A, v, c);
 						++u;
 					}
 				}
 			}
 			__syncwarp();
-			if (R.off[lane] != 0xffffffffu) ka[my_kb] = my_pos0 + R.off[lane]; /* rows resolved through the tables */
+			if (R.off[lane] != 0xffffffffu) kseq[base + i0 + lane] = my_pos0 + R.off[lane]; /* rows resolved through the tables */
 			v = __shfl_sync(0xffffffffu, v, 0);
 			ended = __shfl_sync(0xffffffffu, ended, 0);
 			__syncwarp(); /* the rows are consumed before they are overwritten */
 		}
-		const int64_t u2 = S.succ[t];
+		const bool more = d == len && !ended && t + 1 < S.own_hi && S.d[t + 1] > 0; /* t + 1's only predecessor is t: nobody else touches it */
 		if (lane == 0) {
 			S.d[t] = 0;
-			if (d == len && u2 >= 0) S.arr_lo[t] = S.arr_hi[t] = v;
+			if (d == len) S.arr_lo[t] = S.arr_hi[t] = v;
 		}
-		if (!(d == len && u2 >= 0 && S.d[u2] > 0)) break; /* u2's only predecessor is t: nobody else touches it */
-		t = u2;
+		if (!more) break;
+		++t;
 	}
-	if (lane == 0) { /* nx_n doubles as a statistics block: [1] rows, [2] rows with a wide bracket, [3] longest chain */
-		atomicAdd(nx_n + 1, n_rows); atomicAdd(nx_n + 2, n_wide); atomicMax(nx_n + 3, n_rows);
+	if (lane == 0) { /* [0] rows, [1] rows with a wide bracket, [2] longest chain */
+		atomicAdd(stats, n_rows); atomicAdd(stats + 1, n_wide); atomicMax(stats + 2, n_rows);
 	}
-	(void)nx_seg; (void)nx_val;
 }
 
-/* round >= 2: re-walk the unresolved prefix of each listed segment from its now exact start */
+/* generic fix-up (RLE cells, or bitmap cells without the tables): re-walk the unresolved prefix of each listed slice
+ * from its now exact start; slices that never collapsed put their successor on the next round's list */
 template<class WG>
-__global__ void __launch_bounds__(TPB) k_walk_fix(DevIndex A, Segs S, const uint64_t *__restrict__ lfb, int64_t *__restrict__ ka, int64_t n_items,
+__global__ void __launch_bounds__(TPB) k_walk_fix(DevIndex A, Slices S, const uint8_t *__restrict__ wsym, int64_t *__restrict__ kseq, int64_t n_items,
                                                    const int64_t *__restrict__ wl_seg, const int64_t *__restrict__ wl_val, int64_t *next_item,
                                                    int64_t *__restrict__ nx_seg, int64_t *__restrict__ nx_val, unsigned long long *nx_n)
 {
@@ -468,38 +480,65 @@ __global__ void __launch_bounds__(TPB) k_walk_fix(DevIndex A, Segs S, const uint
 		if (gl == 0) it = (int64_t)atomicAdd((unsigned long long*)next_item, 1ULL);
 		it = __shfl_sync(gmask, it, gbase);
 		if (it >= n_items) break;
-		int64_t t = wl_seg[it], v = wl_val[it], kb = S.row[t], d = S.d[t], len = S.len[t];
-		uint64_t x = __ldg(lfb + kb);
+		const int64_t t = wl_seg[it], d = S.d[t], len = S.slice_len(t), p0 = t * S.seg_len;
+		int64_t v = wl_val[it];
+		int c = 1;
 		for (int64_t i = 0; i < d; ++i) {
-			int c = (int)(x & 7);
-			if (gl == 0) ka[kb] = v;
+			c = (int)wsym[p0 + i];
+			if (gl == 0) kseq[p0 + i] = v;
 			if (c == 0) break;
-			kb = (int64_t)(x >> LFB_SHIFT);
-			x = __ldg(lfb + kb);
 			v = A.acc[c] + WG::rank(A, v, c);
 		}
 		if (gl == 0) {
 			S.d[t] = 0;
-			int64_t u = S.succ[t];
-			if (d == len && u >= 0) { /* never collapsed: only now is the arrival value known */
+			if (d == len && c != 0) { /* never collapsed: only now is the arrival value known */
 				S.arr_lo[t] = S.arr_hi[t] = v;
-				if (S.d[u] > 0) { /* u is processed by nobody else in this round: its only predecessor is t */
+				if (t + 1 < S.own_hi && S.d[t + 1] > 0) { /* t + 1 is processed by nobody else in this round */
 					unsigned long long o = atomicAdd(nx_n, 1ULL);
-					nx_seg[o] = u; nx_val[o] = v;
+					nx_seg[o] = t + 1; nx_val[o] = v;
 				}
 			}
 		}
 	}
 }
 
-__global__ void k_seg_check(Segs S, unsigned long long *sums)
+/* back to row order: ka[rows[i]] = vals[i] */
+template<typename RowT>
+__global__ void k_scatter_ka(int64_t n, const RowT *__restrict__ rows, const int64_t *__restrict__ vals, int64_t *__restrict__ ka, unsigned long long *n_unres)
 {
-	int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= S.n_seg) return;
-	if (S.role[s] != 1) return;
-	if (S.d[s]) atomicAdd(&sums[0], (unsigned long long)S.d[s]);
-	atomicAdd(&sums[1], (unsigned long long)S.len[s]);
-	atomicAdd(&sums[2], 1ULL);
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned int bad = 0;
+	if (i < n) {
+		const int64_t v = vals[i];
+		if (v & KS_UNRES) bad = 1;
+		else ka[(int64_t)rows[i]] = v;
+	}
+	bad = __popc(__ballot_sync(0xffffffffu, bad));
+	if (bad && (threadIdx.x & 31) == 0) atomicAdd(n_unres, (unsigned long long)bad);
+}
+
+/* A scatter of 8-byte values over a target much larger than L2 costs a DRAM read-modify-write of a sector per value.
+ * For large batches the (row, value) pairs are therefore first partitioned by the high bits of the row (one or two
+ * radix passes, streaming), so that the scatter proper works on windows of 2^19 rows (4 MB) that stay in L2. */
+template<typename RowT>
+static int scatter_to_rows(int64_t n, int64_t len, const RowT *rows, const int64_t *vals, int64_t *ka, unsigned long long *n_unres)
+{
+	if (n <= 0) return RB3B_OK;
+	const int win_bits = (int)rb3b_get_param("scatter_win_bits", 19);
+	int bits = 1;
+	while ((1LL << bits) < len) ++bits;
+	if (n >= rb3b_get_param("scatter_bucket_min", 24LL << 20) && bits > win_bits) {
+		DBuf<RowT> r2; DBuf<int64_t> v2; DBuf<uint8_t> tmp;
+		size_t tb = 0;
+		TRY(r2.alloc(n)); TRY(v2.alloc(n));
+		CK(cub::DeviceRadixSort::SortPairs(0, tb, rows, r2.p, vals, v2.p, n, win_bits, bits, rb3b_stream));
+		TRY(tmp.alloc(tb));
+		CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, rows, r2.p, vals, v2.p, n, win_bits, bits, rb3b_stream));
+		k_scatter_ka<RowT><<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, r2.p, v2.p, ka, n_unres); CKK();
+	} else {
+		k_scatter_ka<RowT><<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, rows, vals, ka, n_unres); CKK();
+	}
+	return RB3B_OK;
 }
 
 /* rb[i] = (ka+i)<<6 | B[i]<<3 | first symbol of suffix i (fm-index.c:168) */
@@ -520,23 +559,60 @@ __global__ void k_check_monotone(int64_t len, const int64_t *__restrict__ ka, in
 	if (v < 0 || v > nA || (i > 0 && ka[i - 1] > v)) *bad = 1;
 }
 
-int64_t rb3b_get_param(const char *key, int64_t dflt); /* rb3b_runtime.cu */
+
+/* everything of the rank phase that depends on the width of the batch's LF table */
+template<typename LfT, typename RowT>
+static int walk_order(int64_t len, const uint8_t *d_bwt, int64_t nt, const int64_t *tex, const Acc7 &acc, Fine &F,
+                      DBuf<uint8_t> &wsym, void **wrow_out)
+{
+	DBuf<LfT> lf;
+	DBuf<RowT> wrow;
+	TRY(lf.alloc(len)); TRY(wrow.alloc(len));
+	k_prep_lf<LfT><<<(unsigned)nt, TPB, 0, rb3b_stream>>>(len, d_bwt, nt, tex, acc, lf.p); CKK();
+	DBuf<FNode> nd; /* two buffers of list-ranking nodes (ping-pong) */
+	DBuf<int64_t> fc, ch; /* chain_of; chain_len, chain_base */
+	if (F.n_fine >= (1LL << 31)) return rb3b_fail(RB3B_EINVAL, "batch too large: %lld fine marks", (long long)F.n_fine);
+	TRY(nd.alloc(F.n_fine * 2)); TRY(fc.alloc(F.n_fine)); TRY(ch.alloc(F.n_seq * 2));
+	FNode *pp[2] = { nd.p, nd.p + F.n_fine };
+	int64_t *f_cof = fc.p, *c_len = ch.p, *c_base = ch.p + F.n_seq;
+	k_fine_walk<LfT><<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, lf.p, pp[0]); CKK();
+	int cur = 0;
+	for (int64_t span = 1; span < F.n_fine; span <<= 1) {
+		k_list_rank<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F.n_fine, pp[cur], pp[cur ^ 1]); CKK();
+		cur ^= 1;
+	}
+	const FNode *node = pp[cur];
+	CK(cudaMemsetAsync(f_cof, 0xff, F.n_fine * 8, rb3b_stream));
+	k_chain_len<<<nblk(F.n_seq, TPB), TPB, 0, rb3b_stream>>>(F.n_seq, node, c_len, f_cof); CKK();
+	TRY(rb3b_scan_excl_i64(c_len, c_base, F.n_seq));
+	int64_t last[2];
+	CK(cudaMemcpyAsync(&last[0], c_base + F.n_seq - 1, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+	CK(cudaMemcpyAsync(&last[1], c_len + F.n_seq - 1, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+	CK(cudaStreamSynchronize(rb3b_stream));
+	if (last[0] + last[1] != len) /* LF_B is a permutation, so the chains are disjoint: they cover the batch iff their lengths add up */
+		return rb3b_fail(RB3B_EINVAL, "batch is not the BWT of a sentinel-terminated string set (%lld of %lld rows reachable from the sentinels)",
+		                 (long long)(last[0] + last[1]), (long long)len);
+	k_write_walk<LfT, RowT><<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, len, lf.p, node, f_cof, c_base, c_len, wrow.p, wsym.p); CKK();
+	*wrow_out = wrow.p;
+	return RB3B_OK;
+}
 
 /* interleave positions of the batch in device memory: ka[len], accB */
-/* part/n_parts: see k_seg_role.  ka_out != NULL: write there instead of allocating.  *incomplete is set when a part could
- * not resolve all of its own rows locally (only possible with n_parts > 1). */
+/* part/n_parts: device `part` resolves the slices [part, part+1) * n_seg / n_parts and walks a halo of slices before them
+ * speculatively so that its first slice receives an exact value without any exchange.  ka_out != NULL: write there
+ * instead of allocating (rows of other parts are set to -1).  *incomplete is set when a part could not resolve all of
+ * its own rows locally (only possible with n_parts > 1). */
 static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, DBuf<int64_t> &ka, int64_t accB[RB3B_ASIZE + 1],
                       int part = 0, int n_parts = 1, int64_t *ka_out = 0, int *incomplete = 0)
 {
 	int64_t nt = (len + PREP_TILE - 1) / PREP_TILE;
 	DBuf<int64_t> tcnt, tex;
 	DBuf<int> bad;
-	DBuf<uint64_t> lfb;
 	int hbad = 0;
 	if (len <= 0) return rb3b_fail(RB3B_EINVAL, "empty batch");
 	if (A->n_cells == 0) return rb3b_fail(RB3B_EINVAL, "rank phase on an empty index");
 	/* batch LF mapping */
-	TRY(tcnt.alloc((nt + 1) * RB3B_ASIZE)); TRY(tex.alloc((nt + 1) * RB3B_ASIZE)); TRY(bad.alloc(1)); TRY(lfb.alloc(len));
+	TRY(tcnt.alloc((nt + 1) * RB3B_ASIZE)); TRY(tex.alloc((nt + 1) * RB3B_ASIZE)); TRY(bad.alloc(1));
 	CK(cudaMemsetAsync(bad.p, 0, sizeof(int), rb3b_stream));
 	rb3b_tic(T_PREP);
 	k_prep_count<<<(unsigned)nt, TPB, 0, rb3b_stream>>>(len, d_bwt, nt, tcnt.p, bad.p); CKK();
@@ -554,127 +630,107 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	for (int a = 0; a < RB3B_ASIZE; ++a) acc.v[a + 1] = acc.v[a] + (tot[a] - base[a]);
 	memcpy(accB, acc.v, sizeof(acc.v));
 	if (acc.v[1] <= 0) return rb3b_fail(RB3B_EINVAL, "batch BWT holds no sentinel");
-	/* fine marks, their list ranks, coarse marks */
-	int64_t seg_len = rb3b_seg_len;
+	/* the batch in walk order */
+	int64_t seg_len = (rb3b_seg_len + 7) / 8 * 8;
 	Fine F;
 	F.n_seq = acc.v[1];
-	F.fine_len = rb3b_get_param("fine_len", 32);
-	if (F.fine_len > seg_len) F.fine_len = seg_len;
-	if (F.fine_len < 1) F.fine_len = 1;
-	F.m0 = (F.n_seq + F.fine_len - 1) / F.fine_len;
-	int64_t n_samp = (len - 1) / F.fine_len - F.m0 + 1;
+	int64_t fine_len = rb3b_get_param("fine_len", 32);
+	if (fine_len > seg_len) fine_len = seg_len;
+	F.fshift = 0;
+	while ((2LL << F.fshift) <= fine_len) ++F.fshift; /* largest power of two <= fine_len */
+	F.m0 = (F.n_seq + (1LL << F.fshift) - 1) >> F.fshift;
+	int64_t n_samp = ((len - 1) >> F.fshift) - F.m0 + 1;
 	F.n_fine = F.n_seq + (n_samp > 0 ? n_samp : 0);
-	k_prep_lf<<<(unsigned)nt, TPB, 0, rb3b_stream>>>(len, d_bwt, nt, tex.p, acc, F.fine_len, lfb.p); CKK();
-	DBuf<int64_t> fn; /* succ, piece, 2 x (succ, dist, term) ping-pong, flag, sid, chain_len */
-	DBuf<int32_t> cmap;
-	TRY(fn.alloc(F.n_fine * 11)); TRY(cmap.alloc(F.n_fine));
-	int64_t *f_succ = fn.p, *f_piece = fn.p + F.n_fine;
-	int64_t *pp[2][3] = { { fn.p + 2 * F.n_fine, fn.p + 3 * F.n_fine, fn.p + 4 * F.n_fine }, { fn.p + 5 * F.n_fine, fn.p + 6 * F.n_fine, fn.p + 7 * F.n_fine } };
-	int64_t *f_flag = fn.p + 8 * F.n_fine, *f_sid = fn.p + 9 * F.n_fine, *f_clen = fn.p + 10 * F.n_fine;
-	k_fine_walk<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, lfb.p, f_succ, f_piece); CKK();
-	const int64_t *cs = f_succ, *cd = f_piece, *ct = 0;
-	int cur = 0;
-	for (int64_t span = 1; span < F.n_fine || ct == 0; span <<= 1) { /* at least once: it also initialises the terminal marks */
-		k_list_rank<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F.n_fine, cs, cd, ct, pp[cur][0], pp[cur][1], pp[cur][2]); CKK();
-		cs = pp[cur][0]; cd = pp[cur][1]; ct = pp[cur][2]; cur ^= 1;
+	DBuf<uint8_t> wsym;
+	void *wrow = 0;
+	TRY(wsym.alloc(len + 16)); /* padded: the walks read whole 8-byte words */
+	const bool narrow_lf = len < LF32_MAX_LEN && !rb3b_get_param("wide_lf", 0);
+	if (narrow_lf) TRY((walk_order<uint32_t, uint32_t>(len, d_bwt, nt, tex.p, acc, F, wsym, &wrow)));
+	else TRY((walk_order<uint64_t, int64_t>(len, d_bwt, nt, tex.p, acc, F, wsym, &wrow)));
+	/* slices */
+	Slices S;
+	S.len = len; S.seg_len = seg_len;
+	S.n_seg = (len + seg_len - 1) / seg_len;
+	S.own_lo = 0; S.own_hi = S.n_seg; S.walk_lo = 0;
+	if (n_parts > 1) {
+		S.own_lo = S.n_seg * part / n_parts; S.own_hi = S.n_seg * (part + 1) / n_parts;
+		S.walk_lo = S.own_lo - rb3b_get_param("halo_segments", 8);
+		if (S.walk_lo < 0) S.walk_lo = 0;
 	}
-	CK(cudaMemsetAsync(f_flag, 0, F.n_fine * 8, rb3b_stream));
-	k_coarse_flag<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, seg_len, f_succ, f_piece, cd, f_flag); CKK();
-	TRY(rb3b_scan_excl_i64(f_flag, f_sid, F.n_fine));
-	int64_t last[2];
-	CK(cudaMemcpyAsync(&last[0], f_sid + F.n_fine - 1, 8, cudaMemcpyDeviceToHost, rb3b_stream));
-	CK(cudaMemcpyAsync(&last[1], f_flag + F.n_fine - 1, 8, cudaMemcpyDeviceToHost, rb3b_stream));
-	CK(cudaStreamSynchronize(rb3b_stream));
-	/* segments */
-	Segs S;
-	S.n_seq = F.n_seq;
-	S.n_seg = last[0] + last[1];
-	DBuf<int64_t> seg, wl, ctr;
-	DBuf<uint8_t> role;
-	TRY(seg.alloc(S.n_seg * 6)); TRY(wl.alloc(S.n_seg * 4)); TRY(ctr.alloc(8)); TRY(role.alloc(S.n_seg));
+	const int64_t n_walk = S.own_hi - S.walk_lo;
+	DBuf<int64_t> seg, wl, ctr, kseq;
+	TRY(seg.alloc(S.n_seg * 3)); TRY(wl.alloc(S.n_seg * 4)); TRY(ctr.alloc(16)); TRY(kseq.alloc(len + 8));
 	if (ka_out) ka.p = ka_out; else TRY(ka.alloc(len));
-	CK(cudaMemsetAsync(seg.p, 0, S.n_seg * 5 * 8, rb3b_stream)); /* d = 0 for the segments other devices walk */
-	k_chain_len<<<nblk(F.n_seq, TPB), TPB, 0, rb3b_stream>>>(F.n_seq, cd, ct, f_clen); CKK();
-	k_seg_role<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, f_flag, f_sid, cd, ct, f_clen, part, n_parts,
-		rb3b_get_param("halo_segments", 8) * seg_len, 4 * seg_len, role.p); CKK();
-	S.role = role.p;
-	S.d = seg.p; S.len = seg.p + S.n_seg; S.succ = seg.p + 2 * S.n_seg; S.arr_lo = seg.p + 3 * S.n_seg; S.arr_hi = seg.p + 4 * S.n_seg;
-	S.row = seg.p + 5 * S.n_seg; S.cmap = cmap.p;
-	k_coarse_fill<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, f_flag, f_sid, seg.p + 5 * S.n_seg, cmap.p, lfb.p); CKK();
-	const bool bm = A->kind == RB3B_KIND_BM;
-	DBuf<int64_t> seglen, logbase, logbuf;
-	S.logbase = 0; S.log = 0;
-	if (bm && rb3b_get_param("fix_log", 1) && len * 16 <= rb3b_get_param("fix_log_max_bytes", 16LL << 30)) {
-		TRY(seglen.alloc(S.n_seg)); TRY(logbase.alloc(S.n_seg)); TRY(logbuf.alloc(2 * len));
-		k_seg_len<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, f_flag, f_sid, f_succ, f_piece, seglen.p); CKK();
-		TRY(rb3b_scan_excl_i64(seglen.p, logbase.p, S.n_seg));
-		S.logbase = logbase.p; S.log = (longlong2*)logbuf.p;
-	}
+	S.d = seg.p; S.arr_lo = seg.p + S.n_seg; S.arr_hi = seg.p + 2 * S.n_seg;
 	rb3b_toc(T_PREP);
-	CK(cudaMemsetAsync(ctr.p, 0, 8 * 8, rb3b_stream));
-	CK(cudaMemsetAsync(ka.p, 0xff, len * 8, rb3b_stream));
+	CK(cudaMemsetAsync(ctr.p, 0, 16 * 8, rb3b_stream));
+	if (n_parts > 1) CK(cudaMemsetAsync(ka.p, 0xff, len * 8, rb3b_stream));
 	DevIndex dA = rb3b_dev_view(A);
-	/* the batch LF table is hit once per row at random: keep it resident in L2 while the index cells stream through */
-	const bool pin = rb3b_get_param("pin_lfb", 0) != 0; /* measured slower on B200 (set-aside shrinks the L2 left for cells, ka and the log): off by default */
-	if (pin) rb3b_l2_pin(lfb.p, (size_t)len * 8);
-	/* bitmap walks are single threads: small CTAs spread the few thousand walks over all SMs */
+	const bool bm = A->kind == RB3B_KIND_BM;
+	/* bitmap walks are single threads: small CTAs spread the walks over all SMs */
 	const int wg = bm ? 1 : 8, wtpb = bm ? 32 : TPB;
-	int64_t want = (S.n_seg * wg + wtpb - 1) / wtpb, cap = (int64_t)n_sm() * (bm ? 32 : 8);
+	int64_t want = (n_walk * wg + wtpb - 1) / wtpb, cap = (int64_t)n_sm() * (bm ? 32 : 8);
+	if (want < 1) want = 1;
 	rb3b_tic(T_WALK1);
-	if (bm) k_walk_first<BmRank><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, acc, S, F, lfb.p, ka.p, ctr.p);
-	else k_walk_first<Grp<8> ><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, acc, S, F, lfb.p, ka.p, ctr.p);
+	if (bm) k_walk_first<BmRank><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
+	else k_walk_first<Grp<8> ><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
 	CKK();
 	rb3b_toc(T_WALK1);
 	int64_t *wl_seg[2] = { wl.p, wl.p + 2 * S.n_seg }, *wl_val[2] = { wl.p + S.n_seg, wl.p + 3 * S.n_seg };
-	k_collect_first<<<nblk(S.n_seg, TPB), TPB, 0, rb3b_stream>>>(S, wl_seg[0], wl_val[0], (unsigned long long*)(ctr.p + 1)); CKK();
-	int64_t n_items = 0, rounds = 1, fix_rows = 0;
+	k_collect_first<<<nblk(n_walk > 0 ? n_walk : 1, TPB), TPB, 0, rb3b_stream>>>(S, wl_seg[0], wl_val[0], (unsigned long long*)(ctr.p + 1)); CKK();
+	int64_t n_items = 0, rounds = 1, fix_items = 0;
 	CK(cudaMemcpyAsync(&n_items, ctr.p + 1, 8, cudaMemcpyDeviceToHost, rb3b_stream));
 	CK(cudaStreamSynchronize(rb3b_stream));
-	cur = 0;
+	const bool use_log = bm && rb3b_get_param("fix_log", 1) != 0;
+	int cur = 0;
 	while (n_items > 0) {
-		/* ctr[2] = item cursor, ctr[3] = size of the next list */
+		/* ctr[2] = item cursor, ctr[3] = size of the next list, ctr[4..6] = statistics */
 		CK(cudaMemsetAsync(ctr.p + 2, 0, 40, rb3b_stream));
 		want = (n_items * wg + wtpb - 1) / wtpb;
 		rb3b_tic(T_WALKFIX);
-		if (bm && S.logbase) k_walk_fix_log<<<nblk(n_items * 32, 128), 128, 0, rb3b_stream>>>(dA, S, ka.p, n_items, wl_seg[cur], wl_val[cur],
+		if (use_log) k_walk_fix_log<<<nblk(n_items * 32, 128), 128, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, n_items, wl_seg[cur], wl_val[cur],
+			(unsigned long long*)(ctr.p + 4));
+		else if (bm) k_walk_fix<BmRank><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, n_items, wl_seg[cur], wl_val[cur], ctr.p + 2,
 			wl_seg[cur ^ 1], wl_val[cur ^ 1], (unsigned long long*)(ctr.p + 3));
-		else if (bm) k_walk_fix<BmRank><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, S, lfb.p, ka.p, n_items, wl_seg[cur], wl_val[cur], ctr.p + 2,
-			wl_seg[cur ^ 1], wl_val[cur ^ 1], (unsigned long long*)(ctr.p + 3));
-		else k_walk_fix<Grp<8> ><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, S, lfb.p, ka.p, n_items, wl_seg[cur], wl_val[cur], ctr.p + 2,
+		else k_walk_fix<Grp<8> ><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, n_items, wl_seg[cur], wl_val[cur], ctr.p + 2,
 			wl_seg[cur ^ 1], wl_val[cur ^ 1], (unsigned long long*)(ctr.p + 3));
 		CKK();
 		rb3b_toc(T_WALKFIX);
-		fix_rows += n_items;
+		fix_items += n_items;
 		int64_t fst[4] = {0, 0, 0, 0};
 		CK(cudaMemcpyAsync(fst, ctr.p + 3, 32, cudaMemcpyDeviceToHost, rb3b_stream));
 		CK(cudaStreamSynchronize(rb3b_stream));
 		n_items = fst[0];
-		if (bm && S.logbase) { rb3b_stat_set("fix_rows", fst[1]); rb3b_stat_set("fix_wide_rows", fst[2]); rb3b_stat_set("fix_longest_chain", fst[3]); }
+		if (use_log) { rb3b_stat_set("fix_rows", fst[1]); rb3b_stat_set("fix_wide_rows", fst[2]); rb3b_stat_set("fix_longest_chain", fst[3]); }
 		rb3b_tflush();
 		cur ^= 1; ++rounds;
 	}
-	if (pin) rb3b_l2_pin(0, 0);
-	unsigned long long sums[3];
-	CK(cudaMemsetAsync(ctr.p + 4, 0, 24, rb3b_stream));
-	k_seg_check<<<nblk(S.n_seg, TPB), TPB, 0, rb3b_stream>>>(S, (unsigned long long*)(ctr.p + 4)); CKK();
-	CK(cudaMemcpyAsync(sums, ctr.p + 4, 24, cudaMemcpyDeviceToHost, rb3b_stream));
+	/* back to row order */
+	unsigned long long unres = 0;
+	const int64_t own_rows = (S.own_hi * seg_len < len ? S.own_hi * seg_len : len) - S.own_lo * seg_len;
+	CK(cudaMemsetAsync(ctr.p + 8, 0, 8, rb3b_stream));
+	rb3b_tic(T_SCATTER);
+	const int64_t own_p0 = S.own_lo * seg_len;
+	if (narrow_lf) TRY(scatter_to_rows<uint32_t>(own_rows, len, (const uint32_t*)wrow + own_p0, kseq.p + own_p0, ka.p, (unsigned long long*)(ctr.p + 8)));
+	else TRY(scatter_to_rows<int64_t>(own_rows, len, (const int64_t*)wrow + own_p0, kseq.p + own_p0, ka.p, (unsigned long long*)(ctr.p + 8)));
+	rb3b_toc(T_SCATTER);
+	CK(cudaMemcpyAsync(&unres, ctr.p + 8, 8, cudaMemcpyDeviceToHost, rb3b_stream));
 	CK(cudaStreamSynchronize(rb3b_stream));
 	rb3b_tflush();
 	rb3b_stat_set("n_segments", S.n_seg);
 	rb3b_stat_set("n_fine", F.n_fine);
 	rb3b_stat_set("fix_rounds", rounds - 1);
 	rb3b_stat_add("fix_rounds_total", rounds - 1);
-	rb3b_stat_set("fix_segments", fix_rows);
-	rb3b_stat_set("unresolved_rows", (int64_t)sums[0]);
-	rb3b_stat_set("own_segments", (int64_t)sums[2]);
-	rb3b_stat_set("own_rows", (int64_t)sums[1]);
+	rb3b_stat_set("fix_segments", fix_items);
+	rb3b_stat_set("unresolved_rows", (int64_t)unres);
+	rb3b_stat_set("own_segments", S.own_hi - S.own_lo);
+	rb3b_stat_set("own_rows", own_rows);
 	if (n_parts > 1) { /* completeness of the whole batch is checked after the exchange */
-		if (incomplete) *incomplete = sums[0] != 0;
+		if (incomplete) *incomplete = unres != 0;
 		return RB3B_OK;
 	}
-	if (sums[0] != 0 || (int64_t)sums[1] != len)
-		return rb3b_fail(RB3B_EINVAL, "batch is not the BWT of a sentinel-terminated string set (%lld of %lld rows reachable, %lld unresolved)",
-		                 (long long)sums[1], (long long)len, (long long)sums[0]);
+	if (unres != 0)
+		return rb3b_fail(RB3B_EINVAL, "batch is not the BWT of a sentinel-terminated string set (%lld rows unresolved)", (long long)unres);
 	return RB3B_OK;
 }
 

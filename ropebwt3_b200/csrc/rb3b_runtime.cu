@@ -73,7 +73,7 @@ int rb3b_fail(int code, const char *fmt, ...)
 int64_t rb3b_n_launch = 0;
 static cudaEvent_t g_ev[T_COUNT][2];
 static int g_ev_ok = 0, g_ev_pending[T_COUNT];
-static const char *g_ev_name[T_COUNT] = { "us_prep", "us_walk_first", "us_walk_fix", "us_merge", "us_finalize", "us_bwt" };
+static const char *g_ev_name[T_COUNT] = { "us_prep", "us_walk_first", "us_walk_fix", "us_merge", "us_scatter", "us_bwt" };
 
 void rb3b_tic(int id)
 {

@@ -224,13 +224,16 @@ def test_bitmap_to_rle_transition(rb3, oracle, golden):
         rb3.set_param("bitmap_max_symbols", 24000000000)
 
 
-@pytest.mark.parametrize("knob,value", [("fix_log", 0), ("pin_lfb", 1), ("fine_len", 7), ("fix_log_max_bytes", 1000)])
+@pytest.mark.parametrize("knob,value", [("fix_log", 0), ("wide_lf", 1), ("fine_len", 7), ("fine_len", 1), ("scatter_win_bits", 5)])
 def test_optional_code_paths(rb3, oracle, golden, knob, value):
-    """The tuning knobs select other kernels (multi-round fix-up without the log, persisting-L2 window, other mark
-    spacing); every one of them must give the reference's interleave array and merged index."""
+    """The tuning knobs select other kernels (multi-round fix-up without the tables, 64-bit LF table and rows, other mark
+    spacing, the two-pass bucketed scatter of large batches); every one of them must give the reference's interleave
+    array and merged index."""
     g = golden("merge_dup")
-    defaults = {"fix_log": 1, "pin_lfb": 0, "fine_len": 32, "fix_log_max_bytes": 16 << 30}
+    defaults = {"fix_log": 1, "wide_lf": 0, "fine_len": 32, "scatter_win_bits": 19}
     rb3.set_param(knob, value)
+    if knob == "scatter_win_bits":
+        rb3.set_param("scatter_bucket_min", 1)
     rb3.set_param("seg_len", 64)
     try:
         idx = rb3.Index.from_plain(g["bwt0"])
@@ -243,6 +246,7 @@ def test_optional_code_paths(rb3, oracle, golden, knob, value):
         assert np.array_equal(s, s0) and np.array_equal(l, l0)
     finally:
         rb3.set_param(knob, defaults[knob])
+        rb3.set_param("scatter_bucket_min", 24 << 20)
         rb3.set_param("seg_len", 512)
 
 
