@@ -454,6 +454,11 @@ def run_reference(a):
 
 if __name__ == "__main__":
     args = parse()
+    # stdout carries the one JSON line and nothing else: libraries that print to fd 1 (the NCCL banner) go to stderr
+    sys.stdout.flush()
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _real_stdout
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -149,7 +149,7 @@ __device__ __forceinline__ int32_t fnode_term(const FNode &n) { return (int32_t)
 
 /* walk every piece once (LF_B only, no rank): its length and the piece that follows it */
 template<typename LfT>
-__global__ void k_fine_walk(Fine F, const LfT *__restrict__ lf, FNode *__restrict__ node)
+__global__ void k_fine_walk(Fine F, const LfT *__restrict__ lf, FNode *__restrict__ node, int32_t *__restrict__ piece_len)
 {
 	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (f >= F.n_fine) return;
@@ -162,6 +162,7 @@ __global__ void k_fine_walk(Fine F, const LfT *__restrict__ lf, FNode *__restric
 		if (F.is_mark(kb)) { nx = F.of_row(kb); break; }
 	}
 	node[f] = fnode(n, (int32_t)nx, (int32_t)f);
+	piece_len[f] = (int32_t)n;
 }
 
 /* Wyllie pointer jumping: after ceil(log2 n) rounds x = #rows from fine mark f to the start of its sequence.  One 16-byte
@@ -209,7 +210,7 @@ template<> struct RowVec<int64_t> {
 template<typename LfT, typename RowT>
 __global__ void k_write_walk(Fine F, int64_t len, const LfT *__restrict__ lf, const FNode *__restrict__ node,
                              const int64_t *__restrict__ chain_of, const int64_t *__restrict__ chain_base, const int64_t *__restrict__ chain_len,
-                             RowT *__restrict__ wrow, uint8_t *__restrict__ wsym)
+                             const int32_t *__restrict__ piece_len, int64_t p_lo, int64_t p_hi, RowT *__restrict__ wrow, uint8_t *__restrict__ wsym)
 {
 	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (f >= F.n_fine) return;
@@ -218,6 +219,7 @@ __global__ void k_write_walk(Fine F, int64_t len, const LfT *__restrict__ lf, co
 	if (p < 0) return; /* not on a chain that starts at a sentinel: not a valid BWT, reported by the caller */
 	int64_t pos = chain_base[p] + chain_len[p] - me.x, kb = F.row(f);
 	if (pos < 0 || pos + me.x > len) return; /* cannot happen for a valid BWT */
+	if (pos >= p_hi || pos + piece_len[f] <= p_lo) return; /* another device walks these positions */
 	uint64_t sw = 0;
 	int ns = 0, nr = 0; /* symbols / rows collected */
 	RowVec<RowT> rv;
@@ -563,7 +565,7 @@ __global__ void k_check_monotone(int64_t len, const int64_t *__restrict__ ka, in
 /* everything of the rank phase that depends on the width of the batch's LF table */
 template<typename LfT, typename RowT>
 static int walk_order(int64_t len, const uint8_t *d_bwt, int64_t nt, const int64_t *tex, const Acc7 &acc, Fine &F,
-                      DBuf<uint8_t> &wsym, void **wrow_out)
+                      int64_t p_lo, int64_t p_hi, DBuf<uint8_t> &wsym, void **wrow_out)
 {
 	DBuf<LfT> lf;
 	DBuf<RowT> wrow;
@@ -571,11 +573,12 @@ static int walk_order(int64_t len, const uint8_t *d_bwt, int64_t nt, const int64
 	k_prep_lf<LfT><<<(unsigned)nt, TPB, 0, rb3b_stream>>>(len, d_bwt, nt, tex, acc, lf.p); CKK();
 	DBuf<FNode> nd; /* two buffers of list-ranking nodes (ping-pong) */
 	DBuf<int64_t> fc, ch; /* chain_of; chain_len, chain_base */
+	DBuf<int32_t> pl;
 	if (F.n_fine >= (1LL << 31)) return rb3b_fail(RB3B_EINVAL, "batch too large: %lld fine marks", (long long)F.n_fine);
-	TRY(nd.alloc(F.n_fine * 2)); TRY(fc.alloc(F.n_fine)); TRY(ch.alloc(F.n_seq * 2));
+	TRY(nd.alloc(F.n_fine * 2)); TRY(fc.alloc(F.n_fine)); TRY(ch.alloc(F.n_seq * 2)); TRY(pl.alloc(F.n_fine));
 	FNode *pp[2] = { nd.p, nd.p + F.n_fine };
 	int64_t *f_cof = fc.p, *c_len = ch.p, *c_base = ch.p + F.n_seq;
-	k_fine_walk<LfT><<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, lf.p, pp[0]); CKK();
+	k_fine_walk<LfT><<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, lf.p, pp[0], pl.p); CKK();
 	int cur = 0;
 	for (int64_t span = 1; span < F.n_fine; span <<= 1) {
 		k_list_rank<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F.n_fine, pp[cur], pp[cur ^ 1]); CKK();
@@ -592,7 +595,7 @@ static int walk_order(int64_t len, const uint8_t *d_bwt, int64_t nt, const int64
 	if (last[0] + last[1] != len) /* LF_B is a permutation, so the chains are disjoint: they cover the batch iff their lengths add up */
 		return rb3b_fail(RB3B_EINVAL, "batch is not the BWT of a sentinel-terminated string set (%lld of %lld rows reachable from the sentinels)",
 		                 (long long)(last[0] + last[1]), (long long)len);
-	k_write_walk<LfT, RowT><<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, len, lf.p, node, f_cof, c_base, c_len, wrow.p, wsym.p); CKK();
+	k_write_walk<LfT, RowT><<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, len, lf.p, node, f_cof, c_base, c_len, pl.p, p_lo, p_hi, wrow.p, wsym.p); CKK();
 	*wrow_out = wrow.p;
 	return RB3B_OK;
 }
@@ -641,12 +644,6 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	F.m0 = (F.n_seq + (1LL << F.fshift) - 1) >> F.fshift;
 	int64_t n_samp = ((len - 1) >> F.fshift) - F.m0 + 1;
 	F.n_fine = F.n_seq + (n_samp > 0 ? n_samp : 0);
-	DBuf<uint8_t> wsym;
-	void *wrow = 0;
-	TRY(wsym.alloc(len + 16)); /* padded: the walks read whole 8-byte words */
-	const bool narrow_lf = len < LF32_MAX_LEN && !rb3b_get_param("wide_lf", 0);
-	if (narrow_lf) TRY((walk_order<uint32_t, uint32_t>(len, d_bwt, nt, tex.p, acc, F, wsym, &wrow)));
-	else TRY((walk_order<uint64_t, int64_t>(len, d_bwt, nt, tex.p, acc, F, wsym, &wrow)));
 	/* slices */
 	Slices S;
 	S.len = len; S.seg_len = seg_len;
@@ -657,6 +654,13 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 		S.walk_lo = S.own_lo - rb3b_get_param("halo_segments", 8);
 		if (S.walk_lo < 0) S.walk_lo = 0;
 	}
+	DBuf<uint8_t> wsym;
+	void *wrow = 0;
+	TRY(wsym.alloc(len + 16)); /* padded: the walks read whole 8-byte words */
+	const bool narrow_lf = len < LF32_MAX_LEN && !rb3b_get_param("wide_lf", 0);
+	const int64_t p_lo = S.walk_lo * seg_len - 1, p_hi = S.own_hi * seg_len; /* walk-order positions this device reads */
+	if (narrow_lf) TRY((walk_order<uint32_t, uint32_t>(len, d_bwt, nt, tex.p, acc, F, p_lo, p_hi, wsym, &wrow)));
+	else TRY((walk_order<uint64_t, int64_t>(len, d_bwt, nt, tex.p, acc, F, p_lo, p_hi, wsym, &wrow)));
 	const int64_t n_walk = S.own_hi - S.walk_lo;
 	DBuf<int64_t> seg, wl, ctr, kseq;
 	TRY(seg.alloc(S.n_seg * 3)); TRY(wl.alloc(S.n_seg * 4)); TRY(ctr.alloc(16)); TRY(kseq.alloc(len + 8));
