@@ -170,7 +170,8 @@ static int usage(FILE *fp)
 	fprintf(fp, "  -S FILE  save the index (.fmr) after every input file\n");
 	fprintf(fp, "  -l INT   leaf block length of the .fmr dump [512]   -n INT  max children per node [64]\n");
 	fprintf(fp, "  -t INT / -p INT  accepted for compatibility; the device provides the parallelism\n");
-	fprintf(fp, "  -2 -s -r -T -e   not supported by this engine (ropebwt2 insertion order, tree dump, BRE)\n");
+	fprintf(fp, "  -2 / -s / -r   ropebwt2 insertion: input order / RLO / RCLO (mr_insert_multi)\n");
+	fprintf(fp, "  -T -e    not supported by this engine (tree dump: there is no tree; BRE)\n");
 	fprintf(fp, "Environment: RB3B_DEVICE=<cuda device>\n");
 	return fp == stdout ? 0 : 1;
 }
@@ -180,6 +181,7 @@ static int usage(FILE *fp)
 int main(int argc, char *argv[])
 {
 	int c, i, is_line = 0, no_for = 0, no_rev = 0, fmt = 0 /* 0 plain, 1 fmd, 2 fmr */, block_len = 512, max_nodes = 64;
+	int use_rb2 = 0, sort_order = 0; /* build.c:153-155 */
 	int64_t batch = 7000000000LL;
 	const char *fn_in = 0, *fn_tmp = 0;
 	str_t seq = {0, 0, 0}, rec = {0, 0, 0}, tmp = {0, 0, 0};
@@ -204,8 +206,11 @@ int main(int argc, char *argv[])
 		else if (c == 'd') fmt = 1;
 		else if (c == 'b') fmt = 2;
 		else if (c == 'S') fn_tmp = optarg;
-		else if (c == '2' || c == 's' || c == 'r' || c == 'T' || c == 'e') {
-			fprintf(stderr, "ERROR: option -%c (ropebwt2 insertion / tree dump / BRE) is outside this engine's scope; use the CPU ropebwt3 for it\n", c);
+		else if (c == '2') use_rb2 = 1;
+		else if (c == 's') use_rb2 = 1, sort_order = 1;
+		else if (c == 'r') use_rb2 = 1, sort_order = 2;
+		else if (c == 'T' || c == 'e') {
+			fprintf(stderr, "ERROR: option -%c (tree dump / BRE) is outside this engine's scope; use the CPU ropebwt3 for it\n", c);
 			return 1;
 		} else return usage(stderr);
 	}
@@ -248,6 +253,15 @@ int main(int argc, char *argv[])
 				if (d_text == 0) { fprintf(stderr, "ERROR: %s\n", rb3b_last_error()); return 1; }
 			}
 			DIE_IF(rb3b_h2d(d_text, seq.s, (int64_t)seq.l), "host to device copy");
+			if (use_rb2) { /* build.c:214-218; an index loaded with -i keeps its own order, like mr->so */
+				if (idx == 0) {
+					idx = rb3b_index_create();
+					DIE_IF(rb3b_index_set_order(idx, sort_order), "sorting order");
+				}
+				DIE_IF(rb3b_insert_multi_dev(idx, (int64_t)seq.l, (const uint8_t*)d_text), "inserting the batch");
+				LOG("inserted %ld symbols", (long)seq.l);
+				continue;
+			}
 			DIE_IF(rb3b_build_bwt_dev((int64_t)seq.l, (const uint8_t*)d_text, (uint8_t*)d_text), "partial BWT"); /* rb3_build_sais, in place */
 			LOG("constructed partial BWT for %ld symbols", (long)seq.l);
 			if (idx == 0) {

@@ -51,6 +51,11 @@ void          rb3b_index_destroy(rb3b_index_t *idx);
  * to n_symbols; device buffers are sized once instead of being regrown by the merges */
 int           rb3b_index_reserve(rb3b_index_t *idx, int64_t n_symbols);
 
+/* sorting order of the collection = third argument of mr_init (mrope.c:15, mrope.h:6-8): 0 input order (default),
+ * 1 RLO, 2 RCLO.  Only rb3b_insert_multi honours it; it is stored in / restored from the .fmr header. */
+int           rb3b_index_set_order(rb3b_index_t *idx, int sorting_order);
+int           rb3b_index_get_order(const rb3b_index_t *idx);
+
 /* ---- building blocks of `build` -------------------------------------------- */
 /* rb3_enc_plain2fmr (fm-index.c:114-137): first batch, BWT in host memory. */
 int rb3b_index_from_plain(rb3b_index_t *idx, int64_t len, const uint8_t *bwt);
@@ -65,6 +70,12 @@ int rb3b_index_from_runs_device(rb3b_index_t *idx, int64_t n_runs, const uint8_t
 int rb3b_merge_plain(rb3b_index_t *idx, int64_t len, const uint8_t *bwt);
 /* same, partial BWT already in device memory (no host<->device copies) */
 int rb3b_merge_plain_dev(rb3b_index_t *idx, int64_t len, const uint8_t *d_bwt);
+
+/* mr_insert_multi (mrope.c:300-385), the `build -2/-s/-r` path (build.c:214-218): insert the strings of `text`
+ * (concatenated 0-terminated nt6 strings exactly as rb3_seq_read delivers them; the reference reverses them first with
+ * rb3_reverse_all, this call does not need that) into the index in the index's sorting order. */
+int rb3b_insert_multi(rb3b_index_t *idx, int64_t len, const uint8_t *text);
+int rb3b_insert_multi_dev(rb3b_index_t *idx, int64_t len, const uint8_t *d_text);
 
 /* rb3_mg_rank_plain (fm-index.c:202-225): the interleave array only.  rb[i] =
  * (ka+i)<<6 | B[i]<<3 | bucket(i) exactly as fm-index.c:168; acc[7] = C[] of the batch. */
@@ -116,6 +127,9 @@ void    rb3b_host_free(void *p);
 /* text: concatenated 0-terminated nt6 strings (host); bwt_out: host, len bytes (may alias text). */
 int rb3b_build_bwt(int64_t len, const uint8_t *text, uint8_t *bwt_out);
 int rb3b_build_bwt_dev(int64_t len, const uint8_t *d_text, uint8_t *d_bwt_out);
+/* same in RLO (1) / RCLO (2) order: the BWT that mr_insert_multi (mrope.c:300) produces for this batch on an empty rope */
+int rb3b_build_bwt_so(int64_t len, const uint8_t *text, int sorting_order, uint8_t *bwt_out);
+int rb3b_build_bwt_so_dev(int64_t len, const uint8_t *d_text, int sorting_order, uint8_t *d_bwt_out);
 
 /* ---- device memory helpers for callers without a CUDA runtime of their own -- */
 void *rb3b_dev_alloc(int64_t bytes);

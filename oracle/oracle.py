@@ -195,3 +195,112 @@ def encode_batch(seqs, fwd=True, rev=True):
 
 def to_ascii(bwt):
     return np.frombuffer(b"$ACGTN", np.uint8)[np.asarray(bwt, np.uint8)].tobytes().decode()
+
+
+# ---------------------------------------------------------------- ropebwt2 insertion (build -2 / -s / -r)
+def _split_strings(text):
+    t = np.asarray(text, np.uint8)
+    z = np.flatnonzero(t == 0)
+    out, s = [], 0
+    for e in z:
+        out.append([int(x) for x in t[s:e]])
+        s = int(e) + 1
+    return out
+
+
+def _comp6(c):
+    return 5 - c if 1 <= c <= 4 else c  # rope_comp6, mrope.c:224
+
+
+def insert_multi(ropes, text, so):
+    """mr_insert_multi + mr_insert_multi_aux (mrope.c:226-385) restated on six plain Python lists: ropes[b] holds the
+    BWT symbols of the rows whose suffix starts with symbol b (mrope.h:10-14).  `text`: the reads as read, 0-terminated;
+    they are reversed here as build.c:216 (rb3_reverse_all) does.  so: 0 input order, 1 RLO, 2 RCLO.  Pure Python, small
+    cases only.  Returns ropes (modified in place)."""
+    strs = [s[::-1] + [0] for s in _split_strings(text)]  # reversed, NUL-terminated (mrope.c:310-319)
+    m = len(strs)
+    is_srt, is_comp = so != 0, so == 2
+    n0 = sum(r.count(0) for r in ropes)  # mrope.c:321
+    # triple64_t (mrope.c:216-220): [l, u, c, string, read offset]
+    prev = [[0, n0, 0, s, 0] if is_srt else [n0 + k, n0 + k, 0, s, 0] for k, s in enumerate(strs)]  # mrope.c:322-326
+
+    def insert_run(rope, x, b, n):  # rope_insert_run (rope.c:114): returns rank(b, x)
+        r = rope[:x].count(b)
+        rope[x:x] = [b] * n
+        return r
+
+    def aux(rope, a):  # mr_insert_multi_aux, mrope.c:226-275
+        for t in a:
+            t[2] = t[3][t[4]]
+            t[4] += 1
+        beg = 0
+        for k in range(1, len(a) + 1):
+            if k == len(a) or a[k][1] != a[k - 1][1]:
+                l, u = a[beg][0], a[beg][1]
+                if l == u and k == beg + 1:
+                    a[beg][0] = a[beg][1] = insert_run(rope, l, a[beg][2], 1)
+                    beg = k
+                    continue
+                tl = [rope[:l].count(b) for b in range(6)] if l != u else [0] * 6
+                tu = [rope[:u].count(b) for b in range(6)] if l != u else [0] * 6
+                c = [0] * 6
+                for i in range(beg, k):
+                    c[a[i][2]] += 1
+                if c[0]:
+                    insert_run(rope, l, 0, c[0])
+                x = l + c[0] + (tu[0] - tl[0])
+                for b in ([4, 3, 2, 1] if is_comp else [1, 2, 3, 4]):  # mrope.c:249-260
+                    size = tu[b] - tl[b]
+                    if c[b]:
+                        tl[b] = insert_run(rope, x, b, c[b])
+                        tu[b] = tl[b] + size
+                    x += c[b] + size
+                if c[5]:
+                    tu[5] -= tl[5]
+                    tl[5] = insert_run(rope, x, 5, c[5])
+                    tu[5] += tl[5]
+                for i in range(beg, k):
+                    a[i][0], a[i][1] = tl[a[i][2]], tu[a[i][2]]
+                beg = k
+
+    aux(ropes[0], prev)  # the first (actually the last) column, mrope.c:327
+    live = prev
+    while live:
+        buckets = [[t for t in live if t[2] == b] for b in range(6)]  # stable counting sort, mrope.c:343-349
+        for b in range(1, 6):
+            if buckets[b]:
+                aux(ropes[b], buckets[b])
+        ac = [0] * 6
+        for b in range(1, 6):  # mrope.c:372-380
+            for a in range(6):
+                ac[a] += ropes[b - 1].count(a)
+            for t in buckets[b]:
+                t[0] += ac[t[2]]
+                t[1] += ac[t[2]]
+        live = [t for b in range(1, 6) for t in buckets[b]]
+    return ropes
+
+
+def rb2_bwt(texts, so):
+    """BWT (uint8 array) after inserting the batches `texts` one after the other with insert_multi."""
+    ropes = [[] for _ in range(6)]
+    for t in texts:
+        insert_multi(ropes, t, so)
+    return np.array([c for r in ropes for c in r], np.uint8)
+
+
+def sorted_bwt(text, so):
+    """The same BWT by its closed form: suffix t of string S sorts by S[t:] + '$' and then by the symbols that precede
+    it, S[t-1], S[t-2], ..., under the RLO ($ACGTN) or RCLO ($TGCAN) order with the start of the string smallest; in
+    input order (so == 0) equal suffixes sort by string number (sais-ss.c)."""
+    strs = _split_strings(text)
+    keys = []
+    for i, s in enumerate(strs):
+        for t in range(len(s) + 1):
+            if so == 0:
+                tb = (i,)
+            else:
+                tb = tuple((_comp6(c) if so == 2 else c) + 1 for c in s[:t][::-1]) + (0,)
+            keys.append((tuple(s[t:]) + (0,) + tb, s[t - 1] if t > 0 else 0))
+    keys.sort(key=lambda kv: kv[0])
+    return np.array([kv[1] for kv in keys], np.uint8)

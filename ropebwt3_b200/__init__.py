@@ -77,6 +77,18 @@ class Index:
         capi.check(x._L.rb3b_restore(x.h, fn.encode()))
         return x
 
+    def set_order(self, so):
+        """mr_init's sorting order: 0 input order, 1 RLO, 2 RCLO (mrope.h:6-8)."""
+        capi.check(self._L.rb3b_index_set_order(self.h, int(so)))
+
+    def get_order(self):
+        return int(self._L.rb3b_index_get_order(self.h))
+
+    def insert_multi(self, text):
+        """mr_insert_multi (mrope.c:300): insert the 0-terminated strings of `text` in the index's sorting order."""
+        t = _u8(text)
+        capi.check(self._L.rb3b_insert_multi(self.h, len(t), capi.ptr(t)))
+
     def reserve(self, n_symbols):
         """Size hint: the index will grow to about n_symbols (avoids regrowing device buffers merge after merge)."""
         capi.check(self._L.rb3b_index_reserve(self.h, int(n_symbols)))
@@ -168,6 +180,19 @@ def rb3_build_sais(text):
     out = np.empty_like(t)
     capi.check(capi.lib().rb3b_build_bwt(len(t), capi.ptr(t), capi.ptr(out)))
     return out
+
+
+def build_bwt_so(text, so):
+    """BWT of the batch in input (0), RLO (1) or RCLO (2) order (what mr_insert_multi builds on an empty rope)."""
+    t = _u8(text)
+    out = np.empty_like(t)
+    capi.check(capi.lib().rb3b_build_bwt_so(len(t), capi.ptr(t), int(so), capi.ptr(out)))
+    return out
+
+
+def mr_insert_multi(mr, text, is_thr=0):
+    """mrope.c:300-385.  `text`: the reads as read (not reversed)."""
+    mr.insert_multi(text)
 
 
 def fmd_image(sym, ln):

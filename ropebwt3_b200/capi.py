@@ -27,6 +27,12 @@ SIGNATURES = {
     "rb3b_index_create": (_vp, []),
     "rb3b_index_destroy": (None, [_vp]),
     "rb3b_index_reserve": (_int, [_vp, _i64]),
+    "rb3b_index_set_order": (_int, [_vp, _int]),
+    "rb3b_index_get_order": (_int, [_vp]),
+    "rb3b_insert_multi": (_int, [_vp, _i64, _vp]),
+    "rb3b_insert_multi_dev": (_int, [_vp, _i64, _vp]),
+    "rb3b_build_bwt_so": (_int, [_i64, _vp, _int, _vp]),
+    "rb3b_build_bwt_so_dev": (_int, [_i64, _vp, _int, _vp]),
     "rb3b_index_from_plain": (_int, [_vp, _i64, _vp]),
     "rb3b_index_from_plain_dev": (_int, [_vp, _i64, _vp]),
     "rb3b_index_from_runs": (_int, [_vp, _i64, _vp, _vp]),

@@ -24,7 +24,7 @@
 
 static inline unsigned nblk(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
-__global__ void k_kmer_keys(uint32_t n, const uint8_t *__restrict__ T, uint64_t *__restrict__ key, uint32_t *__restrict__ idx, int *__restrict__ bad)
+__global__ void k_kmer_keys(uint32_t n, const uint8_t *__restrict__ T, int n_sym, uint64_t *__restrict__ key, uint32_t *__restrict__ idx, int *__restrict__ bad)
 {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -33,7 +33,7 @@ __global__ void k_kmer_keys(uint32_t n, const uint8_t *__restrict__ T, uint64_t 
 	for (int j = 0; j < KMER; ++j) {
 		uint32_t p = i + j;
 		int c = (!ended && p < n) ? T[p] : 0;
-		if (c >= RB3B_ASIZE) { *bad = 1; c = 5; }
+		if (c >= n_sym) { *bad = 1; c = 5; }
 		k = k << 3 | (uint64_t)c;
 		if (c == 0) ended = 1;
 	}
@@ -99,7 +99,7 @@ static int scan_max_u32(uint32_t *d, uint32_t n)
 }
 
 /* suffix array of the batch (generalised, sentinel order by position) into sa[len] (device, uint32) */
-static int suffix_sort(int64_t len, const uint8_t *d_text, DBuf<uint32_t> &sa)
+static int suffix_sort(int64_t len, const uint8_t *d_text, DBuf<uint32_t> &sa, int n_sym = RB3B_ASIZE)
 {
 	if (len >= (1LL << 32) - 2) return rb3b_fail(RB3B_EINVAL, "batches of 2^32 symbols or more are not supported by the device suffix sorter yet");
 	uint32_t n = (uint32_t)len;
@@ -113,7 +113,7 @@ static int suffix_sort(int64_t len, const uint8_t *d_text, DBuf<uint32_t> &sa)
 	DBuf<unsigned long long> amb;
 	TRY(key0.alloc(n)); TRY(key1.alloc(n)); TRY(idx0.alloc(n)); TRY(sa.alloc(n)); TRY(rank.alloc(n)); TRY(head.alloc(n)); TRY(bad.alloc(1)); TRY(amb.alloc(1));
 	CK(cudaMemsetAsync(bad.p, 0, sizeof(int), rb3b_stream));
-	k_kmer_keys<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, d_text, key0.p, idx0.p, bad.p); CKK();
+	k_kmer_keys<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, d_text, n_sym, key0.p, idx0.p, bad.p); CKK();
 	int rounds = 0;
 	for (uint64_t h = KMER;; h <<= 1) {
 		TRY(sort_pairs(key0.p, key1.p, idx0.p, sa.p, n, 64));
@@ -163,6 +163,122 @@ extern "C" int rb3b_build_bwt(int64_t len, const uint8_t *text, uint8_t *bwt_out
 	TRY(t.alloc(len)); TRY(b.alloc(len));
 	CK(cudaMemcpyAsync(t.p, text, len, cudaMemcpyHostToDevice, rb3b_stream));
 	TRY(rb3b_build_bwt_dev(len, t.p, b.p));
+	CK(cudaMemcpyAsync(bwt_out, b.p, len, cudaMemcpyDeviceToHost, rb3b_stream));
+	CK(cudaStreamSynchronize(rb3b_stream));
+	return RB3B_OK;
+}
+
+/* ---- BWT of a batch in RLO / RCLO order (build -s / -r; mr_insert_multi, mrope.c:300-385) ---- */
+/*
+ * The reference inserts the reads of a batch column by column (BCR); strings that share the suffix inserted so far
+ * are kept as one SA interval and ordered by the symbol inserted next -- '$' first, then A,C,G,T (RLO) or T,G,C,A
+ * (RCLO), then N (mrope.c:244-265).  The resulting order is canonical: suffix t of string S sorts by
+ *     S[t..) '$'  followed by  S[t-1], S[t-2], ..., S[0], <start of string>
+ * with the second half compared under the RLO/RCLO symbol order and the start of the string smallest.  Equal suffixes
+ * have equal length, so this is the plain suffix order of the augmented string  S '$' rev(S) 0  (symbols shifted up
+ * by one, 0 = terminator): one device suffix sort of a text twice as long replaces the max-read-length BCR rounds.
+ */
+__global__ void k_zero_flags(int64_t len, const uint8_t *__restrict__ T, int64_t *__restrict__ flag)
+{
+	int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q < len) flag[q] = T[q] == 0;
+}
+
+__global__ void k_zero_pos(int64_t len, const uint8_t *__restrict__ T, const int64_t *__restrict__ sid, int64_t *__restrict__ Z)
+{
+	int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q < len && T[q] == 0) Z[sid[q]] = q;
+}
+
+/* U = augmented text (2 * len symbols), emit[p] = BWT symbol of the suffix of U starting at p when that suffix stands
+ * for a suffix of the batch (first half of an augmented string), 255 otherwise */
+__global__ void k_augment(int64_t len, const uint8_t *__restrict__ T, const int64_t *__restrict__ sid, const int64_t *__restrict__ Z, int so,
+                          uint8_t *__restrict__ U, uint8_t *__restrict__ emit, int *__restrict__ bad)
+{
+	int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= len) return;
+	const int64_t i = sid[q], s = i ? Z[i - 1] + 1 : 0, e = Z[i], L = e - s, base = 2 * s, o = q - s;
+	if (q < e) {
+		int c = T[q];
+		if (c >= RB3B_ASIZE) { *bad = 1; c = 5; }
+		const int pc = (so == 2 && c >= 1 && c <= 4) ? 5 - c : c; /* rope_comp6, mrope.c:224 */
+		U[base + o] = (uint8_t)(c + 1); emit[base + o] = o == 0 ? 0 : T[q - 1];
+		const int64_t r = base + L + 1 + (e - 1 - q);
+		U[r] = (uint8_t)(pc + 1); emit[r] = 255;
+	} else {
+		U[base + L] = 1; emit[base + L] = L > 0 ? T[e - 1] : 0;
+		U[base + 2 * L + 1] = 0; emit[base + 2 * L + 1] = 255;
+	}
+}
+
+__global__ void k_emit_flags(int64_t n, const uint32_t *__restrict__ sa, const uint8_t *__restrict__ emit, int64_t *__restrict__ flag)
+{
+	int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j < n) flag[j] = emit[sa[j]] != 255;
+}
+
+__global__ void k_emit_bwt(int64_t n, const uint32_t *__restrict__ sa, const uint8_t *__restrict__ emit, const int64_t *__restrict__ dst, uint8_t *__restrict__ bwt)
+{
+	int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	const uint8_t c = emit[sa[j]];
+	if (c != 255) bwt[dst[j]] = c;
+}
+
+extern "C" int rb3b_build_bwt_so_dev(int64_t len, const uint8_t *d_text, int so, uint8_t *d_bwt_out)
+{ /* declared in include/rb3_b200.h */
+	if (so == 0) return rb3b_build_bwt_dev(len, d_text, d_bwt_out);
+	ApiScope scope_;
+	TRY(rb3b_ensure_init());
+	if (so < 0 || so > 2) return rb3b_fail(RB3B_EINVAL, "sorting order must be 0, 1 (RLO) or 2 (RCLO)");
+	if (len <= 0) return rb3b_fail(RB3B_EINVAL, "empty batch");
+	uint8_t last = 1;
+	CK(cudaMemcpyAsync(&last, d_text + len - 1, 1, cudaMemcpyDeviceToHost, rb3b_stream));
+	CK(cudaStreamSynchronize(rb3b_stream));
+	if (last != 0) return rb3b_fail(RB3B_EINVAL, "the batch text must end with a sentinel (mrope.c:310 asserts the same)");
+	DBuf<int64_t> flag, sid, Z;
+	DBuf<uint8_t> U, emit;
+	DBuf<uint32_t> sa;
+	DBuf<int> bad;
+	int hbad = 0;
+	TRY(flag.alloc(2 * len)); TRY(sid.alloc(2 * len)); TRY(U.alloc(2 * len)); TRY(emit.alloc(2 * len)); TRY(bad.alloc(1));
+	CK(cudaMemsetAsync(bad.p, 0, sizeof(int), rb3b_stream));
+	rb3b_tic(T_BWT);
+	k_zero_flags<<<nblk(len, TPB), TPB, 0, rb3b_stream>>>(len, d_text, flag.p); CKK();
+	TRY(rb3b_scan_excl_i64(flag.p, sid.p, len));
+	int64_t n_seq = 0;
+	CK(cudaMemcpyAsync(&n_seq, sid.p + len - 1, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+	CK(cudaStreamSynchronize(rb3b_stream));
+	++n_seq; /* the last symbol is a sentinel */
+	TRY(Z.alloc(n_seq));
+	k_zero_pos<<<nblk(len, TPB), TPB, 0, rb3b_stream>>>(len, d_text, sid.p, Z.p); CKK();
+	k_augment<<<nblk(len, TPB), TPB, 0, rb3b_stream>>>(len, d_text, sid.p, Z.p, so, U.p, emit.p, bad.p); CKK();
+	CK(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, rb3b_stream));
+	CK(cudaStreamSynchronize(rb3b_stream));
+	if (hbad) return rb3b_fail(RB3B_EINVAL, "batch text holds a symbol >= %d", RB3B_ASIZE);
+	TRY(suffix_sort(2 * len, U.p, sa, RB3B_ASIZE + 1));
+	k_emit_flags<<<nblk(2 * len, TPB), TPB, 0, rb3b_stream>>>(2 * len, sa.p, emit.p, flag.p); CKK();
+	TRY(rb3b_scan_excl_i64(flag.p, sid.p, 2 * len));
+	DBuf<uint8_t> tmp;
+	uint8_t *dst = d_bwt_out;
+	if (d_bwt_out == d_text) { TRY(tmp.alloc(len)); dst = tmp.p; }
+	k_emit_bwt<<<nblk(2 * len, TPB), TPB, 0, rb3b_stream>>>(2 * len, sa.p, emit.p, sid.p, dst); CKK();
+	if (dst != d_bwt_out) CK(cudaMemcpyAsync(d_bwt_out, dst, len, cudaMemcpyDeviceToDevice, rb3b_stream));
+	rb3b_toc(T_BWT);
+	CK(cudaStreamSynchronize(rb3b_stream));
+	rb3b_tflush();
+	return RB3B_OK;
+}
+
+extern "C" int rb3b_build_bwt_so(int64_t len, const uint8_t *text, int so, uint8_t *bwt_out)
+{
+	ApiScope scope_;
+	TRY(rb3b_ensure_init());
+	if (len <= 0) return rb3b_fail(RB3B_EINVAL, "empty batch");
+	DBuf<uint8_t> t, b;
+	TRY(t.alloc(len)); TRY(b.alloc(len));
+	CK(cudaMemcpyAsync(t.p, text, len, cudaMemcpyHostToDevice, rb3b_stream));
+	TRY(rb3b_build_bwt_so_dev(len, t.p, so, b.p));
 	CK(cudaMemcpyAsync(bwt_out, b.p, len, cudaMemcpyDeviceToHost, rb3b_stream));
 	CK(cudaStreamSynchronize(rb3b_stream));
 	return RB3B_OK;

@@ -157,7 +157,9 @@ int rb3b_index_free_dev(rb3b_index_s *x)
 	if (x->ovf) cudaFreeAsync(x->ovf, rb3b_stream);
 	if (x->cells2) cudaFreeAsync(x->cells2, rb3b_stream);
 	if (x->ovf2) cudaFreeAsync(x->ovf2, rb3b_stream);
+	const int so = x->so; /* a property of the collection, not of the device buffers */
 	memset(x, 0, sizeof(*x));
+	x->so = so;
 	return RB3B_OK;
 }
 
@@ -362,6 +364,16 @@ extern "C" rb3b_index_t *rb3b_index_create(void)
 	memset(x, 0, sizeof(*x));
 	return x;
 }
+
+extern "C" int rb3b_index_set_order(rb3b_index_t *x, int so)
+{ /* mr_init(max_nodes, block_len, sorting_order), mrope.c:15 */
+	if (so < 0 || so > 2) return rb3b_fail(RB3B_EINVAL, "sorting order must be 0 (input), 1 (RLO) or 2 (RCLO)");
+	if (x->n > 0 && so != x->so) return rb3b_fail(RB3B_EINVAL, "the sorting order of a non-empty index cannot be changed");
+	x->so = so;
+	return RB3B_OK;
+}
+
+extern "C" int rb3b_index_get_order(const rb3b_index_t *x) { return x->so; }
 
 extern "C" int rb3b_index_reserve(rb3b_index_t *x, int64_t n_symbols)
 { /* like vector::reserve: size both ping-pong halves for an index of n_symbols so that merges never reallocate */

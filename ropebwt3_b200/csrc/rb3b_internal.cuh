@@ -56,6 +56,7 @@ struct rb3b_index_s {
 	int64_t acc[RB3B_ASIZE + 1];  /* C[] */
 	int shift;                    /* log2 of the cell span */
 	int kind;                     /* RB3B_KIND_RLE or RB3B_KIND_BM */
+	int so;                       /* order of the sentinels / of equal suffixes: 0 input order, 1 RLO, 2 RCLO (mrope.h:6-8) */
 	int64_t n_cells, n_ovf, n_entries;
 	uint4 *cells, *ovf;           /* n_cells * 8 and n_ovf * 8 quads */
 	uint4 *cells2, *ovf2;         /* the other half of the ping-pong pair: the next merge writes here */

@@ -399,6 +399,7 @@ extern "C" int rb3b_dump_fmr(const rb3b_index_t *x, const char *fn, int max_node
 	if (block_len < 64 || (block_len & 7)) return rb3b_fail(RB3B_EINVAL, "block_len must be a multiple of 8 and >= 64 (rope.c:59-61)");
 	bytes_t img;
 	fmr_encode(sym.data(), len.data(), (int64_t)sym.size(), max_nodes, block_len, img);
+	if (img.size() >= 4) img[3] = (uint8_t)x->so; /* mr_dump writes the sorting order after the magic, mrope.c:155-156 */
 	return write_file(fn, img.data(), img.size());
 }
 
@@ -429,5 +430,7 @@ extern "C" int rb3b_restore(rb3b_index_t *x, const char *fn)
 	else if (img.size() >= 4 && memcmp(img.data(), "RB\2", 3) == 0) rc = fmr_parse(img, runs);
 	else return rb3b_fail(RB3B_EFORMAT, "'%s' is neither FMD nor FMR", fn);
 	if (rc != RB3B_OK) return rc;
-	return rb3b_index_from_runs(x, (int64_t)runs.sym.size(), runs.sym.data(), runs.len.data());
+	TRY(rb3b_index_from_runs(x, (int64_t)runs.sym.size(), runs.sym.data(), runs.len.data()));
+	if (memcmp(img.data(), "RB\2", 3) == 0 && img[3] <= 2) x->so = img[3]; /* mr_restore, mrope.c:166-168; an FMD does not record the order */
+	return RB3B_OK;
 }

@@ -269,8 +269,55 @@ struct Slices {
 /* The walk kernels are written for a "ranker" WG: Grp<8> (RLE cells, 8 lanes per walk) or BmRank (bitmap cells,
  * one thread per walk). */
 
-/* round 1: every slice is walked from its first position to its last */
+/* ---- RLO / RCLO collections (build -s / -r; mr_insert_multi_aux, mrope.c:226-275) ----
+ * In a sorted collection the sentinel of a new string does not go after all old ones: rows whose suffix runs to the end
+ * of the string ("S_t $") are ordered by the symbols that PRECEDE them, '$' (start of string) first, then A,C,G,T (RLO)
+ * or T,G,C,A (RCLO), then N.  Walking a new string from its sentinel, [l,u) = rows of A with exactly the same suffix
+ * (the reference's triple64_t interval, mrope.c:216-220); l and u both advance by LF; the row goes to
+ *     ka_t = l_t + less_t + (ka_{t+1} - l_{t+1}),   less_t = #rows of A[l_t,u_t) preceded by a smaller symbol
+ * (mrope.c:247-265: the new run is placed before the existing equal symbols), i.e. ka_t = l_t + sum_{s>=t} less_s; once
+ * the interval is empty the position is exact and the ordinary walk takes over.  These "heads" are short (log_4 of the
+ * number of strings for reads) and are resolved by one walk per new string BEFORE the sliced walk, which then skips
+ * rows flagged KS_HEAD and restarts from the exact value flagged KS_SEED. */
+#define KS_HEAD (1LL << 60)
+#define KS_SEED (1LL << 59)
+
+__device__ __forceinline__ int so_rank(int so, int c) { return (so == 2 && c >= 1 && c <= 4) ? 5 - c : c; } /* rope_comp6, mrope.c:224 */
+
 template<class WG>
+__global__ void __launch_bounds__(TPB) k_so_heads(DevIndex A, int so, int64_t n_seq, const int64_t *__restrict__ chain_base, const int64_t *__restrict__ chain_len,
+                                                   const uint8_t *__restrict__ wsym, int64_t *__restrict__ kseq)
+{
+	const int gl = WG::lane();
+	const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / WG::G;
+	if (p >= n_seq) return; /* group-uniform */
+	const int64_t pos0 = chain_base[p], L = chain_len[p];
+	int64_t l = 0, u = A.acc[1], P = 0, t = 0;
+	bool ended = false;
+	while (t < L && l < u) {
+		const int c = (int)wsym[pos0 + t];
+		int64_t tl[RB3B_ASIZE], tu[RB3B_ASIZE], less = 0;
+#pragma unroll
+		for (int b = 0; b < RB3B_ASIZE; ++b) { tl[b] = WG::rank(A, l, b); tu[b] = WG::rank(A, u, b); }
+#pragma unroll
+		for (int b = 0; b < RB3B_ASIZE; ++b) if (so_rank(so, b) < so_rank(so, c)) less += tu[b] - tl[b];
+		if (gl == 0) kseq[pos0 + t] = l - P; /* + the final P = l + sum_{s >= t} less_s */
+		P += less;
+		++t;
+		if (c == 0) { ended = true; break; }
+		int64_t nl = 0, nu = 0;
+#pragma unroll
+		for (int b = 0; b < RB3B_ASIZE; ++b) if (b == c) { nl = tl[b]; nu = tu[b]; }
+		l = A.acc[c] + nl; u = A.acc[c] + nu;
+	}
+	if (gl == 0) {
+		for (int64_t s = 0; s < t; ++s) kseq[pos0 + s] = (kseq[pos0 + s] + P) | KS_HEAD;
+		if (!ended && t < L) kseq[pos0 + t] = l | KS_SEED;
+	}
+}
+
+/* round 1: every slice is walked from its first position to its last */
+template<class WG, bool SO>
 __global__ void __launch_bounds__(TPB) k_walk_first(DevIndex A, Slices S, const uint8_t *__restrict__ wsym, int64_t *__restrict__ kseq, int64_t *next_seg)
 {
 	const int gl = WG::lane(), gbase = WG::base();
@@ -283,20 +330,31 @@ __global__ void __launch_bounds__(TPB) k_walk_first(DevIndex A, Slices S, const 
 		const int64_t p0 = s * S.seg_len, n = S.slice_len(s);
 		const int c0 = s == 0 ? 0 : (int)wsym[p0 - 1]; /* the symbol that led here = first symbol of this row's suffix */
 		int64_t lo, hi, d = 0;
-		if (c0 == 0) lo = hi = A.acc[1]; /* a sentinel row: new sentinels sort after all old ones, fm-index.c:164 */
+		if (c0 == 0) lo = hi = SO ? 0 : A.acc[1]; /* a sentinel row: new sentinels sort after all old ones, fm-index.c:164 (SO: flagged rows follow) */
 		else { lo = A.acc[c0]; hi = A.acc[c0 + 1]; }
 		uint64_t w = __ldg((const uint64_t*)(wsym + p0)); /* wsym is padded: whole words can always be read */
 		for (int64_t j = 0; j < n; j += 8) {
 			const uint64_t wn = j + 8 < n ? __ldg((const uint64_t*)(wsym + p0 + j + 8)) : 0; /* the symbols do not depend on A: fetch ahead */
 			int64_t vb[8];
+			if (SO) { /* rows resolved or seeded by k_so_heads */
+#pragma unroll
+				for (int jj = 0; jj < 8; ++jj) vb[jj] = j + jj < n ? kseq[p0 + j + jj] : 0;
+			}
 #pragma unroll
 			for (int jj = 0; jj < 8; ++jj) {
 				const int c = (int)(w >> (8 * jj)) & 7;
 				const bool live = j + jj < n;
+				bool head = false;
+				if (SO) {
+					const int64_t f = vb[jj];
+					if (f & KS_HEAD) { head = true; vb[jj] = f & ~KS_HEAD; lo = hi = 0; }
+					else if (f & KS_SEED) lo = hi = f & (int64_t)RB3B_M42;
+				}
+				if (head) continue;
 				if (lo == hi) vb[jj] = lo;
 				else { vb[jj] = lo | KS_UNRES | (hi - lo <= LOG_WIDTH ? KS_NARROW : 0); d += live; }
 				if (live) {
-					if (c == 0) lo = hi = A.acc[1]; /* first symbol of the sequence (fm-index.c:170): the next position is a sentinel row */
+					if (c == 0) lo = hi = SO ? 0 : A.acc[1]; /* first symbol of the sequence (fm-index.c:170): the next position is a sentinel row */
 					else {
 						int64_t r1, r2;
 						/* the walks that currently run together take the two-position path only while one of them still
@@ -565,7 +623,7 @@ __global__ void k_check_monotone(int64_t len, const int64_t *__restrict__ ka, in
 /* everything of the rank phase that depends on the width of the batch's LF table */
 template<typename LfT, typename RowT>
 static int walk_order(int64_t len, const uint8_t *d_bwt, int64_t nt, const int64_t *tex, const Acc7 &acc, Fine &F,
-                      int64_t p_lo, int64_t p_hi, DBuf<uint8_t> &wsym, void **wrow_out)
+                      int64_t p_lo, int64_t p_hi, DBuf<uint8_t> &wsym, void **wrow_out, const int64_t **chain_base_out, const int64_t **chain_len_out)
 {
 	DBuf<LfT> lf;
 	DBuf<RowT> wrow;
@@ -596,7 +654,7 @@ static int walk_order(int64_t len, const uint8_t *d_bwt, int64_t nt, const int64
 		return rb3b_fail(RB3B_EINVAL, "batch is not the BWT of a sentinel-terminated string set (%lld of %lld rows reachable from the sentinels)",
 		                 (long long)(last[0] + last[1]), (long long)len);
 	k_write_walk<LfT, RowT><<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, len, lf.p, node, f_cof, c_base, c_len, pl.p, p_lo, p_hi, wrow.p, wsym.p); CKK();
-	*wrow_out = wrow.p;
+	*wrow_out = wrow.p; *chain_base_out = c_base; *chain_len_out = c_len; /* arena memory: lives until the API call returns */
 	return RB3B_OK;
 }
 
@@ -606,7 +664,7 @@ static int walk_order(int64_t len, const uint8_t *d_bwt, int64_t nt, const int64
  * instead of allocating (rows of other parts are set to -1).  *incomplete is set when a part could not resolve all of
  * its own rows locally (only possible with n_parts > 1). */
 static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, DBuf<int64_t> &ka, int64_t accB[RB3B_ASIZE + 1],
-                      int part = 0, int n_parts = 1, int64_t *ka_out = 0, int *incomplete = 0)
+                      int part = 0, int n_parts = 1, int64_t *ka_out = 0, int *incomplete = 0, int so = 0)
 {
 	int64_t nt = (len + PREP_TILE - 1) / PREP_TILE;
 	DBuf<int64_t> tcnt, tex;
@@ -658,9 +716,11 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	void *wrow = 0;
 	TRY(wsym.alloc(len + 16)); /* padded: the walks read whole 8-byte words */
 	const bool narrow_lf = len < LF32_MAX_LEN && !rb3b_get_param("wide_lf", 0);
-	const int64_t p_lo = S.walk_lo * seg_len - 1, p_hi = S.own_hi * seg_len; /* walk-order positions this device reads */
-	if (narrow_lf) TRY((walk_order<uint32_t, uint32_t>(len, d_bwt, nt, tex.p, acc, F, p_lo, p_hi, wsym, &wrow)));
-	else TRY((walk_order<uint64_t, int64_t>(len, d_bwt, nt, tex.p, acc, F, p_lo, p_hi, wsym, &wrow)));
+	/* walk-order positions this device reads (everything for a sorted collection: the heads are resolved on every device) */
+	const int64_t p_lo = so ? -1 : S.walk_lo * seg_len - 1, p_hi = so ? len : S.own_hi * seg_len;
+	const int64_t *c_base = 0, *c_len = 0;
+	if (narrow_lf) TRY((walk_order<uint32_t, uint32_t>(len, d_bwt, nt, tex.p, acc, F, p_lo, p_hi, wsym, &wrow, &c_base, &c_len)));
+	else TRY((walk_order<uint64_t, int64_t>(len, d_bwt, nt, tex.p, acc, F, p_lo, p_hi, wsym, &wrow, &c_base, &c_len)));
 	const int64_t n_walk = S.own_hi - S.walk_lo;
 	DBuf<int64_t> seg, wl, ctr, kseq;
 	TRY(seg.alloc(S.n_seg * 3)); TRY(wl.alloc(S.n_seg * 4)); TRY(ctr.alloc(16)); TRY(kseq.alloc(len + 8));
@@ -676,8 +736,18 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	int64_t want = (n_walk * wg + wtpb - 1) / wtpb, cap = (int64_t)n_sm() * (bm ? 32 : 8);
 	if (want < 1) want = 1;
 	rb3b_tic(T_WALK1);
-	if (bm) k_walk_first<BmRank><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
-	else k_walk_first<Grp<8> ><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
+	const unsigned wgrid = (unsigned)(want < cap ? want : cap);
+	if (so) {
+		CK(cudaMemsetAsync(kseq.p, 0, (len + 8) * 8, rb3b_stream));
+		if (bm) k_so_heads<BmRank><<<nblk(F.n_seq, TPB), TPB, 0, rb3b_stream>>>(dA, so, F.n_seq, c_base, c_len, wsym.p, kseq.p);
+		else k_so_heads<Grp<8> ><<<nblk(F.n_seq * 8, TPB), TPB, 0, rb3b_stream>>>(dA, so, F.n_seq, c_base, c_len, wsym.p, kseq.p);
+		CKK();
+		if (bm) k_walk_first<BmRank, true><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
+		else k_walk_first<Grp<8>, true><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
+	} else {
+		if (bm) k_walk_first<BmRank, false><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
+		else k_walk_first<Grp<8>, false><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
+	}
 	CKK();
 	rb3b_toc(T_WALK1);
 	int64_t *wl_seg[2] = { wl.p, wl.p + 2 * S.n_seg }, *wl_val[2] = { wl.p + S.n_seg, wl.p + 3 * S.n_seg };
@@ -837,6 +907,38 @@ extern "C" int rb3b_merge_plain_dev(rb3b_index_t *x, int64_t len, const uint8_t 
 	int64_t accB[RB3B_ASIZE + 1];
 	TRY(rank_phase(x, len, d_bwt, ka, accB));
 	return merge_phase(x, len, d_bwt, ka.p);
+}
+
+/* mr_insert_multi (mrope.c:300-385; build -2/-s/-r, build.c:214-218): insert the strings of `text` (concatenated,
+ * 0-terminated, as read -- the reference reverses them first, rb3_reverse_all) in the index's sorting order.  The BCR
+ * rounds are replaced by one device suffix sort of the batch in that order and one merge whose sentinel rows are placed
+ * by k_so_heads.  In input order (so == 0) this is exactly build + merge_plain. */
+extern "C" int rb3b_insert_multi_dev(rb3b_index_t *x, int64_t len, const uint8_t *d_text)
+{
+	ApiScope scope_;
+	TRY(rb3b_ensure_init());
+	if (len <= 0) return RB3B_OK;
+	DBuf<uint8_t> bwt;
+	TRY(bwt.alloc(len));
+	TRY(rb3b_build_bwt_so_dev(len, d_text, x->so, bwt.p));
+	if (x->n_cells == 0) return rb3b_index_from_plain_dev(x, len, bwt.p);
+	DBuf<int64_t> ka;
+	int64_t accB[RB3B_ASIZE + 1];
+	TRY(rank_phase(x, len, bwt.p, ka, accB, 0, 1, 0, 0, x->so));
+	return merge_phase(x, len, bwt.p, ka.p);
+}
+
+extern "C" int rb3b_insert_multi(rb3b_index_t *x, int64_t len, const uint8_t *text)
+{
+	ApiScope scope_;
+	TRY(rb3b_ensure_init());
+	DBuf<uint8_t> d;
+	if (len <= 0) return RB3B_OK;
+	TRY(d.alloc(len));
+	CK(cudaMemcpyAsync(d.p, text, len, cudaMemcpyHostToDevice, rb3b_stream));
+	TRY(rb3b_insert_multi_dev(x, len, d.p));
+	CK(cudaStreamSynchronize(rb3b_stream));
+	return RB3B_OK;
 }
 
 extern "C" int rb3b_merge_plain(rb3b_index_t *x, int64_t len, const uint8_t *bwt)

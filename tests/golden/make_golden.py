@@ -111,6 +111,48 @@ def long_runs():
     np.savez_compressed(os.path.join(OUT, "long_runs.npz"), sym=sym, len=ln, fmd=u8(fmd), fmr=fmr, q_k=k, q_ok=ok, q_ret=ret, q_ret_fmd=ret2)
 
 
+def rb2_set():
+    """build -2 / -s / -r (ropebwt2 insertion, mr_insert_multi): reads with errors, Ns, exact duplicates and reads that
+    are suffixes / prefixes of other reads; one batch and several batches (-m); outputs of the reference CLI."""
+    rng = np.random.default_rng(46)
+    anc = rng.integers(1, 5, 3000).astype(np.uint8)
+    reads = []
+    for _ in range(400):
+        s = int(rng.integers(0, len(anc) - 60))
+        r = anc[s:s + int(rng.integers(20, 61))].copy()
+        m = rng.random(len(r)) < 0.01
+        r[m] = rng.integers(1, 6, int(m.sum()))
+        reads.append(r)
+    reads += [reads[3].copy(), reads[3][7:].copy(), reads[11][:-5].copy(), reads[3].copy(), reads[200].copy()]
+    lines = [O.to_ascii(r) for r in reads]
+    inp = ("\n".join(lines) + "\n").encode()
+    batch_m = 6000
+    d = {"lines": u8(inp), "batch_m": np.int64(batch_m)}
+    # the batches rb3_seq_read forms with -m (io.c:114,119: a batch closes after the record that exceeds -m)
+    bounds, n = [0], 0
+    for i, l in enumerate(lines):
+        n += 2 * len(l) + 2
+        if n > batch_m:
+            bounds.append(i + 1)
+            n = 0
+    if bounds[-1] != len(lines):
+        bounds.append(len(lines))
+    d["batch_bounds"] = np.array(bounds, np.int64)
+    first = ("\n".join(lines[:bounds[1]]) + "\n").encode()
+    asc = np.zeros(256, np.uint8)
+    for i, ch in enumerate(b"$ACGTN"):
+        asc[ch] = i
+    for so, flag in [(0, "-2"), (1, "-s"), (2, "-r")]:
+        one = R.run(["build", "-L", flag, "-"], stdin=inp)
+        many = R.run(["build", "-L", flag, "-m", str(batch_m), "-"], stdin=inp)
+        assert one == many
+        d["bwt_so%d" % so] = asc[u8(one.strip())]
+        d["first_so%d" % so] = asc[u8(R.run(["build", "-L", flag, "-"], stdin=first).strip())]
+        d["fmd_so%d" % so] = u8(R.run(["build", "-L", "-d", flag, "-m", str(batch_m), "-"], stdin=inp))
+    d["fmr_so2"] = u8(R.run(["build", "-L", "-b", "-r", "-"], stdin=inp))
+    np.savez_compressed(os.path.join(OUT, "rb2.npz"), **d)
+
+
 if __name__ == "__main__":
     assert R.available(), "build the reference first: make -C oracle ref"
     toy()
@@ -119,5 +161,6 @@ if __name__ == "__main__":
     merge_set("merge_dup", 4, 2500, 45, 0.0, 0.0)          # exact duplicates: the walk never collapses
     reads_set()
     long_runs()
+    rb2_set()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -109,5 +109,46 @@ def test_error_behaviour(files):
     assert p.returncode == 1 and b"failed to open file" in p.stderr
     p = run(CLI, ["build", "-d", "/nonexistent.fa"] + files["fa"][:1], check=False)                           # bad file skipped, rest built
     assert p.returncode == 0 and p.stdout == run(files["ref"], ["build", "-d"] + files["fa"][:1]).stdout
-    assert run(CLI, ["build", "-r", files["multi"]], check=False).returncode == 1                             # documented scope limit
+    assert run(CLI, ["build", "-T", files["multi"]], check=False).returncode == 1                             # documented scope limit
     assert run(CLI, ["build"], check=False).returncode == 1
+
+
+@pytest.mark.parametrize("flag", ["-2", "-s", "-r"])
+def test_ropebwt2_insertion_orders(files, flag):
+    """build -2/-s/-r (mr_insert_multi): reads in one batch and in many (-m), FASTQ, both strands, and
+    appending to an index written in that order; plain output and .fmd equal the reference CLI's."""
+    d = files["dir"]
+    assert run(CLI, ["build", flag, files["fq"]]).stdout == run(files["ref"], ["build", flag, files["fq"]]).stdout
+    want = run(files["ref"], ["build", flag, "-d", "-m", "9k", files["fq"]]).stdout
+    assert run(CLI, ["build", flag, "-d", "-m", "9k", files["fq"]]).stdout == want
+    assert run(CLI, ["build", flag, "-d", files["fq"]]).stdout == want
+    toy = b"AGG\nAGC\n"
+    assert run(CLI, ["build", "-L", flag, "-"], stdin=toy).stdout == {"-2": b"GTCT$$G$CGGA$ACC\n", "-s": b"CGTT$$G$CGGA$ACC\n", "-r": b"TTGC$$G$GCGA$ACC\n"}[flag]
+    # -i keeps the order recorded in the .fmr (mr->so); the reference can continue from our file and we from its
+    mine, theirs = str(d / ("rb2%s.fmr" % flag)), str(d / ("rb2%s.ref.fmr" % flag))
+    run(CLI, ["build", flag, "-b", "-o", mine, files["fq"]])
+    open(theirs, "wb").write(run(files["ref"], ["build", flag, "-b", files["fq"]]).stdout)
+    more = files["fa"][0]
+    want2 = run(files["ref"], ["build", flag, "-d", files["fq"], more]).stdout
+    assert run(CLI, ["build", flag, "-d", "-i", mine, more]).stdout == want2
+    assert run(CLI, ["build", flag, "-d", "-i", theirs, more]).stdout == want2
+    assert run(files["ref"], ["build", flag, "-d", "-i", mine, more]).stdout == want2
+
+
+def test_config0_reads_rclo(files, oracle):
+    """BASELINE.json configs[0]: `build -r` of 10k synthetic 150 bp reads (0.5% errors incl. N) -- here against the
+    reference binary at the full size."""
+    d = files["dir"]
+    rng = np.random.default_rng(42)
+    anc = rng.integers(1, 5, 100000).astype(np.uint8)
+    fn = str(d / "c0.txt")
+    with open(fn, "w") as f:
+        for _ in range(10000):
+            s0 = int(rng.integers(0, len(anc) - 150))
+            r = anc[s0:s0 + 150].copy()
+            m = rng.random(150) < 0.005
+            r[m] = rng.integers(1, 6, int(m.sum()))
+            f.write(oracle.to_ascii(r) + "\n")
+    want = run(files["ref"], ["build", "-r", "-L", "-t1", "-d", fn]).stdout
+    assert run(CLI, ["build", "-r", "-L", "-t1", "-d", fn]).stdout == want
+    assert run(CLI, ["build", "-r", "-L", "-d", "-m", "500k", fn]).stdout == want

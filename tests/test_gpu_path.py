@@ -424,3 +424,70 @@ def test_against_reference_binary_midsize(rb3, oracle):
         idx.dump_fmd(out)
         got = open(out, "rb").read()
         assert got == want, "fmd differs from the reference: %d vs %d bytes" % (len(got), len(want))
+
+
+# ---------------------------------------------------------------- ropebwt2 insertion order (build -2/-s/-r)
+
+def _rb2_batches(oracle, g):
+    lines = bytes(g["lines"]).decode().split()
+    b = [int(x) for x in g["batch_bounds"]]
+    return lines, [oracle.encode_batch(lines[b[i]:b[i + 1]]) for i in range(len(b) - 1)]
+
+
+@pytest.mark.parametrize("so", [0, 1, 2])
+def test_build_bwt_sorted_orders(rb3, oracle, golden, so):
+    """BWT of one batch in input / RLO / RCLO order == what the reference's mr_insert_multi builds on an empty rope."""
+    g = golden("rb2")
+    lines, batches = _rb2_batches(oracle, g)
+    assert np.array_equal(rb3.build_bwt_so(batches[0], so), g["first_so%d" % so])
+    assert np.array_equal(rb3.build_bwt_so(oracle.encode_batch(lines), so), g["bwt_so%d" % so])
+    toy = oracle.encode_batch(["AGG", "AGC"])
+    assert oracle.to_ascii(rb3.build_bwt_so(toy, so)) == ["GTCT$$G$CGGA$ACC", "CGTT$$G$CGGA$ACC", "TTGC$$G$GCGA$ACC"][so]
+
+
+@pytest.mark.parametrize("so", [0, 1, 2])
+@pytest.mark.parametrize("seg_len", [16, 512])
+def test_insert_multi_batches(rb3, oracle, golden, so, seg_len):
+    """mr_insert_multi batch after batch (build -2/-s/-r -m ...): the index after every batch equals the reference
+    algorithm's (oracle BCR restatement), the final one the reference CLI's output and .fmd."""
+    g = golden("rb2")
+    lines, batches = _rb2_batches(oracle, g)
+    rb3.set_param("seg_len", seg_len)
+    try:
+        idx = rb3.Index()
+        idx.set_order(so)
+        ropes = [[] for _ in range(6)]
+        for i, t in enumerate(batches):
+            rb3.mr_insert_multi(idx, t)
+            if i < 3:
+                oracle.insert_multi(ropes, t, so)
+                s0, l0 = oracle.plain2runs(np.array([c for r in ropes for c in r], np.uint8))
+                s, l = runs_of(idx, oracle)
+                assert np.array_equal(s, s0) and np.array_equal(l, l0), (so, i)
+        s, l = runs_of(idx, oracle)
+        assert np.array_equal(oracle.runs2plain(s, l), g["bwt_so%d" % so])
+        assert rb3.fmd_image(s, l) == bytes(g["fmd_so%d" % so])
+        assert idx.get_order() == so
+    finally:
+        rb3.set_param("seg_len", 512)
+
+
+def test_insert_multi_duplicates_and_order_in_fmr(rb3, oracle, golden, tmp_path):
+    """Inserting the same reads again (every new string equals an old one: the sorted-order heads run to the start of the
+    string) and the sorting order surviving an .fmr round trip."""
+    g = golden("rb2")
+    lines, batches = _rb2_batches(oracle, g)
+    for so in (1, 2):
+        idx = rb3.Index()
+        idx.set_order(so)
+        rb3.mr_insert_multi(idx, batches[0])
+        fn = str(tmp_path / ("x%d.fmr" % so))
+        idx.dump_fmr(fn)
+        idx2 = rb3.Index.restore(fn)
+        assert idx2.get_order() == so
+        rb3.mr_insert_multi(idx2, batches[0])
+        rb3.mr_insert_multi(idx2, batches[1])
+        want = oracle.rb2_bwt([batches[0], batches[0], batches[1]], so)
+        s, l = runs_of(idx2, oracle)
+        assert np.array_equal(oracle.runs2plain(s, l), want)
+    assert oracle.fmr_decode(bytes(g["fmr_so2"]))[3][0] == 2  # the reference writes the order there too

@@ -125,3 +125,38 @@ def test_live_reference_differential(oracle):
         os.unlink(t.name)
         fmd_ref = rope.to_fmd()
         assert r2.to_fmd() == fmd_ref == oracle.fmd_encode(sym, ln)
+
+
+# ---------------------------------------------------------------- ropebwt2 insertion (build -2/-s/-r)
+
+def _rb2_batches(oracle, g):
+    lines = bytes(g["lines"]).decode().split()
+    b = [int(x) for x in g["batch_bounds"]]
+    return lines, [oracle.encode_batch(lines[b[i]:b[i + 1]]) for i in range(len(b) - 1)]
+
+
+@pytest.mark.parametrize("so", [0, 1, 2])
+def test_rb2_insert_multi_against_golden(oracle, golden, so):
+    """mr_insert_multi restated (BCR rounds on plain lists) == the reference CLI's `build -2/-s/-r`, for the first batch
+    and for the whole multi-batch build; and == the closed form (one sort) the CUDA path uses."""
+    g = golden("rb2")
+    lines, batches = _rb2_batches(oracle, g)
+    ropes = [[] for _ in range(6)]
+    oracle.insert_multi(ropes, batches[0], so)
+    assert np.array_equal(np.array([c for r in ropes for c in r], np.uint8), g["first_so%d" % so])
+    assert np.array_equal(oracle.sorted_bwt(batches[0], so), g["first_so%d" % so])
+    for t in batches[1:]:
+        oracle.insert_multi(ropes, t, so)
+    final = np.array([c for r in ropes for c in r], np.uint8)
+    assert np.array_equal(final, g["bwt_so%d" % so])
+    assert np.array_equal(oracle.sorted_bwt(oracle.encode_batch(lines), so), g["bwt_so%d" % so])
+    sym, ln = oracle.plain2runs(final)
+    assert oracle.fmd_encode(sym, ln) == bytes(g["fmd_so%d" % so])
+
+
+def test_rb2_toy_known_answers(oracle, golden):
+    g = golden("toy")
+    seqs = txt(g["agg_Ls_in"]).split()
+    for key, so in [("agg_L", 0), ("agg_Ls", 1), ("agg_Lr", 2)]:
+        assert oracle.to_ascii(oracle.rb2_bwt([oracle.encode_batch(seqs)], so)) == txt(g[key + "_out"]).strip()
+    assert txt(g["agg_Lr_out"]) == "TTGC$$G$GCGA$ACC\n" and txt(g["agg_Ls_out"]) == "CGTT$$G$CGGA$ACC\n"  # SURVEY 4.4
