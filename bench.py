@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--seg-len", type=int, default=0)
     ap.add_argument("--genomes-per-merge", type=int, default=0,
                     help="genomes per batch (one batch = one partial BWT = one merge); default: the number of GPUs, i.e. weak scaling")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: CPU seconds all steps together may take")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-rank-bench", action="store_true")
@@ -427,7 +428,7 @@ def run_reference(a):
     t0 = time.time()
     rope.merge_plain(bwt, cores)
     rate = len(probe) / (time.time() - t0)
-    frag = int(max(20_000, min(a.genome_len, rate * 150.0 / (a.steps + a.warmup) / G)))
+    frag = int(max(20_000, min(a.genome_len, rate * a.ref_budget_s / (a.steps + a.warmup) / G)))
     times, nb = [], 0
     for i in range(a.warmup + a.steps):
         pieces = [rest[(i * G + j + 1) % len(rest)][:frag] for j in range(G)]
@@ -442,8 +443,8 @@ def run_reference(a):
     rope.close()
     tot = sum(times)
     val = nb / tot
-    sample = "each step = rb3_fmi_merge_plain(n_threads=%d) of %.2f Mb prefixes of the next %d genome(s) (both strands, %d symbols) into the reference's own index (first %d genomes + earlier steps); sized from a 100 kb probe so that %d steps take ~150 s" % (
-        cores, frag / 1e6, G, G * (2 * frag + 2), n0, a.steps + a.warmup)
+    sample = "each step = rb3_fmi_merge_plain(n_threads=%d) of %.2f Mb prefixes of the next %d genome(s) (both strands, %d symbols) into the reference's own index (first %d genomes + earlier steps); sized from a 100 kb probe so that %d steps take ~%d s" % (
+        cores, frag / 1e6, G, G * (2 * frag + 2), n0, a.steps + a.warmup, int(a.ref_budget_s))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": tot * 1e3 / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/int64", "data": "synthetic", "config": config_of(a, {"sample_bases_per_step": frag * G}),

@@ -237,8 +237,15 @@ int main(int argc, char *argv[])
 		}
 		r->is_line = is_line; r->last = -2;
 		while (!eof) {
-			int64_t n_seq = 0;
+			int64_t n_seq = 0, acc[7], fit;
 			seq.l = 0;
+			/* clamp the batch to what the device can sort and merge next to the current index; the output does not
+			 * depend on the batching */
+			fit = rb3b_max_batch_symbols(idx ? rb3b_get_acc(idx, acc) : 0);
+			if (fit > 0 && (batch <= 0 || batch > fit)) {
+				LOG("batch size limited to %ld symbols by device memory", (long)fit);
+				batch = fit;
+			}
 			while (rd_record(r, &rec, &tmp) == 0) {
 				seq_add(&seq, &rec, !no_for, !no_rev, &n_seq);
 				if (batch > 0 && (int64_t)seq.l > batch) break; /* io.c:114,119 */

@@ -131,6 +131,10 @@ int rb3b_build_bwt_dev(int64_t len, const uint8_t *d_text, uint8_t *d_bwt_out);
 int rb3b_build_bwt_so(int64_t len, const uint8_t *text, int sorting_order, uint8_t *bwt_out);
 int rb3b_build_bwt_so_dev(int64_t len, const uint8_t *d_text, int sorting_order, uint8_t *d_bwt_out);
 
+/* Largest batch (in symbols) that fits the device next to an index of index_symbols: lets a caller clamp -m (build.c:39,
+ * default 7G) to the device.  The .fmd is the same for any batching. */
+int64_t rb3b_max_batch_symbols(int64_t index_symbols);
+
 /* ---- device memory helpers for callers without a CUDA runtime of their own -- */
 void *rb3b_dev_alloc(int64_t bytes);
 void  rb3b_dev_free(void *p);

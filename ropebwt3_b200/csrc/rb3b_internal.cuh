@@ -183,6 +183,7 @@ static __device__ __noinline__ uint32_t rb3b_ovf_count(const uint4 *__restrict__
  */
 template<int G_> struct Grp {
 	static const int G = G_;
+	static const bool ALWAYS2 = false;
 	static const int NQ = 8 / G;
 	__device__ __forceinline__ static int lane() { return threadIdx.x & (G - 1); }
 	__device__ __forceinline__ static int base() { return threadIdx.x & 31 & ~(G - 1); }
@@ -346,6 +347,7 @@ __device__ __forceinline__ uint32_t rb3b_bm_popc_below(const uint4 p, uint32_t o
 /* one thread per query */
 struct BmRank {
 	static const int G = 1;
+	static const bool ALWAYS2 = false;
 	__device__ __forceinline__ static int lane() { return 0; }
 	__device__ __forceinline__ static int base() { return threadIdx.x & 31; }
 	__device__ __forceinline__ static unsigned mask() { return 1u << (threadIdx.x & 31); }
@@ -372,6 +374,25 @@ struct BmRank {
 		int64_t q1 = k1 < x.n ? k1 : x.n - 1, q2 = k2 < x.n ? k2 : x.n - 1, t = x.tot[c];
 		r1 = count(x, q1, c); r2 = count(x, q2, c);
 		r1 = k1 < x.n ? r1 : t; r2 = k2 < x.n ? r2 : t;
+	}
+};
+
+/* two lanes per walk: while a walk carries a bracket [lo,hi] the even lane ranks lo and the odd lane hi, so that each
+ * lane executes the instruction stream of ONE rank per step (the walk is bound by the instruction latency of the few
+ * resident warps, not by bandwidth); for an exact walk both lanes load the same cell, which the LSU merges */
+struct BmPair {
+	static const int G = 2;
+	static const bool ALWAYS2 = true;
+	__device__ __forceinline__ static int lane() { return threadIdx.x & 1; }
+	__device__ __forceinline__ static int base() { return threadIdx.x & 30; }
+	__device__ __forceinline__ static unsigned mask() { return 3u << (threadIdx.x & 30); }
+	__device__ __forceinline__ static int64_t rank(const DevIndex &x, int64_t k, int c) { return BmRank::rank(x, k, c); }
+	__device__ __forceinline__ static void rank2(const DevIndex &x, int64_t k1, int64_t k2, int c, int64_t &r1, int64_t &r2)
+	{
+		const int odd = threadIdx.x & 1;
+		const int64_t mine = BmRank::rank(x, odd ? k2 : k1, c);
+		const int64_t other = __shfl_xor_sync(mask(), mine, 1);
+		r1 = odd ? other : mine; r2 = odd ? mine : other;
 	}
 };
 

@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(TPB) k_walk_first(DevIndex A, Slices S, const 
 						/* the walks that currently run together take the two-position path only while one of them still
 						 * carries a bracket; either path is correct for an exact walk, so this is purely a cost choice
 						 * (a private per-thread branch was measured slower: the two paths serialise) */
-						if (__any_sync(__activemask(), lo != hi)) WG::rank2(A, lo, hi, c, r1, r2);
+						if (WG::ALWAYS2 || __any_sync(__activemask(), lo != hi)) WG::rank2(A, lo, hi, c, r1, r2);
 						else r1 = r2 = WG::rank(A, lo, c);
 						lo = A.acc[c] + r1; hi = A.acc[c] + r2;
 					}
@@ -731,8 +731,9 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	if (n_parts > 1) CK(cudaMemsetAsync(ka.p, 0xff, len * 8, rb3b_stream));
 	DevIndex dA = rb3b_dev_view(A);
 	const bool bm = A->kind == RB3B_KIND_BM;
-	/* bitmap walks are single threads: small CTAs spread the walks over all SMs */
-	const int wg = bm ? 1 : 8, wtpb = bm ? 32 : TPB;
+	/* bitmap walks are lane pairs (single threads in the fix-up): small CTAs spread the walks over all SMs */
+	const bool pair = bm && rb3b_get_param("walk_pair", 1) != 0;
+	const int wg = bm ? (pair ? 2 : 1) : 8, wtpb = bm ? 32 : TPB;
 	int64_t want = (n_walk * wg + wtpb - 1) / wtpb, cap = (int64_t)n_sm() * (bm ? 32 : 8);
 	if (want < 1) want = 1;
 	rb3b_tic(T_WALK1);
@@ -742,10 +743,12 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 		if (bm) k_so_heads<BmRank><<<nblk(F.n_seq, TPB), TPB, 0, rb3b_stream>>>(dA, so, F.n_seq, c_base, c_len, wsym.p, kseq.p);
 		else k_so_heads<Grp<8> ><<<nblk(F.n_seq * 8, TPB), TPB, 0, rb3b_stream>>>(dA, so, F.n_seq, c_base, c_len, wsym.p, kseq.p);
 		CKK();
-		if (bm) k_walk_first<BmRank, true><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
+		if (pair) k_walk_first<BmPair, true><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
+		else if (bm) k_walk_first<BmRank, true><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
 		else k_walk_first<Grp<8>, true><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
 	} else {
-		if (bm) k_walk_first<BmRank, false><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
+		if (pair) k_walk_first<BmPair, false><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
+		else if (bm) k_walk_first<BmRank, false><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
 		else k_walk_first<Grp<8>, false><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
 	}
 	CKK();

@@ -224,13 +224,13 @@ def test_bitmap_to_rle_transition(rb3, oracle, golden):
         rb3.set_param("bitmap_max_symbols", 24000000000)
 
 
-@pytest.mark.parametrize("knob,value", [("fix_log", 0), ("wide_lf", 1), ("fine_len", 7), ("fine_len", 1), ("scatter_win_bits", 5)])
+@pytest.mark.parametrize("knob,value", [("fix_log", 0), ("wide_lf", 1), ("fine_len", 7), ("fine_len", 1), ("scatter_win_bits", 5), ("walk_pair", 0)])
 def test_optional_code_paths(rb3, oracle, golden, knob, value):
     """The tuning knobs select other kernels (multi-round fix-up without the tables, 64-bit LF table and rows, other mark
     spacing, the two-pass bucketed scatter of large batches); every one of them must give the reference's interleave
     array and merged index."""
     g = golden("merge_dup")
-    defaults = {"fix_log": 1, "wide_lf": 0, "fine_len": 32, "scatter_win_bits": 19}
+    defaults = {"fix_log": 1, "wide_lf": 0, "fine_len": 32, "scatter_win_bits": 19, "walk_pair": 1}
     rb3.set_param(knob, value)
     if knob == "scatter_win_bits":
         rb3.set_param("scatter_bucket_min", 1)
