@@ -30,7 +30,8 @@ METRIC = "bases/sec indexed (build)"
 UNIT = "bases/s"
 GENOME_LEN = 5_000_000
 SEED = 43  # 42 + config index
-LF_STEP_BYTES = 160  # 128-B index cell + 8 B query + 8 B result + 8 B LF_B read + 8 B ka write
+LF_STEP_BYTES = 160  # SURVEY 8d, whole LF-walk step: 128-B index cell + 8 B query + 8 B result + 8 B LF_B read + 8 B ka write
+WALK_ROW_BYTES = 137  # what k_walk_first itself must move per row: one 128-B cell line + 1 B symbol in + 8 B position out
 
 
 def parse():
@@ -44,6 +45,7 @@ def parse():
     ap.add_argument("--genomes-per-merge", type=int, default=0,
                     help="genomes per batch (one batch = one partial BWT = one merge); default: the number of GPUs, i.e. weak scaling")
     ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: CPU seconds all steps together may take")
+    ap.add_argument("--param", action="append", default=[], help="engine tuning knob key=value (rb3b_set_param), repeatable")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-rank-bench", action="store_true")
@@ -134,6 +136,9 @@ def run_b200(a):
     capi.check(capi.lib().rb3b_set_stream(stream.cuda_stream))
     if a.seg_len:
         R.set_param("seg_len", a.seg_len)
+    for kv in a.param:
+        k, v = kv.split("=")
+        R.set_param(k, int(v))
 
     # ---- synthetic input, partial BWTs built on the device (untimed producer of the path's input)
     t0 = time.time()
@@ -273,7 +278,9 @@ def run_b200(a):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     walk_s = st["us_walk_first"] / 1e6
-    achieved = LF_STEP_BYTES * timed_syms / walk_s / 1e9 if walk_s > 0 else 0.0
+    achieved = WALK_ROW_BYTES * timed_syms / walk_s / 1e9 if walk_s > 0 else 0.0
+    phase_s = (st["us_prep"] + st["us_walk_first"] + st["us_walk_fix"] + st["us_scatter"]) / 1e6
+    phase_gbs = LF_STEP_BYTES * timed_syms / phase_s / 1e9 if phase_s > 0 else 0.0
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "walk_first_traffic.json"))).get("dram_bytes_per_launch")
@@ -283,17 +290,19 @@ def run_b200(a):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/int64", "data": "synthetic",
-        "config": config_of(a, {"seg_len": a.seg_len or R.get_stat("seg_len"), "parallelism": "1 GPU" if world == 1 else "weak scaling: %d genomes per merge on %d GPUs; index replicated; rank phase of every merge split over the ranks (chain stretches + halo), NCCL all-reduce(MAX) of the 8 B/row interleave array, merge replicated; %d of %d merges sharded" % (G, world, n_sharded, a.steps)}),
+        "config": config_of(a, {"seg_len": a.seg_len or R.get_stat("seg_len_used"), "parallelism": "1 GPU" if world == 1 else "weak scaling: %d genomes per merge on %d GPUs; index replicated; rank phase of every merge split over the ranks (chain stretches + halo), NCCL all-reduce(MAX) of the 8 B/row interleave array, merge replicated; %d of %d merges sharded" % (G, world, n_sharded, a.steps)}),
         "e2e": None if a.no_e2e else {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(np.mean(lens[1 + a.warmup:])), "d2h_bytes_per_step": int(d2h),
                                       "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": int(st["kernel_launches"]),
         "clocks": clocks,
-        "roofline": {"kernel": "k_walk_first<BmRank> (round 1 of the segmented LF walk: per row one LF_B gather, one or two rank lookups in the bitmap cells, one interleave-position scatter)",
+        "roofline": {"kernel": "k_walk_first<BmPair> (sliced LF walk over the index: per row one symbol streamed in, one rank lookup per lane in the bitmap cells, one 8-byte position streamed out)",
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                     "traffic": traffic, "bytes_per_unit": LF_STEP_BYTES, "units_per_launch": timed_syms / a.steps,
+                     "traffic": traffic, "bytes_per_unit": WALK_ROW_BYTES, "units_per_launch": timed_syms / a.steps,
                      "avg_launch_ms": walk_s * 1e3 / a.steps,
-                     "note": "dependent chains: one DRAM access per row per walk and only n/seg_len walks in flight, so the kernel is bound by DRAM latency x random-sector throughput, not by streaming bandwidth; the rank primitive itself is measured under rank_kernel; see DESIGN.md 5 and profiles/"},
+                     "rank_phase": {"bytes_per_unit": LF_STEP_BYTES, "achieved": phase_gbs, "frac": phase_gbs / peak, "ms_per_step": phase_s * 1e3 / a.steps,
+                                    "what": "SURVEY 8d's 160 B per LF-walk step over ALL kernels of the rank phase (LF table, list ranking, walk-order rewrite, walk, fix-up, scatter)"},
+                     "note": "one dependent random 64-B access per row per walk; with one genome per batch only len/seg_len = 26 k walks exist and the kernel is bound by the instruction + DRAM latency of a step, with ten genomes per batch by DRAM random-access throughput (see DESIGN.md 5); the rank primitive itself is measured under rank_kernel"},
         "phase_ms_per_step": {k[3:]: st[k] / 1e3 / a.steps for k in st if k.startswith("us_")},
         "wall_ms_per_step": wall_dev * 1e3 / a.steps,
         "setup": {"genomes_and_bwt_s": t_setup, "device_bwt_build_s": t_bwt, "bwt_build_bases_per_s": sum(bases) / t_bwt},

@@ -441,6 +441,15 @@ static __global__ void __launch_bounds__(EMIT_TPB) k_bm_fin_write(EmitOut O, con
 	}
 }
 
+/* out[a] = last - first of row a of an exclusive scan laid out as RB3B_ASIZE rows of `stride` entries: the six totals in
+ * one 48-byte read-back (a dozen 8-byte copies cost ~10 us each in stream order) */
+static __global__ void k_gather_tot(const int64_t *__restrict__ ex, int64_t stride, const int *__restrict__ flag, int64_t *__restrict__ out)
+{
+	const int a = threadIdx.x;
+	if (a < RB3B_ASIZE) out[a] = ex[a * stride + stride - 1] - ex[a * stride];
+	if (a == RB3B_ASIZE) out[a] = flag ? *flag : 0;
+}
+
 template<class Src>
 static int rb3b_emit_build_bm(rb3b_index_s *x, Src src, int64_t n_src, int64_t lenB, const int64_t *d_ka, const uint8_t *d_bwt)
 {
@@ -463,11 +472,11 @@ static int rb3b_emit_build_bm(rb3b_index_s *x, Src src, int64_t n_src, int64_t l
 	CKK();
 	TRY(rb3b_scan_excl_i64(ctot.p, cex.p, (O.n_chunks + 1) * RB3B_ASIZE));
 	k_bm_fin_write<<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(O, lcnt.p, cex.p); CKK();
-	int64_t tot[RB3B_ASIZE], base[RB3B_ASIZE];
-	for (int a = 0; a < RB3B_ASIZE; ++a) {
-		CK(cudaMemcpyAsync(&tot[a], cex.p + a * (O.n_chunks + 1) + O.n_chunks, 8, cudaMemcpyDeviceToHost, rb3b_stream));
-		CK(cudaMemcpyAsync(&base[a], cex.p + a * (O.n_chunks + 1), 8, cudaMemcpyDeviceToHost, rb3b_stream));
-	}
+	int64_t tot[RB3B_ASIZE + 1], base[RB3B_ASIZE] = {0, 0, 0, 0, 0, 0};
+	DBuf<int64_t> gt;
+	TRY(gt.alloc(RB3B_ASIZE + 1));
+	k_gather_tot<<<1, 32, 0, rb3b_stream>>>(cex.p, O.n_chunks + 1, 0, gt.p); CKK();
+	CK(cudaMemcpyAsync(tot, gt.p, sizeof(tot), cudaMemcpyDeviceToHost, rb3b_stream));
 	CK(cudaStreamSynchronize(rb3b_stream));
 	{ uint4 *t = x->cells; x->cells = x->cells2; x->cells2 = t; int64_t c = x->cap_cells; x->cap_cells = x->cap_cells2; x->cap_cells2 = c; }
 	x->kind = RB3B_KIND_BM; x->shift = RB3B_BM_SHIFT; x->n_cells = O.n_cells; x->n_ovf = 0; x->n_entries = 0;

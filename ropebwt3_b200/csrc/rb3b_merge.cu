@@ -678,13 +678,13 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	rb3b_tic(T_PREP);
 	k_prep_count<<<(unsigned)nt, TPB, 0, rb3b_stream>>>(len, d_bwt, nt, tcnt.p, bad.p); CKK();
 	TRY(rb3b_scan_excl_i64(tcnt.p, tex.p, (nt + 1) * RB3B_ASIZE));
-	int64_t tot[RB3B_ASIZE], base[RB3B_ASIZE];
-	for (int a = 0; a < RB3B_ASIZE; ++a) {
-		CK(cudaMemcpyAsync(&tot[a], tex.p + a * (nt + 1) + nt, 8, cudaMemcpyDeviceToHost, rb3b_stream));
-		CK(cudaMemcpyAsync(&base[a], tex.p + a * (nt + 1), 8, cudaMemcpyDeviceToHost, rb3b_stream));
-	}
-	CK(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, rb3b_stream));
+	int64_t tot[RB3B_ASIZE + 1], base[RB3B_ASIZE] = {0, 0, 0, 0, 0, 0};
+	DBuf<int64_t> gt;
+	TRY(gt.alloc(RB3B_ASIZE + 1));
+	k_gather_tot<<<1, 32, 0, rb3b_stream>>>(tex.p, nt + 1, bad.p, gt.p); CKK();
+	CK(cudaMemcpyAsync(tot, gt.p, sizeof(tot), cudaMemcpyDeviceToHost, rb3b_stream));
 	CK(cudaStreamSynchronize(rb3b_stream));
+	hbad = (int)tot[RB3B_ASIZE];
 	if (hbad) return rb3b_fail(RB3B_EINVAL, "batch BWT holds a symbol >= %d", RB3B_ASIZE);
 	Acc7 acc;
 	acc.v[0] = 0;
@@ -692,10 +692,14 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	memcpy(accB, acc.v, sizeof(acc.v));
 	if (acc.v[1] <= 0) return rb3b_fail(RB3B_EINVAL, "batch BWT holds no sentinel");
 	/* the batch in walk order */
-	int64_t seg_len = (rb3b_seg_len + 7) / 8 * 8;
+	/* few slices (one genome per batch): the walks are latency bound, shorter slices and pieces give more of them; many
+	 * slices: DRAM-access bound, longer slices leave fewer rows to the fix-up */
+	const bool big = len >= (32LL << 20);
+	int64_t seg_len = ((rb3b_seg_len > 0 ? rb3b_seg_len : big ? 512 : 384) + 7) / 8 * 8;
 	Fine F;
 	F.n_seq = acc.v[1];
-	int64_t fine_len = rb3b_get_param("fine_len", 32);
+	int64_t fine_len = rb3b_get_param("fine_len", 0);
+	if (fine_len <= 0) fine_len = big ? 32 : 16;
 	if (fine_len > seg_len) fine_len = seg_len;
 	F.fshift = 0;
 	while ((2LL << F.fshift) <= fine_len) ++F.fshift; /* largest power of two <= fine_len */
@@ -795,6 +799,7 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	CK(cudaStreamSynchronize(rb3b_stream));
 	rb3b_tflush();
 	rb3b_stat_set("n_segments", S.n_seg);
+	rb3b_stat_set("seg_len_used", seg_len);
 	rb3b_stat_set("n_fine", F.n_fine);
 	rb3b_stat_set("fix_rounds", rounds - 1);
 	rb3b_stat_add("fix_rounds_total", rounds - 1);

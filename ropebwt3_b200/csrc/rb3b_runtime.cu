@@ -10,7 +10,7 @@
 #include "rb3b_internal.cuh"
 
 cudaStream_t rb3b_stream = 0;
-int64_t rb3b_seg_len = 512;       /* target LF-walk segment length ("seg_len") */
+int64_t rb3b_seg_len = 0;         /* target LF-walk segment length ("seg_len") */
 int64_t rb3b_rank_variant = 0;    /* 0: LDG.128 per lane, 1: cp.async.bulk (TMA) staged */
 
 static int g_inited = 0, g_device = 0, g_own_stream = 0;
@@ -175,7 +175,7 @@ extern "C" int rb3b_sync(void)
 
 extern "C" int rb3b_set_param(const char *key, int64_t value)
 {
-	if (!strcmp(key, "seg_len")) { if (value < 16) return rb3b_fail(RB3B_EINVAL, "seg_len must be >= 16"); rb3b_seg_len = value; }
+	if (!strcmp(key, "seg_len")) { if (value != 0 && value < 16) return rb3b_fail(RB3B_EINVAL, "seg_len must be >= 16 (0 = automatic)"); rb3b_seg_len = value; }
 	else if (!strcmp(key, "rank_variant")) rb3b_rank_variant = value;
 	else g_params[key] = value;
 	return RB3B_OK;

@@ -170,7 +170,7 @@ def test_merge_chain_golden(rb3, oracle, golden, name, seg_len):
         ok, ret = idx.rank1a(g["q_k"])
         assert np.array_equal(ok, g["q_ok"]) and np.array_equal(ret, g["q_ret"])
     finally:
-        rb3.set_param("seg_len", 512)
+        rb3.set_param("seg_len", 0)
 
 
 def test_merge_vs_oracle_seeded(rb3, oracle):
@@ -200,7 +200,7 @@ def test_merge_vs_oracle_seeded(rb3, oracle):
             s, l = runs_of(idx, oracle)
             assert np.array_equal(s, sym) and np.array_equal(l, ln), "merged runs differ at batch %d" % i
     finally:
-        rb3.set_param("seg_len", 512)
+        rb3.set_param("seg_len", 0)
 
 
 def test_bitmap_to_rle_transition(rb3, oracle, golden):
@@ -230,7 +230,7 @@ def test_optional_code_paths(rb3, oracle, golden, knob, value):
     spacing, the two-pass bucketed scatter of large batches); every one of them must give the reference's interleave
     array and merged index."""
     g = golden("merge_dup")
-    defaults = {"fix_log": 1, "wide_lf": 0, "fine_len": 32, "scatter_win_bits": 19, "walk_pair": 1}
+    defaults = {"fix_log": 1, "wide_lf": 0, "fine_len": 0, "scatter_win_bits": 19, "walk_pair": 1}
     rb3.set_param(knob, value)
     if knob == "scatter_win_bits":
         rb3.set_param("scatter_bucket_min", 1)
@@ -247,7 +247,7 @@ def test_optional_code_paths(rb3, oracle, golden, knob, value):
     finally:
         rb3.set_param(knob, defaults[knob])
         rb3.set_param("scatter_bucket_min", 24 << 20)
-        rb3.set_param("seg_len", 512)
+        rb3.set_param("seg_len", 0)
 
 
 def test_build_bwt_golden(rb3, golden):
@@ -381,7 +381,7 @@ def test_sharded_rank_phase(rb3, oracle, n_parts):
         with pytest.raises(rb3.Rb3bError):
             capi.check(L.rb3b_merge_with_ka(idx.h, n, d_bwt.data_ptr(), bad.data_ptr()))
     finally:
-        rb3.set_param("seg_len", 512)
+        rb3.set_param("seg_len", 0)
 
 
 def test_device_pointer_entry_points(rb3, golden):
@@ -469,7 +469,7 @@ def test_insert_multi_batches(rb3, oracle, golden, so, seg_len):
         assert rb3.fmd_image(s, l) == bytes(g["fmd_so%d" % so])
         assert idx.get_order() == so
     finally:
-        rb3.set_param("seg_len", 512)
+        rb3.set_param("seg_len", 0)
 
 
 def test_insert_multi_duplicates_and_order_in_fmr(rb3, oracle, golden, tmp_path):
