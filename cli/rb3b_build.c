@@ -19,6 +19,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
 #include <stdint.h>
 #include <unistd.h>
 #include <time.h>
@@ -182,7 +183,8 @@ int main(int argc, char *argv[])
 {
 	int c, i, is_line = 0, no_for = 0, no_rev = 0, fmt = 0 /* 0 plain, 1 fmd, 2 fmr */, block_len = 512, max_nodes = 64;
 	int use_rb2 = 0, sort_order = 0; /* build.c:153-155 */
-	int64_t batch = 7000000000LL;
+	int64_t batch = 7000000000LL, batch_user, est_symbols = 0;
+	int fit_said = 0, reserved = 0;
 	const char *fn_in = 0, *fn_tmp = 0;
 	str_t seq = {0, 0, 0}, rec = {0, 0, 0}, tmp = {0, 0, 0};
 	rb3b_index_t *idx = 0;
@@ -215,6 +217,15 @@ int main(int argc, char *argv[])
 		} else return usage(stderr);
 	}
 	if (argc == optind && fn_in == 0) return usage(stderr);
+	batch_user = batch;
+	/* size hint for the device index: about two symbols (both strands) per input byte, more for compressed input; the
+	 * ping-pong buffers are then allocated once instead of being regrown by the merges (rb3b_index_reserve) */
+	for (i = optind; i < argc; ++i) {
+		struct stat st;
+		size_t l = strlen(argv[i]);
+		if (stat(argv[i], &st) == 0) est_symbols += (int64_t)st.st_size * ((l > 3 && strcmp(argv[i] + l - 3, ".gz") == 0) ? 8 : 2);
+	}
+	if (est_symbols > 40000000000LL) est_symbols = 40000000000LL;
 	if (no_for && no_rev) { fprintf(stderr, "ERROR: -F and -R together leave nothing to index\n"); return 1; }
 
 	DIE_IF(rb3b_init(getenv("RB3B_DEVICE") ? atoi(getenv("RB3B_DEVICE")) : 0), "no usable CUDA device");
@@ -225,6 +236,7 @@ int main(int argc, char *argv[])
 			return 1;
 		}
 		LOG("loaded the index from file '%s'", fn_in);
+		{ int64_t acc0[7]; rb3b_index_reserve(idx, rb3b_get_acc(idx, acc0) + est_symbols); reserved = 1; }
 	}
 	for (i = optind; i < argc; ++i) {
 		reader_t *r = (reader_t*)calloc(1, sizeof(reader_t));
@@ -242,10 +254,11 @@ int main(int argc, char *argv[])
 			/* clamp the batch to what the device can sort and merge next to the current index; the output does not
 			 * depend on the batching */
 			fit = rb3b_max_batch_symbols(idx ? rb3b_get_acc(idx, acc) : 0);
-			if (fit > 0 && (batch <= 0 || batch > fit)) {
-				LOG("batch size limited to %ld symbols by device memory", (long)fit);
+			if (fit > 0 && (batch_user <= 0 || batch_user > fit)) {
+				if (!fit_said) LOG("batch size limited to %ld symbols by device memory", (long)fit);
+				fit_said = 1;
 				batch = fit;
-			}
+			} else batch = batch_user;
 			while (rd_record(r, &rec, &tmp) == 0) {
 				seq_add(&seq, &rec, !no_for, !no_rev, &n_seq);
 				if (batch > 0 && (int64_t)seq.l > batch) break; /* io.c:114,119 */
@@ -267,6 +280,7 @@ int main(int argc, char *argv[])
 				}
 				DIE_IF(rb3b_insert_multi_dev(idx, (int64_t)seq.l, (const uint8_t*)d_text), "inserting the batch");
 				LOG("inserted %ld symbols", (long)seq.l);
+				if (!reserved) { rb3b_index_reserve(idx, est_symbols); reserved = 1; } /* after the first batch: building the first index resets the buffers */
 				continue;
 			}
 			DIE_IF(rb3b_build_bwt_dev((int64_t)seq.l, (const uint8_t*)d_text, (uint8_t*)d_text), "partial BWT"); /* rb3_build_sais, in place */
@@ -275,6 +289,7 @@ int main(int argc, char *argv[])
 				idx = rb3b_index_create();
 				DIE_IF(rb3b_index_from_plain_dev(idx, (int64_t)seq.l, (const uint8_t*)d_text), "encoding the partial BWT");
 				LOG("encoded the partial BWT for %ld symbols", (long)seq.l);
+				if (!reserved) { rb3b_index_reserve(idx, est_symbols); reserved = 1; }
 			} else {
 				DIE_IF(rb3b_merge_plain_dev(idx, (int64_t)seq.l, (const uint8_t*)d_text), "merging the partial BWT");
 				LOG("merged the partial BWT for %ld symbols", (long)seq.l);

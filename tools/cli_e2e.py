@@ -30,6 +30,8 @@ def main():
     p = subprocess.run([os.path.join(ROOT, "cli", "ropebwt3-b200"), "build", "-d", "-o", os.path.join(d, "mine.fmd")] + files, stderr=subprocess.PIPE)
     out["b200_cli_s"] = time.time() - t0
     assert p.returncode == 0, p.stderr.decode()[-500:]
+    if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+        open(os.path.join(ROOT, "gpurun_out", "cli_e2e_stderr.txt"), "wb").write(p.stderr)
     ref = os.path.join(ROOT, "oracle", "_ref", "ropebwt3")
     t0 = time.time()
     p = subprocess.run([ref, "build", "-t%d" % (os.cpu_count() or 1), "-d", "-o", os.path.join(d, "ref.fmd")] + files, stderr=subprocess.PIPE)
