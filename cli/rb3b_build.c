@@ -12,8 +12,13 @@
  * a batch, interleave array, merge -- runs on the device through librb3b200.so;
  * this file only parses options and sequence files.
  *
- * Not covered (documented in DESIGN.md): -2/-s/-r (ropebwt2 insertion, config 0),
- * -T (tree dump: there is no tree), -e (BRE).  -t and -p are accepted and
+ * -2/-s/-r go through rb3b_insert_multi (mr_insert_multi, build.c:214-218).
+ *
+ * Like the reference's pipeline mode (build.c:55-83,186-201: kt_pipeline of read+SAIS and merge) the host work overlaps
+ * the device work, here always and for any number of input files: a reader thread parses and encodes batch i+1 while
+ * the main thread runs the partial BWT and the merge of batch i on the device (two batch buffers).
+ *
+ * Not covered (documented in DESIGN.md): -T (tree dump: there is no tree), -e (BRE).  -t and -p are accepted and
  * ignored (parallelism comes from the device); -l/-n only shape the .fmr dump.
  */
 #include <stdio.h>
@@ -25,6 +30,7 @@
 #include <time.h>
 #include <sys/resource.h>
 #include <zlib.h>
+#include <pthread.h>
 #include "../include/rb3_b200.h"
 
 static const unsigned char nt6_table[128] = { /* io.c:12-21: $ACGTN = 0..5 */
@@ -161,6 +167,99 @@ static void seq_add(str_t *seq, const str_t *rec, int is_for, int is_rev, int64_
 	}
 }
 
+/* ---- reader thread: produces batches in input order ---- */
+
+typedef struct {
+	str_t seq;          /* encoded batch */
+	int64_t n_seq;
+	int file;           /* index into argv of the file the batch came from */
+	int last_of_file;   /* the file ends with this batch (-S checkpoint point); n_seq == 0: nothing left in the file */
+	int open_failed;
+} batch_t;
+
+typedef struct {
+	int argc, first; char **argv;
+	int is_line, no_for, no_rev;
+	int64_t batch;
+	batch_t slot[2];
+	int n_full, head, tail, done; /* ring of two slots */
+	pthread_mutex_t mu; pthread_cond_t cv;
+} pipe_t;
+
+static batch_t *pipe_claim(pipe_t *p)
+{ /* reader: wait for a free slot */
+	pthread_mutex_lock(&p->mu);
+	while (p->n_full == 2) pthread_cond_wait(&p->cv, &p->mu);
+	pthread_mutex_unlock(&p->mu);
+	return &p->slot[p->tail];
+}
+
+static void pipe_publish(pipe_t *p)
+{
+	pthread_mutex_lock(&p->mu);
+	p->tail ^= 1; ++p->n_full;
+	pthread_cond_broadcast(&p->cv);
+	pthread_mutex_unlock(&p->mu);
+}
+
+static batch_t *pipe_next(pipe_t *p)
+{ /* consumer: next batch in order, NULL when the reader is finished */
+	batch_t *b = 0;
+	pthread_mutex_lock(&p->mu);
+	while (p->n_full == 0 && !p->done) pthread_cond_wait(&p->cv, &p->mu);
+	if (p->n_full) b = &p->slot[p->head];
+	pthread_mutex_unlock(&p->mu);
+	return b;
+}
+
+static void pipe_release(pipe_t *p)
+{
+	pthread_mutex_lock(&p->mu);
+	p->head ^= 1; --p->n_full;
+	pthread_cond_broadcast(&p->cv);
+	pthread_mutex_unlock(&p->mu);
+}
+
+static void *reader_main(void *arg)
+{
+	pipe_t *p = (pipe_t*)arg;
+	str_t rec = {0, 0, 0}, tmp = {0, 0, 0};
+	int i;
+	for (i = p->first; i < p->argc; ++i) {
+		reader_t *r = (reader_t*)calloc(1, sizeof(reader_t));
+		int eof = 0;
+		batch_t *b;
+		r->fp = strcmp(p->argv[i], "-") ? gzopen(p->argv[i], "r") : gzdopen(0, "r");
+		if (r->fp == 0) { /* build.c:207-210: report and go on */
+			b = pipe_claim(p);
+			b->seq.l = 0; b->n_seq = 0; b->file = i; b->last_of_file = 0; b->open_failed = 1;
+			pipe_publish(p);
+			free(r);
+			continue;
+		}
+		r->is_line = p->is_line; r->last = -2;
+		while (!eof) {
+			b = pipe_claim(p);
+			b->seq.l = 0; b->n_seq = 0; b->file = i; b->open_failed = 0;
+			while (rd_record(r, &rec, &tmp) == 0) {
+				seq_add(&b->seq, &rec, !p->no_for, !p->no_rev, &b->n_seq);
+				if (p->batch > 0 && (int64_t)b->seq.l > p->batch) break; /* io.c:114,119 */
+			}
+			if (b->n_seq == 0 || p->batch <= 0 || (int64_t)b->seq.l <= p->batch) eof = 1;
+			b->last_of_file = eof;
+			pipe_publish(p);
+		}
+		gzclose(r->fp);
+		free(r);
+	}
+	pthread_mutex_lock(&p->mu);
+	p->done = 1;
+	pthread_cond_broadcast(&p->cv);
+	pthread_mutex_unlock(&p->mu);
+	free(rec.s); free(tmp.s);
+	return 0;
+}
+
 static int usage(FILE *fp)
 {
 	fprintf(fp, "Usage: ropebwt3-b200 build [options] <in.fa> [...]\n");
@@ -183,10 +282,10 @@ int main(int argc, char *argv[])
 {
 	int c, i, is_line = 0, no_for = 0, no_rev = 0, fmt = 0 /* 0 plain, 1 fmd, 2 fmr */, block_len = 512, max_nodes = 64;
 	int use_rb2 = 0, sort_order = 0; /* build.c:153-155 */
-	int64_t batch = 7000000000LL, batch_user, est_symbols = 0;
-	int fit_said = 0, reserved = 0;
+	int64_t batch = 7000000000LL, est_symbols = 0;
+	int reserved = 0;
 	const char *fn_in = 0, *fn_tmp = 0;
-	str_t seq = {0, 0, 0}, rec = {0, 0, 0}, tmp = {0, 0, 0};
+
 	rb3b_index_t *idx = 0;
 	void *d_text = 0;
 	int64_t d_cap = 0;
@@ -217,7 +316,6 @@ int main(int argc, char *argv[])
 		} else return usage(stderr);
 	}
 	if (argc == optind && fn_in == 0) return usage(stderr);
-	batch_user = batch;
 	/* size hint for the device index: about two symbols (both strands) per input byte, more for compressed input; the
 	 * ping-pong buffers are then allocated once instead of being regrown by the merges (rb3b_index_reserve) */
 	for (i = optind; i < argc; ++i) {
@@ -238,69 +336,66 @@ int main(int argc, char *argv[])
 		LOG("loaded the index from file '%s'", fn_in);
 		{ int64_t acc0[7]; rb3b_index_reserve(idx, rb3b_get_acc(idx, acc0) + est_symbols); reserved = 1; }
 	}
-	for (i = optind; i < argc; ++i) {
-		reader_t *r = (reader_t*)calloc(1, sizeof(reader_t));
-		int eof = 0;
-		r->fp = strcmp(argv[i], "-") ? gzopen(argv[i], "r") : gzdopen(0, "r");
-		if (r->fp == 0) { /* build.c:207-210: report and go on */
-			fprintf(stderr, "ERROR: failed to open file '%s'\n", argv[i]);
-			free(r);
-			continue;
+	{
+		pipe_t P;
+		pthread_t tid;
+		batch_t *b;
+		int64_t acc[7], fit;
+		memset(&P, 0, sizeof(P));
+		P.argc = argc; P.argv = argv; P.first = optind; P.is_line = is_line; P.no_for = no_for; P.no_rev = no_rev;
+		/* clamp the batch to what the device can sort and merge next to the finished index; the output does not depend
+		 * on the batching */
+		fit = rb3b_max_batch_symbols((idx ? rb3b_get_acc(idx, acc) : 0) + est_symbols);
+		if (fit > 0 && (batch <= 0 || batch > fit)) {
+			LOG("batch size limited to %ld symbols by device memory", (long)fit);
+			batch = fit;
 		}
-		r->is_line = is_line; r->last = -2;
-		while (!eof) {
-			int64_t n_seq = 0, acc[7], fit;
-			seq.l = 0;
-			/* clamp the batch to what the device can sort and merge next to the current index; the output does not
-			 * depend on the batching */
-			fit = rb3b_max_batch_symbols(idx ? rb3b_get_acc(idx, acc) : 0);
-			if (fit > 0 && (batch_user <= 0 || batch_user > fit)) {
-				if (!fit_said) LOG("batch size limited to %ld symbols by device memory", (long)fit);
-				fit_said = 1;
-				batch = fit;
-			} else batch = batch_user;
-			while (rd_record(r, &rec, &tmp) == 0) {
-				seq_add(&seq, &rec, !no_for, !no_rev, &n_seq);
-				if (batch > 0 && (int64_t)seq.l > batch) break; /* io.c:114,119 */
-			}
-			if (n_seq == 0) break;
-			if (batch <= 0 || (int64_t)seq.l <= batch) eof = 1;
-			LOG("read %ld symbols from file '%s'", (long)seq.l, argv[i]);
-			if ((int64_t)seq.l > d_cap) {
-				rb3b_dev_free(d_text);
-				d_cap = (int64_t)seq.l + (int64_t)(seq.l >> 2);
-				d_text = rb3b_dev_alloc(d_cap);
-				if (d_text == 0) { fprintf(stderr, "ERROR: %s\n", rb3b_last_error()); return 1; }
-			}
-			DIE_IF(rb3b_h2d(d_text, seq.s, (int64_t)seq.l), "host to device copy");
-			if (use_rb2) { /* build.c:214-218; an index loaded with -i keeps its own order, like mr->so */
-				if (idx == 0) {
-					idx = rb3b_index_create();
-					DIE_IF(rb3b_index_set_order(idx, sort_order), "sorting order");
+		P.batch = batch;
+		pthread_mutex_init(&P.mu, 0); pthread_cond_init(&P.cv, 0);
+		if (pthread_create(&tid, 0, reader_main, &P) != 0) { fprintf(stderr, "ERROR: failed to start the reader thread\n"); return 1; }
+		while ((b = pipe_next(&P)) != 0) {
+			const char *fn = argv[b->file];
+			if (b->open_failed) fprintf(stderr, "ERROR: failed to open file '%s'\n", fn);
+			else if (b->n_seq > 0) {
+				str_t seq = b->seq;
+				LOG("read %ld symbols from file '%s'", (long)seq.l, fn);
+				if ((int64_t)seq.l > d_cap) {
+					rb3b_dev_free(d_text);
+					d_cap = (int64_t)seq.l + (int64_t)(seq.l >> 2);
+					d_text = rb3b_dev_alloc(d_cap);
+					if (d_text == 0) { fprintf(stderr, "ERROR: %s\n", rb3b_last_error()); return 1; }
 				}
-				DIE_IF(rb3b_insert_multi_dev(idx, (int64_t)seq.l, (const uint8_t*)d_text), "inserting the batch");
-				LOG("inserted %ld symbols", (long)seq.l);
-				if (!reserved) { rb3b_index_reserve(idx, est_symbols); reserved = 1; } /* after the first batch: building the first index resets the buffers */
-				continue;
-			}
-			DIE_IF(rb3b_build_bwt_dev((int64_t)seq.l, (const uint8_t*)d_text, (uint8_t*)d_text), "partial BWT"); /* rb3_build_sais, in place */
-			LOG("constructed partial BWT for %ld symbols", (long)seq.l);
-			if (idx == 0) {
-				idx = rb3b_index_create();
-				DIE_IF(rb3b_index_from_plain_dev(idx, (int64_t)seq.l, (const uint8_t*)d_text), "encoding the partial BWT");
-				LOG("encoded the partial BWT for %ld symbols", (long)seq.l);
+				DIE_IF(rb3b_h2d(d_text, seq.s, (int64_t)seq.l), "host to device copy");
+				if (use_rb2) { /* build.c:214-218; an index loaded with -i keeps its own order, like mr->so */
+					if (idx == 0) {
+						idx = rb3b_index_create();
+						DIE_IF(rb3b_index_set_order(idx, sort_order), "sorting order");
+					}
+					DIE_IF(rb3b_insert_multi_dev(idx, (int64_t)seq.l, (const uint8_t*)d_text), "inserting the batch");
+					LOG("inserted %ld symbols", (long)seq.l);
+				} else {
+					DIE_IF(rb3b_build_bwt_dev((int64_t)seq.l, (const uint8_t*)d_text, (uint8_t*)d_text), "partial BWT"); /* rb3_build_sais, in place */
+					LOG("constructed partial BWT for %ld symbols", (long)seq.l);
+					if (idx == 0) {
+						idx = rb3b_index_create();
+						DIE_IF(rb3b_index_from_plain_dev(idx, (int64_t)seq.l, (const uint8_t*)d_text), "encoding the partial BWT");
+						LOG("encoded the partial BWT for %ld symbols", (long)seq.l);
+					} else {
+						DIE_IF(rb3b_merge_plain_dev(idx, (int64_t)seq.l, (const uint8_t*)d_text), "merging the partial BWT");
+						LOG("merged the partial BWT for %ld symbols", (long)seq.l);
+					}
+				}
+				/* after the first batch: building the first index resets the buffers */
 				if (!reserved) { rb3b_index_reserve(idx, est_symbols); reserved = 1; }
-			} else {
-				DIE_IF(rb3b_merge_plain_dev(idx, (int64_t)seq.l, (const uint8_t*)d_text), "merging the partial BWT");
-				LOG("merged the partial BWT for %ld symbols", (long)seq.l);
 			}
+			if (!b->open_failed && b->last_of_file && fn_tmp && idx) { /* build.c:232-238 */
+				DIE_IF(rb3b_dump_fmr(idx, fn_tmp, max_nodes, block_len), "saving the index");
+				LOG("saved the current index to '%s'", fn_tmp);
+			}
+			pipe_release(&P);
 		}
-		gzclose(r->fp);
-		free(r);
-		if (fn_tmp && idx) {
-			DIE_IF(rb3b_dump_fmr(idx, fn_tmp, max_nodes, block_len), "saving the index");
-			LOG("saved the current index to '%s'", fn_tmp);
-		}
+		pthread_join(tid, 0);
+		free(P.slot[0].seq.s); free(P.slot[1].seq.s);
 	}
 	if (idx == 0) return 1; /* build.c:243 */
 	if (fmt == 2) DIE_IF(rb3b_dump_fmr(idx, "-", max_nodes, block_len), "writing .fmr");
@@ -308,7 +403,6 @@ int main(int argc, char *argv[])
 	else DIE_IF(rb3b_dump_plain(idx, "-"), "writing the BWT");
 	rb3b_index_destroy(idx);
 	rb3b_dev_free(d_text);
-	free(seq.s); free(rec.s); free(tmp.s);
 	fprintf(stderr, "[M::main] Real time: %.3f sec; CPU: %.3f sec\n", realtime() - t_real0, cputime());
 	return 0;
 }
