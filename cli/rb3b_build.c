@@ -262,7 +262,7 @@ static void *reader_main(void *arg)
 
 static int usage(FILE *fp)
 {
-	fprintf(fp, "Usage: ropebwt3-b200 build [options] <in.fa> [...]\n");
+	fprintf(fp, "Usage: ropebwt3-b200 build [options] <in.fa> [...]\n       ropebwt3-b200 ssa [-s INT] [-o FILE] <in.fmd>\n");
 	fprintf(fp, "Options (those of `ropebwt3 build`):\n");
 	fprintf(fp, "  -m NUM   batch size [7G]             -i FILE  append to an existing .fmr/.fmd index\n");
 	fprintf(fp, "  -L       one sequence per line       -F/-R    skip forward / reverse strand\n");
@@ -292,6 +292,26 @@ int main(int argc, char *argv[])
 
 	t_real0 = realtime();
 	if (argc >= 2 && strcmp(argv[1], "version") == 0) { puts(rb3b_version()); return 0; }
+	if (argc >= 2 && strcmp(argv[1], "ssa") == 0) { /* main_ssa, ssa.c:247-279 */
+		int ss = 8;
+		const char *fn_out = "-";
+		--argc; ++argv;
+		while ((c = getopt(argc, argv, "t:s:o:")) >= 0) {
+			if (c == 's') ss = atoi(optarg);
+			else if (c == 'o') fn_out = optarg;
+		}
+		if (argc == optind) {
+			fprintf(stderr, "Usage: ropebwt3-b200 ssa [options] <in.fmd>\nOptions:\n  -t INT     accepted for compatibility\n");
+			fprintf(stderr, "  -s INT     sample rate one SA per 2**INT bases [8]\n  -o FILE    output to file [stdout]\n");
+			return 1;
+		}
+		DIE_IF(rb3b_init(getenv("RB3B_DEVICE") ? atoi(getenv("RB3B_DEVICE")) : 0), "no usable CUDA device");
+		idx = rb3b_index_create();
+		if (rb3b_restore(idx, argv[optind]) < 0) { fprintf(stderr, "[E::main_ssa] failed to load the FM-index\n"); return 1; }
+		DIE_IF(rb3b_ssa_dump(idx, ss, fn_out), "sampled suffix array");
+		rb3b_index_destroy(idx);
+		return 0;
+	}
 	if (argc < 2 || strcmp(argv[1], "build") != 0) return usage(stderr);
 	--argc; ++argv;
 	while ((c = getopt(argc, argv, "l:n:m:t:2sri:LFRo:dbTS:p:e")) >= 0) {

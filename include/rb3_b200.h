@@ -123,6 +123,14 @@ int64_t rb3b_fmd_image(int64_t n_runs, const uint8_t *sym, const int64_t *len, u
 int64_t rb3b_fmr_image(int64_t n_runs, const uint8_t *sym, const int64_t *len, int max_nodes, int block_len, uint8_t **out);
 void    rb3b_host_free(void *p);
 
+/* ---- sampled suffix array (`ropebwt3 ssa`, ssa.c) ---------------------------------- */
+/* rb3_ssa_gen (ssa.c:55-81): sizes of the two arrays for sample shift ss: m = #strings, n_ssa, ms = bits of a string id */
+int rb3b_ssa_sizes(const rb3b_index_t *idx, int ssa_shift, int64_t *m, int64_t *n_ssa, int *ms);
+/* rb3_ssa_gen into device arrays d_r2i[m], d_ssa[n_ssa] with the layout of rb3_ssa_t (fm-index.h, ssa.c:28-38) */
+int rb3b_ssa_gen_dev(const rb3b_index_t *idx, int ssa_shift, uint64_t *d_r2i, uint64_t *d_ssa);
+/* rb3_ssa_gen + rb3_ssa_dump (ssa.c:198-213): byte-identical .ssa file; fn "-" = stdout */
+int rb3b_ssa_dump(const rb3b_index_t *idx, int ssa_shift, const char *fn);
+
 /* ---- partial BWT of a batch (rb3_build_sais, sais-ss.c:50-56) on the GPU ----- */
 /* text: concatenated 0-terminated nt6 strings (host); bwt_out: host, len bytes (may alias text). */
 int rb3b_build_bwt(int64_t len, const uint8_t *text, uint8_t *bwt_out);

@@ -304,3 +304,41 @@ def sorted_bwt(text, so):
             keys.append((tuple(s[t:]) + (0,) + tb, s[t - 1] if t > 0 else 0))
     keys.sort(key=lambda kv: kv[0])
     return np.array([kv[1] for kv in keys], np.uint8)
+
+
+# ---------------------------------------------------------------- sampled suffix array (ropebwt3 ssa)
+def ssa_image(bwt, ss):
+    """rb3_ssa_gen + ssa_gen1 + rb3_ssa_dump (ssa.c:17-81,198-213) restated on a plain BWT: bytes of the .ssa file."""
+    b = np.asarray(bwt, np.uint8)
+    n = len(b)
+    cnt = np.bincount(b, minlength=6)[:6]
+    acc = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    occ = np.zeros((6, n + 1), np.int64)  # occ[c][k] = #c in b[0:k]
+    for c in range(6):
+        occ[c, 1:] = np.cumsum(b == c)
+    m = int(acc[1])
+    ms = 1
+    while (1 << ms) < m:
+        ms += 1
+    n_ssa = (n - m + (1 << ss) - 1) >> ss
+    r2i = np.zeros(m, np.uint64)
+    ssa = np.zeros(n_ssa, np.uint64)
+    mask = (1 << ss) - 1
+    for k0 in range(m):  # ssa_gen1, ssa.c:17-41
+        k, l, buf = k0, 0, []
+        while True:
+            l += 1
+            c = int(b[k])
+            k = int(acc[c] + occ[c, k])
+            if c:
+                if ((k - m) & mask) == 0:
+                    x = (k - m) >> ss
+                    ssa[x] = l
+                    buf.append(x)
+            else:
+                r2i[k] = k0
+                break
+        for x in buf:
+            ssa[x] = ((l - 1 - int(ssa[x])) << ms) | k0
+    import struct
+    return b"SSA\x01" + struct.pack("<IIqq", ss, ms, m, n_ssa) + r2i.tobytes() + ssa.tobytes()

@@ -153,6 +153,10 @@ class Index:
     def dump_fmr(self, fn, max_nodes=64, block_len=512):
         capi.check(self._L.rb3b_dump_fmr(self.h, fn.encode(), max_nodes, block_len))
 
+    def ssa_dump(self, fn, ssa_shift=8):
+        """rb3_ssa_gen + rb3_ssa_dump (ssa.c:55-81,198-213)."""
+        capi.check(self._L.rb3b_ssa_dump(self.h, int(ssa_shift), fn.encode()))
+
     def dump_plain(self, fn):
         capi.check(self._L.rb3b_dump_plain(self.h, fn.encode()))
 

@@ -60,6 +60,9 @@ SIGNATURES = {
     "rb3b_build_bwt": (_int, [_i64, _vp, _vp]),
     "rb3b_build_bwt_dev": (_int, [_i64, _vp, _vp]),
     "rb3b_max_batch_symbols": (_i64, [_i64]),
+    "rb3b_ssa_sizes": (_int, [_vp, _int, _vp, _vp, _vp]),
+    "rb3b_ssa_gen_dev": (_int, [_vp, _int, _vp, _vp]),
+    "rb3b_ssa_dump": (_int, [_vp, _int, C.c_char_p]),
     "rb3b_dev_alloc": (_vp, [_i64]),
     "rb3b_dev_free": (None, [_vp]),
     "rb3b_h2d": (_int, [_vp, _vp, _i64]),

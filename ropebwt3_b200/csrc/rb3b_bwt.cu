@@ -298,18 +298,26 @@ __global__ void k_runs_to_plain(int64_t n_runs, int64_t n, const uint8_t *__rest
 	out[i] = sym[lo];
 }
 
+/* the BWT of an index as one byte per symbol (arena memory) */
+int rb3b_index_to_plain_dev(const rb3b_index_s *x, DBuf<uint8_t> &plain)
+{
+	DBuf<uint8_t> sym;
+	DBuf<int64_t> len, start;
+	int64_t n_runs;
+	TRY(rb3b_export_runs_dev(x, sym, len, &n_runs));
+	TRY(start.alloc(n_runs)); TRY(plain.alloc(x->n));
+	TRY(rb3b_scan_excl_i64(len.p, start.p, n_runs));
+	k_runs_to_plain<<<nblk(x->n, TPB), TPB, 0, rb3b_stream>>>(n_runs, x->n, sym.p, start.p, plain.p); CKK();
+	return RB3B_OK;
+}
+
 extern "C" int rb3b_merge_index(rb3b_index_t *x, const rb3b_index_t *other)
 {
 	ApiScope scope_;
 	TRY(rb3b_ensure_init());
 	if (other->n == 0) return RB3B_OK;
-	DBuf<uint8_t> sym, plain;
-	DBuf<int64_t> len, start;
-	int64_t n_runs;
-	TRY(rb3b_export_runs_dev(other, sym, len, &n_runs));
-	TRY(start.alloc(n_runs)); TRY(plain.alloc(other->n));
-	TRY(rb3b_scan_excl_i64(len.p, start.p, n_runs));
-	k_runs_to_plain<<<nblk(other->n, TPB), TPB, 0, rb3b_stream>>>(n_runs, other->n, sym.p, start.p, plain.p); CKK();
+	DBuf<uint8_t> plain;
+	TRY(rb3b_index_to_plain_dev(other, plain));
 	TRY(rb3b_merge_plain_dev(x, other->n, plain.p));
 	CK(cudaStreamSynchronize(rb3b_stream));
 	return RB3B_OK;

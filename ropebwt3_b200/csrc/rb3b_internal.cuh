@@ -133,6 +133,7 @@ int rb3b_scan_excl_i64(const int64_t *d_in, int64_t *d_out, int64_t n);         
 int rb3b_index_free_dev(rb3b_index_s *x);
 int rb3b_index_from_runs_dev(rb3b_index_s *x, int64_t n_runs, const uint8_t *d_sym, const int64_t *d_len);
 int rb3b_export_runs_dev(const rb3b_index_s *x, DBuf<uint8_t> &sym, DBuf<int64_t> &len, int64_t *n_runs);
+int rb3b_index_to_plain_dev(const rb3b_index_s *x, DBuf<uint8_t> &plain);   /* rb3b_bwt.cu */
 int rb3b_pick_shift(int64_t n, int64_t n_entries_est);
 int rb3b_want_bitmap(int64_t n_symbols);
 

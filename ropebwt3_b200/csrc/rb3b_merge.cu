@@ -623,7 +623,7 @@ __global__ void k_check_monotone(int64_t len, const int64_t *__restrict__ ka, in
 /* everything of the rank phase that depends on the width of the batch's LF table */
 template<typename LfT, typename RowT>
 static int walk_order(int64_t len, const uint8_t *d_bwt, int64_t nt, const int64_t *tex, const Acc7 &acc, Fine &F,
-                      int64_t p_lo, int64_t p_hi, DBuf<uint8_t> &wsym, void **wrow_out, const int64_t **chain_base_out, const int64_t **chain_len_out)
+                      int64_t p_lo, int64_t p_hi, DBuf<uint8_t> &wsym, void **wrow_out, const int64_t **chain_base_out, const int64_t **chain_len_out, const void **lf_out = 0)
 {
 	DBuf<LfT> lf;
 	DBuf<RowT> wrow;
@@ -655,6 +655,7 @@ static int walk_order(int64_t len, const uint8_t *d_bwt, int64_t nt, const int64
 		                 (long long)(last[0] + last[1]), (long long)len);
 	k_write_walk<LfT, RowT><<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, len, lf.p, node, f_cof, c_base, c_len, pl.p, p_lo, p_hi, wrow.p, wsym.p); CKK();
 	*wrow_out = wrow.p; *chain_base_out = c_base; *chain_len_out = c_len; /* arena memory: lives until the API call returns */
+	if (lf_out) *lf_out = lf.p;
 	return RB3B_OK;
 }
 
@@ -814,6 +815,124 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	if (unres != 0)
 		return rb3b_fail(RB3B_EINVAL, "batch is not the BWT of a sentinel-terminated string set (%lld rows unresolved)", (long long)unres);
 	return RB3B_OK;
+}
+
+
+/* ------------------------------------------------------------------ */
+/* sampled suffix array (`ropebwt3 ssa`)                     */
+/* ------------------------------------------------------------------ */
+/*
+ * rb3_ssa_gen / ssa_gen1 (ssa.c:17-81) walk every string from its sentinel with one rank1a per symbol and remember, for
+ * the rows at multiples of 2^ss behind the sentinel block, how far from the start of the string they are.  That walk is
+ * the walk order of the collection itself: the index's own BWT goes through the same list ranking as a batch
+ * (walk_order), after which position p of chain k0 IS "l = p - base steps from sentinel k0", so
+ *     ssa[(row - C[1]) >> ss] = (L - 1 - l) << ms | k0        (ssa.c:28-38)
+ *     r2i[LF(last row of the chain)] = k0                      (ssa.c:36)
+ * are one data-parallel pass.  No dependent chain of length n/m is left.
+ */
+template<typename LfT, typename RowT>
+__global__ void k_ssa_emit(int64_t len, int64_t n_seq, int64_t acc1, int ss, int ms, const RowT *__restrict__ wrow, const LfT *__restrict__ lf,
+                           const int64_t *__restrict__ chain_base, const int64_t *__restrict__ chain_len, uint64_t *__restrict__ ssa, uint64_t *__restrict__ r2i)
+{
+	const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= len) return;
+	int64_t lo = 0, hi = n_seq; /* last chain with base <= p */
+	while (hi - lo > 1) {
+		const int64_t mid = (lo + hi) >> 1;
+		if (chain_base[mid] <= p) lo = mid; else hi = mid;
+	}
+	const int64_t l = p - chain_base[lo], L = chain_len[lo], row = (int64_t)wrow[p];
+	if (l > 0 && row >= acc1 && ((row - acc1) & ((1LL << ss) - 1)) == 0)
+		ssa[(row - acc1) >> ss] = (uint64_t)(L - 1 - l) << ms | (uint64_t)lo;
+	if (l == L - 1) r2i[(int64_t)((uint64_t)lf[row] >> LF_SHIFT)] = (uint64_t)lo;
+}
+
+template<typename LfT, typename RowT>
+static int ssa_gen_t(int64_t len, const uint8_t *d_bwt, int64_t nt, const int64_t *tex, const Acc7 &acc, Fine &F, int ss, int ms, uint64_t *d_ssa, uint64_t *d_r2i)
+{
+	DBuf<uint8_t> wsym;
+	void *wrow = 0;
+	const void *lf = 0;
+	const int64_t *c_base = 0, *c_len = 0;
+	TRY(wsym.alloc(len + 16));
+	TRY((walk_order<LfT, RowT>(len, d_bwt, nt, tex, acc, F, -1, len, wsym, &wrow, &c_base, &c_len, &lf)));
+	k_ssa_emit<LfT, RowT><<<nblk(len, TPB), TPB, 0, rb3b_stream>>>(len, F.n_seq, acc.v[1], ss, ms, (const RowT*)wrow, (const LfT*)lf, c_base, c_len, d_ssa, d_r2i); CKK();
+	return RB3B_OK;
+}
+
+/* device arrays: d_r2i[m], d_ssa[n_ssa] (sizes from rb3b_ssa_sizes) */
+extern "C" int rb3b_ssa_sizes(const rb3b_index_t *x, int ssa_shift, int64_t *m, int64_t *n_ssa, int *ms)
+{ /* rb3_ssa_gen, ssa.c:62-66 */
+	if (ssa_shift < 0 || ssa_shift > 30) return rb3b_fail(RB3B_EINVAL, "bad SSA sample shift %d", ssa_shift);
+	*m = x->acc[1];
+	int b = 1;
+	while ((1LL << b) < *m) ++b;
+	*ms = b;
+	*n_ssa = (x->n - x->acc[1] + (1LL << ssa_shift) - 1) >> ssa_shift;
+	return RB3B_OK;
+}
+
+extern "C" int rb3b_ssa_gen_dev(const rb3b_index_t *x, int ssa_shift, uint64_t *d_r2i, uint64_t *d_ssa)
+{
+	ApiScope scope_;
+	TRY(rb3b_ensure_init());
+	int64_t m, n_ssa;
+	int ms;
+	TRY(rb3b_ssa_sizes(x, ssa_shift, &m, &n_ssa, &ms));
+	if (x->n == 0 || m == 0) return rb3b_fail(RB3B_EINVAL, "SSA of an empty index");
+	const int64_t len = x->n, nt = (len + PREP_TILE - 1) / PREP_TILE;
+	DBuf<uint8_t> plain;
+	DBuf<int64_t> tcnt, tex;
+	DBuf<int> bad;
+	TRY(rb3b_index_to_plain_dev(x, plain));
+	TRY(tcnt.alloc((nt + 1) * RB3B_ASIZE)); TRY(tex.alloc((nt + 1) * RB3B_ASIZE)); TRY(bad.alloc(1));
+	CK(cudaMemsetAsync(bad.p, 0, sizeof(int), rb3b_stream));
+	k_prep_count<<<(unsigned)nt, TPB, 0, rb3b_stream>>>(len, plain.p, nt, tcnt.p, bad.p); CKK();
+	TRY(rb3b_scan_excl_i64(tcnt.p, tex.p, (nt + 1) * RB3B_ASIZE));
+	Acc7 acc;
+	for (int a = 0; a <= RB3B_ASIZE; ++a) acc.v[a] = x->acc[a]; /* the batch IS the index: its C[] is known */
+	Fine F;
+	F.n_seq = m;
+	F.fshift = len >= (32LL << 20) ? 5 : 4;
+	F.m0 = (F.n_seq + (1LL << F.fshift) - 1) >> F.fshift;
+	int64_t n_samp = ((len - 1) >> F.fshift) - F.m0 + 1;
+	F.n_fine = F.n_seq + (n_samp > 0 ? n_samp : 0);
+	CK(cudaMemsetAsync(d_ssa, 0, n_ssa * 8, rb3b_stream));
+	CK(cudaMemsetAsync(d_r2i, 0, m * 8, rb3b_stream));
+	if (len < LF32_MAX_LEN && !rb3b_get_param("wide_lf", 0)) TRY((ssa_gen_t<uint32_t, uint32_t>(len, plain.p, nt, tex.p, acc, F, ssa_shift, ms, d_ssa, d_r2i)));
+	else TRY((ssa_gen_t<uint64_t, int64_t>(len, plain.p, nt, tex.p, acc, F, ssa_shift, ms, d_ssa, d_r2i)));
+	CK(cudaStreamSynchronize(rb3b_stream));
+	return RB3B_OK;
+}
+
+/* rb3_ssa_gen + rb3_ssa_dump (ssa.c:55-81,198-213): the .ssa file of `ropebwt3 ssa -s ssa_shift`; fn "-" = stdout */
+extern "C" int rb3b_ssa_dump(const rb3b_index_t *x, int ssa_shift, const char *fn)
+{
+	ApiScope scope_;
+	TRY(rb3b_ensure_init());
+	int64_t m, n_ssa;
+	int ms;
+	TRY(rb3b_ssa_sizes(x, ssa_shift, &m, &n_ssa, &ms));
+	DBuf<uint64_t> d;
+	TRY(d.alloc(m + n_ssa));
+	TRY(rb3b_ssa_gen_dev(x, ssa_shift, d.p, d.p + m));
+	uint64_t *h = (uint64_t*)malloc((size_t)(m + n_ssa) * 8);
+	if (h == 0) return rb3b_fail(RB3B_ENOMEM, "out of host memory");
+	cudaError_t e = cudaMemcpyAsync(h, d.p, (size_t)(m + n_ssa) * 8, cudaMemcpyDeviceToHost, rb3b_stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(rb3b_stream);
+	if (e != cudaSuccess) { free(h); return rb3b_fail(RB3B_ENODEV, "copying the SSA to the host: %s", cudaGetErrorString(e)); }
+	FILE *fp = strcmp(fn, "-") ? fopen(fn, "wb") : stdout;
+	if (!fp) { free(h); return rb3b_fail(RB3B_EIO, "failed to open '%s' for writing", fn); }
+	uint32_t y;
+	fwrite("SSA\1", 1, 4, fp);
+	y = (uint32_t)ssa_shift; fwrite(&y, 4, 1, fp);
+	y = (uint32_t)ms; fwrite(&y, 4, 1, fp);
+	fwrite(&m, 8, 1, fp);
+	fwrite(&n_ssa, 8, 1, fp);
+	size_t w = fwrite(h, 8, (size_t)(m + n_ssa), fp);
+	free(h);
+	if (fp != stdout) fclose(fp); else fflush(fp);
+	return w == (size_t)(m + n_ssa) ? RB3B_OK : rb3b_fail(RB3B_EIO, "short write to '%s'", fn);
 }
 
 /* ------------------------------------------------------------------ */

@@ -153,6 +153,20 @@ def rb2_set():
     np.savez_compressed(os.path.join(OUT, "rb2.npz"), **d)
 
 
+def ssa_set():
+    """`ropebwt3 ssa -s SS idx.fmd` of two committed indexes (the merge_small genomes; the RCLO read set)."""
+    import tempfile
+    d = {}
+    for name, key in [("merge_small", "fmd"), ("rb2", "fmd_so2")]:
+        g = np.load(os.path.join(OUT, name + ".npz"))
+        with tempfile.TemporaryDirectory() as t:
+            fn = os.path.join(t, "x.fmd")
+            open(fn, "wb").write(bytes(g[key]))
+            for ss in (0, 3, 8):
+                d["%s_ss%d" % (name, ss)] = u8(R.run(["ssa", "-s", str(ss), "-t", "2", fn]))
+    np.savez_compressed(os.path.join(OUT, "ssa.npz"), **d)
+
+
 if __name__ == "__main__":
     assert R.available(), "build the reference first: make -C oracle ref"
     toy()
@@ -162,5 +176,6 @@ if __name__ == "__main__":
     reads_set()
     long_runs()
     rb2_set()
+    ssa_set()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -152,3 +152,15 @@ def test_config0_reads_rclo(files, oracle):
     want = run(files["ref"], ["build", "-r", "-L", "-t1", "-d", fn]).stdout
     assert run(CLI, ["build", "-r", "-L", "-t1", "-d", fn]).stdout == want
     assert run(CLI, ["build", "-r", "-L", "-d", "-m", "500k", fn]).stdout == want
+
+
+def test_ssa_subcommand(files):
+    """`ropebwt3-b200 ssa` == `ropebwt3 ssa` on an index built by either tool."""
+    d = files["dir"]
+    fmd = str(d / "ssa_in.fmd")
+    open(fmd, "wb").write(run(CLI, ["build", "-d"] + files["fa"][:3]).stdout)
+    for ss in ("8", "4"):
+        assert run(CLI, ["ssa", "-s", ss, fmd]).stdout == run(files["ref"], ["ssa", "-s", ss, "-t4", fmd]).stdout
+    out = str(d / "x.ssa")
+    run(CLI, ["ssa", "-o", out, fmd])
+    assert open(out, "rb").read() == run(files["ref"], ["ssa", fmd]).stdout

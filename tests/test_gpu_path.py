@@ -491,3 +491,35 @@ def test_insert_multi_duplicates_and_order_in_fmr(rb3, oracle, golden, tmp_path)
         s, l = runs_of(idx2, oracle)
         assert np.array_equal(oracle.runs2plain(s, l), want)
     assert oracle.fmr_decode(bytes(g["fmr_so2"]))[3][0] == 2  # the reference writes the order there too
+
+
+# ---------------------------------------------------------------- sampled suffix array (ropebwt3 ssa)
+
+@pytest.mark.parametrize("wide", [0, 1])
+def test_ssa_golden(rb3, oracle, golden, tmp_path, wide):
+    """rb3_ssa_gen + rb3_ssa_dump on the device == the reference's `ropebwt3 ssa -s SS idx.fmd`, byte for byte."""
+    g = golden("ssa")
+    rb3.set_param("wide_lf", wide)
+    try:
+        for name, key in [("merge_small", "fmd"), ("rb2", "fmd_so2")]:
+            fmd = str(tmp_path / (name + ".fmd"))
+            open(fmd, "wb").write(bytes(golden(name)[key]))
+            idx = rb3.Index.restore(fmd)
+            for ss in (0, 3, 8):
+                out = str(tmp_path / ("%s.%d.ssa" % (name, ss)))
+                idx.ssa_dump(out, ss)
+                assert open(out, "rb").read() == bytes(g["%s_ss%d" % (name, ss)]), (name, ss)
+    finally:
+        rb3.set_param("wide_lf", 0)
+
+
+def test_ssa_larger_against_oracle(rb3, oracle, tmp_path):
+    """20 genomes of 30 kb merged on the device, then the SSA of the result against the oracle restatement."""
+    from ropebwt3_b200 import synth
+    gs = synth.genomes(8, 30000, seed=9)
+    idx = rb3.Index.from_plain(rb3.rb3_build_sais(synth.batch_text(gs[:4])))
+    idx.merge_plain(rb3.rb3_build_sais(synth.batch_text(gs[4:])))
+    s, l = idx.export_runs()
+    out = str(tmp_path / "x.ssa")
+    idx.ssa_dump(out, 6)
+    assert open(out, "rb").read() == oracle.ssa_image(oracle.runs2plain(s, l), 6)

@@ -160,3 +160,13 @@ def test_rb2_toy_known_answers(oracle, golden):
     for key, so in [("agg_L", 0), ("agg_Ls", 1), ("agg_Lr", 2)]:
         assert oracle.to_ascii(oracle.rb2_bwt([oracle.encode_batch(seqs)], so)) == txt(g[key + "_out"]).strip()
     assert txt(g["agg_Lr_out"]) == "TTGC$$G$GCGA$ACC\n" and txt(g["agg_Ls_out"]) == "CGTT$$G$CGGA$ACC\n"
+
+
+def test_ssa_against_golden(oracle, golden):
+    """ssa_gen1 / rb3_ssa_dump restated (ssa.c:17-81,198-213) == `ropebwt3 ssa -s SS` of the reference, byte for byte."""
+    g = golden("ssa")
+    for name, key in [("merge_small", "fmd"), ("rb2", "fmd_so2")]:
+        s, l, _ = oracle.fmd_decode(bytes(golden(name)[key]))
+        bwt = oracle.runs2plain(s, l)
+        for ss in (0, 3, 8):
+            assert oracle.ssa_image(bwt, ss) == bytes(g["%s_ss%d" % (name, ss)]), (name, ss)
