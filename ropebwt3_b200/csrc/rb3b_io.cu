@@ -10,12 +10,19 @@
  * Everything works on the canonical run list exported from the device index.
  */
 #include <string.h>
+#include <time.h>
 #include <stdlib.h>
 #include <string>
 #include <vector>
+#include <thread>
+#include <algorithm>
+#include <functional>
+#include <memory>
 #include "rb3b_internal.cuh"
 
 typedef std::vector<uint8_t> bytes_t;
+
+int64_t rb3b_get_param(const char *key, int64_t dflt); /* rb3b_runtime.cu */
 
 static inline int ilog2_u64(uint64_t v) { return v ? 63 - __builtin_clzll(v) : -1; }
 
@@ -141,6 +148,173 @@ private:
 		return n_frames;
 	}
 };
+
+
+/* ------------------------------------------------------------------ */
+/* parallel FMD writer                                                  */
+/* ------------------------------------------------------------------ */
+/*
+ * The writer above is the reference's greedy bit packer (rld_enc1, rld0.c:137-151): a run's code goes into the open
+ * block iff the payload bits used so far plus its width stay BELOW the block's payload capacity (the check only fires in
+ * the last usable word, and a code is < 64 bits wide, so this is equivalent), and the header width of a block depends on
+ * the number of symbols in the block before it.  Both only need prefix sums of code widths and run lengths, so:
+ *   1. widths and the two prefix sums                       -- all threads
+ *   2. block boundaries, one bounded binary search per block -- one thread (blocks are ~60 runs, so this is ~2 % of the work)
+ *   3. headers and payload bits of disjoint block ranges     -- all threads
+ *   4. the rank index (frames) from the headers              -- one thread, as before
+ * The image is byte-identical to FmdWriter's (tests/test_host.py).  A block with >= 2^30 symbols (64-bit headers) makes
+ * the whole call fall back to the sequential writer: that corner is exercised too rarely to deserve a second restatement.
+ */
+static inline int fmd_code_width(int64_t len) { int y = ilog2_u64((uint64_t)len), z = ilog2_u64((uint64_t)y + 1); return 2 * z + 1 + y + 3; }
+
+static void par_for(int n_threads, int64_t n, const std::function<void(int, int64_t, int64_t)> &f)
+{
+	if (n_threads <= 1 || n < 2) { f(0, 0, n); return; }
+	std::vector<std::thread> th;
+	for (int t = 0; t < n_threads; ++t) {
+		int64_t a = n * t / n_threads, b = n * (t + 1) / n_threads;
+		th.emplace_back([=, &f]() { f(t, a, b); });
+	}
+	for (auto &x : th) x.join();
+}
+
+/* sym/len: run list.  Returns false when the sequential writer must be used (list not canonical, 64-bit headers). */
+static bool fmd_encode_parallel(const uint8_t *sym, const int64_t *len, int64_t R, int n_threads, bytes_t &out)
+{
+	if (R < 2) return false;
+	struct timespec ts_; clock_gettime(CLOCK_MONOTONIC, &ts_); double t0_ = ts_.tv_sec + 1e-9 * ts_.tv_nsec;
+#define FMD_T(name) do { clock_gettime(CLOCK_MONOTONIC, &ts_); double t1_ = ts_.tv_sec + 1e-9 * ts_.tv_nsec; rb3b_stat_set("us_fmd_" name, (int64_t)((t1_ - t0_) * 1e6)); t0_ = t1_; } while (0)
+	/* 1. code widths (one byte per run), symbol totals, and the check that the list is canonical */
+	std::unique_ptr<uint8_t[]> wid(new uint8_t[(size_t)R]);
+	std::vector<uint64_t> tsym((size_t)n_threads * RB3B_ASIZE, 0);
+	std::vector<int> tbad(n_threads, 0);
+	par_for(n_threads, R, [&](int t, int64_t a, int64_t b) {
+		uint64_t c[RB3B_ASIZE] = {0, 0, 0, 0, 0, 0};
+		int bad = 0;
+		for (int64_t j = a; j < b; ++j) {
+			if (len[j] <= 0 || sym[j] >= RB3B_ASIZE || (j > 0 && sym[j] == sym[j - 1])) { bad = 1; break; }
+			wid[j] = (uint8_t)fmd_code_width(len[j]);
+			c[sym[j]] += (uint64_t)len[j];
+		}
+		tbad[t] = bad;
+		for (int i = 0; i < RB3B_ASIZE; ++i) tsym[(size_t)t * RB3B_ASIZE + i] = c[i];
+	});
+	uint64_t tot_sym[RB3B_ASIZE] = {0, 0, 0, 0, 0, 0}, total = 0;
+	for (int t = 0; t < n_threads; ++t) {
+		if (tbad[t]) return false;
+		for (int i = 0; i < RB3B_ASIZE; ++i) { tot_sym[i] += tsym[(size_t)t * RB3B_ASIZE + i]; total += tsym[(size_t)t * RB3B_ASIZE + i]; }
+	}
+	FMD_T("widths");
+	/* 2. block boundaries: one sequential scan over 9 bytes per run */
+	std::vector<int64_t> bstart;           /* first run of block b */
+	std::vector<uint8_t> btype;            /* header type of block b */
+	bstart.reserve((size_t)(R / 40 + 16)); btype.reserve(bstart.capacity());
+	{
+		int64_t j = 0, head = 0;
+		int type = 0;
+		while (j < R) {
+			const int64_t tail = head + FMD_SSIZE - (((head + FMD_SSIZE) & (FMD_LSIZE - 1)) == 0 ? 2 : 1);
+			const int64_t cap = (tail + 1 - (head + FMD_HDR_WORDS[type])) * 64;
+			if (type == 2 || cap <= 0) return false;
+			bstart.push_back(j); btype.push_back((uint8_t)type);
+			int64_t used = 0;
+			uint64_t nsym = 0;
+			while (j < R && used + wid[j] < cap) { used += wid[j]; nsym += (uint64_t)len[j]; ++j; } /* the first run always fits: a code is < 64 bits */
+			type = nsym < 0x4000 ? 0 : nsym < 0x40000000 ? 1 : 2;
+			head += FMD_SSIZE;
+		}
+		bstart.push_back(R); btype.push_back((uint8_t)type); /* trailing header-only block (rld_enc_finish, rld0.c:206-216) */
+		if (type == 2) return false;
+	}
+	FMD_T("bounds");
+	const int64_t n_blk = (int64_t)bstart.size(); /* including the trailing one */
+	const uint64_t n_words = (uint64_t)(n_blk - 1) * FMD_SSIZE + FMD_HDR_WORDS[btype[n_blk - 1]];
+	const uint64_t n_bytes = n_words * 8;
+	const uint64_t n_blks = n_words / FMD_SSIZE + 1, last = n_words / FMD_SSIZE * FMD_SSIZE;
+	const int ibits = ilog2_u64(total / n_blks) + 4;
+	const uint64_t n_frames = ((total + (1ULL << ibits) - 1) >> ibits) + 1;
+	const int W = RB3B_ASIZE + 1;
+	bytes_t().swap(out);
+	{ /* the image is written in place; only the part the threads do not cover is zeroed here */
+		std::unique_ptr<uint8_t[]> raw; (void)raw;
+		out.reserve(80 + (size_t)n_blk * FMD_SSIZE * 8 + (size_t)n_frames * W * 8);
+		out.resize(80 + (size_t)n_blk * FMD_SSIZE * 8);
+	}
+	uint64_t *words = (uint64_t*)(out.data() + 80); /* 80 is a multiple of 8 and vector storage is suitably aligned */
+	/* 3. headers + payload */
+	par_for(n_threads, n_blk, [&](int, int64_t b0, int64_t b1) {
+		for (int64_t b = b0; b < b1; ++b) {
+			uint64_t *blk = words + (size_t)b * FMD_SSIZE;
+			const int type = btype[b];
+			if (b > 0) { /* header = counts of the previous block (enc_next_block, rld0.c:107-135) */
+				uint64_t delta[RB3B_ASIZE + 1] = {0, 0, 0, 0, 0, 0, 0};
+				for (int64_t j = bstart[b - 1]; j < bstart[b]; ++j) { delta[0] += (uint64_t)len[j]; delta[sym[j] + 1] += (uint64_t)len[j]; }
+				uint8_t *dst = (uint8_t*)blk;
+				for (int i = 0; i <= RB3B_ASIZE; ++i) {
+					if (type == 0) { uint16_t v = (uint16_t)delta[i]; memcpy(dst + 2 * i, &v, 2); }
+					else { uint32_t v = (uint32_t)delta[i]; memcpy(dst + 4 * i, &v, 4); }
+				}
+				blk[0] |= (uint64_t)type << 62;
+			}
+			if (b == n_blk - 1) break; /* trailing block: header only */
+			int cur = FMD_HDR_WORDS[type], fr = 64;
+			for (int64_t j = bstart[b]; j < bstart[b + 1]; ++j) { /* rld_delta_enc1 + rld_enc1 */
+				const int y = ilog2_u64((uint64_t)len[j]), width = wid[j];
+				const uint64_t bits = ((((uint64_t)len[j] ^ (1ULL << y)) | (uint64_t)(y + 1) << y) << 3) | (uint64_t)sym[j];
+				if (width > fr) {
+					const int spill = width - fr;
+					blk[cur++] |= bits >> spill;
+					fr = 64 - spill;
+					blk[cur] = bits << fr;
+				} else {
+					fr -= width;
+					blk[cur] |= bits << fr;
+				}
+			}
+		}
+	});
+	FMD_T("encode");
+	/* 4. frames (rld_rank_index, rld0.c:163-204) and the header of the file */
+	std::vector<uint64_t> fr((size_t)n_frames * W, 0);
+	{
+		uint64_t k = 1, sofar[RB3B_ASIZE] = {0, 0, 0, 0, 0, 0};
+		for (uint64_t i = FMD_SSIZE; i <= last; i += FMD_SSIZE) {
+			const uint8_t *src = (const uint8_t*)&words[i];
+			const int type = (int)(words[i] >> 62);
+			uint64_t sum = 0;
+			for (int j = 1; j <= RB3B_ASIZE; ++j) {
+				if (type == 0) { uint16_t v; memcpy(&v, src + 2 * j, 2); sofar[j - 1] += v; }
+				else { uint32_t v; memcpy(&v, src + 4 * j, 4); sofar[j - 1] += v & 0x3fffffffu; }
+				sum += sofar[j - 1];
+			}
+			while (sum >= k << ibits) ++k;
+			if (k < n_frames) { fr[k * W] = i; memcpy(&fr[k * W + 1], sofar, sizeof(sofar)); }
+		}
+		for (k = 1; k < n_frames; ++k)
+			if (fr[k * W] == 0) memcpy(&fr[k * W], &fr[(k - 1) * W], W * 8);
+	}
+	out.resize(80 + n_bytes); /* drops the unused tail of the trailing block */
+	uint8_t *o = out.data();
+	const char magic[4] = { 'R', 'L', 'D', 3 };
+	const uint32_t geom = RB3B_ASIZE << 16 | 3;
+	const uint64_t zero = 0;
+	memcpy(o, magic, 4); memcpy(o + 4, &geom, 4); memcpy(o + 8, &zero, 8); memcpy(o + 16, &n_bytes, 8); memcpy(o + 24, &n_frames, 8);
+	memcpy(o + 32, tot_sym, RB3B_ASIZE * 8);
+	out.insert(out.end(), (const uint8_t*)fr.data(), (const uint8_t*)fr.data() + fr.size() * 8);
+	FMD_T("frames_image");
+	return true;
+}
+
+/* run list (not necessarily canonical) -> .fmd image; large lists go through the parallel writer */
+static void fmd_encode_any(const uint8_t *sym, const int64_t *len, int64_t n_runs, bytes_t &img)
+{
+	int n_threads = (int)rb3b_get_param("fmd_threads", 0);
+	if (n_threads <= 0) { n_threads = (int)std::thread::hardware_concurrency(); if (n_threads > 32) n_threads = 32; if (n_threads < 1) n_threads = 1; }
+	if (n_runs >= rb3b_get_param("fmd_parallel_min_runs", 1 << 20) && fmd_encode_parallel(sym, len, n_runs, n_threads, img)) return;
+	FmdWriter w;
+	for (int64_t i = 0; i < n_runs; ++i) w.put(sym[i], len[i]);
+	w.finish(img);
+}
 
 /* ------------------------------------------------------------------ */
 /* FMD reader (rld0.h:85-125 restated on a flat image)                  */
@@ -359,10 +533,8 @@ static int fetch_runs(const rb3b_index_t *x, std::vector<uint8_t> &sym, std::vec
 /* in-memory variants used by the tests and the CLI */
 extern "C" int64_t rb3b_fmd_image(int64_t n_runs, const uint8_t *sym, const int64_t *len, uint8_t **out)
 {
-	FmdWriter w;
 	bytes_t img;
-	for (int64_t i = 0; i < n_runs; ++i) w.put(sym[i], len[i]);
-	w.finish(img);
+	fmd_encode_any(sym, len, n_runs, img);
 	*out = (uint8_t*)malloc(img.size() ? img.size() : 1);
 	memcpy(*out, img.data(), img.size());
 	return (int64_t)img.size();
@@ -383,10 +555,8 @@ extern "C" int rb3b_dump_fmd(const rb3b_index_t *x, const char *fn)
 {
 	std::vector<uint8_t> sym; std::vector<int64_t> len;
 	TRY(fetch_runs(x, sym, len));
-	FmdWriter w;
 	bytes_t img;
-	for (size_t i = 0; i < sym.size(); ++i) w.put(sym[i], len[i]);
-	w.finish(img);
+	fmd_encode_any(sym.data(), len.data(), (int64_t)sym.size(), img);
 	return write_file(fn, img.data(), img.size());
 }
 

@@ -68,6 +68,41 @@ def test_product_fmd_writer_random_vs_oracle(oracle):
         assert R.fmd_image(sym, ln) == oracle.fmd_encode(sym, ln)
 
 
+@pytest.mark.parametrize("n,p,big,huge,threads", [(2, 0.3, 0, 0, 2), (9, 0.3, 0, 0, 4), (5000, 0.5, 20, 0, 3), (300000, 0.05, 3000, 0, 5),
+                                                    (400000, 0.3, 50, 0, 8), (200000, 0.3, 100, 3, 4), (3000000, 0.9, 0, 0, 7)])
+def test_parallel_fmd_writer_equals_sequential(oracle, n, p, big, huge, threads):
+    """The multi-threaded .fmd writer (prefix-free block boundaries, threads fill disjoint block ranges) must give the
+    bytes of the sequential restatement of rld_enc*/rld_rank_index (rld0.c:107-243): short runs, 32-bit block headers
+    (runs of 2^14..2^29), the 64-bit-header fall-back (runs >= 2^30), and non-canonical input."""
+    import ropebwt3_b200 as R
+    rng = np.random.default_rng(n + threads)
+    sym = (np.cumsum(rng.integers(1, 6, n)) % 6).astype(np.uint8)
+    ln = rng.geometric(p, n).astype(np.int64)
+    if big:
+        ln[rng.integers(0, n, big)] = rng.integers(1 << 14, 1 << 29, big)
+    if huge:
+        ln[rng.integers(0, n, huge)] = rng.integers(1 << 30, 1 << 33, huge)
+    try:
+        R.set_param("fmd_parallel_min_runs", 1 << 62)
+        seq = R.fmd_image(sym, ln)
+        R.set_param("fmd_parallel_min_runs", 2)
+        R.set_param("fmd_threads", threads)
+        assert R.fmd_image(sym, ln) == seq
+        if n <= 400000:
+            assert seq == oracle.fmd_encode(sym, ln)
+        if n >= 10:  # equal neighbours and empty runs: the parallel path must decline and the result still be right
+            sym2, ln2 = sym.copy(), ln.copy()
+            sym2[n // 2] = sym2[n // 2 - 1]
+            ln2[n // 3] = 0
+            R.set_param("fmd_parallel_min_runs", 1 << 62)
+            seq2 = R.fmd_image(sym2, ln2)
+            R.set_param("fmd_parallel_min_runs", 2)
+            assert R.fmd_image(sym2, ln2) == seq2
+    finally:
+        R.set_param("fmd_parallel_min_runs", 1 << 20)
+        R.set_param("fmd_threads", 0)
+
+
 @pytest.mark.parametrize("geom", [(64, 512), (16, 128), (4, 64)])
 def test_product_fmr_writer_roundtrip(oracle, geom):
     import ropebwt3_b200 as R
