@@ -63,7 +63,7 @@ def config_of(a, extra=None):
     c = {"workload": "configs[1]: merge-build of synthetic %.1f Mb bacterial genomes (0.5%% subst + 0.05%% indel from a random earlier genome), %d genome(s) = one batch = one merge of %d symbols (both strands); %d genomes in total" % (
         a.genome_len / 1e6, g, g * (2 * a.genome_len + 2), g * (1 + a.warmup + a.steps)),
         "genome_len": a.genome_len, "genomes": g * (1 + a.warmup + a.steps), "genomes_per_merge": g, "seed": SEED,
-        "l2": "no explicit flush needed: every step touches a new 10 MB batch, ~330 MB of per-batch LF/interleave/log arrays and an index of 40 MB to 1 GB (1 B/symbol), all far above the 126 MB L2"}
+        "l2": "no explicit flush needed: every step touches a new 10 MB batch, ~260 MB of per-batch LF / walk-order / interleave arrays and an index of 40 MB to 1 GB (1 B/symbol), all far above the 126 MB L2"}
     if extra:
         c.update(extra)
     return c
@@ -162,6 +162,14 @@ def run_b200(a):
         h_bwt.append(hb)
         lens.append(len(text))
     bases = [sum(len(g) for g in gs[b * G:(b + 1) * G]) for b in range(n_g)]
+    # what the finished index must hold (both strands + two sentinels per genome); full parity lives in tests/
+    expect = np.zeros(6, np.int64)
+    for g in gs:
+        cnt = np.bincount(g, minlength=6)[:6]
+        expect += cnt + cnt[[0, 4, 3, 2, 1, 5]]
+        expect[0] += 2
+    if world > 1:
+        del gs   # N genomes per step on N ranks: keep the host footprint of every rank down
     t_setup = time.time() - t0
 
     def barrier():
@@ -248,17 +256,13 @@ def run_b200(a):
         wall_e2e = time.time() - w0
         ms_e2e = max(e0.elapsed_time(e1), wall_e2e * 1e3)
         assert np.array_equal(acc_host, acc_dev), "host-buffer and device-pointer builds disagree"
-        # D2H per merge: 2x6 totals of the batch, 3 scalars (tiles), 2x6 totals + 2 counters of the new index, worklist counters
-        d2h = 8 * (12 + 3 + 12 + 2 + 2 + 2 * max(1, st["fix_rounds"] // max(1, a.steps)))
+        # D2H per merge: 7 words (batch totals + flag), 2 (chain cover), 1 (worklist size), 4 per fix-up round, 1 (unresolved),
+        # 1 (monotone flag), 7 (totals of the new index)
+        d2h = 8 * (7 + 2 + 1 + 4 * max(1, st["fix_rounds_total"] // max(1, a.steps)) + 1 + 1 + 7)
         e2e_val = timed_bases / (ms_e2e / 1e3)
     clocks = sampler.stop()
 
     # ---- sanity of the result (full parity lives in tests/): totals must add up
-    expect = np.zeros(6, np.int64)
-    for g in gs:
-        cnt = np.bincount(g, minlength=6)[:6]
-        expect += cnt + cnt[[0, 4, 3, 2, 1, 5]]
-        expect[0] += 2
     assert np.array_equal(np.diff(acc_dev), expect), "symbol totals of the built index are wrong"
 
     # max over ranks
