@@ -366,6 +366,7 @@ int main(int argc, char *argv[])
 		/* clamp the batch to what the device can sort and merge next to the finished index; the output does not depend
 		 * on the batching */
 		fit = rb3b_max_batch_symbols((idx ? rb3b_get_acc(idx, acc) : 0) + est_symbols);
+		if (use_rb2 && (sort_order || (idx && rb3b_index_get_order(idx)))) fit /= 2; /* RLO/RCLO batches are sorted as augmented strings of twice the length */
 		if (fit > 0 && (batch <= 0 || batch > fit)) {
 			LOG("batch size limited to %ld symbols by device memory", (long)fit);
 			batch = fit;

@@ -41,7 +41,7 @@ const char *rb3b_last_error(void);
 const char *rb3b_version(void);
 int         rb3b_set_stream(void *cuda_stream);    /* run on a caller-owned cudaStream_t (NULL = own stream) */
 int         rb3b_sync(void);
-int         rb3b_set_param(const char *key, int64_t value);   /* tuning knobs: "seg_len", "splitter", "rank_lanes" */
+int         rb3b_set_param(const char *key, int64_t value);   /* tuning knobs, all optional: "seg_len" (walk slice length, 0 = by batch size), "fine_len", "halo_segments", "index_kind", "bitmap_max_symbols", "fmd_threads", ... */
 int64_t     rb3b_get_stat(const char *key);        /* counters of the last call: "kernel_launches", "n_segments", "fix_rounds", "unresolved_rows", "n_blocks" ... */
 
 /* ---- index life cycle (replaces mr_init / mr_destroy, mrope.c:15-34) ------- */

@@ -96,7 +96,6 @@ enum { T_PREP, T_WALK1, T_WALKFIX, T_MERGE, T_SCATTER, T_BWT, T_COUNT };
 void rb3b_tic(int id);
 void rb3b_toc(int id);
 void rb3b_tflush(void);
-void rb3b_l2_pin(const void *p, size_t bytes);   /* persisting-L2 access window for the library stream; (0,0) clears it */
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
 	return rb3b_fail(RB3B_ENODEV, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)

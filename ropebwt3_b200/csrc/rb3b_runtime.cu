@@ -98,35 +98,6 @@ void rb3b_tflush(void)
 		}
 }
 
-void rb3b_l2_pin(const void *p, size_t bytes)
-{
-	static size_t max_win = 0, set_aside = 0;
-	static int probed = 0;
-	if (!probed) {
-		int dev = 0, v = 0;
-		probed = 1;
-		cudaGetDevice(&dev);
-		if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, dev) == cudaSuccess) max_win = (size_t)v;
-		if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, dev) == cudaSuccess) set_aside = (size_t)v;
-		if (set_aside) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside);
-		cudaGetLastError();
-		rb3b_stat_set("l2_persist_max", (int64_t)set_aside);
-	}
-	if (max_win == 0 || set_aside == 0) return;
-	cudaStreamAttrValue a;
-	memset(&a, 0, sizeof(a));
-	if (p && bytes) {
-		a.accessPolicyWindow.base_ptr = (void*)p;
-		a.accessPolicyWindow.num_bytes = bytes < max_win ? bytes : max_win;
-		a.accessPolicyWindow.hitRatio = bytes <= set_aside ? 1.0f : (float)set_aside / (float)bytes;
-		a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-		a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-	}
-	cudaStreamSetAttribute(rb3b_stream, cudaStreamAttributeAccessPolicyWindow, &a);
-	if (!p) cudaCtxResetPersistingL2Cache();
-	cudaGetLastError();
-}
-
 void rb3b_stat_set(const char *key, int64_t v) { g_stats[key] = v; }
 void rb3b_stat_add(const char *key, int64_t v) { g_stats[key] += v; }
 
