@@ -170,3 +170,24 @@ def test_ssa_against_golden(oracle, golden):
         bwt = oracle.runs2plain(s, l)
         for ss in (0, 3, 8):
             assert oracle.ssa_image(bwt, ss) == bytes(g["%s_ss%d" % (name, ss)]), (name, ss)
+
+
+def test_rb2_closed_form_fuzz_against_live_reference(oracle):
+    """Random tiny read sets (small alphabets, duplicates, reads that are suffixes of others, Ns, one or both strands):
+    the closed form of the RLO/RCLO order that the CUDA path sorts by == the reference CLI's `build -s/-r/-2`."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(2024)
+    for it in range(40):
+        n, alpha = int(rng.integers(1, 12)), int(rng.integers(1, 6))
+        reads = ["".join("ACGTN"[int(x)] for x in rng.integers(0, alpha, int(rng.integers(1, 9)))) for _ in range(n)]
+        if rng.random() < 0.5 and n > 1:
+            reads.append(reads[0])
+        if rng.random() < 0.3:
+            reads.append(reads[0][1:] or "A")
+        inp = ("\n".join(reads) + "\n").encode()
+        both = rng.random() < 0.5
+        for so, flag in [(1, "-s"), (2, "-r"), (0, "-2")]:
+            want = ref.run(["build", "-L", flag] + ([] if both else ["-R"]) + ["-"], stdin=inp).decode().strip()
+            assert oracle.to_ascii(oracle.sorted_bwt(oracle.encode_batch(reads, rev=both), so)) == want, (flag, both, reads)
