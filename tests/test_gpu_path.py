@@ -523,3 +523,47 @@ def test_ssa_larger_against_oracle(rb3, oracle, tmp_path):
     out = str(tmp_path / "x.ssa")
     idx.ssa_dump(out, 6)
     assert open(out, "rb").read() == oracle.ssa_image(oracle.runs2plain(s, l), 6)
+
+
+# ---------------------------------------------------------------- BASELINE config 1 at full size
+
+def test_config1_full_size_batching_invariance(rb3, index_kind):
+    """BASELINE.json configs[1] at its full size (100 synthetic 5 Mb genomes, 10^9 symbols; bench.py's exact set): the
+    reference's canonical-index property (the same collection gives the same BWT for any batching) checked
+    between 99 merges of one genome and 9 merges of ten genomes, plus the symbol totals the collection must have."""
+    if index_kind == "rle":
+        pytest.skip("full size is run on the default (bitmap) layout only")
+    import torch
+    from ropebwt3_b200 import synth, capi
+    gs = synth.genomes(100, 5_000_000, seed=43, sub=0.005, indel=0.0005)
+    expect = np.zeros(6, np.int64)
+    for g in gs:
+        cnt = np.bincount(g, minlength=6)[:6]
+        expect += cnt + cnt[[0, 4, 3, 2, 1, 5]]
+        expect[0] += 2
+
+    def build(per_merge):
+        idx = None
+        for b in range(0, len(gs), per_merge):
+            text = synth.batch_text(gs[b:b + per_merge])
+            d_text = torch.from_numpy(text).cuda()
+            d_bwt = torch.empty_like(d_text)
+            capi.check(capi.lib().rb3b_build_bwt_dev(len(text), d_text.data_ptr(), d_bwt.data_ptr()))
+            if idx is None:
+                idx = rb3.Index.from_plain_dev(d_bwt.data_ptr(), len(text))
+                idx.reserve(int(expect.sum()))
+            else:
+                idx.merge_plain_dev(d_bwt.data_ptr(), len(text))
+            rb3.sync()
+        return idx
+
+    one, ten = build(1), build(10)
+    assert np.array_equal(np.diff(one.acc()), expect) and np.array_equal(np.diff(ten.acc()), expect)
+    s1, l1 = one.export_runs()
+    s10, l10 = ten.export_runs()
+    assert len(s1) == len(s10) and np.array_equal(s1, s10) and np.array_equal(l1, l10)
+    rng = np.random.default_rng(1)
+    k = rng.integers(0, int(expect.sum()), 2000).astype(np.int64)
+    ok1, r1 = one.rank1a(k)
+    ok10, r10 = ten.rank1a(k)
+    assert np.array_equal(ok1, ok10) and np.array_equal(r1, r10)
