@@ -384,9 +384,11 @@ static int rle_put(uint8_t *p, int c, int64_t l)
 
 static const int64_t RLE_MAX_RUN = (1LL << 43) - 1; /* rle.h:68-73 */
 
-struct Leaf { int64_t cnt[RB3B_ASIZE]; std::vector<uint8_t> code; };
+/* the leaves of one rope: run codes back to back in `code`, one LeafMeta per leaf */
+struct LeafMeta { int64_t cnt[RB3B_ASIZE]; size_t off; uint16_t nb; };
+struct RopeImg { std::vector<uint8_t> code; std::vector<LeafMeta> leaf; bytes_t out; };
 
-static void fmr_node(bytes_t &o, const std::vector<Leaf> &lv, size_t lo, size_t hi, int height, int fan)
+static void fmr_node(bytes_t &o, const RopeImg &R, size_t lo, size_t hi, int height, int fan)
 { /* pre-order node record, rope.c:265-280 */
 	size_t per = 1;
 	for (int i = 0; i < height; ++i) per *= fan;
@@ -399,55 +401,96 @@ static void fmr_node(bytes_t &o, const std::vector<Leaf> &lv, size_t lo, size_t 
 		/* spread the leaves evenly over the children */
 		size_t a = lo + (hi - lo) * i / n_child, b = lo + (hi - lo) * (i + 1) / n_child;
 		if (is_bottom) {
-			const Leaf &L = lv[a];
-			uint16_t nb = (uint16_t)L.code.size();
+			const LeafMeta &L = R.leaf[a];
 			o.insert(o.end(), (const uint8_t*)L.cnt, (const uint8_t*)L.cnt + 48);
-			o.insert(o.end(), (uint8_t*)&nb, (uint8_t*)&nb + 2);
-			o.insert(o.end(), L.code.begin(), L.code.end());
-		} else fmr_node(o, lv, a, b, height - 1, fan);
+			o.insert(o.end(), (const uint8_t*)&L.nb, (const uint8_t*)&L.nb + 2);
+			o.insert(o.end(), R.code.begin() + L.off, R.code.begin() + L.off + L.nb);
+		} else fmr_node(o, R, a, b, height - 1, fan);
 	}
+}
+
+/* rope a = rows [lo, hi) of the BWT (mrope.c:157, fm-index.c:72-81), starting `used` symbols into run ri */
+static void fmr_rope(const uint8_t *sym, const int64_t *len, int64_t n_runs, int64_t ri, int64_t used, int64_t lo, int64_t hi, int max_nodes, int block_len, RopeImg &R)
+{
+	const int leaf_cap = block_len - 18 - 16; /* keep clear of the split trigger nbytes + 18 > block_len (rope.c:143) */
+	const int fan = max_nodes > 4 ? max_nodes / 2 : 2; /* half-full nodes: the CPU code splits full ones on the way down */
+	int psym = -1;
+	int64_t plen = 0, pos = lo;
+	{ /* a guess of the code size: ~1.3 bytes per run, a share of the runs proportional to the rope's share of the rows is too crude, so cap it */
+		int64_t guess = (hi - lo) / 4 + 64, cap = n_runs / 2 + 64;
+		R.code.resize((size_t)(guess < cap ? guess : cap));
+	}
+	size_t n_code = 0; /* bytes of R.code in use; the vector is grown in large steps and trimmed at the end */
+	LeafMeta *cur = 0;
+	auto emit = [&](int c, int64_t left) { /* one (fused) run of the rope, cut into codable pieces */
+		while (left > 0) {
+			const int64_t l = left < RLE_MAX_RUN ? left : RLE_MAX_RUN;
+			if (n_code + 8 > R.code.size()) R.code.resize(R.code.size() + R.code.size() / 2 + 4096);
+			const int nb = rle_put(&R.code[n_code], c, l);
+			if (cur == 0 || (int)cur->nb + nb > leaf_cap) {
+				LeafMeta m;
+				memset(m.cnt, 0, sizeof(m.cnt)); m.off = n_code; m.nb = 0;
+				R.leaf.push_back(m);
+				cur = &R.leaf.back();
+			}
+			n_code += nb;
+			cur->nb = (uint16_t)(cur->nb + nb);
+			cur->cnt[c] += l;
+			left -= l;
+		}
+	};
+	while (pos < hi) {
+		int64_t t = len[ri] - used;
+		if (t > hi - pos) t = hi - pos;
+		if (t > 0) { /* neighbours with the same symbol are fused, empty runs dropped (the list need not be canonical) */
+			if (sym[ri] == psym) plen += t;
+			else { if (plen) emit(psym, plen); psym = sym[ri]; plen = t; }
+		}
+		used += t; pos += t;
+		if (used == len[ri]) ++ri, used = 0;
+	}
+	if (plen) emit(psym, plen);
+	R.code.resize(n_code);
+	if (R.leaf.empty()) { LeafMeta m; memset(m.cnt, 0, sizeof(m.cnt)); m.off = 0; m.nb = 0; R.leaf.push_back(m); } /* empty rope: one empty leaf (rope.c:64-67) */
+	int32_t mn = max_nodes, bl = block_len;
+	R.out.reserve(R.code.size() + R.leaf.size() * 52 + 64);
+	R.out.insert(R.out.end(), (uint8_t*)&mn, (uint8_t*)&mn + 4);
+	R.out.insert(R.out.end(), (uint8_t*)&bl, (uint8_t*)&bl + 4);
+	int height = 0;
+	for (size_t cap = fan; cap < R.leaf.size(); cap *= fan) ++height;
+	fmr_node(R.out, R, 0, R.leaf.size(), height, fan);
 }
 
 static void fmr_encode(const uint8_t *sym, const int64_t *len, int64_t n_runs, int max_nodes, int block_len, bytes_t &o)
 {
 	int64_t acc[RB3B_ASIZE + 1] = {0, 0, 0, 0, 0, 0, 0};
-	for (int64_t i = 0; i < n_runs; ++i) acc[sym[i] + 1] += len[i];
+	for (int64_t i = 0; i < n_runs; ++i) acc[sym[i] + 1] += len[i] > 0 ? len[i] : 0;
 	for (int a = 0; a < RB3B_ASIZE; ++a) acc[a + 1] += acc[a];
-	const uint8_t hdr[4] = { 'R', 'B', 2, 0 }; /* sorting order 0: input order */
-	o.assign(hdr, hdr + 4);
-	const int leaf_cap = block_len - 18 - 16; /* keep clear of the split trigger nbytes + 18 > block_len (rope.c:143) */
-	const int fan = max_nodes > 4 ? max_nodes / 2 : 2; /* half-full nodes: the CPU code splits full ones on the way down */
-	int64_t ri = 0, used = 0, pos = 0;
-	for (int a = 0; a < RB3B_ASIZE; ++a) {
-		std::vector<Leaf> lv;
-		RunList rope; /* rope a = rows [acc[a], acc[a+1]) (mrope.c:157, fm-index.c:72-81) */
-		while (pos < acc[a + 1]) {
-			int64_t t = len[ri] - used;
-			if (t > acc[a + 1] - pos) t = acc[a + 1] - pos;
-			rope.add(sym[ri], t);
-			used += t; pos += t;
-			if (used == len[ri]) ++ri, used = 0;
+	/* where every rope starts in the run list */
+	int64_t start_ri[RB3B_ASIZE], start_used[RB3B_ASIZE];
+	{
+		int64_t pos = 0, ri = 0;
+		for (int a = 0; a < RB3B_ASIZE; ++a) {
+			while (ri < n_runs && pos + (len[ri] > 0 ? len[ri] : 0) <= acc[a] && !(pos == acc[a] && len[ri] > 0)) { pos += len[ri] > 0 ? len[ri] : 0; ++ri; }
+			start_ri[a] = ri; start_used[a] = acc[a] - pos;
 		}
-		for (size_t i = 0; i < rope.sym.size(); ++i) {
-			int64_t left = rope.len[i];
-			while (left > 0) {
-				int64_t l = left < RLE_MAX_RUN ? left : RLE_MAX_RUN;
-				uint8_t tmp[8];
-				int nb = rle_put(tmp, rope.sym[i], l);
-				if (lv.empty() || (int)lv.back().code.size() + nb > leaf_cap) { lv.push_back(Leaf()); memset(lv.back().cnt, 0, 48); }
-				lv.back().code.insert(lv.back().code.end(), tmp, tmp + nb);
-				lv.back().cnt[rope.sym[i]] += l;
-				left -= l;
-			}
-		}
-		if (lv.empty()) { lv.push_back(Leaf()); memset(lv.back().cnt, 0, 48); } /* empty rope: one empty leaf (rope.c:64-67) */
-		int32_t mn = max_nodes, bl = block_len;
-		o.insert(o.end(), (uint8_t*)&mn, (uint8_t*)&mn + 4);
-		o.insert(o.end(), (uint8_t*)&bl, (uint8_t*)&bl + 4);
-		int height = 0;
-		for (size_t cap = fan; cap < lv.size(); cap *= fan) ++height;
-		fmr_node(o, lv, 0, lv.size(), height, fan);
 	}
+	RopeImg R[RB3B_ASIZE];
+	int n_threads = (int)rb3b_get_param("fmd_threads", 0);
+	auto work = [&](int a) { if (acc[a + 1] > acc[a]) fmr_rope(sym, len, n_runs, start_ri[a], start_used[a], acc[a], acc[a + 1], max_nodes, block_len, R[a]);
+	                         else fmr_rope(sym, len, n_runs, 0, 0, 0, 0, max_nodes, block_len, R[a]); };
+	if (n_threads == 1 || n_runs < (1 << 16)) { for (int a = 0; a < RB3B_ASIZE; ++a) work(a); }
+	else { /* the six ropes are independent */
+		std::vector<std::thread> th;
+		for (int a = 0; a < RB3B_ASIZE; ++a) th.emplace_back(work, a);
+		for (auto &t : th) t.join();
+	}
+	const uint8_t hdr[4] = { 'R', 'B', 2, 0 }; /* sorting order 0: input order (rb3b_dump_fmr patches it) */
+	size_t tot = 4;
+	for (int a = 0; a < RB3B_ASIZE; ++a) tot += R[a].out.size();
+	o.clear(); o.reserve(tot);
+	o.insert(o.end(), hdr, hdr + 4);
+	for (int a = 0; a < RB3B_ASIZE; ++a) o.insert(o.end(), R[a].out.begin(), R[a].out.end());
 }
 
 struct FmrCursor { const uint8_t *p, *end; };
