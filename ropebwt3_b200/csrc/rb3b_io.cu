@@ -234,12 +234,10 @@ static bool fmd_encode_parallel(const uint8_t *sym, const int64_t *len, int64_t 
 	const int ibits = ilog2_u64(total / n_blks) + 4;
 	const uint64_t n_frames = ((total + (1ULL << ibits) - 1) >> ibits) + 1;
 	const int W = RB3B_ASIZE + 1;
+	/* the image is assembled in place: header, then whole blocks (zero-filled, the threads OR their bits in), frames last */
 	bytes_t().swap(out);
-	{ /* the image is written in place; only the part the threads do not cover is zeroed here */
-		std::unique_ptr<uint8_t[]> raw; (void)raw;
-		out.reserve(80 + (size_t)n_blk * FMD_SSIZE * 8 + (size_t)n_frames * W * 8);
-		out.resize(80 + (size_t)n_blk * FMD_SSIZE * 8);
-	}
+	out.reserve(80 + (size_t)n_blk * FMD_SSIZE * 8 + (size_t)n_frames * W * 8);
+	out.resize(80 + (size_t)n_blk * FMD_SSIZE * 8);
 	uint64_t *words = (uint64_t*)(out.data() + 80); /* 80 is a multiple of 8 and vector storage is suitably aligned */
 	/* 3. headers + payload */
 	par_for(n_threads, n_blk, [&](int, int64_t b0, int64_t b1) {
@@ -302,6 +300,7 @@ static bool fmd_encode_parallel(const uint8_t *sym, const int64_t *len, int64_t 
 	memcpy(o + 32, tot_sym, RB3B_ASIZE * 8);
 	out.insert(out.end(), (const uint8_t*)fr.data(), (const uint8_t*)fr.data() + fr.size() * 8);
 	FMD_T("frames_image");
+#undef FMD_T
 	return true;
 }
 
