@@ -292,6 +292,34 @@ int main(int argc, char *argv[])
 
 	t_real0 = realtime();
 	if (argc >= 2 && strcmp(argv[1], "version") == 0) { puts(rb3b_version()); return 0; }
+	if (argc >= 2 && strcmp(argv[1], "batches") == 0) { /* host-only: what the reader thread hands to the device, one line per batch */
+		pipe_t P;
+		pthread_t tid;
+		batch_t *b;
+		memset(&P, 0, sizeof(P));
+		--argc; ++argv;
+		while ((c = getopt(argc, argv, "m:LFR")) >= 0) {
+			if (c == 'm') batch = parse_num(optarg);
+			else if (c == 'L') is_line = 1;
+			else if (c == 'F') no_for = 1;
+			else if (c == 'R') no_rev = 1;
+		}
+		P.argc = argc; P.argv = argv; P.first = optind; P.is_line = is_line; P.no_for = no_for; P.no_rev = no_rev; P.batch = batch;
+		pthread_mutex_init(&P.mu, 0); pthread_cond_init(&P.cv, 0);
+		if (pthread_create(&tid, 0, reader_main, &P) != 0) return 1;
+		while ((b = pipe_next(&P)) != 0) {
+			size_t k;
+			if (b->open_failed) printf("%d\t-1\t!\n", b->file - optind);
+			else {
+				printf("%d\t%ld\t", b->file - optind, (long)b->n_seq);
+				for (k = 0; k < b->seq.l; ++k) putchar("$ACGTN"[(unsigned char)b->seq.s[k] < 6 ? (unsigned char)b->seq.s[k] : 5]);
+				printf("\t%d\n", b->last_of_file);
+			}
+			pipe_release(&P);
+		}
+		pthread_join(tid, 0);
+		return 0;
+	}
 	if (argc >= 2 && strcmp(argv[1], "ssa") == 0) { /* main_ssa, ssa.c:247-279 */
 		int ss = 8;
 		const char *fn_out = "-";

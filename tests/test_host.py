@@ -150,3 +150,61 @@ def test_synth_is_seeded():
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
     t = synth.batch_text(a[:1])
     assert t[-1] == 0 and (t == 0).sum() == 2
+
+
+def _cli_batches(args, stdin=None):
+    import subprocess
+    cli = os.path.join(ROOT, "cli", "ropebwt3-b200")
+    if not os.path.exists(cli):
+        pytest.fail("cli/ropebwt3-b200 is not built (run __graft_entry__.build())")
+    p = subprocess.run([cli, "batches"] + [str(a) for a in args], input=stdin, stdout=subprocess.PIPE, check=True)
+    out = []
+    for line in p.stdout.decode().splitlines():
+        f = line.split("\t")
+        out.append((int(f[0]), int(f[1]), f[2], int(f[3]) if len(f) > 3 else 0))
+    return out
+
+
+def test_cli_reader_and_batching(oracle, tmp_path):
+    """The host side of `build` that feeds the device (reader thread of cli/rb3b_build.c), without a GPU: FASTA
+    (multi-line, lower case, Ns, CRLF), FASTQ, gzip, one-sequence-per-line, stdin; forward strand then reverse complement
+    per record (io.c:84-102); a batch closes after the record that makes it longer than -m (io.c:114,119); an unopenable
+    file is reported and skipped (build.c:207-210)."""
+    import gzip
+    rng = np.random.default_rng(8)
+    seqs = ["".join("ACGTN"[int(x)] for x in rng.integers(0, 5, int(rng.integers(1, 200)))) for _ in range(40)]
+    fa = tmp_path / "a.fa"
+    with open(fa, "w") as f:
+        for i, s in enumerate(seqs):
+            body = s.lower() if i % 3 == 0 else s
+            f.write(">s%d desc\r\n" % i if i % 5 == 0 else ">s%d\n" % i)
+            f.write("\n".join(body[k:k + 60] for k in range(0, len(body), 60)) + ("\r\n" if i % 5 == 0 else "\n"))
+    fq = tmp_path / "a.fq.gz"
+    with gzip.open(fq, "wt") as f:
+        for i, s in enumerate(seqs):
+            f.write("@r%d\n%s\n+\n%s\n" % (i, s, "@" * len(s)))  # '@' in the quality line must not start a record
+    ln = tmp_path / "a.txt"
+    open(ln, "w").write("\n".join(seqs) + "\n")
+    want = oracle.to_ascii(oracle.encode_batch(seqs))
+    for fn, extra in [(fa, []), (fq, []), (ln, ["-L"])]:
+        got = _cli_batches(extra + [fn])
+        assert len(got) == 1 and got[0][:3] == (0, 2 * len(seqs), want) and got[0][3] == 1, fn
+    assert _cli_batches(["-L", "-"], stdin=open(ln, "rb").read())[0][2] == want
+    assert _cli_batches(["-L", "-R", ln])[0][2] == oracle.to_ascii(oracle.encode_batch(seqs, rev=False))
+    assert _cli_batches(["-L", "-F", ln])[0][2] == oracle.to_ascii(oracle.encode_batch(seqs, fwd=False))
+    # batching
+    m = 500
+    got = _cli_batches(["-m", m, fa, "/nonexistent.fa", ln, "-L"])   # options permute like ketopt/getopt
+    exp, cur, n = [], [], 0
+    for s in seqs:
+        cur.append(s)
+        n += 2 * len(s) + 2
+        if n > m:
+            exp.append(cur)
+            cur, n = [], 0
+    if cur:
+        exp.append(cur)
+    mine = [g for g in got if g[0] == 2 and g[1] > 0]
+    assert [g[2] for g in mine] == [oracle.to_ascii(oracle.encode_batch(b)) for b in exp]
+    assert all(len(g[2]) > m for g in mine[:-1]) and mine[-1][3] == 1 or (got[-1][0] == 2 and got[-1][3] == 1)
+    assert any(g[0] == 1 and g[1] == -1 for g in got)               # the unopenable file
