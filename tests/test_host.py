@@ -208,3 +208,21 @@ def test_cli_reader_and_batching(oracle, tmp_path):
     assert [g[2] for g in mine] == [oracle.to_ascii(oracle.encode_batch(b)) for b in exp]
     assert all(len(g[2]) > m for g in mine[:-1]) and mine[-1][3] == 1 or (got[-1][0] == 2 and got[-1][3] == 1)
     assert any(g[0] == 1 and g[1] == -1 for g in got)               # the unopenable file
+
+
+def test_cli_reader_against_live_reference_on_odd_input(oracle):
+    """Our reader + the oracle's BWT == the reference CLI end to end, on inputs that stress the parser (blank lines,
+    IUPAC codes and gaps, spaces, CRLF, no trailing newline, multi-line FASTQ, junk before the first header)."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    asc = np.zeros(256, np.uint8)
+    for i, ch in enumerate(b"$ACGTN"):
+        asc[ch] = i
+    cases = [([], b">a\nACGT\n\nACG\n>b\n\nTT\n"), ([], b">a\nACGRYKMSWNnacgtBDHV\n>b\nAC-GT*AC\n"), ([], b">a desc more\nAC GT\tAC\n>b\nGGA\n"),
+             ([], b">a\r\nACGT\r\nAC\r\n>b\r\nGG\r\n"), ([], b">a\nACGT\n>b\nGGC"), ([], b"@r1\nACGT\nACG\n+\nIIII\nIII\n@r2\nGGA\n+r2\n@@@\n"),
+             ([], b"junk\n>a\nACG\n>b\nTTG\n"), ([], b">a\nAC>GT\n>b\nGG\n"), (["-L"], b"ACGT\r\nGG\r\n"), (["-L"], b"acgtn\nGG\n"), (["-L"], b"ACG\nTT")]
+    for opts, data in cases:
+        got = _cli_batches(opts + ["-"], stdin=data)
+        text = np.concatenate([asc[np.frombuffer(g[2].encode(), np.uint8)] for g in got if g[1] > 0])
+        assert oracle.to_ascii(oracle.build_bwt(text)) == ref.run(["build"] + opts + ["-"], stdin=data).decode().strip(), data
