@@ -121,6 +121,10 @@ int rb3b_restore(rb3b_index_t *idx, const char *fn);
  * rld_enc/rld_enc_finish/rld_rank_index/rld_dump (rld0.c:137-243) and mr_dump/rope_dump_node (mrope.c:152, rope.c:265-287). */
 int64_t rb3b_fmd_image(int64_t n_runs, const uint8_t *sym, const int64_t *len, uint8_t **out);
 int64_t rb3b_fmr_image(int64_t n_runs, const uint8_t *sym, const int64_t *len, int max_nodes, int block_len, uint8_t **out);
+/* host-only reader behind rb3b_restore (rld_restore + the decode loop of rb3_enc_fmd2fmr, fm-index.c:56-85; mr_restore,
+ * mrope.c:161-177): a .fmd or .fmr file image -> canonical run list in malloc'd arrays (rb3b_host_free), returns the
+ * number of runs; *sorting_order = the .fmr's order byte (0 for .fmd) */
+int64_t rb3b_runs_from_image(const uint8_t *image, int64_t n_bytes, uint8_t **sym, int64_t **len, int *sorting_order);
 void    rb3b_host_free(void *p);
 
 /* ---- sampled suffix array (`ropebwt3 ssa`, ssa.c) ---------------------------------- */

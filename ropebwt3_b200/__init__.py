@@ -219,3 +219,16 @@ def fmr_image(sym, ln, max_nodes=64, block_len=512):
     out = C.string_at(p, n)
     capi.lib().rb3b_host_free(p)
     return out
+
+
+def runs_from_image(img):
+    """Host-only: bytes of a .fmd / .fmr file -> (sym, len, sorting_order), the canonical run list rb3b_restore loads."""
+    import ctypes as C
+    a = np.frombuffer(img, np.uint8)
+    ps, pl, so = C.c_void_p(), C.c_void_p(), C.c_int(0)
+    n = capi.check(capi.lib().rb3b_runs_from_image(capi.ptr(a), len(a), C.byref(ps), C.byref(pl), C.byref(so)))
+    sym = np.frombuffer(C.string_at(ps, n), np.uint8).copy()
+    ln = np.frombuffer(C.string_at(pl, n * 8), np.int64).copy()
+    capi.lib().rb3b_host_free(ps)
+    capi.lib().rb3b_host_free(pl)
+    return sym, ln, so.value

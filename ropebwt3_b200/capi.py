@@ -56,6 +56,7 @@ SIGNATURES = {
     "rb3b_restore": (_int, [_vp, C.c_char_p]),
     "rb3b_fmd_image": (_i64, [_i64, _vp, _vp, C.POINTER(_vp)]),
     "rb3b_fmr_image": (_i64, [_i64, _vp, _vp, _int, _int, C.POINTER(_vp)]),
+    "rb3b_runs_from_image": (_i64, [_vp, _i64, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_int)]),
     "rb3b_host_free": (None, [_vp]),
     "rb3b_build_bwt": (_int, [_i64, _vp, _vp]),
     "rb3b_build_bwt_dev": (_int, [_i64, _vp, _vp]),

@@ -340,6 +340,41 @@ static uint64_t payload_bits(const uint64_t *w, int64_t first, int64_t tail, int
 	return x;
 }
 
+static int host_threads(void)
+{
+	int n = (int)rb3b_get_param("fmd_threads", 0);
+	if (n <= 0) { n = (int)std::thread::hardware_concurrency(); if (n > 32) n = 32; if (n < 1) n = 1; }
+	return n;
+}
+
+/* append b to a, fusing the junction */
+static void runs_append(RunList &a, const RunList &b)
+{
+	size_t i = 0;
+	if (!a.sym.empty() && !b.sym.empty() && a.sym.back() == b.sym[0]) { a.len.back() += b.len[0]; i = 1; }
+	a.sym.insert(a.sym.end(), b.sym.begin() + i, b.sym.end());
+	a.len.insert(a.len.end(), b.len.begin() + i, b.len.end());
+}
+
+/* the runs of blocks [h0, h1) (word offsets, multiples of FMD_SSIZE) */
+static void fmd_decode_blocks(const uint64_t *w, int64_t h0, int64_t h1, RunList &runs)
+{
+	for (int64_t h = h0; h < h1; h += FMD_SSIZE) {
+		int64_t first = h + FMD_HDR_WORDS[w[h] >> 62 > 2 ? 2 : w[h] >> 62], tail = h + FMD_SSIZE - (((h + FMD_SSIZE) & (FMD_LSIZE - 1)) == 0 ? 2 : 1), bit = 0;
+		for (;;) {
+			uint64_t x = payload_bits(w, first, tail, bit);
+			if (x >> 58 == 0) break; /* six zero bits cannot start a code */
+			int z = __builtin_clzll(x);
+			int y = (int)(x << z >> (63 - z)) - 1;
+			uint64_t l = (y ? payload_bits(w, first, tail, bit + 2 * z + 1) >> (64 - y) : 0) | 1ULL << y;
+			int c = (int)(payload_bits(w, first, tail, bit + 2 * z + 1 + y) >> 61);
+			if (c >= RB3B_ASIZE) break;
+			runs.add(c, (int64_t)l);
+			bit += 2 * z + 1 + y + 3;
+		}
+	}
+}
+
 static int fmd_parse(const bytes_t &img, RunList &runs)
 {
 	if (img.size() < 80 || memcmp(img.data(), "RLD\3", 4) != 0) return RB3B_EFORMAT;
@@ -347,22 +382,16 @@ static int fmd_parse(const bytes_t &img, RunList &runs)
 	memcpy(&geom, &img[4], 4); memcpy(&n_bytes, &img[16], 8); memcpy(&n_frames, &img[24], 8);
 	if (geom != (RB3B_ASIZE << 16 | 3)) return rb3b_fail(RB3B_EFORMAT, "FMD with asize/sbits 0x%x is not supported (only 6/3)", geom);
 	if (img.size() < 80 + n_bytes) return rb3b_fail(RB3B_EFORMAT, "truncated FMD");
-	std::vector<uint64_t> w(n_bytes / 8 + 1, 0);
+	std::vector<uint64_t> w(n_bytes / 8 + FMD_SSIZE + 1, 0);
 	memcpy(w.data(), &img[80], n_bytes);
-	int64_t n_words = n_bytes / 8, last = n_words / FMD_SSIZE * FMD_SSIZE;
-	for (int64_t h = 0; h < last; h += FMD_SSIZE) {
-		int64_t first = h + FMD_HDR_WORDS[w[h] >> 62], tail = h + FMD_SSIZE - (((h + FMD_SSIZE) & (FMD_LSIZE - 1)) == 0 ? 2 : 1), bit = 0;
-		for (;;) {
-			uint64_t x = payload_bits(w.data(), first, tail, bit);
-			if (x >> 58 == 0) break; /* six zero bits cannot start a code */
-			int z = __builtin_clzll(x);
-			int y = (int)(x << z >> (63 - z)) - 1;
-			uint64_t l = (y ? payload_bits(w.data(), first, tail, bit + 2 * z + 1) >> (64 - y) : 0) | 1ULL << y;
-			int c = (int)(payload_bits(w.data(), first, tail, bit + 2 * z + 1 + y) >> 61);
-			if (c >= RB3B_ASIZE) break;
-			runs.add(c, (int64_t)l);
-			bit += 2 * z + 1 + y + 3;
-		}
+	const int64_t n_words = n_bytes / 8, n_blk = n_words / FMD_SSIZE;
+	/* the blocks are self-contained (rld0.h:85-125): every thread decodes a range of them, the pieces are joined in order */
+	const int T = n_blk >= 4096 ? host_threads() : 1;
+	std::vector<RunList> part(T);
+	par_for(T, n_blk, [&](int t, int64_t b0, int64_t b1) { fmd_decode_blocks(w.data(), b0 * FMD_SSIZE, b1 * FMD_SSIZE, part[t]); });
+	for (int t = 0; t < T; ++t) {
+		if (t == 0) { runs.sym.swap(part[0].sym); runs.len.swap(part[0].len); }
+		else runs_append(runs, part[t]);
 	}
 	return RB3B_OK;
 }
@@ -493,20 +522,32 @@ static void fmr_encode(const uint8_t *sym, const int64_t *len, int64_t n_runs, i
 }
 
 struct FmrCursor { const uint8_t *p, *end; };
+struct LeafRef { const uint8_t *p; uint16_t nb; };
 
-static int fmr_read_node(FmrCursor &c, RunList &runs, int depth)
-{ /* rope.c:289-317 */
+/* walk the node records (rope.c:289-317) and list the leaves in order; nothing is decoded here */
+static int fmr_collect(FmrCursor &c, std::vector<LeafRef> &leaves, int depth)
+{
 	if (c.p + 3 > c.end || depth > 64) return RB3B_EFORMAT;
 	uint8_t is_bottom = c.p[0];
 	int16_t n; memcpy(&n, c.p + 1, 2);
 	c.p += 3;
 	for (int i = 0; i < n; ++i) {
-		if (!is_bottom) { int rc = fmr_read_node(c, runs, depth + 1); if (rc) return rc; continue; }
+		if (!is_bottom) { int rc = fmr_collect(c, leaves, depth + 1); if (rc) return rc; continue; }
 		if (c.p + 50 > c.end) return RB3B_EFORMAT;
 		uint16_t nb; memcpy(&nb, c.p + 48, 2);
 		c.p += 50;
 		if (c.p + nb > c.end) return RB3B_EFORMAT;
-		for (const uint8_t *q = c.p, *e = c.p + nb; q < e;) { /* rle_dec1, rle.h:39-51 */
+		LeafRef r = { c.p, nb };
+		leaves.push_back(r);
+		c.p += nb;
+	}
+	return RB3B_OK;
+}
+
+static int fmr_decode_leaves(const LeafRef *lv, int64_t n, RunList &runs)
+{
+	for (int64_t i = 0; i < n; ++i)
+		for (const uint8_t *q = lv[i].p, *e = lv[i].p + lv[i].nb; q < e;) { /* rle_dec1, rle.h:39-51 */
 			int sym = q[0] & 7, n_byte;
 			int64_t l;
 			if ((q[0] & 0x80) == 0) { l = q[0] >> 3; n_byte = 1; }
@@ -516,12 +557,10 @@ static int fmr_read_node(FmrCursor &c, RunList &runs, int depth)
 				l = q[0] >> 3 & 1;
 				for (int j = 1; j < n_byte; ++j) l = l << 6 | (q[j] & 0x3f);
 			}
-			if (sym >= RB3B_ASIZE) return RB3B_EFORMAT;
+			if (sym >= RB3B_ASIZE || q + n_byte > e) return RB3B_EFORMAT;
 			runs.add(sym, l);
 			q += n_byte;
 		}
-		c.p += nb;
-	}
 	return RB3B_OK;
 }
 
@@ -529,10 +568,21 @@ static int fmr_parse(const bytes_t &img, RunList &runs)
 {
 	if (img.size() < 4 || memcmp(img.data(), "RB\2", 3) != 0) return RB3B_EFORMAT;
 	FmrCursor c = { img.data() + 4, img.data() + img.size() };
+	std::vector<LeafRef> leaves;
 	for (int a = 0; a < RB3B_ASIZE; ++a) {
 		if (c.p + 8 > c.end) return rb3b_fail(RB3B_EFORMAT, "truncated FMR");
 		c.p += 8; /* max_nodes, block_len */
-		if (fmr_read_node(c, runs, 0) != RB3B_OK) return rb3b_fail(RB3B_EFORMAT, "corrupt FMR node record");
+		if (fmr_collect(c, leaves, 0) != RB3B_OK) return rb3b_fail(RB3B_EFORMAT, "corrupt FMR node record");
+	}
+	const int64_t n = (int64_t)leaves.size();
+	const int T = n >= 4096 ? host_threads() : 1;
+	std::vector<RunList> part(T);
+	std::vector<int> rc(T, RB3B_OK);
+	par_for(T, n, [&](int t, int64_t a, int64_t b) { rc[t] = fmr_decode_leaves(leaves.data() + a, b - a, part[t]); });
+	for (int t = 0; t < T; ++t) {
+		if (rc[t] != RB3B_OK) return rb3b_fail(RB3B_EFORMAT, "corrupt FMR leaf");
+		if (t == 0) { runs.sym.swap(part[0].sym); runs.len.swap(part[0].len); }
+		else runs_append(runs, part[t]);
 	}
 	return RB3B_OK;
 }
@@ -589,6 +639,24 @@ extern "C" int64_t rb3b_fmr_image(int64_t n_runs, const uint8_t *sym, const int6
 	*out = (uint8_t*)malloc(img.size());
 	memcpy(*out, img.data(), img.size());
 	return (int64_t)img.size();
+}
+
+/* host-only reader behind rb3b_restore: .fmd or .fmr image -> canonical run list (malloc'd), returns the number of runs */
+extern "C" int64_t rb3b_runs_from_image(const uint8_t *image, int64_t n_bytes, uint8_t **sym, int64_t **len, int *sorting_order)
+{
+	bytes_t img(image, image + (n_bytes > 0 ? n_bytes : 0));
+	RunList runs;
+	int rc, so = 0;
+	if (img.size() >= 4 && memcmp(img.data(), "RLD\3", 4) == 0) rc = fmd_parse(img, runs);
+	else if (img.size() >= 4 && memcmp(img.data(), "RB\2", 3) == 0) { rc = fmr_parse(img, runs); so = img[3] <= 2 ? img[3] : 0; }
+	else return rb3b_fail(RB3B_EFORMAT, "neither FMD nor FMR");
+	if (rc != RB3B_OK) return rc;
+	const size_t n = runs.sym.size();
+	*sym = (uint8_t*)malloc(n ? n : 1); *len = (int64_t*)malloc((n ? n : 1) * 8);
+	if (*sym == 0 || *len == 0) return rb3b_fail(RB3B_ENOMEM, "out of host memory");
+	if (n) { memcpy(*sym, runs.sym.data(), n); memcpy(*len, runs.len.data(), n * 8); }
+	if (sorting_order) *sorting_order = so;
+	return (int64_t)n;
 }
 
 extern "C" void rb3b_host_free(void *p) { free(p); }

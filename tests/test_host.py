@@ -226,3 +226,34 @@ def test_cli_reader_against_live_reference_on_odd_input(oracle):
         got = _cli_batches(opts + ["-"], stdin=data)
         text = np.concatenate([asc[np.frombuffer(g[2].encode(), np.uint8)] for g in got if g[1] > 0])
         assert oracle.to_ascii(oracle.build_bwt(text)) == ref.run(["build"] + opts + ["-"], stdin=data).decode().strip(), data
+
+
+@pytest.mark.parametrize("threads", [1, 5])
+def test_product_readers(oracle, golden, threads):
+    """The host readers behind rb3b_restore (serial and multi-threaded): reference-made .fmd / .fmr images and our own
+    encoders' output decode to the run list the oracle's decoder gives; FMR sorting-order byte; corrupt input is refused."""
+    import ropebwt3_b200 as R
+    R.set_param("fmd_threads", threads)
+    try:
+        for name in ["merge_small", "merge_div", "long_runs"]:
+            g = golden(name)
+            s0, l0, _ = oracle.fmd_decode(bytes(g["fmd"]))
+            s, l, so = R.runs_from_image(bytes(g["fmd"]))
+            assert np.array_equal(s, s0) and np.array_equal(l, l0) and so == 0
+            s, l, so = R.runs_from_image(bytes(g["fmr"]))
+            assert np.array_equal(s, s0) and np.array_equal(l, l0) and so == 0
+        assert R.runs_from_image(bytes(golden("rb2")["fmr_so2"]))[2] == 2
+        rng = np.random.default_rng(17)
+        n = 600000   # > 4096 blocks / leaves: the multi-threaded paths
+        sym = (np.cumsum(rng.integers(1, 6, n)) % 6).astype(np.uint8)
+        ln = rng.geometric(0.2, n).astype(np.int64)
+        ln[rng.integers(0, n, 300)] = rng.integers(1 << 14, 1 << 40, 300)
+        for img in (R.fmd_image(sym, ln), R.fmr_image(sym, ln), R.fmr_image(sym, ln, 8, 128)):
+            s, l, _ = R.runs_from_image(img)
+            assert np.array_equal(s, sym) and np.array_equal(l, ln)
+        with pytest.raises(R.Rb3bError):
+            R.runs_from_image(b"not an index")
+        with pytest.raises(R.Rb3bError):
+            R.runs_from_image(R.fmr_image(sym, ln)[:1000])
+    finally:
+        R.set_param("fmd_threads", 0)
