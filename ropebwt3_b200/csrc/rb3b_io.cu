@@ -359,18 +359,30 @@ static void runs_append(RunList &a, const RunList &b)
 /* the runs of blocks [h0, h1) (word offsets, multiples of FMD_SSIZE) */
 static void fmd_decode_blocks(const uint64_t *w, int64_t h0, int64_t h1, RunList &runs)
 {
+	runs.sym.reserve((size_t)(h1 - h0) / FMD_SSIZE * 40); runs.len.reserve((size_t)(h1 - h0) / FMD_SSIZE * 40);
+	int last = -1; /* symbol of the last run added, to fuse equal neighbours (blocks cut runs nowhere, but stay safe) */
+	if (!runs.sym.empty()) last = runs.sym.back();
 	for (int64_t h = h0; h < h1; h += FMD_SSIZE) {
 		int64_t first = h + FMD_HDR_WORDS[w[h] >> 62 > 2 ? 2 : w[h] >> 62], tail = h + FMD_SSIZE - (((h + FMD_SSIZE) & (FMD_LSIZE - 1)) == 0 ? 2 : 1), bit = 0;
 		for (;;) {
-			uint64_t x = payload_bits(w, first, tail, bit);
+			/* a code is at most 59 bits wide (rld_delta_enc1, rld0.c:45-51; runs < 2^43 plus 3 symbol bits): one 64-bit window holds it */
+			const uint64_t x = payload_bits(w, first, tail, bit);
 			if (x >> 58 == 0) break; /* six zero bits cannot start a code */
-			int z = __builtin_clzll(x);
-			int y = (int)(x << z >> (63 - z)) - 1;
-			uint64_t l = (y ? payload_bits(w, first, tail, bit + 2 * z + 1) >> (64 - y) : 0) | 1ULL << y;
-			int c = (int)(payload_bits(w, first, tail, bit + 2 * z + 1 + y) >> 61);
+			const int z = __builtin_clzll(x);
+			const int y = (int)(x << z >> (63 - z)) - 1;
+			const int width = 2 * z + 1 + y + 3;
+			uint64_t l; int c;
+			if (width <= 64) {
+				l = (y ? (x << (2 * z + 1)) >> (64 - y) : 0) | 1ULL << y;
+				c = (int)((x << (2 * z + 1 + y)) >> 61);
+			} else { /* wider than any code the encoders write: take the slow, general path */
+				l = (y ? payload_bits(w, first, tail, bit + 2 * z + 1) >> (64 - y) : 0) | 1ULL << y;
+				c = (int)(payload_bits(w, first, tail, bit + 2 * z + 1 + y) >> 61);
+			}
 			if (c >= RB3B_ASIZE) break;
-			runs.add(c, (int64_t)l);
-			bit += 2 * z + 1 + y + 3;
+			if (c == last) runs.len.back() += (int64_t)l;
+			else { runs.sym.push_back((uint8_t)c); runs.len.push_back((int64_t)l); last = c; }
+			bit += width;
 		}
 	}
 }
