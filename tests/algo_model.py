@@ -1,0 +1,139 @@
+"""A plain-Python model of the device algorithm of the rank phase (csrc/rb3b_merge.cu), kernel by kernel, so that the
+ALGORITHM -- not only its CUDA implementation -- is pinned to the reference's interleave arrays on a CPU-only box:
+walk order from the batch's LF mapping, equal slices walked with a bracket [lo, hi], fix-up from the exact arrival of
+the previous slice, sorted-order heads (RLO/RCLO), scatter back to row order.  Small inputs only."""
+import numpy as np
+
+
+def _occ(bwt):
+    n = len(bwt)
+    occ = np.zeros((6, n + 1), np.int64)
+    for c in range(6):
+        occ[c, 1:] = np.cumsum(bwt == c)
+    acc = np.concatenate([[0], np.cumsum(occ[:, n])]).astype(np.int64)
+    return occ, acc
+
+
+def walk_order(b):
+    """k_prep_lf + k_fine_walk/k_list_rank/k_write_walk: the batch in the order the reference's loop meets its rows
+    (fm-index.c:165-174), all sequences one after the other.  -> (wrow, wsym, chain_base, chain_len)"""
+    occ, acc = _occ(b)
+    lf = np.array([acc[c] + occ[c, i] for i, c in enumerate(b)], np.int64)
+    wrow, base, length = [], [], []
+    for p in range(int(acc[1])):          # chain p starts at sentinel row p
+        base.append(len(wrow))
+        k = p
+        while True:
+            wrow.append(k)
+            if b[k] == 0:
+                break
+            k = int(lf[k])
+        length.append(len(wrow) - base[-1])
+    assert len(wrow) == len(b), "not the BWT of a sentinel-terminated string set"
+    wrow = np.array(wrow, np.int64)
+    return wrow, b[wrow], np.array(base, np.int64), np.array(length, np.int64), lf
+
+
+def interleave(a_bwt, b_bwt, seg_len=16, so=0, part=0, n_parts=1, halo=2):
+    """-> ka[len(b)] (or -1 for rows another part resolves) and the number of rows left unresolved."""
+    A, Bv = np.asarray(a_bwt, np.uint8), np.asarray(b_bwt, np.uint8)
+    occ, acc = _occ(A)
+    nA = len(A)
+
+    def rank(c, k):
+        return int(occ[c, min(max(k, 0), nA)])
+
+    wrow, wsym, cbase, clen, _ = walk_order(Bv)
+    n = len(Bv)
+    UNRES, HEAD, SEED = 1 << 62, 1 << 60, 1 << 59
+    kseq = np.zeros(n, np.int64)
+    pi = (lambda c: 5 - c if 1 <= c <= 4 else c) if so == 2 else (lambda c: c)
+    if so:   # k_so_heads (mr_insert_multi_aux, mrope.c:226-275)
+        for p in range(len(cbase)):
+            l, u, P, t, ended = 0, int(acc[1]), 0, 0, False
+            p0, L = int(cbase[p]), int(clen[p])
+            raw = []
+            while t < L and l < u:
+                c = int(wsym[p0 + t])
+                tl = [rank(x, l) for x in range(6)]
+                tu = [rank(x, u) for x in range(6)]
+                less = sum(tu[x] - tl[x] for x in range(6) if pi(x) < pi(c))
+                raw.append(l - P)
+                P += less
+                t += 1
+                if c == 0:
+                    ended = True
+                    break
+                l, u = int(acc[c]) + tl[c], int(acc[c]) + tu[c]
+            for s_, r in enumerate(raw):
+                kseq[p0 + s_] = (r + P) | HEAD
+            if not ended and t < L:
+                kseq[p0 + t] = l | SEED
+    n_seg = (n + seg_len - 1) // seg_len
+    own_lo, own_hi = n_seg * part // n_parts, n_seg * (part + 1) // n_parts
+    walk_lo = max(0, own_lo - halo) if n_parts > 1 else 0
+    d = np.zeros(n_seg, np.int64)
+    arr = [None] * n_seg
+    for s in range(walk_lo, own_hi):      # k_walk_first
+        p0 = s * seg_len
+        c0 = 0 if s == 0 else int(wsym[p0 - 1])
+        if c0 == 0:
+            lo = hi = 0 if so else int(acc[1])
+        else:
+            lo, hi = int(acc[c0]), int(acc[c0 + 1])
+        for p in range(p0, min(n, p0 + seg_len)):
+            c = int(wsym[p])
+            f = int(kseq[p]) if so else 0
+            if f & HEAD:
+                kseq[p] = f & ~HEAD
+                lo = hi = 0
+                continue
+            if f & SEED:
+                lo = hi = f & ((1 << 42) - 1)
+            if lo == hi:
+                kseq[p] = lo
+            else:
+                kseq[p] = lo | UNRES
+                d[s] += 1
+            if c == 0:
+                lo = hi = 0 if so else int(acc[1])
+            else:
+                lo, hi = int(acc[c]) + rank(c, lo), int(acc[c]) + rank(c, hi)
+        arr[s] = (lo, hi)
+    for s in range(walk_lo, own_hi - 1):  # k_collect_first + k_walk_fix[_log], cascading
+        t, v = s + 1, None
+        if arr[s][0] == arr[s][1] and d[t] > 0:
+            v = arr[s][0]
+        while v is not None:
+            p0, cnt, c = t * seg_len, int(d[t]), 1
+            full = cnt == min(seg_len, n - p0)
+            for p in range(p0, p0 + cnt):
+                c = int(wsym[p])
+                kseq[p] = v
+                if c == 0:
+                    break
+                v = int(acc[c]) + rank(c, v)
+            d[t] = 0
+            if full and c != 0:
+                arr[t] = (v, v)
+                t += 1
+                if not (t < own_hi and d[t] > 0):
+                    v = None
+            else:
+                v = None
+    ka = np.full(n, -1, np.int64)         # k_scatter_ka
+    unres = 0
+    for p in range(own_lo * seg_len, min(n, own_hi * seg_len)):
+        if int(kseq[p]) & UNRES:
+            unres += 1
+        else:
+            ka[wrow[p]] = kseq[p]
+    return ka, unres
+
+
+def pack_rb(ka, b_bwt):
+    """fm-index.c:168: (ka + i) << 6 | B[i] << 3 | first symbol of suffix i"""
+    b = np.asarray(b_bwt, np.uint8)
+    acc = np.concatenate([[0], np.cumsum(np.bincount(b, minlength=6)[:6])])
+    bucket = np.searchsorted(acc[1:], np.arange(len(b)), side="right")
+    return (ka + np.arange(len(b))) << 6 | b.astype(np.int64) << 3 | bucket
