@@ -37,6 +37,19 @@ class OracleEngine:
         self.sym, self.ln = O.merge_runs(self.sym, self.ln, rb)
 
 
+class ModelEngine(OracleEngine):
+    """Stand-in that shards like the device does (tests/algo_model.py): part p resolves its slices of walk order from a
+    speculative halo and reports 1 when the halo did not give it an exact start (duplicated sequences)."""
+
+    def rank_part(self, bwt, n, part, n_parts, ka):
+        from oracle import oracle as O
+        import algo_model as M
+        out, unres = M.interleave(O.runs2plain(self.sym, self.ln), bwt, 64, part=part, n_parts=n_parts, halo=2)
+        ka.copy_(torch.from_numpy(out))
+        self.calls.append((part, n_parts))
+        return 1 if unres else 0
+
+
 def _worker(rank, world, port, force, q):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -45,10 +58,15 @@ def _worker(rank, world, port, force, q):
     from oracle import oracle as O
     from ropebwt3_b200 import synth
     from ropebwt3_b200.dist import merge_plain_sharded
-    gs = synth.genomes(3, 1500, seed=21)
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    if force == "model":         # real slice sharding; the third genome is an exact copy of the second: no halo can resolve it
+        gs = synth.genomes(2, 1500, seed=21)
+        gs.append(gs[1].copy())
+    else:
+        gs = synth.genomes(3, 1500, seed=21)
     b0 = O.build_bwt(synth.batch_text(gs[:1]))
     sym, ln = O.plain2runs(b0)
-    eng = OracleEngine(sym, ln, force)
+    eng = ModelEngine(sym, ln) if force == "model" else OracleEngine(sym, ln, force)
     used = []
     for g in gs[1:]:
         bwt = O.build_bwt(synth.batch_text([g]))
@@ -91,3 +109,12 @@ def test_fallback_when_a_rank_is_incomplete():
     for rank, ok, used, calls in res:
         assert ok and used == [False, False]            # every rank recomputed the whole array
         assert calls == [(rank, 2), (0, 1), (rank, 2), (0, 1)]
+
+
+def test_slice_sharding_model_and_natural_fallback():
+    """The device's sharding rule (slices + halo) behind the same collectives: a diverged genome is resolved by the two
+    parts together, an exact duplicate makes part 1 report 'incomplete' and every rank falls back -- same result."""
+    res = _run("model")
+    for rank, ok, used, calls in res:
+        assert ok and used == [True, False]
+        assert calls == [(rank, 2), (rank, 2), (0, 1)]
