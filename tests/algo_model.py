@@ -137,3 +137,27 @@ def pack_rb(ka, b_bwt):
     acc = np.concatenate([[0], np.cumsum(np.bincount(b, minlength=6)[:6])])
     bucket = np.searchsorted(acc[1:], np.arange(len(b)), side="right")
     return (ka + np.arange(len(b))) << 6 | b.astype(np.int64) << 3 | bucket
+
+
+def ssa_image(bwt, ss):
+    """k_ssa_emit: the sampled suffix array read off the walk order of the index's own BWT (no per-string walk)."""
+    import struct
+    b = np.asarray(bwt, np.uint8)
+    wrow, _, cbase, clen, lf = walk_order(b)
+    acc1 = int(np.count_nonzero(b == 0))
+    m, n = acc1, len(b)
+    ms = 1
+    while (1 << ms) < m:
+        ms += 1
+    n_ssa = (n - m + (1 << ss) - 1) >> ss
+    r2i = np.zeros(m, np.uint64)
+    ssa = np.zeros(n_ssa, np.uint64)
+    chain = np.searchsorted(cbase, np.arange(n), side="right") - 1
+    for p in range(n):
+        k0 = int(chain[p])
+        l, L, row = p - int(cbase[k0]), int(clen[k0]), int(wrow[p])
+        if l > 0 and row >= acc1 and ((row - acc1) & ((1 << ss) - 1)) == 0:
+            ssa[(row - acc1) >> ss] = ((L - 1 - l) << ms) | k0
+        if l == L - 1:
+            r2i[int(lf[row])] = k0
+    return b"SSA\x01" + struct.pack("<IIqq", ss, ms, m, n_ssa) + r2i.tobytes() + ssa.tobytes()

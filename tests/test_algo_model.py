@@ -57,3 +57,13 @@ def test_sorted_order_heads(oracle, golden, so):
         cur = merged
         oracle.insert_multi(ropes, t, so)
         assert np.array_equal(cur, np.array([c for r in ropes for c in r], np.uint8))
+
+
+def test_ssa_from_walk_order(oracle, golden):
+    """The data-parallel SSA rule of the device == ssa_gen1's per-string walk == the reference's .ssa files."""
+    g = golden("ssa")
+    for name, key in [("merge_small", "fmd"), ("rb2", "fmd_so2")]:
+        s, l, _ = oracle.fmd_decode(bytes(golden(name)[key]))
+        bwt = oracle.runs2plain(s, l)
+        for ss in (0, 3, 8):
+            assert M.ssa_image(bwt, ss) == bytes(g["%s_ss%d" % (name, ss)]), (name, ss)
