@@ -168,14 +168,16 @@ extern "C" int64_t rb3b_get_stat(const char *key)
 }
 
 /* Largest batch (symbols) the device can take next to an index that will grow by it: the suffix sorter needs ~44 bytes
- * per symbol, the rank phase ~40, both ping-pong halves of the index ~2 x 1 byte per symbol; 32-bit suffix array. */
+ * per symbol; the rank phase of a batch beyond 2^29 rows 8 (LF) + 8 (rows) + 1 (symbols) + 8 (kseq) + 8 (ka) + 1 (list
+ * nodes) + 16 (bucketed scatter) + sort scratch ~ 60; the scratch arena keeps its high-water mark; both ping-pong halves
+ * of the index ~2 x 1 byte per symbol; 32-bit suffix array. */
 extern "C" int64_t rb3b_max_batch_symbols(int64_t index_symbols)
 {
 	size_t fr = 0, tot = 0;
 	if (rb3b_ensure_init() != RB3B_OK) return -1;
 	if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return -1;
 	int64_t avail = (int64_t)tot - (int64_t)(tot >> 4) - 2 * index_symbols; /* what this process already holds counts as available */
-	int64_t n = avail / 48;
+	int64_t n = avail / 72;
 	const int64_t cap = (1LL << 32) - 4096;
 	if (n > cap) n = cap;
 	return n > 0 ? n : 0;
