@@ -180,7 +180,8 @@ typedef struct {
 typedef struct {
 	int argc, first; char **argv;
 	int is_line, no_for, no_rev;
-	int64_t batch;
+	int64_t batch;      /* -m: soft limit, a batch closes after the record that crosses it (io.c:114,119) */
+	int64_t hard;       /* what the device can sort and merge at once: a batch closes BEFORE the record that would cross it */
 	batch_t slot[2];
 	int n_full, head, tail, done; /* ring of two slots */
 	pthread_mutex_t mu; pthread_cond_t cv;
@@ -238,16 +239,23 @@ static void *reader_main(void *arg)
 			continue;
 		}
 		r->is_line = p->is_line; r->last = -2;
-		while (!eof) {
-			b = pipe_claim(p);
-			b->seq.l = 0; b->n_seq = 0; b->file = i; b->open_failed = 0;
-			while (rd_record(r, &rec, &tmp) == 0) {
-				seq_add(&b->seq, &rec, !p->no_for, !p->no_rev, &b->n_seq);
-				if (p->batch > 0 && (int64_t)b->seq.l > p->batch) break; /* io.c:114,119 */
+		{
+			int pending = 0; /* rec holds a record that did not fit the previous batch */
+			while (!eof) {
+				int closed = 0;
+				b = pipe_claim(p);
+				b->seq.l = 0; b->n_seq = 0; b->file = i; b->open_failed = 0;
+				while (pending || rd_record(r, &rec, &tmp) == 0) {
+					const int64_t need = (int64_t)(rec.l + 1) * ((p->no_for ? 0 : 1) + (p->no_rev ? 0 : 1));
+					if (!pending && p->hard > 0 && b->n_seq > 0 && (int64_t)b->seq.l + need > p->hard) { pending = 1; closed = 1; break; }
+					pending = 0;
+					seq_add(&b->seq, &rec, !p->no_for, !p->no_rev, &b->n_seq);
+					if (p->batch > 0 && (int64_t)b->seq.l > p->batch) { closed = 1; break; } /* io.c:114,119 */
+				}
+				if (!closed) eof = 1;
+				b->last_of_file = eof;
+				pipe_publish(p);
 			}
-			if (b->n_seq == 0 || p->batch <= 0 || (int64_t)b->seq.l <= p->batch) eof = 1;
-			b->last_of_file = eof;
-			pipe_publish(p);
 		}
 		gzclose(r->fp);
 		free(r);
@@ -399,7 +407,7 @@ int main(int argc, char *argv[])
 			LOG("batch size limited to %ld symbols by device memory", (long)fit);
 			batch = fit;
 		}
-		P.batch = batch;
+		P.batch = batch; P.hard = fit;
 		pthread_mutex_init(&P.mu, 0); pthread_cond_init(&P.cv, 0);
 		if (pthread_create(&tid, 0, reader_main, &P) != 0) { fprintf(stderr, "ERROR: failed to start the reader thread\n"); return 1; }
 		while ((b = pipe_next(&P)) != 0) {

@@ -393,7 +393,7 @@ static int fmd_parse(const bytes_t &img, RunList &runs)
 	uint32_t geom; uint64_t n_bytes, n_frames;
 	memcpy(&geom, &img[4], 4); memcpy(&n_bytes, &img[16], 8); memcpy(&n_frames, &img[24], 8);
 	if (geom != (RB3B_ASIZE << 16 | 3)) return rb3b_fail(RB3B_EFORMAT, "FMD with asize/sbits 0x%x is not supported (only 6/3)", geom);
-	if (img.size() < 80 + n_bytes) return rb3b_fail(RB3B_EFORMAT, "truncated FMD");
+	if (n_bytes > img.size() - 80 || (n_bytes & 7) != 0) return rb3b_fail(RB3B_EFORMAT, "truncated or corrupt FMD (n_bytes = %llu, file holds %zu)", (unsigned long long)n_bytes, img.size() - 80);
 	std::vector<uint64_t> w(n_bytes / 8 + FMD_SSIZE + 1, 0);
 	memcpy(w.data(), &img[80], n_bytes);
 	const int64_t n_words = n_bytes / 8, n_blk = n_words / FMD_SSIZE;
@@ -405,6 +405,12 @@ static int fmd_parse(const bytes_t &img, RunList &runs)
 		if (t == 0) { runs.sym.swap(part[0].sym); runs.len.swap(part[0].len); }
 		else runs_append(runs, part[t]);
 	}
+	/* the decoded symbol totals must be the marginal counts of the header (rld0.c:230-236): catches corrupt payloads */
+	uint64_t got[RB3B_ASIZE] = {0, 0, 0, 0, 0, 0}, want[RB3B_ASIZE];
+	memcpy(want, &img[32], sizeof(want));
+	for (size_t i = 0; i < runs.sym.size(); ++i) got[runs.sym[i]] += (uint64_t)runs.len[i];
+	for (int a = 0; a < RB3B_ASIZE; ++a)
+		if (got[a] != want[a]) return rb3b_fail(RB3B_EFORMAT, "corrupt FMD: decoded %llu symbols of code %d, the header says %llu", (unsigned long long)got[a], a, (unsigned long long)want[a]);
 	return RB3B_OK;
 }
 
@@ -560,16 +566,15 @@ static int fmr_decode_leaves(const LeafRef *lv, int64_t n, RunList &runs)
 {
 	for (int64_t i = 0; i < n; ++i)
 		for (const uint8_t *q = lv[i].p, *e = lv[i].p + lv[i].nb; q < e;) { /* rle_dec1, rle.h:39-51 */
-			int sym = q[0] & 7, n_byte;
+			const int sym = q[0] & 7, n_byte = (q[0] & 0x80) == 0 ? 1 : q[0] >> 5 == 6 ? 2 : (q[0] & 0x10) ? 8 : 4;
 			int64_t l;
-			if ((q[0] & 0x80) == 0) { l = q[0] >> 3; n_byte = 1; }
-			else if (q[0] >> 5 == 6) { l = (int64_t)(q[0] & 0x18) << 3 | (q[1] & 0x3f); n_byte = 2; }
+			if (sym >= RB3B_ASIZE || q + n_byte > e) return RB3B_EFORMAT; /* before the continuation bytes are read */
+			if (n_byte == 1) l = q[0] >> 3;
+			else if (n_byte == 2) l = (int64_t)(q[0] & 0x18) << 3 | (q[1] & 0x3f);
 			else {
-				n_byte = (q[0] & 0x10) ? 8 : 4;
 				l = q[0] >> 3 & 1;
 				for (int j = 1; j < n_byte; ++j) l = l << 6 | (q[j] & 0x3f);
 			}
-			if (sym >= RB3B_ASIZE || q + n_byte > e) return RB3B_EFORMAT;
 			runs.add(sym, l);
 			q += n_byte;
 		}
@@ -654,8 +659,14 @@ extern "C" int64_t rb3b_fmr_image(int64_t n_runs, const uint8_t *sym, const int6
 }
 
 /* host-only reader behind rb3b_restore: .fmd or .fmr image -> canonical run list (malloc'd), returns the number of runs */
+/* no C++ exception may cross the C ABI: allocation failures of the host codecs become error codes */
+#define GUARD_BEGIN try {
+#define GUARD_END } catch (const std::bad_alloc &) { return rb3b_fail(RB3B_ENOMEM, "out of host memory"); } \
+	catch (const std::exception &e_) { return rb3b_fail(RB3B_EFORMAT, "malformed input (%s)", e_.what()); }
+
 extern "C" int64_t rb3b_runs_from_image(const uint8_t *image, int64_t n_bytes, uint8_t **sym, int64_t **len, int *sorting_order)
 {
+	GUARD_BEGIN
 	bytes_t img(image, image + (n_bytes > 0 ? n_bytes : 0));
 	RunList runs;
 	int rc, so = 0;
@@ -669,21 +680,25 @@ extern "C" int64_t rb3b_runs_from_image(const uint8_t *image, int64_t n_bytes, u
 	if (n) { memcpy(*sym, runs.sym.data(), n); memcpy(*len, runs.len.data(), n * 8); }
 	if (sorting_order) *sorting_order = so;
 	return (int64_t)n;
+	GUARD_END
 }
 
 extern "C" void rb3b_host_free(void *p) { free(p); }
 
 extern "C" int rb3b_dump_fmd(const rb3b_index_t *x, const char *fn)
 {
+	GUARD_BEGIN
 	std::vector<uint8_t> sym; std::vector<int64_t> len;
 	TRY(fetch_runs(x, sym, len));
 	bytes_t img;
 	fmd_encode_any(sym.data(), len.data(), (int64_t)sym.size(), img);
 	return write_file(fn, img.data(), img.size());
+	GUARD_END
 }
 
 extern "C" int rb3b_dump_fmr(const rb3b_index_t *x, const char *fn, int max_nodes, int block_len)
 {
+	GUARD_BEGIN
 	std::vector<uint8_t> sym; std::vector<int64_t> len;
 	TRY(fetch_runs(x, sym, len));
 	if (max_nodes <= 0) max_nodes = 64;
@@ -693,6 +708,7 @@ extern "C" int rb3b_dump_fmr(const rb3b_index_t *x, const char *fn, int max_node
 	fmr_encode(sym.data(), len.data(), (int64_t)sym.size(), max_nodes, block_len, img);
 	if (img.size() >= 4) img[3] = (uint8_t)x->so; /* mr_dump writes the sorting order after the magic, mrope.c:155-156 */
 	return write_file(fn, img.data(), img.size());
+	GUARD_END
 }
 
 extern "C" int rb3b_dump_plain(const rb3b_index_t *x, const char *fn)
@@ -714,6 +730,7 @@ extern "C" int rb3b_dump_plain(const rb3b_index_t *x, const char *fn)
 
 extern "C" int rb3b_restore(rb3b_index_t *x, const char *fn)
 { /* rb3_fmi_restore (fm-index.h:123-133): FMD magic first, then FMR */
+	GUARD_BEGIN
 	bytes_t img;
 	RunList runs;
 	TRY(read_file(fn, img));
@@ -725,4 +742,5 @@ extern "C" int rb3b_restore(rb3b_index_t *x, const char *fn)
 	TRY(rb3b_index_from_runs(x, (int64_t)runs.sym.size(), runs.sym.data(), runs.len.data()));
 	if (memcmp(img.data(), "RB\2", 3) == 0 && img[3] <= 2) x->so = img[3]; /* mr_restore, mrope.c:166-168; an FMD does not record the order */
 	return RB3B_OK;
+	GUARD_END
 }

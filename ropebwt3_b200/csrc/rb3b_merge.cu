@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(TPB) k_walk_first(DevIndex A, Slices S, const 
 						/* the walks that currently run together take the two-position path only while one of them still
 						 * carries a bracket; either path is correct for an exact walk, so this is purely a cost choice
 						 * (a private per-thread branch was measured slower: the two paths serialise) */
-						if (WG::ALWAYS2 || __any_sync(__activemask(), lo != hi)) WG::rank2(A, lo, hi, c, r1, r2);
+						if (WG::ALWAYS2 || __any_sync(gmask, lo != hi)) WG::rank2(A, lo, hi, c, r1, r2); /* vote over the whole group only: lo, hi are group-uniform */
 						else r1 = r2 = WG::rank(A, lo, c);
 						lo = A.acc[c] + r1; hi = A.acc[c] + r2;
 					}
@@ -462,6 +462,9 @@ __global__ void __launch_bounds__(128) k_walk_fix_log(DevIndex A, Slices S, cons
 	unsigned long long n_rows = 0, n_wide = 0; /* statistics only */
 	for (;;) {
 		const int64_t d = S.d[t], len = S.slice_len(t), base = t * S.seg_len;
+		/* a slice that collapsed exactly on its last row already had an exact arrival in round 1: k_collect_first queued
+		 * its successor as an item of its own, so it must not be entered from here as well */
+		const bool was_exact = S.arr_lo[t] == S.arr_hi[t];
 		int ended = 0;
 		LogRow nxt;
 		nxt.load(A, kseq, wsym, base + lane, lane < d);
@@ -513,7 +516,8 @@ __global__ void __launch_bounds__(128) k_walk_fix_log(DevIndex A, Slices S, cons
 			ended = __shfl_sync(0xffffffffu, ended, 0);
 			__syncwarp(); /* the rows are consumed before they are overwritten */
 		}
-		const bool more = d == len && !ended && t + 1 < S.own_hi && S.d[t + 1] > 0; /* t + 1's only predecessor is t: nobody else touches it */
+		const bool more = d == len && !ended && !was_exact && t + 1 < S.own_hi && S.d[t + 1] > 0; /* t + 1's only predecessor is t and t + 1 is on nobody's list */
+		__syncwarp();
 		if (lane == 0) {
 			S.d[t] = 0;
 			if (d == len) S.arr_lo[t] = S.arr_hi[t] = v;
@@ -541,6 +545,7 @@ __global__ void __launch_bounds__(TPB) k_walk_fix(DevIndex A, Slices S, const ui
 		it = __shfl_sync(gmask, it, gbase);
 		if (it >= n_items) break;
 		const int64_t t = wl_seg[it], d = S.d[t], len = S.slice_len(t), p0 = t * S.seg_len;
+		const bool was_exact = S.arr_lo[t] == S.arr_hi[t]; /* then t + 1 was already listed by whoever made t's arrival exact */
 		int64_t v = wl_val[it];
 		int c = 1;
 		for (int64_t i = 0; i < d; ++i) {
@@ -553,7 +558,7 @@ __global__ void __launch_bounds__(TPB) k_walk_fix(DevIndex A, Slices S, const ui
 			S.d[t] = 0;
 			if (d == len && c != 0) { /* never collapsed: only now is the arrival value known */
 				S.arr_lo[t] = S.arr_hi[t] = v;
-				if (t + 1 < S.own_hi && S.d[t + 1] > 0) { /* t + 1 is processed by nobody else in this round */
+				if (!was_exact && t + 1 < S.own_hi && S.d[t + 1] > 0) { /* t + 1 is processed by nobody else */
 					unsigned long long o = atomicAdd(nx_n, 1ULL);
 					nx_seg[o] = t + 1; nx_val[o] = v;
 				}
