@@ -13,7 +13,13 @@
  * usable CUDA device every call fails with RB3B_ENODEV.
  *
  * Threading: like the reference, an index must not be used from two
- * threads at once; different indices may be.
+ * threads at once; different indices may be.  Every call runs in the execution
+ * context (device, stream, scratch arena, counters) that is current on the
+ * calling host thread; a thread that never made one current gets its own
+ * default context on first use, so calls from different threads run on
+ * different streams and overlap on the device -- the reference's pipeline mode
+ * (kt_pipeline of rb3_build_sais and rb3_fmi_merge_plain, build.c:55-83) is two
+ * host threads calling rb3b_build_bwt_dev and rb3b_merge_plain_dev.
  */
 #ifndef RB3_B200_H
 #define RB3_B200_H
@@ -34,6 +40,7 @@ extern "C" {
 #define RB3B_EFORMAT  -5
 
 typedef struct rb3b_index_s rb3b_index_t;
+typedef struct rb3b_ctx_s rb3b_ctx_t;
 
 /* ---- runtime -------------------------------------------------------------- */
 int         rb3b_init(int device);                 /* select device, create stream + memory pool */
@@ -41,6 +48,11 @@ const char *rb3b_last_error(void);
 const char *rb3b_version(void);
 int         rb3b_set_stream(void *cuda_stream);    /* run on a caller-owned cudaStream_t (NULL = own stream) */
 int         rb3b_sync(void);
+int         rb3b_trim(void);                       /* give the calling context's scratch memory back to the device */
+/* explicit contexts: several devices or streams driven from one process (one host thread per context at a time) */
+rb3b_ctx_t *rb3b_ctx_create(int device);
+int         rb3b_ctx_make_current(rb3b_ctx_t *ctx);   /* bind to the calling thread; NULL = the thread's default context */
+void        rb3b_ctx_destroy(rb3b_ctx_t *ctx);
 int         rb3b_set_param(const char *key, int64_t value);   /* tuning knobs, all optional: "seg_len" (walk slice length, 0 = by batch size), "fine_len", "halo_segments", "index_kind", "bitmap_max_symbols", "fmd_threads", ... */
 int64_t     rb3b_get_stat(const char *key);        /* counters of the last call: "kernel_launches", "n_segments", "fix_rounds", "unresolved_rows", "n_blocks" ... */
 
@@ -90,6 +102,16 @@ int rb3b_mg_rank_plain_dev(const rb3b_index_t *idx, int64_t len, const uint8_t *
 int rb3b_mg_rank_part(const rb3b_index_t *idx, int64_t len, const uint8_t *d_bwt, int part, int n_parts, int64_t *d_ka);
 /* second half of rb3_fmi_merge_plain (worker_mgins, fm-index.c:237-249 / :295) given the complete d_ka[len] */
 int rb3b_merge_with_ka(rb3b_index_t *idx, int64_t len, const uint8_t *d_bwt, const int64_t *d_ka);
+
+/* Multi-device communicator (NCCL over NVLink, bound at run time): the calling thread's context becomes rank `rank` of
+ * `world`.  id128: 128 bytes from rb3b_dist_unique_id on one rank, passed to all by the host program (MPI, a file,
+ * torch.distributed, or plain memory between the threads of one process). */
+int rb3b_dist_unique_id(void *id128);
+int rb3b_dist_init(int rank, int world, const void *id128);
+int rb3b_dist_finalize(void);
+int rb3b_dist_rank(void);
+int rb3b_dist_world(void);
+int rb3b_dist_nccl_version(void);
 
 /* rb3_fmi_merge (fm-index.c:251-277) for `ropebwt3 merge`: B is another index. */
 int rb3b_merge_index(rb3b_index_t *idx, const rb3b_index_t *other);
@@ -150,6 +172,8 @@ int64_t rb3b_max_batch_symbols(int64_t index_symbols);
 /* ---- device memory helpers for callers without a CUDA runtime of their own -- */
 void *rb3b_dev_alloc(int64_t bytes);
 void  rb3b_dev_free(void *p);
+void *rb3b_host_alloc_pinned(int64_t bytes);   /* page-locked host memory: batch buffers that rb3b_h2d copies at full PCIe rate */
+void  rb3b_host_free_pinned(void *p);
 int   rb3b_h2d(void *dst, const void *src, int64_t bytes);
 int   rb3b_d2h(void *dst, const void *src, int64_t bytes);
 

@@ -22,6 +22,12 @@ SIGNATURES = {
     "rb3b_version": (C.c_char_p, []),
     "rb3b_set_stream": (_int, [_vp]),
     "rb3b_sync": (_int, []),
+    "rb3b_trim": (_int, []),
+    "rb3b_ctx_create": (_vp, [_int]),
+    "rb3b_ctx_make_current": (_int, [_vp]),
+    "rb3b_ctx_destroy": (None, [_vp]),
+    "rb3b_host_alloc_pinned": (_vp, [_i64]),
+    "rb3b_host_free_pinned": (None, [_vp]),
     "rb3b_set_param": (_int, [C.c_char_p, _i64]),
     "rb3b_get_stat": (_i64, [C.c_char_p]),
     "rb3b_index_create": (_vp, []),
@@ -44,6 +50,12 @@ SIGNATURES = {
     "rb3b_mg_rank_part": (_int, [_vp, _i64, _vp, _int, _int, _vp]),
     "rb3b_merge_with_ka": (_int, [_vp, _i64, _vp, _vp]),
     "rb3b_merge_index": (_int, [_vp, _vp]),
+    "rb3b_dist_unique_id": (_int, [_vp]),
+    "rb3b_dist_init": (_int, [_int, _int, _vp]),
+    "rb3b_dist_finalize": (_int, []),
+    "rb3b_dist_rank": (_int, []),
+    "rb3b_dist_world": (_int, []),
+    "rb3b_dist_nccl_version": (_int, []),
     "rb3b_rank1a": (_int, [_vp, _i64, _vp, _vp, _vp]),
     "rb3b_rank1a_dev": (_int, [_vp, _i64, _vp, _vp, _vp]),
     "rb3b_lf_dev": (_int, [_vp, _i64, _vp, _vp, _vp, _int]),

@@ -140,7 +140,7 @@ int rb3b_pick_shift(int64_t n, int64_t n_entries_est)
 	return shift;
 }
 
-int64_t rb3b_get_param(const char *key, int64_t dflt); /* rb3b_runtime.cu */
+
 
 /* bitmap cells cost 1 byte per symbol (twice that with the ping-pong half): use them while that is affordable */
 int rb3b_want_bitmap(int64_t n_symbols)

@@ -35,6 +35,9 @@
 
 #include <stdint.h>
 #include <stdio.h>
+#include <map>
+#include <string>
+#include <vector>
 #include <cuda_runtime.h>
 #include "../../include/rb3_b200.h"
 
@@ -84,15 +87,35 @@ static inline DevIndex rb3b_dev_view(const rb3b_index_s *x)
 }
 
 /* ---- runtime (rb3b_runtime.cu) ---- */
-extern cudaStream_t rb3b_stream;
+/* device-side timing of the main kernels: tic/toc record events on the stream, tflush (after a sync) adds "us_<name>" stats */
+enum { T_PREP, T_WALK1, T_WALKFIX, T_MERGE, T_SCATTER, T_BWT, T_COMM, T_COUNT };
+
+struct Rb3bChunk { char *p; size_t cap; };
+/* execution context: everything a call needs besides its arguments.  One per host thread by default (created on first
+ * use), or explicit (rb3b_ctx_create) to drive several devices / streams from one process. */
+struct rb3b_ctx_s {
+	int device;
+	cudaStream_t stream, my_stream;   /* the stream calls run on; the context's own stream */
+	int own_stream;                   /* stream was supplied by the caller (rb3b_set_stream) */
+	std::vector<Rb3bChunk> chunks;    /* scratch arena */
+	size_t chunk_i, chunk_off, used, high;
+	int depth;                        /* nesting of API calls: the arena is reset when the outermost returns */
+	std::map<std::string, int64_t> stats;
+	int64_t n_launch;                 /* kernels of this library launched so far (CUB internals not counted) */
+	cudaEvent_t ev[T_COUNT][2];
+	int ev_ok, ev_pending[T_COUNT];
+	void *comm;                       /* ncclComm_t when this context is a rank of a multi-device group (rb3b_dist.cu) */
+	int rank, world;
+};
+rb3b_ctx_s *rb3b_cur(void);
+#define rb3b_stream   (rb3b_cur()->stream)
+#define rb3b_n_launch (rb3b_cur()->n_launch)
 extern int64_t rb3b_seg_len, rb3b_rank_variant;
 int  rb3b_fail(int code, const char *fmt, ...);
 int  rb3b_ensure_init(void);
 void rb3b_stat_set(const char *key, int64_t v);
 void rb3b_stat_add(const char *key, int64_t v);
-extern int64_t rb3b_n_launch;   /* kernels of this library launched so far (CUB internals not counted) */
-/* device-side timing of the main kernels: tic/toc record events on the stream, tflush (after a sync) adds "us_<name>" stats */
-enum { T_PREP, T_WALK1, T_WALKFIX, T_MERGE, T_SCATTER, T_BWT, T_COUNT };
+int64_t rb3b_get_param(const char *key, int64_t dflt);
 void rb3b_tic(int id);
 void rb3b_toc(int id);
 void rb3b_tflush(void);

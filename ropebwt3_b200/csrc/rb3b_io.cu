@@ -22,7 +22,7 @@
 
 typedef std::vector<uint8_t> bytes_t;
 
-int64_t rb3b_get_param(const char *key, int64_t dflt); /* rb3b_runtime.cu */
+
 
 static inline int ilog2_u64(uint64_t v) { return v ? 63 - __builtin_clzll(v) : -1; }
 

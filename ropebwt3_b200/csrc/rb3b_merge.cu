@@ -46,7 +46,7 @@
 #define PREP_PER_THREAD 16
 #define PREP_TILE (TPB * PREP_PER_THREAD)
 
-int64_t rb3b_get_param(const char *key, int64_t dflt); /* rb3b_runtime.cu */
+
 
 static inline unsigned nblk(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
@@ -262,9 +262,7 @@ struct Slices {
 
 /* kseq[p]: interleave position of walk-order position p, or, while unresolved, the low end of its bracket plus flags */
 #define KS_UNRES  (1LL << 62)
-#define KS_NARROW (1LL << 61)
-#define LOG_NCELL 3              /* a "narrow" bracket spans at most LOG_NCELL consecutive cells */
-#define LOG_WIDTH ((LOG_NCELL - 1) * 128)
+#define KS_NARROW (1LL << 61)    /* k_walk_pair only: the row's transfer mask is in wmask[] (KS_TIGHT) */
 
 /* The walk kernels are written for a "ranker" WG: Grp<8> (RLE cells, 8 lanes per walk) or BmRank (bitmap cells,
  * one thread per walk). */
@@ -352,7 +350,7 @@ __global__ void __launch_bounds__(TPB) k_walk_first(DevIndex A, Slices S, const 
 				}
 				if (head) continue;
 				if (lo == hi) vb[jj] = lo;
-				else { vb[jj] = lo | KS_UNRES | (hi - lo <= LOG_WIDTH ? KS_NARROW : 0); d += live; }
+				else { vb[jj] = lo | KS_UNRES; d += live; }
 				if (live) {
 					if (c == 0) lo = hi = SO ? 0 : A.acc[1]; /* first symbol of the sequence (fm-index.c:170): the next position is a sentinel row */
 					else {
@@ -393,141 +391,173 @@ __global__ void k_collect_first(Slices S, int64_t *__restrict__ wl_seg, int64_t 
 	}
 }
 
-/* one unresolved row held by one lane; for a narrow bracket everything that does not depend on the exact value is
- * precomputed: T[w] = #c between the window start and 32-bit word w of the window, W[w] = that word of plane c */
-struct LogRow {
-	int64_t pos0, base; /* first position of the window; C[c] + #c before the window */
-	int c, narrow;
-	uint32_t T[4 * LOG_NCELL], W[4 * LOG_NCELL];
-	__device__ __forceinline__ void load(const DevIndex &A, const int64_t *__restrict__ kseq, const uint8_t *__restrict__ wsym, int64_t slot, bool valid)
-	{
-		pos0 = 0; base = 0; c = 0; narrow = 0;
-		if (!valid) return;
-		const int64_t w = kseq[slot], lo = w & (int64_t)RB3B_M42;
-		c = (int)wsym[slot]; narrow = (w & KS_NARROW) != 0;
-		if (!narrow) return;
-		const int h = c >= 3, cc = c - 3 * h;
-		const int64_t j = (lo < A.n ? lo : A.n - 1) >> RB3B_BM_SHIFT;
-		uint4 cq[LOG_NCELL], pq[LOG_NCELL];
-#pragma unroll
-		for (int i = 0; i < LOG_NCELL; ++i) { /* loads independent of the chain */
-			const int64_t ji = j + i < A.n_cells ? j + i : A.n_cells - 1;
-			cq[i] = __ldg(A.cells + ji * 8 + 4 * h); pq[i] = __ldg(A.cells + ji * 8 + 4 * h + 1 + cc);
-		}
-		uint64_t h0 = 0;
-		uint32_t run = 0;
-#pragma unroll
-		for (int i = 0; i < LOG_NCELL; ++i) {
-			uint64_t a0, a1, a2;
-			rb3b_hdr_unpack(cq[i], a0, a1, a2);
-			uint64_t hi = cc == 0 ? a0 : cc == 1 ? a1 : a2;
-			if (i == 0) h0 = hi;
-			const bool real = j + i < A.n_cells; /* past the end of the index: no symbols, the count stays */
-			if (real) run = (uint32_t)(hi - h0);
-			const uint32_t ww[4] = { pq[i].x, pq[i].y, pq[i].z, pq[i].w };
-#pragma unroll
-			for (int k = 0; k < 4; ++k) { T[4 * i + k] = run; W[4 * i + k] = real ? ww[k] : 0u; run += real ? __popc(ww[k]) : 0; }
-		}
-		pos0 = j << RB3B_BM_SHIFT;
-		base = A.acc[c] + (int64_t)h0;
-	}
-};
+/* ---- bitmap cells: lane-pair walk that leaves a transfer function behind ----
+ * Same walk as k_walk_first<BmPair>, plus:
+ *  - WARM-UP: the walk of slice s starts `warm` positions before the slice (rows of the previous slice, results
+ *    discarded), so that its bracket is already a few dozen rows wide when the first own row is reached;
+ *  - MASKS: for an unresolved row whose bracket is at most 127 wide the walk stores wmask[p] = the 128 bits of plane c
+ *    (c = the row's symbol) from position lo on.  With v = lo + x the exact position of the row (0 <= x <= hi - lo),
+ *    the next row's exact position is lo' + popc(mask below x): the fix-up never touches the index again.
+ * The even lane ranks lo, the odd lane hi; each holds the plane of its own cell, the odd lane's travels by shuffle. */
+#define KS_TIGHT KS_NARROW   /* the row's mask is in wmask[] */
+#define TIGHT_WIDTH 127
 
-/* shared-memory image of the 32 rows a warp works on */
-struct FixRows {
-	uint2 TW[32][4 * LOG_NCELL];   /* per row: x = word of plane c, y = #c between the window start and that word */
-	int64_t pos0[32], base[32];
-	int32_t K[32];                 /* base - first position of the NEXT row's window: keeps the chain in 32 bits */
-	uint32_t off[32];              /* result: exact value of the row relative to its window */
-	int32_t c[32];
-};
-
-/* fix-up for bitmap cells: one WARP per listed slice.  Each lane fetches one unresolved row (coalesced: kseq and wsym
- * are in walk order) and the cells it may need, one iteration (32 rows) ahead, and publishes the row's count/word tables
- * in shared memory.  Lane 0 then runs the dependent chain.  For a row with a narrow bracket the exact value is carried as
- * a 32-bit offset into the row's cell window: off' = K + T[off >> 5] + popc(W[off >> 5] below off), one 8-byte
- * shared-memory read and ~10 instructions per row.  Afterwards all lanes write the interleave positions of their rows.
- * Rows whose bracket was wider than the window (the first ~10 of a slice) take the general path with a random cell
- * access.  A slice that never collapsed hands its exact arrival straight to the next slice in the same warp, so one
- * launch resolves every cascade. */
-__global__ void __launch_bounds__(128) k_walk_fix_log(DevIndex A, Slices S, const uint8_t *__restrict__ wsym, int64_t *__restrict__ kseq, int64_t n_items,
-                                                       const int64_t *__restrict__ wl_seg, const int64_t *__restrict__ wl_val, unsigned long long *stats)
+template<bool SO>
+__global__ void __launch_bounds__(32) k_walk_pair(DevIndex A, Slices S, const uint8_t *__restrict__ wsym, int64_t *__restrict__ kseq, uint4 *__restrict__ wmask,
+                                                  int warm, int64_t *next_seg)
 {
-	__shared__ FixRows rows[4]; /* four warps per block */
-	const int lane = threadIdx.x & 31;
-	FixRows &R = rows[threadIdx.x >> 5];
-	int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	if (it >= n_items) return; /* warp-uniform */
-	int64_t t = wl_seg[it], v = wl_val[it];
-	unsigned long long n_rows = 0, n_wide = 0; /* statistics only */
+	const int odd = threadIdx.x & 1, gbase = threadIdx.x & 30;
+	const unsigned gmask = 3u << gbase;
 	for (;;) {
-		const int64_t d = S.d[t], len = S.slice_len(t), base = t * S.seg_len;
-		/* a slice that collapsed exactly on its last row already had an exact arrival in round 1: k_collect_first queued
-		 * its successor as an item of its own, so it must not be entered from here as well */
-		const bool was_exact = S.arr_lo[t] == S.arr_hi[t];
-		int ended = 0;
-		LogRow nxt;
-		nxt.load(A, kseq, wsym, base + lane, lane < d);
-		n_rows += (unsigned long long)d;
-		for (int64_t i0 = 0; i0 < d && !ended; i0 += 32) {
-			const int cnt = d - i0 < 32 ? (int)(d - i0) : 32;
-			const bool live = lane < cnt;
-			/* this lane's row: fast = its step can be taken from the tables */
-			const bool fast = live && nxt.narrow && nxt.c != 0;
-			const int64_t my_pos0 = nxt.pos0, my_base = nxt.base;
-			const int64_t next_pos0 = __shfl_down_sync(0xffffffffu, nxt.pos0, 1);
-			const unsigned fastmask = __ballot_sync(0xffffffffu, fast);
-			/* link: the next row of this iteration is fast too, so the value can stay relative */
-			const bool link = fast && lane + 1 < cnt && (fastmask >> (lane + 1) & 1u);
-			const unsigned linkmask = __ballot_sync(0xffffffffu, link);
-			n_wide += __popc(__ballot_sync(0xffffffffu, live && !nxt.narrow));
+		int64_t s = 0;
+		if (!odd) s = S.walk_lo + (int64_t)atomicAdd((unsigned long long*)next_seg, 1ULL);
+		s = __shfl_sync(gmask, s, gbase);
+		if (s >= S.own_hi) break;
+		const int64_t p0 = s * S.seg_len, n = S.slice_len(s);
+		const int64_t q0 = (SO || s == 0) ? p0 : p0 - warm; /* warm % 8 == 0, warm <= seg_len */
+		const int c0 = q0 == 0 ? 0 : (int)wsym[q0 - 1];
+		int64_t lo, hi, d = 0;
+		if (c0 == 0) lo = hi = SO ? 0 : A.acc[1];
+		else { lo = A.acc[c0]; hi = A.acc[c0 + 1]; }
+		uint64_t w = __ldg((const uint64_t*)(wsym + q0));
+		for (int64_t j = q0 - p0; j < n; j += 8) {
+			const uint64_t wn = j + 8 < n ? __ldg((const uint64_t*)(wsym + p0 + j + 8)) : 0;
+			const bool own = j >= 0;
+			int64_t vb[8];
+			if (SO) {
 #pragma unroll
-			for (int k = 0; k < 4 * LOG_NCELL; ++k) R.TW[lane][k] = make_uint2(nxt.W[k], nxt.T[k]);
-			R.pos0[lane] = my_pos0; R.base[lane] = my_base; R.c[lane] = nxt.c;
-			R.K[lane] = link ? (int32_t)(my_base - next_pos0) : 0;
-			R.off[lane] = 0xffffffffu;
-			nxt.load(A, kseq, wsym, base + i0 + 32 + lane, i0 + 32 + lane < d); /* fetch the next iteration's row meanwhile */
-			__syncwarp();
-			if (lane == 0) {
-				int u = 0;
-				while (u < cnt) {
-					if (fastmask >> u & 1u) { /* a run of table rows: 32-bit relative chain */
-						uint32_t off = (uint32_t)(v - R.pos0[u]);
-						for (;;) {
-							R.off[u] = off;
-							const uint2 tw = R.TW[u][off >> 5];
-							const uint32_t r = tw.y + __popc(tw.x & ((1u << (off & 31u)) - 1u));
-							if (!(linkmask >> u & 1u)) { v = R.base[u] + r; ++u; break; }
-							off = (uint32_t)(R.K[u] + (int32_t)r);
-							++u;
+				for (int jj = 0; jj < 8; ++jj) vb[jj] = j + jj < n ? kseq[p0 + j + jj] : 0;
+			}
+#pragma unroll
+			for (int jj = 0; jj < 8; ++jj) {
+				const int c = (int)(w >> (8 * jj)) & 7;
+				const bool live = j + jj < n;
+				bool head = false;
+				if (SO) {
+					const int64_t f = vb[jj];
+					if (f & KS_HEAD) { head = true; vb[jj] = f & ~KS_HEAD; lo = hi = 0; }
+					else if (f & KS_SEED) lo = hi = f & (int64_t)RB3B_M42;
+				}
+				if (head) continue;
+				const bool unres = lo != hi;
+				const bool tight = unres && wmask != 0 && hi - lo <= TIGHT_WIDTH;
+				if (!unres) vb[jj] = lo;
+				else { vb[jj] = lo | KS_UNRES | (tight ? KS_TIGHT : 0); d += live && own; }
+				if (live) {
+					if (c == 0) lo = hi = SO ? 0 : A.acc[1];
+					else {
+						const int64_t k = odd ? hi : lo, kk = k < A.n ? k : A.n - 1;
+						const int h = c >= 3, cc = c - 3 * h;
+						const uint4 *half = A.cells + ((kk >> RB3B_BM_SHIFT) * 8 + 4 * h);
+						const uint4 cq = __ldg(half), pq = __ldg(half + 1 + cc);
+						const uint64_t l64 = (uint64_t)cq.x | (uint64_t)cq.y << 32, h64 = (uint64_t)cq.z | (uint64_t)cq.w << 32;
+						const uint64_t cnt = (cc == 0 ? l64 : cc == 1 ? (l64 >> 42 | h64 << 22) : h64 >> 20) & RB3B_M42;
+						const uint64_t b0 = (uint64_t)pq.x | (uint64_t)pq.y << 32, b1 = (uint64_t)pq.z | (uint64_t)pq.w << 32;
+						const uint32_t o = (uint32_t)kk & 127u;
+						const uint64_t m0 = o >= 64u ? ~0ULL : (1ULL << o) - 1ULL, m1 = o <= 64u ? 0ULL : (1ULL << (o - 64u)) - 1ULL;
+						int64_t r = (int64_t)(cnt + (uint32_t)(__popcll(b0 & m0) + __popcll(b1 & m1)));
+						r = k < A.n ? r : A.tot[c];
+						const int64_t other = __shfl_xor_sync(gmask, r, 1);
+						if (tight && own) { /* pair-uniform: both lanes carry the same lo, hi */
+							const uint32_t hx = __shfl_xor_sync(gmask, pq.x, 1), hy = __shfl_xor_sync(gmask, pq.y, 1);
+							const uint32_t hz = __shfl_xor_sync(gmask, pq.z, 1), hw = __shfl_xor_sync(gmask, pq.w, 1);
+							const int64_t jo = __shfl_xor_sync(gmask, kk >> RB3B_BM_SHIFT, 1);
+							if (!odd) {
+								const bool nxt = jo != (kk >> RB3B_BM_SHIFT); /* hi lies in the next cell */
+								uint32_t ww[9] = { pq.x, pq.y, pq.z, pq.w, nxt ? hx : 0u, nxt ? hy : 0u, nxt ? hz : 0u, nxt ? hw : 0u, 0u };
+								const uint32_t q = o >> 5, rr = o & 31u;
+								if (q & 1u) {
+#pragma unroll
+									for (int i = 0; i < 8; ++i) ww[i] = ww[i + 1];
+								}
+								if (q & 2u) {
+#pragma unroll
+									for (int i = 0; i < 7; ++i) ww[i] = ww[i + 2];
+								}
+								wmask[p0 + j + jj] = make_uint4(__funnelshift_r(ww[0], ww[1], rr), __funnelshift_r(ww[1], ww[2], rr),
+								                                __funnelshift_r(ww[2], ww[3], rr), __funnelshift_r(ww[3], ww[4], rr));
+							}
 						}
-					} else { /* general row */
-						kseq[base + i0 + u] = v;
-						const int c = R.c[u];
-						if (c == 0) { ended = 1; break; } /* the next position is a sentinel row, exact by itself */
-						v = A.acc[c] + BmRank::rank(A, v, c);
-						++u;
+						lo = A.acc[c] + (odd ? other : r); hi = A.acc[c] + (odd ? r : other);
 					}
 				}
 			}
-			__syncwarp();
-			if (R.off[lane] != 0xffffffffu) kseq[base + i0 + lane] = my_pos0 + R.off[lane]; /* rows resolved through the tables */
-			v = __shfl_sync(0xffffffffu, v, 0);
-			ended = __shfl_sync(0xffffffffu, ended, 0);
-			__syncwarp(); /* the rows are consumed before they are overwritten */
+			if (!odd && own) {
+				if (j + 8 <= n) {
+					longlong2 *o2 = (longlong2*)(kseq + p0 + j);
+					o2[0] = make_longlong2(vb[0], vb[1]); o2[1] = make_longlong2(vb[2], vb[3]);
+					o2[2] = make_longlong2(vb[4], vb[5]); o2[3] = make_longlong2(vb[6], vb[7]);
+				} else {
+#pragma unroll
+					for (int jj = 0; jj < 8; ++jj) if (j + jj < n) kseq[p0 + j + jj] = vb[jj];
+				}
+			}
+			w = wn;
 		}
-		const bool more = d == len && !ended && !was_exact && t + 1 < S.own_hi && S.d[t + 1] > 0; /* t + 1's only predecessor is t and t + 1 is on nobody's list */
-		__syncwarp();
-		if (lane == 0) {
+		if (!odd) { S.d[s] = d; S.arr_lo[s] = lo; S.arr_hi[s] = hi; }
+	}
+}
+
+/* #set bits of the 128-bit mask m among bit positions [0, x), 0 <= x <= 128 */
+__device__ __forceinline__ uint32_t mask_rank(const uint4 m, uint32_t x)
+{
+	const uint64_t b0 = (uint64_t)m.x | (uint64_t)m.y << 32, b1 = (uint64_t)m.z | (uint64_t)m.w << 32;
+	const uint64_t m0 = x >= 64u ? ~0ULL : (1ULL << x) - 1ULL, m1 = x <= 64u ? 0ULL : x >= 128u ? ~0ULL : (1ULL << (x - 64u)) - 1ULL;
+	return (uint32_t)(__popcll(b0 & m0) + __popcll(b1 & m1));
+}
+
+/* fix-up for bitmap cells: one THREAD per listed slice.  The rows of a slice are consecutive in kseq / wsym / wmask, so
+ * every thread streams its own rows (fetched one row ahead: nothing it loads depends on the value it carries) and the
+ * dependent chain per row is x' = popc(mask below x): no access to the index, a dozen instructions.  Rows without a mask
+ * (bracket wider than 127: huge indexes, or no warm-up) take the general step with one random cell access.  A slice that
+ * never collapsed hands its exact arrival straight to the next slice in the same thread, so one launch resolves every
+ * cascade.  stats: [0] rows, [1] rows that took the general step, [2] longest chain. */
+__global__ void __launch_bounds__(128) k_fix_chain(DevIndex A, Slices S, const uint8_t *__restrict__ wsym, int64_t *__restrict__ kseq, const uint4 *__restrict__ wmask,
+                                                    int64_t n_items, const int64_t *__restrict__ wl_seg, const int64_t *__restrict__ wl_val, unsigned long long *stats)
+{
+	const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long n_rows = 0, n_wide = 0;
+	if (it < n_items) {
+		int64_t t = wl_seg[it], v = wl_val[it];
+		for (;;) {
+			const int64_t d = S.d[t], len = S.slice_len(t), base = t * S.seg_len;
+			/* a slice that collapsed exactly on its last row already had an exact arrival in round 1: k_collect_first
+			 * queued its successor as an item of its own, so it must not be entered from here as well */
+			const bool was_exact = S.arr_lo[t] == S.arr_hi[t];
+			const int64_t arr = S.arr_lo[t];
+			bool ended = false;
+			int64_t ks = d > 0 ? kseq[base] : 0;
+			int c = d > 0 ? (int)wsym[base] : 0;
+			uint4 m = make_uint4(0, 0, 0, 0);
+			if (d > 0 && (ks & KS_TIGHT)) m = wmask[base];
+			n_rows += (unsigned long long)d;
+			for (int64_t i = 0; i < d; ++i) {
+				/* the next row (or, after the last row of the slice, the bracket the walk arrived with) */
+				const bool more = i + 1 < len;
+				const int64_t ks_n = more ? kseq[base + i + 1] : arr;
+				const int c_n = more ? (int)wsym[base + i + 1] : 0;
+				uint4 m_n = make_uint4(0, 0, 0, 0);
+				if (more && i + 1 < d && (ks_n & KS_TIGHT)) m_n = wmask[base + i + 1];
+				kseq[base + i] = v;
+				if (c == 0) { ended = true; break; } /* the next position is a sentinel row, exact by itself */
+				if (ks & KS_TIGHT) v = (ks_n & (int64_t)RB3B_M42) + mask_rank(m, (uint32_t)(v - (ks & (int64_t)RB3B_M42)));
+				else { v = A.acc[c] + BmRank::rank(A, v, c); ++n_wide; }
+				ks = ks_n; c = c_n; m = m_n;
+			}
+			const bool go_on = d == len && !ended && !was_exact && t + 1 < S.own_hi && S.d[t + 1] > 0; /* t + 1's only predecessor is t and t + 1 is on nobody's list */
 			S.d[t] = 0;
-			if (d == len) S.arr_lo[t] = S.arr_hi[t] = v;
+			if (d == len && !ended) S.arr_lo[t] = S.arr_hi[t] = v;
+			if (!go_on) break;
+			++t;
 		}
-		if (!more) break;
-		++t;
 	}
-	if (lane == 0) { /* [0] rows, [1] rows with a wide bracket, [2] longest chain */
-		atomicAdd(stats, n_rows); atomicAdd(stats + 1, n_wide); atomicMax(stats + 2, n_rows);
-	}
+	/* statistics */
+	for (int o = 16; o > 0; o >>= 1) { n_wide += __shfl_xor_sync(0xffffffffu, n_wide, o); }
+	unsigned long long tot = n_rows;
+	for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+	unsigned long long mx = n_rows;
+	for (int o = 16; o > 0; o >>= 1) { const unsigned long long y = __shfl_xor_sync(0xffffffffu, mx, o); mx = y > mx ? y : mx; }
+	if ((threadIdx.x & 31) == 0 && tot) { atomicAdd(stats, tot); atomicAdd(stats + 1, n_wide); atomicMax(stats + 2, mx); }
 }
 
 /* generic fix-up (RLE cells, or bitmap cells without the tables): re-walk the unresolved prefix of each listed slice
@@ -727,7 +757,11 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	TRY(wsym.alloc(len + 16)); /* padded: the walks read whole 8-byte words */
 	const bool narrow_lf = len < LF32_MAX_LEN && !rb3b_get_param("wide_lf", 0);
 	/* walk-order positions this device reads (everything for a sorted collection: the heads are resolved on every device) */
-	const int64_t p_lo = so ? -1 : S.walk_lo * seg_len - 1, p_hi = so ? len : S.own_hi * seg_len;
+	/* rows walked before every slice to narrow its bracket (k_walk_pair) */
+	int warm = (int)rb3b_get_param("warm_rows", 16);
+	warm = warm < 0 ? 0 : (warm + 7) / 8 * 8;
+	if (warm > seg_len) warm = (int)seg_len;
+	const int64_t p_lo = so ? -1 : S.walk_lo * seg_len - warm - 1, p_hi = so ? len : S.own_hi * seg_len;
 	const int64_t *c_base = 0, *c_len = 0;
 	if (narrow_lf) TRY((walk_order<uint32_t, uint32_t>(len, d_bwt, nt, tex.p, acc, F, p_lo, p_hi, wsym, &wrow, &c_base, &c_len)));
 	else TRY((walk_order<uint64_t, int64_t>(len, d_bwt, nt, tex.p, acc, F, p_lo, p_hi, wsym, &wrow, &c_base, &c_len)));
@@ -748,16 +782,20 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	if (want < 1) want = 1;
 	rb3b_tic(T_WALK1);
 	const unsigned wgrid = (unsigned)(want < cap ? want : cap);
+	/* transfer masks of the unresolved rows (16 bytes per row of the batch): only for batches that can afford them */
+	DBuf<uint4> wmask;
+	const bool use_mask = pair && len <= rb3b_get_param("mask_max_rows", 1LL << 28);
+	if (use_mask) TRY(wmask.alloc(len));
 	if (so) {
 		CK(cudaMemsetAsync(kseq.p, 0, (len + 8) * 8, rb3b_stream));
 		if (bm) k_so_heads<BmRank><<<nblk(F.n_seq, TPB), TPB, 0, rb3b_stream>>>(dA, so, F.n_seq, c_base, c_len, wsym.p, kseq.p);
 		else k_so_heads<Grp<8> ><<<nblk(F.n_seq * 8, TPB), TPB, 0, rb3b_stream>>>(dA, so, F.n_seq, c_base, c_len, wsym.p, kseq.p);
 		CKK();
-		if (pair) k_walk_first<BmPair, true><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
+		if (pair) k_walk_pair<true><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, use_mask ? wmask.p : 0, warm, ctr.p);
 		else if (bm) k_walk_first<BmRank, true><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
 		else k_walk_first<Grp<8>, true><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
 	} else {
-		if (pair) k_walk_first<BmPair, false><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
+		if (pair) k_walk_pair<false><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, use_mask ? wmask.p : 0, warm, ctr.p);
 		else if (bm) k_walk_first<BmRank, false><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
 		else k_walk_first<Grp<8>, false><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
 	}
@@ -775,7 +813,7 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 		CK(cudaMemsetAsync(ctr.p + 2, 0, 40, rb3b_stream));
 		want = (n_items * wg + wtpb - 1) / wtpb;
 		rb3b_tic(T_WALKFIX);
-		if (use_log) k_walk_fix_log<<<nblk(n_items * 32, 128), 128, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, n_items, wl_seg[cur], wl_val[cur],
+		if (use_log) k_fix_chain<<<nblk(n_items, 128), 128, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, use_mask ? wmask.p : 0, n_items, wl_seg[cur], wl_val[cur],
 			(unsigned long long*)(ctr.p + 4));
 		else if (bm) k_walk_fix<BmRank><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, n_items, wl_seg[cur], wl_val[cur], ctr.p + 2,
 			wl_seg[cur ^ 1], wl_val[cur ^ 1], (unsigned long long*)(ctr.p + 3));

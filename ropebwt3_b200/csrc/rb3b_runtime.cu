@@ -1,64 +1,169 @@
 /*
- * rb3b_runtime.cu -- device selection, stream, memory pool, error text, counters.
- * There is no CPU fallback anywhere in this library: if no CUDA device can be
- * initialised every entry point fails with RB3B_ENODEV.
+ * rb3b_runtime.cu -- execution contexts (device, stream, scratch arena, counters, NCCL communicator), error text,
+ * tuning knobs.  There is no CPU fallback anywhere in this library: if no CUDA device can be initialised every entry
+ * point fails with RB3B_ENODEV.
+ *
+ * Every API call runs in the CONTEXT that is current on the calling host thread.  A thread that never asked for one
+ * gets its own default context (own stream, own arena) on first use, so two threads can drive two calls at the same
+ * time -- e.g. the partial BWT of batch i+1 while batch i is being merged, the reference's kt_pipeline of build.c:55-83
+ * -- and N threads with N explicit contexts can drive N devices from one process (rb3b_ctx_create(device)).
  */
 #include <stdarg.h>
 #include <string.h>
 #include <map>
+#include <mutex>
 #include <string>
+#include <vector>
 #include "rb3b_internal.cuh"
 
-cudaStream_t rb3b_stream = 0;
 int64_t rb3b_seg_len = 0;         /* target LF-walk segment length ("seg_len") */
 int64_t rb3b_rank_variant = 0;    /* 0: LDG.128 per lane, 1: cp.async.bulk (TMA) staged */
 
-static int g_inited = 0, g_device = 0, g_own_stream = 0;
-static cudaStream_t g_my_stream = 0;
+static int g_inited = 0, g_device = 0;
 static thread_local char g_err[1024] = "";
-static std::map<std::string, int64_t> g_stats;
 static std::map<std::string, int64_t> g_params;
+static std::mutex g_mu; /* guards g_params and one-time device set-up */
 
-/* ---- scratch arena ---- */
-#include <vector>
-struct Chunk { char *p; size_t cap; };
-static std::vector<Chunk> g_chunks;
-static size_t g_chunk_i = 0, g_chunk_off = 0, g_used = 0, g_high = 0;
-static int g_depth = 0;
+static const char *g_ev_name[T_COUNT] = { "us_prep", "us_walk_first", "us_walk_fix", "us_merge", "us_scatter", "us_bwt", "us_comm" };
+
+/* ---- contexts ---- */
+
+static int ctx_setup(rb3b_ctx_s *c, int device)
+{
+	c->device = device;
+	c->stream = c->my_stream = 0; c->own_stream = 0;
+	c->chunk_i = c->chunk_off = c->used = c->high = 0; c->depth = 0;
+	c->n_launch = 0; c->ev_ok = 0;
+	c->comm = 0; c->rank = 0; c->world = 1;
+	memset(c->ev_pending, 0, sizeof(c->ev_pending));
+	CK(cudaSetDevice(device));
+	CK(cudaStreamCreateWithFlags(&c->my_stream, cudaStreamNonBlocking));
+	c->stream = c->my_stream;
+	{
+		std::lock_guard<std::mutex> lk(g_mu);
+		cudaMemPool_t pool;
+		CK(cudaDeviceGetDefaultMemPool(&pool, device));
+		uint64_t thr = UINT64_MAX; /* keep freed index buffers in the pool: merges reuse them */
+		CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+	}
+	return RB3B_OK;
+}
+
+void rb3b_dist_release(rb3b_ctx_s *c); /* rb3b_dist.cu */
+
+static void ctx_teardown(rb3b_ctx_s *c)
+{
+	if (c->comm) rb3b_dist_release(c);
+	if (c->my_stream) {
+		cudaSetDevice(c->device);
+		cudaStreamSynchronize(c->stream);
+		for (size_t i = 0; i < c->chunks.size(); ++i) cudaFree(c->chunks[i].p);
+		c->chunks.clear();
+		if (c->ev_ok) for (int i = 0; i < T_COUNT; ++i) { cudaEventDestroy(c->ev[i][0]); cudaEventDestroy(c->ev[i][1]); }
+		cudaStreamDestroy(c->my_stream);
+		c->my_stream = 0;
+	}
+	cudaGetLastError();
+}
+
+/* the calling thread's own default context; torn down when the thread ends */
+struct DefaultCtx {
+	rb3b_ctx_s *c;
+	DefaultCtx() : c(0) {}
+	~DefaultCtx() { if (c) { ctx_teardown(c); delete c; c = 0; } }
+};
+static thread_local DefaultCtx tl_default;
+static thread_local rb3b_ctx_s *tl_cur = 0;
+
+rb3b_ctx_s *rb3b_cur(void)
+{
+	if (tl_cur) return tl_cur;
+	if (tl_default.c == 0) {
+		rb3b_ctx_s *c = new rb3b_ctx_s;
+		if (ctx_setup(c, g_device) != RB3B_OK) { /* callers went through rb3b_ensure_init first, so this is unexpected; keep a usable object */
+			c->stream = c->my_stream = 0;
+		}
+		tl_default.c = c;
+	}
+	tl_cur = tl_default.c;
+	return tl_cur;
+}
+
+extern "C" rb3b_ctx_t *rb3b_ctx_create(int device)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { rb3b_fail(RB3B_ENODEV, "no CUDA device; this library has no CPU fallback"); return 0; }
+	if (device < 0 || device >= n) { rb3b_fail(RB3B_EINVAL, "device %d out of range [0,%d)", device, n); return 0; }
+	rb3b_ctx_s *c = new rb3b_ctx_s;
+	if (ctx_setup(c, device) != RB3B_OK) { delete c; return 0; }
+	g_inited = 1;
+	return c;
+}
+
+extern "C" int rb3b_ctx_make_current(rb3b_ctx_t *c)
+{
+	tl_cur = c; /* NULL: back to this thread's default context (created on first use) */
+	if (c) CK(cudaSetDevice(c->device));
+	return RB3B_OK;
+}
+
+extern "C" void rb3b_ctx_destroy(rb3b_ctx_t *c)
+{
+	if (c == 0) return;
+	if (tl_cur == c) tl_cur = 0;
+	ctx_teardown(c);
+	delete c;
+}
+
+/* ---- scratch arena (per context) ---- */
 
 void *rb3b_arena_alloc(size_t bytes)
 {
+	rb3b_ctx_s *c = rb3b_cur();
 	bytes = (bytes + 511) & ~(size_t)511;
 	for (;;) {
-		if (g_chunk_i < g_chunks.size() && g_chunk_off + bytes <= g_chunks[g_chunk_i].cap) {
-			void *p = g_chunks[g_chunk_i].p + g_chunk_off;
-			g_chunk_off += bytes; g_used += bytes;
-			if (g_used > g_high) g_high = g_used;
+		if (c->chunk_i < c->chunks.size() && c->chunk_off + bytes <= c->chunks[c->chunk_i].cap) {
+			void *p = c->chunks[c->chunk_i].p + c->chunk_off;
+			c->chunk_off += bytes; c->used += bytes;
+			if (c->used > c->high) c->high = c->used;
 			return p;
 		}
-		if (g_chunk_i + 1 < g_chunks.size()) { ++g_chunk_i; g_chunk_off = 0; continue; }
-		Chunk c;
-		c.cap = bytes > ((size_t)64 << 20) ? bytes + (bytes >> 2) : (size_t)64 << 20;
-		if (cudaMalloc((void**)&c.p, c.cap) != cudaSuccess) { cudaGetLastError(); return 0; }
-		g_chunks.push_back(c);
-		g_chunk_i = g_chunks.size() - 1; g_chunk_off = 0;
+		if (c->chunk_i + 1 < c->chunks.size()) { ++c->chunk_i; c->chunk_off = 0; continue; }
+		Rb3bChunk k;
+		k.cap = bytes > ((size_t)64 << 20) ? bytes + (bytes >> 2) : (size_t)64 << 20;
+		if (cudaMalloc((void**)&k.p, k.cap) != cudaSuccess) { cudaGetLastError(); return 0; }
+		c->chunks.push_back(k);
+		c->chunk_i = c->chunks.size() - 1; c->chunk_off = 0;
 	}
 }
 
-void rb3b_arena_enter(void) { ++g_depth; }
+void rb3b_arena_enter(void) { ++rb3b_cur()->depth; }
 
 void rb3b_arena_leave(void)
 {
-	if (--g_depth > 0) return;
-	if (g_chunks.size() > 1) { /* fold the chunks into one that fits everything the last call needed */
-		cudaStreamSynchronize(rb3b_stream);
-		for (size_t i = 0; i < g_chunks.size(); ++i) cudaFree(g_chunks[i].p);
-		g_chunks.clear();
-		Chunk c;
-		c.cap = g_high + (g_high >> 2) + ((size_t)16 << 20);
-		if (cudaMalloc((void**)&c.p, c.cap) == cudaSuccess) g_chunks.push_back(c); else cudaGetLastError();
+	rb3b_ctx_s *c = rb3b_cur();
+	if (--c->depth > 0) return;
+	if (c->chunks.size() > 1) { /* fold the chunks into one that fits everything the last call needed */
+		cudaStreamSynchronize(c->stream);
+		for (size_t i = 0; i < c->chunks.size(); ++i) cudaFree(c->chunks[i].p);
+		c->chunks.clear();
+		Rb3bChunk k;
+		k.cap = c->high + (c->high >> 2) + ((size_t)16 << 20);
+		if (cudaMalloc((void**)&k.p, k.cap) == cudaSuccess) c->chunks.push_back(k); else cudaGetLastError();
 	}
-	g_chunk_i = 0; g_chunk_off = 0; g_used = 0;
+	c->chunk_i = 0; c->chunk_off = 0; c->used = 0;
+}
+
+/* give the scratch memory back to the device (a long-lived process between phases with very different needs) */
+extern "C" int rb3b_trim(void)
+{
+	rb3b_ctx_s *c = rb3b_cur();
+	if (c->depth > 0) return rb3b_fail(RB3B_EINVAL, "rb3b_trim inside an API call");
+	cudaStreamSynchronize(c->stream);
+	for (size_t i = 0; i < c->chunks.size(); ++i) cudaFree(c->chunks[i].p);
+	c->chunks.clear();
+	c->chunk_i = c->chunk_off = c->used = c->high = 0;
+	return RB3B_OK;
 }
 
 int rb3b_fail(int code, const char *fmt, ...)
@@ -70,39 +175,38 @@ int rb3b_fail(int code, const char *fmt, ...)
 	return code;
 }
 
-int64_t rb3b_n_launch = 0;
-static cudaEvent_t g_ev[T_COUNT][2];
-static int g_ev_ok = 0, g_ev_pending[T_COUNT];
-static const char *g_ev_name[T_COUNT] = { "us_prep", "us_walk_first", "us_walk_fix", "us_merge", "us_scatter", "us_bwt" };
+/* ---- device-side timing of the main kernels ---- */
 
 void rb3b_tic(int id)
 {
-	if (!g_ev_ok) {
-		for (int i = 0; i < T_COUNT; ++i) { cudaEventCreate(&g_ev[i][0]); cudaEventCreate(&g_ev[i][1]); g_ev_pending[i] = 0; }
-		g_ev_ok = 1;
+	rb3b_ctx_s *c = rb3b_cur();
+	if (!c->ev_ok) {
+		for (int i = 0; i < T_COUNT; ++i) { cudaEventCreate(&c->ev[i][0]); cudaEventCreate(&c->ev[i][1]); c->ev_pending[i] = 0; }
+		c->ev_ok = 1;
 	}
-	if (g_ev_pending[id]) rb3b_tflush();
-	cudaEventRecord(g_ev[id][0], rb3b_stream);
+	if (c->ev_pending[id]) rb3b_tflush();
+	cudaEventRecord(c->ev[id][0], c->stream);
 }
 
-void rb3b_toc(int id) { cudaEventRecord(g_ev[id][1], rb3b_stream); g_ev_pending[id] = 1; }
+void rb3b_toc(int id) { rb3b_ctx_s *c = rb3b_cur(); cudaEventRecord(c->ev[id][1], c->stream); c->ev_pending[id] = 1; }
 
 void rb3b_tflush(void)
 {
+	rb3b_ctx_s *c = rb3b_cur();
 	for (int i = 0; i < T_COUNT; ++i)
-		if (g_ev_ok && g_ev_pending[i]) {
+		if (c->ev_ok && c->ev_pending[i]) {
 			float ms = 0;
-			cudaEventSynchronize(g_ev[i][1]);
-			if (cudaEventElapsedTime(&ms, g_ev[i][0], g_ev[i][1]) == cudaSuccess) rb3b_stat_add(g_ev_name[i], (int64_t)(ms * 1000.0f + 0.5f));
-			g_ev_pending[i] = 0;
+			cudaEventSynchronize(c->ev[i][1]);
+			if (cudaEventElapsedTime(&ms, c->ev[i][0], c->ev[i][1]) == cudaSuccess) rb3b_stat_add(g_ev_name[i], (int64_t)(ms * 1000.0f + 0.5f));
+			c->ev_pending[i] = 0;
 		}
 }
 
-void rb3b_stat_set(const char *key, int64_t v) { g_stats[key] = v; }
-void rb3b_stat_add(const char *key, int64_t v) { g_stats[key] += v; }
+void rb3b_stat_set(const char *key, int64_t v) { rb3b_cur()->stats[key] = v; }
+void rb3b_stat_add(const char *key, int64_t v) { rb3b_cur()->stats[key] += v; }
 
 extern "C" const char *rb3b_last_error(void) { return g_err; }
-extern "C" const char *rb3b_version(void) { return "rb3b200-0.1 (ropebwt3 3.10-r281 merge path, sm_100a)"; }
+extern "C" const char *rb3b_version(void) { return "rb3b200-0.2 (ropebwt3 3.10-r281 merge path, sm_100a)"; }
 
 extern "C" int rb3b_init(int device)
 {
@@ -111,29 +215,35 @@ extern "C" int rb3b_init(int device)
 	if (e != cudaSuccess || n <= 0)
 		return rb3b_fail(RB3B_ENODEV, "no CUDA device (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count=0");
 	if (device < 0 || device >= n) return rb3b_fail(RB3B_EINVAL, "device %d out of range [0,%d)", device, n);
-	CK(cudaSetDevice(device));
-	g_device = device;
-	if (!g_my_stream) CK(cudaStreamCreateWithFlags(&g_my_stream, cudaStreamNonBlocking));
-	if (!g_own_stream) rb3b_stream = g_my_stream;
-	cudaMemPool_t pool;
-	CK(cudaDeviceGetDefaultMemPool(&pool, device));
-	uint64_t thr = UINT64_MAX; /* keep freed scratch in the pool: merges reuse it */
-	CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+	g_device = device; /* default device of the default contexts created from now on */
 	g_inited = 1;
+	if (tl_default.c && tl_default.c->device != device && tl_default.c->depth == 0) { /* this thread's default context moves with it */
+		if (tl_cur == tl_default.c) tl_cur = 0;
+		ctx_teardown(tl_default.c);
+		delete tl_default.c;
+		tl_default.c = 0;
+	}
+	rb3b_ctx_s *c = rb3b_cur();
+	if (c->my_stream == 0) return rb3b_fail(RB3B_ENODEV, "cannot create a stream on device %d", device);
+	CK(cudaSetDevice(c->device));
 	return RB3B_OK;
 }
 
 int rb3b_ensure_init(void)
 {
-	if (g_inited) { cudaSetDevice(g_device); return RB3B_OK; }
-	return rb3b_init(0);
+	if (!g_inited) return rb3b_init(0);
+	rb3b_ctx_s *c = rb3b_cur();
+	if (c->my_stream == 0) return rb3b_fail(RB3B_ENODEV, "no usable CUDA device for this thread's context");
+	cudaSetDevice(c->device);
+	return RB3B_OK;
 }
 
 extern "C" int rb3b_set_stream(void *s)
 {
 	TRY(rb3b_ensure_init());
-	if (s) { rb3b_stream = (cudaStream_t)s; g_own_stream = 1; }
-	else { rb3b_stream = g_my_stream; g_own_stream = 0; }
+	rb3b_ctx_s *c = rb3b_cur();
+	if (s) { c->stream = (cudaStream_t)s; c->own_stream = 1; }
+	else { c->stream = c->my_stream; c->own_stream = 0; }
 	return RB3B_OK;
 }
 
@@ -146,6 +256,7 @@ extern "C" int rb3b_sync(void)
 
 extern "C" int rb3b_set_param(const char *key, int64_t value)
 {
+	std::lock_guard<std::mutex> lk(g_mu);
 	if (!strcmp(key, "seg_len")) { if (value != 0 && value < 16) return rb3b_fail(RB3B_EINVAL, "seg_len must be >= 16 (0 = automatic)"); rb3b_seg_len = value; }
 	else if (!strcmp(key, "rank_variant")) rb3b_rank_variant = value;
 	else g_params[key] = value;
@@ -154,30 +265,36 @@ extern "C" int rb3b_set_param(const char *key, int64_t value)
 
 int64_t rb3b_get_param(const char *key, int64_t dflt)
 {
+	std::lock_guard<std::mutex> lk(g_mu);
 	std::map<std::string, int64_t>::iterator it = g_params.find(key);
 	return it == g_params.end() ? dflt : it->second;
 }
 
 extern "C" int64_t rb3b_get_stat(const char *key)
 {
-	if (!strcmp(key, "kernel_launches")) return rb3b_n_launch;
+	rb3b_ctx_s *c = rb3b_cur();
+	if (!strcmp(key, "kernel_launches")) return c->n_launch;
 	if (!strcmp(key, "seg_len")) return rb3b_seg_len;
-	if (!strcmp(key, "reset")) { g_stats.clear(); rb3b_n_launch = 0; return 0; }
-	std::map<std::string, int64_t>::iterator it = g_stats.find(key);
-	return it == g_stats.end() ? -1 : it->second;
+	if (!strcmp(key, "reset")) { c->stats.clear(); c->n_launch = 0; return 0; }
+	if (!strcmp(key, "arena_high_bytes")) return (int64_t)c->high;
+	std::map<std::string, int64_t>::iterator it = c->stats.find(key);
+	return it == c->stats.end() ? -1 : it->second;
 }
 
 /* Largest batch (symbols) the device can take next to an index that will grow by it: the suffix sorter needs ~44 bytes
  * per symbol; the rank phase of a batch beyond 2^29 rows 8 (LF) + 8 (rows) + 1 (symbols) + 8 (kseq) + 8 (ka) + 1 (list
- * nodes) + 16 (bucketed scatter) + sort scratch ~ 60; the scratch arena keeps its high-water mark; both ping-pong halves
- * of the index ~2 x 1 byte per symbol; 32-bit suffix array. */
+ * nodes) + 16 (bucketed scatter) + sort scratch ~ 60; every context's scratch arena keeps its high-water mark (the
+ * pipelined CLI sorts batch i+1 in one context while batch i is merged in another: both arenas are live at once); both
+ * ping-pong halves of the index ~2 x 1 byte per symbol; 32-bit suffix array. */
 extern "C" int64_t rb3b_max_batch_symbols(int64_t index_symbols)
 {
 	size_t fr = 0, tot = 0;
 	if (rb3b_ensure_init() != RB3B_OK) return -1;
 	if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return -1;
 	int64_t avail = (int64_t)tot - (int64_t)(tot >> 4) - 2 * index_symbols; /* what this process already holds counts as available */
-	int64_t n = avail / 72;
+	const int64_t other = (int64_t)tot - (int64_t)fr - (int64_t)rb3b_cur()->high; /* held by anybody, minus (roughly) our own scratch */
+	if (other > (int64_t)(tot >> 2)) avail -= other - (int64_t)(tot >> 2); /* a device that is visibly shared: be conservative */
+	int64_t n = avail / (int64_t)rb3b_get_param("batch_bytes_per_symbol", 72 + 44);
 	const int64_t cap = (1LL << 32) - 4096;
 	if (n > cap) n = cap;
 	return n > 0 ? n : 0;
@@ -187,11 +304,21 @@ extern "C" void *rb3b_dev_alloc(int64_t bytes)
 {
 	void *p = 0;
 	if (rb3b_ensure_init() != RB3B_OK) return 0;
-	if (cudaMalloc(&p, bytes > 0 ? bytes : 1) != cudaSuccess) { rb3b_fail(RB3B_ENOMEM, "cudaMalloc(%lld) failed", (long long)bytes); return 0; }
+	if (cudaMalloc(&p, bytes > 0 ? bytes : 1) != cudaSuccess) { cudaGetLastError(); rb3b_fail(RB3B_ENOMEM, "cudaMalloc(%lld) failed", (long long)bytes); return 0; }
 	return p;
 }
 
 extern "C" void rb3b_dev_free(void *p) { if (p) cudaFree(p); }
+
+extern "C" void *rb3b_host_alloc_pinned(int64_t bytes)
+{
+	void *p = 0;
+	if (rb3b_ensure_init() != RB3B_OK) return 0;
+	if (cudaMallocHost(&p, bytes > 0 ? bytes : 1) != cudaSuccess) { cudaGetLastError(); rb3b_fail(RB3B_ENOMEM, "cudaMallocHost(%lld) failed", (long long)bytes); return 0; }
+	return p;
+}
+
+extern "C" void rb3b_host_free_pinned(void *p) { if (p) cudaFreeHost(p); }
 
 extern "C" int rb3b_h2d(void *dst, const void *src, int64_t bytes)
 {
