@@ -498,24 +498,55 @@ __global__ void __launch_bounds__(32) k_walk_pair(DevIndex A, Slices S, const ui
 	}
 }
 
+/* mask of the low min(max(t, 0), 32) bits */
+__device__ __forceinline__ uint32_t below32(int t)
+{
+	uint32_t r;
+	const uint32_t tt = (uint32_t)max(t, 0);
+	asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(r) : "r"(0u), "r"(tt));
+	return r;
+}
+
 /* #set bits of the 128-bit mask m among bit positions [0, x), 0 <= x <= 128 */
 __device__ __forceinline__ uint32_t mask_rank(const uint4 m, uint32_t x)
 {
-	const uint64_t b0 = (uint64_t)m.x | (uint64_t)m.y << 32, b1 = (uint64_t)m.z | (uint64_t)m.w << 32;
-	const uint64_t m0 = x >= 64u ? ~0ULL : (1ULL << x) - 1ULL, m1 = x <= 64u ? 0ULL : x >= 128u ? ~0ULL : (1ULL << (x - 64u)) - 1ULL;
-	return (uint32_t)(__popcll(b0 & m0) + __popcll(b1 & m1));
+	return __popc(m.x & below32((int)x)) + __popc(m.y & below32((int)x - 32)) + __popc(m.z & below32((int)x - 64)) + __popc(m.w & below32((int)x - 96));
 }
 
-/* fix-up for bitmap cells: one THREAD per listed slice.  The rows of a slice are consecutive in kseq / wsym / wmask, so
- * every thread streams its own rows (fetched one row ahead: nothing it loads depends on the value it carries) and the
- * dependent chain per row is x' = popc(mask below x): no access to the index, a dozen instructions.  Rows without a mask
- * (bracket wider than 127: huge indexes, or no warm-up) take the general step with one random cell access.  A slice that
- * never collapsed hands its exact arrival straight to the next slice in the same thread, so one launch resolves every
- * cascade.  stats: [0] rows, [1] rows that took the general step, [2] longest chain. */
-__global__ void __launch_bounds__(128) k_fix_chain(DevIndex A, Slices S, const uint8_t *__restrict__ wsym, int64_t *__restrict__ kseq, const uint4 *__restrict__ wmask,
-                                                    int64_t n_items, const int64_t *__restrict__ wl_seg, const int64_t *__restrict__ wl_val, unsigned long long *stats)
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{ asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory"); }
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
+{ asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+#define FIX_TPB 32
+#define FIX_STAGES 4
+/* shared-memory ring of a fix-up CTA: per thread and stage eight consecutive rows of its slice (thread-interleaved so that
+ * the threads of a warp hit different banks) */
+struct FixRing {
+	uint4 m[FIX_STAGES][8][FIX_TPB];        /* transfer masks */
+	longlong2 ks[FIX_STAGES][4][FIX_TPB];   /* kseq words (low end of the bracket + flags) */
+	uint64_t sym[FIX_STAGES][FIX_TPB];
+	int64_t lo_next[FIX_STAGES][FIX_TPB];   /* kseq word of the row after the eight */
+};
+
+/* fix-up for bitmap cells: one THREAD per listed slice.  The rows of a slice are consecutive in kseq / wsym / wmask / wrow,
+ * so every thread streams its own rows in blocks of eight through a private cp.async ring in shared memory (FIX_STAGES
+ * blocks in flight: nothing it fetches depends on the value it carries) and the dependent chain per row is
+ * x' = popc(mask below x), 32-bit, no access to the index.  Rows without a mask (bracket wider than 127: huge indexes, or
+ * no warm-up) take the general step with one random cell access.  A slice that never collapsed hands its exact arrival
+ * straight to the next slice in the same thread, so one launch resolves every cascade.
+ * stats: [0] rows, [1] rows that took the general step, [2] longest chain.
+ * (Tried and dropped: scattering the exact rows to ka[wrow[p]] from inside the walk and this kernel instead of a separate
+ * pass -- the random stores compete with the walk's own dependent accesses, 0.31 -> 0.67 ms for the walk; and G = 4..32 lanes
+ * per slice with the mask travelling by shuffle -- 0.53-0.61 ms against 0.27 ms for one thread per slice.) */
+__global__ void __launch_bounds__(FIX_TPB) k_fix_chain(DevIndex A, Slices S, const uint8_t *__restrict__ wsym, int64_t *__restrict__ kseq, const uint4 *__restrict__ wmask,
+                                                        int64_t n_items, const int64_t *__restrict__ wl_seg, const int64_t *__restrict__ wl_val, unsigned long long *stats)
 {
-	const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	__shared__ FixRing R;
+	const int tx = threadIdx.x;
+	const int64_t it = (int64_t)blockIdx.x * blockDim.x + tx;
 	unsigned long long n_rows = 0, n_wide = 0;
 	if (it < n_items) {
 		int64_t t = wl_seg[it], v = wl_val[it];
@@ -525,25 +556,52 @@ __global__ void __launch_bounds__(128) k_fix_chain(DevIndex A, Slices S, const u
 			 * queued its successor as an item of its own, so it must not be entered from here as well */
 			const bool was_exact = S.arr_lo[t] == S.arr_hi[t];
 			const int64_t arr = S.arr_lo[t];
+			const int nb = (int)((d + 7) >> 3);
 			bool ended = false;
-			int64_t ks = d > 0 ? kseq[base] : 0;
-			int c = d > 0 ? (int)wsym[base] : 0;
-			uint4 m = make_uint4(0, 0, 0, 0);
-			if (d > 0 && (ks & KS_TIGHT)) m = wmask[base];
 			n_rows += (unsigned long long)d;
-			for (int64_t i = 0; i < d; ++i) {
-				/* the next row (or, after the last row of the slice, the bracket the walk arrived with) */
-				const bool more = i + 1 < len;
-				const int64_t ks_n = more ? kseq[base + i + 1] : arr;
-				const int c_n = more ? (int)wsym[base + i + 1] : 0;
-				uint4 m_n = make_uint4(0, 0, 0, 0);
-				if (more && i + 1 < d && (ks_n & KS_TIGHT)) m_n = wmask[base + i + 1];
-				kseq[base + i] = v;
-				if (c == 0) { ended = true; break; } /* the next position is a sentinel row, exact by itself */
-				if (ks & KS_TIGHT) v = (ks_n & (int64_t)RB3B_M42) + mask_rank(m, (uint32_t)(v - (ks & (int64_t)RB3B_M42)));
-				else { v = A.acc[c] + BmRank::rank(A, v, c); ++n_wide; }
-				ks = ks_n; c = c_n; m = m_n;
+			/* blocks are fetched whole (8 rows, aligned): the buffers are padded past the last slice */
+#define FIX_ISSUE(b) do { if ((b) < nb) { const int st_ = (b) % FIX_STAGES; const int64_t p_ = base + 8 * (int64_t)(b); \
+				for (int i_ = 0; i_ < 4; ++i_) cp_async16(&R.ks[st_][i_][tx], kseq + p_ + 2 * i_); \
+				cp_async8(&R.sym[st_][tx], wsym + p_); \
+				if (wmask) for (int i_ = 0; i_ < 8; ++i_) cp_async16(&R.m[st_][i_][tx], wmask + p_ + i_); \
+				if (8 * (int64_t)(b) + 8 < len) cp_async8(&R.lo_next[st_][tx], kseq + p_ + 8); } \
+				cp_async_commit(); } while (0)
+			for (int b = 0; b < FIX_STAGES - 1; ++b) FIX_ISSUE(b);
+			int64_t x = v - (kseq[base] & (int64_t)RB3B_M42); /* the exact value relative to the current row's low end */
+			for (int b = 0; b < nb && !ended; ++b) {
+				FIX_ISSUE(b + FIX_STAGES - 1);
+				cp_async_wait<FIX_STAGES - 1>();
+				const int st = b % FIX_STAGES;
+				const int64_t i0 = 8 * (int64_t)b;
+				int64_t ksv[9], out[8];
+#pragma unroll
+				for (int i = 0; i < 4; ++i) { const longlong2 q = R.ks[st][i][tx]; ksv[2 * i] = q.x; ksv[2 * i + 1] = q.y; }
+				ksv[8] = i0 + 8 < len ? R.lo_next[st][tx] : arr;
+				const uint64_t sym = R.sym[st][tx];
+#pragma unroll
+				for (int u = 0; u < 8; ++u) {
+					out[u] = ksv[u]; /* rows past the unresolved prefix keep what they hold */
+					if (!ended && i0 + u < d) {
+						const int c = (int)(sym >> (8 * u)) & 7;
+						const int64_t lo = ksv[u] & (int64_t)RB3B_M42, lo_n = ksv[u + 1] & (int64_t)RB3B_M42;
+						out[u] = lo + x;
+						if (c == 0) ended = true; /* the next position is a sentinel row, exact by itself */
+						else if (ksv[u] & KS_TIGHT) x = (int64_t)mask_rank(R.m[st][u][tx], (uint32_t)x);
+						else { x = A.acc[c] + BmRank::rank(A, lo + x, c) - lo_n; ++n_wide; }
+					}
+				}
+				if (i0 + 8 <= len) {
+					longlong2 *o2 = (longlong2*)(kseq + base + i0);
+					o2[0] = make_longlong2(out[0], out[1]); o2[1] = make_longlong2(out[2], out[3]);
+					o2[2] = make_longlong2(out[4], out[5]); o2[3] = make_longlong2(out[6], out[7]);
+				} else {
+#pragma unroll
+					for (int u = 0; u < 8; ++u) if (i0 + u < len) kseq[base + i0 + u] = out[u];
+				}
 			}
+			cp_async_wait<0>(); /* the ring is restarted for the next slice */
+#undef FIX_ISSUE
+			v = arr + x; /* meaningful only when the slice never collapsed */
 			const bool go_on = d == len && !ended && !was_exact && t + 1 < S.own_hi && S.d[t + 1] > 0; /* t + 1's only predecessor is t and t + 1 is on nobody's list */
 			S.d[t] = 0;
 			if (d == len && !ended) S.arr_lo[t] = S.arr_hi[t] = v;
@@ -552,12 +610,14 @@ __global__ void __launch_bounds__(128) k_fix_chain(DevIndex A, Slices S, const u
 		}
 	}
 	/* statistics */
-	for (int o = 16; o > 0; o >>= 1) { n_wide += __shfl_xor_sync(0xffffffffu, n_wide, o); }
-	unsigned long long tot = n_rows;
-	for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-	unsigned long long mx = n_rows;
-	for (int o = 16; o > 0; o >>= 1) { const unsigned long long y = __shfl_xor_sync(0xffffffffu, mx, o); mx = y > mx ? y : mx; }
-	if ((threadIdx.x & 31) == 0 && tot) { atomicAdd(stats, tot); atomicAdd(stats + 1, n_wide); atomicMax(stats + 2, mx); }
+	unsigned long long tot = n_rows, mx = n_rows;
+	for (int o = 16; o > 0; o >>= 1) {
+		n_wide += __shfl_xor_sync(0xffffffffu, n_wide, o);
+		tot += __shfl_xor_sync(0xffffffffu, tot, o);
+		const unsigned long long y = __shfl_xor_sync(0xffffffffu, mx, o);
+		mx = y > mx ? y : mx;
+	}
+	if ((tx & 31) == 0 && tot) { atomicAdd(stats, tot); atomicAdd(stats + 1, n_wide); atomicMax(stats + 2, mx); }
 }
 
 /* generic fix-up (RLE cells, or bitmap cells without the tables): re-walk the unresolved prefix of each listed slice
@@ -662,7 +722,7 @@ static int walk_order(int64_t len, const uint8_t *d_bwt, int64_t nt, const int64
 {
 	DBuf<LfT> lf;
 	DBuf<RowT> wrow;
-	TRY(lf.alloc(len)); TRY(wrow.alloc(len));
+	TRY(lf.alloc(len)); TRY(wrow.alloc(len + 8)); /* padded: read in whole groups of eight */
 	k_prep_lf<LfT><<<(unsigned)nt, TPB, 0, rb3b_stream>>>(len, d_bwt, nt, tex, acc, lf.p); CKK();
 	DBuf<FNode> nd; /* two buffers of list-ranking nodes (ping-pong) */
 	DBuf<int64_t> fc, ch; /* chain_of; chain_len, chain_base */
@@ -731,7 +791,7 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	/* few slices (one genome per batch): the walks are latency bound, shorter slices and pieces give more of them; many
 	 * slices: DRAM-access bound, longer slices leave fewer rows to the fix-up */
 	const bool big = len >= (32LL << 20);
-	int64_t seg_len = ((rb3b_seg_len > 0 ? rb3b_seg_len : big ? 512 : 384) + 7) / 8 * 8;
+	int64_t seg_len = ((rb3b_seg_len > 0 ? rb3b_seg_len : big ? 512 : A->kind == RB3B_KIND_BM ? 192 : 384) + 7) / 8 * 8;
 	Fine F;
 	F.n_seq = acc.v[1];
 	int64_t fine_len = rb3b_get_param("fine_len", 0);
@@ -754,7 +814,7 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	}
 	DBuf<uint8_t> wsym;
 	void *wrow = 0;
-	TRY(wsym.alloc(len + 16)); /* padded: the walks read whole 8-byte words */
+	TRY(wsym.alloc(len + 64)); /* padded: the walks read whole 8-byte words, the fix-up whole chunks */
 	const bool narrow_lf = len < LF32_MAX_LEN && !rb3b_get_param("wide_lf", 0);
 	/* walk-order positions this device reads (everything for a sorted collection: the heads are resolved on every device) */
 	/* rows walked before every slice to narrow its bracket (k_walk_pair) */
@@ -767,7 +827,7 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	else TRY((walk_order<uint64_t, int64_t>(len, d_bwt, nt, tex.p, acc, F, p_lo, p_hi, wsym, &wrow, &c_base, &c_len)));
 	const int64_t n_walk = S.own_hi - S.walk_lo;
 	DBuf<int64_t> seg, wl, ctr, kseq;
-	TRY(seg.alloc(S.n_seg * 3)); TRY(wl.alloc(S.n_seg * 4)); TRY(ctr.alloc(16)); TRY(kseq.alloc(len + 8));
+	TRY(seg.alloc(S.n_seg * 3)); TRY(wl.alloc(S.n_seg * 4)); TRY(ctr.alloc(16)); TRY(kseq.alloc(len + 64));
 	if (ka_out) ka.p = ka_out; else TRY(ka.alloc(len));
 	S.d = seg.p; S.arr_lo = seg.p + S.n_seg; S.arr_hi = seg.p + 2 * S.n_seg;
 	rb3b_toc(T_PREP);
@@ -785,9 +845,10 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	/* transfer masks of the unresolved rows (16 bytes per row of the batch): only for batches that can afford them */
 	DBuf<uint4> wmask;
 	const bool use_mask = pair && len <= rb3b_get_param("mask_max_rows", 1LL << 28);
-	if (use_mask) TRY(wmask.alloc(len));
+	if (use_mask) TRY(wmask.alloc(len + 64));
+	const bool use_log = bm && rb3b_get_param("fix_log", 1) != 0;
 	if (so) {
-		CK(cudaMemsetAsync(kseq.p, 0, (len + 8) * 8, rb3b_stream));
+		CK(cudaMemsetAsync(kseq.p, 0, (len + 64) * 8, rb3b_stream));
 		if (bm) k_so_heads<BmRank><<<nblk(F.n_seq, TPB), TPB, 0, rb3b_stream>>>(dA, so, F.n_seq, c_base, c_len, wsym.p, kseq.p);
 		else k_so_heads<Grp<8> ><<<nblk(F.n_seq * 8, TPB), TPB, 0, rb3b_stream>>>(dA, so, F.n_seq, c_base, c_len, wsym.p, kseq.p);
 		CKK();
@@ -806,14 +867,13 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	int64_t n_items = 0, rounds = 1, fix_items = 0;
 	CK(cudaMemcpyAsync(&n_items, ctr.p + 1, 8, cudaMemcpyDeviceToHost, rb3b_stream));
 	CK(cudaStreamSynchronize(rb3b_stream));
-	const bool use_log = bm && rb3b_get_param("fix_log", 1) != 0;
 	int cur = 0;
 	while (n_items > 0) {
 		/* ctr[2] = item cursor, ctr[3] = size of the next list, ctr[4..6] = statistics */
 		CK(cudaMemsetAsync(ctr.p + 2, 0, 40, rb3b_stream));
 		want = (n_items * wg + wtpb - 1) / wtpb;
 		rb3b_tic(T_WALKFIX);
-		if (use_log) k_fix_chain<<<nblk(n_items, 128), 128, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, use_mask ? wmask.p : 0, n_items, wl_seg[cur], wl_val[cur],
+		if (use_log) k_fix_chain<<<nblk(n_items, FIX_TPB), FIX_TPB, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, use_mask ? wmask.p : 0, n_items, wl_seg[cur], wl_val[cur],
 			(unsigned long long*)(ctr.p + 4));
 		else if (bm) k_walk_fix<BmRank><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, n_items, wl_seg[cur], wl_val[cur], ctr.p + 2,
 			wl_seg[cur ^ 1], wl_val[cur ^ 1], (unsigned long long*)(ctr.p + 3));
