@@ -134,6 +134,9 @@ def run_b200(a):
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     capi.check(capi.lib().rb3b_set_stream(stream.cuda_stream))
+    from ropebwt3_b200 import dist as rdist
+    if world > 1:
+        rdist.init_library_comm()   # the library's own NCCL communicator; torch.distributed only carries the id
     if a.seg_len:
         R.set_param("seg_len", a.seg_len)
     for kv in a.param:
@@ -183,8 +186,7 @@ def run_b200(a):
     idx.reserve(sum(lens))   # the CLI knows its input size too; see rb3b_index_reserve
     for i in range(1, 1 + a.warmup):
         if world > 1:
-            from ropebwt3_b200 import dist as rdist0
-            rdist0.merge_plain_sharded(rdist0.DeviceEngine(idx), d_bwt[i].data_ptr(), lens[i])
+            rdist.merge_plain_dist_dev(idx, d_bwt[i].data_ptr(), lens[i])
         else:
             idx.merge_plain_dev(d_bwt[i].data_ptr(), lens[i])
     barrier()
@@ -193,19 +195,18 @@ def run_b200(a):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.time()
     e0.record(stream)
-    from ropebwt3_b200 import dist as rdist
-    eng = rdist.DeviceEngine(idx)
     n_sharded = 0
     for i in range(1 + a.warmup, n_g):
         if world > 1:   # rank phase split over the ranks + one NCCL all-reduce (MAX) of the interleave array
-            n_sharded += int(rdist.merge_plain_sharded(eng, d_bwt[i].data_ptr(), lens[i]))
+            n_sharded += int(rdist.merge_plain_dist_dev(idx, d_bwt[i].data_ptr(), lens[i]))
         else:
             idx.merge_plain_dev(d_bwt[i].data_ptr(), lens[i])
+    R.sync()   # asynchronous merges run on the library's second stream: the timed region ends when they have
     e1.record(stream)
     barrier()
     wall_dev = time.time() - w0
     ms_dev = e0.elapsed_time(e1)
-    st = {k: R.get_stat(k) for k in ["us_prep", "us_walk_first", "us_walk_fix", "us_merge", "us_scatter", "kernel_launches", "n_segments", "fix_rounds", "fix_rounds_total", "n_cells", "n_ovf_cells", "cell_shift", "fix_rows", "fix_wide_rows", "fix_longest_chain"]}
+    st = {k: R.get_stat(k) for k in ["us_prep", "us_walk_first", "us_walk_fix", "us_merge", "us_scatter", "us_comm", "kernel_launches", "n_segments", "fix_rounds", "fix_rounds_total", "n_cells", "n_ovf_cells", "cell_shift", "fix_rows", "fix_wide_rows", "fix_longest_chain"]}
     acc_dev = idx.acc()
     index_bytes = idx.nbytes()
     timed_bases = sum(bases[1 + a.warmup:])
@@ -218,18 +219,15 @@ def run_b200(a):
         # the timed region, then the sharded merge; the result read back is the new C[] of the index
         idx2 = R.Index.from_plain(h_bwt[0].numpy())
         idx2.reserve(sum(lens))
-        eng2 = rdist.DeviceEngine(idx2)
-        stage = torch.empty(max(lens), dtype=torch.uint8, device="cuda")
         for i in range(1, 1 + a.warmup):
-            stage[:lens[i]].copy_(h_bwt[i], non_blocking=True)
-            rdist.merge_plain_sharded(eng2, stage.data_ptr(), lens[i])
+            rdist.merge_plain_dist(idx2, h_bwt[i].data_ptr(), lens[i])
         barrier()
         e0.record(stream)
         w0 = time.time()
         for i in range(1 + a.warmup, n_g):
-            stage[:lens[i]].copy_(h_bwt[i], non_blocking=True)
-            rdist.merge_plain_sharded(eng2, stage.data_ptr(), lens[i])
+            rdist.merge_plain_dist(idx2, h_bwt[i].data_ptr(), lens[i])   # H2D of this rank's share + NVLink all-gather + sharded merge
             acc_host = idx2.acc()
+        R.sync()   # asynchronous merges run on the library's second stream: the timed region ends when they have
         e1.record(stream)
         barrier()
         wall_e2e = time.time() - w0
@@ -251,6 +249,7 @@ def run_b200(a):
         for i in range(1 + a.warmup, n_g):
             capi.check(L.rb3b_merge_plain(idx2.h, lens[i], hp[i]))       # H2D of the batch + merge + sync
             L.rb3b_get_acc(idx2.h, acc_host.ctypes.data)                   # the step's result: new C[] of the index
+        R.sync()   # asynchronous merges run on the library's second stream: the timed region ends when they have
         e1.record(stream)
         barrier()
         wall_e2e = time.time() - w0

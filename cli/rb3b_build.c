@@ -14,9 +14,13 @@
  *
  * -2/-s/-r go through rb3b_insert_multi (mr_insert_multi, build.c:214-218).
  *
- * Like the reference's pipeline mode (build.c:55-83,186-201: kt_pipeline of read+SAIS and merge) the host work overlaps
- * the device work, here always and for any number of input files: a reader thread parses and encodes batch i+1 while
- * the main thread runs the partial BWT and the merge of batch i on the device (two batch buffers).
+ * Like the reference's pipeline mode (build.c:55-83,186-201: kt_pipeline of read+SAIS and merge) everything overlaps,
+ * here always and for any number of input files: a reader thread parses and encodes batch i+2, a second thread copies
+ * batch i+1 to the device and builds its partial BWT there (rb3_build_sais's place in the reference's step 0), and the
+ * main thread merges batch i (step 1).  The two device-side threads run in their own library contexts, i.e. on their own
+ * CUDA streams, so the suffix sort of one batch and the merge of the previous one share the GPU.
+ *
+ * `merge` (main.c:84-133): rb3_fmi_merge of further indexes into the first one, both sides on the device.
  *
  * Not covered (documented in DESIGN.md): -T (tree dump: there is no tree), -e (BRE).  -t and -p are accepted and
  * ignored (parallelism comes from the device); -l/-n only shape the .fmr dump.
@@ -268,9 +272,80 @@ static void *reader_main(void *arg)
 	return 0;
 }
 
+/* ---- second stage: batches resident on the device, partial BWT built (two device buffers) ---- */
+
+typedef struct {
+	void *d; int64_t cap, len, n_seq;
+	int file, last_of_file, open_failed;
+} dbatch_t;
+
+typedef struct {
+	pipe_t *in;
+	int use_rb2;        /* -2/-s/-r: the batch stays text, rb3b_insert_multi_dev sorts it itself */
+	dbatch_t slot[2];
+	int n_full, head, tail, done, failed;
+	pthread_mutex_t mu; pthread_cond_t cv;
+} dpipe_t;
+
+static void *bwt_main(void *arg)
+{ /* runs in its own library context (own stream): rb3_build_sais of batch i+1 overlaps the merge of batch i */
+	dpipe_t *q = (dpipe_t*)arg;
+	batch_t *b;
+	while ((b = pipe_next(q->in)) != 0) {
+		dbatch_t *o;
+		pthread_mutex_lock(&q->mu);
+		while (q->n_full == 2) pthread_cond_wait(&q->cv, &q->mu);
+		pthread_mutex_unlock(&q->mu);
+		o = &q->slot[q->tail];
+		o->len = (int64_t)b->seq.l; o->n_seq = b->n_seq; o->file = b->file; o->last_of_file = b->last_of_file; o->open_failed = b->open_failed;
+		if (!b->open_failed && b->n_seq > 0) {
+			LOG("read %ld symbols from file '%s'", (long)b->seq.l, q->in->argv[b->file]);
+			if (o->len > o->cap) {
+				rb3b_dev_free(o->d);
+				o->cap = o->len + (o->len >> 2);
+				o->d = rb3b_dev_alloc(o->cap);
+			}
+			if (o->d == 0 || rb3b_h2d(o->d, b->seq.s, o->len) < 0) { fprintf(stderr, "ERROR: host to device copy: %s\n", rb3b_last_error()); q->failed = 1; }
+			else if (!q->use_rb2) {
+				if (rb3b_build_bwt_dev(o->len, (const uint8_t*)o->d, (uint8_t*)o->d) < 0) { fprintf(stderr, "ERROR: partial BWT: %s\n", rb3b_last_error()); q->failed = 1; } /* rb3_build_sais, in place */
+				else LOG("constructed partial BWT for %ld symbols", (long)o->len);
+			}
+		}
+		pipe_release(q->in);
+		pthread_mutex_lock(&q->mu);
+		q->tail ^= 1; ++q->n_full;
+		pthread_cond_broadcast(&q->cv);
+		pthread_mutex_unlock(&q->mu);
+		if (q->failed) break;
+	}
+	pthread_mutex_lock(&q->mu);
+	q->done = 1;
+	pthread_cond_broadcast(&q->cv);
+	pthread_mutex_unlock(&q->mu);
+	return 0;
+}
+
+static dbatch_t *dpipe_next(dpipe_t *q)
+{
+	dbatch_t *b = 0;
+	pthread_mutex_lock(&q->mu);
+	while (q->n_full == 0 && !q->done) pthread_cond_wait(&q->cv, &q->mu);
+	if (q->n_full) b = &q->slot[q->head];
+	pthread_mutex_unlock(&q->mu);
+	return b;
+}
+
+static void dpipe_release(dpipe_t *q)
+{
+	pthread_mutex_lock(&q->mu);
+	q->head ^= 1; --q->n_full;
+	pthread_cond_broadcast(&q->cv);
+	pthread_mutex_unlock(&q->mu);
+}
+
 static int usage(FILE *fp)
 {
-	fprintf(fp, "Usage: ropebwt3-b200 build [options] <in.fa> [...]\n       ropebwt3-b200 ssa [-s INT] [-o FILE] <in.fmd>\n");
+	fprintf(fp, "Usage: ropebwt3-b200 build [options] <in.fa> [...]\n       ropebwt3-b200 merge [-o FILE] [-S FILE] <base.fmr> <other1.fmr> [...]\n       ropebwt3-b200 ssa [-s INT] [-o FILE] <in.fmd>\n");
 	fprintf(fp, "Options (those of `ropebwt3 build`):\n");
 	fprintf(fp, "  -m NUM   batch size [7G]             -i FILE  append to an existing .fmr/.fmd index\n");
 	fprintf(fp, "  -L       one sequence per line       -F/-R    skip forward / reverse strand\n");
@@ -295,8 +370,6 @@ int main(int argc, char *argv[])
 	const char *fn_in = 0, *fn_tmp = 0;
 
 	rb3b_index_t *idx = 0;
-	void *d_text = 0;
-	int64_t d_cap = 0;
 
 	t_real0 = realtime();
 	if (argc >= 2 && strcmp(argv[1], "version") == 0) { puts(rb3b_version()); return 0; }
@@ -348,6 +421,33 @@ int main(int argc, char *argv[])
 		rb3b_index_destroy(idx);
 		return 0;
 	}
+	if (argc >= 2 && strcmp(argv[1], "merge") == 0) { /* main_merge, main.c:84-133 */
+		rb3b_index_t *other;
+		--argc; ++argv;
+		while ((c = getopt(argc, argv, "t:o:S:")) >= 0) {
+			if (c == 'o') { if (freopen(optarg, "wb", stdout) == 0) { fprintf(stderr, "ERROR: failed to open '%s' for writing\n", optarg); return 1; } }
+			else if (c == 'S') fn_tmp = optarg;
+		}
+		if (argc - optind < 2) {
+			fprintf(stdout, "Usage: ropebwt3-b200 merge [options] <base.fmr> <other1.fmr> [...]\nOptions:\n  -t INT     accepted for compatibility\n");
+			fprintf(stdout, "  -o FILE    output FMR to FILE [stdout]\n  -S FILE    save the current index to FILE after each input file []\n");
+			return 1;
+		}
+		DIE_IF(rb3b_init(getenv("RB3B_DEVICE") ? atoi(getenv("RB3B_DEVICE")) : 0), "no usable CUDA device");
+		idx = rb3b_index_create();
+		if (rb3b_restore(idx, argv[optind]) < 0) { fprintf(stderr, "ERROR: failed to load FMR file '%s'\n", argv[optind]); return 1; }
+		for (i = optind + 1; i < argc; ++i) {
+			other = rb3b_index_create();
+			if (rb3b_restore(other, argv[i]) < 0) { fprintf(stderr, "ERROR: failed to load FMR/FMD file '%s'\n", argv[i]); rb3b_index_destroy(other); break; }
+			DIE_IF(rb3b_merge_index(idx, other), "merging"); /* rb3_fmi_merge(r, &fb, n_threads, 1) */
+			rb3b_index_destroy(other);
+			LOG("merged '%s'", argv[i]);
+			if (fn_tmp) { DIE_IF(rb3b_dump_fmr(idx, fn_tmp, max_nodes, block_len), "saving the index"); LOG("saved the current index to '%s'", fn_tmp); }
+		}
+		DIE_IF(rb3b_dump_fmr(idx, "-", max_nodes, block_len), "writing .fmr"); /* mr_dump(r, stdout) */
+		rb3b_index_destroy(idx);
+		return 0;
+	}
 	if (argc < 2 || strcmp(argv[1], "build") != 0) return usage(stderr);
 	--argc; ++argv;
 	while ((c = getopt(argc, argv, "l:n:m:t:2sri:LFRo:dbTS:p:e")) >= 0) {
@@ -394,8 +494,9 @@ int main(int argc, char *argv[])
 	}
 	{
 		pipe_t P;
-		pthread_t tid;
-		batch_t *b;
+		dpipe_t Q;
+		pthread_t tid, tid2;
+		dbatch_t *db;
 		int64_t acc[7], fit;
 		memset(&P, 0, sizeof(P));
 		P.argc = argc; P.argv = argv; P.first = optind; P.is_line = is_line; P.no_for = no_for; P.no_rev = no_rev;
@@ -410,47 +511,42 @@ int main(int argc, char *argv[])
 		P.batch = batch; P.hard = fit;
 		pthread_mutex_init(&P.mu, 0); pthread_cond_init(&P.cv, 0);
 		if (pthread_create(&tid, 0, reader_main, &P) != 0) { fprintf(stderr, "ERROR: failed to start the reader thread\n"); return 1; }
-		while ((b = pipe_next(&P)) != 0) {
-			const char *fn = argv[b->file];
-			if (b->open_failed) fprintf(stderr, "ERROR: failed to open file '%s'\n", fn);
-			else if (b->n_seq > 0) {
-				str_t seq = b->seq;
-				LOG("read %ld symbols from file '%s'", (long)seq.l, fn);
-				if ((int64_t)seq.l > d_cap) {
-					rb3b_dev_free(d_text);
-					d_cap = (int64_t)seq.l + (int64_t)(seq.l >> 2);
-					d_text = rb3b_dev_alloc(d_cap);
-					if (d_text == 0) { fprintf(stderr, "ERROR: %s\n", rb3b_last_error()); return 1; }
-				}
-				DIE_IF(rb3b_h2d(d_text, seq.s, (int64_t)seq.l), "host to device copy");
+		memset(&Q, 0, sizeof(Q));
+		Q.in = &P; Q.use_rb2 = use_rb2;
+		pthread_mutex_init(&Q.mu, 0); pthread_cond_init(&Q.cv, 0);
+		if (pthread_create(&tid2, 0, bwt_main, &Q) != 0) { fprintf(stderr, "ERROR: failed to start the BWT thread\n"); return 1; }
+		while ((db = dpipe_next(&Q)) != 0) {
+			const char *fn = argv[db->file];
+			if (Q.failed) return 1;
+			if (db->open_failed) fprintf(stderr, "ERROR: failed to open file '%s'\n", fn);
+			else if (db->n_seq > 0) {
 				if (use_rb2) { /* build.c:214-218; an index loaded with -i keeps its own order, like mr->so */
 					if (idx == 0) {
 						idx = rb3b_index_create();
 						DIE_IF(rb3b_index_set_order(idx, sort_order), "sorting order");
 					}
-					DIE_IF(rb3b_insert_multi_dev(idx, (int64_t)seq.l, (const uint8_t*)d_text), "inserting the batch");
-					LOG("inserted %ld symbols", (long)seq.l);
+					DIE_IF(rb3b_insert_multi_dev(idx, db->len, (const uint8_t*)db->d), "inserting the batch");
+					LOG("inserted %ld symbols", (long)db->len);
+				} else if (idx == 0) {
+					idx = rb3b_index_create();
+					DIE_IF(rb3b_index_from_plain_dev(idx, db->len, (const uint8_t*)db->d), "encoding the partial BWT");
+					LOG("encoded the partial BWT for %ld symbols", (long)db->len);
 				} else {
-					DIE_IF(rb3b_build_bwt_dev((int64_t)seq.l, (const uint8_t*)d_text, (uint8_t*)d_text), "partial BWT"); /* rb3_build_sais, in place */
-					LOG("constructed partial BWT for %ld symbols", (long)seq.l);
-					if (idx == 0) {
-						idx = rb3b_index_create();
-						DIE_IF(rb3b_index_from_plain_dev(idx, (int64_t)seq.l, (const uint8_t*)d_text), "encoding the partial BWT");
-						LOG("encoded the partial BWT for %ld symbols", (long)seq.l);
-					} else {
-						DIE_IF(rb3b_merge_plain_dev(idx, (int64_t)seq.l, (const uint8_t*)d_text), "merging the partial BWT");
-						LOG("merged the partial BWT for %ld symbols", (long)seq.l);
-					}
+					DIE_IF(rb3b_merge_plain_dev(idx, db->len, (const uint8_t*)db->d), "merging the partial BWT");
+					LOG("merged the partial BWT for %ld symbols", (long)db->len);
 				}
 				/* after the first batch: building the first index resets the buffers */
 				if (!reserved) { rb3b_index_reserve(idx, est_symbols); reserved = 1; }
 			}
-			if (!b->open_failed && b->last_of_file && fn_tmp && idx) { /* build.c:232-238 */
+			if (!db->open_failed && db->last_of_file && fn_tmp && idx) { /* build.c:232-238 */
 				DIE_IF(rb3b_dump_fmr(idx, fn_tmp, max_nodes, block_len), "saving the index");
 				LOG("saved the current index to '%s'", fn_tmp);
 			}
-			pipe_release(&P);
+			dpipe_release(&Q);
 		}
+		pthread_join(tid2, 0);
+		if (Q.failed) return 1;
+		rb3b_dev_free(Q.slot[0].d); rb3b_dev_free(Q.slot[1].d);
 		pthread_join(tid, 0);
 		free(P.slot[0].seq.s); free(P.slot[1].seq.s);
 	}
@@ -459,7 +555,6 @@ int main(int argc, char *argv[])
 	else if (fmt == 1) DIE_IF(rb3b_dump_fmd(idx, "-"), "writing .fmd");
 	else DIE_IF(rb3b_dump_plain(idx, "-"), "writing the BWT");
 	rb3b_index_destroy(idx);
-	rb3b_dev_free(d_text);
 	fprintf(stderr, "[M::main] Real time: %.3f sec; CPU: %.3f sec\n", realtime() - t_real0, cputime());
 	return 0;
 }

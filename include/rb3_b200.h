@@ -113,6 +113,14 @@ int rb3b_dist_rank(void);
 int rb3b_dist_world(void);
 int rb3b_dist_nccl_version(void);
 
+/* rb3_fmi_merge_plain (fm-index.c:279-303) across the ranks of the communicator: every rank holds a replica of the index
+ * and passes the same batch; the rank phase -- what the reference spreads over host threads with kt_for (fm-index.c:220) --
+ * is split over the devices, the interleave positions are exchanged over NVLink and every replica is merged.  Returns 0,
+ * 1 when the ranks had to fall back to the unsharded rank phase (still exact), < 0 on error. */
+int rb3b_merge_plain_dist_dev(rb3b_index_t *idx, int64_t len, const uint8_t *d_bwt);
+/* same with the batch in host memory visible to every rank: each rank copies 1/world of it over PCIe, NVLink does the rest */
+int rb3b_merge_plain_dist(rb3b_index_t *idx, int64_t len, const uint8_t *bwt);
+
 /* rb3_fmi_merge (fm-index.c:251-277) for `ropebwt3 merge`: B is another index. */
 int rb3b_merge_index(rb3b_index_t *idx, const rb3b_index_t *other);
 
@@ -127,6 +135,12 @@ int rb3b_lf_dev(const rb3b_index_t *idx, int64_t nq, const int64_t *d_k, const u
 /* rb3_fmi_get_acc (fm-index.c:544-550): acc[c] = #symbols < c; returns total length */
 int64_t rb3b_get_acc(const rb3b_index_t *idx, int64_t acc[RB3B_ASIZE + 1]);
 int64_t rb3b_index_bytes(const rb3b_index_t *idx);   /* device bytes held by the index */
+/* With rb3b_set_param("async_merge", 1), rb3b_merge_plain[_dev] into a bitmap index only QUEUES the streaming merge (on the
+ * context's second stream) and returns once the interleave positions are known: the next call overlaps with it until it
+ * needs the merged cells.  The index's host-side state (rb3b_get_acc ...) is already that of the merged index.
+ * rb3b_index_wait blocks until the merge has finished and reports what its kernels found (a batch that is not a BWT leaves
+ * the index unusable).  Every other entry point waits by itself.  Off by default (measured gain: 3 %). */
+int     rb3b_index_wait(rb3b_index_t *idx);
 
 /* ---- export ---------------------------------------------------------------- */
 /* canonical (coalesced) run list; call with sym==NULL to get the count. mr_itr_next_block loop (fm-index.c:41-51). */

@@ -50,6 +50,8 @@ SIGNATURES = {
     "rb3b_mg_rank_part": (_int, [_vp, _i64, _vp, _int, _int, _vp]),
     "rb3b_merge_with_ka": (_int, [_vp, _i64, _vp, _vp]),
     "rb3b_merge_index": (_int, [_vp, _vp]),
+    "rb3b_merge_plain_dist_dev": (_int, [_vp, _i64, _vp]),
+    "rb3b_merge_plain_dist": (_int, [_vp, _i64, _vp]),
     "rb3b_dist_unique_id": (_int, [_vp]),
     "rb3b_dist_init": (_int, [_int, _int, _vp]),
     "rb3b_dist_finalize": (_int, []),
@@ -61,6 +63,7 @@ SIGNATURES = {
     "rb3b_lf_dev": (_int, [_vp, _i64, _vp, _vp, _vp, _int]),
     "rb3b_get_acc": (_i64, [_vp, _vp]),
     "rb3b_index_bytes": (_i64, [_vp]),
+    "rb3b_index_wait": (_int, [_vp]),
     "rb3b_export_runs": (_i64, [_vp, _vp, _vp, _i64]),
     "rb3b_dump_fmd": (_int, [_vp, C.c_char_p]),
     "rb3b_dump_fmr": (_int, [_vp, C.c_char_p, _int, _int]),

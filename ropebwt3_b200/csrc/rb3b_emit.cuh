@@ -450,8 +450,10 @@ static __global__ void k_gather_tot(const int64_t *__restrict__ ex, int64_t stri
 	if (a == RB3B_ASIZE) out[a] = flag ? *flag : 0;
 }
 
+/* d_async_flag != 0: asynchronous merge -- nothing here waits for the device; the totals the kernels counted and *d_async_flag
+ * go to x->pend_host and are checked against x->pend_expect by rb3b_index_wait_i */
 template<class Src>
-static int rb3b_emit_build_bm(rb3b_index_s *x, Src src, int64_t n_src, int64_t lenB, const int64_t *d_ka, const uint8_t *d_bwt)
+static int rb3b_emit_build_bm(rb3b_index_s *x, Src src, int64_t n_src, int64_t lenB, const int64_t *d_ka, const uint8_t *d_bwt, const int *d_async_flag)
 {
 	const int64_t n_out = n_src + lenB;
 	DBuf<int64_t> ilo, ctot, cex;
@@ -475,9 +477,14 @@ static int rb3b_emit_build_bm(rb3b_index_s *x, Src src, int64_t n_src, int64_t l
 	int64_t tot[RB3B_ASIZE + 1], base[RB3B_ASIZE] = {0, 0, 0, 0, 0, 0};
 	DBuf<int64_t> gt;
 	TRY(gt.alloc(RB3B_ASIZE + 1));
-	k_gather_tot<<<1, 32, 0, rb3b_stream>>>(cex.p, O.n_chunks + 1, 0, gt.p); CKK();
-	CK(cudaMemcpyAsync(tot, gt.p, sizeof(tot), cudaMemcpyDeviceToHost, rb3b_stream));
-	CK(cudaStreamSynchronize(rb3b_stream));
+	k_gather_tot<<<1, 32, 0, rb3b_stream>>>(cex.p, O.n_chunks + 1, d_async_flag, gt.p); CKK();
+	if (d_async_flag) {
+		CK(cudaMemcpyAsync(x->pend_host, gt.p, sizeof(tot), cudaMemcpyDeviceToHost, rb3b_stream));
+		for (int a = 0; a < RB3B_ASIZE; ++a) tot[a] = x->pend_expect[a];
+	} else {
+		CK(cudaMemcpyAsync(tot, gt.p, sizeof(tot), cudaMemcpyDeviceToHost, rb3b_stream));
+		CK(cudaStreamSynchronize(rb3b_stream));
+	}
 	{ uint4 *t = x->cells; x->cells = x->cells2; x->cells2 = t; int64_t c = x->cap_cells; x->cap_cells = x->cap_cells2; x->cap_cells2 = c; }
 	x->kind = RB3B_KIND_BM; x->shift = RB3B_BM_SHIFT; x->n_cells = O.n_cells; x->n_ovf = 0; x->n_entries = 0;
 	x->acc[0] = 0;

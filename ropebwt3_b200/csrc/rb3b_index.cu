@@ -151,8 +151,36 @@ int rb3b_want_bitmap(int64_t n_symbols)
 	return n_symbols <= rb3b_get_param("bitmap_max_symbols", 24000000000LL);
 }
 
+/* host side of an asynchronous merge: wait for it and run the checks that were deferred (rb3b_merge.cu, merge_phase) */
+int rb3b_index_wait_i(rb3b_index_s *x)
+{
+	if (x->pending) {
+		CK(cudaEventSynchronize(x->ready_ev));
+		x->pending = 0;
+		if (x->pend_host[RB3B_ASIZE]) { x->broken = 1; return rb3b_fail(RB3B_EINVAL, "interleave positions are not monotone: the batch is not a valid BWT (the index is unusable now)"); }
+		for (int a = 0; a < RB3B_ASIZE; ++a)
+			if (x->pend_host[a] != x->pend_expect[a]) {
+				x->broken = 1;
+				return rb3b_fail(RB3B_EINVAL, "internal error: the merge wrote %lld symbols of code %d, expected %lld", (long long)x->pend_host[a], a, (long long)x->pend_expect[a]);
+			}
+	}
+	if (x->broken) return rb3b_fail(RB3B_EINVAL, "the index was left unusable by an earlier failed merge");
+	return RB3B_OK;
+}
+
+/* device side: whatever is launched on the current stream from now on runs after the in-flight merge of x */
+int rb3b_index_use(const rb3b_index_s *x)
+{
+	if (x->has_ev) CK(cudaStreamWaitEvent(rb3b_stream, x->ready_ev, 0));
+	return RB3B_OK;
+}
+
 int rb3b_index_free_dev(rb3b_index_s *x)
 {
+	if (x->pending) { cudaEventSynchronize(x->ready_ev); x->pending = 0; }
+	if (x->has_ev) { cudaStreamWaitEvent(rb3b_stream, x->ready_ev, 0); cudaEventDestroy(x->ready_ev); }
+	if (x->ms) cudaFreeAsync(x->ms, rb3b_stream);
+	if (x->pend_host) cudaFreeHost(x->pend_host);
 	if (x->cells) cudaFreeAsync(x->cells, rb3b_stream);
 	if (x->ovf) cudaFreeAsync(x->ovf, rb3b_stream);
 	if (x->cells2) cudaFreeAsync(x->cells2, rb3b_stream);
@@ -185,7 +213,7 @@ int rb3b_index_from_runs_dev(rb3b_index_s *x, int64_t n_runs, const uint8_t *d_s
 	if (n >= (1LL << 42)) return rb3b_fail(RB3B_EINVAL, "index longer than 2^42 symbols is not supported by the 42-bit cell headers");
 	RunSrc src;
 	src.sym = d_sym; src.start = start.p; src.n_runs = n_runs; src.n = n; src.r = 0; src.rem64 = 0; src.cur = -1;
-	if (rb3b_want_bitmap(n)) return rb3b_emit_build_bm(x, src, n, 0, 0, 0);
+	if (rb3b_want_bitmap(n)) return rb3b_emit_build_bm(x, src, n, 0, 0, 0, 0);
 	return rb3b_emit_build(x, src, n, 0, 0, 0, n_runs);
 }
 
@@ -237,6 +265,7 @@ static int export_with(Reader R, const rb3b_index_s *x, DBuf<uint8_t> &sym, DBuf
 int rb3b_export_runs_dev(const rb3b_index_s *x, DBuf<uint8_t> &sym, DBuf<int64_t> &len, int64_t *n_runs)
 {
 	*n_runs = 0;
+	TRY(rb3b_index_wait_i((rb3b_index_s*)x)); TRY(rb3b_index_use(x));
 	if (x->n_cells == 0) return RB3B_OK;
 	if (x->kind == RB3B_KIND_BM) {
 		BmReader R;
@@ -378,6 +407,7 @@ extern "C" int rb3b_index_get_order(const rb3b_index_t *x) { return x->so; }
 extern "C" int rb3b_index_reserve(rb3b_index_t *x, int64_t n_symbols)
 { /* like vector::reserve: size both ping-pong halves for an index of n_symbols so that merges never reallocate */
 	TRY(rb3b_ensure_init());
+	TRY(rb3b_index_wait_i(x)); TRY(rb3b_index_use(x));
 	if (!rb3b_want_bitmap(n_symbols)) return RB3B_OK; /* RLE cells: size depends on the data; grown on demand */
 	int64_t quads = ((n_symbols + 127) >> RB3B_BM_SHIFT) * 8;
 	if (x->cap_cells2 < quads) {
@@ -452,6 +482,7 @@ extern "C" int rb3b_rank1a_dev(const rb3b_index_t *x, int64_t nq, const int64_t 
 	ApiScope scope_;
 	TRY(rb3b_ensure_init());
 	if (nq <= 0) return RB3B_OK;
+	TRY(rb3b_index_wait_i((rb3b_index_s*)x)); TRY(rb3b_index_use(x));
 	int64_t want = (nq * RB3B_GROUP + TPB - 1) / TPB, cap = (int64_t)n_sm() * 8 * 4;
 	if (x->n_cells == 0) { /* empty index: every count is zero (mrope.c:89-93 with zero totals) */
 		CK(cudaMemsetAsync(d_ok, 0, nq * RB3B_ASIZE * 8, rb3b_stream));
@@ -489,6 +520,7 @@ extern "C" int rb3b_lf_dev(const rb3b_index_t *x, int64_t nq, const int64_t *d_k
 	ApiScope scope_;
 	TRY(rb3b_ensure_init());
 	if (nq <= 0) return RB3B_OK;
+	TRY(rb3b_index_wait_i((rb3b_index_s*)x)); TRY(rb3b_index_use(x));
 	if (x->n_cells == 0) return rb3b_fail(RB3B_EINVAL, "empty index");
 	if (x->kind == RB3B_KIND_BM) { /* bitmap cells have a single kernel: two 16-B loads and a popcount per query */
 		int64_t want = (nq + TPB - 1) / TPB, cap = (int64_t)n_sm() * 8 * 4;
@@ -515,6 +547,13 @@ extern "C" int64_t rb3b_get_acc(const rb3b_index_t *x, int64_t acc[RB3B_ASIZE + 
 }
 
 extern "C" int64_t rb3b_index_bytes(const rb3b_index_t *x) { return (int64_t)x->bytes; }
+
+/* block until an asynchronous merge into idx has finished (its batch buffer may then be reused) and report its deferred checks */
+extern "C" int rb3b_index_wait(rb3b_index_t *x)
+{
+	TRY(rb3b_ensure_init());
+	return rb3b_index_wait_i(x);
+}
 
 extern "C" int64_t rb3b_export_runs(const rb3b_index_t *x, uint8_t *sym, int64_t *len, int64_t cap)
 {

@@ -65,6 +65,18 @@ struct rb3b_index_s {
 	uint4 *cells2, *ovf2;         /* the other half of the ping-pong pair: the next merge writes here */
 	int64_t cap_cells, cap_ovf, cap_cells2, cap_ovf2; /* capacities in quads */
 	size_t bytes;
+	/* asynchronous merge (bitmap -> bitmap): the merge kernels run on the context's second stream while the caller goes on
+	 * (typically into the next batch's LF table and walk-order rewrite, which do not need the index).  The host-side fields
+	 * above already describe the merged index (its totals are known beforehand: old totals + batch totals). */
+	cudaEvent_t ready_ev;         /* recorded behind the last kernel that writes the current cells */
+	int has_ev;
+	int pending;                  /* a merge is in flight; its deferred checks are in pend_host once ready_ev has fired */
+	int broken;                   /* a deferred check failed: the cells are not the index the host fields describe */
+	int64_t *pend_host;           /* pinned: [0..5] symbol totals the merge kernels counted, [6] "positions not monotone" flag */
+	int64_t pend_expect[RB3B_ASIZE];
+	int ms_flip;                  /* which of the two batch copies the NEXT merge uses (the merge in flight reads the other) */
+	int64_t ms_rows;              /* the scratch is laid out for batches of up to this many rows (grow-only, so that the regions of consecutive merges coincide) */
+	char *ms; size_t ms_cap, ms_used; /* scratch that must outlive the call: interleave positions and batch copy (ms_used bytes), then the merge's tables */
 };
 
 /* by-value kernel argument */
@@ -106,6 +118,9 @@ struct rb3b_ctx_s {
 	int ev_ok, ev_pending[T_COUNT];
 	void *comm;                       /* ncclComm_t when this context is a rank of a multi-device group (rb3b_dist.cu) */
 	int rank, world;
+	cudaStream_t stream2;             /* asynchronous merges run here */
+	cudaEvent_t ev_hand;              /* hand-over between the two streams */
+	char *bump; size_t bump_off, bump_cap; /* when set, scratch comes from this region (an index's merge scratch) instead of the arena */
 };
 rb3b_ctx_s *rb3b_cur(void);
 #define rb3b_stream   (rb3b_cur()->stream)
@@ -153,6 +168,8 @@ private:
 int rb3b_reserve(void **p, int64_t *cap, int64_t need, size_t elt);
 int rb3b_scan_excl_i64(const int64_t *d_in, int64_t *d_out, int64_t n);              /* exclusive prefix sum */
 int rb3b_index_free_dev(rb3b_index_s *x);
+int rb3b_index_wait_i(rb3b_index_s *x);          /* host: wait for the in-flight merge of x and run its deferred checks */
+int rb3b_index_use(const rb3b_index_s *x);       /* device: kernels launched on the current stream from now on see the merged cells */
 int rb3b_index_from_runs_dev(rb3b_index_s *x, int64_t n_runs, const uint8_t *d_sym, const int64_t *d_len);
 int rb3b_export_runs_dev(const rb3b_index_s *x, DBuf<uint8_t> &sym, DBuf<int64_t> &len, int64_t *n_runs);
 int rb3b_index_to_plain_dev(const rb3b_index_s *x, DBuf<uint8_t> &plain);   /* rb3b_bwt.cu */

@@ -35,9 +35,12 @@ static int ctx_setup(rb3b_ctx_s *c, int device)
 	c->chunk_i = c->chunk_off = c->used = c->high = 0; c->depth = 0;
 	c->n_launch = 0; c->ev_ok = 0;
 	c->comm = 0; c->rank = 0; c->world = 1;
+	c->stream2 = 0; c->ev_hand = 0; c->bump = 0; c->bump_off = c->bump_cap = 0;
 	memset(c->ev_pending, 0, sizeof(c->ev_pending));
 	CK(cudaSetDevice(device));
 	CK(cudaStreamCreateWithFlags(&c->my_stream, cudaStreamNonBlocking));
+	CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+	CK(cudaEventCreateWithFlags(&c->ev_hand, cudaEventDisableTiming));
 	c->stream = c->my_stream;
 	{
 		std::lock_guard<std::mutex> lk(g_mu);
@@ -57,6 +60,8 @@ static void ctx_teardown(rb3b_ctx_s *c)
 	if (c->my_stream) {
 		cudaSetDevice(c->device);
 		cudaStreamSynchronize(c->stream);
+		if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); c->stream2 = 0; }
+		if (c->ev_hand) { cudaEventDestroy(c->ev_hand); c->ev_hand = 0; }
 		for (size_t i = 0; i < c->chunks.size(); ++i) cudaFree(c->chunks[i].p);
 		c->chunks.clear();
 		if (c->ev_ok) for (int i = 0; i < T_COUNT; ++i) { cudaEventDestroy(c->ev[i][0]); cudaEventDestroy(c->ev[i][1]); }
@@ -121,6 +126,12 @@ void *rb3b_arena_alloc(size_t bytes)
 {
 	rb3b_ctx_s *c = rb3b_cur();
 	bytes = (bytes + 511) & ~(size_t)511;
+	if (c->bump) { /* scratch of an asynchronous merge: a fixed region that outlives the call */
+		if (c->bump_off + bytes > c->bump_cap) return 0;
+		void *p = c->bump + c->bump_off;
+		c->bump_off += bytes;
+		return p;
+	}
 	for (;;) {
 		if (c->chunk_i < c->chunks.size() && c->chunk_off + bytes <= c->chunks[c->chunk_i].cap) {
 			void *p = c->chunks[c->chunk_i].p + c->chunk_off;
@@ -185,6 +196,7 @@ void rb3b_tic(int id)
 		c->ev_ok = 1;
 	}
 	if (c->ev_pending[id]) rb3b_tflush();
+	if (c->ev_pending[id]) { cudaEventSynchronize(c->ev[id][1]); rb3b_tflush(); }
 	cudaEventRecord(c->ev[id][0], c->stream);
 }
 
@@ -196,6 +208,7 @@ void rb3b_tflush(void)
 	for (int i = 0; i < T_COUNT; ++i)
 		if (c->ev_ok && c->ev_pending[i]) {
 			float ms = 0;
+			if (i == T_MERGE && cudaEventQuery(c->ev[i][1]) == cudaErrorNotReady) continue; /* an asynchronous merge still running: next time */
 			cudaEventSynchronize(c->ev[i][1]);
 			if (cudaEventElapsedTime(&ms, c->ev[i][0], c->ev[i][1]) == cudaSuccess) rb3b_stat_add(g_ev_name[i], (int64_t)(ms * 1000.0f + 0.5f));
 			c->ev_pending[i] = 0;
@@ -251,6 +264,8 @@ extern "C" int rb3b_sync(void)
 {
 	TRY(rb3b_ensure_init());
 	CK(cudaStreamSynchronize(rb3b_stream));
+	CK(cudaStreamSynchronize(rb3b_cur()->stream2)); /* asynchronous merges */
+	rb3b_tflush();
 	return RB3B_OK;
 }
 

@@ -1,11 +1,45 @@
 """Multi-GPU merge (first step): one process per GPU, the index replicated on every device, the rows of the
-batch split among the ranks for the rank phase, one NCCL all-reduce (MAX) of the 8-byte-per-row interleave array, then
-the same streaming merge on every rank.  torch.distributed is plumbing only; the compute is in librb3b200.so.
+batch split among the ranks for the rank phase, the interleave positions combined over NVLink, then the same streaming
+merge on every rank.
 
-The engine is passed in so that the collective logic can be tested on CPU with gloo and a stand-in engine.
+The product path is inside the C ABI: `init_library_comm()` makes this process's librb3b200 context a rank of an NCCL
+communicator owned by the library (torch.distributed only carries the 128-byte NCCL id to the other ranks), after which
+`rb3b_merge_plain_dist[_dev]` does the sharded rank phase, the NCCL exchange and the merge in one call.
+
+`merge_plain_sharded()` below is the same orchestration written against an engine object, so that the collective logic
+(partial arrays, MAX-combine, the fallback flag) can be tested on CPU with gloo and a stand-in engine.
 """
 import torch
 import torch.distributed as dist
+
+
+def init_library_comm(group=None):
+    """rb3b_dist_init for this process: rank 0 draws the NCCL unique id, every rank joins.  Call after rb3b_init(device)."""
+    import ctypes as C
+    from . import capi
+    L = capi.lib()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        capi.check(L.rb3b_dist_unique_id(buf))
+    box = [buf.raw]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0, group=group)
+    capi.check(L.rb3b_dist_init(rank, world, C.create_string_buffer(box[0], 128)))
+    return rank, world
+
+
+def merge_plain_dist_dev(index, d_bwt, n):
+    """rb3_fmi_merge_plain across the library's communicator, batch in device memory -> True when sharded (no fallback)."""
+    from . import capi
+    return capi.check(capi.lib().rb3b_merge_plain_dist_dev(index.h, n, int(d_bwt))) == 0
+
+
+def merge_plain_dist(index, h_bwt_ptr, n):
+    """same, batch in (pinned) host memory: every rank copies 1/world of it, NVLink all-gathers the rest"""
+    from . import capi
+    return capi.check(capi.lib().rb3b_merge_plain_dist(index.h, n, int(h_bwt_ptr))) == 0
 
 
 class DeviceEngine:

@@ -164,3 +164,23 @@ def test_ssa_subcommand(files):
     out = str(d / "x.ssa")
     run(CLI, ["ssa", "-o", out, fmd])
     assert open(out, "rb").read() == run(files["ref"], ["ssa", fmd]).stdout
+
+
+def test_merge_subcommand(files):
+    """`ropebwt3 merge` (main.c:84-133): base.fmr + other indexes (.fmd and .fmr) -> FMR on stdout / -o, -S checkpoint after
+    every input; the merged collection must be the reference's, compared through the canonical .fmd."""
+    from oracle import ref
+    d = files["dir"]
+    a, b, c = str(d / "ma.fmr"), str(d / "mb.fmd"), str(d / "mc.fmr")
+    open(a, "wb").write(run(ref.BIN, ["build", "-b", files["fa"][0], files["fa"][1]]).stdout)
+    open(b, "wb").write(run(ref.BIN, ["build", "-d", files["fa"][2]]).stdout)
+    open(c, "wb").write(run(ref.BIN, ["build", "-b", files["fa"][3], files["fa"][4]]).stdout)
+    want_fmr = str(d / "want.fmr")
+    open(want_fmr, "wb").write(run(ref.BIN, ["merge", a, b, c]).stdout)
+    want = run(ref.BIN, ["build", "-i", want_fmr, "-d"]).stdout
+    mine, ckpt = str(d / "mine.fmr"), str(d / "ckpt.fmr")
+    run(CLI, ["merge", "-t", "4", "-o", mine, "-S", ckpt, a, b, c])
+    assert run(ref.BIN, ["build", "-i", mine, "-d"]).stdout == want      # the reference reads our merged FMR
+    assert run(CLI, ["build", "-i", ckpt, "-d"]).stdout == want          # the checkpoint after the last input is the result
+    assert run(CLI, ["merge", a], check=False).returncode == 1           # usage: needs two indexes
+    assert run(CLI, ["merge", str(d / "nope.fmr"), b], check=False).returncode == 1

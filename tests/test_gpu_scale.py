@@ -78,7 +78,7 @@ def test_a_one_genome_per_merge_5mb(rb3, genomes6, ref_one_per_merge, kind, tmp_
             assert np.array_equal(acc, R["acc"][i - 1])
             bad = np.flatnonzero(rb != R["rb"][i - 1])
             assert len(bad) == 0, "merge %d: %d of %d rb[] entries differ, first at row %d" % (i, len(bad), len(rb), bad[0])
-            assert rb3.get_stat("seg_len_used") == 384 and rb3.get_stat("fix_segments") > 1000   # default knobs, real fix-up
+            assert rb3.get_stat("seg_len_used") == (192 if kind == "bitmap" else 384) and rb3.get_stat("fix_segments") > 1000   # default knobs, real fix-up
             idx.merge_plain(bwt)
         assert rb3.get_stat("index_kind") == (1 if kind == "bitmap" else 0)
         fn = str(tmp_path / "a.fmd")
