@@ -149,10 +149,10 @@ __device__ __forceinline__ int32_t fnode_term(const FNode &n) { return (int32_t)
 
 /* walk every piece once (LF_B only, no rank): its length and the piece that follows it */
 template<typename LfT>
-__global__ void k_fine_walk(Fine F, const LfT *__restrict__ lf, FNode *__restrict__ node, int32_t *__restrict__ piece_len)
+__global__ void k_fine_walk(Fine F, const LfT *__restrict__ lf, FNode *__restrict__ node, int32_t *__restrict__ piece_len, int64_t f_lo, int64_t f_hi)
 {
-	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (f >= F.n_fine) return;
+	int64_t f = f_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (f >= f_hi) return;
 	int64_t kb = F.row(f), n = 0, nx = -1;
 	for (;;) {
 		const uint64_t x = __ldg(lf + kb);
@@ -163,6 +163,13 @@ __global__ void k_fine_walk(Fine F, const LfT *__restrict__ lf, FNode *__restric
 	}
 	node[f] = fnode(n, (int32_t)nx, (int32_t)f);
 	piece_len[f] = (int32_t)n;
+}
+
+/* multi-device: the pieces were walked by their owners and the nodes exchanged; every device needs all piece lengths */
+__global__ void k_piece_len(int64_t n, const FNode *__restrict__ node, int32_t *__restrict__ piece_len)
+{
+	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (f < n) piece_len[f] = (int32_t)node[f].x;
 }
 
 /* Wyllie pointer jumping: after ceil(log2 n) rounds x = #rows from fine mark f to the start of its sequence.  One 16-byte
@@ -672,6 +679,57 @@ __global__ void k_scatter_ka(int64_t n, const RowT *__restrict__ rows, const int
 	if (bad && (threadIdx.x & 31) == 0) atomicAdd(n_unres, (unsigned long long)bad);
 }
 
+/* rows still flagged unresolved (multi-device exchange: nothing else looks at every value before it leaves) */
+__global__ void k_count_flagged(int64_t n, const int64_t *__restrict__ vals, unsigned long long *n_unres)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned int bad = i < n && (vals[i] & KS_UNRES) ? 1u : 0u;
+	bad = __popc(__ballot_sync(0xffffffffu, bad));
+	if (bad && (threadIdx.x & 31) == 0) atomicAdd(n_unres, (unsigned long long)bad);
+}
+
+/* ---- exchange between devices: (row, position) pairs are routed to the device that owns the row's range ---- */
+#define MAX_RANKS 64
+
+__global__ void __launch_bounds__(TPB) k_dest_count(int64_t n, const uint32_t *__restrict__ rows, int64_t chunk, int n_ranks, unsigned long long *__restrict__ cnt)
+{
+	__shared__ unsigned int sh[MAX_RANKS];
+	if (threadIdx.x < MAX_RANKS) sh[threadIdx.x] = 0;
+	__syncthreads();
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) atomicAdd(&sh[rows[i] / (uint32_t)chunk], 1u);
+	__syncthreads();
+	if (threadIdx.x < n_ranks && sh[threadIdx.x]) atomicAdd(&cnt[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+/* base[d] = where destination d's pairs start in the packed arrays; cursor[d] = pairs of d placed so far */
+__global__ void __launch_bounds__(TPB) k_dest_pack(int64_t n, const uint32_t *__restrict__ rows, const int64_t *__restrict__ vals, int64_t chunk, int n_ranks,
+                                                   const int64_t *__restrict__ base, unsigned long long *__restrict__ cursor,
+                                                   uint32_t *__restrict__ prow, int64_t *__restrict__ pval)
+{
+	__shared__ unsigned int sh[MAX_RANKS];
+	__shared__ unsigned long long at[MAX_RANKS];
+	if (threadIdx.x < MAX_RANKS) sh[threadIdx.x] = 0;
+	__syncthreads();
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t r = 0, d = 0, li = 0;
+	if (i < n) { r = rows[i]; d = r / (uint32_t)chunk; li = atomicAdd(&sh[d], 1u); }
+	__syncthreads();
+	if (threadIdx.x < n_ranks && sh[threadIdx.x]) at[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+	__syncthreads();
+	if (i < n) {
+		const int64_t o = base[d] + (int64_t)at[d] + li;
+		prow[o] = r; pval[o] = vals[i];
+	}
+}
+
+/* the pairs this device received: into its dense range of the interleave array */
+__global__ void k_fill_dense(int64_t n, const uint32_t *__restrict__ rows, const int64_t *__restrict__ vals, int64_t row0, int64_t *__restrict__ dense)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) dense[(int64_t)rows[i] - row0] = vals[i];
+}
+
 /* A scatter of 8-byte values over a target much larger than L2 costs a DRAM read-modify-write of a sector per value.
  * For large batches the (row, value) pairs are therefore first partitioned by the high bits of the row (one or two
  * radix passes, streaming), so that the scatter proper works on windows of 2^19 rows (4 MB) that stay in L2. */
@@ -716,9 +774,14 @@ __global__ void k_check_monotone(int64_t len, const int64_t *__restrict__ ka, in
 
 
 /* everything of the rank phase that depends on the width of the batch's LF table */
+int rb3b_all_gather(const void *send, void *recv, size_t bytes_per_rank); /* rb3b_dist.cu */
+
+/* part / n_parts > 1: the ranks of the communicator share the first walk of the pieces (each walks a contiguous range of
+ * fine marks, the 16-byte nodes are all-gathered over NVLink); LF table and list ranking are replicated */
 template<typename LfT, typename RowT>
 static int walk_order(int64_t len, const uint8_t *d_bwt, int64_t nt, const int64_t *tex, const Acc7 &acc, Fine &F,
-                      int64_t p_lo, int64_t p_hi, DBuf<uint8_t> &wsym, void **wrow_out, const int64_t **chain_base_out, const int64_t **chain_len_out, const void **lf_out = 0)
+                      int64_t p_lo, int64_t p_hi, DBuf<uint8_t> &wsym, void **wrow_out, const int64_t **chain_base_out, const int64_t **chain_len_out, const void **lf_out = 0,
+                      int part = 0, int n_parts = 1)
 {
 	DBuf<LfT> lf;
 	DBuf<RowT> wrow;
@@ -728,10 +791,17 @@ static int walk_order(int64_t len, const uint8_t *d_bwt, int64_t nt, const int64
 	DBuf<int64_t> fc, ch; /* chain_of; chain_len, chain_base */
 	DBuf<int32_t> pl;
 	if (F.n_fine >= (1LL << 31)) return rb3b_fail(RB3B_EINVAL, "batch too large: %lld fine marks", (long long)F.n_fine);
-	TRY(nd.alloc(F.n_fine * 2)); TRY(fc.alloc(F.n_fine)); TRY(ch.alloc(F.n_seq * 2)); TRY(pl.alloc(F.n_fine));
-	FNode *pp[2] = { nd.p, nd.p + F.n_fine };
+	const bool share = n_parts > 1 && rb3b_cur()->world == n_parts && rb3b_cur()->comm != 0 && rb3b_get_param("share_fine_walk", 1) != 0;
+	const int64_t f_chunk = share ? (F.n_fine + n_parts - 1) / n_parts : F.n_fine, f_pad = share ? f_chunk * n_parts : F.n_fine;
+	TRY(nd.alloc(f_pad * 2)); TRY(fc.alloc(F.n_fine)); TRY(ch.alloc(F.n_seq * 2)); TRY(pl.alloc(F.n_fine));
+	FNode *pp[2] = { nd.p, nd.p + f_pad };
 	int64_t *f_cof = fc.p, *c_len = ch.p, *c_base = ch.p + F.n_seq;
-	k_fine_walk<LfT><<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, lf.p, pp[0], pl.p); CKK();
+	if (share) {
+		const int64_t f_lo = f_chunk * part, f_hi = f_lo + f_chunk < F.n_fine ? f_lo + f_chunk : F.n_fine;
+		if (f_hi > f_lo) { k_fine_walk<LfT><<<nblk(f_hi - f_lo, TPB), TPB, 0, rb3b_stream>>>(F, lf.p, pp[0], pl.p, f_lo, f_hi); CKK(); }
+		TRY(rb3b_all_gather(pp[0] + f_lo, pp[0], (size_t)f_chunk * sizeof(FNode)));
+		k_piece_len<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F.n_fine, pp[0], pl.p); CKK();
+	} else { k_fine_walk<LfT><<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, lf.p, pp[0], pl.p, 0, F.n_fine); CKK(); }
 	int cur = 0;
 	for (int64_t span = 1; span < F.n_fine; span <<= 1) {
 		k_list_rank<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F.n_fine, pp[cur], pp[cur ^ 1]); CKK();
@@ -759,8 +829,12 @@ static int walk_order(int64_t len, const uint8_t *d_bwt, int64_t nt, const int64
  * speculatively so that its first slice receives an exact value without any exchange.  ka_out != NULL: write there
  * instead of allocating (rows of other parts are set to -1).  *incomplete is set when a part could not resolve all of
  * its own rows locally (only possible with n_parts > 1). */
+/* what a device resolved itself, still in walk order: (row, position) pairs for the exchange between devices */
+struct OwnPairs { const uint32_t *rows; const int64_t *vals; int64_t n; };
+
+/* pairs != 0 (32-bit rows only): nothing is scattered, ka stays untouched, the device's own rows are handed back */
 static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, DBuf<int64_t> &ka, int64_t accB[RB3B_ASIZE + 1],
-                      int part = 0, int n_parts = 1, int64_t *ka_out = 0, int *incomplete = 0, int so = 0)
+                      int part = 0, int n_parts = 1, int64_t *ka_out = 0, int *incomplete = 0, int so = 0, OwnPairs *pairs = 0)
 {
 	int64_t nt = (len + PREP_TILE - 1) / PREP_TILE;
 	DBuf<int64_t> tcnt, tex;
@@ -791,7 +865,8 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	/* few slices (one genome per batch): the walks are latency bound, shorter slices and pieces give more of them; many
 	 * slices: DRAM-access bound, longer slices leave fewer rows to the fix-up */
 	const bool big = len >= (32LL << 20);
-	int64_t seg_len = ((rb3b_seg_len > 0 ? rb3b_seg_len : big ? 512 : A->kind == RB3B_KIND_BM ? 192 : 384) + 7) / 8 * 8;
+	/* the slice length follows the rows THIS device walks */
+	int64_t seg_len = ((rb3b_seg_len > 0 ? rb3b_seg_len : len / n_parts >= (32LL << 20) ? 512 : A->kind == RB3B_KIND_BM ? 192 : 384) + 7) / 8 * 8;
 	Fine F;
 	F.n_seq = acc.v[1];
 	int64_t fine_len = rb3b_get_param("fine_len", 0);
@@ -823,12 +898,14 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	if (warm > seg_len) warm = (int)seg_len;
 	const int64_t p_lo = so ? -1 : S.walk_lo * seg_len - warm - 1, p_hi = so ? len : S.own_hi * seg_len;
 	const int64_t *c_base = 0, *c_len = 0;
-	if (narrow_lf) TRY((walk_order<uint32_t, uint32_t>(len, d_bwt, nt, tex.p, acc, F, p_lo, p_hi, wsym, &wrow, &c_base, &c_len)));
-	else TRY((walk_order<uint64_t, int64_t>(len, d_bwt, nt, tex.p, acc, F, p_lo, p_hi, wsym, &wrow, &c_base, &c_len)));
+	if (narrow_lf) TRY((walk_order<uint32_t, uint32_t>(len, d_bwt, nt, tex.p, acc, F, p_lo, p_hi, wsym, &wrow, &c_base, &c_len, 0, part, n_parts)));
+	else TRY((walk_order<uint64_t, int64_t>(len, d_bwt, nt, tex.p, acc, F, p_lo, p_hi, wsym, &wrow, &c_base, &c_len, 0, part, n_parts)));
 	const int64_t n_walk = S.own_hi - S.walk_lo;
 	DBuf<int64_t> seg, wl, ctr, kseq;
 	TRY(seg.alloc(S.n_seg * 3)); TRY(wl.alloc(S.n_seg * 4)); TRY(ctr.alloc(16)); TRY(kseq.alloc(len + 64));
-	if (ka_out) ka.p = ka_out; else TRY(ka.alloc(len));
+	if (pairs && !narrow_lf) return rb3b_fail(RB3B_EINVAL, "internal error: pair output needs 32-bit rows");
+	if (pairs) ka.p = 0;
+	else if (ka_out) ka.p = ka_out; else TRY(ka.alloc(len));
 	S.d = seg.p; S.arr_lo = seg.p + S.n_seg; S.arr_hi = seg.p + 2 * S.n_seg;
 	rb3b_toc(T_PREP);
 	/* everything up to here needed the batch only: it may have run while the previous merge into A was still writing the
@@ -836,7 +913,7 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	if (A->broken) return rb3b_fail(RB3B_EINVAL, "the index was left unusable by an earlier failed merge");
 	TRY(rb3b_index_use(A));
 	CK(cudaMemsetAsync(ctr.p, 0, 16 * 8, rb3b_stream));
-	if (n_parts > 1) CK(cudaMemsetAsync(ka.p, 0xff, len * 8, rb3b_stream));
+	if (n_parts > 1 && !pairs) CK(cudaMemsetAsync(ka.p, 0xff, len * 8, rb3b_stream));
 	DevIndex dA = rb3b_dev_view(A);
 	const bool bm = A->kind == RB3B_KIND_BM;
 	/* bitmap walks are lane pairs (single threads in the fix-up): small CTAs spread the walks over all SMs */
@@ -900,7 +977,10 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	CK(cudaMemsetAsync(ctr.p + 8, 0, 8, rb3b_stream));
 	rb3b_tic(T_SCATTER);
 	const int64_t own_p0 = S.own_lo * seg_len;
-	if (narrow_lf) TRY(scatter_to_rows<uint32_t>(own_rows, len, (const uint32_t*)wrow + own_p0, kseq.p + own_p0, ka.p, (unsigned long long*)(ctr.p + 8)));
+	if (pairs) {
+		pairs->rows = (const uint32_t*)wrow + own_p0; pairs->vals = kseq.p + own_p0; pairs->n = own_rows;
+		k_count_flagged<<<nblk(own_rows > 0 ? own_rows : 1, TPB), TPB, 0, rb3b_stream>>>(own_rows, pairs->vals, (unsigned long long*)(ctr.p + 8)); CKK();
+	} else if (narrow_lf) TRY(scatter_to_rows<uint32_t>(own_rows, len, (const uint32_t*)wrow + own_p0, kseq.p + own_p0, ka.p, (unsigned long long*)(ctr.p + 8)));
 	else TRY(scatter_to_rows<int64_t>(own_rows, len, (const int64_t*)wrow + own_p0, kseq.p + own_p0, ka.p, (unsigned long long*)(ctr.p + 8)));
 	rb3b_toc(T_SCATTER);
 	CK(cudaMemcpyAsync(&unres, ctr.p + 8, 8, cudaMemcpyDeviceToHost, rb3b_stream));
@@ -1177,6 +1257,7 @@ static int async_buffers(rb3b_index_s *x, int64_t len, const uint8_t *d_bwt, int
 /* collectives of rb3b_dist.cu (NCCL on the current context's stream) */
 int rb3b_all_gather(const void *send, void *recv, size_t bytes_per_rank);
 int rb3b_all_reduce_max_i64(void *buf, size_t n);
+int rb3b_all_to_all_v(const void *send, const int64_t *soff, const int64_t *scnt, void *recv, const int64_t *roff, const int64_t *rcnt);
 
 /* rb3_fmi_merge_plain on the ranks of the current communicator (rb3b_dist_init): every rank holds a replica of the index
  * and calls this with the same batch; rank r resolves the slices [r, r+1) * n_slices / world of walk order (plus a
@@ -1196,20 +1277,56 @@ extern "C" int rb3b_merge_plain_dist_dev(rb3b_index_t *x, int64_t len, const uin
 	int64_t accB[RB3B_ASIZE + 1], hflag = 0, *aka;
 	uint8_t *bcopy;
 	int incomplete = 0, fell_back = 0;
+	const int W = ctx->world;
+	/* the exchange: every device owns a range of `chunk` rows of the interleave array; (row, position) pairs go to the
+	 * owner of the row (one all-to-all, 12 bytes per row), the dense ranges are all-gathered (8 bytes per row).  Batches
+	 * with 64-bit rows, or more ranks than MAX_RANKS, use the all-reduce(MAX) of partial arrays instead. */
+	const bool by_pairs = len < LF32_MAX_LEN && !rb3b_get_param("wide_lf", 0) && W <= MAX_RANKS && rb3b_get_param("dist_pairs", 0) != 0; /* off by default: measured slower than the NVLS all-reduce (N=4: 1.40 vs 0.91 + 0.40 ms scatter) */
+	const int64_t chunk = ((len + W - 1) / W + 63) / 64 * 64;
 	TRY(async_buffers(x, len, d_bwt, &aka, &bcopy));
-	if (aka) { ka.p = aka; d_bwt = bcopy; } else TRY(ka.alloc(len));
-	TRY(flag.alloc(1));
-	TRY(rank_phase(x, len, d_bwt, ka, accB, ctx->rank, ctx->world, ka.p, &incomplete));
+	if (aka && (!by_pairs || chunk * W <= x->ms_rows)) { ka.p = aka; d_bwt = bcopy; } else { aka = 0; TRY(ka.alloc(by_pairs ? chunk * W : len)); }
+	TRY(flag.alloc(2 + 2 * MAX_RANKS + (size_t)W * W));
+	OwnPairs own;
+	int64_t *const ka_full = ka.p;
+	TRY(rank_phase(x, len, d_bwt, ka, accB, ctx->rank, ctx->world, ka.p, &incomplete, 0, by_pairs ? &own : 0));
+	ka.p = ka_full; /* with pair output the rank phase leaves the array alone */
 	hflag = incomplete;
 	rb3b_tic(T_COMM);
+	unsigned long long *d_cnt = (unsigned long long*)(flag.p + 2), *d_cur = d_cnt + MAX_RANKS;
+	int64_t *d_all = flag.p + 2 + 2 * MAX_RANKS;
 	CK(cudaMemcpyAsync(flag.p, &hflag, 8, cudaMemcpyHostToDevice, rb3b_stream));
+	if (by_pairs) {
+		CK(cudaMemsetAsync(d_cnt, 0, 2 * MAX_RANKS * 8, rb3b_stream));
+		if (own.n > 0) { k_dest_count<<<nblk(own.n, TPB), TPB, 0, rb3b_stream>>>(own.n, own.rows, chunk, W, d_cnt); CKK(); }
+		TRY(rb3b_all_gather(d_cnt, d_all, (size_t)W * 8)); /* row r of d_all: how many pairs rank r has for every destination */
+	}
 	TRY(rb3b_all_reduce_max_i64(flag.p, 1));
+	std::vector<int64_t> hall((size_t)W * W + 1, 0);
 	CK(cudaMemcpyAsync(&hflag, flag.p, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+	if (by_pairs) CK(cudaMemcpyAsync(hall.data(), d_all, (size_t)W * W * 8, cudaMemcpyDeviceToHost, rb3b_stream));
 	CK(cudaStreamSynchronize(rb3b_stream));
 	if (hflag) { /* rare: every rank computes everything */
 		DBuf<int64_t> ka2;
 		TRY(rank_phase(x, len, d_bwt, ka2, accB, 0, 1, ka.p));
 		fell_back = 1;
+	} else if (by_pairs) {
+		int64_t soff[MAX_RANKS], scnt[MAX_RANKS], roff[MAX_RANKS], rcnt[MAX_RANKS], n_recv = 0, n_send = 0, b4[MAX_RANKS], c4[MAX_RANKS], b8[MAX_RANKS], c8[MAX_RANKS];
+		for (int p = 0; p < W; ++p) { scnt[p] = hall[(size_t)ctx->rank * W + p]; soff[p] = n_send; n_send += scnt[p]; rcnt[p] = hall[(size_t)p * W + ctx->rank]; roff[p] = n_recv; n_recv += rcnt[p]; }
+		DBuf<int64_t> d_base, pval, rval;
+		DBuf<uint32_t> prow, rrow;
+		TRY(d_base.alloc(MAX_RANKS)); TRY(pval.alloc(n_send)); TRY(prow.alloc(n_send)); TRY(rval.alloc(n_recv)); TRY(rrow.alloc(n_recv));
+		CK(cudaMemcpyAsync(d_base.p, soff, (size_t)W * 8, cudaMemcpyHostToDevice, rb3b_stream));
+		if (own.n > 0) { k_dest_pack<<<nblk(own.n, TPB), TPB, 0, rb3b_stream>>>(own.n, own.rows, own.vals, chunk, W, d_base.p, d_cur, prow.p, pval.p); CKK(); }
+		for (int p = 0; p < W; ++p) { b4[p] = soff[p] * 4; c4[p] = scnt[p] * 4; b8[p] = soff[p] * 8; c8[p] = scnt[p] * 8; }
+		int64_t rb4[MAX_RANKS], rc4[MAX_RANKS], rb8[MAX_RANKS], rc8[MAX_RANKS];
+		for (int p = 0; p < W; ++p) { rb4[p] = roff[p] * 4; rc4[p] = rcnt[p] * 4; rb8[p] = roff[p] * 8; rc8[p] = rcnt[p] * 8; }
+		TRY(rb3b_all_to_all_v(prow.p, b4, c4, rrow.p, rb4, rc4));
+		TRY(rb3b_all_to_all_v(pval.p, b8, c8, rval.p, rb8, rc8));
+		const int64_t row0 = chunk * ctx->rank, mine = len - row0 < chunk ? (len - row0 > 0 ? len - row0 : 0) : chunk;
+		if (n_recv != mine) return rb3b_fail(RB3B_EINVAL, "internal error: device %d received %lld pairs for a range of %lld rows", ctx->rank, (long long)n_recv, (long long)mine);
+		if (n_recv > 0) { k_fill_dense<<<nblk(n_recv, TPB), TPB, 0, rb3b_stream>>>(n_recv, rrow.p, rval.p, row0, ka.p + row0); CKK(); }
+		TRY(rb3b_all_gather(ka.p + row0, ka.p, (size_t)chunk * 8));
+		CK(cudaStreamSynchronize(rb3b_stream)); /* the packed buffers are scratch of this call */
 	} else TRY(rb3b_all_reduce_max_i64(ka.p, (size_t)len)); /* rows another rank resolved are -1 here */
 	rb3b_toc(T_COMM);
 	if (aka) TRY(merge_phase(x, len, bcopy, aka, accB));
