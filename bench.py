@@ -44,12 +44,25 @@ def parse():
     ap.add_argument("--seg-len", type=int, default=0)
     ap.add_argument("--genomes-per-merge", type=int, default=0,
                     help="genomes per batch (one batch = one partial BWT = one merge); default: the number of GPUs, i.e. weak scaling")
-    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: CPU seconds all steps together may take")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0, help="--impl reference: CPU seconds all steps together may take (the number of timed steps shrinks to fit, never the genomes)")
+    ap.add_argument("--config", default="c1", choices=["c1", "c2s"],
+                    help="c1: BASELINE configs[1] (default).  c2s: configs[2] scaled to one box's memory budget: --c2s-genomes x 5 Mb in batches of 100 genomes (10^9 symbols per merge)")
+    ap.add_argument("--c2s-genomes", type=int, default=1000)
     ap.add_argument("--param", action="append", default=[], help="engine tuning knob key=value (rb3b_set_param), repeatable")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-rank-bench", action="store_true")
     return ap.parse_args()
+
+
+def apply_config(a):
+    if a.config == "c2s":
+        if a.genomes_per_merge <= 0:
+            a.genomes_per_merge = 100
+        n_batches = max(3, a.c2s_genomes // a.genomes_per_merge)
+        a.warmup = 1
+        a.steps = n_batches - 2
+    return a
 
 
 def gpm_of(a):
@@ -63,7 +76,9 @@ def config_of(a, extra=None):
     c = {"workload": "configs[1]: merge-build of synthetic %.1f Mb bacterial genomes (0.5%% subst + 0.05%% indel from a random earlier genome), %d genome(s) = one batch = one merge of %d symbols (both strands); %d genomes in total" % (
         a.genome_len / 1e6, g, g * (2 * a.genome_len + 2), g * (1 + a.warmup + a.steps)),
         "genome_len": a.genome_len, "genomes": g * (1 + a.warmup + a.steps), "genomes_per_merge": g, "seed": SEED,
-        "l2": "no explicit flush needed: every step touches a new 10 MB batch, ~260 MB of per-batch LF / walk-order / interleave arrays and an index of 40 MB to 1 GB (1 B/symbol), all far above the 126 MB L2"}
+        "l2": "no explicit flush: every step works on a NEW batch (%d MB) and ~26 bytes per batch symbol of freshly written LF / walk-order / interleave arrays (%d MB per step, above the 126 MB L2), so nothing a step reads was left in L2 by the step before except index cells; the index itself (1 byte per symbol) grows from %d MB to %d MB during the timed steps, i.e. the walk's random cell reads are partly L2 hits while it is below ~126 MB -- the ncu capture in roofline.traffic says how many bytes really came from DRAM" % (
+            g * (2 * a.genome_len + 2) // 1000000, 26 * g * (2 * a.genome_len + 2) // 1000000,
+            g * (1 + a.warmup) * (2 * a.genome_len + 2) // 1000000, g * (1 + a.warmup + a.steps) * (2 * a.genome_len + 2) // 1000000)}
     if extra:
         c.update(extra)
     return c
@@ -148,7 +163,7 @@ def run_b200(a):
     gs = make_genomes(a)
     G = gpm_of(a)
     n_g = len(gs) // G          # batches
-    d_bwt, h_bwt, lens = [], [], []
+    d_bwt, h_bwt, lens, bwt_ms = [], [], [], []
     t_bwt = 0.0
     for b in range(n_g):
         text = synth.batch_text(gs[b * G:(b + 1) * G])
@@ -159,6 +174,7 @@ def run_b200(a):
         capi.check(capi.lib().rb3b_build_bwt_dev(len(text), d_text.data_ptr(), out.data_ptr()))
         R.sync()
         t_bwt += time.time() - t1
+        bwt_ms.append((time.time() - t1) * 1e3)
         d_bwt.append(out)
         hb = torch.empty(len(text), dtype=torch.uint8).pin_memory()
         hb.copy_(out)
@@ -274,6 +290,10 @@ def run_b200(a):
             e2e_val = timed_bases / (ms_e2e / 1e3)
 
     value = timed_bases / (ms_dev / 1e3)
+    # the same steps with the partial BWT of every batch (device suffix sort, timed on its own above) added: what the metric's
+    # name promises -- text in, merged index out
+    ms_build = ms_dev + sum(bwt_ms[1 + a.warmup:])
+    build_value = timed_bases / (ms_build / 1e3)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -281,12 +301,17 @@ def run_b200(a):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     walk_s = st["us_walk_first"] / 1e6
-    achieved = WALK_ROW_BYTES * timed_syms / walk_s / 1e9 if walk_s > 0 else 0.0
+    # per-launch figures are THIS rank's: at N > 1 a rank walks 1/N of the batch's rows (plus its halo)
+    rank_syms = timed_syms / world
+    achieved = WALK_ROW_BYTES * rank_syms / walk_s / 1e9 if walk_s > 0 else 0.0
     phase_s = (st["us_prep"] + st["us_walk_first"] + st["us_walk_fix"] + st["us_scatter"]) / 1e6
-    phase_gbs = LF_STEP_BYTES * timed_syms / phase_s / 1e9 if phase_s > 0 else 0.0
-    traffic = None
+    phase_gbs = LF_STEP_BYTES * rank_syms / phase_s / 1e9 if phase_s > 0 else 0.0
+    traffic, traffic_note = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "walk_first_traffic.json"))).get("dram_bytes_per_launch")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "walk_first_traffic.json")))
+        if world == 1 and G == 1 and a.genome_len == GENOME_LEN:   # the capture is of this workload; anything else has no measured traffic
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_note = "STATIC: from the committed ncu --set full capture %s (%s), not measured in this run" % (tj.get("source"), tj.get("what"))
     except Exception:
         pass
     line = {
@@ -298,10 +323,12 @@ def run_b200(a):
                                       "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": int(st["kernel_launches"]),
         "clocks": clocks,
-        "roofline": {"kernel": "k_walk_first<BmPair> (sliced LF walk over the index: per row one symbol streamed in, one rank lookup per lane in the bitmap cells, one 8-byte position streamed out)",
+        "build_value": {"value": build_value, "unit": UNIT, "ms_per_step": ms_build / a.steps,
+                        "what": "value with the device suffix sort of every timed batch (rb3b_build_bwt_dev, timed separately with a host sync) added to the merge time: text in, merged index out"},
+        "roofline": {"kernel": "k_walk_pair (sliced LF walk over the index, two lanes per walk: per row one symbol streamed in, one rank lookup per lane in the bitmap cells, one 8-byte position streamed out, a 16-byte transfer mask for rows still under a bracket)",
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                     "traffic": traffic, "bytes_per_unit": WALK_ROW_BYTES, "units_per_launch": timed_syms / a.steps,
+                     "traffic": traffic, "traffic_note": traffic_note, "bytes_per_unit": WALK_ROW_BYTES, "units_per_launch": rank_syms / a.steps,
                      "avg_launch_ms": walk_s * 1e3 / a.steps,
                      "rank_phase": {"bytes_per_unit": LF_STEP_BYTES, "achieved": phase_gbs, "frac": phase_gbs / peak, "ms_per_step": phase_s * 1e3 / a.steps,
                                     "what": "SURVEY 8d's 160 B per LF-walk step over ALL kernels of the rank phase (LF table, list ranking, walk-order rewrite, walk, fix-up, scatter)"},
@@ -373,31 +400,45 @@ def ref_index_of(gs, n_threads):
 
 
 def cpu_baseline(a, gs, idx_state_genomes, budget_s):
-    """The reference's rb3_fmi_merge_plain (oracle/_ref/librb3ref.so) on the host cores, on a bounded sample."""
+    """The reference's rb3_fmi_merge_plain (oracle/_ref/librb3ref.so) on the host cores, on a bounded sample of the SAME
+    workload: whole genomes, same batching, as many merges as fit the budget.  The .fmd of what it built is compared with
+    the .fmd our engine builds from the same genomes (`parity_checked`)."""
     from oracle import ref
     from ropebwt3_b200 import synth
+    import ropebwt3_b200 as R
     cores = os.cpu_count() or 1
     if not ref.available():
         return port_baseline(a, gs, budget_s)
     G = gpm_of(a)
-    n0 = min(idx_state_genomes * G, 4)
-    rope = ref_index_of(gs[:n0], cores)
-    frag = min(a.genome_len, 1_000_000)
-    done_bases, t_used, n_merge = 0, 0.0, 0
-    for b in range(n0, len(gs) - G + 1, G):
-        pieces = [g[:frag] for g in gs[b:b + G]]
-        bwt = ref.build_sais(synth.batch_text(pieces), 2 * G, cores)
+    rope = ref_index_of(gs[:G], cores)
+    done_bases, t_used, n_merge, last = 0, 0.0, 0, G
+    for b in range(G, len(gs) - G + 1, G):
+        bwt = ref.build_sais(synth.batch_text(gs[b:b + G]), 2 * G, cores)
         t0 = time.time()
         rope.merge_plain(bwt, cores)
         t_used += time.time() - t0
-        done_bases += sum(len(x) for x in pieces)
+        done_bases += sum(len(x) for x in gs[b:b + G])
         n_merge += 1
+        last = b + G
         if t_used > budget_s:
             break
-    rope.close()
+    want = rope.to_fmd()   # consumes the rope
+    # our engine on the same genomes, same batching
+    idx = None
+    for b in range(0, last, G):
+        bwt = R.rb3_build_sais(synth.batch_text(gs[b:b + G]))
+        if idx is None:
+            idx = R.Index.from_plain(bwt)
+        else:
+            idx.merge_plain(bwt)
+    s_, l_ = idx.export_runs()
+    same = R.fmd_image(s_, l_) == want
+    idx.close()
     return {"value": done_bases / t_used, "unit": UNIT, "cores": cores, "kind": "reference",
-            "sample": "%d merges (rb3_fmi_merge_plain, n_threads=%d) of %d genome prefix(es) of %.1f Mb each (both strands) into the reference's index of the first %d genomes; %.1f s of CPU wall time; only %d chains per merge exist, so the reference's rank phase cannot use more than %d threads here" % (
-                n_merge, cores, G, frag / 1e6, n0, t_used, 2 * G, 2 * G)}
+            "parity_checked": {"fmd_identical": bool(same), "genomes": last, "fmd_bytes": len(want),
+                               "what": "the .fmd of the index the reference built in this sample vs the .fmd of our engine's index of the same genomes, byte for byte"},
+            "sample": "%d merges (rb3_fmi_merge_plain, n_threads=%d) of %d whole genome(s) each (%.1f Mb, both strands) into the reference's index of the first %d genome(s); %.1f s of CPU wall time; only %d chains per merge exist, so the reference's rank phase cannot use more than %d threads here" % (
+                n_merge, cores, G, a.genome_len / 1e6, G, t_used, 2 * G, 2 * G)}
 
 
 def port_baseline(a, gs, budget_s):
@@ -414,6 +455,9 @@ def port_baseline(a, gs, budget_s):
 
 
 def run_reference(a):
+    """The reference arm: the unmodified reference's rb3_fmi_merge_plain (oracle/_ref) on the host cores, on the b200 arm's
+    workload -- the same seeded genomes, the same batching, whole genomes, no genome inserted twice.  If the requested steps
+    do not fit the time budget the number of TIMED steps shrinks (reported in `steps`), never the genomes."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
@@ -421,52 +465,47 @@ def run_reference(a):
     from ropebwt3_b200 import synth
     cores = os.cpu_count() or 1
     G = gpm_of(a)
-    # the bounded sample never needs more than a few dozen genomes; the generator is seeded, so these are the first
-    # genomes of the b200 arm's set
-    gs = synth.genomes(min(G * (1 + a.warmup + a.steps), 4 + 8 * G), a.genome_len, seed=SEED, sub=0.005, indel=0.0005)
     if not ref.available():
+        gs = synth.genomes(2, a.genome_len, seed=SEED, sub=0.005, indel=0.0005)
         b = port_baseline(a, gs, 20.0)
         line = {"impl": "reference", "metric": METRIC, "value": b["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64", "data": "synthetic",
                 "config": config_of(a), "cpu_baseline": b, "e2e": {"value": b["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
-    n0 = min(1 + a.warmup, 4)
-    rope = ref_index_of(gs[:n0], cores)
-    rest = gs[n0:] if len(gs) > n0 else gs[-1:]
-    # size the per-step sample so that the whole run stays within ~150 s of merge time
-    probe = rest[0][:100_000]
-    bwt = ref.build_sais(synth.batch_text([probe]), 2, cores)
-    t0 = time.time()
-    rope.merge_plain(bwt, cores)
-    rate = len(probe) / (time.time() - t0)
-    frag = int(max(20_000, min(a.genome_len, rate * a.ref_budget_s / (a.steps + a.warmup) / G)))
-    times, nb = [], 0
+    gen = synth.genome_stream(a.genome_len, seed=SEED, sub=0.005, indel=0.0005)   # the b200 arm's genomes, produced as needed
+    take = lambda k: [next(gen) for _ in range(k)]
+    rope = ref_index_of(take(G), cores)
+    times, nb, t_all = [], 0, 0.0
     for i in range(a.warmup + a.steps):
-        pieces = [rest[(i * G + j + 1) % len(rest)][:frag] for j in range(G)]
-        piece = np.concatenate(pieces)
+        pieces = take(G)
         bwt = ref.build_sais(synth.batch_text(pieces), 2 * G, cores)
         t0 = time.time()
         rope.merge_plain(bwt, cores)
         dt = time.time() - t0
+        t_all += dt
         if i >= a.warmup:
             times.append(dt)
-            nb += len(piece)
+            nb += sum(len(x) for x in pieces)
+        # stop early when the remaining steps would not fit the budget (at least 3 timed steps)
+        if len(times) >= 3 and t_all + dt > a.ref_budget_s:
+            break
     rope.close()
     tot = sum(times)
     val = nb / tot
-    sample = "each step = rb3_fmi_merge_plain(n_threads=%d) of %.2f Mb prefixes of the next %d genome(s) (both strands, %d symbols) into the reference's own index (first %d genomes + earlier steps); sized from a 100 kb probe so that %d steps take ~%d s" % (
-        cores, frag / 1e6, G, G * (2 * frag + 2), n0, a.steps + a.warmup, int(a.ref_budget_s))
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+    sample = "each step = rb3_fmi_merge_plain(n_threads=%d) of the next %d whole genome(s) of the b200 arm's set (%.1f Mb each, both strands, %d symbols) into the reference's own index (first %d genome(s) + earlier steps); %d warm-up + %d timed steps%s" % (
+        cores, G, a.genome_len / 1e6, G * (2 * a.genome_len + 2), G, a.warmup, len(times),
+        "" if len(times) == a.steps else " (of the %d requested: the rest did not fit --ref-budget-s %d)" % (a.steps, int(a.ref_budget_s)))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": len(times), "warmup": a.warmup,
             "ms_per_step": tot * 1e3 / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8/int64", "data": "synthetic", "config": config_of(a, {"sample_bases_per_step": frag * G}),
+            "dtype": "u8/int64", "data": "synthetic", "config": config_of(a),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 if __name__ == "__main__":
-    args = parse()
+    args = apply_config(parse())
     # stdout carries the one JSON line and nothing else: libraries that print to fd 1 (the NCCL banner) go to stderr
     sys.stdout.flush()
     _real_stdout = os.fdopen(os.dup(1), "w")

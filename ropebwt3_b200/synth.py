@@ -28,6 +28,18 @@ def genomes(n_genomes, length, seed=43, sub=0.005, indel=0.0005):
     return out
 
 
+def genome_stream(length, seed=43, sub=0.005, indel=0.0005):
+    """The same sequence of genomes as genomes(), one at a time (every earlier genome is kept: later ones derive from them)."""
+    rng = np.random.default_rng(seed)
+    out = [rng.integers(1, 5, length).astype(np.uint8)]
+    yield out[0]
+    i = 1
+    while True:
+        out.append(mutate(rng, out[int(rng.integers(0, i))], sub, indel))
+        yield out[-1]
+        i += 1
+
+
 def batch_text(gs, both=True):
     """Concatenate genomes as the reference reader does (io.c:84-102): forward strand,
     0, reverse complement, 0."""
