@@ -10,8 +10,8 @@
  * all suffixes by their first 21 symbols packed 3 bits each (cut after a
  * sentinel; the stable sort orders equal sentinel-terminated prefixes by
  * position, which is exactly the sentinel order); every later round doubles
- * the compared length by sorting the still ambiguous suffixes' (rank[i],
- * rank[i+h]) pairs.
+ * the compared length by sorting the still ambiguous suffixes, group by
+ * group, by rank[i+h] (a segmented sort over a compact list of them).
  *
  * Also here: rb3b_merge_index, the BWT-vs-BWT flavour (rb3_fmi_merge,
  * fm-index.c:251-277), which expands the other index and reuses merge_plain.
@@ -98,6 +98,71 @@ static int scan_max_u32(uint32_t *d, uint32_t n)
 	return RB3B_OK;
 }
 
+/* ---- refinement rounds on the still ambiguous suffixes only ----
+ * After round 0 the sorted order is final except inside groups of suffixes with equal 21-symbol prefixes.  The ambiguous
+ * suffixes are kept as a compact list in sorted order: suf[t] (the suffix), grp[t] (its group = the sorted position of the
+ * group's first member = its current rank).  A round sorts every group by rank[suf + h] (one segmented sort: the groups
+ * are the segments), gives every sub-group its new rank, writes the now final stretch of the suffix array back and keeps
+ * only the members of sub-groups that are still larger than one. */
+
+__global__ void k_amb_flags(uint32_t n, const uint32_t *__restrict__ head, uint8_t *__restrict__ flag)
+{
+	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	flag[j] = head[j] != j || (j + 1 < n && head[j + 1] == head[j]);
+}
+
+/* second key of every listed suffix, and the segment starts (first list index of every group) */
+__global__ void k_list_keys(uint32_t m, uint32_t n, uint32_t h, const uint32_t *__restrict__ suf, const uint32_t *__restrict__ grp, const uint32_t *__restrict__ rank,
+                            uint32_t *__restrict__ key, uint8_t *__restrict__ segflag)
+{
+	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= m) return;
+	const uint64_t q = (uint64_t)suf[t] + h;
+	key[t] = q < n ? rank[q] : 0;
+	segflag[t] = t == 0 || grp[t] != grp[t - 1];
+}
+
+/* after the segmented sort: sub-group heads.  pos[t] = grp[t] + (t - first list index of the group) is the sorted position
+ * of list element t; sub[t] = pos of the first element of its sub-group (max-scan of the heads' positions) */
+__global__ void k_sub_heads(uint32_t m, const uint32_t *__restrict__ grp, const uint32_t *__restrict__ key, const uint32_t *__restrict__ segfirst, uint32_t *__restrict__ sub)
+{
+	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= m) return;
+	const bool headp = t == 0 || grp[t] != grp[t - 1] || key[t] != key[t - 1];
+	sub[t] = headp ? grp[t] + (t - segfirst[t]) : 0;
+}
+
+__global__ void k_seg_first(uint32_t m, const uint32_t *__restrict__ grp, uint32_t *__restrict__ segfirst)
+{
+	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= m) return;
+	segfirst[t] = (t == 0 || grp[t] != grp[t - 1]) ? t : 0;
+}
+
+/* write back: the suffix array stretch, the new ranks, and who stays on the list */
+__global__ void k_list_apply(uint32_t m, const uint32_t *__restrict__ suf, const uint32_t *__restrict__ grp, const uint32_t *__restrict__ segfirst, const uint32_t *__restrict__ sub,
+                             uint32_t *__restrict__ sa, uint32_t *__restrict__ rank, uint8_t *__restrict__ keep)
+{
+	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= m) return;
+	const uint32_t pos = grp[t] + (t - segfirst[t]), s = sub[t], i = suf[t];
+	sa[pos] = i;
+	if (s != grp[t]) rank[i] = s; /* the first sub-group keeps the group's rank */
+	const bool next_same = t + 1 < m && grp[t + 1] == grp[t] && sub[t + 1] == s;
+	keep[t] = s != pos || next_same;
+}
+
+template<typename T> static int select_flagged(const T *in, const uint8_t *flag, T *out, uint32_t n, unsigned long long *d_count)
+{
+	size_t tmp = 0;
+	CK(cub::DeviceSelect::Flagged((void*)0, tmp, in, flag, out, d_count, (int64_t)n, rb3b_stream));
+	DBuf<uint8_t> t;
+	TRY(t.alloc(tmp));
+	CK(cub::DeviceSelect::Flagged((void*)t.p, tmp, in, flag, out, d_count, (int64_t)n, rb3b_stream));
+	return RB3B_OK;
+}
+
 /* suffix array of the batch (generalised, sentinel order by position) into sa[len] (device, uint32) */
 static int suffix_sort(int64_t len, const uint8_t *d_text, DBuf<uint32_t> &sa, int n_sym = RB3B_ASIZE)
 {
@@ -111,25 +176,84 @@ static int suffix_sort(int64_t len, const uint8_t *d_text, DBuf<uint32_t> &sa, i
 	DBuf<uint32_t> idx0, rank, head;
 	DBuf<int> bad;
 	DBuf<unsigned long long> amb;
-	TRY(key0.alloc(n)); TRY(key1.alloc(n)); TRY(idx0.alloc(n)); TRY(sa.alloc(n)); TRY(rank.alloc(n)); TRY(head.alloc(n)); TRY(bad.alloc(1)); TRY(amb.alloc(1));
+	DBuf<uint8_t> flag;
+	TRY(key0.alloc(n)); TRY(key1.alloc(n)); TRY(idx0.alloc(n)); TRY(sa.alloc(n)); TRY(rank.alloc(n)); TRY(head.alloc(n)); TRY(bad.alloc(1)); TRY(amb.alloc(1)); TRY(flag.alloc(n));
 	CK(cudaMemsetAsync(bad.p, 0, sizeof(int), rb3b_stream));
+	/* round 0: all suffixes by their first 21 symbols */
 	k_kmer_keys<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, d_text, n_sym, key0.p, idx0.p, bad.p); CKK();
-	int rounds = 0;
-	for (uint64_t h = KMER;; h <<= 1) {
+	TRY(sort_pairs(key0.p, key1.p, idx0.p, sa.p, n, 64));
+	k_group_heads<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, key1.p, 1, head.p); CKK();
+	TRY(scan_max_u32(head.p, n));
+	CK(cudaMemsetAsync(amb.p, 0, 8, rb3b_stream));
+	k_assign_rank<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, sa.p, head.p, rank.p, amb.p); CKK();
+	unsigned long long n_amb = 0;
+	int hbad = 0, rounds = 1;
+	CK(cudaMemcpyAsync(&n_amb, amb.p, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+	CK(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, rb3b_stream));
+	CK(cudaStreamSynchronize(rb3b_stream));
+	if (hbad) return rb3b_fail(RB3B_EINVAL, "batch text holds a symbol >= %d", RB3B_ASIZE);
+	rb3b_stat_set("sa_ambiguous_after_round0", (int64_t)n_amb);
+	if (n_amb > 0 && n_amb < (1ULL << 31) && rb3b_get_param("sa_discard", 1) != 0) {
+		/* the list of ambiguous suffixes: reuse the round-0 buffers (the 64-bit key arrays hold four 32-bit arrays) */
+		uint32_t m = (uint32_t)n_amb;
+		uint32_t *suf = (uint32_t*)key0.p, *grp = suf + n, *key = (uint32_t*)key1.p, *ksorted = key + n; /* each has room for n */
+		DBuf<uint32_t> vsorted, segfirst, sub, off, tmp32;
+		TRY(vsorted.alloc(m)); TRY(segfirst.alloc(m)); TRY(sub.alloc(m)); TRY(off.alloc((size_t)m + 1)); TRY(tmp32.alloc(m));
+		k_amb_flags<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, head.p, flag.p); CKK();
+		TRY(select_flagged<uint32_t>(sa.p, flag.p, suf, n, amb.p));
+		TRY(select_flagged<uint32_t>(head.p, flag.p, grp, n, amb.p));
+		for (uint64_t h = KMER; m > 0 && h < n; h <<= 1) {
+			/* segments = groups */
+			k_list_keys<<<nblk(m, TPB), TPB, 0, rb3b_stream>>>(m, n, (uint32_t)h, suf, grp, rank.p, key, flag.p); CKK();
+			k_seg_first<<<nblk(m, TPB), TPB, 0, rb3b_stream>>>(m, grp, segfirst.p); CKK();
+			TRY(scan_max_u32(segfirst.p, m));
+			/* segment offsets: the list indices where a group starts, then m */
+			{
+				size_t tb = 0;
+				cub::CountingInputIterator<uint32_t> cnt(0);
+				CK(cub::DeviceSelect::Flagged((void*)0, tb, cnt, flag.p, off.p, amb.p, (int64_t)m, rb3b_stream));
+				DBuf<uint8_t> t;
+				TRY(t.alloc(tb));
+				CK(cub::DeviceSelect::Flagged((void*)t.p, tb, cnt, flag.p, off.p, amb.p, (int64_t)m, rb3b_stream));
+			}
+			unsigned long long n_seg = 0;
+			CK(cudaMemcpyAsync(&n_seg, amb.p, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+			CK(cudaStreamSynchronize(rb3b_stream));
+			CK(cudaMemcpyAsync(off.p + n_seg, &m, 4, cudaMemcpyHostToDevice, rb3b_stream));
+			{
+				size_t tb = 0;
+				CK(cub::DeviceSegmentedSort::SortPairs((void*)0, tb, key, ksorted, suf, vsorted.p, (int)m, (int)n_seg, off.p, off.p + 1, rb3b_stream));
+				DBuf<uint8_t> t;
+				TRY(t.alloc(tb));
+				CK(cub::DeviceSegmentedSort::SortPairs((void*)t.p, tb, key, ksorted, suf, vsorted.p, (int)m, (int)n_seg, off.p, off.p + 1, rb3b_stream));
+			}
+			k_sub_heads<<<nblk(m, TPB), TPB, 0, rb3b_stream>>>(m, grp, ksorted, segfirst.p, sub.p); CKK();
+			TRY(scan_max_u32(sub.p, m));
+			k_list_apply<<<nblk(m, TPB), TPB, 0, rb3b_stream>>>(m, vsorted.p, grp, segfirst.p, sub.p, sa.p, rank.p, flag.p); CKK();
+			/* the survivors, with their sub-group as the new group */
+			TRY(select_flagged<uint32_t>(vsorted.p, flag.p, suf, m, amb.p));
+			TRY(select_flagged<uint32_t>(sub.p, flag.p, tmp32.p, m, amb.p));
+			unsigned long long m2 = 0;
+			CK(cudaMemcpyAsync(&m2, amb.p, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+			CK(cudaStreamSynchronize(rb3b_stream));
+			if (m2) CK(cudaMemcpyAsync(grp, tmp32.p, (size_t)m2 * 4, cudaMemcpyDeviceToDevice, rb3b_stream));
+			m = (uint32_t)m2;
+			++rounds;
+		}
+		rb3b_stat_set("sa_rounds", rounds);
+		return RB3B_OK;
+	}
+	/* every round re-sorts all suffixes (lists of 2^31 ambiguous suffixes or more; "sa_discard" = 0) */
+	for (uint64_t h = KMER; n_amb > 0 && h < n; h <<= 1) {
+		k_pair_keys<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, (uint32_t)h, rank.p, key0.p, idx0.p); CKK();
 		TRY(sort_pairs(key0.p, key1.p, idx0.p, sa.p, n, 64));
-		k_group_heads<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, key1.p, rounds == 0, head.p); CKK();
+		k_group_heads<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, key1.p, 0, head.p); CKK();
 		TRY(scan_max_u32(head.p, n));
 		CK(cudaMemsetAsync(amb.p, 0, 8, rb3b_stream));
 		k_assign_rank<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, sa.p, head.p, rank.p, amb.p); CKK();
-		unsigned long long n_amb = 0;
-		int hbad = 0;
 		CK(cudaMemcpyAsync(&n_amb, amb.p, 8, cudaMemcpyDeviceToHost, rb3b_stream));
-		if (rounds == 0) CK(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, rb3b_stream));
 		CK(cudaStreamSynchronize(rb3b_stream));
-		if (hbad) return rb3b_fail(RB3B_EINVAL, "batch text holds a symbol >= %d", RB3B_ASIZE);
 		++rounds;
-		if (n_amb == 0 || h >= n) break;
-		k_pair_keys<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, (uint32_t)h, rank.p, key0.p, idx0.p); CKK();
 	}
 	rb3b_stat_set("sa_rounds", rounds);
 	return RB3B_OK;
