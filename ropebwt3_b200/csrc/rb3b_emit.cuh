@@ -350,9 +350,10 @@ __global__ void __launch_bounds__(EMIT_TPB) k_emit_bm(Src src, EmitOut O, int64_
 
 
 /* Bitmap -> bitmap merge without decoding runs.  The A symbols of an output cell are 128 consecutive bits (per plane)
- * of at most two A cells: X = (A planes >> offset).  With k batch rows landing at output offsets b_0 < ... < b_{k-1}
- * the output is, per plane, the OR over t = 0..k of (X << t) restricted to the gap between b_{t-1} and b_t, plus the
- * one-hot bits of the inserted rows: per gap a 128-bit mask-and-or and a shift by one for six planes. */
+ * of at most two A cells: X = (A planes >> offset).  The batch rows landing in the cell are bits that have to be INSERTED
+ * into that stream (a software PDEP): the cell is produced one 32-bit word at a time; a word starts as the next 32 source
+ * bits of every plane, every row landing in it (ascending offsets) opens a gap at its bit and sets the bit in its symbol's
+ * plane -- six planes x six instructions per row -- and the source stream advances by 32 minus the rows of the word. */
 static __global__ void __launch_bounds__(EMIT_TPB) k_emit_bm_fast(const uint4 *__restrict__ A, int64_t nA, int64_t nA_cells, EmitOut O,
                                                                    const int64_t *__restrict__ ka, const uint8_t *__restrict__ bwt, const int64_t *__restrict__ ilo,
                                                                    uint4 *__restrict__ lcnt, int64_t *__restrict__ ctot)
@@ -380,31 +381,45 @@ static __global__ void __launch_bounds__(EMIT_TPB) k_emit_bm_fast(const uint4 *_
 			for (int i = 0; i < 7; ++i) w[i] = i + 2 < 9 ? w[i + 2] : 0u;
 		}
 #pragma unroll
-		for (int i = 0; i < 4; ++i) { X[s][i] = __funnelshift_r(w[i], w[i + 1], r); OUT[s][i] = 0; }
+		for (int i = 0; i < 4; ++i) X[s][i] = __funnelshift_r(w[i], w[i + 1], r);
 	}
-	int prev = -1;
-	const int k = (int)(i1 - i0);
-	for (int t = 0; t <= k && live; ++t) {
-		int b = n_out, sym = -1;
-		if (t < k) { b = (int)(ka[i0 + t] + i0 + t - P0); sym = bwt[i0 + t]; }
-		const int lo = prev + 1, hi = b; /* gap [lo, hi) receives A symbols */
+	/* the rows of this cell, in ascending output offset */
+	int64_t t = i0;
+	int b = 1 << 30, sym = 0; /* offset and symbol of the next row (1 << 30: none left) */
+	if (t < i1) { b = (int)(ka[t] + t - P0); sym = bwt[t]; }
 #pragma unroll
-		for (int i = 0; i < 4; ++i) {
-			int l = lo - 32 * i, h = hi - 32 * i;
-			l = l < 0 ? 0 : l; h = h > 32 ? 32 : h;
-			uint32_t m = l < h ? ((h == 32 ? 0xffffffffu : (1u << h) - 1u) & ~((1u << l) - 1u)) : 0u;
-			uint32_t one = (sym >= 0 && (b >> 5) == i) ? 1u << (b & 31) : 0u;
+	for (int w = 0; w < 4; ++w) {
+		uint32_t o[RB3B_ASIZE];
 #pragma unroll
-			for (int s = 0; s < RB3B_ASIZE; ++s) OUT[s][i] |= (X[s][i] & m) | (s == sym ? one : 0u);
+		for (int s = 0; s < RB3B_ASIZE; ++s) o[s] = X[s][0];
+		int n_ins = 0;
+		while (b < 32 * (w + 1)) { /* rows landing in this word */
+			const int bb = b & 31;
+			const uint32_t lowm = (1u << bb) - 1u, bit = 1u << bb;
+#pragma unroll
+			for (int s = 0; s < RB3B_ASIZE; ++s) o[s] = (o[s] & lowm) | ((o[s] & ~lowm) << 1) | (s == sym ? bit : 0u);
+			++n_ins; ++t;
+			if (t < i1) { b = (int)(ka[t] + t - P0); sym = bwt[t]; } else b = 1 << 30;
 		}
+		/* positions past the end of the index hold nothing */
+		const int valid = n_out - 32 * w;
+		const uint32_t vm = valid >= 32 ? 0xffffffffu : valid <= 0 ? 0u : (1u << valid) - 1u;
 #pragma unroll
-		for (int s = 0; s < RB3B_ASIZE; ++s) { /* X <<= 1 */
-			X[s][3] = __funnelshift_l(X[s][2], X[s][3], 1);
-			X[s][2] = __funnelshift_l(X[s][1], X[s][2], 1);
-			X[s][1] = __funnelshift_l(X[s][0], X[s][1], 1);
-			X[s][0] <<= 1;
+		for (int s = 0; s < RB3B_ASIZE; ++s) OUT[s][w] = o[s] & vm;
+		/* the source stream advances by the A symbols this word consumed */
+		const int adv = 32 - n_ins;
+		if (adv >= 32) {
+#pragma unroll
+			for (int s = 0; s < RB3B_ASIZE; ++s) { X[s][0] = X[s][1]; X[s][1] = X[s][2]; X[s][2] = X[s][3]; X[s][3] = 0u; }
+		} else {
+#pragma unroll
+			for (int s = 0; s < RB3B_ASIZE; ++s) {
+				X[s][0] = __funnelshift_r(X[s][0], X[s][1], adv);
+				X[s][1] = __funnelshift_r(X[s][1], X[s][2], adv);
+				X[s][2] = __funnelshift_r(X[s][2], X[s][3], adv);
+				X[s][3] >>= adv;
+			}
 		}
-		prev = b;
 	}
 	rb3b_bm_finish_cell(O, j, live, OUT, lcnt, ctot);
 }
