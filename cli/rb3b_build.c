@@ -276,6 +276,7 @@ static void *reader_main(void *arg)
 
 typedef struct {
 	void *d; int64_t cap, len, n_seq;
+	rb3b_batch_t *pb;   /* the batch prepared for merging: partial BWT + walk order (NULL for -2/-s/-r) */
 	int file, last_of_file, open_failed;
 } dbatch_t;
 
@@ -297,6 +298,7 @@ static void *bwt_main(void *arg)
 		while (q->n_full == 2) pthread_cond_wait(&q->cv, &q->mu);
 		pthread_mutex_unlock(&q->mu);
 		o = &q->slot[q->tail];
+		o->pb = 0;
 		o->len = (int64_t)b->seq.l; o->n_seq = b->n_seq; o->file = b->file; o->last_of_file = b->last_of_file; o->open_failed = b->open_failed;
 		if (!b->open_failed && b->n_seq > 0) {
 			LOG("read %ld symbols from file '%s'", (long)b->seq.l, q->in->argv[b->file]);
@@ -307,7 +309,8 @@ static void *bwt_main(void *arg)
 			}
 			if (o->d == 0 || rb3b_h2d(o->d, b->seq.s, o->len) < 0) { fprintf(stderr, "ERROR: host to device copy: %s\n", rb3b_last_error()); q->failed = 1; }
 			else if (!q->use_rb2) {
-				if (rb3b_build_bwt_dev(o->len, (const uint8_t*)o->d, (uint8_t*)o->d) < 0) { fprintf(stderr, "ERROR: partial BWT: %s\n", rb3b_last_error()); q->failed = 1; } /* rb3_build_sais, in place */
+				o->pb = rb3b_batch_prepare_dev(o->len, (const uint8_t*)o->d); /* rb3_build_sais + the batch-only half of the rank phase */
+				if (o->pb == 0) { fprintf(stderr, "ERROR: partial BWT: %s\n", rb3b_last_error()); q->failed = 1; }
 				else LOG("constructed partial BWT for %ld symbols", (long)o->len);
 			}
 		}
@@ -529,12 +532,13 @@ int main(int argc, char *argv[])
 					LOG("inserted %ld symbols", (long)db->len);
 				} else if (idx == 0) {
 					idx = rb3b_index_create();
-					DIE_IF(rb3b_index_from_plain_dev(idx, db->len, (const uint8_t*)db->d), "encoding the partial BWT");
+					DIE_IF(rb3b_merge_prepared(idx, db->pb), "encoding the partial BWT"); /* rb3_enc_plain2fmr: the index is empty */
 					LOG("encoded the partial BWT for %ld symbols", (long)db->len);
 				} else {
-					DIE_IF(rb3b_merge_plain_dev(idx, db->len, (const uint8_t*)db->d), "merging the partial BWT");
+					DIE_IF(rb3b_merge_prepared(idx, db->pb), "merging the partial BWT"); /* rb3_fmi_merge_plain */
 					LOG("merged the partial BWT for %ld symbols", (long)db->len);
 				}
+				if (db->pb) { rb3b_batch_destroy(db->pb); db->pb = 0; }
 				/* after the first batch: building the first index resets the buffers */
 				if (!reserved) { rb3b_index_reserve(idx, est_symbols); reserved = 1; }
 			}

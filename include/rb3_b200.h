@@ -41,6 +41,7 @@ extern "C" {
 
 typedef struct rb3b_index_s rb3b_index_t;
 typedef struct rb3b_ctx_s rb3b_ctx_t;
+typedef struct rb3b_batch_s rb3b_batch_t;
 
 /* ---- runtime -------------------------------------------------------------- */
 int         rb3b_init(int device);                 /* select device, create stream + memory pool */
@@ -178,6 +179,18 @@ int rb3b_build_bwt_dev(int64_t len, const uint8_t *d_text, uint8_t *d_bwt_out);
 /* same in RLO (1) / RCLO (2) order: the BWT that mr_insert_multi (mrope.c:300) produces for this batch on an empty rope */
 int rb3b_build_bwt_so(int64_t len, const uint8_t *text, int sorting_order, uint8_t *bwt_out);
 int rb3b_build_bwt_so_dev(int64_t len, const uint8_t *d_text, int sorting_order, uint8_t *d_bwt_out);
+
+/* Prepared batches: the two steps of the reference's pipeline mode (kt_pipeline in build.c:55-83 -- step 0 rb3_build_sais,
+ * step 1 rb3_fmi_merge_plain / rb3_enc_plain2fmr).  Step 0 needs no index, so a host thread with its own context can
+ * prepare batch i+1 while another merges batch i.  The prepared batch holds the partial BWT AND the batch in walk order
+ * (its text read backwards with the inverse suffix array alongside, which the suffix sort yields for free), so step 1 skips
+ * the LF chase the BWT-only seam call needs.  text: concatenated 0-terminated nt6 strings, as for rb3b_build_bwt. */
+rb3b_batch_t  *rb3b_batch_prepare(int64_t len, const uint8_t *text);
+rb3b_batch_t  *rb3b_batch_prepare_dev(int64_t len, const uint8_t *d_text);
+void           rb3b_batch_destroy(rb3b_batch_t *b);
+int64_t        rb3b_batch_len(const rb3b_batch_t *b);
+const uint8_t *rb3b_batch_bwt_dev(const rb3b_batch_t *b);   /* the partial BWT in device memory (owned by the batch) */
+int            rb3b_merge_prepared(rb3b_index_t *idx, const rb3b_batch_t *b);
 
 /* Largest batch (in symbols) that fits the device next to an index of index_symbols: lets a caller clamp -m (build.c:39,
  * default 7G) to the device.  The .fmd is the same for any batching. */

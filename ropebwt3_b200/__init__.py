@@ -161,6 +161,46 @@ class Index:
         capi.check(self._L.rb3b_dump_plain(self.h, fn.encode()))
 
 
+class Batch:
+    """A batch prepared for merging: step 0 of the reference's pipeline (rb3_build_sais, build.c:55-83) plus the batch-only
+    half of the rank phase -- partial BWT and walk order, device resident."""
+
+    def __init__(self, h):
+        self._L = capi.lib()
+        if not h:
+            raise Rb3bError(-1, self._L.rb3b_last_error().decode())
+        self.h = h
+
+    @classmethod
+    def prepare(cls, text):
+        t = _u8(text)
+        return cls(capi.lib().rb3b_batch_prepare(len(t), capi.ptr(t)))
+
+    @classmethod
+    def prepare_dev(cls, d_text, n):
+        return cls(capi.lib().rb3b_batch_prepare_dev(n, capi.ptr(d_text)))
+
+    def __len__(self):
+        return int(self._L.rb3b_batch_len(self.h))
+
+    def bwt(self):
+        out = np.empty(len(self), np.uint8)
+        capi.check(self._L.rb3b_d2h(capi.ptr(out), self._L.rb3b_batch_bwt_dev(self.h), len(self)))
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.rb3b_batch_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+def merge_prepared(index, batch):
+    """rb3_fmi_merge_plain (or rb3_enc_plain2fmr for an empty index) on a prepared batch."""
+    capi.check(capi.lib().rb3b_merge_prepared(index.h, batch.h))
+
+
 # ---- the reference's names for the seam (fm-index.h:53-66) ------------------
 
 def rb3_enc_plain2fmr(bwt, max_nodes=0, block_len=0, n_threads=1):

@@ -76,6 +76,12 @@ SIGNATURES = {
     "rb3b_build_bwt": (_int, [_i64, _vp, _vp]),
     "rb3b_build_bwt_dev": (_int, [_i64, _vp, _vp]),
     "rb3b_max_batch_symbols": (_i64, [_i64]),
+    "rb3b_batch_prepare": (_vp, [_i64, _vp]),
+    "rb3b_batch_prepare_dev": (_vp, [_i64, _vp]),
+    "rb3b_batch_destroy": (None, [_vp]),
+    "rb3b_batch_len": (_i64, [_vp]),
+    "rb3b_batch_bwt_dev": (_vp, [_vp]),
+    "rb3b_merge_prepared": (_int, [_vp, _vp]),
     "rb3b_ssa_sizes": (_int, [_vp, _int, _vp, _vp, _vp]),
     "rb3b_ssa_gen_dev": (_int, [_vp, _int, _vp, _vp]),
     "rb3b_ssa_dump": (_int, [_vp, _int, C.c_char_p]),

@@ -16,6 +16,7 @@
  * Also here: rb3b_merge_index, the BWT-vs-BWT flavour (rb3_fmi_merge,
  * fm-index.c:251-277), which expands the other index and reuses merge_plain.
  */
+#include <string.h>
 #include <cub/cub.cuh>
 #include "rb3b_internal.cuh"
 
@@ -164,7 +165,8 @@ template<typename T> static int select_flagged(const T *in, const uint8_t *flag,
 }
 
 /* suffix array of the batch (generalised, sentinel order by position) into sa[len] (device, uint32) */
-static int suffix_sort(int64_t len, const uint8_t *d_text, DBuf<uint32_t> &sa, int n_sym = RB3B_ASIZE)
+/* rank_keep != 0: the final rank of every suffix (the inverse suffix array) is left there */
+static int suffix_sort(int64_t len, const uint8_t *d_text, DBuf<uint32_t> &sa, int n_sym = RB3B_ASIZE, DBuf<uint32_t> *rank_keep = 0)
 {
 	if (len >= (1LL << 32) - 2) return rb3b_fail(RB3B_EINVAL, "batches of 2^32 symbols or more are not supported by the device suffix sorter yet");
 	uint32_t n = (uint32_t)len;
@@ -173,7 +175,8 @@ static int suffix_sort(int64_t len, const uint8_t *d_text, DBuf<uint32_t> &sa, i
 	CK(cudaStreamSynchronize(rb3b_stream));
 	if (last != 0) return rb3b_fail(RB3B_EINVAL, "the batch text must end with a sentinel (mrope.c:310 asserts the same)");
 	DBuf<uint64_t> key0, key1;
-	DBuf<uint32_t> idx0, rank, head;
+	DBuf<uint32_t> idx0, rank_own, head;
+	DBuf<uint32_t> &rank = rank_keep ? *rank_keep : rank_own;
 	DBuf<int> bad;
 	DBuf<unsigned long long> amb;
 	DBuf<uint8_t> flag;
@@ -276,6 +279,141 @@ extern "C" int rb3b_build_bwt_dev(int64_t len, const uint8_t *d_text, uint8_t *d
 	CK(cudaStreamSynchronize(rb3b_stream));
 	rb3b_tflush();
 	return RB3B_OK;
+}
+
+/* ---- prepared batches: BWT + walk order straight from the suffix sort ---- */
+/*
+ * The reference's merge recovers the order in which it meets the rows of the batch by chasing LF over the batch BWT
+ * (rb3_mg_rank1_plain, fm-index.c:160-175); our seam call does the same with a list ranking (rb3b_merge.cu).  When the
+ * batch is sorted here anyway, that order is known: walk-order position st + l of a string occupying text positions
+ * [st, e] (e = its sentinel) is the suffix starting at e - l, i.e. row ISA[e - l], and its BWT symbol is T[e - l - 1].
+ * So the batch in walk order is the text read backwards string by string, with the inverse suffix array alongside.
+ */
+__global__ void k_zero_flags(int64_t len, const uint8_t *__restrict__ T, int64_t *__restrict__ flag);
+__global__ void k_zero_pos(int64_t len, const uint8_t *__restrict__ T, const int64_t *__restrict__ sid, int64_t *__restrict__ Z);
+
+__global__ void k_text_walk_order(int64_t len, const uint8_t *__restrict__ T, const uint32_t *__restrict__ isa, const int64_t *__restrict__ sid, const int64_t *__restrict__ Z,
+                                  uint8_t *__restrict__ wsym, uint32_t *__restrict__ wrow, int64_t *__restrict__ c_base, int64_t *__restrict__ c_len)
+{
+	const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= len) return;
+	const int64_t s = sid[q], st = s ? Z[s - 1] + 1 : 0, e = Z[s], src = st + e - q;
+	wrow[q] = isa[src];
+	wsym[q] = src > 0 ? T[src - 1] : 0; /* the symbol before the first string is the last sentinel */
+	if (q == e) { c_base[s] = st; c_len[s] = e - st + 1; }
+}
+
+__global__ void k_count_zero(int64_t len, const uint8_t *__restrict__ T, unsigned long long *__restrict__ cnt)
+{
+	unsigned int c = 0;
+	for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16, k = 0; k < 16 && i + k < len; ++k) c += T[i + k] == 0;
+	for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+	if ((threadIdx.x & 31) == 0 && c) atomicAdd(cnt, (unsigned long long)c);
+}
+
+__global__ void k_batch_count(int64_t len, const uint8_t *__restrict__ bwt, unsigned long long *__restrict__ cnt)
+{
+	__shared__ unsigned int sh[8];
+	if (threadIdx.x < 8) sh[threadIdx.x] = 0;
+	__syncthreads();
+	unsigned int c[RB3B_ASIZE] = {0, 0, 0, 0, 0, 0};
+	for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16, k = 0; k < 16 && i + k < len; ++k) {
+		const int a = bwt[i + k];
+#pragma unroll
+		for (int b = 0; b < RB3B_ASIZE; ++b) c[b] += a == b;
+	}
+#pragma unroll
+	for (int b = 0; b < RB3B_ASIZE; ++b) {
+		unsigned int v = c[b];
+		for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+		if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sh[b], v);
+	}
+	__syncthreads();
+	if (threadIdx.x < RB3B_ASIZE && sh[threadIdx.x]) atomicAdd(&cnt[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+extern "C" void rb3b_batch_destroy(rb3b_batch_t *b)
+{
+	if (b == 0) return;
+	cudaSetDevice(b->device);
+	/* one stream-ordered block (the pool keeps it for the next batch: no cudaMalloc / cudaFree per batch) */
+	if (b->bwt) cudaFreeAsync(b->bwt, rb3b_stream);
+	delete b;
+}
+
+extern "C" int64_t rb3b_batch_len(const rb3b_batch_t *b) { return b ? b->len : 0; }
+extern "C" const uint8_t *rb3b_batch_bwt_dev(const rb3b_batch_t *b) { return b ? b->bwt : 0; }
+
+static int batch_prepare_i(rb3b_batch_s *B, int64_t len, const uint8_t *d_text)
+{
+	DBuf<uint32_t> sa, isa;
+	DBuf<int64_t> flag, sid, Z;
+	DBuf<unsigned long long> cnt;
+	TRY(isa.alloc(len));
+	rb3b_tic(T_BWT);
+	TRY(suffix_sort(len, d_text, sa, RB3B_ASIZE, &isa));
+	/* layout of the one block: bwt | wsym | wrow | c_base, c_len (the number of strings is not known yet: sized for the
+	 * worst case only when small, else allocated after counting) */
+	const bool want_order = len < (1LL << 29) && rb3b_get_param("prepare_walk_order", 1) != 0;
+	const size_t o_sym = ((size_t)len + 511) & ~(size_t)511, o_row = o_sym + (((size_t)len + 64 + 511) & ~(size_t)511), o_chain = o_row + ((((size_t)len + 8) * 4 + 511) & ~(size_t)511);
+	DBuf<unsigned long long> cnt0;
+	TRY(cnt0.alloc(8));
+	CK(cudaMemsetAsync(cnt0.p, 0, 64, rb3b_stream));
+	k_count_zero<<<nblk((len + 15) / 16, TPB), TPB, 0, rb3b_stream>>>(len, d_text, cnt0.p); CKK();
+	unsigned long long n_zero = 0;
+	CK(cudaMemcpyAsync(&n_zero, cnt0.p, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+	CK(cudaStreamSynchronize(rb3b_stream));
+	const size_t total = want_order ? o_chain + (size_t)n_zero * 16 + 512 : (size_t)len;
+	if (cudaMallocAsync((void**)&B->bwt, total, rb3b_stream) != cudaSuccess) { cudaGetLastError(); B->bwt = 0; return rb3b_fail(RB3B_ENOMEM, "out of device memory for the batch (%zu bytes)", total); }
+	k_sa_to_bwt<<<nblk(len, TPB), TPB, 0, rb3b_stream>>>((uint32_t)len, d_text, sa.p, B->bwt); CKK();
+	TRY(cnt.alloc(8));
+	CK(cudaMemsetAsync(cnt.p, 0, 64, rb3b_stream));
+	k_batch_count<<<nblk((len + 15) / 16, TPB), TPB, 0, rb3b_stream>>>(len, B->bwt, cnt.p); CKK();
+	unsigned long long hc[8];
+	CK(cudaMemcpyAsync(hc, cnt.p, 64, cudaMemcpyDeviceToHost, rb3b_stream));
+	CK(cudaStreamSynchronize(rb3b_stream));
+	B->acc[0] = 0;
+	for (int a = 0; a < RB3B_ASIZE; ++a) B->acc[a + 1] = B->acc[a] + (int64_t)hc[a];
+	B->n_seq = (int64_t)hc[0];
+	if (!want_order) { rb3b_toc(T_BWT); CK(cudaStreamSynchronize(rb3b_stream)); return RB3B_OK; } /* 64-bit rows: the seam call rebuilds the order */
+	if ((unsigned long long)B->n_seq != n_zero) return rb3b_fail(RB3B_EINVAL, "internal error: %lld sentinels in the BWT, %llu in the text", (long long)B->n_seq, n_zero);
+	B->wsym = B->bwt + o_sym; B->wrow = (uint32_t*)(B->bwt + o_row); B->c_base = (int64_t*)(B->bwt + o_chain);
+	B->c_len = B->c_base + B->n_seq;
+	TRY(flag.alloc(len)); TRY(sid.alloc(len)); TRY(Z.alloc(B->n_seq));
+	k_zero_flags<<<nblk(len, TPB), TPB, 0, rb3b_stream>>>(len, d_text, flag.p); CKK();
+	TRY(rb3b_scan_excl_i64(flag.p, sid.p, len));
+	k_zero_pos<<<nblk(len, TPB), TPB, 0, rb3b_stream>>>(len, d_text, sid.p, Z.p); CKK();
+	CK(cudaMemsetAsync(B->wsym + len, 0, 64, rb3b_stream));
+	CK(cudaMemsetAsync(B->wrow + len, 0, 32, rb3b_stream));
+	k_text_walk_order<<<nblk(len, TPB), TPB, 0, rb3b_stream>>>(len, d_text, isa.p, sid.p, Z.p, B->wsym, B->wrow, B->c_base, B->c_len); CKK();
+	rb3b_toc(T_BWT);
+	CK(cudaStreamSynchronize(rb3b_stream));
+	rb3b_tflush();
+	return RB3B_OK;
+}
+
+/* rb3_build_sais (sais-ss.c:50-56) + the batch-only half of rb3_mg_rank_plain: text in device memory -> prepared batch */
+extern "C" rb3b_batch_t *rb3b_batch_prepare_dev(int64_t len, const uint8_t *d_text)
+{
+	ApiScope scope_;
+	if (rb3b_ensure_init() != RB3B_OK) return 0;
+	if (len <= 0) { rb3b_fail(RB3B_EINVAL, "empty batch"); return 0; }
+	rb3b_batch_s *B = new rb3b_batch_s;
+	memset(B, 0, sizeof(*B));
+	B->len = len; B->device = rb3b_cur()->device;
+	if (batch_prepare_i(B, len, d_text) != RB3B_OK) { rb3b_batch_destroy(B); return 0; }
+	return B;
+}
+
+extern "C" rb3b_batch_t *rb3b_batch_prepare(int64_t len, const uint8_t *text)
+{
+	ApiScope scope_;
+	if (rb3b_ensure_init() != RB3B_OK) return 0;
+	if (len <= 0) { rb3b_fail(RB3B_EINVAL, "empty batch"); return 0; }
+	DBuf<uint8_t> t;
+	if (t.alloc(len) != RB3B_OK) return 0;
+	if (cudaMemcpyAsync(t.p, text, (size_t)len, cudaMemcpyHostToDevice, rb3b_stream) != cudaSuccess) { rb3b_fail(RB3B_ENODEV, "host to device copy failed"); return 0; }
+	return rb3b_batch_prepare_dev(len, t.p);
 }
 
 extern "C" int rb3b_build_bwt(int64_t len, const uint8_t *text, uint8_t *bwt_out)

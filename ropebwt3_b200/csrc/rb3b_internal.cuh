@@ -79,6 +79,18 @@ struct rb3b_index_s {
 	char *ms; size_t ms_cap, ms_used; /* scratch that must outlive the call: interleave positions and batch copy (ms_used bytes), then the merge's tables */
 };
 
+/* a batch prepared for merging (rb3b_batch_prepare*): its partial BWT and the batch in walk order, all in device memory
+ * owned by the object.  Replaces what step 0 of the reference's pipeline hands to step 1 (build.c:55-83). */
+struct rb3b_batch_s {
+	int64_t len, n_seq;
+	int64_t acc[RB3B_ASIZE + 1];  /* C[] of the batch */
+	int device;
+	uint8_t *bwt;                 /* len */
+	uint8_t *wsym;                /* len + 64, or NULL: only the BWT was prepared (batches of 2^29 symbols or more) */
+	uint32_t *wrow;               /* len + 8 */
+	int64_t *c_base, *c_len;      /* n_seq each */
+};
+
 /* by-value kernel argument */
 struct DevIndex {
 	const uint4 *cells, *ovf;

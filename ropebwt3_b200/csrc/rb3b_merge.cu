@@ -860,9 +860,12 @@ static int walk_order(int64_t len, const uint8_t *d_bwt, int64_t nt, const int64
 /* what a device resolved itself, still in walk order: (row, position) pairs for the exchange between devices */
 struct OwnPairs { const uint32_t *rows; const int64_t *vals; int64_t n; };
 
-/* pairs != 0 (32-bit rows only): nothing is scattered, ka stays untouched, the device's own rows are handed back */
+/* pairs != 0 (32-bit rows only): nothing is scattered, ka stays untouched, the device's own rows are handed back.
+ * pre != 0: the batch comes with its walk order (rb3b_batch_prepare: straight from the suffix sort) -- no LF table, no
+ * chase, no list ranking; d_bwt is not read. */
 static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, DBuf<int64_t> &ka, int64_t accB[RB3B_ASIZE + 1],
-                      int part = 0, int n_parts = 1, int64_t *ka_out = 0, int *incomplete = 0, int so = 0, OwnPairs *pairs = 0)
+                      int part = 0, int n_parts = 1, int64_t *ka_out = 0, int *incomplete = 0, int so = 0, OwnPairs *pairs = 0,
+                      const rb3b_batch_s *pre = 0)
 {
 	int64_t nt = (len + PREP_TILE - 1) / PREP_TILE;
 	DBuf<int64_t> tcnt, tex;
@@ -870,10 +873,13 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	int hbad = 0;
 	if (len <= 0) return rb3b_fail(RB3B_EINVAL, "empty batch");
 	if (A->n_cells == 0) return rb3b_fail(RB3B_EINVAL, "rank phase on an empty index");
+	Acc7 acc;
+	rb3b_tic(T_PREP);
+	if (pre) memcpy(acc.v, pre->acc, sizeof(acc.v));
+	else {
 	/* batch LF mapping */
 	TRY(tcnt.alloc((nt + 1) * RB3B_ASIZE)); TRY(tex.alloc((nt + 1) * RB3B_ASIZE)); TRY(bad.alloc(1));
 	CK(cudaMemsetAsync(bad.p, 0, sizeof(int), rb3b_stream));
-	rb3b_tic(T_PREP);
 	k_prep_count<<<(unsigned)nt, TPB, 0, rb3b_stream>>>(len, d_bwt, nt, tcnt.p, bad.p); CKK();
 	TRY(rb3b_scan_excl_i64(tcnt.p, tex.p, (nt + 1) * RB3B_ASIZE));
 	int64_t tot[RB3B_ASIZE + 1], base[RB3B_ASIZE] = {0, 0, 0, 0, 0, 0};
@@ -884,9 +890,9 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	CK(cudaStreamSynchronize(rb3b_stream));
 	hbad = (int)tot[RB3B_ASIZE];
 	if (hbad) return rb3b_fail(RB3B_EINVAL, "batch BWT holds a symbol >= %d", RB3B_ASIZE);
-	Acc7 acc;
 	acc.v[0] = 0;
 	for (int a = 0; a < RB3B_ASIZE; ++a) acc.v[a + 1] = acc.v[a] + (tot[a] - base[a]);
+	}
 	memcpy(accB, acc.v, sizeof(acc.v));
 	if (acc.v[1] <= 0) return rb3b_fail(RB3B_EINVAL, "batch BWT holds no sentinel");
 	/* the batch in walk order */
@@ -917,8 +923,9 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	}
 	DBuf<uint8_t> wsym;
 	void *wrow = 0;
-	TRY(wsym.alloc(len + 64)); /* padded: the walks read whole 8-byte words, the fix-up whole chunks */
-	const bool narrow_lf = len < LF32_MAX_LEN && !rb3b_get_param("wide_lf", 0);
+	if (pre) wsym.p = pre->wsym;
+	else TRY(wsym.alloc(len + 64)); /* padded: the walks read whole 8-byte words, the fix-up whole chunks */
+	const bool narrow_lf = pre ? true : len < LF32_MAX_LEN && !rb3b_get_param("wide_lf", 0);
 	/* walk-order positions this device reads (everything for a sorted collection: the heads are resolved on every device) */
 	/* rows walked before every slice to narrow its bracket (k_walk_pair) */
 	int warm = (int)rb3b_get_param("warm_rows", 16);
@@ -926,7 +933,8 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	if (warm > seg_len) warm = (int)seg_len;
 	const int64_t p_lo = so ? -1 : S.walk_lo * seg_len - warm - 1, p_hi = so ? len : S.own_hi * seg_len;
 	const int64_t *c_base = 0, *c_len = 0;
-	if (narrow_lf) TRY((walk_order<uint32_t, uint32_t>(len, d_bwt, nt, tex.p, acc, F, p_lo, p_hi, wsym, &wrow, &c_base, &c_len, 0, part, n_parts)));
+	if (pre) { wrow = pre->wrow; c_base = pre->c_base; c_len = pre->c_len; F.n_fine = 0; }
+	else if (narrow_lf) TRY((walk_order<uint32_t, uint32_t>(len, d_bwt, nt, tex.p, acc, F, p_lo, p_hi, wsym, &wrow, &c_base, &c_len, 0, part, n_parts)));
 	else TRY((walk_order<uint64_t, int64_t>(len, d_bwt, nt, tex.p, acc, F, p_lo, p_hi, wsym, &wrow, &c_base, &c_len, 0, part, n_parts)));
 	const int64_t n_walk = S.own_hi - S.walk_lo;
 	DBuf<int64_t> seg, wl, ctr, kseq;
@@ -1431,6 +1439,21 @@ extern "C" int rb3b_merge_plain_dev(rb3b_index_t *x, int64_t len, const uint8_t 
 	}
 	TRY(rank_phase(x, len, d_bwt, ka, accB));
 	return merge_phase(x, len, d_bwt, ka.p);
+}
+
+/* rb3_fmi_merge_plain / rb3_enc_plain2fmr on a batch prepared by rb3b_batch_prepare* (rb3b_bwt.cu): the walk order comes with
+ * the batch, so only the walk over the index, the fix-up, the scatter and the merge are left */
+extern "C" int rb3b_merge_prepared(rb3b_index_t *x, const rb3b_batch_t *b)
+{
+	ApiScope scope_;
+	TRY(rb3b_ensure_init());
+	if (b == 0 || b->len <= 0) return rb3b_fail(RB3B_EINVAL, "empty batch");
+	if (x->n_cells == 0) return rb3b_index_from_plain_dev(x, b->len, b->bwt);
+	if (b->wsym == 0) return rb3b_merge_plain_dev(x, b->len, b->bwt); /* very large batch: only its BWT was prepared */
+	DBuf<int64_t> ka;
+	int64_t accB[RB3B_ASIZE + 1];
+	TRY(rank_phase(x, b->len, b->bwt, ka, accB, 0, 1, 0, 0, 0, 0, b));
+	return merge_phase(x, b->len, b->bwt, ka.p);
 }
 
 /* mr_insert_multi (mrope.c:300-385; build -2/-s/-r, build.c:214-218): insert the strings of `text` (concatenated,

@@ -173,6 +173,28 @@ def test_merge_chain_golden(rb3, oracle, golden, name, seg_len):
         rb3.set_param("seg_len", 0)
 
 
+@pytest.mark.parametrize("seg_len", [16, 0])
+@pytest.mark.parametrize("name", MERGE_SETS)
+def test_prepared_batches_golden(rb3, oracle, golden, name, seg_len):
+    """The two-step form (rb3b_batch_prepare + rb3b_merge_prepared: walk order straight from the suffix sort, no LF chase)
+    must build exactly what the reference built from the same texts."""
+    g = golden(name)
+    rb3.set_param("seg_len", seg_len)
+    try:
+        idx = rb3.Index()
+        for b in range(int(g["n_batches"])):
+            batch = rb3.Batch.prepare(g["text%d" % b])
+            assert np.array_equal(batch.bwt(), g["bwt%d" % b]), (name, b)
+            rb3.merge_prepared(idx, batch)
+            batch.close()
+            if b > 0:
+                assert np.array_equal(idx.acc(), g["accA%d" % b])
+        sym, ln = runs_of(idx, oracle)
+        assert rb3.fmd_image(sym, ln) == bytes(g["fmd"])
+    finally:
+        rb3.set_param("seg_len", 0)
+
+
 def test_merge_vs_oracle_seeded(rb3, oracle):
     """Fresh seeded inputs (not in the fixtures), device BWT construction included."""
     from ropebwt3_b200 import synth

@@ -89,6 +89,20 @@ def test_a_one_genome_per_merge_5mb(rb3, genomes6, ref_one_per_merge, kind, tmp_
         _set_kind(rb3, "auto")
 
 
+def test_a2_prepared_batches_5mb(rb3, genomes6, ref_one_per_merge, tmp_path):
+    """the same four genomes through rb3b_batch_prepare + rb3b_merge_prepared (walk order from the suffix sort)"""
+    from ropebwt3_b200 import synth
+    R = ref_one_per_merge
+    idx = rb3.Index()
+    for i, g in enumerate(genomes6[:4]):
+        batch = rb3.Batch.prepare(synth.batch_text([g]))
+        rb3.merge_prepared(idx, batch)
+        batch.close()
+    fn = str(tmp_path / "a2.fmd")
+    idx.dump_fmd(fn)
+    assert open(fn, "rb").read() == R["fmd"]
+
+
 @pytest.fixture(scope="module")
 def ref_big_batch(genomes6):
     """The reference's merge of ONE batch of genomes 2..5 (40 M rows, 8 chains) into the index of genomes 0..1."""

@@ -3,7 +3,7 @@
 tag=$1; shift
 i=0
 for args in "$@"; do
-  python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-rank-bench --no-e2e $args > gpurun_out/r2_sweep_${tag}_$i.json 2> gpurun_out/r2_sweep_${tag}_$i.err
+  python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-rank-bench --no-e2e --no-build $args > gpurun_out/r2_sweep_${tag}_$i.json 2> gpurun_out/r2_sweep_${tag}_$i.err
   python - <<PY
 import json
 try:
