@@ -685,9 +685,30 @@ extern "C" int64_t rb3b_runs_from_image(const uint8_t *image, int64_t n_bytes, u
 
 extern "C" void rb3b_host_free(void *p) { free(p); }
 
+int64_t rb3b_fmd_image_dev(int64_t R, const uint8_t *d_sym, const int64_t *d_len, const int64_t tot_sym[RB3B_ASIZE], uint8_t **out); /* rb3b_fmd_dev.cu */
+
 extern "C" int rb3b_dump_fmd(const rb3b_index_t *x, const char *fn)
 {
 	GUARD_BEGIN
+	if (rb3b_get_param("fmd_device", 1) != 0 && x->n > 0) { /* encode on the device: only the finished image crosses PCIe */
+		ApiScope scope_;
+		TRY(rb3b_ensure_init());
+		DBuf<uint8_t> ds; DBuf<int64_t> dl;
+		int64_t n_runs = 0;
+		TRY(rb3b_export_runs_dev(x, ds, dl, &n_runs));
+		if (n_runs >= rb3b_get_param("fmd_device_min_runs", 4096)) {
+			uint8_t *img = 0;
+			const int64_t sz = rb3b_fmd_image_dev(n_runs, ds.p, dl.p, x->tot, &img);
+			if (sz < 0) return (int)sz;
+			if (sz > 0) {
+				const int rc = write_file(fn, img, (size_t)sz);
+				free(img);
+				rb3b_stat_set("fmd_encoded_on_device", 1);
+				return rc;
+			}
+		}
+	}
+	rb3b_stat_set("fmd_encoded_on_device", 0);
 	std::vector<uint8_t> sym; std::vector<int64_t> len;
 	TRY(fetch_runs(x, sym, len));
 	bytes_t img;

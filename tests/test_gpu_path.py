@@ -195,6 +195,52 @@ def test_prepared_batches_golden(rb3, oracle, golden, name, seg_len):
         rb3.set_param("seg_len", 0)
 
 
+def _fast_runs(rng, n_runs, max_len, big_every=0):
+    sym = (np.cumsum(rng.integers(1, 6, n_runs)) % 6).astype(np.uint8)   # neighbours always differ
+    ln = rng.integers(1, max_len + 1, n_runs).astype(np.int64)
+    if big_every:
+        ln[::big_every] = rng.integers(1, 1 << 18, len(ln[::big_every]))
+    return sym, ln
+
+
+@pytest.mark.parametrize("n_runs,max_len,big", [(5000, 9, 0), (300000, 6, 0), (300000, 40, 13), (200000, 3000, 3), (20000, 1 << 17, 0)])
+def test_fmd_device_encoder(rb3, oracle, golden, tmp_path, n_runs, max_len, big):
+    """rld_enc / enc_next_block / rld_rank_index on the device (rb3b_fmd_dev.cu): the file must equal the host writer's image,
+    which tests/test_host.py pins to reference-made .fmd files -- 16-bit and 32-bit block headers, short and long runs."""
+    rng = np.random.default_rng(n_runs + max_len + big)
+    sym, ln = _fast_runs(rng, n_runs, max_len, big)
+    idx = rb3.Index.from_runs(sym, ln)
+    fn = str(tmp_path / "d.fmd")
+    idx.dump_fmd(fn)
+    assert rb3.get_stat("fmd_encoded_on_device") == 1
+    got = open(fn, "rb").read()
+    want = rb3.fmd_image(sym, ln)
+    assert got == want, "device .fmd differs: %d vs %d bytes, first difference at byte %d" % (
+        len(got), len(want), next((i for i in range(min(len(got), len(want))) if got[i] != want[i]), -1))
+    rb3.set_param("fmd_device", 0)
+    try:
+        idx.dump_fmd(fn)
+        assert rb3.get_stat("fmd_encoded_on_device") == 0 and open(fn, "rb").read() == want
+    finally:
+        rb3.set_param("fmd_device", 1)
+
+
+def test_fmd_device_encoder_golden(rb3, golden, tmp_path):
+    """the reference-made .fmd files, re-encoded on the device from the restored index (small lists forced onto the device)"""
+    rb3.set_param("fmd_device_min_runs", 1)
+    try:
+        for name, key in [("merge_small", "fmd"), ("merge_div", "fmd"), ("merge_dup", "fmd"), ("long_runs", "fmd"), ("rb2", "fmd_so2")]:
+            src = str(tmp_path / (name + ".fmd"))
+            open(src, "wb").write(bytes(golden(name)[key]))
+            idx = rb3.Index.restore(src)
+            out = str(tmp_path / (name + ".out.fmd"))
+            idx.dump_fmd(out)
+            assert rb3.get_stat("fmd_encoded_on_device") == 1, name
+            assert open(out, "rb").read() == bytes(golden(name)[key]), name
+    finally:
+        rb3.set_param("fmd_device_min_runs", 4096)
+
+
 def test_merge_vs_oracle_seeded(rb3, oracle):
     """Fresh seeded inputs (not in the fixtures), device BWT construction included."""
     from ropebwt3_b200 import synth

@@ -103,6 +103,22 @@ def test_a2_prepared_batches_5mb(rb3, genomes6, ref_one_per_merge, tmp_path):
     assert open(fn, "rb").read() == R["fmd"]
 
 
+def test_e_fmd_device_encoder_chunk_boundary(rb3, tmp_path):
+    """1.1e8 short runs = more than 2^20 blocks: the device encoder crosses a 2^23-word chunk boundary (the last block of a
+    chunk is one word shorter, rld0.h:81) and must still equal the host writer byte for byte"""
+    rng = np.random.default_rng(7)
+    n = 110_000_000
+    sym = (np.cumsum(rng.integers(1, 6, n, dtype=np.int8), dtype=np.int64) % 6).astype(np.uint8)
+    ln = rng.integers(1, 4, n).astype(np.int64)
+    idx = rb3.Index.from_runs(sym, ln)
+    fn = str(tmp_path / "big.fmd")
+    idx.dump_fmd(fn)
+    assert rb3.get_stat("fmd_encoded_on_device") == 1 and rb3.get_stat("fmd_device_blocks") > (1 << 20)
+    got = np.fromfile(fn, np.uint8)
+    want = np.frombuffer(rb3.fmd_image(sym, ln), np.uint8)
+    assert len(got) == len(want) and np.array_equal(got, want)
+
+
 @pytest.fixture(scope="module")
 def ref_big_batch(genomes6):
     """The reference's merge of ONE batch of genomes 2..5 (40 M rows, 8 chains) into the index of genomes 0..1."""
