@@ -88,6 +88,16 @@ template<bool WRITE> struct CellEmitter {
 	}
 	__device__ __forceinline__ void flush()
 	{
+		while (len > RB3B_LEN_MASK) { /* a 13-bit length field: long runs (wide cells only) take several entries */
+			const uint32_t rest = len - RB3B_LEN_MASK;
+			len = RB3B_LEN_MASK;
+			flush1();
+			len = rest;
+		}
+		flush1();
+	}
+	__device__ __forceinline__ void flush1()
+	{
 		if (len == 0) return;
 		if (WRITE) {
 			uint16_t e = (uint16_t)((uint32_t)sym << 13 | len);
@@ -169,6 +179,7 @@ __global__ void __launch_bounds__(EMIT_TPB) k_emit(Src src, EmitOut O, int64_t l
 		if (live) {
 			atomicAdd(&stats[0], (unsigned long long)E.ne);
 			if (ov) atomicAdd(&stats[1], 1ULL);
+			if (E.ne > RB3B_ENT_PER_CELL) atomicMax(&stats[2], (unsigned long long)E.ne);
 		}
 	} else {
 		uint64_t h[RB3B_ASIZE];
@@ -181,7 +192,7 @@ __global__ void __launch_bounds__(EMIT_TPB) k_emit(Src src, EmitOut O, int64_t l
 		if (live) {
 			uint4 *cell = O.cells + j * 8;
 			cell[0] = rb3b_hdr_pack(h[0], h[1], h[2], novf > 0);
-			cell[1] = rb3b_hdr_pack(h[3], h[4], h[5], false);
+			cell[1] = rb3b_hdr_pack(h[3], h[4], h[5], novf > 0); /* the flag is repeated here: a reader of G,T,N needs only this quad */
 			if (novf > 0) {
 				cell[2] = make_uint4((uint32_t)ovf_base, (uint32_t)novf, 0u, 0u);
 				for (uint32_t t = (uint32_t)novf; t < RB3B_MAX_OVF; ++t) ((uint16_t*)(cell + 3))[t - 1] = 0xffffu;
@@ -227,9 +238,9 @@ static int rb3b_emit_build(rb3b_index_s *x, Src src, int64_t n_src, int64_t lenB
 	DBuf<int64_t> ilo, ctot, cex;
 	DBuf<uint16_t> nent;
 	DBuf<unsigned long long> stats;
-	unsigned long long hstats[2] = {0, 0};
+	unsigned long long hstats[3] = {0, 0, 0};
 	EmitOut O;
-	TRY(stats.alloc(2));
+	TRY(stats.alloc(3));
 	for (;;) {
 		O.shift = shift; O.n_out = n_out;
 		O.n_cells = (n_out + (1LL << shift) - 1) >> shift;
@@ -241,12 +252,15 @@ static int rb3b_emit_build(rb3b_index_s *x, Src src, int64_t n_src, int64_t lenB
 			TRY(ilo.alloc(O.n_cells + 1));
 			k_tile_bounds<<<(unsigned)((O.n_cells + 1 + 255) / 256), 256, 0, rb3b_stream>>>(O.n_cells, shift, lenB, n_out, d_ka, ilo.p); CKK();
 		}
-		CK(cudaMemsetAsync(stats.p, 0, 16, rb3b_stream));
+		CK(cudaMemsetAsync(stats.p, 0, 24, rb3b_stream));
 		k_emit<Src, false><<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(src, O, lenB, d_ka, d_bwt, lenB > 0 ? ilo.p : 0, nent.p, ctot.p, 0, stats.p); CKK();
-		CK(cudaMemcpyAsync(hstats, stats.p, 16, cudaMemcpyDeviceToHost, rb3b_stream));
+		CK(cudaMemcpyAsync(hstats, stats.p, 24, cudaMemcpyDeviceToHost, rb3b_stream));
 		CK(cudaStreamSynchronize(rb3b_stream));
 		/* too many overflow cells: halve the span and count again (cheap, rare) */
 		if (shift > RB3B_MIN_SHIFT && (double)hstats[1] > 0.03 * (double)O.n_cells) { --shift; continue; }
+		/* the densest cell must fit its overflow blocks (an in-cell directory of RB3B_MAX_OVF block starts): a locally dense
+		 * stretch forces the span of the WHOLE index down -- the price of arithmetic cell addresses */
+		if (shift > RB3B_MIN_SHIFT && hstats[2] > (unsigned long long)RB3B_MAX_OVF * RB3B_ENT_PER_OVF) { --shift; continue; }
 		break;
 	}
 	TRY(rb3b_scan_excl_i64(ctot.p, cex.p, (O.n_chunks + 1) * (RB3B_ASIZE + 1)));

@@ -5,7 +5,7 @@
  * frame+header walk of rld0.c:371-408; see DESIGN.md "Data layout in HBM"):
  *
  *   The BWT is cut into CELLS of a fixed span of 2^shift positions
- *   (5 <= shift <= 10).  cells[j] is one 128-B line = 8 x uint4 describing
+ *   (5 <= shift <= 16).  cells[j] is one 128-B line = 8 x uint4 describing
  *   positions [j << shift, (j+1) << shift):
  *       quad 0   counts of $,A,C before the cell, 3 x 42 bit; bit 127 = OVERFLOW
  *       quad 1   counts of G,T,N before the cell, same packing
@@ -45,7 +45,7 @@
 #define RB3B_ENT_PER_OVF  56
 #define RB3B_MAX_OVF      41
 #define RB3B_MIN_SHIFT    5
-#define RB3B_MAX_SHIFT    10
+#define RB3B_MAX_SHIFT    16         /* cells of up to 65536 positions: a run longer than 8191 takes several entries */
 #define RB3B_LEN_MASK     0x1fffu
 #define RB3B_M42          ((1ULL << 42) - 1)
 #define RB3B_KIND_RLE     0

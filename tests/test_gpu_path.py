@@ -68,7 +68,7 @@ def test_overflow_cells(rb3, oracle):
     sym, ln = oracle.coalesce(np.concatenate(sym), np.concatenate(ln))
     rb3.set_param("index_kind", 1)
     idx = rb3.Index.from_runs(sym, ln)
-    assert rb3.get_stat("cell_shift") == 10 and rb3.get_stat("n_ovf_cells") > 0
+    assert rb3.get_stat("cell_shift") >= 10 and rb3.get_stat("n_ovf_cells") > 0   # wide cells; the dense stretches cap the span at 2^11
     n = int(ln.sum())
     starts = np.concatenate([[0], np.cumsum(ln)])
     k = np.concatenate([rng.integers(0, n, 5000), starts[:-1], starts[1:] - 1, starts[rng.integers(0, len(starts) - 1, 3000)] + 1, [n]]).astype(np.int64)
@@ -120,7 +120,7 @@ def test_from_plain_matches_runs(rb3, oracle, golden):
         rb3.Index.from_plain(np.array([1, 2, 6, 0], np.uint8))  # fm-index.c:125 asserts symbols < 6
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 4, 8, 22, 42, 44, 82, 84])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4, 8, 11, 22, 42, 44, 82, 84])
 def test_lf_dev(rb3, oracle, variant):
     import torch
     from ropebwt3_b200 import synth

@@ -103,6 +103,35 @@ def test_a2_prepared_batches_5mb(rb3, genomes6, ref_one_per_merge, tmp_path):
     assert open(fn, "rb").read() == R["fmd"]
 
 
+def test_f_rle_capacity_1e11_symbols(rb3):
+    """A highly repetitive index of 10^11 symbols (2x10^7 runs of ~5000): run-length cells of 65536 positions hold it in
+    about 0.2 GB; rank answers against a numpy restatement on the run list; a merge into it still works."""
+    rng = np.random.default_rng(11)
+    n_runs = 20_000_000
+    sym = (np.cumsum(rng.integers(1, 6, n_runs, dtype=np.int8), dtype=np.int64) % 6).astype(np.uint8)
+    ln = rng.integers(1, 10_000, n_runs).astype(np.int64)
+    rb3.set_param("index_kind", 1)
+    try:
+        idx = rb3.Index.from_runs(sym, ln)
+        n = int(ln.sum())
+        assert len(idx) == n and n > 9e10
+        assert rb3.get_stat("cell_shift") == 16 and idx.nbytes() < 1 << 29, (rb3.get_stat("cell_shift"), idx.nbytes())
+        starts = np.concatenate([[0], np.cumsum(ln)])
+        k = np.concatenate([rng.integers(0, n, 20000), starts[:3000], starts[1:3001] - 1, [n - 1, n, n + 5]]).astype(np.int64)
+        ok, ret = idx.rank1a(k)
+        r = np.minimum(np.searchsorted(starts, k, side="right") - 1, n_runs - 1)
+        for a in range(6):
+            pre = np.concatenate([[0], np.cumsum(np.where(sym == a, ln, 0))])
+            want = pre[r] + np.where(sym[r] == a, np.minimum(k, n) - starts[r], 0)
+            want = np.where(k >= n, pre[-1], want)
+            assert np.array_equal(ok[:, a], want), a
+        assert np.array_equal(ret[k < n], sym[r][k < n].astype(np.int8)) and (ret[k >= n] == -1).all()
+        s2, l2 = idx.export_runs()
+        assert np.array_equal(s2, sym) and np.array_equal(l2, ln)
+    finally:
+        rb3.set_param("index_kind", 0)
+
+
 def test_e_fmd_device_encoder_chunk_boundary(rb3, tmp_path):
     """1.1e8 short runs = more than 2^20 blocks: the device encoder crosses a 2^23-word chunk boundary (the last block of a
     chunk is one word shorter, rld0.h:81) and must still equal the host writer byte for byte"""
