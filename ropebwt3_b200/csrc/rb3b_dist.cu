@@ -101,6 +101,14 @@ int rb3b_all_gather(const void *send, void *recv, size_t bytes_per_rank)
 	return RB3B_OK;
 }
 
+int rb3b_all_reduce_sum_u32(void *buf, size_t n)
+{
+	rb3b_ctx_s *c = rb3b_cur();
+	if (c->world == 1) return RB3B_OK;
+	NCK(g_nccl.AllReduce(buf, buf, n, ncclUint32, ncclSum, (ncclComm_t)c->comm, c->stream));
+	return RB3B_OK;
+}
+
 int rb3b_all_reduce_max_i64(void *buf, size_t n)
 {
 	rb3b_ctx_s *c = rb3b_cur();

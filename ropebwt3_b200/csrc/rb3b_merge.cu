@@ -690,15 +690,15 @@ __global__ void __launch_bounds__(TPB) k_walk_fix(DevIndex A, Slices S, const ui
 }
 
 /* back to row order: ka[rows[i]] = vals[i] */
-template<typename RowT>
-__global__ void k_scatter_ka(int64_t n, const RowT *__restrict__ rows, const int64_t *__restrict__ vals, int64_t *__restrict__ ka, unsigned long long *n_unres)
+template<typename RowT, typename KaT>
+__global__ void k_scatter_ka(int64_t n, const RowT *__restrict__ rows, const int64_t *__restrict__ vals, KaT *__restrict__ ka, unsigned long long *n_unres)
 {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	unsigned int bad = 0;
 	if (i < n) {
 		const int64_t v = vals[i];
 		if (v & KS_UNRES) bad = 1;
-		else ka[(int64_t)rows[i]] = v;
+		else ka[(int64_t)rows[i]] = (KaT)v;
 	}
 	bad = __popc(__ballot_sync(0xffffffffu, bad));
 	if (bad && (threadIdx.x & 31) == 0) atomicAdd(n_unres, (unsigned long long)bad);
@@ -758,8 +758,8 @@ __global__ void k_fill_dense(int64_t n, const uint32_t *__restrict__ rows, const
 /* A scatter of 8-byte values over a target much larger than L2 costs a DRAM read-modify-write of a sector per value.
  * For large batches the (row, value) pairs are therefore first partitioned by the high bits of the row (one or two
  * radix passes, streaming), so that the scatter proper works on windows of 2^19 rows (4 MB) that stay in L2. */
-template<typename RowT>
-static int scatter_to_rows(int64_t n, int64_t len, const RowT *rows, const int64_t *vals, int64_t *ka, unsigned long long *n_unres)
+template<typename RowT, typename KaT>
+static int scatter_to_rows(int64_t n, int64_t len, const RowT *rows, const int64_t *vals, KaT *ka, unsigned long long *n_unres)
 {
 	if (n <= 0) return RB3B_OK;
 	const int win_bits = (int)rb3b_get_param("scatter_win_bits", 19);
@@ -772,11 +772,17 @@ static int scatter_to_rows(int64_t n, int64_t len, const RowT *rows, const int64
 		CK(cub::DeviceRadixSort::SortPairs(0, tb, rows, r2.p, vals, v2.p, n, win_bits, bits, rb3b_stream));
 		TRY(tmp.alloc(tb));
 		CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, rows, r2.p, vals, v2.p, n, win_bits, bits, rb3b_stream));
-		k_scatter_ka<RowT><<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, r2.p, v2.p, ka, n_unres); CKK();
+		k_scatter_ka<RowT, KaT><<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, r2.p, v2.p, ka, n_unres); CKK();
 	} else {
-		k_scatter_ka<RowT><<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, rows, vals, ka, n_unres); CKK();
+		k_scatter_ka<RowT, KaT><<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, rows, vals, ka, n_unres); CKK();
 	}
 	return RB3B_OK;
+}
+
+__global__ void k_widen_ka(int64_t n, const uint32_t *__restrict__ in, int64_t *__restrict__ out)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = (int64_t)in[i];
 }
 
 /* rb[i] = (ka+i)<<6 | B[i]<<3 | first symbol of suffix i (fm-index.c:168) */
@@ -865,7 +871,7 @@ struct OwnPairs { const uint32_t *rows; const int64_t *vals; int64_t n; };
  * chase, no list ranking; d_bwt is not read. */
 static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, DBuf<int64_t> &ka, int64_t accB[RB3B_ASIZE + 1],
                       int part = 0, int n_parts = 1, int64_t *ka_out = 0, int *incomplete = 0, int so = 0, OwnPairs *pairs = 0,
-                      const rb3b_batch_s *pre = 0)
+                      const rb3b_batch_s *pre = 0, uint32_t *ka32 = 0 /* multi-device: 32-bit partial array (0 = nobody's), every position fits */)
 {
 	int64_t nt = (len + PREP_TILE - 1) / PREP_TILE;
 	DBuf<int64_t> tcnt, tex;
@@ -940,7 +946,7 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	DBuf<int64_t> seg, wl, ctr, kseq;
 	TRY(seg.alloc(S.n_seg * 3)); TRY(wl.alloc(S.n_seg * 4)); TRY(ctr.alloc(16)); TRY(kseq.alloc(len + 64));
 	if (pairs && !narrow_lf) return rb3b_fail(RB3B_EINVAL, "internal error: pair output needs 32-bit rows");
-	if (pairs) ka.p = 0;
+	if (pairs || ka32) ka.p = 0;
 	else if (ka_out) ka.p = ka_out; else TRY(ka.alloc(len));
 	S.d = seg.p; S.arr_lo = seg.p + S.n_seg; S.arr_hi = seg.p + 2 * S.n_seg;
 	rb3b_toc(T_PREP);
@@ -949,7 +955,8 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	if (A->broken) return rb3b_fail(RB3B_EINVAL, "the index was left unusable by an earlier failed merge");
 	TRY(rb3b_index_use(A));
 	CK(cudaMemsetAsync(ctr.p, 0, 16 * 8, rb3b_stream));
-	if (n_parts > 1 && !pairs) CK(cudaMemsetAsync(ka.p, 0xff, len * 8, rb3b_stream));
+	if (ka32) CK(cudaMemsetAsync(ka32, 0, len * 4, rb3b_stream));
+	else if (n_parts > 1 && !pairs) CK(cudaMemsetAsync(ka.p, 0xff, len * 8, rb3b_stream));
 	DevIndex dA = rb3b_dev_view(A);
 	const bool bm = A->kind == RB3B_KIND_BM;
 	/* bitmap walks are lane pairs (single threads in the fix-up): small CTAs spread the walks over all SMs */
@@ -1016,8 +1023,10 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	if (pairs) {
 		pairs->rows = (const uint32_t*)wrow + own_p0; pairs->vals = kseq.p + own_p0; pairs->n = own_rows;
 		k_count_flagged<<<nblk(own_rows > 0 ? own_rows : 1, TPB), TPB, 0, rb3b_stream>>>(own_rows, pairs->vals, (unsigned long long*)(ctr.p + 8)); CKK();
-	} else if (narrow_lf) TRY(scatter_to_rows<uint32_t>(own_rows, len, (const uint32_t*)wrow + own_p0, kseq.p + own_p0, ka.p, (unsigned long long*)(ctr.p + 8)));
-	else TRY(scatter_to_rows<int64_t>(own_rows, len, (const int64_t*)wrow + own_p0, kseq.p + own_p0, ka.p, (unsigned long long*)(ctr.p + 8)));
+	} else if (ka32 && narrow_lf) TRY((scatter_to_rows<uint32_t, uint32_t>(own_rows, len, (const uint32_t*)wrow + own_p0, kseq.p + own_p0, ka32, (unsigned long long*)(ctr.p + 8))));
+	else if (ka32) TRY((scatter_to_rows<int64_t, uint32_t>(own_rows, len, (const int64_t*)wrow + own_p0, kseq.p + own_p0, ka32, (unsigned long long*)(ctr.p + 8))));
+	else if (narrow_lf) TRY((scatter_to_rows<uint32_t, int64_t>(own_rows, len, (const uint32_t*)wrow + own_p0, kseq.p + own_p0, ka.p, (unsigned long long*)(ctr.p + 8))));
+	else TRY((scatter_to_rows<int64_t, int64_t>(own_rows, len, (const int64_t*)wrow + own_p0, kseq.p + own_p0, ka.p, (unsigned long long*)(ctr.p + 8))));
 	rb3b_toc(T_SCATTER);
 	CK(cudaMemcpyAsync(&unres, ctr.p + 8, 8, cudaMemcpyDeviceToHost, rb3b_stream));
 	CK(cudaStreamSynchronize(rb3b_stream));
@@ -1293,6 +1302,7 @@ static int async_buffers(rb3b_index_s *x, int64_t len, const uint8_t *d_bwt, int
 /* collectives of rb3b_dist.cu (NCCL on the current context's stream) */
 int rb3b_all_gather(const void *send, void *recv, size_t bytes_per_rank);
 int rb3b_all_reduce_max_i64(void *buf, size_t n);
+int rb3b_all_reduce_sum_u32(void *buf, size_t n);
 int rb3b_all_to_all_v(const void *send, const int64_t *soff, const int64_t *scnt, void *recv, const int64_t *roff, const int64_t *rcnt);
 
 /* rb3_fmi_merge_plain on the ranks of the current communicator (rb3b_dist_init): every rank holds a replica of the index
@@ -1324,8 +1334,13 @@ extern "C" int rb3b_merge_plain_dist_dev(rb3b_index_t *x, int64_t len, const uin
 	TRY(flag.alloc(2 + 2 * MAX_RANKS + (size_t)W * W));
 	OwnPairs own;
 	int64_t *const ka_full = ka.p;
-	TRY(rank_phase(x, len, d_bwt, ka, accB, ctx->rank, ctx->world, ka.p, &incomplete, 0, by_pairs ? &own : 0));
-	ka.p = ka_full; /* with pair output the rank phase leaves the array alone */
+	/* positions below 2^32 (every BASELINE config 1 index): the partial arrays are 32-bit with 0 for "not mine" and are
+	 * combined by a SUM all-reduce -- half the bytes of the 64-bit MAX all-reduce */
+	const bool narrow_ka = !by_pairs && x->n + len < (1LL << 32) && rb3b_get_param("dist_ka32", 1) != 0;
+	DBuf<uint32_t> ka32;
+	if (narrow_ka) TRY(ka32.alloc(len));
+	TRY(rank_phase(x, len, d_bwt, ka, accB, ctx->rank, ctx->world, ka.p, &incomplete, 0, by_pairs ? &own : 0, 0, narrow_ka ? ka32.p : 0));
+	ka.p = ka_full; /* with pair / 32-bit output the rank phase leaves the array alone */
 	hflag = incomplete;
 	rb3b_tic(T_COMM);
 	unsigned long long *d_cnt = (unsigned long long*)(flag.p + 2), *d_cur = d_cnt + MAX_RANKS;
@@ -1363,6 +1378,9 @@ extern "C" int rb3b_merge_plain_dist_dev(rb3b_index_t *x, int64_t len, const uin
 		if (n_recv > 0) { k_fill_dense<<<nblk(n_recv, TPB), TPB, 0, rb3b_stream>>>(n_recv, rrow.p, rval.p, row0, ka.p + row0); CKK(); }
 		TRY(rb3b_all_gather(ka.p + row0, ka.p, (size_t)chunk * 8));
 		CK(cudaStreamSynchronize(rb3b_stream)); /* the packed buffers are scratch of this call */
+	} else if (narrow_ka) {
+		TRY(rb3b_all_reduce_sum_u32(ka32.p, (size_t)len));
+		k_widen_ka<<<nblk(len, TPB), TPB, 0, rb3b_stream>>>(len, ka32.p, ka.p); CKK();
 	} else TRY(rb3b_all_reduce_max_i64(ka.p, (size_t)len)); /* rows another rank resolved are -1 here */
 	rb3b_toc(T_COMM);
 	if (aka) TRY(merge_phase(x, len, bcopy, aka, accB));
