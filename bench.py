@@ -334,7 +334,7 @@ def run_b200(a):
         pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "strong" if (a.genomes_per_merge > 0 and a.config == "c1") else "weak", "vs_baseline": None,
         "dtype": "u8/int64", "data": "synthetic",
         "config": config_of(a, {"seg_len": a.seg_len or R.get_stat("seg_len_used"), "parallelism": "1 GPU" if world == 1 else "weak scaling: %d genomes per merge on %d GPUs; index replicated; rank phase of every merge split over the ranks (chain stretches + halo), NCCL all-reduce(MAX) of the 8 B/row interleave array, merge replicated; %d of %d merges sharded" % (G, world, n_sharded, a.steps)}),
         "e2e": None if a.no_e2e else {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(np.mean(lens[1 + a.warmup:])), "d2h_bytes_per_step": int(d2h),

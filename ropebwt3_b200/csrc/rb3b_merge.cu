@@ -433,6 +433,7 @@ __global__ void k_collect_first(Slices S, int64_t *__restrict__ wl_seg, int64_t 
  * The even lane ranks lo, the odd lane hi; each holds the plane of its own cell, the odd lane's travels by shuffle. */
 #define KS_TIGHT KS_NARROW   /* the row's mask is in wmask[] */
 #define TIGHT_WIDTH 127
+#define KS_WIDTH_SHIFT 43    /* tight rows: the width of the bracket (7 bits) above the 42-bit low end */
 
 template<bool SO>
 __global__ void __launch_bounds__(32) k_walk_pair(DevIndex A, Slices S, const uint8_t *__restrict__ wsym, int64_t *__restrict__ kseq, uint4 *__restrict__ wmask,
@@ -474,7 +475,7 @@ __global__ void __launch_bounds__(32) k_walk_pair(DevIndex A, Slices S, const ui
 				const bool unres = lo != hi;
 				const bool tight = unres && wmask != 0 && hi - lo <= TIGHT_WIDTH;
 				if (!unres) vb[jj] = lo;
-				else { vb[jj] = lo | KS_UNRES | (tight ? KS_TIGHT : 0); d += live && own; }
+				else { vb[jj] = lo | KS_UNRES | (tight ? KS_TIGHT | (hi - lo) << KS_WIDTH_SHIFT : 0); d += live && own; }
 				if (live) {
 					if (c == 0) lo = hi = SO ? 0 : A.acc[1];
 					else {
@@ -574,7 +575,8 @@ struct FixRing {
  * pass -- the random stores compete with the walk's own dependent accesses, 0.31 -> 0.67 ms for the walk; and G = 4..32 lanes
  * per slice with the mask travelling by shuffle -- 0.53-0.61 ms against 0.27 ms for one thread per slice.) */
 __global__ void __launch_bounds__(FIX_TPB) k_fix_chain(DevIndex A, Slices S, const uint8_t *__restrict__ wsym, int64_t *__restrict__ kseq, const uint4 *__restrict__ wmask,
-                                                        int64_t n_items, const int64_t *__restrict__ wl_seg, const int64_t *__restrict__ wl_val, unsigned long long *stats)
+                                                        int64_t n_items, const int64_t *__restrict__ wl_seg, const int64_t *__restrict__ wl_val, unsigned long long *stats,
+                                                        int cascade)
 {
 	__shared__ FixRing R;
 	const int tx = threadIdx.x;
@@ -634,7 +636,7 @@ __global__ void __launch_bounds__(FIX_TPB) k_fix_chain(DevIndex A, Slices S, con
 			cp_async_wait<0>(); /* the ring is restarted for the next slice */
 #undef FIX_ISSUE
 			v = arr + x; /* meaningful only when the slice never collapsed */
-			const bool go_on = d == len && !ended && !was_exact && t + 1 < S.own_hi && S.d[t + 1] > 0; /* t + 1's only predecessor is t and t + 1 is on nobody's list */
+			const bool go_on = cascade && d == len && !ended && !was_exact && t + 1 < S.own_hi && S.d[t + 1] > 0; /* t + 1's only predecessor is t and t + 1 is on nobody's list */
 			S.d[t] = 0;
 			if (d == len && !ended) S.arr_lo[t] = S.arr_hi[t] = v;
 			if (!go_on) break;
@@ -650,6 +652,57 @@ __global__ void __launch_bounds__(FIX_TPB) k_fix_chain(DevIndex A, Slices S, con
 		mx = y > mx ? y : mx;
 	}
 	if ((tx & 31) == 0 && tot) { atomicAdd(stats, tot); atomicAdd(stats + 1, n_wide); atomicMax(stats + 2, mx); }
+}
+
+/* ---- cascades without the chain: transfer tables of the slices that never collapsed ----
+ * A slice whose bracket never collapsed maps the offset x_in with which the exact value enters it (0 <= x_in <= w0, the
+ * width of its first bracket) to the offset with which it leaves: a monotone function of at most 128 arguments, independent
+ * of everything outside the slice.  k_fix_tables evaluates it for ALL arguments at once -- one lane per argument, every lane
+ * running the same popc(mask below x) chain over the slice's rows -- for every such slice in parallel.  k_fix_hops then
+ * follows every cascade through the tables (one lookup per slice instead of one chain step per row) and lists every slice
+ * with the exact value it starts from; k_fix_chain resolves all listed slices at once, no slice waiting for another.  The
+ * longest dependent chain of the fix-up drops from the longest cascade (thousands of rows) to one slice. */
+__global__ void __launch_bounds__(128) k_fix_tables(Slices S, const int64_t *__restrict__ kseq, const uint4 *__restrict__ wmask, uint8_t *__restrict__ tab, uint8_t *__restrict__ tab_ok)
+{
+	const int64_t W = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31, cb = (int)(W & 3);
+	const int64_t s = S.walk_lo + (W >> 2);
+	if (s >= S.own_hi) return; /* warp-uniform */
+	const int64_t len = S.slice_len(s), base = s * S.seg_len;
+	if (S.d[s] != len || S.arr_lo[s] == S.arr_hi[s]) return; /* collapsed inside, or exact on its last row: nothing to hand on */
+	const int64_t ks0 = kseq[base];
+	if (!(ks0 & KS_TIGHT)) { if (cb == 0 && lane == 0) tab_ok[s] = 0; return; }
+	const int w0 = (int)(ks0 >> KS_WIDTH_SHIFT) & 127;
+	if (cb * 32 > w0) return;
+	uint32_t x = (uint32_t)(cb * 32 + lane);
+	bool ok = true;
+	for (int64_t u = 0; u < len; ++u) {
+		const int64_t ks = __ldg(kseq + base + u); /* the same address on every lane */
+		if (!(ks & KS_TIGHT)) { ok = false; break; }
+		x = mask_rank(__ldg(wmask + base + u), x);
+	}
+	if (ok) tab[s * 128 + cb * 32 + lane] = (uint8_t)x;
+	if (cb == 0 && lane == 0) tab_ok[s] = ok ? 1 : 0;
+}
+
+__global__ void k_fix_hops(Slices S, const int64_t *__restrict__ kseq, const uint8_t *__restrict__ tab, const uint8_t *__restrict__ tab_ok,
+                           int64_t n_items, const int64_t *__restrict__ wl_seg, const int64_t *__restrict__ wl_val,
+                           int64_t *__restrict__ out_seg, int64_t *__restrict__ out_val, unsigned long long *out_n)
+{
+	const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (it >= n_items) return;
+	int64_t t = wl_seg[it], v = wl_val[it];
+	for (;;) {
+		const unsigned long long o = atomicAdd(out_n, 1ULL);
+		out_seg[o] = t; out_val[o] = v;
+		if (S.d[t] != S.slice_len(t) || S.arr_lo[t] == S.arr_hi[t]) break; /* collapses inside / its successor is an item of its own */
+		if (!tab_ok[t]) break; /* a row without a mask: the general fix-up carries on from here afterwards */
+		const int64_t x = v - (kseq[t * S.seg_len] & (int64_t)RB3B_M42);
+		if (x < 0 || x > TIGHT_WIDTH) break; /* cannot happen for a valid batch */
+		v = S.arr_lo[t] + (int64_t)tab[t * 128 + x];
+		++t;
+		if (t >= S.own_hi || S.d[t] == 0) break;
+	}
 }
 
 /* generic fix-up (RLE cells, or bitmap cells without the tables): re-walk the unresolved prefix of each listed slice
@@ -992,13 +1045,44 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	CK(cudaMemcpyAsync(&n_items, ctr.p + 1, 8, cudaMemcpyDeviceToHost, rb3b_stream));
 	CK(cudaStreamSynchronize(rb3b_stream));
 	int cur = 0;
+	if (n_items > 0 && use_log && use_mask && !so && rb3b_get_param("fix_tables", 0) != 0) {
+		/* cascades through transfer tables: every slice with unresolved rows gets its exact start, then all are resolved
+		 * at once; whatever is left (a row without a mask somewhere) goes through the cascading loop below.
+		 * Off by default: the longest dependent chain drops from ~2150 to 192 rows, but evaluating 128 arguments for every
+		 * slice that never collapsed costs more than the cascades it removes (fix-up 0.39 vs 0.26 ms with one genome per
+		 * merge, 1.16 vs 0.67 ms with ten; gpurun_out/r2_sweep_tables_*.json). */
+		DBuf<uint8_t> tab, tab_ok;
+		TRY(tab.alloc((size_t)S.n_seg * 128)); TRY(tab_ok.alloc(S.n_seg));
+		CK(cudaMemsetAsync(ctr.p + 2, 0, 40, rb3b_stream));
+		CK(cudaMemsetAsync(ctr.p + 9, 0, 8, rb3b_stream));
+		rb3b_tic(T_WALKFIX);
+		k_fix_tables<<<nblk(n_walk * 4 * 32, 128), 128, 0, rb3b_stream>>>(S, kseq.p, wmask.p, tab.p, tab_ok.p); CKK();
+		k_fix_hops<<<nblk(n_items, TPB), TPB, 0, rb3b_stream>>>(S, kseq.p, tab.p, tab_ok.p, n_items, wl_seg[0], wl_val[0], wl_seg[1], wl_val[1], (unsigned long long*)(ctr.p + 9)); CKK();
+		int64_t n2 = 0;
+		CK(cudaMemcpyAsync(&n2, ctr.p + 9, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+		CK(cudaStreamSynchronize(rb3b_stream));
+		if (n2 > 0) { k_fix_chain<<<nblk(n2, FIX_TPB), FIX_TPB, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, wmask.p, n2, wl_seg[1], wl_val[1], (unsigned long long*)(ctr.p + 4), 0); CKK(); }
+		rb3b_toc(T_WALKFIX);
+		fix_items += n2;
+		/* leftovers */
+		CK(cudaMemsetAsync(ctr.p + 1, 0, 8, rb3b_stream));
+		k_collect_first<<<nblk(n_walk > 0 ? n_walk : 1, TPB), TPB, 0, rb3b_stream>>>(S, wl_seg[0], wl_val[0], (unsigned long long*)(ctr.p + 1)); CKK();
+		int64_t fst[4] = {0, 0, 0, 0};
+		CK(cudaMemcpyAsync(&n_items, ctr.p + 1, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+		CK(cudaMemcpyAsync(fst + 1, ctr.p + 4, 24, cudaMemcpyDeviceToHost, rb3b_stream));
+		CK(cudaStreamSynchronize(rb3b_stream));
+		rb3b_stat_set("fix_rows", fst[1]); rb3b_stat_set("fix_wide_rows", fst[2]); rb3b_stat_set("fix_longest_chain", fst[3]);
+		rb3b_stat_set("fix_table_slices", n2); rb3b_stat_set("fix_leftover_items", n_items);
+		rb3b_tflush();
+		++rounds;
+	}
 	while (n_items > 0) {
 		/* ctr[2] = item cursor, ctr[3] = size of the next list, ctr[4..6] = statistics */
 		CK(cudaMemsetAsync(ctr.p + 2, 0, 40, rb3b_stream));
 		want = (n_items * wg + wtpb - 1) / wtpb;
 		rb3b_tic(T_WALKFIX);
 		if (use_log) k_fix_chain<<<nblk(n_items, FIX_TPB), FIX_TPB, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, use_mask ? wmask.p : 0, n_items, wl_seg[cur], wl_val[cur],
-			(unsigned long long*)(ctr.p + 4));
+			(unsigned long long*)(ctr.p + 4), 1);
 		else if (bm) k_walk_fix<BmRank><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, n_items, wl_seg[cur], wl_val[cur], ctr.p + 2,
 			wl_seg[cur ^ 1], wl_val[cur ^ 1], (unsigned long long*)(ctr.p + 3));
 		else k_walk_fix<Grp<8> ><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, n_items, wl_seg[cur], wl_val[cur], ctr.p + 2,

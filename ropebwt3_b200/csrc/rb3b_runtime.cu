@@ -9,6 +9,7 @@
  * -- and N threads with N explicit contexts can drive N devices from one process (rb3b_ctx_create(device)).
  */
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <map>
 #include <mutex>
@@ -48,6 +49,10 @@ static int ctx_setup(rb3b_ctx_s *c, int device)
 		CK(cudaDeviceGetDefaultMemPool(&pool, device));
 		uint64_t thr = UINT64_MAX; /* keep freed index buffers in the pool: merges reuse them */
 		CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+		/* RB3B_L2_FETCH=32|64|128: granularity of L2 fetches from DRAM (a hint; the rank kernels touch one 64-byte half cell
+		 * per query -- see profiles/ for what it does to the DRAM bytes per query) */
+		const char *fg = getenv("RB3B_L2_FETCH");
+		if (fg && atoi(fg) > 0) { if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fg)) != cudaSuccess) cudaGetLastError(); }
 	}
 	return RB3B_OK;
 }
