@@ -147,7 +147,7 @@ def run_b200(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     R.init(local)
-    stream = torch.cuda.Stream()
+    stream = torch.cuda.Stream(priority=-1)   # above the library's second stream (queued merges): the next batch's small kernels go first
     torch.cuda.set_stream(stream)
     capi.check(capi.lib().rb3b_set_stream(stream.cuda_stream))
     from ropebwt3_b200 import dist as rdist
@@ -336,7 +336,7 @@ def run_b200(a):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "strong" if (a.genomes_per_merge > 0 and a.config == "c1") else "weak", "vs_baseline": None,
         "dtype": "u8/int64", "data": "synthetic",
-        "config": config_of(a, {"seg_len": a.seg_len or R.get_stat("seg_len_used"), "parallelism": "1 GPU" if world == 1 else "weak scaling: %d genomes per merge on %d GPUs; index replicated; rank phase of every merge split over the ranks (chain stretches + halo), NCCL all-reduce(MAX) of the 8 B/row interleave array, merge replicated; %d of %d merges sharded" % (G, world, n_sharded, a.steps)}),
+        "config": config_of(a, {"seg_len": a.seg_len or R.get_stat("seg_len_used"), "parallelism": "1 GPU" if world == 1 else "weak scaling: %d genomes per merge on %d GPUs; index replicated; rank phase of every merge split over the ranks (walk-order slices + halo, first walk of the pieces shared by an all-gather), one NCCL all-reduce of the partial interleave arrays (32-bit SUM while positions fit, else 64-bit MAX), merge replicated; %d of %d merges sharded" % (G, world, n_sharded, a.steps)}),
         "e2e": None if a.no_e2e else {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(np.mean(lens[1 + a.warmup:])), "d2h_bytes_per_step": int(d2h),
                                       "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": int(st["kernel_launches"]),

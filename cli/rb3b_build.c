@@ -548,6 +548,7 @@ int main(int argc, char *argv[])
 			}
 			dpipe_release(&Q);
 		}
+		LOG("all batches merged");
 		pthread_join(tid2, 0);
 		if (Q.failed) return 1;
 		rb3b_dev_free(Q.slot[0].d); rb3b_dev_free(Q.slot[1].d);
@@ -558,6 +559,7 @@ int main(int argc, char *argv[])
 	if (fmt == 2) DIE_IF(rb3b_dump_fmr(idx, "-", max_nodes, block_len), "writing .fmr");
 	else if (fmt == 1) DIE_IF(rb3b_dump_fmd(idx, "-"), "writing .fmd");
 	else DIE_IF(rb3b_dump_plain(idx, "-"), "writing the BWT");
+	LOG("wrote the index");
 	rb3b_index_destroy(idx);
 	fprintf(stderr, "[M::main] Real time: %.3f sec; CPU: %.3f sec\n", realtime() - t_real0, cputime());
 	return 0;

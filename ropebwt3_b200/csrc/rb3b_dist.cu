@@ -30,6 +30,7 @@ struct Nccl {
 	ncclResult_t (*GroupEnd)(void);
 	const char *(*GetErrorString)(ncclResult_t);
 	ncclResult_t (*GetVersion)(int*);
+	ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*); /* optional (NCCL >= 2.18) */
 };
 
 Nccl g_nccl;
@@ -46,6 +47,7 @@ int nccl_load(void)
 	SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(AllGather); SYM(AllReduce); SYM(Send); SYM(Recv);
 	SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString); SYM(GetVersion);
 #undef SYM
+	*(void**)&g_nccl.CommSplit = dlsym(h, "ncclCommSplit");
 	g_nccl.h = h;
 	return RB3B_OK;
 }
@@ -57,8 +59,9 @@ int nccl_load(void)
 
 void rb3b_dist_release(rb3b_ctx_s *c)
 {
+	if (c->comm2 && g_nccl.h) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream2); g_nccl.CommDestroy((ncclComm_t)c->comm2); }
 	if (c->comm && g_nccl.h) { cudaSetDevice(c->device); g_nccl.CommDestroy((ncclComm_t)c->comm); }
-	c->comm = 0; c->rank = 0; c->world = 1;
+	c->comm = 0; c->comm2 = 0; c->rank = 0; c->world = 1;
 }
 
 extern "C" int rb3b_dist_unique_id(void *id128)
@@ -83,6 +86,14 @@ extern "C" int rb3b_dist_init(int rank, int world, const void *id128)
 	ncclComm_t comm;
 	NCK(g_nccl.CommInitRank(&comm, world, id, rank));
 	c->comm = comm; c->rank = rank; c->world = world;
+	/* a second communicator for the context's second stream: the exchange of the interleave positions and the merge of
+	 * batch i run there while the first stream already prepares batch i + 1 (whose shared first walk all-gathers on the
+	 * first communicator); collectives of one communicator must not overlap, those of two may */
+	if (g_nccl.CommSplit) {
+		ncclComm_t comm2 = 0;
+		NCK(g_nccl.CommSplit(comm, 0, rank, &comm2, 0));
+		c->comm2 = comm2;
+	}
 	return RB3B_OK;
 }
 
@@ -92,6 +103,9 @@ extern "C" int rb3b_dist_world(void) { return rb3b_cur()->world; }
 extern "C" int rb3b_dist_nccl_version(void) { int v = 0; if (nccl_load() != RB3B_OK) return -1; g_nccl.GetVersion(&v); return v; }
 
 /* ---- collectives on the current context's stream (used by rb3b_merge.cu) ---- */
+
+/* work queued on the second stream goes through the second communicator */
+static inline ncclComm_t cur_comm(rb3b_ctx_s *c) { return (ncclComm_t)(c->stream == c->stream2 && c->comm2 ? c->comm2 : c->comm); }
 
 int rb3b_all_gather(const void *send, void *recv, size_t bytes_per_rank)
 {
@@ -105,7 +119,7 @@ int rb3b_all_reduce_sum_u32(void *buf, size_t n)
 {
 	rb3b_ctx_s *c = rb3b_cur();
 	if (c->world == 1) return RB3B_OK;
-	NCK(g_nccl.AllReduce(buf, buf, n, ncclUint32, ncclSum, (ncclComm_t)c->comm, c->stream));
+	NCK(g_nccl.AllReduce(buf, buf, n, ncclUint32, ncclSum, cur_comm(c), c->stream));
 	return RB3B_OK;
 }
 
@@ -113,7 +127,7 @@ int rb3b_all_reduce_max_i64(void *buf, size_t n)
 {
 	rb3b_ctx_s *c = rb3b_cur();
 	if (c->world == 1) return RB3B_OK;
-	NCK(g_nccl.AllReduce(buf, buf, n, ncclInt64, ncclMax, (ncclComm_t)c->comm, c->stream));
+	NCK(g_nccl.AllReduce(buf, buf, n, ncclInt64, ncclMax, cur_comm(c), c->stream));
 	return RB3B_OK;
 }
 

@@ -129,6 +129,7 @@ struct rb3b_ctx_s {
 	cudaEvent_t ev[T_COUNT][2];
 	int ev_ok, ev_pending[T_COUNT];
 	void *comm;                       /* ncclComm_t when this context is a rank of a multi-device group (rb3b_dist.cu) */
+	void *comm2;                      /* a second communicator of the same ranks for collectives queued on stream2 (0: none) */
 	int rank, world;
 	cudaStream_t stream2;             /* asynchronous merges run here */
 	cudaEvent_t ev_hand;              /* hand-over between the two streams */

@@ -1381,7 +1381,7 @@ extern "C" int rb3b_mg_rank_part(const rb3b_index_t *x, int64_t len, const uint8
 	return incomplete ? 1 : RB3B_OK;
 }
 
-static int async_buffers(rb3b_index_s *x, int64_t len, const uint8_t *d_bwt, int64_t **ka, uint8_t **bcopy);
+static int async_buffers(rb3b_index_s *x, int64_t len, const uint8_t *d_bwt, int64_t **ka, uint8_t **bcopy, uint32_t **ka32 = 0);
 
 /* collectives of rb3b_dist.cu (NCCL on the current context's stream) */
 int rb3b_all_gather(const void *send, void *recv, size_t bytes_per_rank);
@@ -1413,7 +1413,8 @@ extern "C" int rb3b_merge_plain_dist_dev(rb3b_index_t *x, int64_t len, const uin
 	 * with 64-bit rows, or more ranks than MAX_RANKS, use the all-reduce(MAX) of partial arrays instead. */
 	const bool by_pairs = len < LF32_MAX_LEN && !rb3b_get_param("wide_lf", 0) && W <= MAX_RANKS && rb3b_get_param("dist_pairs", 0) != 0; /* off by default: measured slower than the NVLS all-reduce (N=4: 1.40 vs 0.91 + 0.40 ms scatter) */
 	const int64_t chunk = ((len + W - 1) / W + 63) / 64 * 64;
-	TRY(async_buffers(x, len, d_bwt, &aka, &bcopy));
+	uint32_t *aka32 = 0;
+	TRY(async_buffers(x, len, d_bwt, &aka, &bcopy, &aka32));
 	if (aka && (!by_pairs || chunk * W <= x->ms_rows)) { ka.p = aka; d_bwt = bcopy; } else { aka = 0; TRY(ka.alloc(by_pairs ? chunk * W : len)); }
 	TRY(flag.alloc(2 + 2 * MAX_RANKS + (size_t)W * W));
 	OwnPairs own;
@@ -1422,11 +1423,14 @@ extern "C" int rb3b_merge_plain_dist_dev(rb3b_index_t *x, int64_t len, const uin
 	 * combined by a SUM all-reduce -- half the bytes of the 64-bit MAX all-reduce */
 	const bool narrow_ka = !by_pairs && x->n + len < (1LL << 32) && rb3b_get_param("dist_ka32", 1) != 0;
 	DBuf<uint32_t> ka32;
-	if (narrow_ka) TRY(ka32.alloc(len));
+	if (narrow_ka) { if (aka) ka32.p = aka32; else TRY(ka32.alloc(len)); }
 	TRY(rank_phase(x, len, d_bwt, ka, accB, ctx->rank, ctx->world, ka.p, &incomplete, 0, by_pairs ? &own : 0, 0, narrow_ka ? ka32.p : 0));
 	ka.p = ka_full; /* with pair / 32-bit output the rank phase leaves the array alone */
 	hflag = incomplete;
-	rb3b_tic(T_COMM);
+	/* asynchronous exchange + merge: the partial arrays live in the index's own scratch, so the all-reduce and the merge are
+	 * only QUEUED on the second stream (second communicator) and the caller's next batch is prepared meanwhile */
+	const bool comm_on_2 = aka != 0 && !by_pairs && ctx->comm2 != 0;
+	if (!comm_on_2) rb3b_tic(T_COMM);
 	unsigned long long *d_cnt = (unsigned long long*)(flag.p + 2), *d_cur = d_cnt + MAX_RANKS;
 	int64_t *d_all = flag.p + 2 + 2 * MAX_RANKS;
 	CK(cudaMemcpyAsync(flag.p, &hflag, 8, cudaMemcpyHostToDevice, rb3b_stream));
@@ -1462,11 +1466,24 @@ extern "C" int rb3b_merge_plain_dist_dev(rb3b_index_t *x, int64_t len, const uin
 		if (n_recv > 0) { k_fill_dense<<<nblk(n_recv, TPB), TPB, 0, rb3b_stream>>>(n_recv, rrow.p, rval.p, row0, ka.p + row0); CKK(); }
 		TRY(rb3b_all_gather(ka.p + row0, ka.p, (size_t)chunk * 8));
 		CK(cudaStreamSynchronize(rb3b_stream)); /* the packed buffers are scratch of this call */
-	} else if (narrow_ka) {
-		TRY(rb3b_all_reduce_sum_u32(ka32.p, (size_t)len));
-		k_widen_ka<<<nblk(len, TPB), TPB, 0, rb3b_stream>>>(len, ka32.p, ka.p); CKK();
-	} else TRY(rb3b_all_reduce_max_i64(ka.p, (size_t)len)); /* rows another rank resolved are -1 here */
-	rb3b_toc(T_COMM);
+	} else {
+		cudaStream_t s1 = ctx->stream;
+		int rc = RB3B_OK;
+		if (comm_on_2) {
+			CK(cudaEventRecord(ctx->ev_hand, s1)); /* the second stream goes on where the rank phase stops */
+			CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_hand, 0));
+			ctx->stream = ctx->stream2;
+			rb3b_tic(T_COMM);
+		}
+		if (narrow_ka) {
+			rc = rb3b_all_reduce_sum_u32(ka32.p, (size_t)len);
+			if (rc == RB3B_OK) { k_widen_ka<<<nblk(len, TPB), TPB, 0, rb3b_stream>>>(len, ka32.p, ka.p); ++rb3b_n_launch; }
+		} else rc = rb3b_all_reduce_max_i64(ka.p, (size_t)len); /* rows another rank resolved are -1 here */
+		if (comm_on_2) { rb3b_toc(T_COMM); ctx->stream = s1; }
+		if (rc != RB3B_OK) return rc;
+		if (cudaGetLastError() != cudaSuccess) return rb3b_fail(RB3B_ENODEV, "launching the exchange failed");
+	}
+	if (!comm_on_2) rb3b_toc(T_COMM);
 	if (aka) TRY(merge_phase(x, len, bcopy, aka, accB));
 	else TRY(merge_phase(x, len, d_bwt, ka.p));
 	rb3b_stat_add("dist_fallbacks", fell_back);
@@ -1506,20 +1523,28 @@ extern "C" int rb3b_merge_with_ka(rb3b_index_t *x, int64_t len, const uint8_t *d
  * caller may reuse its batch buffer as soon as the call returns).  Two batch copies alternate: the merge in flight reads
  * the other one, so this one can be filled right away; the interleave array is written only after the caller's rank phase
  * has waited for that merge (rb3b_index_use). */
-static int async_buffers(rb3b_index_s *x, int64_t len, const uint8_t *d_bwt, int64_t **ka, uint8_t **bcopy)
+/* ka32 != 0 (multi-device, "dist_async"): also a 32-bit partial array -- the all-reduce of the partial arrays then runs on
+ * the second stream as well, see rb3b_merge_plain_dist_dev.  Off by default as well: at N = 2 the exchange + merge of batch i
+ * do overlap the preparation of batch i + 1, but both phases slow down by what they overlap (prep 0.80 -> 1.17 ms, merge
+ * 0.51 -> 0.83 ms, step 2.50 -> 2.53 ms; gpurun_out/r2_dist_async*_n2.json): the list ranking and the streaming merge
+ * compete for the same memory system. */
+static int async_buffers(rb3b_index_s *x, int64_t len, const uint8_t *d_bwt, int64_t **ka, uint8_t **bcopy, uint32_t **ka32)
 {
 	*ka = 0; *bcopy = 0;
-	if (x->kind != RB3B_KIND_BM || !rb3b_want_bitmap(x->n + len) || rb3b_get_param("async_merge", 0) == 0) return RB3B_OK; /* off by default: measured gain 3 % (1.573 vs 1.615 ms per merge, tools/async_probe.py) */
+	if (ka32) *ka32 = 0;
+	const bool on = ka32 ? rb3b_get_param("dist_async", 0) != 0 : rb3b_get_param("async_merge", 0) != 0; /* single device: off by default, measured gain 3 % (1.573 vs 1.615 ms per merge, tools/async_probe.py) */
+	if (x->kind != RB3B_KIND_BM || !rb3b_want_bitmap(x->n + len) || !on) return RB3B_OK;
 	const int64_t n_cells = (x->n + len + 127) >> RB3B_BM_SHIFT;
 	if (len > x->ms_rows) { /* a new layout: nothing may be in flight in the old one */
 		TRY(rb3b_index_wait_i(x));
 		x->ms_rows = len + len / 4;
 	}
-	const size_t ka_b = al512((size_t)x->ms_rows * 8), bw_b = al512((size_t)x->ms_rows);
+	const size_t ka_b = al512((size_t)x->ms_rows * 8) + al512((size_t)x->ms_rows * 4) /* one layout for both uses */, bw_b = al512((size_t)x->ms_rows);
 	const size_t tables = (size_t)(n_cells + 1) * 8 + (size_t)n_cells * 16 + 4 * (size_t)(n_cells / EMIT_TPB + 2) * RB3B_ASIZE * 8 + ((size_t)8 << 20);
 	TRY(ms_reserve(x, ka_b + 2 * bw_b + tables));
 	x->ms_used = ka_b + 2 * bw_b;
 	*ka = (int64_t*)x->ms; *bcopy = (uint8_t*)(x->ms + ka_b + (x->ms_flip ? bw_b : 0));
+	if (ka32) *ka32 = (uint32_t*)(x->ms + al512((size_t)x->ms_rows * 8));
 	x->ms_flip ^= 1;
 	CK(cudaMemcpyAsync(*bcopy, d_bwt, (size_t)len, cudaMemcpyDeviceToDevice, rb3b_stream)); /* done when the rank phase returns: it waits for the device */
 	return RB3B_OK;

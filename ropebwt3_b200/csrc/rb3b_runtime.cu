@@ -35,12 +35,16 @@ static int ctx_setup(rb3b_ctx_s *c, int device)
 	c->stream = c->my_stream = 0; c->own_stream = 0;
 	c->chunk_i = c->chunk_off = c->used = c->high = 0; c->depth = 0;
 	c->n_launch = 0; c->ev_ok = 0;
-	c->comm = 0; c->rank = 0; c->world = 1;
+	c->comm = 0; c->comm2 = 0; c->rank = 0; c->world = 1;
 	c->stream2 = 0; c->ev_hand = 0; c->bump = 0; c->bump_off = c->bump_cap = 0;
 	memset(c->ev_pending, 0, sizeof(c->ev_pending));
 	CK(cudaSetDevice(device));
-	CK(cudaStreamCreateWithFlags(&c->my_stream, cudaStreamNonBlocking));
-	CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+	/* the second stream carries the bandwidth-bound merge of batch i while the first runs the latency-bound preparation of
+	 * batch i + 1: the first gets the higher priority, so its small kernels are placed as soon as a merge CTA retires */
+	int pr_least = 0, pr_greatest = 0;
+	CK(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
+	CK(cudaStreamCreateWithPriority(&c->my_stream, cudaStreamNonBlocking, pr_greatest));
+	CK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, pr_least));
 	CK(cudaEventCreateWithFlags(&c->ev_hand, cudaEventDisableTiming));
 	c->stream = c->my_stream;
 	{
@@ -213,7 +217,7 @@ void rb3b_tflush(void)
 	for (int i = 0; i < T_COUNT; ++i)
 		if (c->ev_ok && c->ev_pending[i]) {
 			float ms = 0;
-			if (i == T_MERGE && cudaEventQuery(c->ev[i][1]) == cudaErrorNotReady) continue; /* an asynchronous merge still running: next time */
+			if ((i == T_MERGE || i == T_COMM) && cudaEventQuery(c->ev[i][1]) == cudaErrorNotReady) continue; /* an asynchronous merge (or its exchange) still running: next time */
 			cudaEventSynchronize(c->ev[i][1]);
 			if (cudaEventElapsedTime(&ms, c->ev[i][0], c->ev[i][1]) == cudaSuccess) rb3b_stat_add(g_ev_name[i], (int64_t)(ms * 1000.0f + 0.5f));
 			c->ev_pending[i] = 0;

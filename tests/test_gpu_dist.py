@@ -36,7 +36,7 @@ def _expected(rb3, gs, per):
     return idx.export_runs()
 
 
-def _proc(rank, world, port, q, pairs=0):
+def _proc(rank, world, port, q, pairs=0, dist_async=0):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
@@ -47,6 +47,7 @@ def _proc(rank, world, port, q, pairs=0):
     from ropebwt3_b200 import synth, dist as rdist
     R.init(rank)
     R.set_param("dist_pairs", pairs)   # 1: (row, position) pairs routed by all-to-all + all-gather instead of the all-reduce
+    R.set_param("dist_async", dist_async)   # 1: exchange + merge queued on the second stream / second communicator (default 0)
     rdist.init_library_comm()
     gs = _genomes()
     idx, sharded = None, []
@@ -66,8 +67,8 @@ def _proc(rank, world, port, q, pairs=0):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,pairs", [(2, 0), (2, 1), (4, 0), (4, 1)])
-def test_dist_merge_processes(rb3, world, pairs):
+@pytest.mark.parametrize("world,pairs,dist_async", [(2, 0, 0), (2, 0, 1), (2, 1, 0), (4, 0, 0), (4, 1, 0), (4, 0, 1)])
+def test_dist_merge_processes(rb3, world, pairs, dist_async):
     if _n_gpus() < world:
         pytest.skip("needs %d GPUs" % world)
     import torch.multiprocessing as mp
@@ -77,7 +78,7 @@ def test_dist_merge_processes(rb3, world, pairs):
         port = sk.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    ps = [ctx.Process(target=_proc, args=(r, world, port, q, pairs)) for r in range(world)]
+    ps = [ctx.Process(target=_proc, args=(r, world, port, q, pairs, dist_async)) for r in range(world)]
     for p in ps:
         p.start()
     res = [q.get(timeout=600) for _ in range(world)]
