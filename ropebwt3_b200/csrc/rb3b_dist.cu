@@ -86,14 +86,19 @@ extern "C" int rb3b_dist_init(int rank, int world, const void *id128)
 	ncclComm_t comm;
 	NCK(g_nccl.CommInitRank(&comm, world, id, rank));
 	c->comm = comm; c->rank = rank; c->world = world;
-	/* a second communicator for the context's second stream: the exchange of the interleave positions and the merge of
-	 * batch i run there while the first stream already prepares batch i + 1 (whose shared first walk all-gathers on the
-	 * first communicator); collectives of one communicator must not overlap, those of two may */
-	if (g_nccl.CommSplit) {
-		ncclComm_t comm2 = 0;
-		NCK(g_nccl.CommSplit(comm, 0, rank, &comm2, 0));
-		c->comm2 = comm2;
-	}
+	return RB3B_OK;
+}
+
+/* a second communicator for the context's second stream ("dist_async"): the exchange of the interleave positions and the
+ * merge of batch i run there while the first stream already prepares batch i + 1, whose shared first walk all-gathers on
+ * the first communicator; collectives of one communicator must not overlap, those of two may.  Collective: every rank
+ * calls it at the same point (the first asynchronous multi-device merge).  Failure just leaves the synchronous path. */
+int rb3b_dist_second_comm(void)
+{
+	rb3b_ctx_s *c = rb3b_cur();
+	if (c->comm2 || c->comm == 0 || g_nccl.CommSplit == 0) return RB3B_OK;
+	ncclComm_t comm2 = 0;
+	if (g_nccl.CommSplit((ncclComm_t)c->comm, 0, c->rank, &comm2, 0) == ncclSuccess) c->comm2 = comm2;
 	return RB3B_OK;
 }
 

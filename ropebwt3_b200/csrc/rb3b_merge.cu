@@ -1388,6 +1388,7 @@ int rb3b_all_gather(const void *send, void *recv, size_t bytes_per_rank);
 int rb3b_all_reduce_max_i64(void *buf, size_t n);
 int rb3b_all_reduce_sum_u32(void *buf, size_t n);
 int rb3b_all_to_all_v(const void *send, const int64_t *soff, const int64_t *scnt, void *recv, const int64_t *roff, const int64_t *rcnt);
+int rb3b_dist_second_comm(void);
 
 /* rb3_fmi_merge_plain on the ranks of the current communicator (rb3b_dist_init): every rank holds a replica of the index
  * and calls this with the same batch; rank r resolves the slices [r, r+1) * n_slices / world of walk order (plus a
@@ -1414,6 +1415,7 @@ extern "C" int rb3b_merge_plain_dist_dev(rb3b_index_t *x, int64_t len, const uin
 	const bool by_pairs = len < LF32_MAX_LEN && !rb3b_get_param("wide_lf", 0) && W <= MAX_RANKS && rb3b_get_param("dist_pairs", 0) != 0; /* off by default: measured slower than the NVLS all-reduce (N=4: 1.40 vs 0.91 + 0.40 ms scatter) */
 	const int64_t chunk = ((len + W - 1) / W + 63) / 64 * 64;
 	uint32_t *aka32 = 0;
+	if (rb3b_get_param("dist_async", 0) != 0) TRY(rb3b_dist_second_comm()); /* collective, first time only */
 	TRY(async_buffers(x, len, d_bwt, &aka, &bcopy, &aka32));
 	if (aka && (!by_pairs || chunk * W <= x->ms_rows)) { ka.p = aka; d_bwt = bcopy; } else { aka = 0; TRY(ka.alloc(by_pairs ? chunk * W : len)); }
 	TRY(flag.alloc(2 + 2 * MAX_RANKS + (size_t)W * W));
