@@ -370,13 +370,18 @@ __global__ void __launch_bounds__(EMIT_TPB) k_emit_bm(Src src, EmitOut O, int64_
  * plane -- six planes x six instructions per row -- and the source stream advances by 32 minus the rows of the word. */
 static __global__ void __launch_bounds__(EMIT_TPB) k_emit_bm_fast(const uint4 *__restrict__ A, int64_t nA, int64_t nA_cells, EmitOut O,
                                                                    const int64_t *__restrict__ ka, const uint8_t *__restrict__ bwt, const int64_t *__restrict__ ilo,
-                                                                   uint4 *__restrict__ lcnt, int64_t *__restrict__ ctot)
+                                                                   uint4 *__restrict__ lcnt, int64_t *__restrict__ ctot, int64_t lenB, int *__restrict__ bad)
 {
 	const int64_t j = (int64_t)blockIdx.x * EMIT_TPB + threadIdx.x;
 	const bool live = j < O.n_cells;
 	const int64_t P0 = j << RB3B_BM_SHIFT;
 	const int n_out = !live ? 0 : (int)(O.n_out - P0 < 128 ? O.n_out - P0 : 128);
-	const int64_t i0 = live ? ilo[j] : 0, i1 = live ? ilo[j + 1] : 0, a0 = P0 - i0;
+	int64_t i0 = live ? ilo[j] : 0, i1 = live ? ilo[j + 1] : 0, a0 = P0 - i0;
+	/* The interleave positions are validated HERE (bad != 0) instead of by a pass of their own: they are valid iff the
+	 * cells' row ranges tile [0, lenB) in order and every cell finds its rows at strictly increasing offsets inside its
+	 * own 128 positions.  Anything else sets *bad (the caller then keeps the old cells) and is made harmless. */
+	bool wrong = live && (i1 < i0 || a0 < 0 || a0 > nA || (j == 0 && i0 != 0) || (j == O.n_cells - 1 && i1 != lenB));
+	if (wrong) { i0 = i1 = 0; a0 = 0; }
 	const int64_t jA = a0 >> RB3B_BM_SHIFT;
 	const uint32_t q = ((uint32_t)a0 & 127u) >> 5, r = (uint32_t)a0 & 31u;
 	uint32_t X[RB3B_ASIZE][4], OUT[RB3B_ASIZE][4];
@@ -399,8 +404,8 @@ static __global__ void __launch_bounds__(EMIT_TPB) k_emit_bm_fast(const uint4 *_
 	}
 	/* the rows of this cell, in ascending output offset */
 	int64_t t = i0;
-	int b = 1 << 30, sym = 0; /* offset and symbol of the next row (1 << 30: none left) */
-	if (t < i1) { b = (int)(ka[t] + t - P0); sym = bwt[t]; }
+	int b = 1 << 30, sym = 0, last_b = -1; /* offset and symbol of the next row (1 << 30: none left) */
+	if (t < i1) { const int64_t bq = ka[t] + t - P0; b = bq < 0 || bq > 127 ? 128 : (int)bq; sym = bwt[t]; }
 #pragma unroll
 	for (int w = 0; w < 4; ++w) {
 		uint32_t o[RB3B_ASIZE];
@@ -413,7 +418,9 @@ static __global__ void __launch_bounds__(EMIT_TPB) k_emit_bm_fast(const uint4 *_
 #pragma unroll
 			for (int s = 0; s < RB3B_ASIZE; ++s) o[s] = (o[s] & lowm) | ((o[s] & ~lowm) << 1) | (s == sym ? bit : 0u);
 			++n_ins; ++t;
-			if (t < i1) { b = (int)(ka[t] + t - P0); sym = bwt[t]; } else b = 1 << 30;
+			wrong |= b <= last_b;
+			last_b = b;
+			if (t < i1) { const int64_t bq = ka[t] + t - P0; b = bq < 0 || bq > 127 ? 128 : (int)bq; sym = bwt[t]; } else b = 1 << 30;
 		}
 		/* positions past the end of the index hold nothing */
 		const int valid = n_out - 32 * w;
@@ -435,14 +442,17 @@ static __global__ void __launch_bounds__(EMIT_TPB) k_emit_bm_fast(const uint4 *_
 			}
 		}
 	}
+	wrong |= t < i1; /* a row that does not land in this cell */
+	if (wrong && bad) *bad = 1;
 	rb3b_bm_finish_cell(O, j, live, OUT, lcnt, ctot);
 }
 
-template<class Src> static inline bool rb3b_launch_emit_bm_fast(const Src &, const EmitOut &, int64_t, const int64_t *, const uint8_t *, const int64_t *, uint4 *, int64_t *) { return false; }
-static inline bool rb3b_launch_emit_bm_fast(const BmSrc &src, const EmitOut &O, int64_t lenB, const int64_t *d_ka, const uint8_t *d_bwt, const int64_t *d_ilo, uint4 *lcnt, int64_t *ctot)
+/* *validated = 1: the kernel checked the interleave positions itself (d_bad is set when they are not monotone) */
+template<class Src> static inline bool rb3b_launch_emit_bm_fast(const Src &, const EmitOut &, int64_t, const int64_t *, const uint8_t *, const int64_t *, uint4 *, int64_t *, int *) { return false; }
+static inline bool rb3b_launch_emit_bm_fast(const BmSrc &src, const EmitOut &O, int64_t lenB, const int64_t *d_ka, const uint8_t *d_bwt, const int64_t *d_ilo, uint4 *lcnt, int64_t *ctot, int *d_bad)
 {
 	if (lenB <= 0 || d_ilo == 0) return false;
-	k_emit_bm_fast<<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(src.R.cells, src.n, (src.n + 127) >> RB3B_BM_SHIFT, O, d_ka, d_bwt, d_ilo, lcnt, ctot);
+	k_emit_bm_fast<<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(src.R.cells, src.n, (src.n + 127) >> RB3B_BM_SHIFT, O, d_ka, d_bwt, d_ilo, lcnt, ctot, lenB, d_bad);
 	return true;
 }
 
@@ -479,11 +489,14 @@ static __global__ void k_gather_tot(const int64_t *__restrict__ ex, int64_t stri
 	if (a == RB3B_ASIZE) out[a] = flag ? *flag : 0;
 }
 
-/* d_async_flag != 0: asynchronous merge -- nothing here waits for the device; the totals the kernels counted and *d_async_flag
- * go to x->pend_host and are checked against x->pend_expect by rb3b_index_wait_i */
+/* d_flag: device word, zero on entry, set when the interleave positions turn out not to be monotone (the bitmap -> bitmap
+ * kernel validates them while it merges; every other source is validated by the caller beforehand).
+ * async: asynchronous merge -- nothing here waits for the device; the totals the kernels counted and *d_flag go to
+ * x->pend_host and are checked against x->pend_expect by rb3b_index_wait_i */
 template<class Src>
-static int rb3b_emit_build_bm(rb3b_index_s *x, Src src, int64_t n_src, int64_t lenB, const int64_t *d_ka, const uint8_t *d_bwt, const int *d_async_flag)
+static int rb3b_emit_build_bm(rb3b_index_s *x, Src src, int64_t n_src, int64_t lenB, const int64_t *d_ka, const uint8_t *d_bwt, int *d_flag, bool async = false)
 {
+	const int *d_async_flag = async ? d_flag : 0;
 	const int64_t n_out = n_src + lenB;
 	DBuf<int64_t> ilo, ctot, cex;
 	DBuf<uint4> lcnt;
@@ -498,7 +511,7 @@ static int rb3b_emit_build_bm(rb3b_index_s *x, Src src, int64_t n_src, int64_t l
 	}
 	TRY(rb3b_reserve((void**)&x->cells2, &x->cap_cells2, O.n_cells * 8, sizeof(uint4)));
 	O.cells = x->cells2; O.ovf = 0;
-	if (!rb3b_launch_emit_bm_fast(src, O, lenB, d_ka, d_bwt, lenB > 0 ? ilo.p : 0, lcnt.p, ctot.p))
+	if (!rb3b_launch_emit_bm_fast(src, O, lenB, d_ka, d_bwt, lenB > 0 ? ilo.p : 0, lcnt.p, ctot.p, d_flag))
 		k_emit_bm<Src><<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(src, O, lenB, d_ka, d_bwt, lenB > 0 ? ilo.p : 0, lcnt.p, ctot.p);
 	CKK();
 	TRY(rb3b_scan_excl_i64(ctot.p, cex.p, (O.n_chunks + 1) * RB3B_ASIZE));
@@ -506,13 +519,14 @@ static int rb3b_emit_build_bm(rb3b_index_s *x, Src src, int64_t n_src, int64_t l
 	int64_t tot[RB3B_ASIZE + 1], base[RB3B_ASIZE] = {0, 0, 0, 0, 0, 0};
 	DBuf<int64_t> gt;
 	TRY(gt.alloc(RB3B_ASIZE + 1));
-	k_gather_tot<<<1, 32, 0, rb3b_stream>>>(cex.p, O.n_chunks + 1, d_async_flag, gt.p); CKK();
+	k_gather_tot<<<1, 32, 0, rb3b_stream>>>(cex.p, O.n_chunks + 1, d_flag, gt.p); CKK();
 	if (d_async_flag) {
 		CK(cudaMemcpyAsync(x->pend_host, gt.p, sizeof(tot), cudaMemcpyDeviceToHost, rb3b_stream));
 		for (int a = 0; a < RB3B_ASIZE; ++a) tot[a] = x->pend_expect[a];
 	} else {
 		CK(cudaMemcpyAsync(tot, gt.p, sizeof(tot), cudaMemcpyDeviceToHost, rb3b_stream));
 		CK(cudaStreamSynchronize(rb3b_stream));
+		if (tot[RB3B_ASIZE]) return rb3b_fail(RB3B_EINVAL, "interleave positions are not monotone: the batch is not a valid BWT"); /* the old cells stay current */
 	}
 	{ uint4 *t = x->cells; x->cells = x->cells2; x->cells2 = t; int64_t c = x->cap_cells; x->cap_cells = x->cap_cells2; x->cap_cells2 = c; }
 	x->kind = RB3B_KIND_BM; x->shift = RB3B_BM_SHIFT; x->n_cells = O.n_cells; x->n_ovf = 0; x->n_entries = 0;

@@ -413,9 +413,18 @@ __global__ void __launch_bounds__(TPB) k_walk_first(DevIndex A, Slices S, const 
 }
 
 /* after round 1: slices whose predecessor arrived with an exact value and that have unresolved rows */
-__global__ void k_collect_first(Slices S, int64_t *__restrict__ wl_seg, int64_t *__restrict__ wl_val, unsigned long long *wl_n)
+/* nc_of != 0: also number the slices that never collapsed and hand an inexact bracket on (nc_of[s] = 0, 1, ...; -1 for all
+ * others): the ones that get a transfer table (k_fix_tables) */
+__global__ void k_collect_first(Slices S, int64_t *__restrict__ wl_seg, int64_t *__restrict__ wl_val, unsigned long long *wl_n,
+                                int32_t *__restrict__ nc_of = 0, int32_t *__restrict__ nc_list = 0, unsigned long long *nc_n = 0)
 {
 	int64_t s = S.walk_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= S.own_hi) return;
+	if (nc_of) {
+		int32_t id = -1;
+		if (S.d[s] == S.slice_len(s) && S.arr_lo[s] != S.arr_hi[s]) { id = (int32_t)atomicAdd(nc_n, 1ULL); nc_list[id] = (int32_t)(s - S.walk_lo); }
+		nc_of[s - S.walk_lo] = id;
+	}
 	if (s + 1 >= S.own_hi) return;
 	if (S.arr_lo[s] == S.arr_hi[s] && S.d[s + 1] > 0) {
 		unsigned long long o = atomicAdd(wl_n, 1ULL);
@@ -553,15 +562,17 @@ __device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
-#define FIX_TPB 32
-#define FIX_STAGES 4
+#define FIX_TPB 32      /* default threads per CTA of the fix-up ("fix_tpb": 16 or 32) */
+#define FIX_STAGES 4    /* default depth of its cp.async ring ("fix_stages": 2 or 4) */
 /* shared-memory ring of a fix-up CTA: per thread and stage eight consecutive rows of its slice (thread-interleaved so that
- * the threads of a warp hit different banks) */
+ * the threads of a warp hit different banks).  T threads x ST stages x 208 bytes: the ring, not the registers, bounds how
+ * many of these one-warp CTAs an SM holds (32 x 4: 8 CTAs; 16 x 2: 32 CTAs) */
+template<int T, int ST>
 struct FixRing {
-	uint4 m[FIX_STAGES][8][FIX_TPB];        /* transfer masks */
-	longlong2 ks[FIX_STAGES][4][FIX_TPB];   /* kseq words (low end of the bracket + flags) */
-	uint64_t sym[FIX_STAGES][FIX_TPB];
-	int64_t lo_next[FIX_STAGES][FIX_TPB];   /* kseq word of the row after the eight */
+	uint4 m[ST][8][T];        /* transfer masks */
+	longlong2 ks[ST][4][T];   /* kseq words (low end of the bracket + flags) */
+	uint64_t sym[ST][T];
+	int64_t lo_next[ST][T];   /* kseq word of the row after the eight */
 };
 
 /* fix-up for bitmap cells: one THREAD per listed slice.  The rows of a slice are consecutive in kseq / wsym / wmask / wrow,
@@ -574,13 +585,23 @@ struct FixRing {
  * (Tried and dropped: scattering the exact rows to ka[wrow[p]] from inside the walk and this kernel instead of a separate
  * pass -- the random stores compete with the walk's own dependent accesses, 0.31 -> 0.67 ms for the walk; and G = 4..32 lanes
  * per slice with the mask travelling by shuffle -- 0.53-0.61 ms against 0.27 ms for one thread per slice.) */
-__global__ void __launch_bounds__(FIX_TPB) k_fix_chain(DevIndex A, Slices S, const uint8_t *__restrict__ wsym, int64_t *__restrict__ kseq, const uint4 *__restrict__ wmask,
-                                                        int64_t n_items, const int64_t *__restrict__ wl_seg, const int64_t *__restrict__ wl_val, unsigned long long *stats,
-                                                        int cascade)
+/* the general step of a row without a mask: one random cell access (kept out of line: the chain loop stays short) */
+__device__ __noinline__ int64_t fix_wide_step(const uint4 *cells, int64_t n, int64_t tot_c, int64_t acc_c, int64_t pos, int c, int64_t lo_n)
 {
-	__shared__ FixRing R;
+	DevIndex A;
+	A.cells = cells; A.n = n; A.tot[c] = tot_c;
+	return acc_c + BmRank::rank(A, pos, c) - lo_n;
+}
+
+template<int T, int ST>
+__global__ void __launch_bounds__(T) k_fix_chain(DevIndex A, Slices S, const uint8_t *__restrict__ wsym, int64_t *__restrict__ kseq, const uint4 *__restrict__ wmask,
+                                                  int64_t n_items, const int64_t *__restrict__ wl_seg, const int64_t *__restrict__ wl_val, unsigned long long *stats,
+                                                  int cascade, const unsigned long long *__restrict__ n_items_dev)
+{
+	__shared__ FixRing<T, ST> R;
 	const int tx = threadIdx.x;
 	const int64_t it = (int64_t)blockIdx.x * blockDim.x + tx;
+	if (n_items_dev) n_items = (int64_t)*n_items_dev; /* the list was counted on the device: the grid covers an upper bound */
 	unsigned long long n_rows = 0, n_wide = 0;
 	if (it < n_items) {
 		int64_t t = wl_seg[it], v = wl_val[it];
@@ -590,47 +611,81 @@ __global__ void __launch_bounds__(FIX_TPB) k_fix_chain(DevIndex A, Slices S, con
 			 * queued its successor as an item of its own, so it must not be entered from here as well */
 			const bool was_exact = S.arr_lo[t] == S.arr_hi[t];
 			const int64_t arr = S.arr_lo[t];
-			const int nb = (int)((d + 7) >> 3);
+			const int nb = (int)((d + 7) >> 3), nd = (int)d, nl = (int)len;
 			bool ended = false;
 			n_rows += (unsigned long long)d;
 			/* blocks are fetched whole (8 rows, aligned): the buffers are padded past the last slice */
-#define FIX_ISSUE(b) do { if ((b) < nb) { const int st_ = (b) % FIX_STAGES; const int64_t p_ = base + 8 * (int64_t)(b); \
-				for (int i_ = 0; i_ < 4; ++i_) cp_async16(&R.ks[st_][i_][tx], kseq + p_ + 2 * i_); \
-				cp_async8(&R.sym[st_][tx], wsym + p_); \
-				if (wmask) for (int i_ = 0; i_ < 8; ++i_) cp_async16(&R.m[st_][i_][tx], wmask + p_ + i_); \
-				if (8 * (int64_t)(b) + 8 < len) cp_async8(&R.lo_next[st_][tx], kseq + p_ + 8); } \
+			const int64_t *ksp = kseq + base;
+			const uint8_t *syp = wsym + base;
+			const uint4 *mkp = wmask ? wmask + base : 0;
+#define FIX_ISSUE(b) do { if ((b) < nb) { const int st_ = (b) & (ST - 1); const int p_ = 8 * (b); \
+				for (int i_ = 0; i_ < 4; ++i_) cp_async16(&R.ks[st_][i_][tx], ksp + p_ + 2 * i_); \
+				cp_async8(&R.sym[st_][tx], syp + p_); \
+				if (mkp) for (int i_ = 0; i_ < 8; ++i_) cp_async16(&R.m[st_][i_][tx], mkp + p_ + i_); \
+				if (p_ + 8 < nl) cp_async8(&R.lo_next[st_][tx], ksp + p_ + 8); } \
 				cp_async_commit(); } while (0)
-			for (int b = 0; b < FIX_STAGES - 1; ++b) FIX_ISSUE(b);
+			for (int b = 0; b < ST - 1; ++b) FIX_ISSUE(b);
 			int64_t x = v - (kseq[base] & (int64_t)RB3B_M42); /* the exact value relative to the current row's low end */
 			for (int b = 0; b < nb && !ended; ++b) {
-				FIX_ISSUE(b + FIX_STAGES - 1);
-				cp_async_wait<FIX_STAGES - 1>();
-				const int st = b % FIX_STAGES;
-				const int64_t i0 = 8 * (int64_t)b;
-				int64_t ksv[9], out[8];
+				FIX_ISSUE(b + ST - 1);
+				cp_async_wait<ST - 1>();
+				const int st = b & (ST - 1);
+				const int i0 = 8 * b;
+				int64_t ksv[8];
 #pragma unroll
 				for (int i = 0; i < 4; ++i) { const longlong2 q = R.ks[st][i][tx]; ksv[2 * i] = q.x; ksv[2 * i + 1] = q.y; }
-				ksv[8] = i0 + 8 < len ? R.lo_next[st][tx] : arr;
-				const uint64_t sym = R.sym[st][tx];
+				const uint64_t sym = R.sym[st][tx] & 0x0707070707070707ULL;
+				/* rows of this block still to resolve; a sentinel symbol among them ends the chain (the next position is a
+				 * sentinel row, exact by itself): its row is the last one written */
+				int du = nd - i0 < 8 ? nd - i0 : 8;
+				const uint64_t z = (sym - 0x0101010101010101ULL) & ~sym & 0x8080808080808080ULL; /* lowest flagged byte = first zero byte */
+				const int zi = z ? (__ffsll((long long)z) - 1) >> 3 : 8;
+				if (zi < du) { du = zi + 1; ended = true; }
+				const int n_upd = ended ? du - 1 : du; /* rows after which x moves on */
+				uint4 mk[8]; /* all eight masks up front: the shared-memory latency stays off the chain */
+#pragma unroll
+				for (int u = 0; u < 8; ++u) mk[u] = R.m[st][u][tx];
+				const int64_t all_tight = ksv[0] & ksv[1] & ksv[2] & ksv[3] & ksv[4] & ksv[5] & ksv[6] & ksv[7] & KS_TIGHT;
+				if (n_upd == 8 && all_tight) {
+					/* the common block -- eight rows, all with a mask, no sentinel: straight-line code.  Only the eight
+					 * popc steps depend on each other; the positions are added up beside them */
+					uint32_t xs[9];
+					xs[0] = (uint32_t)x;
+					const int64_t any_w = ksv[0] | ksv[1] | ksv[2] | ksv[3] | ksv[4] | ksv[5] | ksv[6] | ksv[7];
+					if (((any_w >> (KS_WIDTH_SHIFT + 5)) & 3) == 0) { /* every bracket narrower than 32: x stays below 32, one word of the mask decides */
+#pragma unroll
+						for (int u = 0; u < 8; ++u) xs[u + 1] = __popc(mk[u].x & below32((int)xs[u]));
+					} else {
+#pragma unroll
+						for (int u = 0; u < 8; ++u) xs[u + 1] = mask_rank(mk[u], xs[u]);
+					}
+#pragma unroll
+					for (int u = 0; u < 8; ++u) ksv[u] = (ksv[u] & (int64_t)RB3B_M42) + (int64_t)xs[u];
+					x = (int64_t)xs[8];
+				} else
 #pragma unroll
 				for (int u = 0; u < 8; ++u) {
-					out[u] = ksv[u]; /* rows past the unresolved prefix keep what they hold */
-					if (!ended && i0 + u < d) {
-						const int c = (int)(sym >> (8 * u)) & 7;
-						const int64_t lo = ksv[u] & (int64_t)RB3B_M42, lo_n = ksv[u + 1] & (int64_t)RB3B_M42;
-						out[u] = lo + x;
-						if (c == 0) ended = true; /* the next position is a sentinel row, exact by itself */
-						else if (ksv[u] & KS_TIGHT) x = (int64_t)mask_rank(R.m[st][u][tx], (uint32_t)x);
-						else { x = A.acc[c] + BmRank::rank(A, lo + x, c) - lo_n; ++n_wide; }
+					if (u < du) {
+						const int64_t ks = ksv[u];
+						ksv[u] = (ks & (int64_t)RB3B_M42) + x;
+						if (u < n_upd) {
+							if (ks & KS_TIGHT) x = (int64_t)mask_rank(mk[u], (uint32_t)x);
+							else {
+								const int c = (int)(sym >> (8 * u)) & 7;
+								const int64_t nx = u < 7 ? ksv[u + 1] : (i0 + 8 < nl ? R.lo_next[st][tx] : arr);
+								x = fix_wide_step(A.cells, A.n, A.tot[c], A.acc[c], ksv[u], c, nx & (int64_t)RB3B_M42);
+								++n_wide;
+							}
+						}
 					}
 				}
-				if (i0 + 8 <= len) {
+				if (i0 + 8 <= nl) {
 					longlong2 *o2 = (longlong2*)(kseq + base + i0);
-					o2[0] = make_longlong2(out[0], out[1]); o2[1] = make_longlong2(out[2], out[3]);
-					o2[2] = make_longlong2(out[4], out[5]); o2[3] = make_longlong2(out[6], out[7]);
+					o2[0] = make_longlong2(ksv[0], ksv[1]); o2[1] = make_longlong2(ksv[2], ksv[3]);
+					o2[2] = make_longlong2(ksv[4], ksv[5]); o2[3] = make_longlong2(ksv[6], ksv[7]);
 				} else {
 #pragma unroll
-					for (int u = 0; u < 8; ++u) if (i0 + u < len) kseq[base + i0 + u] = out[u];
+					for (int u = 0; u < 8; ++u) if (i0 + u < nl) kseq[base + i0 + u] = ksv[u];
 				}
 			}
 			cp_async_wait<0>(); /* the ring is restarted for the next slice */
@@ -643,15 +698,31 @@ __global__ void __launch_bounds__(FIX_TPB) k_fix_chain(DevIndex A, Slices S, con
 			++t;
 		}
 	}
-	/* statistics */
+	/* statistics (all T threads of the CTA arrive here together) */
 	unsigned long long tot = n_rows, mx = n_rows;
-	for (int o = 16; o > 0; o >>= 1) {
-		n_wide += __shfl_xor_sync(0xffffffffu, n_wide, o);
-		tot += __shfl_xor_sync(0xffffffffu, tot, o);
-		const unsigned long long y = __shfl_xor_sync(0xffffffffu, mx, o);
+	const unsigned lanes = T == 32 ? 0xffffffffu : (1u << T) - 1u;
+	for (int o = T / 2; o > 0; o >>= 1) {
+		n_wide += __shfl_xor_sync(lanes, n_wide, o);
+		tot += __shfl_xor_sync(lanes, tot, o);
+		const unsigned long long y = __shfl_xor_sync(lanes, mx, o);
 		mx = y > mx ? y : mx;
 	}
-	if ((tx & 31) == 0 && tot) { atomicAdd(stats, tot); atomicAdd(stats + 1, n_wide); atomicMax(stats + 2, mx); }
+	if (tx == 0 && tot) { atomicAdd(stats, tot); atomicAdd(stats + 1, n_wide); atomicMax(stats + 2, mx); }
+}
+
+/* fix_tpb x fix_stages: 32 x 4 (eight one-warp CTAs per SM) or fewer threads / stages per CTA, i.e. more warps per scheduler
+ * to cover the latency of the dependent chain */
+static int launch_fix_chain(const DevIndex &dA, const Slices &S, const uint8_t *wsym, int64_t *kseq, const uint4 *wmask, int64_t n_items,
+                            const int64_t *wl_seg, const int64_t *wl_val, unsigned long long *stats, int cascade, const unsigned long long *n_items_dev = 0)
+{
+	const int tpb = rb3b_get_param("fix_tpb", FIX_TPB) == 16 ? 16 : 32, st = rb3b_get_param("fix_stages", FIX_STAGES) == 2 ? 2 : 4;
+	const unsigned grid = (unsigned)((n_items + tpb - 1) / tpb);
+	if (tpb == 32 && st == 4) k_fix_chain<32, 4><<<grid, 32, 0, rb3b_stream>>>(dA, S, wsym, kseq, wmask, n_items, wl_seg, wl_val, stats, cascade, n_items_dev);
+	else if (tpb == 32) k_fix_chain<32, 2><<<grid, 32, 0, rb3b_stream>>>(dA, S, wsym, kseq, wmask, n_items, wl_seg, wl_val, stats, cascade, n_items_dev);
+	else if (st == 4) k_fix_chain<16, 4><<<grid, 16, 0, rb3b_stream>>>(dA, S, wsym, kseq, wmask, n_items, wl_seg, wl_val, stats, cascade, n_items_dev);
+	else k_fix_chain<16, 2><<<grid, 16, 0, rb3b_stream>>>(dA, S, wsym, kseq, wmask, n_items, wl_seg, wl_val, stats, cascade, n_items_dev);
+	CKK();
+	return RB3B_OK;
 }
 
 /* ---- cascades without the chain: transfer tables of the slices that never collapsed ----
@@ -662,32 +733,46 @@ __global__ void __launch_bounds__(FIX_TPB) k_fix_chain(DevIndex A, Slices S, con
  * follows every cascade through the tables (one lookup per slice instead of one chain step per row) and lists every slice
  * with the exact value it starts from; k_fix_chain resolves all listed slices at once, no slice waiting for another.  The
  * longest dependent chain of the fix-up drops from the longest cascade (thousands of rows) to one slice. */
-__global__ void __launch_bounds__(128) k_fix_tables(Slices S, const int64_t *__restrict__ kseq, const uint4 *__restrict__ wmask, uint8_t *__restrict__ tab, uint8_t *__restrict__ tab_ok)
+__global__ void __launch_bounds__(128) k_fix_tables(Slices S, const int64_t *__restrict__ kseq, const uint4 *__restrict__ wmask, int64_t n_nc, const int32_t *__restrict__ nc_list,
+                                                      uint8_t *__restrict__ tab, uint8_t *__restrict__ tab_ok)
 {
+	/* one warp per (listed slice, block of 32 arguments); the rows' masks are fetched 32 rows at a time (one row per lane,
+	 * coalesced) and handed round by shuffle, so the chain never waits for memory */
 	const int64_t W = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const int lane = threadIdx.x & 31, cb = (int)(W & 3);
-	const int64_t s = S.walk_lo + (W >> 2);
-	if (s >= S.own_hi) return; /* warp-uniform */
+	if ((W >> 2) >= n_nc) return; /* warp-uniform */
+	const int64_t id = W >> 2, s = S.walk_lo + nc_list[id];
 	const int64_t len = S.slice_len(s), base = s * S.seg_len;
-	if (S.d[s] != len || S.arr_lo[s] == S.arr_hi[s]) return; /* collapsed inside, or exact on its last row: nothing to hand on */
-	const int64_t ks0 = kseq[base];
-	if (!(ks0 & KS_TIGHT)) { if (cb == 0 && lane == 0) tab_ok[s] = 0; return; }
+	const int64_t ks0 = __ldg(kseq + base);
+	if (!(ks0 & KS_TIGHT)) { if (cb == 0 && lane == 0) tab_ok[id] = 0; return; }
 	const int w0 = (int)(ks0 >> KS_WIDTH_SHIFT) & 127;
 	if (cb * 32 > w0) return;
 	uint32_t x = (uint32_t)(cb * 32 + lane);
 	bool ok = true;
-	for (int64_t u = 0; u < len; ++u) {
-		const int64_t ks = __ldg(kseq + base + u); /* the same address on every lane */
-		if (!(ks & KS_TIGHT)) { ok = false; break; }
-		x = mask_rank(__ldg(wmask + base + u), x);
+	for (int64_t u0 = 0; u0 < len && ok; u0 += 32) {
+		const int64_t r = u0 + lane;
+		const bool have = r < len;
+		const int64_t ks = have ? __ldg(kseq + base + r) : (int64_t)KS_TIGHT;
+		const uint4 m = have ? __ldg(wmask + base + r) : make_uint4(0, 0, 0, 0);
+		const unsigned loose = __ballot_sync(0xffffffffu, !(ks & KS_TIGHT));
+		int n = len - u0 < 32 ? (int)(len - u0) : 32;
+		if (loose) { ok = false; n = 0; } /* a row without a mask: the general fix-up handles this cascade */
+		for (int j = 0; j < n; ++j) {
+			uint4 mj;
+			mj.x = __shfl_sync(0xffffffffu, m.x, j); mj.y = __shfl_sync(0xffffffffu, m.y, j);
+			mj.z = __shfl_sync(0xffffffffu, m.z, j); mj.w = __shfl_sync(0xffffffffu, m.w, j);
+			x = mask_rank(mj, x);
+		}
 	}
-	if (ok) tab[s * 128 + cb * 32 + lane] = (uint8_t)x;
-	if (cb == 0 && lane == 0) tab_ok[s] = ok ? 1 : 0;
+	if (ok) tab[id * 128 + cb * 32 + lane] = (uint8_t)x;
+	if (cb == 0 && lane == 0) tab_ok[id] = ok ? 1 : 0;
 }
 
-__global__ void k_fix_hops(Slices S, const int64_t *__restrict__ kseq, const uint8_t *__restrict__ tab, const uint8_t *__restrict__ tab_ok,
+/* follow every cascade through the tables: one lookup per slice.  Every slice met is listed with the exact value it starts
+ * from.  n_stop counts cascades that ran into a slice without a table (left to the general fix-up). */
+__global__ void k_fix_hops(Slices S, const int64_t *__restrict__ kseq, const int32_t *__restrict__ nc_of, const uint8_t *__restrict__ tab, const uint8_t *__restrict__ tab_ok,
                            int64_t n_items, const int64_t *__restrict__ wl_seg, const int64_t *__restrict__ wl_val,
-                           int64_t *__restrict__ out_seg, int64_t *__restrict__ out_val, unsigned long long *out_n)
+                           int64_t *__restrict__ out_seg, int64_t *__restrict__ out_val, unsigned long long *out_n, unsigned long long *n_stop)
 {
 	const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (it >= n_items) return;
@@ -695,11 +780,12 @@ __global__ void k_fix_hops(Slices S, const int64_t *__restrict__ kseq, const uin
 	for (;;) {
 		const unsigned long long o = atomicAdd(out_n, 1ULL);
 		out_seg[o] = t; out_val[o] = v;
-		if (S.d[t] != S.slice_len(t) || S.arr_lo[t] == S.arr_hi[t]) break; /* collapses inside / its successor is an item of its own */
-		if (!tab_ok[t]) break; /* a row without a mask: the general fix-up carries on from here afterwards */
+		const int32_t id = nc_of[t - S.walk_lo];
+		if (id < 0) break; /* collapses inside, or hands an exact value on: its successor is an item of its own */
+		if (!tab_ok[id]) { atomicAdd(n_stop, 1ULL); break; } /* a row without a mask: the general fix-up carries on from here afterwards */
 		const int64_t x = v - (kseq[t * S.seg_len] & (int64_t)RB3B_M42);
-		if (x < 0 || x > TIGHT_WIDTH) break; /* cannot happen for a valid batch */
-		v = S.arr_lo[t] + (int64_t)tab[t * 128 + x];
+		if (x < 0 || x > TIGHT_WIDTH) { atomicAdd(n_stop, 1ULL); break; } /* cannot happen for a valid batch */
+		v = S.arr_lo[t] + (int64_t)tab[(int64_t)id * 128 + x];
 		++t;
 		if (t >= S.own_hi || S.d[t] == 0) break;
 	}
@@ -1040,39 +1126,66 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	CKK();
 	rb3b_toc(T_WALK1);
 	int64_t *wl_seg[2] = { wl.p, wl.p + 2 * S.n_seg }, *wl_val[2] = { wl.p + S.n_seg, wl.p + 3 * S.n_seg };
-	k_collect_first<<<nblk(n_walk > 0 ? n_walk : 1, TPB), TPB, 0, rb3b_stream>>>(S, wl_seg[0], wl_val[0], (unsigned long long*)(ctr.p + 1)); CKK();
-	int64_t n_items = 0, rounds = 1, fix_items = 0;
-	CK(cudaMemcpyAsync(&n_items, ctr.p + 1, 8, cudaMemcpyDeviceToHost, rb3b_stream));
-	CK(cudaStreamSynchronize(rb3b_stream));
+	const bool use_tab = use_log && use_mask && !so && rb3b_get_param("fix_tables", 0) != 0;
+	DBuf<int32_t> nc; /* nc_of[n_walk], nc_list[n_walk] */
+	if (use_tab) TRY(nc.alloc((size_t)(n_walk > 0 ? n_walk : 1) * 2));
+	k_collect_first<<<nblk(n_walk > 0 ? n_walk : 1, TPB), TPB, 0, rb3b_stream>>>(S, wl_seg[0], wl_val[0], (unsigned long long*)(ctr.p + 1),
+		use_tab ? nc.p : 0, use_tab ? nc.p + n_walk : 0, (unsigned long long*)(ctr.p + 10)); CKK();
+	int64_t n_items = 0, rounds = 1, fix_items = 0, cnt2[2] = {0, 0};
 	int cur = 0;
-	if (n_items > 0 && use_log && use_mask && !so && rb3b_get_param("fix_tables", 0) != 0) {
-		/* cascades through transfer tables: every slice with unresolved rows gets its exact start, then all are resolved
-		 * at once; whatever is left (a row without a mask somewhere) goes through the cascading loop below.
-		 * Off by default: the longest dependent chain drops from ~2150 to 192 rows, but evaluating 128 arguments for every
-		 * slice that never collapsed costs more than the cascades it removes (fix-up 0.39 vs 0.26 ms with one genome per
-		 * merge, 1.16 vs 0.67 ms with ten; gpurun_out/r2_sweep_tables_*.json). */
-		DBuf<uint8_t> tab, tab_ok;
-		TRY(tab.alloc((size_t)S.n_seg * 128)); TRY(tab_ok.alloc(S.n_seg));
-		CK(cudaMemsetAsync(ctr.p + 2, 0, 40, rb3b_stream));
-		CK(cudaMemsetAsync(ctr.p + 9, 0, 8, rb3b_stream));
+	if (use_log && !use_tab && n_walk > 0) {
+		/* the chain fix-up resolves every cascade in ONE launch, so it needs no list size on the host: the grid covers the
+		 * upper bound (every slice on the list) and the kernel reads the count the collection left on the device.  One
+		 * read-back per rank phase less. */
 		rb3b_tic(T_WALKFIX);
-		k_fix_tables<<<nblk(n_walk * 4 * 32, 128), 128, 0, rb3b_stream>>>(S, kseq.p, wmask.p, tab.p, tab_ok.p); CKK();
-		k_fix_hops<<<nblk(n_items, TPB), TPB, 0, rb3b_stream>>>(S, kseq.p, tab.p, tab_ok.p, n_items, wl_seg[0], wl_val[0], wl_seg[1], wl_val[1], (unsigned long long*)(ctr.p + 9)); CKK();
-		int64_t n2 = 0;
-		CK(cudaMemcpyAsync(&n2, ctr.p + 9, 8, cudaMemcpyDeviceToHost, rb3b_stream));
-		CK(cudaStreamSynchronize(rb3b_stream));
-		if (n2 > 0) { k_fix_chain<<<nblk(n2, FIX_TPB), FIX_TPB, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, wmask.p, n2, wl_seg[1], wl_val[1], (unsigned long long*)(ctr.p + 4), 0); CKK(); }
+		TRY(launch_fix_chain(dA, S, wsym.p, kseq.p, use_mask ? wmask.p : 0, n_walk, wl_seg[0], wl_val[0], (unsigned long long*)(ctr.p + 4), 1, (const unsigned long long*)(ctr.p + 1)));
 		rb3b_toc(T_WALKFIX);
-		fix_items += n2;
-		/* leftovers */
-		CK(cudaMemsetAsync(ctr.p + 1, 0, 8, rb3b_stream));
-		k_collect_first<<<nblk(n_walk > 0 ? n_walk : 1, TPB), TPB, 0, rb3b_stream>>>(S, wl_seg[0], wl_val[0], (unsigned long long*)(ctr.p + 1)); CKK();
 		int64_t fst[4] = {0, 0, 0, 0};
 		CK(cudaMemcpyAsync(&n_items, ctr.p + 1, 8, cudaMemcpyDeviceToHost, rb3b_stream));
 		CK(cudaMemcpyAsync(fst + 1, ctr.p + 4, 24, cudaMemcpyDeviceToHost, rb3b_stream));
 		CK(cudaStreamSynchronize(rb3b_stream));
 		rb3b_stat_set("fix_rows", fst[1]); rb3b_stat_set("fix_wide_rows", fst[2]); rb3b_stat_set("fix_longest_chain", fst[3]);
-		rb3b_stat_set("fix_table_slices", n2); rb3b_stat_set("fix_leftover_items", n_items);
+		rb3b_tflush();
+		fix_items += n_items;
+		if (n_items > 0) ++rounds;
+		n_items = 0; /* nothing is ever left for a second round */
+	} else {
+		CK(cudaMemcpyAsync(&n_items, ctr.p + 1, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+		CK(cudaMemcpyAsync(cnt2, ctr.p + 10, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+		CK(cudaStreamSynchronize(rb3b_stream));
+	}
+	const int64_t n_nc = cnt2[0];
+	if (n_items > 0 && use_tab && n_nc > 0) {
+		/* cascades through transfer tables (above k_fix_tables): every slice with unresolved rows gets its exact start, then
+		 * all are resolved at once -- the longest dependent chain is one slice instead of the longest cascade.  Whatever is
+		 * left (a cascade through a row without a mask) goes through the cascading loop below. */
+		DBuf<uint8_t> tab, tab_ok;
+		TRY(tab.alloc((size_t)n_nc * 128)); TRY(tab_ok.alloc(n_nc));
+		CK(cudaMemsetAsync(ctr.p + 2, 0, 40, rb3b_stream));
+		CK(cudaMemsetAsync(ctr.p + 9, 0, 8, rb3b_stream));
+		CK(cudaMemsetAsync(ctr.p + 11, 0, 8, rb3b_stream));
+		rb3b_tic(T_WALKFIX);
+		k_fix_tables<<<nblk(n_nc * 4 * 32, 128), 128, 0, rb3b_stream>>>(S, kseq.p, wmask.p, n_nc, nc.p + n_walk, tab.p, tab_ok.p); CKK();
+		k_fix_hops<<<nblk(n_items, TPB), TPB, 0, rb3b_stream>>>(S, kseq.p, nc.p, tab.p, tab_ok.p, n_items, wl_seg[0], wl_val[0], wl_seg[1], wl_val[1],
+			(unsigned long long*)(ctr.p + 9), (unsigned long long*)(ctr.p + 11)); CKK();
+		int64_t n2 = 0, n_stop = 0;
+		CK(cudaMemcpyAsync(&n2, ctr.p + 9, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+		CK(cudaMemcpyAsync(&n_stop, ctr.p + 11, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+		CK(cudaStreamSynchronize(rb3b_stream));
+		if (n2 > 0) TRY(launch_fix_chain(dA, S, wsym.p, kseq.p, wmask.p, n2, wl_seg[1], wl_val[1], (unsigned long long*)(ctr.p + 4), 0));
+		rb3b_toc(T_WALKFIX);
+		fix_items += n2;
+		n_items = 0;
+		int64_t fst[4] = {0, 0, 0, 0};
+		if (n_stop > 0) { /* leftovers: slices behind a cascade that stopped at a slice without a table */
+			CK(cudaMemsetAsync(ctr.p + 1, 0, 8, rb3b_stream));
+			k_collect_first<<<nblk(n_walk > 0 ? n_walk : 1, TPB), TPB, 0, rb3b_stream>>>(S, wl_seg[0], wl_val[0], (unsigned long long*)(ctr.p + 1)); CKK();
+			CK(cudaMemcpyAsync(&n_items, ctr.p + 1, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+		}
+		CK(cudaMemcpyAsync(fst + 1, ctr.p + 4, 24, cudaMemcpyDeviceToHost, rb3b_stream));
+		CK(cudaStreamSynchronize(rb3b_stream));
+		rb3b_stat_set("fix_rows", fst[1]); rb3b_stat_set("fix_wide_rows", fst[2]); rb3b_stat_set("fix_longest_chain", fst[3]);
+		rb3b_stat_set("fix_table_slices", n_nc); rb3b_stat_set("fix_leftover_items", n_items);
 		rb3b_tflush();
 		++rounds;
 	}
@@ -1081,8 +1194,7 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 		CK(cudaMemsetAsync(ctr.p + 2, 0, 40, rb3b_stream));
 		want = (n_items * wg + wtpb - 1) / wtpb;
 		rb3b_tic(T_WALKFIX);
-		if (use_log) k_fix_chain<<<nblk(n_items, FIX_TPB), FIX_TPB, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, use_mask ? wmask.p : 0, n_items, wl_seg[cur], wl_val[cur],
-			(unsigned long long*)(ctr.p + 4), 1);
+		if (use_log) { TRY(launch_fix_chain(dA, S, wsym.p, kseq.p, use_mask ? wmask.p : 0, n_items, wl_seg[cur], wl_val[cur], (unsigned long long*)(ctr.p + 4), 1)); --rb3b_n_launch; }
 		else if (bm) k_walk_fix<BmRank><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, n_items, wl_seg[cur], wl_val[cur], ctr.p + 2,
 			wl_seg[cur ^ 1], wl_val[cur ^ 1], (unsigned long long*)(ctr.p + 3));
 		else k_walk_fix<Grp<8> ><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, n_items, wl_seg[cur], wl_val[cur], ctr.p + 2,
@@ -1293,11 +1405,10 @@ static int merge_phase(rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, const
 			if ((rc = bad.alloc(1)) != RB3B_OK) break;
 			if (cudaMemsetAsync(bad.p, 0, sizeof(int), rb3b_stream) != cudaSuccess) { rc = rb3b_fail(RB3B_ENODEV, "cudaMemsetAsync failed"); break; }
 			rb3b_tic(T_MERGE);
-			k_check_monotone<<<nblk(len, TPB), TPB, 0, rb3b_stream>>>(len, d_ka, A->n, bad.p); ++rb3b_n_launch;
 			BmSrc src;
 			src.R.cells = A->cells; src.R.n = A->n; src.R.pos = 0; src.R.cur = -1; src.R.rem = 0;
 			src.n = A->n; src.cur = -1;
-			rc = rb3b_emit_build_bm(A, src, A->n, len, d_ka, d_bwt, bad.p);
+			rc = rb3b_emit_build_bm(A, src, A->n, len, d_ka, d_bwt, bad.p, true); /* validates the positions while it merges */
 			rb3b_toc(T_MERGE);
 			cudaEventRecord(A->ready_ev, rb3b_stream);
 		} while (0);
@@ -1312,16 +1423,19 @@ static int merge_phase(rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, const
 	TRY(bad.alloc(1));
 	CK(cudaMemsetAsync(bad.p, 0, sizeof(int), rb3b_stream));
 	rb3b_tic(T_MERGE);
-	k_check_monotone<<<nblk(len, TPB), TPB, 0, rb3b_stream>>>(len, d_ka, A->n, bad.p); CKK();
-	CK(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, rb3b_stream));
-	CK(cudaStreamSynchronize(rb3b_stream));
-	if (hbad) return rb3b_fail(RB3B_EINVAL, "interleave positions are not monotone: the batch is not a valid BWT");
+	const bool fused_check = A->kind == RB3B_KIND_BM && rb3b_want_bitmap(A->n + len); /* the bitmap -> bitmap kernel validates the positions itself */
+	if (!fused_check) {
+		k_check_monotone<<<nblk(len, TPB), TPB, 0, rb3b_stream>>>(len, d_ka, A->n, bad.p); CKK();
+		CK(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, rb3b_stream));
+		CK(cudaStreamSynchronize(rb3b_stream));
+		if (hbad) return rb3b_fail(RB3B_EINVAL, "interleave positions are not monotone: the batch is not a valid BWT");
+	}
 	int rc;
 	if (A->kind == RB3B_KIND_BM) {
 		BmSrc src;
 		src.R.cells = A->cells; src.R.n = A->n; src.R.pos = 0; src.R.cur = -1; src.R.rem = 0;
 		src.n = A->n; src.cur = -1;
-		if (rb3b_want_bitmap(A->n + len)) rc = rb3b_emit_build_bm(A, src, A->n, len, d_ka, d_bwt, 0);
+		if (rb3b_want_bitmap(A->n + len)) rc = rb3b_emit_build_bm(A, src, A->n, len, d_ka, d_bwt, bad.p);
 		else rc = rb3b_emit_build(A, src, A->n, len, d_ka, d_bwt, (A->n + len) / 16); /* outgrew 1 B/symbol: switch to RLE cells */
 	} else {
 		CellSrc src;
