@@ -526,7 +526,7 @@ static int rb3b_emit_build_bm(rb3b_index_s *x, Src src, int64_t n_src, int64_t l
 	} else {
 		CK(cudaMemcpyAsync(tot, gt.p, sizeof(tot), cudaMemcpyDeviceToHost, rb3b_stream));
 		CK(cudaStreamSynchronize(rb3b_stream));
-		if (tot[RB3B_ASIZE]) return rb3b_fail(RB3B_EINVAL, "interleave positions are not monotone: the batch is not a valid BWT"); /* the old cells stay current */
+		if (tot[RB3B_ASIZE]) return rb3b_fail(RB3B_EINVAL, "interleave positions are not monotone or not all resolved: the batch is not a valid BWT"); /* the old cells stay current */
 	}
 	{ uint4 *t = x->cells; x->cells = x->cells2; x->cells2 = t; int64_t c = x->cap_cells; x->cap_cells = x->cap_cells2; x->cap_cells2 = c; }
 	x->kind = RB3B_KIND_BM; x->shift = RB3B_BM_SHIFT; x->n_cells = O.n_cells; x->n_ovf = 0; x->n_entries = 0;

@@ -1010,7 +1010,9 @@ struct OwnPairs { const uint32_t *rows; const int64_t *vals; int64_t n; };
  * chase, no list ranking; d_bwt is not read. */
 static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, DBuf<int64_t> &ka, int64_t accB[RB3B_ASIZE + 1],
                       int part = 0, int n_parts = 1, int64_t *ka_out = 0, int *incomplete = 0, int so = 0, OwnPairs *pairs = 0,
-                      const rb3b_batch_s *pre = 0, uint32_t *ka32 = 0 /* multi-device: 32-bit partial array (0 = nobody's), every position fits */)
+                      const rb3b_batch_s *pre = 0, uint32_t *ka32 = 0 /* multi-device: 32-bit partial array (0 = nobody's), every position fits */,
+                      const unsigned long long **defer_unres = 0 /* single device: leave the count of unresolved rows on the device (arena memory)
+                                                                    for the merge to check with its own read-back, instead of waiting for it here */)
 {
 	int64_t nt = (len + PREP_TILE - 1) / PREP_TILE;
 	DBuf<int64_t> tcnt, tex;
@@ -1224,16 +1226,20 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	else if (narrow_lf) TRY((scatter_to_rows<uint32_t, int64_t>(own_rows, len, (const uint32_t*)wrow + own_p0, kseq.p + own_p0, ka.p, (unsigned long long*)(ctr.p + 8))));
 	else TRY((scatter_to_rows<int64_t, int64_t>(own_rows, len, (const int64_t*)wrow + own_p0, kseq.p + own_p0, ka.p, (unsigned long long*)(ctr.p + 8))));
 	rb3b_toc(T_SCATTER);
-	CK(cudaMemcpyAsync(&unres, ctr.p + 8, 8, cudaMemcpyDeviceToHost, rb3b_stream));
-	CK(cudaStreamSynchronize(rb3b_stream));
-	rb3b_tflush();
+	const bool deferred = defer_unres != 0 && n_parts == 1;
+	if (deferred) *defer_unres = (const unsigned long long*)(ctr.p + 8);
+	else {
+		CK(cudaMemcpyAsync(&unres, ctr.p + 8, 8, cudaMemcpyDeviceToHost, rb3b_stream));
+		CK(cudaStreamSynchronize(rb3b_stream));
+		rb3b_tflush();
+	}
 	rb3b_stat_set("n_segments", S.n_seg);
 	rb3b_stat_set("seg_len_used", seg_len);
 	rb3b_stat_set("n_fine", F.n_fine);
 	rb3b_stat_set("fix_rounds", rounds - 1);
 	rb3b_stat_add("fix_rounds_total", rounds - 1);
 	rb3b_stat_set("fix_segments", fix_items);
-	rb3b_stat_set("unresolved_rows", (int64_t)unres);
+	rb3b_stat_set("unresolved_rows", deferred ? -1 : (int64_t)unres);
 	rb3b_stat_set("own_segments", S.own_hi - S.own_lo);
 	rb3b_stat_set("own_rows", own_rows);
 	if (n_parts > 1) { /* completeness of the whole batch is checked after the exchange */
@@ -1386,7 +1392,11 @@ static inline size_t al512(size_t b) { return (b + 511) & ~(size_t)511; }
  * only QUEUED, on the context's second stream; d_ka and d_bwt must then lie in A->ms (first A->ms_used bytes) and the
  * merge's own tables are taken from the rest of A->ms.  The caller's next call overlaps with it up to the point where it
  * needs the merged cells (rb3b_index_use); errors the device finds are reported by rb3b_index_wait_i. */
-static int merge_phase(rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, const int64_t *d_ka, const int64_t *accB = 0)
+__global__ void k_flag_if(const unsigned long long *__restrict__ cnt, int *__restrict__ flag) { if (*cnt) *flag = 1; }
+
+/* d_unres != 0: the rank phase left its count of unresolved rows on the device; non-zero = the batch is not a valid BWT,
+ * reported with the merge's own validation */
+static int merge_phase(rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, const int64_t *d_ka, const int64_t *accB = 0, const unsigned long long *d_unres = 0)
 {
 	if (accB != 0 && A->kind == RB3B_KIND_BM && rb3b_want_bitmap(A->n + len) && (const char*)d_ka == A->ms) {
 		rb3b_ctx_s *ctx = rb3b_cur();
@@ -1405,6 +1415,7 @@ static int merge_phase(rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, const
 			if ((rc = bad.alloc(1)) != RB3B_OK) break;
 			if (cudaMemsetAsync(bad.p, 0, sizeof(int), rb3b_stream) != cudaSuccess) { rc = rb3b_fail(RB3B_ENODEV, "cudaMemsetAsync failed"); break; }
 			rb3b_tic(T_MERGE);
+			if (d_unres) { k_flag_if<<<1, 1, 0, rb3b_stream>>>(d_unres, bad.p); ++rb3b_n_launch; }
 			BmSrc src;
 			src.R.cells = A->cells; src.R.n = A->n; src.R.pos = 0; src.R.cur = -1; src.R.rem = 0;
 			src.n = A->n; src.cur = -1;
@@ -1424,11 +1435,12 @@ static int merge_phase(rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, const
 	CK(cudaMemsetAsync(bad.p, 0, sizeof(int), rb3b_stream));
 	rb3b_tic(T_MERGE);
 	const bool fused_check = A->kind == RB3B_KIND_BM && rb3b_want_bitmap(A->n + len); /* the bitmap -> bitmap kernel validates the positions itself */
+	if (d_unres) { k_flag_if<<<1, 1, 0, rb3b_stream>>>(d_unres, bad.p); CKK(); }
 	if (!fused_check) {
 		k_check_monotone<<<nblk(len, TPB), TPB, 0, rb3b_stream>>>(len, d_ka, A->n, bad.p); CKK();
 		CK(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, rb3b_stream));
 		CK(cudaStreamSynchronize(rb3b_stream));
-		if (hbad) return rb3b_fail(RB3B_EINVAL, "interleave positions are not monotone: the batch is not a valid BWT");
+		if (hbad) return rb3b_fail(RB3B_EINVAL, "interleave positions are not monotone or not all resolved: the batch is not a valid BWT");
 	}
 	int rc;
 	if (A->kind == RB3B_KIND_BM) {
@@ -1676,12 +1688,13 @@ extern "C" int rb3b_merge_plain_dev(rb3b_index_t *x, int64_t len, const uint8_t 
 	int64_t accB[RB3B_ASIZE + 1], *aka;
 	uint8_t *bcopy;
 	TRY(async_buffers(x, len, d_bwt, &aka, &bcopy));
+	const unsigned long long *d_unres = 0;
 	if (aka) {
-		TRY(rank_phase(x, len, bcopy, ka, accB, 0, 1, aka));
-		return merge_phase(x, len, bcopy, aka, accB);
+		TRY(rank_phase(x, len, bcopy, ka, accB, 0, 1, aka, 0, 0, 0, 0, 0, &d_unres));
+		return merge_phase(x, len, bcopy, aka, accB, d_unres);
 	}
-	TRY(rank_phase(x, len, d_bwt, ka, accB));
-	return merge_phase(x, len, d_bwt, ka.p);
+	TRY(rank_phase(x, len, d_bwt, ka, accB, 0, 1, 0, 0, 0, 0, 0, 0, &d_unres));
+	return merge_phase(x, len, d_bwt, ka.p, 0, d_unres);
 }
 
 /* rb3_fmi_merge_plain / rb3_enc_plain2fmr on a batch prepared by rb3b_batch_prepare* (rb3b_bwt.cu): the walk order comes with
@@ -1695,8 +1708,9 @@ extern "C" int rb3b_merge_prepared(rb3b_index_t *x, const rb3b_batch_t *b)
 	if (b->wsym == 0) return rb3b_merge_plain_dev(x, b->len, b->bwt); /* very large batch: only its BWT was prepared */
 	DBuf<int64_t> ka;
 	int64_t accB[RB3B_ASIZE + 1];
-	TRY(rank_phase(x, b->len, b->bwt, ka, accB, 0, 1, 0, 0, 0, 0, b));
-	return merge_phase(x, b->len, b->bwt, ka.p);
+	const unsigned long long *d_unres = 0;
+	TRY(rank_phase(x, b->len, b->bwt, ka, accB, 0, 1, 0, 0, 0, 0, b, 0, &d_unres));
+	return merge_phase(x, b->len, b->bwt, ka.p, 0, d_unres);
 }
 
 /* mr_insert_multi (mrope.c:300-385; build -2/-s/-r, build.c:214-218): insert the strings of `text` (concatenated,
