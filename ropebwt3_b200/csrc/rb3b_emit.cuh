@@ -300,6 +300,7 @@ static int rb3b_emit_build(rb3b_index_s *x, Src src, int64_t n_src, int64_t lenB
  * written once; quad 0 temporarily receives the cell's own six symbol counts (6 x u16), which k_bm_fin_* turn into
  * the absolute header counts with a two-level scan. */
 /* common tail of the bitmap emit kernels: write the planes, the compact per-cell counts and the chunk totals */
+template<bool STORE = true>
 __device__ __forceinline__ void rb3b_bm_finish_cell(const EmitOut &O, int64_t j, bool live, uint32_t (&pl)[RB3B_ASIZE][4], uint4 *__restrict__ lcnt, int64_t *__restrict__ ctot)
 {
 	typedef cub::BlockReduce<uint32_t, EMIT_TPB> Red;
@@ -308,7 +309,7 @@ __device__ __forceinline__ void rb3b_bm_finish_cell(const EmitOut &O, int64_t j,
 #pragma unroll
 	for (int a = 0; a < RB3B_ASIZE; ++a) {
 		c[a] = live ? __popc(pl[a][0]) + __popc(pl[a][1]) + __popc(pl[a][2]) + __popc(pl[a][3]) : 0u;
-		if (live) O.cells[j * 8 + rb3b_bm_plane_quad(a)] = make_uint4(pl[a][0], pl[a][1], pl[a][2], pl[a][3]);
+		if (STORE && live) O.cells[j * 8 + rb3b_bm_plane_quad(a)] = make_uint4(pl[a][0], pl[a][1], pl[a][2], pl[a][3]);
 	}
 	if (live) lcnt[j] = make_uint4(c[0] | c[1] << 16, c[2] | c[3] << 16, c[4] | c[5] << 16, 0u);
 #pragma unroll
@@ -368,6 +369,14 @@ __global__ void __launch_bounds__(EMIT_TPB) k_emit_bm(Src src, EmitOut O, int64_
  * into that stream (a software PDEP): the cell is produced one 32-bit word at a time; a word starts as the next 32 source
  * bits of every plane, every row landing in it (ascending offsets) opens a gap at its bit and sets the bit in its symbol's
  * plane -- six planes x six instructions per row -- and the source stream advances by 32 minus the rows of the word. */
+#define EMIT_SRC_CELLS (EMIT_TPB + 4) /* source cells a CTA can touch: its 128 output cells start inside at most 129 consecutive source cells, plus one neighbour */
+__device__ __forceinline__ void emit_cp_async16(void *smem, const void *gmem)
+{ asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory"); }
+
+/* STAGED: the CTA's source cells come in through shared memory with fully coalesced 16-byte cp.async (quad q of cell l is kept
+ * at l * 8 + (q ^ (l & 7)), so that the per-thread reads at a 128-byte stride are free of bank conflicts), and the finished
+ * cells go out the same way as whole 128-byte lines (header quads zero: k_bm_fin_write fills them in). */
+template<bool STAGED>
 static __global__ void __launch_bounds__(EMIT_TPB) k_emit_bm_fast(const uint4 *__restrict__ A, int64_t nA, int64_t nA_cells, EmitOut O,
                                                                    const int64_t *__restrict__ ka, const uint8_t *__restrict__ bwt, const int64_t *__restrict__ ilo,
                                                                    uint4 *__restrict__ lcnt, int64_t *__restrict__ ctot, int64_t lenB, int *__restrict__ bad)
@@ -382,14 +391,38 @@ static __global__ void __launch_bounds__(EMIT_TPB) k_emit_bm_fast(const uint4 *_
 	 * own 128 positions.  Anything else sets *bad (the caller then keeps the old cells) and is made harmless. */
 	bool wrong = live && (i1 < i0 || a0 < 0 || a0 > nA || (j == 0 && i0 != 0) || (j == O.n_cells - 1 && i1 != lenB));
 	if (wrong) { i0 = i1 = 0; a0 = 0; }
-	const int64_t jA = a0 >> RB3B_BM_SHIFT;
+	int64_t jA = a0 >> RB3B_BM_SHIFT;
+	__shared__ __align__(16) uint4 tile[STAGED ? EMIT_SRC_CELLS * 8 : 1];
+	__shared__ int64_t s_first;
+	int lA = 0; /* STAGED: jA relative to the first source cell of the CTA */
+	if (STAGED) {
+		if (threadIdx.x == 0) s_first = jA; /* the first cell of a CTA is always live */
+		__syncthreads();
+		const int64_t first = s_first;
+		int64_t cnt = nA_cells - first;
+		cnt = cnt < 0 ? 0 : cnt > EMIT_SRC_CELLS ? EMIT_SRC_CELLS : cnt;
+		for (int e = threadIdx.x; e < (int)cnt * 8; e += EMIT_TPB) {
+			const int l = e >> 3, qq = e & 7;
+			emit_cp_async16(&tile[l * 8 + (qq ^ (l & 7))], A + first * 8 + e);
+		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+		if (live && (jA < first || jA - first > EMIT_SRC_CELLS - 2)) { wrong = true; i0 = i1 = 0; a0 = first << RB3B_BM_SHIFT; jA = first; } /* only with invalid positions */
+		lA = (int)(jA - first);
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+		__syncthreads();
+	}
 	const uint32_t q = ((uint32_t)a0 & 127u) >> 5, r = (uint32_t)a0 & 31u;
 	uint32_t X[RB3B_ASIZE][4], OUT[RB3B_ASIZE][4];
 #pragma unroll
 	for (int s = 0; s < RB3B_ASIZE; ++s) {
 		uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
-		if (live && jA < nA_cells) c0 = __ldg(A + jA * 8 + rb3b_bm_plane_quad(s));
-		if (live && jA + 1 < nA_cells) c1 = __ldg(A + (jA + 1) * 8 + rb3b_bm_plane_quad(s));
+		if (STAGED) {
+			if (live && jA < nA_cells) c0 = tile[lA * 8 + (rb3b_bm_plane_quad(s) ^ (lA & 7))];
+			if (live && jA + 1 < nA_cells) c1 = tile[(lA + 1) * 8 + (rb3b_bm_plane_quad(s) ^ ((lA + 1) & 7))];
+		} else {
+			if (live && jA < nA_cells) c0 = __ldg(A + jA * 8 + rb3b_bm_plane_quad(s));
+			if (live && jA + 1 < nA_cells) c1 = __ldg(A + (jA + 1) * 8 + rb3b_bm_plane_quad(s));
+		}
 		uint32_t w[9] = { c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, 0u };
 		if (q & 1u) {
 #pragma unroll
@@ -444,7 +477,23 @@ static __global__ void __launch_bounds__(EMIT_TPB) k_emit_bm_fast(const uint4 *_
 	}
 	wrong |= t < i1; /* a row that does not land in this cell */
 	if (wrong && bad) *bad = 1;
-	rb3b_bm_finish_cell(O, j, live, OUT, lcnt, ctot);
+	if (STAGED) {
+		__syncthreads(); /* everybody has read the source tile: it becomes the output tile */
+		const int tl = threadIdx.x;
+		tile[tl * 8 + (0 ^ (tl & 7))] = make_uint4(0, 0, 0, 0);
+		tile[tl * 8 + (4 ^ (tl & 7))] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+		for (int s = 0; s < RB3B_ASIZE; ++s) tile[tl * 8 + (rb3b_bm_plane_quad(s) ^ (tl & 7))] = make_uint4(OUT[s][0], OUT[s][1], OUT[s][2], OUT[s][3]);
+		__syncthreads();
+		const int64_t j0 = (int64_t)blockIdx.x * EMIT_TPB;
+		const int64_t left = O.n_cells - j0;
+		const int n_here = (int)(left < EMIT_TPB ? left : EMIT_TPB);
+		for (int e = threadIdx.x; e < n_here * 8; e += EMIT_TPB) {
+			const int l = e >> 3, qq = e & 7;
+			O.cells[j0 * 8 + e] = tile[l * 8 + (qq ^ (l & 7))];
+		}
+		rb3b_bm_finish_cell<false>(O, j, live, OUT, lcnt, ctot);
+	} else rb3b_bm_finish_cell<true>(O, j, live, OUT, lcnt, ctot);
 }
 
 /* *validated = 1: the kernel checked the interleave positions itself (d_bad is set when they are not monotone) */
@@ -452,7 +501,10 @@ template<class Src> static inline bool rb3b_launch_emit_bm_fast(const Src &, con
 static inline bool rb3b_launch_emit_bm_fast(const BmSrc &src, const EmitOut &O, int64_t lenB, const int64_t *d_ka, const uint8_t *d_bwt, const int64_t *d_ilo, uint4 *lcnt, int64_t *ctot, int *d_bad)
 {
 	if (lenB <= 0 || d_ilo == 0) return false;
-	k_emit_bm_fast<<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(src.R.cells, src.n, (src.n + 127) >> RB3B_BM_SHIFT, O, d_ka, d_bwt, d_ilo, lcnt, ctot, lenB, d_bad);
+	if (rb3b_get_param("emit_staged", 1) != 0)
+		k_emit_bm_fast<true><<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(src.R.cells, src.n, (src.n + 127) >> RB3B_BM_SHIFT, O, d_ka, d_bwt, d_ilo, lcnt, ctot, lenB, d_bad);
+	else
+		k_emit_bm_fast<false><<<(unsigned)O.n_chunks, EMIT_TPB, 0, rb3b_stream>>>(src.R.cells, src.n, (src.n + 127) >> RB3B_BM_SHIFT, O, d_ka, d_bwt, d_ilo, lcnt, ctot, lenB, d_bad);
 	return true;
 }
 
