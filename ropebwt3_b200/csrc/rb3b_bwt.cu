@@ -51,6 +51,41 @@ __global__ void k_group_heads(uint32_t n, const uint64_t *__restrict__ key, int 
 	head[j] = h ? j : 0;
 }
 
+/* ---- round 0 of small batches (< 2^24 symbols: one or two bacterial genomes): keys-only radix sort ----
+ * The suffix position rides in the low 24 bits of the key, so no value array travels through the sort (16 instead of 24
+ * bytes per suffix and pass); only the 40 bits above it are sorted -- 5 passes instead of 8.  Those 40 bits hold the first
+ * 15 symbols as a base-6 number (6^15 < 2^39; same order as the 3-bit packing) and the "fully compared" flag.  The stable
+ * sort leaves equal prefixes in position order, as before. */
+#define KMER6 15
+#define POS_BITS 24
+
+__global__ void k_kmer_keys6(uint32_t n, const uint8_t *__restrict__ T, int n_sym, uint64_t *__restrict__ key, int *__restrict__ bad)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint64_t k = 0;
+	int ended = 0;
+	for (int j = 0; j < KMER6; ++j) {
+		uint32_t p = i + j;
+		int c = (!ended && p < n) ? T[p] : 0;
+		if (c >= n_sym) { *bad = 1; c = 5; }
+		k = k * 6 + (uint64_t)c;
+		if (c == 0) ended = 1;
+	}
+	key[i] = (k << 1 | (uint64_t)ended) << POS_BITS | (uint64_t)i;
+}
+
+/* group heads of the keys-only round + the suffix array stretch it implies */
+__global__ void k_group_heads6(uint32_t n, const uint64_t *__restrict__ key, uint32_t *__restrict__ head, uint32_t *__restrict__ sa)
+{
+	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	const uint64_t k = key[j] >> POS_BITS;
+	bool h = j == 0 || k != key[j - 1] >> POS_BITS || (k & 1);
+	head[j] = h ? j : 0;
+	sa[j] = (uint32_t)(key[j] & ((1u << POS_BITS) - 1u));
+}
+
 /* after the max-scan head[j] is the index of the first element of j's group = the new rank */
 __global__ void k_assign_rank(uint32_t n, const uint32_t *__restrict__ idx, const uint32_t *__restrict__ head, uint32_t *__restrict__ rank, unsigned long long *n_amb)
 {
@@ -182,10 +217,22 @@ static int suffix_sort(int64_t len, const uint8_t *d_text, DBuf<uint32_t> &sa, i
 	DBuf<uint8_t> flag;
 	TRY(key0.alloc(n)); TRY(key1.alloc(n)); TRY(idx0.alloc(n)); TRY(sa.alloc(n)); TRY(rank.alloc(n)); TRY(head.alloc(n)); TRY(bad.alloc(1)); TRY(amb.alloc(1)); TRY(flag.alloc(n));
 	CK(cudaMemsetAsync(bad.p, 0, sizeof(int), rb3b_stream));
-	/* round 0: all suffixes by their first 21 symbols */
-	k_kmer_keys<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, d_text, n_sym, key0.p, idx0.p, bad.p); CKK();
-	TRY(sort_pairs(key0.p, key1.p, idx0.p, sa.p, n, 64));
-	k_group_heads<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, key1.p, 1, head.p); CKK();
+	/* round 0: all suffixes by their first 21 symbols (15 for small batches, keys only) */
+	const bool keys_only = n < (1u << POS_BITS) && n_sym <= 6 && rb3b_get_param("sa_keys_only", 1) != 0; /* base 6: not for the augmented alphabet of the sorted orders */
+	const uint64_t kmer = keys_only ? KMER6 : KMER;
+	if (keys_only) {
+		k_kmer_keys6<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, d_text, n_sym, key0.p, bad.p); CKK();
+		size_t tb = 0;
+		CK(cub::DeviceRadixSort::SortKeys((void*)0, tb, key0.p, key1.p, (int64_t)n, POS_BITS, 64, rb3b_stream));
+		DBuf<uint8_t> t;
+		TRY(t.alloc(tb));
+		CK(cub::DeviceRadixSort::SortKeys((void*)t.p, tb, key0.p, key1.p, (int64_t)n, POS_BITS, 64, rb3b_stream));
+		k_group_heads6<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, key1.p, head.p, sa.p); CKK();
+	} else {
+		k_kmer_keys<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, d_text, n_sym, key0.p, idx0.p, bad.p); CKK();
+		TRY(sort_pairs(key0.p, key1.p, idx0.p, sa.p, n, 64));
+		k_group_heads<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, key1.p, 1, head.p); CKK();
+	}
 	TRY(scan_max_u32(head.p, n));
 	CK(cudaMemsetAsync(amb.p, 0, 8, rb3b_stream));
 	k_assign_rank<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, sa.p, head.p, rank.p, amb.p); CKK();
@@ -205,7 +252,7 @@ static int suffix_sort(int64_t len, const uint8_t *d_text, DBuf<uint32_t> &sa, i
 		k_amb_flags<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, head.p, flag.p); CKK();
 		TRY(select_flagged<uint32_t>(sa.p, flag.p, suf, n, amb.p));
 		TRY(select_flagged<uint32_t>(head.p, flag.p, grp, n, amb.p));
-		for (uint64_t h = KMER; m > 0 && h < n; h <<= 1) {
+		for (uint64_t h = kmer; m > 0 && h < n; h <<= 1) {
 			/* segments = groups */
 			k_list_keys<<<nblk(m, TPB), TPB, 0, rb3b_stream>>>(m, n, (uint32_t)h, suf, grp, rank.p, key, flag.p); CKK();
 			k_seg_first<<<nblk(m, TPB), TPB, 0, rb3b_stream>>>(m, grp, segfirst.p); CKK();
@@ -247,7 +294,7 @@ static int suffix_sort(int64_t len, const uint8_t *d_text, DBuf<uint32_t> &sa, i
 		return RB3B_OK;
 	}
 	/* every round re-sorts all suffixes (lists of 2^31 ambiguous suffixes or more; "sa_discard" = 0) */
-	for (uint64_t h = KMER; n_amb > 0 && h < n; h <<= 1) {
+	for (uint64_t h = kmer; n_amb > 0 && h < n; h <<= 1) {
 		k_pair_keys<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, (uint32_t)h, rank.p, key0.p, idx0.p); CKK();
 		TRY(sort_pairs(key0.p, key1.p, idx0.p, sa.p, n, 64));
 		k_group_heads<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, key1.p, 0, head.p); CKK();

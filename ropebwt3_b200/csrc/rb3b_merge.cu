@@ -219,16 +219,6 @@ __global__ void k_chain_len(int64_t n_seq, const FNode *__restrict__ node, int64
 	if (p < n_seq) { const FNode a = node[p]; chain_len[p] = a.x; chain_of[fnode_term(a)] = p; }
 }
 
-/* sort key of a piece for the second walk: its length, clamped to one byte */
-__global__ void k_piece_keys(int64_t n, const int32_t *__restrict__ piece_len, uint8_t *__restrict__ key, uint32_t *__restrict__ id)
-{
-	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (f >= n) return;
-	const int32_t l = piece_len[f];
-	key[f] = (uint8_t)(l > 255 ? 255 : l);
-	id[f] = (uint32_t)f;
-}
-
 /* second walk of the pieces: write the batch in walk order.  Chain p occupies positions [chain_base[p], +chain_len[p]);
  * the piece of fine mark f starts node[f].x positions before the end of its chain.  Every thread writes one contiguous
  * stretch; it collects 8 symbols / 16 bytes of rows in registers and stores them as one aligned word (the unaligned
@@ -252,12 +242,10 @@ template<> struct RowVec<int64_t> {
 template<typename LfT, typename RowT>
 __global__ void k_write_walk(Fine F, int64_t len, const LfT *__restrict__ lf, const FNode *__restrict__ node,
                              const int64_t *__restrict__ chain_of, const int64_t *__restrict__ chain_base, const int64_t *__restrict__ chain_len,
-                             const int32_t *__restrict__ piece_len, int64_t p_lo, int64_t p_hi, RowT *__restrict__ wrow, uint8_t *__restrict__ wsym,
-                             const uint32_t *__restrict__ order)
+                             const int32_t *__restrict__ piece_len, int64_t p_lo, int64_t p_hi, RowT *__restrict__ wrow, uint8_t *__restrict__ wsym)
 {
 	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (f >= F.n_fine) return;
-	if (order) f = order[f]; /* pieces by descending length: the lanes of a warp run the same number of steps, the longest chases start first */
 	const FNode me = node[f];
 	const int64_t p = chain_of[fnode_term(me)];
 	if (p < 0) return; /* not on a chain that starts at a sentinel: not a valid BWT, reported by the caller */
@@ -1003,22 +991,10 @@ static int walk_order(int64_t len, const uint8_t *d_bwt, int64_t nt, const int64
 	if (last[0] + last[1] != len) /* LF_B is a permutation, so the chains are disjoint: they cover the batch iff their lengths add up */
 		return rb3b_fail(RB3B_EINVAL, "batch is not the BWT of a sentinel-terminated string set (%lld of %lld rows reachable from the sentinels)",
 		                 (long long)(last[0] + last[1]), (long long)len);
-	/* the pieces' lengths are geometric (mean fine_len, longest ~13x that): in piece order a warp of the second walk runs
-	 * as long as its longest piece with a quarter of its lanes busy (ncu: 8.4 of 32).  One 8-bit radix pass puts pieces of
-	 * equal length side by side, longest first. */
-	const uint32_t *order = 0;
-	DBuf<uint8_t> pk; DBuf<uint32_t> po;
-	if (rb3b_get_param("sort_pieces", 1) != 0 && F.n_fine > 1024) {
-		DBuf<uint8_t> tmp;
-		size_t tb = 0;
-		TRY(pk.alloc((size_t)F.n_fine * 2)); TRY(po.alloc((size_t)F.n_fine * 2));
-		k_piece_keys<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F.n_fine, pl.p, pk.p, po.p); CKK();
-		CK(cub::DeviceRadixSort::SortPairsDescending((void*)0, tb, pk.p, pk.p + F.n_fine, po.p, po.p + F.n_fine, F.n_fine, 0, 8, rb3b_stream));
-		TRY(tmp.alloc(tb));
-		CK(cub::DeviceRadixSort::SortPairsDescending((void*)tmp.p, tb, pk.p, pk.p + F.n_fine, po.p, po.p + F.n_fine, F.n_fine, 0, 8, rb3b_stream));
-		order = po.p + F.n_fine;
-	}
-	k_write_walk<LfT, RowT><<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, len, lf.p, node, f_cof, c_base, c_len, pl.p, p_lo, p_hi, wrow.p, wsym.p, order); CKK();
+	/* (Tried: the pieces sorted by length with one 8-bit radix pass, so that the lanes of a warp run equally long and the
+	 * longest chases start first -- ncu shows 8.4 of 32 lanes busy here.  Slower: 0.57 vs 0.51 ms of prep with one genome
+	 * per batch, 6.5 vs 5.6 ms with ten; neighbouring pieces start at neighbouring rows, the sorted order gives that up.) */
+	k_write_walk<LfT, RowT><<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, len, lf.p, node, f_cof, c_base, c_len, pl.p, p_lo, p_hi, wrow.p, wsym.p); CKK();
 	*wrow_out = wrow.p; *chain_base_out = c_base; *chain_len_out = c_len; /* arena memory: lives until the API call returns */
 	if (lf_out) *lf_out = lf.p;
 	return RB3B_OK;

@@ -293,14 +293,14 @@ def test_bitmap_to_rle_transition(rb3, oracle, golden):
 
 
 @pytest.mark.parametrize("knob,value", [("fix_log", 0), ("wide_lf", 1), ("fine_len", 7), ("fine_len", 1), ("scatter_win_bits", 5), ("walk_pair", 0),
-                                        ("warm_rows", 0), ("warm_rows", 40), ("mask_max_rows", 0), ("async_merge", 1), ("fix_tables", 1), ("fix_tpb", 16), ("fix_stages", 2), ("emit_staged", 0), ("sort_pieces", 0)])
+                                        ("warm_rows", 0), ("warm_rows", 40), ("mask_max_rows", 0), ("async_merge", 1), ("fix_tables", 1), ("fix_tpb", 16), ("fix_stages", 2), ("emit_staged", 0)])
 def test_optional_code_paths(rb3, oracle, golden, knob, value):
     """The tuning knobs select other kernels (multi-round generic fix-up, 64-bit LF table and rows, other mark spacing,
     the two-pass bucketed scatter of large batches, single-lane walks, no / longer warm-up before a slice, no transfer
     masks: every row of the fix-up takes the general step); every one of them must give the reference's interleave
     array and merged index."""
     g = golden("merge_dup")
-    defaults = {"fix_log": 1, "wide_lf": 0, "fine_len": 0, "scatter_win_bits": 19, "walk_pair": 1, "warm_rows": 16, "mask_max_rows": 1 << 28, "async_merge": 0, "fix_tables": 0, "fix_tpb": 32, "fix_stages": 4, "emit_staged": 1, "sort_pieces": 1}
+    defaults = {"fix_log": 1, "wide_lf": 0, "fine_len": 0, "scatter_win_bits": 19, "walk_pair": 1, "warm_rows": 16, "mask_max_rows": 1 << 28, "async_merge": 0, "fix_tables": 0, "fix_tpb": 32, "fix_stages": 4, "emit_staged": 1}
     rb3.set_param(knob, value)
     if knob == "scatter_win_bits":
         rb3.set_param("scatter_bucket_min", 1)
@@ -329,6 +329,22 @@ def test_build_bwt_golden(rb3, golden):
     assert np.array_equal(rb3.rb3_build_sais(g["text"]), g["bwt"])
     with pytest.raises(rb3.Rb3bError):
         rb3.rb3_build_sais(np.array([1, 2, 3], np.uint8))  # no trailing sentinel (mrope.c:310)
+
+
+@pytest.mark.parametrize("knob,value", [("sa_keys_only", 0), ("sa_discard", 0)])
+def test_suffix_sorter_paths(rb3, golden, knob, value):
+    """The suffix sorter's other paths -- 21-symbol key/value round 0 instead of the keys-only 15-symbol round of small
+    batches, and refinement rounds that re-sort everything -- give libsais' BWT as well."""
+    rb3.set_param(knob, value)
+    try:
+        for name in MERGE_SETS:
+            g = golden(name)
+            for b in range(int(g["n_batches"])):
+                assert np.array_equal(rb3.rb3_build_sais(g["text%d" % b]), g["bwt%d" % b]), (knob, name, b)
+        g = golden("reads")
+        assert np.array_equal(rb3.rb3_build_sais(g["text"]), g["bwt"])
+    finally:
+        rb3.set_param(knob, 1)
 
 
 def test_merge_errors(rb3, golden):
