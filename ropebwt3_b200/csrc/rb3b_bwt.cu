@@ -141,6 +141,19 @@ static int scan_max_u32(uint32_t *d, uint32_t n)
  * are the segments), gives every sub-group its new rank, writes the now final stretch of the suffix array back and keeps
  * only the members of sub-groups that are still larger than one. */
 
+struct HeadIsAmbiguous { /* sorted position j belongs to a group of more than one suffix */
+	const uint32_t *head; uint32_t n;
+	__host__ __device__ bool operator()(const uint32_t &j) const { return head[j] != j || (j + 1 < n && head[j + 1] == head[j]); }
+};
+
+__global__ void k_amb_gather(uint32_t m, const uint32_t *__restrict__ at, const uint32_t *__restrict__ sa, const uint32_t *__restrict__ head, uint32_t *__restrict__ suf, uint32_t *__restrict__ grp)
+{
+	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= m) return;
+	const uint32_t j = at[t];
+	suf[t] = sa[j]; grp[t] = head[j];
+}
+
 __global__ void k_amb_flags(uint32_t n, const uint32_t *__restrict__ head, uint8_t *__restrict__ flag)
 {
 	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -249,9 +262,16 @@ static int suffix_sort(int64_t len, const uint8_t *d_text, DBuf<uint32_t> &sa, i
 		uint32_t *suf = (uint32_t*)key0.p, *grp = suf + n, *key = (uint32_t*)key1.p, *ksorted = key + n; /* each has room for n */
 		DBuf<uint32_t> vsorted, segfirst, sub, off, tmp32;
 		TRY(vsorted.alloc(m)); TRY(segfirst.alloc(m)); TRY(sub.alloc(m)); TRY(off.alloc((size_t)m + 1)); TRY(tmp32.alloc(m));
-		k_amb_flags<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, head.p, flag.p); CKK();
-		TRY(select_flagged<uint32_t>(sa.p, flag.p, suf, n, amb.p));
-		TRY(select_flagged<uint32_t>(head.p, flag.p, grp, n, amb.p));
+		{ /* sorted positions of the ambiguous suffixes (one select), then their suffixes and groups (one small gather) */
+			cub::CountingInputIterator<uint32_t> pos(0);
+			HeadIsAmbiguous is_amb; is_amb.head = head.p; is_amb.n = n;
+			size_t tb = 0;
+			CK(cub::DeviceSelect::If((void*)0, tb, pos, vsorted.p, amb.p, (int64_t)n, is_amb, rb3b_stream));
+			DBuf<uint8_t> t;
+			TRY(t.alloc(tb));
+			CK(cub::DeviceSelect::If((void*)t.p, tb, pos, vsorted.p, amb.p, (int64_t)n, is_amb, rb3b_stream));
+			k_amb_gather<<<nblk(m, TPB), TPB, 0, rb3b_stream>>>(m, vsorted.p, sa.p, head.p, suf, grp); CKK();
+		}
 		for (uint64_t h = kmer; m > 0 && h < n; h <<= 1) {
 			/* segments = groups */
 			k_list_keys<<<nblk(m, TPB), TPB, 0, rb3b_stream>>>(m, n, (uint32_t)h, suf, grp, rank.p, key, flag.p); CKK();
@@ -339,12 +359,23 @@ extern "C" int rb3b_build_bwt_dev(int64_t len, const uint8_t *d_text, uint8_t *d
 __global__ void k_zero_flags(int64_t len, const uint8_t *__restrict__ T, int64_t *__restrict__ flag);
 __global__ void k_zero_pos(int64_t len, const uint8_t *__restrict__ T, const int64_t *__restrict__ sid, int64_t *__restrict__ Z);
 
-__global__ void k_text_walk_order(int64_t len, const uint8_t *__restrict__ T, const uint32_t *__restrict__ isa, const int64_t *__restrict__ sid, const int64_t *__restrict__ Z,
+struct TextIsZero { /* predicate of the sentinel-position select */
+	const uint8_t *T;
+	__host__ __device__ bool operator()(const int64_t &i) const { return T[i] == 0; }
+};
+
+/* Z[0..n_seq): the sentinel positions, ascending; the string of position q is the first s with Z[s] >= q */
+__global__ void k_text_walk_order(int64_t len, const uint8_t *__restrict__ T, const uint32_t *__restrict__ isa, int64_t n_seq, const int64_t *__restrict__ Z,
                                   uint8_t *__restrict__ wsym, uint32_t *__restrict__ wrow, int64_t *__restrict__ c_base, int64_t *__restrict__ c_len)
 {
 	const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (q >= len) return;
-	const int64_t s = sid[q], st = s ? Z[s - 1] + 1 : 0, e = Z[s], src = st + e - q;
+	int64_t lo = 0, hi = n_seq - 1; /* the last symbol is a sentinel: Z[n_seq - 1] = len - 1 >= q */
+	while (lo < hi) {
+		const int64_t mid = (lo + hi) >> 1;
+		if (__ldg(Z + mid) >= q) hi = mid; else lo = mid + 1;
+	}
+	const int64_t s = lo, st = s ? __ldg(Z + s - 1) + 1 : 0, e = __ldg(Z + s), src = st + e - q;
 	wrow[q] = isa[src];
 	wsym[q] = src > 0 ? T[src - 1] : 0; /* the symbol before the first string is the last sentinel */
 	if (q == e) { c_base[s] = st; c_len[s] = e - st + 1; }
@@ -426,13 +457,19 @@ static int batch_prepare_i(rb3b_batch_s *B, int64_t len, const uint8_t *d_text)
 	if ((unsigned long long)B->n_seq != n_zero) return rb3b_fail(RB3B_EINVAL, "internal error: %lld sentinels in the BWT, %llu in the text", (long long)B->n_seq, n_zero);
 	B->wsym = B->bwt + o_sym; B->wrow = (uint32_t*)(B->bwt + o_row); B->c_base = (int64_t*)(B->bwt + o_chain);
 	B->c_len = B->c_base + B->n_seq;
-	TRY(flag.alloc(len)); TRY(sid.alloc(len)); TRY(Z.alloc(B->n_seq));
-	k_zero_flags<<<nblk(len, TPB), TPB, 0, rb3b_stream>>>(len, d_text, flag.p); CKK();
-	TRY(rb3b_scan_excl_i64(flag.p, sid.p, len));
-	k_zero_pos<<<nblk(len, TPB), TPB, 0, rb3b_stream>>>(len, d_text, sid.p, Z.p); CKK();
+	TRY(Z.alloc(B->n_seq));
+	{ /* the sentinel positions: one select over the text (no per-position string ids, no scan) */
+		cub::CountingInputIterator<int64_t> pos(0);
+		TextIsZero is_zero; is_zero.T = d_text;
+		size_t tb = 0;
+		CK(cub::DeviceSelect::If((void*)0, tb, pos, Z.p, cnt0.p + 1, len, is_zero, rb3b_stream));
+		DBuf<uint8_t> t;
+		TRY(t.alloc(tb));
+		CK(cub::DeviceSelect::If((void*)t.p, tb, pos, Z.p, cnt0.p + 1, len, is_zero, rb3b_stream));
+	}
 	CK(cudaMemsetAsync(B->wsym + len, 0, 64, rb3b_stream));
 	CK(cudaMemsetAsync(B->wrow + len, 0, 32, rb3b_stream));
-	k_text_walk_order<<<nblk(len, TPB), TPB, 0, rb3b_stream>>>(len, d_text, isa.p, sid.p, Z.p, B->wsym, B->wrow, B->c_base, B->c_len); CKK();
+	k_text_walk_order<<<nblk(len, TPB), TPB, 0, rb3b_stream>>>(len, d_text, isa.p, B->n_seq, Z.p, B->wsym, B->wrow, B->c_base, B->c_len); CKK();
 	rb3b_toc(T_BWT);
 	CK(cudaStreamSynchronize(rb3b_stream));
 	rb3b_tflush();

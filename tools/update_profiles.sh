@@ -19,3 +19,18 @@ done
 # SASS of the hot kernels from the built library (what the GPU box ran): mnemonic histogram + full listing of each
 python tools/sass_excerpts.py ropebwt3_b200/librb3b200.so profiles/${R}_sass
 ls profiles | grep "^${R}_" | wc -l
+# roofline.traffic of bench.py: DRAM bytes of the dominant kernel from the ncu --set full capture of this round (static, labelled so)
+python - "$R" <<'PY'
+import csv, json, sys
+R = sys.argv[1]
+rows = list(csv.reader(open('profiles/%s_ncu_k_walk_pair_raw.csv' % R)))
+h, u, r = rows[0], rows[1], rows[2]
+def val(k):
+    i = h.index(k); v = float(r[i].replace(',', '')); return v * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1}[u[i]]
+t = val('dram__bytes_read.sum') + val('dram__bytes_write.sum')
+json.dump({"kernel": "k_walk_pair<false>", "dram_bytes_per_launch": t, "rows_per_launch": 10000002,
+           "source": "profiles/%s_ncu_k_walk_pair_raw.csv" % R,
+           "what": "ncu --set full --clock-control none on bench.py --steps 40 --warmup 3, 31st launch of the kernel (index of ~0.35 G symbols = 0.35 GB of bitmap cells)"},
+          open('profiles/walk_first_traffic.json', 'w'))
+print("walk kernel DRAM bytes per launch: %.3g" % t)
+PY
