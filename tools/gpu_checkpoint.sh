@@ -3,6 +3,7 @@
 # tools/update_profiles.sh copies the summaries into profiles/.   usage: tools/gpu_checkpoint.sh <round tag, e.g. r2>
 R=${1:-r2}
 O=gpurun_out
+if [ -n "$RUN_TESTS" ]; then (time python -m pytest tests -q -m gpu) > $O/${R}_gpu_tests.txt 2>&1; tail -4 $O/${R}_gpu_tests.txt; fi
 timeout 900 python bench.py > $O/${R}_bench_default.json 2> $O/${R}_bench_default.err; tail -c 300 $O/${R}_bench_default.err
 timeout 600 python bench.py --steps 20 --warmup 5 > $O/${R}_bench_steps20.json 2> $O/${R}_bench_steps20.err
 timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > $O/${R}_bench_reference_arm.json 2> $O/${R}_bench_reference_arm.err
@@ -25,7 +26,7 @@ timeout 300 python tools/rank_bench.py --kind bitmap > $O/${R}_rank_bench_bitmap
 timeout 300 python tools/rank_bench.py --kind rle --variants 8,4,2,22,11,1 > $O/${R}_rank_bench_rle.jsonl 2>/dev/null
 timeout 300 python tools/rank_bench.py --kind rle --variants 2,11 --blocks 2.1e6 --max-len 2000 > $O/${R}_rank_bench_rle_1e11_symbols.jsonl 2>/dev/null
 # suffix sorter, CLI end to end, C2-style batches
-timeout 300 python tools/bwt_bench.py 1 4 10 > $O/${R}_bwt_bench.jsonl 2>/dev/null
+timeout 300 python tools/bwt_bench.py 1 2 4 10 > $O/${R}_bwt_bench.jsonl 2>/dev/null
 timeout 600 python tools/cli_e2e.py 24 5000000 > $O/${R}_cli_e2e.json 2> $O/cli_e2e.err
 timeout 900 python bench.py --config c2s --c2s-genomes 600 --no-cpu-baseline --no-rank-bench --no-e2e > $O/${R}_bench_c2s.json 2> $O/${R}_bench_c2s.err; tail -c 300 $O/${R}_bench_c2s.err
 ls $O | wc -l

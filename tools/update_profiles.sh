@@ -9,7 +9,7 @@ for f in bench_default bench_steps20 bench_reference_arm bench_g10 bench_c2s cli
          scale_n2 scale_n4 scale_n8 strong_n1 strong_n2 strong_n4 strong_n8; do
   [ -s $O/${R}_$f.json ] && cp $O/${R}_$f.json profiles/${R}_$f.json
 done
-for f in launches.csv launch_shares.txt rank_bench_bitmap.jsonl rank_bench_rle.jsonl rank_bench_rle_1e11_symbols.jsonl bwt_bench.jsonl fmd_dev_bench.json; do
+for f in gpu_tests.txt launches.csv launch_shares.txt rank_bench_bitmap.jsonl rank_bench_rle.jsonl rank_bench_rle_1e11_symbols.jsonl bwt_bench.jsonl fmd_dev_bench.json; do
   [ -s $O/${R}_$f ] && cp $O/${R}_$f profiles/${R}_$f
 done
 for k in k_walk_pair k_fix_chain k_emit_bm_fast k_write_walk k_lf_bm k_lf_t1; do
