@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--param", action="append", default=[], help="engine tuning knob key=value (rb3b_set_param), repeatable")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-prefetch", action="store_true", help="e2e leg: do not queue the H2D copy of batch i+1 (rb3b_prefetch_batch) before merging batch i")
     ap.add_argument("--no-rank-bench", action="store_true")
     ap.add_argument("--no-build", action="store_true", help="skip the text-in build_value leg")
     return ap.parse_args()
@@ -265,8 +266,12 @@ def run_b200(a):
         acc_host = np.zeros(7, np.int64)
         e0.record(stream)
         w0 = time.time()
+        if not a.no_prefetch:
+            capi.check(L.rb3b_prefetch_batch(lens[1 + a.warmup], hp[1 + a.warmup]))
         for i in range(1 + a.warmup, n_g):
-            capi.check(L.rb3b_merge_plain(idx2.h, lens[i], hp[i]))       # H2D of the batch + merge + sync
+            if not a.no_prefetch and i + 1 < n_g:                          # like the reference's -p pipeline (read batch i+1 while merging batch i):
+                capi.check(L.rb3b_prefetch_batch(lens[i + 1], hp[i + 1]))  # the H2D copy of the NEXT batch is queued on the library's copy stream
+            capi.check(L.rb3b_merge_plain(idx2.h, lens[i], hp[i]))       # (H2D of the batch unless it was copied ahead) + merge + sync
             L.rb3b_get_acc(idx2.h, acc_host.ctypes.data)                   # the step's result: new C[] of the index
         R.sync()   # asynchronous merges run on the library's second stream: the timed region ends when they have
         e1.record(stream)
@@ -340,7 +345,9 @@ def run_b200(a):
         "dtype": "u8/int64", "data": "synthetic",
         "config": config_of(a, {"seg_len": a.seg_len or R.get_stat("seg_len_used"), "parallelism": "1 GPU" if world == 1 else "weak scaling: %d genomes per merge on %d GPUs; index replicated; rank phase of every merge split over the ranks (walk-order slices + halo, first walk of the pieces shared by an all-gather), one NCCL all-reduce of the partial interleave arrays (32-bit SUM while positions fit, else 64-bit MAX), merge replicated; %d of %d merges sharded" % (G, world, n_sharded, a.steps)}),
         "e2e": None if a.no_e2e else {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(np.mean(lens[1 + a.warmup:])), "d2h_bytes_per_step": int(d2h),
-                                      "ms_per_step": ms_e2e / a.steps},
+                                      "ms_per_step": ms_e2e / a.steps,
+                                      "how": "every batch goes from pinned host memory through rb3b_merge_plain (host-pointer C-ABI call) and the new C[] of the index is read back, all inside the timed region" +
+                                             ("" if (a.no_prefetch or world > 1) else "; the H2D copy of batch i+1 is queued with rb3b_prefetch_batch before the merge of batch i (the reference's -p pipeline overlaps reading and merging the same way)")},
         "gpu_launches": int(st["kernel_launches"]),
         "clocks": clocks,
         "build_value": None if build_value is None else {"value": build_value, "unit": UNIT, "ms_per_step": ms_build / a.steps,

@@ -81,6 +81,12 @@ int rb3b_index_from_runs_device(rb3b_index_t *idx, int64_t n_runs, const uint8_t
 /* rb3_fmi_merge_plain (fm-index.c:279-303): merge the partial BWT `bwt` of a new
  * batch (host memory, caller-owned) into the index in place. */
 int rb3b_merge_plain(rb3b_index_t *idx, int64_t len, const uint8_t *bwt);
+/* Optional: start copying a batch to the device now, for a later rb3b_merge_plain(idx, len, host_bwt) or
+ * rb3b_batch_prepare(len, host_text) with the SAME pointer and length, so that the copy of batch i+1 overlaps the merge of
+ * batch i (the reference overlaps reading batch i+1 with merging batch i the same way: kt_pipeline, build.c:55-83,186-201).
+ * Up to two batches may be in flight; the host buffer must stay unchanged until the consuming call returns and should be
+ * pinned (rb3b_host_alloc_pinned) for the copy to be asynchronous.  Not consuming a prefetched batch is harmless. */
+int rb3b_prefetch_batch(int64_t len, const uint8_t *host);
 /* same, partial BWT already in device memory (no host<->device copies) */
 int rb3b_merge_plain_dev(rb3b_index_t *idx, int64_t len, const uint8_t *d_bwt);
 

@@ -45,6 +45,7 @@ SIGNATURES = {
     "rb3b_index_from_runs_device": (_int, [_vp, _i64, _vp, _vp]),
     "rb3b_merge_plain": (_int, [_vp, _i64, _vp]),
     "rb3b_merge_plain_dev": (_int, [_vp, _i64, _vp]),
+    "rb3b_prefetch_batch": (_int, [_i64, _vp]),
     "rb3b_mg_rank_plain": (_int, [_vp, _i64, _vp, _vp, _vp]),
     "rb3b_mg_rank_plain_dev": (_int, [_vp, _i64, _vp, _vp, _vp]),
     "rb3b_mg_rank_part": (_int, [_vp, _i64, _vp, _int, _int, _vp]),

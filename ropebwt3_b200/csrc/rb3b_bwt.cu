@@ -495,8 +495,10 @@ extern "C" rb3b_batch_t *rb3b_batch_prepare(int64_t len, const uint8_t *text)
 	if (rb3b_ensure_init() != RB3B_OK) return 0;
 	if (len <= 0) { rb3b_fail(RB3B_EINVAL, "empty batch"); return 0; }
 	DBuf<uint8_t> t;
-	if (t.alloc(len) != RB3B_OK) return 0;
-	if (cudaMemcpyAsync(t.p, text, (size_t)len, cudaMemcpyHostToDevice, rb3b_stream) != cudaSuccess) { rb3b_fail(RB3B_ENODEV, "host to device copy failed"); return 0; }
+	if ((t.p = rb3b_prefetched(text, len)) == 0) { /* not copied ahead (rb3b_prefetch_batch) */
+		if (t.alloc(len) != RB3B_OK) return 0;
+		if (cudaMemcpyAsync(t.p, text, (size_t)len, cudaMemcpyHostToDevice, rb3b_stream) != cudaSuccess) { rb3b_fail(RB3B_ENODEV, "host to device copy failed"); return 0; }
+	}
 	return rb3b_batch_prepare_dev(len, t.p);
 }
 

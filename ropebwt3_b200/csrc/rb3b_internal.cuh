@@ -134,7 +134,12 @@ struct rb3b_ctx_s {
 	cudaStream_t stream2;             /* asynchronous merges run here */
 	cudaEvent_t ev_hand;              /* hand-over between the two streams */
 	char *bump; size_t bump_off, bump_cap; /* when set, scratch comes from this region (an index's merge scratch) instead of the arena */
+	/* batches copied ahead of the call that consumes them (rb3b_prefetch_batch): two staging buffers, a copy stream */
+	struct { const void *host; int64_t len; uint8_t *dev; size_t cap; cudaEvent_t ev; int valid; } pf[2];
+	int pf_next;
+	cudaStream_t stream_copy;
 };
+uint8_t *rb3b_prefetched(const void *host, int64_t len); /* the device copy of a prefetched batch (the current stream waits for it), or NULL */
 rb3b_ctx_s *rb3b_cur(void);
 #define rb3b_stream   (rb3b_cur()->stream)
 #define rb3b_n_launch (rb3b_cur()->n_launch)

@@ -1754,8 +1754,10 @@ extern "C" int rb3b_merge_plain(rb3b_index_t *x, int64_t len, const uint8_t *bwt
 	TRY(rb3b_ensure_init());
 	DBuf<uint8_t> d;
 	if (len <= 0) return RB3B_OK;
-	TRY(d.alloc(len));
-	CK(cudaMemcpyAsync(d.p, bwt, len, cudaMemcpyHostToDevice, rb3b_stream));
+	if ((d.p = rb3b_prefetched(bwt, len)) == 0) { /* not copied ahead (rb3b_prefetch_batch) */
+		TRY(d.alloc(len));
+		CK(cudaMemcpyAsync(d.p, bwt, len, cudaMemcpyHostToDevice, rb3b_stream));
+	}
 	TRY(rb3b_merge_plain_dev(x, len, d.p));
 	CK(cudaStreamSynchronize(rb3b_stream));
 	return RB3B_OK;

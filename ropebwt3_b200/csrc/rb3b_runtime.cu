@@ -37,6 +37,7 @@ static int ctx_setup(rb3b_ctx_s *c, int device)
 	c->n_launch = 0; c->ev_ok = 0;
 	c->comm = 0; c->comm2 = 0; c->rank = 0; c->world = 1;
 	c->stream2 = 0; c->ev_hand = 0; c->bump = 0; c->bump_off = c->bump_cap = 0;
+	memset(c->pf, 0, sizeof(c->pf)); c->pf_next = 0; c->stream_copy = 0;
 	memset(c->ev_pending, 0, sizeof(c->ev_pending));
 	CK(cudaSetDevice(device));
 	/* the second stream carries the bandwidth-bound merge of batch i while the first runs the latency-bound preparation of
@@ -71,6 +72,9 @@ static void ctx_teardown(rb3b_ctx_s *c)
 		cudaStreamSynchronize(c->stream);
 		if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); c->stream2 = 0; }
 		if (c->ev_hand) { cudaEventDestroy(c->ev_hand); c->ev_hand = 0; }
+		if (c->stream_copy) { cudaStreamSynchronize(c->stream_copy); cudaStreamDestroy(c->stream_copy); c->stream_copy = 0; }
+		for (int i = 0; i < 2; ++i) { if (c->pf[i].dev) cudaFree(c->pf[i].dev); if (c->pf[i].ev) cudaEventDestroy(c->pf[i].ev); }
+		memset(c->pf, 0, sizeof(c->pf));
 		for (size_t i = 0; i < c->chunks.size(); ++i) cudaFree(c->chunks[i].p);
 		c->chunks.clear();
 		if (c->ev_ok) for (int i = 0; i < T_COUNT; ++i) { cudaEventDestroy(c->ev[i][0]); cudaEventDestroy(c->ev[i][1]); }
@@ -350,6 +354,42 @@ extern "C" int rb3b_h2d(void *dst, const void *src, int64_t bytes)
 	CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, rb3b_stream));
 	CK(cudaStreamSynchronize(rb3b_stream));
 	return RB3B_OK;
+}
+
+/* ---- batches copied ahead (see rb3_b200.h) ---- */
+extern "C" int rb3b_prefetch_batch(int64_t len, const uint8_t *host)
+{
+	TRY(rb3b_ensure_init());
+	rb3b_ctx_s *c = rb3b_cur();
+	if (len <= 0 || host == 0) return rb3b_fail(RB3B_EINVAL, "empty batch");
+	if (c->stream_copy == 0) CK(cudaStreamCreateWithFlags(&c->stream_copy, cudaStreamNonBlocking));
+	const int k = c->pf_next;
+	c->pf_next ^= 1;
+	if (c->pf[k].cap < (size_t)len) { /* grow-only; whatever used this buffer two calls ago has returned */
+		CK(cudaStreamSynchronize(c->stream_copy));
+		if (c->pf[k].dev) CK(cudaFree(c->pf[k].dev));
+		c->pf[k].dev = 0; c->pf[k].cap = 0;
+		const size_t want = (size_t)len + (size_t)len / 8 + 512;
+		if (cudaMalloc((void**)&c->pf[k].dev, want) != cudaSuccess) { cudaGetLastError(); return rb3b_fail(RB3B_ENOMEM, "cannot allocate %zu bytes for a prefetched batch", want); }
+		c->pf[k].cap = want;
+	}
+	if (c->pf[k].ev == 0) CK(cudaEventCreateWithFlags(&c->pf[k].ev, cudaEventDisableTiming));
+	CK(cudaMemcpyAsync(c->pf[k].dev, host, (size_t)len, cudaMemcpyHostToDevice, c->stream_copy));
+	CK(cudaEventRecord(c->pf[k].ev, c->stream_copy));
+	c->pf[k].host = host; c->pf[k].len = len; c->pf[k].valid = 1;
+	return RB3B_OK;
+}
+
+uint8_t *rb3b_prefetched(const void *host, int64_t len)
+{
+	rb3b_ctx_s *c = rb3b_cur();
+	for (int k = 0; k < 2; ++k)
+		if (c->pf[k].valid && c->pf[k].host == host && c->pf[k].len == len) {
+			c->pf[k].valid = 0;
+			if (cudaStreamWaitEvent(c->stream, c->pf[k].ev, 0) != cudaSuccess) { cudaGetLastError(); return 0; }
+			return c->pf[k].dev;
+		}
+	return 0;
 }
 
 extern "C" int rb3b_d2h(void *dst, const void *src, int64_t bytes)

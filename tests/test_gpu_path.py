@@ -195,6 +195,40 @@ def test_prepared_batches_golden(rb3, oracle, golden, name, seg_len):
         rb3.set_param("seg_len", 0)
 
 
+def test_prefetched_batches(rb3, oracle, golden):
+    """rb3b_prefetch_batch: the copy of batch i+1 is queued before the merge of batch i; the consuming calls (merge_plain,
+    batch_prepare) must find it by pointer + length, and a prefetched batch nobody consumes, or a second prefetch of the same
+    slot, must be harmless."""
+    from ropebwt3_b200 import capi
+    L = capi.lib()
+    g = golden("merge_div")
+    n = int(g["n_batches"])
+    bw = [np.ascontiguousarray(g["bwt%d" % b]) for b in range(n)]
+    idx = rb3.Index.from_plain(bw[0])
+    capi.check(L.rb3b_prefetch_batch(len(bw[1]), capi.ptr(bw[1])))
+    for b in range(1, n):
+        if b + 1 < n:
+            capi.check(L.rb3b_prefetch_batch(len(bw[b + 1]), capi.ptr(bw[b + 1])))
+        capi.check(L.rb3b_merge_plain(idx.h, len(bw[b]), capi.ptr(bw[b])))
+        assert np.array_equal(idx.acc(), g["accA%d" % b])
+    sym, ln = runs_of(idx, oracle)
+    assert rb3.fmd_image(sym, ln) == bytes(g["fmd"])
+    # texts through the two-step form, with a stray prefetch in between
+    tx = [np.ascontiguousarray(g["text%d" % b]) for b in range(n)]
+    idx2 = rb3.Index()
+    for b in range(n):
+        capi.check(L.rb3b_prefetch_batch(len(tx[b]), capi.ptr(tx[b])))
+        capi.check(L.rb3b_prefetch_batch(len(bw[0]), capi.ptr(bw[0])))   # never consumed
+        batch = rb3.Batch.prepare(tx[b])
+        assert np.array_equal(batch.bwt(), bw[b])
+        rb3.merge_prepared(idx2, batch)
+        batch.close()
+    s2, l2 = runs_of(idx2, oracle)
+    assert np.array_equal(s2, sym) and np.array_equal(l2, ln)
+    with pytest.raises(rb3.Rb3bError):
+        capi.check(L.rb3b_prefetch_batch(0, capi.ptr(bw[0])))
+
+
 def _fast_runs(rng, n_runs, max_len, big_every=0):
     sym = (np.cumsum(rng.integers(1, 6, n_runs)) % 6).astype(np.uint8)   # neighbours always differ
     ln = rng.integers(1, max_len + 1, n_runs).astype(np.int64)
