@@ -279,6 +279,90 @@ __global__ void k_write_walk(Fine F, int64_t len, const LfT *__restrict__ lf, co
 	for (int k = 0; k < nr; ++k) wrow[pos - 1 - k] = rv.last(k);
 }
 
+/* ---- one chase instead of two (large batches: the LF table is far bigger than L2, every chase step is a DRAM access) ----
+ * k_fine_walk_buf is k_fine_walk that also KEEPS what it meets: the first `cap` (row, symbol) pairs of every piece go to a
+ * piece-major buffer (cap entries per piece, written as whole 16-byte / 8-byte words), and the row of step `cap` is
+ * remembered for the few pieces that are longer.  k_copy_walk then moves the buffered pairs to their walk-order positions
+ * -- streaming reads -- and chases only the tails beyond `cap` (cap = 2 x the mean piece length: 13.5% of the rows). */
+template<typename LfT, typename RowT>
+__global__ void k_fine_walk_buf(Fine F, const LfT *__restrict__ lf, FNode *__restrict__ node, int32_t *__restrict__ piece_len,
+                                RowT *__restrict__ rowbuf, uint8_t *__restrict__ symbuf, int cap, RowT *__restrict__ tail_row)
+{
+	const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (f >= F.n_fine) return;
+	int64_t kb = F.row(f), n = 0, nx = -1;
+	RowT *rb = rowbuf + f * cap;
+	uint8_t *sb = symbuf + f * cap;
+	RowVec<RowT> rv;
+	uint64_t sw = 0;
+	for (;;) {
+		const uint64_t x = __ldg(lf + kb);
+		const uint64_t c = x & 7;
+		if (n < cap) {
+			rv.push((RowT)kb);
+			sw = sw >> 8 | c << 56;
+			if (((n + 1) & (RowVec<RowT>::N - 1)) == 0) rv.store(rb + n + 1 - RowVec<RowT>::N);
+			if (((n + 1) & 7) == 0) *(uint64_t*)(sb + n - 7) = sw;
+		}
+		++n;
+		if (c == 0) break; /* first symbol of the sequence: the chain ends here, fm-index.c:170 */
+		kb = (int64_t)(x >> LF_SHIFT);
+		if (n == cap) tail_row[f] = (RowT)kb; /* where the part that is not buffered starts */
+		if (F.is_mark(kb)) { nx = F.of_row(kb); break; }
+	}
+	const int64_t nbuf = n < cap ? n : cap; /* partial last words */
+	for (int k = 0; k < (int)(nbuf & (RowVec<RowT>::N - 1)); ++k) rb[nbuf - 1 - k] = rv.last(k);
+	for (int k = 0; k < (int)(nbuf & 7); ++k) sb[nbuf - 1 - k] = (uint8_t)(sw >> (56 - 8 * k));
+	node[f] = fnode(n, (int32_t)nx, (int32_t)f);
+	piece_len[f] = (int32_t)n;
+}
+
+template<typename LfT, typename RowT>
+__global__ void k_copy_walk(Fine F, int64_t len, const LfT *__restrict__ lf, const FNode *__restrict__ node,
+                            const int64_t *__restrict__ chain_of, const int64_t *__restrict__ chain_base, const int64_t *__restrict__ chain_len,
+                            const int32_t *__restrict__ piece_len, const RowT *__restrict__ rowbuf, const uint8_t *__restrict__ symbuf, int cap,
+                            const RowT *__restrict__ tail_row, RowT *__restrict__ wrow, uint8_t *__restrict__ wsym)
+{
+	const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (f >= F.n_fine) return;
+	const FNode me = node[f];
+	const int64_t p = chain_of[fnode_term(me)];
+	if (p < 0) return; /* not on a chain that starts at a sentinel: not a valid BWT, reported by the caller */
+	int64_t pos = chain_base[p] + chain_len[p] - me.x;
+	const int plen = piece_len[f];
+	if (pos < 0 || pos + me.x > len) return; /* cannot happen for a valid BWT */
+	const RowT *rb = rowbuf + f * cap;
+	const uint8_t *sb = symbuf + f * cap;
+	uint64_t sw = 0;
+	int ns = 0, nr = 0; /* symbols / rows collected */
+	RowVec<RowT> rv;
+	rv.r[0] = rv.r[1] = 0; if (RowVec<RowT>::N == 4) { rv.r[RowVec<RowT>::N - 2] = 0; rv.r[RowVec<RowT>::N - 1] = 0; }
+	int64_t kb = 0;
+	for (int k = 0; k < plen; ++k) {
+		uint64_t c;
+		if (k < cap) { kb = (int64_t)rb[k]; c = sb[k]; }
+		else {
+			if (k == cap) kb = (int64_t)tail_row[f];
+			const uint64_t x = __ldg(lf + kb);
+			c = x & 7;
+			if (ns == 0 && (pos & 7) != 0) wsym[pos] = (uint8_t)c;
+			else { sw = sw >> 8 | c << 56; if (++ns == 8) { *(uint64_t*)(wsym + pos - 7) = sw; ns = 0; } }
+			if (nr == 0 && (pos & (RowVec<RowT>::N - 1)) != 0) wrow[pos] = (RowT)kb;
+			else { rv.push((RowT)kb); if (++nr == RowVec<RowT>::N) { rv.store(wrow + pos - (RowVec<RowT>::N - 1)); nr = 0; } }
+			++pos;
+			kb = (int64_t)(x >> LF_SHIFT);
+			continue;
+		}
+		if (ns == 0 && (pos & 7) != 0) wsym[pos] = (uint8_t)c; /* unaligned head */
+		else { sw = sw >> 8 | c << 56; if (++ns == 8) { *(uint64_t*)(wsym + pos - 7) = sw; ns = 0; } }
+		if (nr == 0 && (pos & (RowVec<RowT>::N - 1)) != 0) wrow[pos] = (RowT)kb;
+		else { rv.push((RowT)kb); if (++nr == RowVec<RowT>::N) { rv.store(wrow + pos - (RowVec<RowT>::N - 1)); nr = 0; } }
+		++pos;
+	}
+	for (int k = 0; k < ns; ++k) wsym[pos - 1 - k] = (uint8_t)(sw >> (56 - 8 * k));
+	for (int k = 0; k < nr; ++k) wrow[pos - 1 - k] = rv.last(k);
+}
+
 /* ------------------------------------------------------------------ */
 /* sliced LF walk over A                                                */
 /* ------------------------------------------------------------------ */
@@ -966,11 +1050,21 @@ static int walk_order(int64_t len, const uint8_t *d_bwt, int64_t nt, const int64
 	TRY(nd.alloc(f_pad * 2)); TRY(fc.alloc(F.n_fine)); TRY(ch.alloc(F.n_seq * 2)); TRY(pl.alloc(F.n_fine));
 	FNode *pp[2] = { nd.p, nd.p + f_pad };
 	int64_t *f_cof = fc.p, *c_len = ch.p, *c_base = ch.p + F.n_seq;
+	/* one chase instead of two (k_fine_walk_buf / k_copy_walk) where a chase step is a DRAM access: batches from 2^25 rows on
+	 * ("piece_buf": 0 never, 1 always, -1 by size); single device only (with several, the walks are split by different keys) */
+	const int64_t pbuf = rb3b_get_param("piece_buf", -1);
+	const bool use_buf = !share && n_parts == 1 && (pbuf > 0 || (pbuf < 0 && len >= (32LL << 20)));
+	const int cap = F.fshift >= 2 ? (int)(2LL << F.fshift) : 8; /* twice the mean piece length; a multiple of 8 (whole-word stores) */
+	DBuf<RowT> rowbuf, tail_row;
+	DBuf<uint8_t> symbuf;
 	if (share) {
 		const int64_t f_lo = f_chunk * part, f_hi = f_lo + f_chunk < F.n_fine ? f_lo + f_chunk : F.n_fine;
 		if (f_hi > f_lo) { k_fine_walk<LfT><<<nblk(f_hi - f_lo, TPB), TPB, 0, rb3b_stream>>>(F, lf.p, pp[0], pl.p, f_lo, f_hi); CKK(); }
 		TRY(rb3b_all_gather(pp[0] + f_lo, pp[0], (size_t)f_chunk * sizeof(FNode)));
 		k_piece_len<<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F.n_fine, pp[0], pl.p); CKK();
+	} else if (use_buf) {
+		TRY(rowbuf.alloc((size_t)F.n_fine * cap)); TRY(symbuf.alloc((size_t)F.n_fine * cap)); TRY(tail_row.alloc(F.n_fine));
+		k_fine_walk_buf<LfT, RowT><<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, lf.p, pp[0], pl.p, rowbuf.p, symbuf.p, cap, tail_row.p); CKK();
 	} else { k_fine_walk<LfT><<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, lf.p, pp[0], pl.p, 0, F.n_fine); CKK(); }
 	int cur = 0, n_rounds = 0;
 	for (int64_t span = 1; span < F.n_fine; span <<= 1) ++n_rounds;
@@ -994,7 +1088,8 @@ static int walk_order(int64_t len, const uint8_t *d_bwt, int64_t nt, const int64
 	/* (Tried: the pieces sorted by length with one 8-bit radix pass, so that the lanes of a warp run equally long and the
 	 * longest chases start first -- ncu shows 8.4 of 32 lanes busy here.  Slower: 0.57 vs 0.51 ms of prep with one genome
 	 * per batch, 6.5 vs 5.6 ms with ten; neighbouring pieces start at neighbouring rows, the sorted order gives that up.) */
-	k_write_walk<LfT, RowT><<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, len, lf.p, node, f_cof, c_base, c_len, pl.p, p_lo, p_hi, wrow.p, wsym.p); CKK();
+	if (use_buf) { k_copy_walk<LfT, RowT><<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, len, lf.p, node, f_cof, c_base, c_len, pl.p, rowbuf.p, symbuf.p, cap, tail_row.p, wrow.p, wsym.p); CKK(); }
+	else { k_write_walk<LfT, RowT><<<nblk(F.n_fine, TPB), TPB, 0, rb3b_stream>>>(F, len, lf.p, node, f_cof, c_base, c_len, pl.p, p_lo, p_hi, wrow.p, wsym.p); CKK(); }
 	*wrow_out = wrow.p; *chain_base_out = c_base; *chain_len_out = c_len; /* arena memory: lives until the API call returns */
 	if (lf_out) *lf_out = lf.p;
 	return RB3B_OK;
@@ -1112,7 +1207,7 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	const unsigned wgrid = (unsigned)(want < cap ? want : cap);
 	/* transfer masks of the unresolved rows (16 bytes per row of the batch): only for batches that can afford them */
 	DBuf<uint4> wmask;
-	const bool use_mask = pair && len <= rb3b_get_param("mask_max_rows", 1LL << 28);
+	const bool use_mask = pair && len <= rb3b_get_param("mask_max_rows", 1LL << 32); /* 16 bytes per row: every batch the device can hold (rb3b_max_batch_symbols counts them) */
 	if (use_mask) TRY(wmask.alloc(len + 64));
 	const bool use_log = bm && rb3b_get_param("fix_log", 1) != 0;
 	if (so) {

@@ -322,7 +322,7 @@ extern "C" int64_t rb3b_max_batch_symbols(int64_t index_symbols)
 	int64_t avail = (int64_t)tot - (int64_t)(tot >> 4) - 2 * index_symbols; /* what this process already holds counts as available */
 	const int64_t other = (int64_t)tot - (int64_t)fr - (int64_t)rb3b_cur()->high; /* held by anybody, minus (roughly) our own scratch */
 	if (other > (int64_t)(tot >> 2)) avail -= other - (int64_t)(tot >> 2); /* a device that is visibly shared: be conservative */
-	int64_t n = avail / (int64_t)rb3b_get_param("batch_bytes_per_symbol", 72 + 44);
+	int64_t n = avail / (int64_t)rb3b_get_param("batch_bytes_per_symbol", 72 + 16 + 44) /* merge arrays + transfer masks + the suffix sort of the next batch */;
 	const int64_t cap = (1LL << 32) - 4096;
 	if (n > cap) n = cap;
 	return n > 0 ? n : 0;
