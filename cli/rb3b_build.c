@@ -358,11 +358,99 @@ static int usage(FILE *fp)
 	fprintf(fp, "  -t INT / -p INT  accepted for compatibility; the device provides the parallelism\n");
 	fprintf(fp, "  -2 / -s / -r   ropebwt2 insertion: input order / RLO / RCLO (mr_insert_multi)\n");
 	fprintf(fp, "  -T -e    not supported by this engine (tree dump: there is no tree; BRE)\n");
-	fprintf(fp, "Environment: RB3B_DEVICE=<cuda device>\n");
+	fprintf(fp, "Environment: RB3B_DEVICE=<cuda device>   RB3B_DEVICES=<d0,d1,...>  several devices: one replica of the index each,\n             the rank phase of every merge split among them (rb3b_merge_plain_dist over NCCL)\n");
 	return fp == stdout ? 0 : 1;
 }
 
 #define DIE_IF(rc, what) do { if ((rc) < 0) { fprintf(stderr, "ERROR: %s: %s\n", what, rb3b_last_error()); exit(1); } } while (0)
+
+/* ---- several devices (RB3B_DEVICES=d0,d1,...): one replica of the index per device, one host thread per device ----
+ * Every thread is a rank of the library's NCCL communicator and takes part in every merge with rb3b_merge_plain_dist:
+ * the rows of the batch are split among the devices for the rank phase, the interleave positions are combined over
+ * NVLink, every replica applies the same merge.  The main thread is rank 0 (it also reads, sorts and writes); the others
+ * only merge.  A failure on any rank ends the process: the other ranks would wait in a collective for ever. */
+typedef struct {
+	int world;
+	unsigned char uid[128];
+	const char *fn_in;            /* -i: every replica loads the index itself */
+	int64_t est_symbols;
+	pthread_mutex_t mu; pthread_cond_t cv;
+	int64_t gen;                  /* batches posted so far */
+	const uint8_t *bwt; int64_t len; /* the batch of generation `gen` (host memory, valid until everybody is done with it) */
+	int quit, n_done, n_ready;
+} mdev_t;
+
+typedef struct { mdev_t *m; int rank, device; pthread_t tid; } mdev_worker_t;
+
+#define MDEV_DIE(cond, what) do { if (cond) { fprintf(stderr, "ERROR: device %d: %s: %s\n", w->device, what, rb3b_last_error()); exit(1); } } while (0)
+
+static void *mdev_main(void *arg)
+{
+	mdev_worker_t *w = (mdev_worker_t*)arg;
+	mdev_t *m = w->m;
+	rb3b_ctx_t *ctx = rb3b_ctx_create(w->device);
+	rb3b_index_t *idx;
+	int64_t seen = 0;
+	int reserved = 0;
+	MDEV_DIE(ctx == 0, "no context");
+	MDEV_DIE(rb3b_ctx_make_current(ctx) < 0, "context");
+	MDEV_DIE(rb3b_dist_init(w->rank, m->world, m->uid) < 0, "joining the communicator");
+	idx = rb3b_index_create();
+	if (m->fn_in) {
+		int64_t acc0[7];
+		MDEV_DIE(rb3b_restore(idx, m->fn_in) < 0, "loading the index");
+		rb3b_index_reserve(idx, rb3b_get_acc(idx, acc0) + m->est_symbols); reserved = 1;
+	}
+	pthread_mutex_lock(&m->mu); ++m->n_ready; pthread_cond_broadcast(&m->cv); pthread_mutex_unlock(&m->mu);
+	for (;;) {
+		const uint8_t *bwt; int64_t len;
+		pthread_mutex_lock(&m->mu);
+		while (m->gen == seen && !m->quit) pthread_cond_wait(&m->cv, &m->mu);
+		if (m->gen == seen) { pthread_mutex_unlock(&m->mu); break; } /* quit */
+		bwt = m->bwt; len = m->len; seen = m->gen;
+		pthread_mutex_unlock(&m->mu);
+		MDEV_DIE(rb3b_merge_plain_dist(idx, len, bwt) < 0, "merging the partial BWT");
+		if (!reserved) { rb3b_index_reserve(idx, m->est_symbols); reserved = 1; }
+		pthread_mutex_lock(&m->mu); ++m->n_done; pthread_cond_broadcast(&m->cv); pthread_mutex_unlock(&m->mu);
+	}
+	rb3b_index_destroy(idx);
+	rb3b_dist_finalize();
+	rb3b_ctx_make_current(0);
+	rb3b_ctx_destroy(ctx);
+	return 0;
+}
+
+/* rank 0's side of one merge: hand the batch to the other ranks, take part, wait for them */
+static int mdev_merge(mdev_t *m, rb3b_index_t *idx, int64_t len, const uint8_t *bwt)
+{
+	int rc;
+	pthread_mutex_lock(&m->mu);
+	m->bwt = bwt; m->len = len; m->n_done = 0; ++m->gen;
+	pthread_cond_broadcast(&m->cv);
+	pthread_mutex_unlock(&m->mu);
+	rc = rb3b_merge_plain_dist(idx, len, bwt);
+	pthread_mutex_lock(&m->mu);
+	while (m->n_done < m->world - 1) pthread_cond_wait(&m->cv, &m->mu);
+	pthread_mutex_unlock(&m->mu);
+	return rc;
+}
+
+/* RB3B_DEVICES -> device ordinals; returns how many (0 or 1: single-device operation) */
+static int mdev_parse(int *dev, int max)
+{
+	const char *e = getenv("RB3B_DEVICES");
+	int n = 0;
+	if (e == 0) return 0;
+	while (*e && n < max) {
+		char *q;
+		long v = strtol(e, &q, 10);
+		if (q == e) break;
+		dev[n++] = (int)v;
+		e = *q == ',' ? q + 1 : q;
+	}
+	return n;
+}
+
 
 int main(int argc, char *argv[])
 {
@@ -371,6 +459,10 @@ int main(int argc, char *argv[])
 	int64_t batch = 7000000000LL, est_symbols = 0;
 	int reserved = 0;
 	const char *fn_in = 0, *fn_tmp = 0;
+	int n_dev = 0, devs[16];       /* RB3B_DEVICES */
+	mdev_t M;
+	mdev_worker_t W[16];
+	uint8_t *hb = 0; int64_t hb_cap = 0; /* several devices: the batch's BWT in pinned host memory */
 
 	rb3b_index_t *idx = 0;
 
@@ -485,7 +577,20 @@ int main(int argc, char *argv[])
 	if (est_symbols > 40000000000LL) est_symbols = 40000000000LL;
 	if (no_for && no_rev) { fprintf(stderr, "ERROR: -F and -R together leave nothing to index\n"); return 1; }
 
-	DIE_IF(rb3b_init(getenv("RB3B_DEVICE") ? atoi(getenv("RB3B_DEVICE")) : 0), "no usable CUDA device");
+	n_dev = use_rb2 ? 0 : mdev_parse(devs, 16); /* -2/-s/-r: one device */
+	DIE_IF(rb3b_init(n_dev > 1 ? devs[0] : getenv("RB3B_DEVICE") ? atoi(getenv("RB3B_DEVICE")) : 0), "no usable CUDA device");
+	if (n_dev > 1) {
+		memset(&M, 0, sizeof(M));
+		M.world = n_dev; M.fn_in = fn_in; M.est_symbols = est_symbols;
+		pthread_mutex_init(&M.mu, 0); pthread_cond_init(&M.cv, 0);
+		DIE_IF(rb3b_dist_unique_id(M.uid), "NCCL");
+		for (i = 1; i < n_dev; ++i) {
+			W[i].m = &M; W[i].rank = i; W[i].device = devs[i];
+			if (pthread_create(&W[i].tid, 0, mdev_main, &W[i]) != 0) { fprintf(stderr, "ERROR: failed to start the thread of device %d\n", devs[i]); return 1; }
+		}
+		DIE_IF(rb3b_dist_init(0, n_dev, M.uid), "joining the communicator");
+		LOG("%d devices, one replica of the index each", n_dev);
+	}
 	if (fn_in) {
 		idx = rb3b_index_create();
 		if (rb3b_restore(idx, fn_in) < 0) { /* build.c:175-178 */
@@ -530,6 +635,17 @@ int main(int argc, char *argv[])
 					}
 					DIE_IF(rb3b_insert_multi_dev(idx, db->len, (const uint8_t*)db->d), "inserting the batch");
 					LOG("inserted %ld symbols", (long)db->len);
+				} else if (n_dev > 1) { /* every device takes part: the batch's BWT goes through host memory to all of them */
+					if (db->len > hb_cap) {
+						rb3b_host_free_pinned(hb);
+						hb_cap = db->len + (db->len >> 2);
+						hb = (uint8_t*)rb3b_host_alloc_pinned(hb_cap);
+						if (hb == 0) { fprintf(stderr, "ERROR: pinned host memory: %s\n", rb3b_last_error()); return 1; }
+					}
+					DIE_IF(rb3b_d2h(hb, rb3b_batch_bwt_dev(db->pb), db->len), "device to host copy");
+					if (idx == 0) idx = rb3b_index_create();
+					DIE_IF(mdev_merge(&M, idx, db->len, hb), "merging the partial BWT"); /* rb3_fmi_merge_plain (rb3_enc_plain2fmr on an empty index) */
+					LOG("merged the partial BWT for %ld symbols on %d devices", (long)db->len, n_dev);
 				} else if (idx == 0) {
 					idx = rb3b_index_create();
 					DIE_IF(rb3b_merge_prepared(idx, db->pb), "encoding the partial BWT"); /* rb3_enc_plain2fmr: the index is empty */
@@ -549,6 +665,11 @@ int main(int argc, char *argv[])
 			dpipe_release(&Q);
 		}
 		LOG("all batches merged");
+		if (n_dev > 1) {
+			pthread_mutex_lock(&M.mu); M.quit = 1; pthread_cond_broadcast(&M.cv); pthread_mutex_unlock(&M.mu);
+			for (i = 1; i < n_dev; ++i) pthread_join(W[i].tid, 0);
+			rb3b_host_free_pinned(hb);
+		}
 		pthread_join(tid2, 0);
 		if (Q.failed) return 1;
 		rb3b_dev_free(Q.slot[0].d); rb3b_dev_free(Q.slot[1].d);

@@ -67,6 +67,29 @@ def test_multi_file_build_fmd(files):
     assert got == want and len(got) > 1000
 
 
+def test_multi_device_build(files, tmp_path):
+    """RB3B_DEVICES=0,1[,2,3]: one host thread and one replica of the index per device, every merge through
+    rb3b_merge_plain_dist; the output must be the reference's, also when appending to an existing .fmr (-i)."""
+    import torch
+    n = min(torch.cuda.device_count(), 4)
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, RB3B_DEVICES=",".join(str(i) for i in range(n)))
+
+    def run_md(args):
+        p = subprocess.run([CLI] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=600)
+        assert p.returncode == 0, p.stderr.decode()[-800:]
+        assert ("%d devices" % n).encode() in p.stderr
+        return p.stdout
+
+    want = run(files["ref"], ["build", "-t4", "-d"] + files["fa"]).stdout
+    assert run_md(["build", "-d"] + files["fa"]) == want
+    assert run_md(["build", "-d", "-m", "50k", files["multi"]]) == run(files["ref"], ["build", "-d", "-m", "50k", files["multi"]]).stdout
+    first = str(tmp_path / "first.fmr")
+    run(CLI, ["build", "-b", "-o", first] + files["fa"][:3])
+    assert run_md(["build", "-d", "-i", first] + files["fa"][3:]) == want
+
+
 @pytest.mark.parametrize("opts", [["-m", "50k"], ["-m", "7g"], ["-R"], ["-F"], ["-m", "100k", "-R"]])
 def test_single_file_batches(files, opts):
     want = run(files["ref"], ["build", "-d"] + opts + [files["multi"]]).stdout
