@@ -580,6 +580,10 @@ int main(int argc, char *argv[])
 	n_dev = use_rb2 ? 0 : mdev_parse(devs, 16); /* -2/-s/-r: one device */
 	DIE_IF(rb3b_init(n_dev > 1 ? devs[0] : getenv("RB3B_DEVICE") ? atoi(getenv("RB3B_DEVICE")) : 0), "no usable CUDA device");
 	if (n_dev > 1) {
+		/* NCCL writes its version banner (NCCL_DEBUG=VERSION) to stdout, where the index goes: keep it out */
+		const char *nd = getenv("NCCL_DEBUG");
+		if (nd == 0 || strcmp(nd, "VERSION") == 0 || strcmp(nd, "version") == 0) setenv("NCCL_DEBUG", "WARN", 1);
+		setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
 		memset(&M, 0, sizeof(M));
 		M.world = n_dev; M.fn_in = fn_in; M.est_symbols = est_symbols;
 		pthread_mutex_init(&M.mu, 0); pthread_cond_init(&M.cv, 0);
