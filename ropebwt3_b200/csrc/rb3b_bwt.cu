@@ -75,6 +75,40 @@ __global__ void k_kmer_keys6(uint32_t n, const uint8_t *__restrict__ T, int n_sy
 	key[i] = (k << 1 | (uint64_t)ended) << POS_BITS | (uint64_t)i;
 }
 
+/* the same keys, eight consecutive positions per thread from three aligned 8-byte loads (T must be 8-byte aligned): the
+ * byte loads of k_kmer_keys6 -- fifteen per suffix -- were most of its time */
+__global__ void k_kmer_keys6x8(uint32_t n, const uint8_t *__restrict__ T, int n_sym, uint64_t *__restrict__ key, int *__restrict__ bad)
+{
+	const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8u;
+	if (i0 >= n) return;
+	uint64_t w[3];
+#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		const uint32_t p = i0 + 8u * k;
+		if (p + 8u <= n) w[k] = __ldg((const uint64_t*)(T + p));
+		else { /* the last words of the text: byte by byte, nothing past the end */
+			w[k] = 0;
+			for (int b = 0; b < 8; ++b) if (p + b < n) w[k] |= (uint64_t)T[p + b] << (8 * b);
+		}
+	}
+	int any_bad = 0;
+#pragma unroll
+	for (int r = 0; r < 8; ++r) {
+		uint64_t k = 0;
+		int ended = 0;
+#pragma unroll
+		for (int j = 0; j < KMER6; ++j) {
+			const int q = r + j; /* byte q of the 24 loaded ones */
+			int c = ended ? 0 : (int)((w[q >> 3] >> (8 * (q & 7))) & 0xff);
+			if (c >= n_sym) { any_bad = 1; c = 5; }
+			k = k * 6 + (uint64_t)c;
+			if (c == 0) ended = 1;
+		}
+		if (i0 + r < n) key[i0 + r] = (k << 1 | (uint64_t)ended) << POS_BITS | (uint64_t)(i0 + r);
+	}
+	if (any_bad) *bad = 1;
+}
+
 /* group heads of the keys-only round + the suffix array stretch it implies */
 __global__ void k_group_heads6(uint32_t n, const uint64_t *__restrict__ key, uint32_t *__restrict__ head, uint32_t *__restrict__ sa)
 {
@@ -234,7 +268,8 @@ static int suffix_sort(int64_t len, const uint8_t *d_text, DBuf<uint32_t> &sa, i
 	const bool keys_only = n < (1u << POS_BITS) && n_sym <= 6 && rb3b_get_param("sa_keys_only", 1) != 0; /* base 6: not for the augmented alphabet of the sorted orders */
 	const uint64_t kmer = keys_only ? KMER6 : KMER;
 	if (keys_only) {
-		k_kmer_keys6<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, d_text, n_sym, key0.p, bad.p); CKK();
+		if (((uintptr_t)d_text & 7) == 0 && rb3b_get_param("sa_keys_x8", 1) != 0) { k_kmer_keys6x8<<<nblk((n + 7) / 8, TPB), TPB, 0, rb3b_stream>>>(n, d_text, n_sym, key0.p, bad.p); CKK(); }
+		else { k_kmer_keys6<<<nblk(n, TPB), TPB, 0, rb3b_stream>>>(n, d_text, n_sym, key0.p, bad.p); CKK(); }
 		size_t tb = 0;
 		CK(cub::DeviceRadixSort::SortKeys((void*)0, tb, key0.p, key1.p, (int64_t)n, POS_BITS, 64, rb3b_stream));
 		DBuf<uint8_t> t;

@@ -365,7 +365,7 @@ def test_build_bwt_golden(rb3, golden):
         rb3.rb3_build_sais(np.array([1, 2, 3], np.uint8))  # no trailing sentinel (mrope.c:310)
 
 
-@pytest.mark.parametrize("knob,value", [("sa_keys_only", 0), ("sa_discard", 0)])
+@pytest.mark.parametrize("knob,value", [("sa_keys_only", 0), ("sa_discard", 0), ("sa_keys_x8", 0)])
 def test_suffix_sorter_paths(rb3, golden, knob, value):
     """The suffix sorter's other paths -- 21-symbol key/value round 0 instead of the keys-only 15-symbol round of small
     batches, and refinement rounds that re-sort everything -- give libsais' BWT as well."""
