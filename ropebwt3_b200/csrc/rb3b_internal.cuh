@@ -336,6 +336,56 @@ template<int G_> struct Grp {
 	}
 };
 
+/* Run-length cells, ONE thread per rank (the arithmetic of k_lf_t1, rb3b_index.cu): the header quad of the symbol's half,
+ * then the entry quads one after the other until the offset is reached.  As a walk ranker (G = 1) it costs ~10x fewer warp
+ * instructions per row than the 8-lane groups: ncu showed the Grp<8> walk bound by instruction issue (135 warp instructions
+ * per row, instruction-cache misses), not by memory. */
+struct RleT1 {
+	static const int G = 1;
+	static const bool ALWAYS2 = false;
+	__device__ __forceinline__ static int lane() { return 0; }
+	__device__ __forceinline__ static int base() { return threadIdx.x & 31; }
+	__device__ __forceinline__ static unsigned mask() { return 1u << (threadIdx.x & 31); }
+	__device__ __forceinline__ static int64_t count(const DevIndex &x, int64_t k, int c)
+	{ /* 0 <= k < n */
+		const uint4 *cell = x.cells + (k >> x.shift) * 8;
+		const int h = c >= 3, cc = c - 3 * h;
+		const uint4 hq = __ldg(cell + h);
+		uint4 e0 = __ldg(cell + 2), e1 = __ldg(cell + 3); /* in flight together with the header */
+		uint64_t a0, a1, a2;
+		rb3b_hdr_unpack(hq, a0, a1, a2);
+		const uint64_t basec = cc == 0 ? a0 : cc == 1 ? a1 : a2;
+		const uint32_t off = (uint32_t)k & ((1u << x.shift) - 1u);
+		uint32_t cnt = 0;
+		if (hq.w >> 31) cnt = rb3b_ovf_count(cell, x.ovf, off, c); /* the overflow flag is repeated in both header quads */
+		else {
+			uint32_t rem = off;
+#pragma unroll 1
+			for (int qd = 2; qd < 8 && rem > 0; qd += 2) {
+				if (qd > 2) { e0 = __ldg(cell + qd); e1 = __ldg(cell + qd + 1); }
+				const uint32_t w[8] = { e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w };
+#pragma unroll
+				for (int i = 0; i < 16; ++i) {
+					const uint32_t e = (w[i >> 1] >> (16 * (i & 1))) & 0xffffu, l = e & RB3B_LEN_MASK, take = min(l, rem);
+					cnt += (e >> 13) == (uint32_t)c ? take : 0u;
+					rem -= take;
+				}
+			}
+		}
+		return (int64_t)(basec + cnt);
+	}
+	__device__ __forceinline__ static int64_t rank(const DevIndex &x, int64_t k, int c)
+	{
+		const int64_t kk = k < x.n ? (k < 0 ? 0 : k) : x.n - 1;
+		const int64_t r = count(x, kk, c);
+		return k < x.n ? r : x.tot[c];
+	}
+	__device__ __forceinline__ static void rank2(const DevIndex &x, int64_t k1, int64_t k2, int c, int64_t &r1, int64_t &r2)
+	{
+		r1 = rank(x, k1, c); r2 = rank(x, k2, c);
+	}
+};
+
 /* Sequential reader of the symbols of an index from a given position on (used by the merge and the export) */
 struct CellReader {
 	const uint4 *cells, *ovf;

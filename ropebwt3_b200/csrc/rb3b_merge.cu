@@ -1200,8 +1200,10 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 	const bool bm = A->kind == RB3B_KIND_BM;
 	/* bitmap walks are lane pairs (single threads in the fix-up): small CTAs spread the walks over all SMs */
 	const bool pair = bm && rb3b_get_param("walk_pair", 1) != 0;
-	const int wg = bm ? (pair ? 2 : 1) : 8, wtpb = bm ? 32 : TPB;
-	int64_t want = (n_walk * wg + wtpb - 1) / wtpb, cap = (int64_t)n_sm() * (bm ? 32 : 8);
+	/* run-length cells: one thread per walk as well ("rle_t1"; 0: groups of 8 lanes, ~10x the instructions per row) */
+	const bool t1 = !bm && rb3b_get_param("rle_t1", 1) != 0;
+	const int wg = bm ? (pair ? 2 : 1) : t1 ? 1 : 8, wtpb = (bm || t1) ? 32 : TPB;
+	int64_t want = (n_walk * wg + wtpb - 1) / wtpb, cap = (int64_t)n_sm() * ((bm || t1) ? 32 : 8);
 	if (want < 1) want = 1;
 	rb3b_tic(T_WALK1);
 	const unsigned wgrid = (unsigned)(want < cap ? want : cap);
@@ -1217,10 +1219,12 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 		CKK();
 		if (pair) k_walk_pair<true><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, use_mask ? wmask.p : 0, warm, ctr.p);
 		else if (bm) k_walk_first<BmRank, true><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
+		else if (t1) k_walk_first<RleT1, true><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
 		else k_walk_first<Grp<8>, true><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
 	} else {
 		if (pair) k_walk_pair<false><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, use_mask ? wmask.p : 0, warm, ctr.p);
 		else if (bm) k_walk_first<BmRank, false><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
+		else if (t1) k_walk_first<RleT1, false><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
 		else k_walk_first<Grp<8>, false><<<wgrid, wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, ctr.p);
 	}
 	CKK();
@@ -1296,6 +1300,8 @@ static int rank_phase(const rb3b_index_s *A, int64_t len, const uint8_t *d_bwt, 
 		rb3b_tic(T_WALKFIX);
 		if (use_log) { TRY(launch_fix_chain(dA, S, wsym.p, kseq.p, use_mask ? wmask.p : 0, n_items, wl_seg[cur], wl_val[cur], (unsigned long long*)(ctr.p + 4), 1)); --rb3b_n_launch; }
 		else if (bm) k_walk_fix<BmRank><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, n_items, wl_seg[cur], wl_val[cur], ctr.p + 2,
+			wl_seg[cur ^ 1], wl_val[cur ^ 1], (unsigned long long*)(ctr.p + 3));
+		else if (t1) k_walk_fix<RleT1><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, n_items, wl_seg[cur], wl_val[cur], ctr.p + 2,
 			wl_seg[cur ^ 1], wl_val[cur ^ 1], (unsigned long long*)(ctr.p + 3));
 		else k_walk_fix<Grp<8> ><<<(unsigned)(want < cap ? want : cap), wtpb, 0, rb3b_stream>>>(dA, S, wsym.p, kseq.p, n_items, wl_seg[cur], wl_val[cur], ctr.p + 2,
 			wl_seg[cur ^ 1], wl_val[cur ^ 1], (unsigned long long*)(ctr.p + 3));

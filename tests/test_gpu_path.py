@@ -327,14 +327,14 @@ def test_bitmap_to_rle_transition(rb3, oracle, golden):
 
 
 @pytest.mark.parametrize("knob,value", [("fix_log", 0), ("wide_lf", 1), ("fine_len", 7), ("fine_len", 1), ("scatter_win_bits", 5), ("walk_pair", 0),
-                                        ("warm_rows", 0), ("warm_rows", 40), ("mask_max_rows", 0), ("async_merge", 1), ("fix_tables", 1), ("fix_tpb", 16), ("fix_stages", 2), ("emit_staged", 0), ("piece_buf", 1), ("piece_buf", 0)])
+                                        ("warm_rows", 0), ("warm_rows", 40), ("mask_max_rows", 0), ("async_merge", 1), ("fix_tables", 1), ("fix_tpb", 16), ("fix_stages", 2), ("emit_staged", 0), ("piece_buf", 1), ("piece_buf", 0), ("rle_t1", 0)])
 def test_optional_code_paths(rb3, oracle, golden, knob, value):
     """The tuning knobs select other kernels (multi-round generic fix-up, 64-bit LF table and rows, other mark spacing,
     the two-pass bucketed scatter of large batches, single-lane walks, no / longer warm-up before a slice, no transfer
     masks: every row of the fix-up takes the general step); every one of them must give the reference's interleave
     array and merged index."""
     g = golden("merge_dup")
-    defaults = {"fix_log": 1, "wide_lf": 0, "fine_len": 0, "scatter_win_bits": 19, "walk_pair": 1, "warm_rows": 16, "mask_max_rows": 1 << 32, "async_merge": 0, "fix_tables": 0, "fix_tpb": 32, "fix_stages": 4, "emit_staged": 1, "piece_buf": -1}
+    defaults = {"fix_log": 1, "wide_lf": 0, "fine_len": 0, "scatter_win_bits": 19, "walk_pair": 1, "warm_rows": 16, "mask_max_rows": 1 << 32, "async_merge": 0, "fix_tables": 0, "fix_tpb": 32, "fix_stages": 4, "emit_staged": 1, "piece_buf": -1, "rle_t1": 1}
     rb3.set_param(knob, value)
     if knob == "scatter_win_bits":
         rb3.set_param("scatter_bucket_min", 1)
