@@ -188,13 +188,6 @@ __global__ void k_amb_gather(uint32_t m, const uint32_t *__restrict__ at, const 
 	suf[t] = sa[j]; grp[t] = head[j];
 }
 
-__global__ void k_amb_flags(uint32_t n, const uint32_t *__restrict__ head, uint8_t *__restrict__ flag)
-{
-	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= n) return;
-	flag[j] = head[j] != j || (j + 1 < n && head[j + 1] == head[j]);
-}
-
 /* second key of every listed suffix, and the segment starts (first list index of every group) */
 __global__ void k_list_keys(uint32_t m, uint32_t n, uint32_t h, const uint32_t *__restrict__ suf, const uint32_t *__restrict__ grp, const uint32_t *__restrict__ rank,
                             uint32_t *__restrict__ key, uint8_t *__restrict__ segflag)
@@ -460,7 +453,7 @@ extern "C" const uint8_t *rb3b_batch_bwt_dev(const rb3b_batch_t *b) { return b ?
 static int batch_prepare_i(rb3b_batch_s *B, int64_t len, const uint8_t *d_text)
 {
 	DBuf<uint32_t> sa, isa;
-	DBuf<int64_t> flag, sid, Z;
+	DBuf<int64_t> Z;
 	DBuf<unsigned long long> cnt;
 	TRY(isa.alloc(len));
 	rb3b_tic(T_BWT);
