@@ -34,8 +34,12 @@ def walk_order(b):
     return wrow, b[wrow], np.array(base, np.int64), np.array(length, np.int64), lf
 
 
-def interleave(a_bwt, b_bwt, seg_len=16, so=0, part=0, n_parts=1, halo=2):
-    """-> ka[len(b)] (or -1 for rows another part resolves) and the number of rows left unresolved."""
+def interleave(a_bwt, b_bwt, seg_len=16, so=0, part=0, n_parts=1, halo=2, warm=0, masks=False):
+    """-> ka[len(b)] (or -1 for rows another part resolves) and the number of rows left unresolved.
+    warm: rows walked before every slice to narrow its bracket (k_walk_pair).  masks: the walk leaves, for every
+    unresolved row whose bracket is at most 127 wide, the 128 bits of the row symbol's plane from `lo` on, and the fix-up
+    (k_fix_chain) advances by x' = popcount(mask below x) without looking at the index; rows without a mask take the
+    general step.  Both must give what the plain rank chain gives."""
     A, Bv = np.asarray(a_bwt, np.uint8), np.asarray(b_bwt, np.uint8)
     occ, acc = _occ(A)
     nA = len(A)
@@ -74,16 +78,26 @@ def interleave(a_bwt, b_bwt, seg_len=16, so=0, part=0, n_parts=1, halo=2):
     walk_lo = max(0, own_lo - halo) if n_parts > 1 else 0
     d = np.zeros(n_seg, np.int64)
     arr = [None] * n_seg
-    for s in range(walk_lo, own_hi):      # k_walk_first
+    tmask = {}                            # p -> (lo, 128-bit transfer mask) of the tight unresolved rows
+    for s in range(walk_lo, own_hi):      # k_walk_first / k_walk_pair
         p0 = s * seg_len
-        c0 = 0 if s == 0 else int(wsym[p0 - 1])
+        q0 = p0 if (so or s == 0) else max(0, p0 - warm)
+        c0 = 0 if q0 == 0 else int(wsym[q0 - 1])
         if c0 == 0:
             lo = hi = 0 if so else int(acc[1])
         else:
             lo, hi = int(acc[c0]), int(acc[c0 + 1])
+        for p in range(q0, p0):           # warm-up rows: results discarded
+            c = int(wsym[p])
+            if c == 0:
+                lo = hi = int(acc[1])
+            else:
+                lo, hi = int(acc[c]) + rank(c, lo), int(acc[c]) + rank(c, hi)
         for p in range(p0, min(n, p0 + seg_len)):
             c = int(wsym[p])
             f = int(kseq[p]) if so else 0
+            if masks and not so and lo != hi and hi - lo <= 127 and c != 0:
+                tmask[p] = (lo, sum(1 << i for i in range(128) if lo + i < nA and A[lo + i] == c))
             if f & HEAD:
                 kseq[p] = f & ~HEAD
                 lo = hi = 0
@@ -109,10 +123,22 @@ def interleave(a_bwt, b_bwt, seg_len=16, so=0, part=0, n_parts=1, halo=2):
             full = cnt == min(seg_len, n - p0)
             for p in range(p0, p0 + cnt):
                 c = int(wsym[p])
+                lo_p = int(kseq[p]) & ((1 << 42) - 1)
                 kseq[p] = v
                 if c == 0:
                     break
-                v = int(acc[c]) + rank(c, v)
+                nv = int(acc[c]) + rank(c, v)
+                if p in tmask:            # k_fix_chain: no index access
+                    lo_m, m = tmask[p]
+                    x = v - lo_p
+                    assert lo_m == lo_p and 0 <= x <= 127
+                    lo_next = (int(kseq[p + 1]) & ((1 << 42) - 1)) if p + 1 < p0 + cnt else None
+                    xn = bin(m & ((1 << x) - 1)).count("1")
+                    if lo_next is not None:
+                        assert lo_next + xn == nv, "transfer mask disagrees with the rank chain"
+                    else:                 # last unresolved row: the next row's low end is where the walk went on from
+                        assert int(acc[c]) + rank(c, lo_p) + xn == nv
+                v = nv
             d[t] = 0
             if full and c != 0:
                 arr[t] = (v, v)

@@ -18,6 +18,20 @@ def test_sliced_walk_reproduces_the_reference_interleave(oracle, golden, name, s
         sym, ln = oracle.merge_runs(sym, ln, g["rb%d" % b])
 
 
+@pytest.mark.parametrize("name", ["merge_small", "merge_dup"])
+@pytest.mark.parametrize("seg_len,warm", [(16, 0), (16, 8), (64, 16)])
+def test_warm_up_rows_and_transfer_masks(oracle, golden, name, seg_len, warm):
+    """k_walk_pair's warm-up and the mask-driven fix-up of k_fix_chain: x' = popcount(mask below x) must equal the rank
+    chain at every tight row (asserted inside the model) and the result must still be the reference's array."""
+    g = golden(name)
+    sym, ln = oracle.plain2runs(g["bwt0"])
+    for b in range(1, int(g["n_batches"])):
+        bwt = g["bwt%d" % b]
+        ka, unres = M.interleave(oracle.runs2plain(sym, ln), bwt, seg_len, warm=warm, masks=True)
+        assert unres == 0 and np.array_equal(M.pack_rb(ka, bwt), g["rb%d" % b]), (name, b)
+        sym, ln = oracle.merge_runs(sym, ln, g["rb%d" % b])
+
+
 @pytest.mark.parametrize("n_parts", [2, 3, 5])
 def test_sharded_slices_cover_the_batch(oracle, golden, n_parts):
     """Every part resolves its own slices from a halo; together they give the whole array (the all-reduce MAX)."""
