@@ -37,6 +37,11 @@ def test_no_cpu_fallback_without_device():
     assert "no CPU fallback" in str(e.value)
     with pytest.raises(R.Rb3bError):
         R.Index.from_plain(np.array([1, 0], np.uint8))
+    from ropebwt3_b200 import capi
+    buf = np.array([1, 2, 0], np.uint8)
+    assert capi.lib().rb3b_prefetch_batch(len(buf), capi.ptr(buf)) < 0          # no device: nothing is staged anywhere
+    assert not capi.lib().rb3b_batch_prepare(len(buf), capi.ptr(buf))           # NULL
+    assert capi.lib().rb3b_merge_plain_dist(None, len(buf), capi.ptr(buf)) < 0
 
 
 @pytest.mark.parametrize("name", ["merge_small", "merge_div", "merge_dup", "long_runs"])
