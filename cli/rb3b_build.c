@@ -150,18 +150,59 @@ static int rd_record(reader_t *r, str_t *rec, str_t *tmp)
 	return 0;
 }
 
+#if defined(__SSE2__) && !defined(RB3B_NO_SIMD)
+#include <emmintrin.h>
+/* nt6_table on 16 characters at once: a/c/g/t in either case -> 1..4, the raw codes 0..4 -> themselves, all else -> 5 */
+static inline __m128i nt6_map16(__m128i c)
+{
+	const __m128i l = _mm_or_si128(c, _mm_set1_epi8(0x20));
+	const __m128i isa = _mm_cmpeq_epi8(l, _mm_set1_epi8('a')), isc = _mm_cmpeq_epi8(l, _mm_set1_epi8('c'));
+	const __m128i isg = _mm_cmpeq_epi8(l, _mm_set1_epi8('g')), ist = _mm_cmpeq_epi8(l, _mm_set1_epi8('t'));
+	const __m128i raw = _mm_cmpeq_epi8(_mm_min_epu8(c, _mm_set1_epi8(4)), c); /* c <= 4 (unsigned) */
+	__m128i v = _mm_set1_epi8(5);
+	v = _mm_sub_epi8(v, _mm_and_si128(isa, _mm_set1_epi8(4)));
+	v = _mm_sub_epi8(v, _mm_and_si128(isc, _mm_set1_epi8(3)));
+	v = _mm_sub_epi8(v, _mm_and_si128(isg, _mm_set1_epi8(2)));
+	v = _mm_sub_epi8(v, _mm_and_si128(ist, _mm_set1_epi8(1)));
+	return _mm_or_si128(_mm_and_si128(raw, c), _mm_andnot_si128(raw, v));
+}
+/* codes 1..4 -> 5 - code (reverse complement), 0 and 5 stay */
+static inline __m128i nt6_comp16(__m128i v)
+{
+	const __m128i keep = _mm_or_si128(_mm_cmpeq_epi8(v, _mm_setzero_si128()), _mm_cmpeq_epi8(v, _mm_set1_epi8(5)));
+	return _mm_or_si128(_mm_and_si128(keep, v), _mm_andnot_si128(keep, _mm_sub_epi8(_mm_set1_epi8(5), v)));
+}
+static inline __m128i rev16(__m128i x)
+{ /* the 16 bytes in reverse order */
+	x = _mm_or_si128(_mm_slli_epi16(x, 8), _mm_srli_epi16(x, 8));
+	x = _mm_shufflelo_epi16(x, 0x1B);
+	x = _mm_shufflehi_epi16(x, 0x1B);
+	return _mm_shuffle_epi32(x, 0x4E);
+}
+#endif
+
 static void seq_add(str_t *seq, const str_t *rec, int is_for, int is_rev, int64_t *n_seq)
 { /* rb3_seq_add, io.c:84-102 */
 	size_t i, l = rec->l;
 	if (is_for) {
 		str_reserve(seq, seq->l + l + 1);
-		for (i = 0; i < l; ++i) { unsigned char c = (unsigned char)rec->s[i]; seq->s[seq->l + i] = c < 128 ? nt6_table[c] : 5; }
+		i = 0;
+#if defined(__SSE2__) && !defined(RB3B_NO_SIMD)
+		for (; i + 16 <= l; i += 16)
+			_mm_storeu_si128((__m128i*)(seq->s + seq->l + i), nt6_map16(_mm_loadu_si128((const __m128i*)(rec->s + i))));
+#endif
+		for (; i < l; ++i) { unsigned char c = (unsigned char)rec->s[i]; seq->s[seq->l + i] = c < 128 ? nt6_table[c] : 5; }
 		seq->s[seq->l + l] = 0;
 		seq->l += l + 1; ++*n_seq;
 	}
 	if (is_rev) {
 		str_reserve(seq, seq->l + l + 1);
-		for (i = 0; i < l; ++i) {
+		i = 0;
+#if defined(__SSE2__) && !defined(RB3B_NO_SIMD)
+		for (; i + 16 <= l; i += 16) /* output positions i..i+15 come from input l-16-i .. l-1-i, reversed */
+			_mm_storeu_si128((__m128i*)(seq->s + seq->l + i), rev16(nt6_comp16(nt6_map16(_mm_loadu_si128((const __m128i*)(rec->s + l - 16 - i))))));
+#endif
+		for (; i < l; ++i) {
 			unsigned char c = (unsigned char)rec->s[l - 1 - i];
 			int x = c < 128 ? nt6_table[c] : 5;
 			seq->s[seq->l + i] = (x >= 1 && x <= 4) ? 5 - x : x;
@@ -474,8 +515,10 @@ int main(int argc, char *argv[])
 		batch_t *b;
 		memset(&P, 0, sizeof(P));
 		--argc; ++argv;
-		while ((c = getopt(argc, argv, "m:LFR")) >= 0) {
+		int quiet = 0; /* -q: sizes and a checksum only (for timing the reader) */
+		while ((c = getopt(argc, argv, "m:LFRq")) >= 0) {
 			if (c == 'm') batch = parse_num(optarg);
+			else if (c == 'q') quiet = 1;
 			else if (c == 'L') is_line = 1;
 			else if (c == 'F') no_for = 1;
 			else if (c == 'R') no_rev = 1;
@@ -486,7 +529,12 @@ int main(int argc, char *argv[])
 		while ((b = pipe_next(&P)) != 0) {
 			size_t k;
 			if (b->open_failed) printf("%d\t-1\t!\n", b->file - optind);
-			else {
+			else if (quiet) {
+				uint64_t h = 0, w;
+				for (k = 0; k + 8 <= b->seq.l; k += 8) { memcpy(&w, b->seq.s + k, 8); h = (h << 1 | h >> 63) ^ w; } /* cheap: the reader must stay the bottleneck */
+				for (; k < b->seq.l; ++k) h = (h << 1 | h >> 63) ^ (unsigned char)b->seq.s[k];
+				printf("%d\t%ld\t%ld symbols, checksum %016llx\t%d\n", b->file - optind, (long)b->n_seq, (long)b->seq.l, (unsigned long long)h, b->last_of_file);
+			} else {
 				printf("%d\t%ld\t", b->file - optind, (long)b->n_seq);
 				for (k = 0; k < b->seq.l; ++k) putchar("$ACGTN"[(unsigned char)b->seq.s[k] < 6 ? (unsigned char)b->seq.s[k] : 5]);
 				printf("\t%d\n", b->last_of_file);

@@ -215,6 +215,29 @@ def test_cli_reader_and_batching(oracle, tmp_path):
     assert any(g[0] == 1 and g[1] == -1 for g in got)               # the unopenable file
 
 
+def test_cli_reader_encodes_every_byte_value():
+    """The vectorised encoder of the reader (16 characters at a time, forward and reverse complement) against the table
+    of io.c:12-21 for every byte value, at every alignment of the 16-byte blocks and tails."""
+    rng = np.random.default_rng(5)
+    tab = np.full(256, 5, np.uint8)
+    tab[:5] = np.arange(5)
+    for ch, v in zip(b"ACGT", (1, 2, 3, 4)):
+        tab[ch] = tab[ch + 32] = v
+    ok = np.array([b for b in range(1, 256) if b not in (10, 13)], np.uint8)   # a line holds anything but its terminator (and no NUL: C strings)
+    lines = [ok[rng.integers(0, len(ok), n)] for n in list(range(1, 70)) + [1000, 4097]]
+    lines.append(ok)   # every value once
+    data = b"\n".join(x.tobytes() for x in lines) + b"\n"
+    got = _cli_batches(["-L", "-"], stdin=data)
+    assert len(got) == 1 and got[0][1] == 2 * len(lines)
+    comp = np.array([0, 4, 3, 2, 1, 5], np.uint8)
+    want = []
+    for x in lines:
+        f = tab[x]
+        want.append(np.concatenate([f, [0], comp[f[::-1]], [0]]))
+    want = np.concatenate(want)
+    assert got[0][2] == "".join("$ACGTN"[v] for v in want)
+
+
 def test_cli_reader_against_live_reference_on_odd_input(oracle):
     """Our reader + the oracle's BWT == the reference CLI end to end, on inputs that stress the parser (blank lines,
     IUPAC codes and gaps, spaces, CRLF, no trailing newline, multi-line FASTQ, junk before the first header)."""
