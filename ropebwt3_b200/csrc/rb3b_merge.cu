@@ -1053,7 +1053,7 @@ static int walk_order(int64_t len, const uint8_t *d_bwt, int64_t nt, const int64
 	/* one chase instead of two (k_fine_walk_buf / k_copy_walk) where a chase step is a DRAM access: batches from 2^25 rows on
 	 * ("piece_buf": 0 never, 1 always, -1 by size); single device only (with several, the walks are split by different keys) */
 	const int64_t pbuf = rb3b_get_param("piece_buf", -1);
-	const bool use_buf = !share && n_parts == 1 && (pbuf > 0 || (pbuf < 0 && len >= (32LL << 20)));
+	const bool use_buf = !share && n_parts == 1 && (pbuf > 0 || (pbuf < 0 && len >= (32LL << 20) && sizeof(RowT) == 4)); /* by size: 32-bit rows only (what was measured) */
 	const int cap = F.fshift >= 2 ? (int)(2LL << F.fshift) : 8; /* twice the mean piece length; a multiple of 8 (whole-word stores) */
 	DBuf<RowT> rowbuf, tail_row;
 	DBuf<uint8_t> symbuf;
